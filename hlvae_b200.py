@@ -1,0 +1,12 @@
+"""Import alias: the package directory is named `hl-vae_b200/` (not a Python identifier),
+so this module loads it once under the importable name `hlvae_b200`."""
+import importlib.util
+import os
+import sys
+
+_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "hl-vae_b200")
+_spec = importlib.util.spec_from_file_location(
+    "hlvae_b200", os.path.join(_dir, "__init__.py"), submodule_search_locations=[_dir])
+_mod = importlib.util.module_from_spec(_spec)
+sys.modules["hlvae_b200"] = _mod
+_spec.loader.exec_module(_mod)

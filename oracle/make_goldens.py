@@ -1,0 +1,300 @@
+"""Pin the oracle against the reference itself and freeze golden fixtures.
+
+TEST INFRASTRUCTURE ONLY.  Run in the build container (needs /root/reference):
+
+    python oracle/make_goldens.py            # validate + (re)write tests/golden/*.npz
+
+What it does, per case:
+  1. imports the UNMODIFIED reference modules from /root/reference (kernel_gen, kernel_spec,
+     elbo_functions, HLVAE, HL_VAE.loglik, HL_VAE.read_functions) behind the stand-ins in
+     oracle/standins (gpytorch, matplotlib are not installable here);
+  2. evaluates the reference on seeded synthetic inputs, with autograd gradients;
+  3. evaluates oracle/hlvae_oracle.py on the same inputs and asserts agreement: 1e-6 relative
+     on kld, 2e-6 on grad_m / grad_H and the gradients of mu, log_v, Z, m, H; 1e-4 on the
+     kernel hyper-parameter gradients, whose float64 round-off floor between two
+     mathematically equal evaluation orders is already 1e-5 here because cond(K0zz + eps I)
+     ~ 1e7 when inducing points are sampled from data rows (hard part
+     1; with well-separated inducing points the same checks agree to 1e-11); likelihood
+     terms 1e-11; argmax maps exactly;
+  4. writes inputs + reference outputs to tests/golden/<case>.npz.
+The GPU box has no /root/reference: tests there read only the .npz files.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF = os.environ.get("HLVAE_REFERENCE", "/root/reference")
+sys.path.insert(0, os.path.join(HERE, "standins"))
+sys.path.insert(1, REF)
+sys.path.insert(2, ROOT)
+warnings.filterwarnings("ignore")
+
+import hlvae_b200  # noqa: E402  (only for the synthetic-input generators)
+from hlvae_b200 import synth  # noqa: E402
+from oracle import hlvae_oracle as orc  # noqa: E402
+
+import elbo_functions as ref_elbo  # noqa: E402  (reference)
+import kernel_gen as ref_kernel_gen  # noqa: E402
+import gpytorch  # noqa: E402  (stand-in)
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+DT = torch.float64
+
+
+def rel(a, b):
+    a, b = torch.as_tensor(a, dtype=DT), torch.as_tensor(b, dtype=DT)
+    return float((a - b).abs().max() / (b.abs().max() + 1e-300))
+
+
+def check(name, a, b, tol=1e-6):
+    r = rel(a, b)
+    if os.environ.get("GOLDEN_REPORT_ONLY"):
+        print(f"    {name}: {r:.2e}")
+        return r
+    assert r <= tol, f"{name}: oracle vs reference rel diff {r:.3e} > {tol}"
+    return r
+
+
+# ------------------------------------------------------------------ kernels / KL
+def ref_modules(L, kargs, gen):
+    k0, k1 = ref_kernel_gen.generate_kernel_batched(L, kargs['cat_kernel'], kargs['bin_kernel'], kargs['sqexp_kernel'],
+                                                    kargs['cat_int_kernel'], kargs['bin_int_kernel'],
+                                                    kargs['covariate_missing_val'], kargs['id_covariate'])
+    lik = gpytorch.likelihoods.GaussianLikelihood(batch_shape=torch.Size([L]),
+                                                  noise_constraint=gpytorch.constraints.GreaterThan(1.0e-8))
+    lik.noise = 1                                    # HLVAE_main.py:211
+    lik.raw_noise.requires_grad = False
+    k0.train().double(); k1.train().double(); lik.train().double()   # HLVAE_main.py:235-237
+    # move the hyper-parameters off their symmetric defaults (keeps the float32-initialised base)
+    with torch.no_grad():
+        for k in (k0, k1):
+            for p in k.parameters():
+                p.add_(0.3 * torch.randn(p.shape, generator=gen, dtype=DT))
+    return k0, k1, lik
+
+
+def extract_params(kmod):
+    """raw_outputscale per component and raw_lengthscale per SE factor (depth-first order)."""
+    ros = torch.stack([k.raw_outputscale.detach().clone() for k in kmod.kernels]) if len(kmod.kernels) else torch.zeros(0, 1, dtype=DT)
+    rls = [mod.raw_lengthscale.detach().reshape(-1).clone() for mod in kmod.modules()
+           if isinstance(mod, gpytorch.kernels.RBFKernel)]
+    rls = torch.stack(rls) if rls else torch.zeros(0, ros.shape[1], dtype=DT)
+    return ros, rls
+
+
+def extract_grads(kmod):
+    gos = torch.stack([k.raw_outputscale.grad.clone() for k in kmod.kernels])
+    gls = [mod.raw_lengthscale.grad.reshape(-1).clone() for mod in kmod.modules()
+           if isinstance(mod, gpytorch.kernels.RBFKernel)]
+    gls = torch.stack(gls) if gls else torch.zeros(0, gos.shape[1], dtype=DT)
+    return gos, gls
+
+
+def kl_case(name, kargs, L, M, n_subj, T, ragged, fixed_T_api, seed, trained_like=False, continuous_age=False,
+            natural_gradient=True, shuffle_rows=False):
+    rng = np.random.default_rng(seed)
+    gen = torch.Generator().manual_seed(seed)
+    x, lens = synth.covariates(n_subj, T, rng, ragged=ragged, t_min=3, continuous_age=continuous_age)
+    pool, _ = synth.covariates(40, T, rng, continuous_age=continuous_age)
+    z0 = synth.inducing_points(torch.cat([x, pool]), L, M, rng)
+    N_b = x.shape[0]
+    if shuffle_rows:                                  # _iter groups by id value, not by position
+        x = x[torch.from_numpy(rng.permutation(N_b))]
+    mu0 = torch.randn(N_b, L, generator=gen, dtype=DT)
+    lv0 = -3.0 * torch.rand(N_b, L, generator=gen, dtype=DT)
+    m, H = synth.variational_state(L, M, gen)
+    k0, k1, lik = ref_modules(L, kargs, gen)
+    eps = 1e-6
+    P_tot, N_tot = 200, 200 * T
+    idc = kargs['id_covariate']
+    spec0, spec1 = orc.compile_spec(**kargs)
+    ros0, rls0 = extract_params(k0)
+    ros1, rls1 = extract_params(k1)
+    noise = lik.noise_covar.noise.detach().reshape(-1).clone()
+
+    def ref_call(m_, H_, mu_, lv_, z_):
+        if fixed_T_api:
+            return ref_elbo.minibatch_KLD_upper_bound(k0, k1, lik, L, m_, H_, x, mu_, lv_, z_, P_tot, n_subj, T,
+                                                      natural_gradient, eps)
+        return ref_elbo.minibatch_KLD_upper_bound_iter(k0, k1, lik, L, m_, H_, x, mu_, lv_, z_, P_tot, n_subj, N_tot,
+                                                       natural_gradient, idc, eps)
+
+    if trained_like:      # a few natural-gradient steps from the reference's own update rule
+        for _ in range(8):
+            with torch.no_grad():
+                _, gm, gH = ref_call(m, H, mu0, lv0, z0)
+            m, H = orc.natural_gradient_update(m, H, gm, gH, 0.3)
+
+    mu = mu0.clone().requires_grad_(True)
+    lv = lv0.clone().requires_grad_(True)
+    z = z0.clone().requires_grad_(True)
+    m_r = m.clone().requires_grad_(True)
+    H_r = H.clone().requires_grad_(True)
+    kld, gm, gH = ref_call(m_r, H_r, mu, lv, z)
+    kld = kld.reshape(())
+    kld.backward()
+    g0os, g0ls = extract_grads(k0)
+    g1os, g1ls = extract_grads(k1)
+
+    # ---- oracle on the same inputs
+    prm0 = orc.KernelParams(ros0.clone(), rls0.clone()).requires_grad_()
+    prm1 = orc.KernelParams(ros1.clone(), rls1.clone()).requires_grad_()
+    mu_o = mu0.clone().requires_grad_(True); lv_o = lv0.clone().requires_grad_(True)
+    z_o = z0.clone().requires_grad_(True)
+    m_o = m.clone().requires_grad_(True); H_o = H.clone().requires_grad_(True)
+    if fixed_T_api:
+        okld, ogm, ogH, terms = orc.minibatch_KLD_upper_bound(spec0, prm0, spec1, prm1, noise, m_o, H_o, x, mu_o, lv_o,
+                                                              z_o, P_tot, n_subj, T, natural_gradient, eps, True)
+    else:
+        okld, ogm, ogH, terms = orc.minibatch_KLD_upper_bound_iter(spec0, prm0, spec1, prm1, noise, m_o, H_o, x, mu_o,
+                                                                   lv_o, z_o, P_tot, n_subj, N_tot, natural_gradient,
+                                                                   idc, eps, True)
+    okld.backward()
+    worst = {}
+    worst['kld'] = check(name + ".kld", okld, kld)
+    if natural_gradient:
+        worst['grad_m'] = check(name + ".grad_m", ogm, gm, 2e-6)
+        worst['grad_H'] = check(name + ".grad_H", ogH, gH, 2e-6)
+    worst['d_mu'] = check(name + ".d_mu", mu_o.grad, mu.grad, 2e-6)
+    worst['d_logv'] = check(name + ".d_logv", lv_o.grad, lv.grad, 2e-6)
+    worst['d_z'] = check(name + ".d_z", z_o.grad, z.grad, 2e-6)
+    worst['d_m'] = check(name + ".d_m", m_o.grad, m_r.grad, 2e-6)
+    worst['d_H'] = check(name + ".d_H", H_o.grad, H_r.grad, 2e-6)
+    worst['d_os0'] = check(name + ".d_os0", prm0.raw_outputscale.grad, g0os, 1e-4)
+    if rls0.numel():
+        worst['d_ls0'] = check(name + ".d_ls0", prm0.raw_lengthscale.grad, g0ls, 1e-4)
+    worst['d_os1'] = check(name + ".d_os1", prm1.raw_outputscale.grad, g1os, 1e-4)
+    if rls1.numel():
+        worst['d_ls1'] = check(name + ".d_ls1", prm1.raw_lengthscale.grad, g1ls, 1e-4)
+
+    # reference dense kernel matrices as extra goldens for the kernel-evaluation op
+    with torch.no_grad():
+        K0xz = k0(x, z0).evaluate()
+        K0zz = k0(z0, z0).evaluate()
+        K1xx = k1(x, x).evaluate()
+        check(name + ".K0xz", orc.eval_additive(spec0, prm0, x, z0), K0xz, 1e-11)
+        check(name + ".K1xx", orc.eval_additive(spec1, prm1, x, x), K1xx, 1e-11)
+
+    npz = dict(
+        kargs=repr(kargs), L=L, M=M, T=T, fixed_T_api=int(fixed_T_api), n_subj=n_subj, P_tot=P_tot, N_tot=N_tot,
+        eps=eps, natural_gradient=int(natural_gradient),
+        x=x.numpy(), lens=np.array(lens), z=z0.numpy(), mu=mu0.numpy(), log_v=lv0.numpy(), m=m.numpy(), H=H.numpy(),
+        noise=noise.numpy(), ros0=ros0.numpy(), rls0=rls0.numpy(), ros1=ros1.numpy(), rls1=rls1.numpy(),
+        kld=kld.detach().numpy(),
+        grad_m=(gm.detach().numpy() if natural_gradient else np.zeros(0)),
+        grad_H=(gH.detach().numpy() if natural_gradient else np.zeros(0)),
+        d_mu=mu.grad.numpy(), d_logv=lv.grad.numpy(), d_z=z.grad.numpy(), d_m=m_r.grad.numpy(), d_H=H_r.grad.numpy(),
+        d_os0=g0os.numpy(), d_ls0=g0ls.numpy(), d_os1=g1os.numpy(), d_ls1=g1ls.numpy(),
+        K0xz=K0xz.numpy(), K0zz=K0zz.numpy(), K1xx=K1xx.numpy(),
+        # individual terms are not returned by the reference; these come from the (just validated) oracle
+        **{"term_" + k: terms[k].detach().numpy() for k in ('A', 'B', 'C', 'D', 'E', 'F', 'kld_qu_pu', 'S', 'p')},
+    )
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **npz)
+    print(f"  {name}: N_b={N_b} kld={float(kld):.6e} worst rel diff {max(worst.values()):.2e}")
+
+
+# ------------------------------------------------------------------ likelihoods
+def loglik_case(name, types, N, seed, conv=False, observed=0.7):
+    import HLVAE as ref_hlvae                               # reference
+    from HL_VAE import read_functions as ref_rf             # reference
+    from HL_VAE.utils import batch_normalization as ref_bn  # reference
+    rng = np.random.default_rng(seed)
+    gen = torch.Generator().manual_seed(seed)
+    torch.manual_seed(seed)
+    data, mask = synth.likelihood_batch(types, N, rng, observed=observed, pixel_like=conv)
+    tinfo = orc.types_info_from_layout(types, conv=conv)
+    descs, E_x, P_th = orc.build_layout(types)
+    D = len(types)
+    if conv:
+        assert D == 1296
+        dims = [D, [16], 4, [16], 5]
+    else:
+        dims = [E_x, [16], 4, [16], 3]
+    model = ref_hlvae.HLVAE(dims, tinfo, D, vy_init=[1., .5], vy_fixed=False, logvar_network=False, conv=conv).double()
+    with torch.no_grad():
+        model._log_vy_real.add_(0.5 * torch.randn(model._log_vy_real.shape, generator=gen, dtype=DT))
+        model._log_vy_pos.add_(0.5 * torch.randn(model._log_vy_pos.shape, generator=gen, dtype=DT))
+    theta0 = torch.randn(N, P_th, generator=gen, dtype=DT) * 1.5
+    if N >= 4 and any(k == 'cat' for k, _ in types):        # exact ties -> first index must win
+        j = next(i for i, v in enumerate(descs) if v.kind == 'cat')
+        theta0[0, descs[j].theta_col:descs[j].theta_col + descs[j].nclass] = 0.25
+        theta0[1, descs[j].theta_col:descs[j].theta_col + descs[j].nclass] = 0.0
+    param_mask = torch.ones(N, P_th, dtype=DT)
+    _, norm = ref_bn(data, mask, param_mask, tinfo)
+    theta = theta0.clone().requires_grad_(True)
+    lpx, lpm, samples, params = model.loglik_and_reconstruction(theta, data, mask, param_mask, norm)
+    g_up = torch.randn(N, D, generator=gen, dtype=DT)       # arbitrary upstream gradient
+    (lpx * g_up).sum().backward()
+    pcat = ref_rf.p_params_concatenation_by_key([{'x': params}], tinfo, N, data.device, 'x').detach()
+    dtr = ref_rf.discrete_variables_transformation(data, tinfo)
+    rmean, rmode = ref_rf.statistics(pcat, tinfo, data.device, conv, [model._log_vy_real, model._log_vy_pos])
+    rmean, rmode = rmean.detach(), rmode.detach()
+
+    # ---- oracle
+    lvr = model._log_vy_real.detach().clone().requires_grad_(True)
+    lvp = model._log_vy_pos.detach().clone().requires_grad_(True)
+    nr = None if (conv or norm[0] == []) else (norm[0][0], norm[0][1])
+    npos = None if norm[1] == [] else (norm[1][0], norm[1][1])
+    th_o = theta0.clone().requires_grad_(True)
+    olpx, olpm, oparams = orc.loglik_and_reconstruction(descs, data, mask, th_o, lvr, lvp, nr, npos, conv)
+    (olpx * g_up).sum().backward()
+    omean, omode = orc.statistics(descs, oparams.detach(), lvp.detach())
+    odtr = orc.discrete_variables_transformation(descs, data)
+    w = [check(name + ".log_p_x", olpx, lpx, 1e-11), check(name + ".log_p_x_missing", olpm, lpm, 1e-11),
+         check(name + ".params", oparams, pcat, 1e-11), check(name + ".d_theta", th_o.grad, theta.grad, 1e-10)]
+    disc = torch.tensor([v.kind in ('cat', 'ordinal') for v in descs])
+    assert torch.equal(omean[:, disc], rmean[:, disc]), name + ": argmax imputation differs"
+    assert torch.equal(odtr, dtr), name + ": discrete transform differs"
+    w.append(check(name + ".mean", omean, rmean, 1e-11))
+    w.append(check(name + ".mode", omode, rmode, 1e-11))
+    if model._log_vy_real.grad is not None and lvr.grad is not None:
+        w.append(check(name + ".d_log_vy_real", lvr.grad, model._log_vy_real.grad, 1e-10))
+    if model._log_vy_pos.grad is not None and lvp.grad is not None:
+        w.append(check(name + ".d_log_vy_pos", lvp.grad, model._log_vy_pos.grad, 1e-10))
+    z = lambda t: np.zeros(0) if t is None else t.detach().numpy()
+    np.savez_compressed(
+        os.path.join(GOLD, name + ".npz"),
+        types=np.array([f"{k}:{c}" for k, c in types]), conv=int(conv),
+        data=data.numpy(), mask=mask.numpy(), theta=theta0.numpy(), g_up=g_up.numpy(),
+        log_vy_real=z(model._log_vy_real), log_vy_pos=z(model._log_vy_pos),
+        norm_real_mean=z(nr[0] if nr else None), norm_real_var=z(nr[1] if nr else None),
+        norm_pos_mean=z(npos[0] if npos else None), norm_pos_var=z(npos[1] if npos else None),
+        log_p_x=lpx.detach().numpy(), log_p_x_missing=lpm.detach().numpy(), params=pcat.numpy(),
+        d_theta=theta.grad.numpy(), d_log_vy_real=z(model._log_vy_real.grad), d_log_vy_pos=z(model._log_vy_pos.grad),
+        recon_mean=rmean.numpy(), recon_mode=rmode.numpy(), data_transformed=dtr.numpy())
+    print(f"  {name}: N={N} D={D} E_x={E_x} worst rel diff {max(w):.2e}")
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    print("KL upper bound: oracle vs unmodified reference (gpytorch stand-in)")
+    kl_case("kl_default_ragged", synth.DEFAULT_KERNEL_ARGS, L=4, M=12, n_subj=6, T=8, ragged=True, fixed_T_api=False, seed=1)
+    kl_case("kl_default_fixedT", synth.DEFAULT_KERNEL_ARGS, L=3, M=10, n_subj=5, T=6, ragged=False, fixed_T_api=True, seed=2)
+    kl_case("kl_sweep_ragged", synth.SWEEP_KERNEL_ARGS, L=4, M=16, n_subj=7, T=10, ragged=True, fixed_T_api=False, seed=3,
+            continuous_age=True)
+    kl_case("kl_masked_bin", synth.MASKED_KERNEL_ARGS, L=2, M=9, n_subj=5, T=7, ragged=True, fixed_T_api=False, seed=4)
+    kl_case("kl_trained_like", synth.DEFAULT_KERNEL_ARGS, L=4, M=12, n_subj=8, T=8, ragged=False, fixed_T_api=False, seed=5,
+            trained_like=True)
+    kl_case("kl_not_natgrad", synth.DEFAULT_KERNEL_ARGS, L=2, M=8, n_subj=4, T=5, ragged=True, fixed_T_api=False, seed=6,
+            natural_gradient=False)
+    kl_case("kl_shuffled_rows", synth.DEFAULT_KERNEL_ARGS, L=2, M=8, n_subj=5, T=6, ragged=True, fixed_T_api=False, seed=7,
+            shuffle_rows=True)
+    kl_case("kl_T32_M40", synth.DEFAULT_KERNEL_ARGS, L=2, M=40, n_subj=3, T=32, ragged=False, fixed_T_api=True, seed=8)
+    print("likelihoods: oracle vs unmodified reference")
+    rng = np.random.default_rng(11)
+    loglik_case("loglik_mixed", synth.mixed_types(rng, 24), N=24, seed=11)
+    loglik_case("loglik_tabular_small", [('count', 1)] * 3 + [('ordinal', 5)] * 3 + [('cat', 5)] * 3 + [('real', 1)] * 2 + [('pos', 1)] * 2,
+                N=16, seed=12)
+    loglik_case("loglik_conv_d4", synth.HEALTHMNIST_D4_TYPES, N=3, seed=13, conv=True, observed=0.75)
+    print("all oracle-vs-reference checks passed; goldens written to", GOLD)
+
+
+if __name__ == "__main__":
+    main()
