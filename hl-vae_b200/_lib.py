@@ -1,0 +1,105 @@
+"""ctypes binding of the C ABI declared in include/hlvae_b200.h.
+
+The shared library is built in-tree by `__graft_entry__.build()` (nvcc, sm_100a) into
+`hl-vae_b200/lib/libhlvae_b200.so`.  There is no fallback: if the library is missing, or a
+tensor is not on a CUDA device, the call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libhlvae_b200.so")
+
+MAX_COMPS, MAX_DISC, MAX_Q, TMAX, MAX_CLASS = 8, 3, 8, 32, 16
+F32, F64 = 0, 1
+KIND_CAT, KIND_BIN = 1, 2
+VAR_KINDS = {"real": 0, "pos": 1, "count": 2, "cat": 3, "ordinal": 4}
+ACC_NAMES = ("S", "p", "gw", "scal", "gZ", "gos0", "gls0", "gos1", "gls1", "total")
+NSCAL = 4
+STATUS_NOT_PD, STATUS_T_TOO_LARGE = 1, 2
+
+
+class Comp(C.Structure):
+    _fields_ = [("se_col", C.c_int32), ("ndisc", C.c_int32),
+                ("disc_kind", C.c_int32 * MAX_DISC), ("disc_col", C.c_int32 * MAX_DISC)]
+
+
+class KSpec(C.Structure):
+    _fields_ = [("ncomp", C.c_int32), ("reserved", C.c_int32), ("comp", Comp * MAX_COMPS)]
+
+
+_lib = None
+
+_P, _I, _L, _D = C.c_void_p, C.c_int, C.c_int64, C.c_double
+_SIGS = {
+    "hlvae_version": ([], _I),
+    "hlvae_sizeof_kspec": ([], _I),
+    "hlvae_kernel_eval_fwd": ([C.POINTER(KSpec), _P, _P, _I, _I, _P, _I, _L, _L, _P, _I, _L, _L, _P, _P], _I),
+    "hlvae_kernel_eval_bwd": ([C.POINTER(KSpec), _P, _P, _I, _I, _P, _I, _L, _L, _P, _I, _L, _L, _P, _P, _P, _P, _P, _P], _I),
+    "hlvae_kl_acc_layout": ([_I, _I, _I, C.POINTER(_L)], _I),
+    "hlvae_kl_subject": ([C.POINTER(KSpec), _P, _P, C.POINTER(KSpec), _P, _P, _P, _I, _I, _P, _L, _P, _P, _P, _I, _I,
+                          _P, _L, _I, _P, _L, _P, _I, _P, _P, _P], _I),
+    "hlvae_kl_panel": ([C.POINTER(KSpec), _P, _P, C.POINTER(KSpec), _P, _P, _I, _I, _I, _P, _L, _P, _P, _P, _P, _I, _I,
+                        _P, _L, _I, _P, _P, _P, _L, _P, _P, _P, _P], _I),
+    "hlvae_loglik_fwd": ([_L, _I, _L, _L, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P], _I),
+    "hlvae_loglik_bwd": ([_L, _I, _L, _L, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _D, _P, _P, _P], _I),
+    "hlvae_statistics": ([_L, _I, _L, _P, _P, _P, _P, _P, _I, _P, _P, _P], _I),
+    "hlvae_discrete_transform": ([_L, _I, _L, _P, _P, _P, _P, _I, _P, _P], _I),
+}
+EXPORTED = tuple(_SIGS)
+
+
+def lib():
+    """The loaded library (loads on first use; raises if it has not been built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"hlvae_b200: CUDA library not built ({LIB_PATH} missing). Run "
+                "`python -c 'import __graft_entry__ as g; g.build()'` at the repo root. There is no CPU fallback.")
+        h = C.CDLL(LIB_PATH)
+        for name, (args, res) in _SIGS.items():
+            fn = getattr(h, name)
+            fn.argtypes = args
+            fn.restype = res
+        if h.hlvae_sizeof_kspec() != C.sizeof(KSpec):
+            raise RuntimeError("hlvae_b200: hlvae_kspec_t layout mismatch between binding and library")
+        _lib = h
+    return _lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        raise RuntimeError(f"hlvae_b200: {what} failed with code {rc}" +
+                           (" (argument error)" if rc == -1 else " (unsupported size)" if rc == -2 else " (CUDA error)"))
+
+
+def ptr(t):
+    """Device pointer of a CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("hlvae_b200: tensors must live on a CUDA device (no CPU fallback)")
+    return C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def dtype_code(t):
+    if t.dtype == torch.float64:
+        return F64
+    if t.dtype == torch.float32:
+        return F32
+    raise TypeError(f"hlvae_b200: unsupported storage dtype {t.dtype}")
+
+
+def acc_layout(L, M, Q):
+    off = (_L * 10)()
+    check(lib().hlvae_kl_acc_layout(L, M, Q, off), "hlvae_kl_acc_layout")
+    return {n: int(off[i]) for i, n in enumerate(ACC_NAMES)}

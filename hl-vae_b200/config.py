@@ -1,0 +1,10 @@
+"""Run-time switches of the host layer."""
+
+# Read the device status words (one small device->host copy) after the KL kernels and raise
+# RuntimeError on a non positive-definite block, like torch.linalg.cholesky does in the reference
+# path (elbo_functions.py:154-157).  The benchmark turns this off to keep the step sync-free.
+check_errors = True
+
+# torch.distributed process group over which the per-latent accumulators are all-reduced
+# (None: single process).  Set by hlvae_b200.parallel.enable().
+process_group = None

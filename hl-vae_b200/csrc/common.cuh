@@ -1,0 +1,136 @@
+// Shared device helpers for the hlvae_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "hlvae_b200.h"
+
+#define HLVAE_WARP 32
+
+namespace hlvae {
+
+// Per-latent-dimension constrained hyper-parameters of one additive kernel, expanded into
+// the forms the inner loops need.
+struct KParams {
+    double os[HLVAE_MAX_COMPS];     // outputscale
+    double hil2[HLVAE_MAX_COMPS];   // 0.5 / lengthscale^2
+    double il2[HLVAE_MAX_COMPS];    // 1 / lengthscale^2
+    double il3[HLVAE_MAX_COMPS];    // 1 / lengthscale^3
+};
+
+__device__ __forceinline__ void load_kparams(KParams& kp, const hlvae_kspec_t& sp, const double* __restrict__ os,
+                                             const double* __restrict__ ls, int L, int l) {
+#pragma unroll
+    for (int r = 0; r < HLVAE_MAX_COMPS; r++) {
+        if (r < sp.ncomp) {
+            double s = os[(int64_t)r * L + l];
+            double e = ls[(int64_t)r * L + l];
+            kp.os[r] = s;
+            double i2 = 1.0 / (e * e);
+            kp.hil2[r] = 0.5 * i2;
+            kp.il2[r] = i2;
+            kp.il3[r] = i2 / e;
+        } else {
+            kp.os[r] = 0.0; kp.hil2[r] = 0.0; kp.il2[r] = 0.0; kp.il3[r] = 0.0;
+        }
+    }
+}
+
+// Discrete factors of one component: CatKernel (kernel_spec.py:26-32) and BinKernel
+// (kernel_spec.py:9-23); true when every factor equals 1.
+__device__ __forceinline__ bool disc_match(const hlvae_comp_t& c, const double* __restrict__ xa,
+                                           const double* __restrict__ xb, int sa, int sb) {
+    bool ok = true;
+#pragma unroll
+    for (int f = 0; f < HLVAE_MAX_DISC; f++) {
+        if (f < c.ndisc) {
+            double a = xa[c.disc_col[f] * sa], b = xb[c.disc_col[f] * sb];
+            ok = ok && ((c.disc_kind[f] == HLVAE_KIND_CAT) ? (a - b == 0.0) : (a + b == 2.0));
+        }
+    }
+    return ok;
+}
+
+// Unscaled value of component r at (xa, xb): prod(disc) * exp(-(xa-xb)^2 / (2 l^2))
+// (GP_model.py:43-69 form of the gpytorch RBFKernel the reference builds at kernel_spec.py:58-69).
+__device__ __forceinline__ double comp_value(const hlvae_comp_t& c, double hil2, const double* __restrict__ xa,
+                                             const double* __restrict__ xb, int sa, int sb, double& d_out) {
+    d_out = 0.0;
+    if (!disc_match(c, xa, xb, sa, sb)) return 0.0;
+    if (c.se_col < 0) return 1.0;
+    double d = xa[c.se_col * sa] - xb[c.se_col * sb];
+    d_out = d;
+    return exp(-(d * d) * hil2);
+}
+
+// K(xa, xb) = sum_r os_r * comp_r   (AdditiveKernel of ScaleKernels, kernel_gen.py:219-310)
+// xa[c * sa], xb[c * sb] address covariate column c (sa = sb = 1 for row-major rows).
+__device__ __forceinline__ double eval_additive(const hlvae_kspec_t& sp, const KParams& kp,
+                                                const double* __restrict__ xa, const double* __restrict__ xb,
+                                                int sa = 1, int sb = 1) {
+    double acc = 0.0;
+#pragma unroll
+    for (int r = 0; r < HLVAE_MAX_COMPS; r++) {
+        if (r < sp.ncomp) {
+            double d;
+            double k = comp_value(sp.comp[r], kp.hil2[r], xa, xb, sa, sb, d);
+            acc = fma(kp.os[r], k, acc);
+        }
+    }
+    return acc;
+}
+
+// Accumulate g * dK/d{os_r, ls_r} and (optionally) g * dK/dxb[se_col_r] into per-component
+// register accumulators.  dK/dls_r = os_r k_r d^2 / l^3 ; dK/dxb = os_r k_r d / l^2 (d = xa - xb).
+template <bool WITH_GX>
+__device__ __forceinline__ void accum_grads(const hlvae_kspec_t& sp, const KParams& kp,
+                                            const double* __restrict__ xa, const double* __restrict__ xb, double g,
+                                            double (&gos)[HLVAE_MAX_COMPS], double (&gls)[HLVAE_MAX_COMPS],
+                                            double (&gxb)[HLVAE_MAX_COMPS], int sa = 1, int sb = 1) {
+#pragma unroll
+    for (int r = 0; r < HLVAE_MAX_COMPS; r++) {
+        if (r < sp.ncomp) {
+            double d;
+            double k = comp_value(sp.comp[r], kp.hil2[r], xa, xb, sa, sb, d);
+            double gk = g * k;
+            gos[r] += gk;
+            double t = gk * kp.os[r] * d;
+            gls[r] = fma(t * d, kp.il3[r], gls[r]);
+            if (WITH_GX) gxb[r] = fma(t, kp.il2[r], gxb[r]);
+        }
+    }
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// D(8x8) += A(8x4) * B(4x8) on the FP64 tensor pipe.
+// A: lane holds a[row = lane/4][col = lane%4]; B: b[row = lane%4][col = lane/4];
+// C: c[row = lane/4][col = 2*(lane%4) + {0,1}].
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+template <typename T>
+__device__ __forceinline__ double ld_as_double(const void* p, int64_t i) {
+    return (double)reinterpret_cast<const T*>(p)[i];
+}
+
+__device__ __forceinline__ void report_status(int32_t* status, int code, int l, int s) {
+    if (status && atomicCAS(status, 0, code) == 0) {
+        status[1] = l;
+        status[2] = s;
+    }
+}
+
+}  // namespace hlvae
+
+#define HLVAE_CHECK_LAUNCH()                              \
+    do {                                                  \
+        cudaError_t e__ = cudaGetLastError();             \
+        if (e__ != cudaSuccess) return (int)e__;          \
+    } while (0)

@@ -1,0 +1,131 @@
+// Dense additive-kernel evaluation K[l, i, j] and its backward.
+// Stands behind `covar_module(x1, x2).evaluate()` (elbo_functions.py:147-148, 222-223).
+#include "common.cuh"
+
+using namespace hlvae;
+
+namespace {
+
+constexpr int EV_THREADS = 256;
+
+// grid: (ceil(n1*n2 / EV_THREADS), L)
+__global__ void __launch_bounds__(EV_THREADS)
+kernel_eval_fwd_k(const __grid_constant__ hlvae_kspec_t sp, const double* __restrict__ os,
+                  const double* __restrict__ ls, int L, int Q, const double* __restrict__ x1, int n1, int64_t ld1,
+                  int64_t bs1, const double* __restrict__ x2, int n2, int64_t ld2, int64_t bs2,
+                  double* __restrict__ out) {
+    const int l = blockIdx.y;
+    KParams kp;
+    load_kparams(kp, sp, os, ls, L, l);
+    int64_t e = (int64_t)blockIdx.x * EV_THREADS + threadIdx.x;
+    if (e >= (int64_t)n1 * n2) return;
+    int i = (int)(e / n2), j = (int)(e % n2);
+    const double* xa = x1 + l * bs1 + (int64_t)i * ld1;
+    const double* xb = x2 + l * bs2 + (int64_t)j * ld2;
+    out[((int64_t)l * n1 + i) * n2 + j] = eval_additive(sp, kp, xa, xb);
+}
+
+// grid: (ceil(n1*n2 / EV_THREADS), L).  Hyper-parameter gradients: block reduce + one atomic
+// per block; covariate gradients: one atomic per (element, SE component) - this op serves the
+// small M x M matrix K0zz and API-compatibility calls, not the streaming path.
+__global__ void __launch_bounds__(EV_THREADS)
+kernel_eval_bwd_k(const __grid_constant__ hlvae_kspec_t sp, const double* __restrict__ os,
+                  const double* __restrict__ ls, int L, int Q, const double* __restrict__ x1, int n1, int64_t ld1,
+                  int64_t bs1, const double* __restrict__ x2, int n2, int64_t ld2, int64_t bs2,
+                  const double* __restrict__ g_out, double* __restrict__ g_os, double* __restrict__ g_ls,
+                  double* __restrict__ g_x1, double* __restrict__ g_x2) {
+    __shared__ double red[2 * HLVAE_MAX_COMPS][EV_THREADS / 32];
+    const int l = blockIdx.y;
+    KParams kp;
+    load_kparams(kp, sp, os, ls, L, l);
+    double gos[HLVAE_MAX_COMPS], gls[HLVAE_MAX_COMPS], gxb[HLVAE_MAX_COMPS];
+#pragma unroll
+    for (int r = 0; r < HLVAE_MAX_COMPS; r++) { gos[r] = 0; gls[r] = 0; gxb[r] = 0; }
+    int64_t e = (int64_t)blockIdx.x * EV_THREADS + threadIdx.x;
+    if (e < (int64_t)n1 * n2) {
+        int i = (int)(e / n2), j = (int)(e % n2);
+        const double* xa = x1 + l * bs1 + (int64_t)i * ld1;
+        const double* xb = x2 + l * bs2 + (int64_t)j * ld2;
+        double g = g_out[((int64_t)l * n1 + i) * n2 + j];
+        accum_grads<true>(sp, kp, xa, xb, g, gos, gls, gxb);
+#pragma unroll
+        for (int r = 0; r < HLVAE_MAX_COMPS; r++) {
+            if (r < sp.ncomp && sp.comp[r].se_col >= 0 && gxb[r] != 0.0) {
+                int c = sp.comp[r].se_col;
+                if (g_x2) atomicAdd(g_x2 + ((int64_t)l * n2 + j) * Q + c, gxb[r]);
+                if (g_x1) atomicAdd(g_x1 + ((int64_t)l * n1 + i) * Q + c, -gxb[r]);
+            }
+        }
+    }
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+#pragma unroll
+    for (int r = 0; r < HLVAE_MAX_COMPS; r++) {
+        if (r < sp.ncomp) {
+            double a = warp_sum(gos[r]), b = warp_sum(gls[r]);
+            if (lane == 0) { red[r][warp] = a; red[HLVAE_MAX_COMPS + r][warp] = b; }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * HLVAE_MAX_COMPS) {
+        int r = threadIdx.x % HLVAE_MAX_COMPS;
+        if (r < sp.ncomp) {
+            double s = 0;
+            for (int w = 0; w < EV_THREADS / 32; w++) s += red[threadIdx.x][w];
+            double* dst = (threadIdx.x < HLVAE_MAX_COMPS) ? g_os : g_ls;
+            if (s != 0.0) atomicAdd(dst + (int64_t)r * L + l, s);
+        }
+    }
+}
+
+bool spec_ok(const hlvae_kspec_t* sp, int Q) {
+    if (!sp || sp->ncomp < 0 || sp->ncomp > HLVAE_MAX_COMPS) return false;
+    for (int r = 0; r < sp->ncomp; r++) {
+        const hlvae_comp_t& c = sp->comp[r];
+        if (c.se_col >= Q || c.ndisc < 0 || c.ndisc > HLVAE_MAX_DISC) return false;
+        for (int f = 0; f < c.ndisc; f++)
+            if (c.disc_col[f] < 0 || c.disc_col[f] >= Q ||
+                (c.disc_kind[f] != HLVAE_KIND_CAT && c.disc_kind[f] != HLVAE_KIND_BIN))
+                return false;
+    }
+    return true;
+}
+
+}  // namespace
+
+namespace hlvae {
+bool spec_valid(const hlvae_kspec_t* sp, int Q) { return spec_ok(sp, Q); }
+}
+
+extern "C" int hlvae_version(void) { return HLVAE_ABI_VERSION; }
+extern "C" int hlvae_sizeof_kspec(void) { return (int)sizeof(hlvae_kspec_t); }
+
+extern "C" int hlvae_kernel_eval_fwd(const hlvae_kspec_t* spec, const double* outputscale, const double* lengthscale,
+                                     int L, int Q, const double* x1, int n1, int64_t ld1, int64_t bs1,
+                                     const double* x2, int n2, int64_t ld2, int64_t bs2, double* out, void* stream) {
+    if (!spec_ok(spec, Q) || L <= 0 || Q <= 0 || Q > HLVAE_MAX_Q || !x1 || !x2 || !out || n1 < 0 || n2 < 0)
+        return HLVAE_E_ARG;
+    if (n1 == 0 || n2 == 0) return 0;
+    int64_t ne = (int64_t)n1 * n2;
+    dim3 grid((unsigned)((ne + EV_THREADS - 1) / EV_THREADS), L);
+    kernel_eval_fwd_k<<<grid, EV_THREADS, 0, (cudaStream_t)stream>>>(*spec, outputscale, lengthscale, L, Q, x1, n1,
+                                                                     ld1, bs1, x2, n2, ld2, bs2, out);
+    HLVAE_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int hlvae_kernel_eval_bwd(const hlvae_kspec_t* spec, const double* outputscale, const double* lengthscale,
+                                     int L, int Q, const double* x1, int n1, int64_t ld1, int64_t bs1,
+                                     const double* x2, int n2, int64_t ld2, int64_t bs2, const double* g_out,
+                                     double* g_os, double* g_ls, double* g_x1, double* g_x2, void* stream) {
+    if (!spec_ok(spec, Q) || L <= 0 || Q <= 0 || Q > HLVAE_MAX_Q || !x1 || !x2 || !g_out || !g_os || !g_ls ||
+        n1 < 0 || n2 < 0)
+        return HLVAE_E_ARG;
+    if (n1 == 0 || n2 == 0) return 0;
+    int64_t ne = (int64_t)n1 * n2;
+    dim3 grid((unsigned)((ne + EV_THREADS - 1) / EV_THREADS), L);
+    kernel_eval_bwd_k<<<grid, EV_THREADS, 0, (cudaStream_t)stream>>>(*spec, outputscale, lengthscale, L, Q, x1, n1,
+                                                                     ld1, bs1, x2, n2, ld2, bs2, g_out, g_os, g_ls,
+                                                                     g_x1, g_x2);
+    HLVAE_CHECK_LAUNCH();
+    return 0;
+}

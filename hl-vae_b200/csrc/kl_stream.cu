@@ -1,0 +1,657 @@
+// Streaming part of the KL upper bound (elbo_functions.py:118-285): everything that scales
+// with the minibatch.  Two kernels:
+//   kl_subject_k : one warp per (subject, latent dim)  - T x T work (B_s, Cholesky, inverse)
+//   kl_panel_k   : one CTA per (latent dim, subject chunk) - K0xz rows on the fly,
+//                  B^-1 K0xz, sufficient statistics on the FP64 tensor pipe, gradients.
+// Forward and backward are produced in one pass: with w = iK m and G = iK H iK - iK held
+// fixed, J = 1/2 (A + B + C + D + E - F) is linear in S, so dJ/d(inputs) needs nothing
+// from a later stage ("single-pass gradient").
+#include "common.cuh"
+
+using namespace hlvae;
+
+namespace hlvae {
+bool spec_valid(const hlvae_kspec_t* sp, int Q);
+}
+
+namespace {
+
+struct AccOff {
+    int64_t o[10];
+};
+
+// =====================================================================================
+// kl_subject_k
+// =====================================================================================
+constexpr int SJ_WARPS = 4;
+
+template <typename TS>
+__global__ void __launch_bounds__(SJ_WARPS * 32)
+kl_subject_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__ os0, const double* __restrict__ ls0,
+             const __grid_constant__ hlvae_kspec_t sp1, const double* __restrict__ os1, const double* __restrict__ ls1,
+             const double* __restrict__ noise, int L, int Q, const double* __restrict__ x, int64_t ldx,
+             const int32_t* __restrict__ row_idx, const int32_t* __restrict__ subj_ptr,
+             const int32_t* __restrict__ tt_ptr, int n_subj, int tcap, const TS* __restrict__ log_v, int64_t ld_lv,
+             double* __restrict__ binv, int64_t tt_total, double* __restrict__ acc, const AccOff off,
+             double* __restrict__ g_logv, int32_t* __restrict__ status) {
+    extern __shared__ double smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ldt = tcap | 1;
+    const int per_warp = tcap * Q + 3 * tcap * ldt;
+    double* xs = smem + (size_t)warp * per_warp;
+    double* Bw = xs + tcap * Q;
+    double* Bi = Bw + tcap * ldt;
+    double* Ks = Bi + tcap * ldt;
+
+    const int64_t pair = (int64_t)blockIdx.x * SJ_WARPS + warp;
+    if (pair >= (int64_t)n_subj * L) return;
+    const int s = (int)(pair / L), l = (int)(pair % L);
+    const int r0 = subj_ptr[s];
+    const int T = subj_ptr[s + 1] - r0;
+    if (T <= 0) return;
+    if (T > tcap || T > HLVAE_TMAX) {
+        if (lane == 0) report_status(status, HLVAE_STATUS_T_TOO_LARGE, l, s);
+        return;
+    }
+    KParams kp0, kp1;
+    load_kparams(kp0, sp0, os0, ls0, L, l);
+    load_kparams(kp1, sp1, os1, ls1, L, l);
+
+    int g = -1;
+    double ev = 0.0, lv = 0.0;
+    if (lane < T) {
+        g = row_idx[r0 + lane];
+        for (int q = 0; q < Q; q++) xs[lane * Q + q] = x[(int64_t)g * ldx + q];
+        lv = (double)log_v[(int64_t)g * ld_lv + l];
+        ev = exp(lv);
+    }
+    __syncwarp();
+    const double nz = noise[l];
+    // B_s = K1(x_s, x_s) + noise I (elbo_functions.py:249-250); Ks = K0(x_s, x_s) (:248) + diag(exp(log_v))
+    for (int e = lane; e < T * T; e += 32) {
+        int i = e / T, j = e % T;
+        double k1 = eval_additive(sp1, kp1, xs + i * Q, xs + j * Q);
+        double k0 = eval_additive(sp0, kp0, xs + i * Q, xs + j * Q);
+        Bw[i * ldt + j] = k1 + (i == j ? nz : 0.0);
+        Ks[i * ldt + j] = k0;
+    }
+    __syncwarp();
+    if (lane < T) Ks[lane * ldt + lane] += ev;
+
+    // Cholesky, lower, left-looking; lane i owns row i.  (:251)
+    double logdet = 0.0;
+    bool bad = false;
+    for (int j = 0; j < T; j++) {
+        double sum = 0.0;
+        if (lane >= j && lane < T) {
+            sum = Bw[lane * ldt + j];
+            for (int k = 0; k < j; k++) sum = fma(-Bw[lane * ldt + k], Bw[j * ldt + k], sum);
+        }
+        double djj = __shfl_sync(0xffffffffu, sum, j);
+        if (!(djj > 0.0)) { bad = true; break; }
+        double d = sqrt(djj);
+        if (lane >= j && lane < T) Bw[lane * ldt + j] = (lane == j) ? d : sum / d;
+        logdet += 2.0 * log(d);                                  // C term (:258)
+        __syncwarp();
+    }
+    if (bad) {
+        if (lane == 0) report_status(status, HLVAE_STATUS_NOT_PD, l, s);
+        return;
+    }
+    // L^-1 column by column: lane c solves L y = e_c, stored in Bi[:, c].
+    if (lane < T) {
+        const int c = lane;
+        for (int i = 0; i < c; i++) Bi[i * ldt + c] = 0.0;
+        Bi[c * ldt + c] = 1.0 / Bw[c * ldt + c];
+        for (int i = c + 1; i < T; i++) {
+            double a = 0.0;
+            for (int k = c; k < i; k++) a = fma(Bw[i * ldt + k], Bi[k * ldt + c], a);
+            Bi[i * ldt + c] = -a / Bw[i * ldt + i];
+        }
+    }
+    __syncwarp();
+    // B^-1 = L^-T L^-1 into Bw (explicit inverse, as :252)
+    for (int e = lane; e < T * T; e += 32) {
+        int i = e / T, j = e % T;
+        double a = 0.0;
+        for (int k = max(i, j); k < T; k++) a = fma(Bi[k * ldt + i], Bi[k * ldt + j], a);
+        Bw[i * ldt + j] = a;
+    }
+    __syncwarp();
+
+    double gos0[HLVAE_MAX_COMPS], gls0[HLVAE_MAX_COMPS], gos1[HLVAE_MAX_COMPS], gls1[HLVAE_MAX_COMPS],
+        dummy[HLVAE_MAX_COMPS];
+#pragma unroll
+    for (int r = 0; r < HLVAE_MAX_COMPS; r++) { gos0[r] = gls0[r] = gos1[r] = gls1[r] = dummy[r] = 0.0; }
+
+    // B + D1 terms: sum(B^-1 * (K0ss + diag e^logv)) (:257,259); dJ/dK0ss = 1/2 B^-1; write B^-1.
+    double bd = 0.0;
+    double* bout = binv + (int64_t)l * tt_total + tt_ptr[s];
+    for (int e = lane; e < T * T; e += 32) {
+        int i = e / T, j = e % T;
+        double bij = Bw[i * ldt + j];
+        bd = fma(bij, Ks[i * ldt + j], bd);
+        bout[e] = bij;
+        accum_grads<false>(sp0, kp0, xs + i * Q, xs + j * Q, 0.5 * bij, gos0, gls0, dummy);
+    }
+    if (lane < T) g_logv[(int64_t)g * L + l] = 0.5 * (Bw[lane * ldt + lane] * ev - 1.0);
+    // X = Ktil B^-1 -> Bi
+    for (int e = lane; e < T * T; e += 32) {
+        int i = e / T, j = e % T;
+        double a = 0.0;
+        for (int k = 0; k < T; k++) a = fma(Ks[i * ldt + k], Bw[k * ldt + j], a);
+        Bi[i * ldt + j] = a;
+    }
+    __syncwarp();
+    // dJ/dB_s (part without K0xz) = 1/2 (B^-1 - B^-1 Ktil B^-1), contracted with dB/d(theta1)
+    for (int e = lane; e < T * T; e += 32) {
+        int i = e / T, j = e % T;
+        double a = 0.0;
+        for (int k = 0; k < T; k++) a = fma(Bw[i * ldt + k], Bi[k * ldt + j], a);
+        double gb = 0.5 * (Bw[i * ldt + j] - a);
+        accum_grads<false>(sp1, kp1, xs + i * Q, xs + j * Q, gb, gos1, gls1, dummy);
+    }
+    bd = warp_sum(bd);
+    double fsum = warp_sum(lv);
+    double* scal = acc + off.o[HLVAE_ACC_SCAL] + (int64_t)l * HLVAE_NSCAL;
+    if (lane == 0) {
+        atomicAdd(scal + 1, bd);
+        atomicAdd(scal + 2, logdet);
+        atomicAdd(scal + 3, fsum);
+    }
+#pragma unroll
+    for (int r = 0; r < HLVAE_MAX_COMPS; r++) {
+        if (r < sp0.ncomp) {
+            double a = warp_sum(gos0[r]), b = warp_sum(gls0[r]);
+            if (lane == 0) {
+                atomicAdd(acc + off.o[HLVAE_ACC_GOS0] + (int64_t)r * L + l, a);
+                if (sp0.comp[r].se_col >= 0) atomicAdd(acc + off.o[HLVAE_ACC_GLS0] + (int64_t)r * L + l, b);
+            }
+        }
+        if (r < sp1.ncomp) {
+            double a = warp_sum(gos1[r]), b = warp_sum(gls1[r]);
+            if (lane == 0) {
+                atomicAdd(acc + off.o[HLVAE_ACC_GOS1] + (int64_t)r * L + l, a);
+                if (sp1.comp[r].se_col >= 0) atomicAdd(acc + off.o[HLVAE_ACC_GLS1] + (int64_t)r * L + l, b);
+            }
+        }
+    }
+}
+
+// =====================================================================================
+// kl_panel_k
+// =====================================================================================
+constexpr int PN_THREADS = 512;
+constexpr int PN_SMAX = 16;   // subjects per panel
+
+template <int MP, int RP, bool G_SMEM>
+struct PanelSmem {
+    static constexpr int LD = MP + 4;          // leading dim of row panels: conflict-free DMMA fragment loads
+    static constexpr int BCAP = RP * HLVAE_TMAX;
+    static constexpr size_t doubles = (size_t)HLVAE_MAX_Q * MP /*Zs*/ + MP /*ws*/ + (G_SMEM ? (size_t)MP * LD : 0) +
+                                      2 * (size_t)RP * LD /*Kb,Vb*/ + BCAP /*Bs*/ + (size_t)RP * HLVAE_MAX_Q /*xs*/ +
+                                      3 * RP /*mus, rv, rho*/ + (size_t)MP * HLVAE_MAX_COMPS /*zacc*/ +
+                                      4 * HLVAE_MAX_COMPS + 8 /*hyper acc + A*/;
+    static constexpr size_t ints = 2 * RP + 2 * (PN_SMAX + 1) + 8;
+    static constexpr size_t bytes = doubles * 8 + ints * 4;
+};
+
+template <int MP, int RP, bool G_SMEM, typename TS>
+__global__ void __launch_bounds__(PN_THREADS, 1)
+kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__ os0, const double* __restrict__ ls0,
+           const __grid_constant__ hlvae_kspec_t sp1, const double* __restrict__ os1, const double* __restrict__ ls1,
+           int L, int Q, int M, const double* __restrict__ x, int64_t ldx, const double* __restrict__ z,
+           const int32_t* __restrict__ row_idx, const int32_t* __restrict__ subj_ptr,
+           const int32_t* __restrict__ tt_ptr, int n_subj, int subj_per_chunk, const TS* __restrict__ mu,
+           int64_t ld_mu, const double* __restrict__ w, const double* __restrict__ G,
+           const double* __restrict__ binv, int64_t tt_total, double* __restrict__ acc, const AccOff off,
+           double* __restrict__ g_mu, int32_t* __restrict__ status) {
+    using SM = PanelSmem<MP, RP, G_SMEM>;
+    constexpr int LD = SM::LD;
+    constexpr int SI = MP / 32;   // S tiles (8x8) per warp per dim; 16 warps as 4 x 4
+    constexpr int WR = RP / 32;   // W tile rows per warp
+    constexpr int WC = MP / 32;   // W tile cols per warp
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* Zs = reinterpret_cast<double*>(smem_raw);          // [Q][MP] transposed
+    double* ws = Zs + HLVAE_MAX_Q * MP;
+    double* Gs = ws + MP;                                      // [MP][LD] if G_SMEM
+    double* Kb = Gs + (G_SMEM ? MP * LD : 0);                  // [RP][LD]  K0xz, later W = V G
+    double* Vb = Kb + RP * LD;                                 // [RP][LD]  B^-1 K0xz
+    double* Bs = Vb + RP * LD;                                 // B^-1 blocks (compact), later dJ/dB blocks
+    double* xs = Bs + SM::BCAP;                                // [RP][Q]
+    double* mus = xs + RP * HLVAE_MAX_Q;
+    double* rv = mus + RP;
+    double* rho = rv + RP;
+    double* zacc = rho + RP;                                   // [MP][MAX_COMPS]
+    double* hyp = zacc + MP * HLVAE_MAX_COMPS;                 // gos0, gls0, gos1, gls1, A
+    int* grow = reinterpret_cast<int*>(hyp + 4 * HLVAE_MAX_COMPS + 8);
+    int* sub_of_row = grow + RP;
+    int* sub_r0 = sub_of_row + RP;                             // [PN_SMAX+1]
+    int* sub_b0 = sub_r0 + PN_SMAX + 1;                        // [PN_SMAX+1]
+    int* meta = sub_b0 + PN_SMAX + 1;                          // nsub, first subject, next subject
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wi = warp >> 2, wj = warp & 3;
+    const int l = blockIdx.y;
+    const int s_begin = blockIdx.x * subj_per_chunk;
+    const int s_end = min(n_subj, s_begin + subj_per_chunk);
+
+    KParams kp0, kp1;
+    load_kparams(kp0, sp0, os0, ls0, L, l);
+    load_kparams(kp1, sp1, os1, ls1, L, l);
+
+    // ---- per-CTA setup: inducing points of this latent dim (transposed), w, G
+    for (int e = tid; e < HLVAE_MAX_Q * MP; e += PN_THREADS) {
+        int q = e / MP, m = e % MP;
+        Zs[e] = (q < Q && m < M) ? z[((int64_t)l * M + m) * Q + q] : 0.0;
+    }
+    for (int m = tid; m < MP; m += PN_THREADS) ws[m] = (m < M) ? w[(int64_t)l * M + m] : 0.0;
+    if (G_SMEM) {
+        for (int e = tid; e < MP * LD; e += PN_THREADS) {
+            int i = e / LD, j = e % LD;
+            Gs[e] = (i < M && j < M) ? G[((int64_t)l * M + i) * M + j] : 0.0;
+        }
+    }
+    for (int e = tid; e < MP * HLVAE_MAX_COMPS + 4 * HLVAE_MAX_COMPS + 8; e += PN_THREADS) zacc[e] = 0.0;
+    const double* Gl = G + (int64_t)l * M * M;
+
+    double sacc[SI][SI][2];
+#pragma unroll
+    for (int a = 0; a < SI; a++)
+#pragma unroll
+        for (int b = 0; b < SI; b++) sacc[a][b][0] = sacc[a][b][1] = 0.0;
+    double p_acc = 0.0, gw_acc = 0.0, a_acc = 0.0;
+
+    if (tid == 0) meta[2] = s_begin;
+    __syncthreads();
+
+    while (true) {
+        // ---- P0: pack whole subjects into a panel of at most RP rows
+        if (tid == 0) {
+            int s = meta[2], ns = 0, rows = 0, bsz = 0;
+            meta[1] = s;
+            sub_r0[0] = 0;
+            sub_b0[0] = 0;
+            while (s < s_end && ns < PN_SMAX) {
+                int T = subj_ptr[s + 1] - subj_ptr[s];
+                if (T > HLVAE_TMAX) {   // reported by kl_subject_k as well; skip here
+                    if (ns == 0) { s++; meta[1] = s; continue; }
+                    break;
+                }
+                if (rows + T > RP) break;
+                rows += T;
+                bsz += T * T;
+                ns++;
+                s++;
+                sub_r0[ns] = rows;
+                sub_b0[ns] = bsz;
+            }
+            meta[0] = ns;
+            meta[2] = s;
+        }
+        __syncthreads();
+        const int nsub = meta[0];
+        if (nsub == 0) break;
+        const int s_first = meta[1];
+        const int R = sub_r0[nsub];
+        const int R8 = (R + 7) & ~7;
+        const int pr0 = subj_ptr[s_first];
+        if (tid < R) {
+            int k = 0;
+            while (tid >= sub_r0[k + 1]) k++;
+            sub_of_row[tid] = k;
+            int g = row_idx[pr0 + tid];
+            grow[tid] = g;
+            for (int q = 0; q < Q; q++) xs[tid * Q + q] = x[(int64_t)g * ldx + q];
+            mus[tid] = (double)mu[(int64_t)g * ld_mu + l];
+        }
+        {
+            const double* bsrc = binv + (int64_t)l * tt_total + tt_ptr[s_first];
+            const int nb = sub_b0[nsub];
+            for (int e = tid; e < nb; e += PN_THREADS) Bs[e] = bsrc[e];
+        }
+        __syncthreads();
+
+        // ---- P1: K0xz rows (elbo_functions.py:147 / :222), zero padded to [R8][MP]
+        for (int e = tid; e < R8 * MP; e += PN_THREADS) {
+            int r = e / MP, m = e % MP;
+            double v = 0.0;
+            if (r < R && m < M) v = eval_additive(sp0, kp0, xs + r * Q, Zs + m, 1, MP);
+            Kb[r * LD + m] = v;
+        }
+        __syncthreads();
+
+        // ---- P2: V = B^-1 K0xz (block diagonal, :160 / :254); r = K0xz w - mu (:166 / :230)
+        for (int e = tid; e < R8 * MP; e += PN_THREADS) {
+            int r = e / MP, m = e % MP;
+            double v = 0.0;
+            if (r < R) {
+                int k = sub_of_row[r];
+                int rs = sub_r0[k], T = sub_r0[k + 1] - rs;
+                const double* brow = Bs + sub_b0[k] + (r - rs) * T;
+                for (int t = 0; t < T; t++) v = fma(brow[t], Kb[(rs + t) * LD + m], v);
+            }
+            Vb[r * LD + m] = v;
+        }
+        for (int r = warp; r < R; r += PN_THREADS / 32) {
+            double a = 0.0;
+            for (int m = lane; m < MP; m += 32) a = fma(Kb[r * LD + m], ws[m], a);
+            a = warp_sum(a);
+            if (lane == 0) rv[r] = a - mus[r];
+        }
+        __syncthreads();
+
+        // ---- P3a: rho = B^-1 r; A += r . rho (:167 / :256); dJ/dmu = -rho
+        if (tid < R) {
+            int k = sub_of_row[tid];
+            int rs = sub_r0[k], T = sub_r0[k + 1] - rs;
+            const double* brow = Bs + sub_b0[k] + (tid - rs) * T;
+            double a = 0.0;
+            for (int t = 0; t < T; t++) a = fma(brow[t], rv[rs + t], a);
+            rho[tid] = a;
+            a_acc = fma(rv[tid], a, a_acc);
+            g_mu[(int64_t)grow[tid] * L + l] = -a;
+        }
+        __syncthreads();
+
+        // ---- P3b: S += K0xz^T V on the FP64 tensor pipe (:161 / :254,266); p, gw
+        {
+            const int R4 = (R + 3) & ~3;
+            const int kr = lane & 3, kc = lane >> 2;
+            for (int k0 = 0; k0 < R4; k0 += 4) {
+                double af[SI], bf[SI];
+#pragma unroll
+                for (int t = 0; t < SI; t++) {
+                    af[t] = Kb[(k0 + kr) * LD + (wi * SI + t) * 8 + kc];
+                    bf[t] = Vb[(k0 + kr) * LD + (wj * SI + t) * 8 + kc];
+                }
+#pragma unroll
+                for (int a = 0; a < SI; a++)
+#pragma unroll
+                    for (int b = 0; b < SI; b++) dmma884(sacc[a][b][0], sacc[a][b][1], af[a], bf[b]);
+            }
+            if (tid < MP) {
+                double pa = 0.0, ga = 0.0;
+                for (int r = 0; r < R; r++) {
+                    pa = fma(Vb[r * LD + tid], mus[r], pa);      // p (:188 / :265)
+                    ga = fma(Kb[r * LD + tid], rho[r], ga);      // dJ/dw
+                }
+                p_acc += pa;
+                gw_acc += ga;
+            }
+        }
+        __syncthreads();
+
+        // ---- P4: W = V G  (dJ/dS = G / 2 applied on both sides -> dJ/dK0xz = W + rho w^T)
+        {
+            const int ar = lane >> 2, ac = lane & 3;
+#pragma unroll
+            for (int tr = 0; tr < WR; tr++) {
+                const int rt = wi * WR + tr;
+                if (rt * 8 < R) {
+                    double c[WC][2];
+#pragma unroll
+                    for (int t = 0; t < WC; t++) c[t][0] = c[t][1] = 0.0;
+                    for (int k0 = 0; k0 < MP; k0 += 4) {
+                        double a = Vb[(rt * 8 + ar) * LD + k0 + ac];
+#pragma unroll
+                        for (int t = 0; t < WC; t++) {
+                            const int col = (wj * WC + t) * 8 + ar;   // B frag: row = k0 + lane%4, col = lane/4
+                            double b;
+                            if (G_SMEM) {
+                                b = Gs[(k0 + ac) * LD + col];
+                            } else {
+                                b = (k0 + ac < M && col < M) ? Gl[(int64_t)(k0 + ac) * M + col] : 0.0;
+                            }
+                            dmma884(c[t][0], c[t][1], a, b);
+                        }
+                    }
+                    // all warps finished reading Kb as K0xz at the barrier above
+#pragma unroll
+                    for (int t = 0; t < WC; t++) {
+                        double2 v2 = make_double2(c[t][0], c[t][1]);
+                        *reinterpret_cast<double2*>(&Kb[(rt * 8 + ar) * LD + (wj * WC + t) * 8 + 2 * ac]) = v2;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- P5: dJ/dB_s (K0xz part) = -1/2 (rho rho^T + W V^T) -> Bs ; dJ/dK0xz -> hyper-parameters and Z
+        {
+            const int nb = sub_b0[nsub];
+            for (int e = tid; e < nb; e += PN_THREADS) {
+                int k = 0;
+                while (e >= sub_b0[k + 1]) k++;
+                int rs = sub_r0[k], T = sub_r0[k + 1] - rs;
+                int le = e - sub_b0[k];
+                int i = le / T, j = le % T;
+                double a = rho[rs + i] * rho[rs + j];
+                const double* wr = Kb + (rs + i) * LD;
+                const double* vr = Vb + (rs + j) * LD;
+                for (int m = 0; m < MP; m++) a = fma(wr[m], vr[m], a);
+                Bs[e] = -0.5 * a;
+            }
+            double gos[HLVAE_MAX_COMPS], gls[HLVAE_MAX_COMPS], gxb[HLVAE_MAX_COMPS];
+#pragma unroll
+            for (int r = 0; r < HLVAE_MAX_COMPS; r++) gos[r] = gls[r] = gxb[r] = 0.0;
+            const int m = tid % MP;   // PN_THREADS is a multiple of MP: one column per thread
+            if (m < M) {
+                for (int r = tid / MP; r < R; r += PN_THREADS / MP) {
+                    double g = Kb[r * LD + m] + rho[r] * ws[m];
+                    accum_grads<true>(sp0, kp0, xs + r * Q, Zs + m, g, gos, gls, gxb, 1, MP);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < HLVAE_MAX_COMPS; r++) {
+                if (r < sp0.ncomp) {
+                    double a = warp_sum(gos[r]), b = warp_sum(gls[r]);
+                    if (lane == 0) {
+                        atomicAdd(&hyp[r], a);
+                        atomicAdd(&hyp[HLVAE_MAX_COMPS + r], b);
+                    }
+                    if (m < M && sp0.comp[r].se_col >= 0 && gxb[r] != 0.0) atomicAdd(&zacc[m * HLVAE_MAX_COMPS + r], gxb[r]);
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- P6: contract dJ/dB_s with dB_s/d(theta1)
+        {
+            double gos[HLVAE_MAX_COMPS], gls[HLVAE_MAX_COMPS], dummy[HLVAE_MAX_COMPS];
+#pragma unroll
+            for (int r = 0; r < HLVAE_MAX_COMPS; r++) gos[r] = gls[r] = dummy[r] = 0.0;
+            const int nb = sub_b0[nsub];
+            for (int e = tid; e < nb; e += PN_THREADS) {
+                int k = 0;
+                while (e >= sub_b0[k + 1]) k++;
+                int rs = sub_r0[k], T = sub_r0[k + 1] - rs;
+                int le = e - sub_b0[k];
+                int i = le / T, j = le % T;
+                accum_grads<false>(sp1, kp1, xs + (rs + i) * Q, xs + (rs + j) * Q, Bs[e], gos, gls, dummy);
+            }
+#pragma unroll
+            for (int r = 0; r < HLVAE_MAX_COMPS; r++) {
+                if (r < sp1.ncomp) {
+                    double a = warp_sum(gos[r]), b = warp_sum(gls[r]);
+                    if (lane == 0) {
+                        atomicAdd(&hyp[2 * HLVAE_MAX_COMPS + r], a);
+                        atomicAdd(&hyp[3 * HLVAE_MAX_COMPS + r], b);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- flush CTA accumulators
+    {
+        double* Sg = acc + off.o[HLVAE_ACC_S] + (int64_t)l * M * M;
+        const int cr = lane >> 2, cc = 2 * (lane & 3);
+#pragma unroll
+        for (int a = 0; a < SI; a++)
+#pragma unroll
+            for (int b = 0; b < SI; b++) {
+                int i = (wi * SI + a) * 8 + cr, j = (wj * SI + b) * 8 + cc;
+                if (i < M) {
+                    if (j < M) atomicAdd(Sg + (int64_t)i * M + j, sacc[a][b][0]);
+                    if (j + 1 < M) atomicAdd(Sg + (int64_t)i * M + j + 1, sacc[a][b][1]);
+                }
+            }
+        if (tid < M) {
+            atomicAdd(acc + off.o[HLVAE_ACC_P] + (int64_t)l * M + tid, p_acc);
+            atomicAdd(acc + off.o[HLVAE_ACC_GW] + (int64_t)l * M + tid, gw_acc);
+        }
+        a_acc = warp_sum(a_acc);
+        if (lane == 0 && a_acc != 0.0) atomicAdd(&hyp[4 * HLVAE_MAX_COMPS], a_acc);
+        __syncthreads();
+        if (tid == 0) atomicAdd(acc + off.o[HLVAE_ACC_SCAL] + (int64_t)l * HLVAE_NSCAL + 0, hyp[4 * HLVAE_MAX_COMPS]);
+        if (tid < HLVAE_MAX_COMPS) {
+            const int r = tid;
+            if (r < sp0.ncomp) {
+                atomicAdd(acc + off.o[HLVAE_ACC_GOS0] + (int64_t)r * L + l, hyp[r]);
+                if (sp0.comp[r].se_col >= 0)
+                    atomicAdd(acc + off.o[HLVAE_ACC_GLS0] + (int64_t)r * L + l, hyp[HLVAE_MAX_COMPS + r]);
+            }
+            if (r < sp1.ncomp) {
+                atomicAdd(acc + off.o[HLVAE_ACC_GOS1] + (int64_t)r * L + l, hyp[2 * HLVAE_MAX_COMPS + r]);
+                if (sp1.comp[r].se_col >= 0)
+                    atomicAdd(acc + off.o[HLVAE_ACC_GLS1] + (int64_t)r * L + l, hyp[3 * HLVAE_MAX_COMPS + r]);
+            }
+        }
+        double* gz = acc + off.o[HLVAE_ACC_GZ] + (int64_t)l * M * Q;
+        for (int e = tid; e < M * HLVAE_MAX_COMPS; e += PN_THREADS) {
+            int m = e / HLVAE_MAX_COMPS, r = e % HLVAE_MAX_COMPS;
+            if (r < sp0.ncomp && sp0.comp[r].se_col >= 0) {
+                double v = zacc[e];
+                if (v != 0.0) atomicAdd(gz + (int64_t)m * Q + sp0.comp[r].se_col, v);
+            }
+        }
+    }
+}
+
+template <int MP, int RP, bool G_SMEM, typename TS>
+int launch_panel(const hlvae_kspec_t* spec0, const double* os0, const double* ls0, const hlvae_kspec_t* spec1,
+                 const double* os1, const double* ls1, int L, int Q, int M, const double* x, int64_t ldx,
+                 const double* z, const int32_t* row_idx, const int32_t* subj_ptr, const int32_t* tt_ptr, int n_subj,
+                 int subj_per_chunk, const void* mu, int64_t ld_mu, const double* w, const double* G,
+                 const double* binv, int64_t tt_total, double* acc, const AccOff& off, double* g_mu, int32_t* status,
+                 cudaStream_t st) {
+    using SM = PanelSmem<MP, RP, G_SMEM>;
+    auto kern = kl_panel_k<MP, RP, G_SMEM, TS>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::bytes);
+    if (e != cudaSuccess) return (int)e;
+    int n_chunks = (n_subj + subj_per_chunk - 1) / subj_per_chunk;
+    dim3 grid(n_chunks, L);
+    kern<<<grid, PN_THREADS, SM::bytes, st>>>(*spec0, os0, ls0, *spec1, os1, ls1, L, Q, M, x, ldx, z, row_idx,
+                                              subj_ptr, tt_ptr, n_subj, subj_per_chunk, (const TS*)mu, ld_mu, w, G,
+                                              binv, tt_total, acc, off, g_mu, status);
+    HLVAE_CHECK_LAUNCH();
+    return 0;
+}
+
+template <typename TS>
+int dispatch_panel(int M, const hlvae_kspec_t* spec0, const double* os0, const double* ls0,
+                   const hlvae_kspec_t* spec1, const double* os1, const double* ls1, int L, int Q, const double* x,
+                   int64_t ldx, const double* z, const int32_t* row_idx, const int32_t* subj_ptr,
+                   const int32_t* tt_ptr, int n_subj, int subj_per_chunk, const void* mu, int64_t ld_mu,
+                   const double* w, const double* G, const double* binv, int64_t tt_total, double* acc,
+                   const AccOff& off, double* g_mu, int32_t* status, cudaStream_t st) {
+#define HLVAE_PANEL(MP, RP, GS)                                                                                       \
+    return launch_panel<MP, RP, GS, TS>(spec0, os0, ls0, spec1, os1, ls1, L, Q, M, x, ldx, z, row_idx, subj_ptr,     \
+                                        tt_ptr, n_subj, subj_per_chunk, mu, ld_mu, w, G, binv, tt_total, acc, off,   \
+                                        g_mu, status, st)
+    if (M <= 32) { HLVAE_PANEL(32, 64, true); }
+    if (M <= 64) { HLVAE_PANEL(64, 64, true); }
+    if (M <= 128) { HLVAE_PANEL(128, 32, false); }
+#undef HLVAE_PANEL
+    return HLVAE_E_UNSUPPORTED;
+}
+
+void fill_offsets(int L, int M, int Q, int64_t* o) {
+    int64_t p = 0;
+    o[HLVAE_ACC_S] = p;    p += (int64_t)L * M * M;
+    o[HLVAE_ACC_P] = p;    p += (int64_t)L * M;
+    o[HLVAE_ACC_GW] = p;   p += (int64_t)L * M;
+    o[HLVAE_ACC_SCAL] = p; p += (int64_t)L * HLVAE_NSCAL;
+    o[HLVAE_ACC_GZ] = p;   p += (int64_t)L * M * Q;
+    o[HLVAE_ACC_GOS0] = p; p += (int64_t)HLVAE_MAX_COMPS * L;
+    o[HLVAE_ACC_GLS0] = p; p += (int64_t)HLVAE_MAX_COMPS * L;
+    o[HLVAE_ACC_GOS1] = p; p += (int64_t)HLVAE_MAX_COMPS * L;
+    o[HLVAE_ACC_GLS1] = p; p += (int64_t)HLVAE_MAX_COMPS * L;
+    o[HLVAE_ACC_TOTAL] = p;
+}
+
+}  // namespace
+
+extern "C" int hlvae_kl_acc_layout(int L, int M, int Q, int64_t* offsets) {
+    if (L <= 0 || M <= 0 || Q <= 0 || !offsets) return HLVAE_E_ARG;
+    fill_offsets(L, M, Q, offsets);
+    return 0;
+}
+
+extern "C" int hlvae_kl_subject(const hlvae_kspec_t* spec0, const double* os0, const double* ls0,
+                                const hlvae_kspec_t* spec1, const double* os1, const double* ls1, const double* noise,
+                                int L, int Q, const double* x, int64_t ldx, const int32_t* row_idx,
+                                const int32_t* subj_ptr, const int32_t* tt_ptr, int n_subj, int t_cap,
+                                const void* log_v, int64_t ld_lv, int dtype, double* binv, int64_t tt_total,
+                                double* acc, int M, double* g_logv, int32_t* status, void* stream) {
+    if (!hlvae::spec_valid(spec0, Q) || !hlvae::spec_valid(spec1, Q) || L <= 0 || Q <= 0 || Q > HLVAE_MAX_Q ||
+        M <= 0 || n_subj < 0 || t_cap <= 0 || t_cap > HLVAE_TMAX || !x || !row_idx || !subj_ptr || !tt_ptr || !log_v ||
+        !binv || !acc || !g_logv || !noise)
+        return HLVAE_E_ARG;
+    if (dtype != HLVAE_F32 && dtype != HLVAE_F64) return HLVAE_E_ARG;
+    if (n_subj == 0) return 0;
+    AccOff off;
+    fill_offsets(L, M, Q, off.o);
+    const int ldt = t_cap | 1;
+    size_t smem = (size_t)SJ_WARPS * ((size_t)t_cap * Q + 3 * (size_t)t_cap * ldt) * sizeof(double);
+    int64_t pairs = (int64_t)n_subj * L;
+    unsigned grid = (unsigned)((pairs + SJ_WARPS - 1) / SJ_WARPS);
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e;
+    if (dtype == HLVAE_F64) {
+        auto kern = kl_subject_k<double>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        kern<<<grid, SJ_WARPS * 32, smem, st>>>(*spec0, os0, ls0, *spec1, os1, ls1, noise, L, Q, x, ldx, row_idx,
+                                                subj_ptr, tt_ptr, n_subj, t_cap, (const double*)log_v, ld_lv, binv,
+                                                tt_total, acc, off, g_logv, status);
+    } else {
+        auto kern = kl_subject_k<float>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        kern<<<grid, SJ_WARPS * 32, smem, st>>>(*spec0, os0, ls0, *spec1, os1, ls1, noise, L, Q, x, ldx, row_idx,
+                                                subj_ptr, tt_ptr, n_subj, t_cap, (const float*)log_v, ld_lv, binv,
+                                                tt_total, acc, off, g_logv, status);
+    }
+    HLVAE_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int hlvae_kl_panel(const hlvae_kspec_t* spec0, const double* os0, const double* ls0,
+                              const hlvae_kspec_t* spec1, const double* os1, const double* ls1, int L, int Q, int M,
+                              const double* x, int64_t ldx, const double* z, const int32_t* row_idx,
+                              const int32_t* subj_ptr, const int32_t* tt_ptr, int n_subj, int subj_per_chunk,
+                              const void* mu, int64_t ld_mu, int dtype, const double* w, const double* G,
+                              const double* binv, int64_t tt_total, double* acc, double* g_mu, int32_t* status,
+                              void* stream) {
+    if (!hlvae::spec_valid(spec0, Q) || !hlvae::spec_valid(spec1, Q) || L <= 0 || Q <= 0 || Q > HLVAE_MAX_Q ||
+        M <= 0 || n_subj < 0 || subj_per_chunk <= 0 || !x || !z || !row_idx || !subj_ptr || !tt_ptr || !mu || !w ||
+        !G || !binv || !acc || !g_mu)
+        return HLVAE_E_ARG;
+    if (M > 128) return HLVAE_E_UNSUPPORTED;
+    if (n_subj == 0) return 0;
+    AccOff off;
+    fill_offsets(L, M, Q, off.o);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == HLVAE_F64)
+        return dispatch_panel<double>(M, spec0, os0, ls0, spec1, os1, ls1, L, Q, x, ldx, z, row_idx, subj_ptr, tt_ptr,
+                                      n_subj, subj_per_chunk, mu, ld_mu, w, G, binv, tt_total, acc, off, g_mu, status,
+                                      st);
+    if (dtype == HLVAE_F32)
+        return dispatch_panel<float>(M, spec0, os0, ls0, spec1, os1, ls1, L, Q, x, ldx, z, row_idx, subj_ptr, tt_ptr,
+                                     n_subj, subj_per_chunk, mu, ld_mu, w, G, binv, tt_total, acc, off, g_mu, status,
+                                     st);
+    return HLVAE_E_ARG;
+}

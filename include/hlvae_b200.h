@@ -1,0 +1,189 @@
+/*
+ * hlvae_b200 - C ABI of the B200-native HL-VAE ELBO hot path.
+ *
+ * The reference (MineOgre/HL-VAE) is pure Python and has no FFI: its boundary for this
+ * path is a set of Python call sites.  Each entry point below names the reference
+ * interface it sits behind (paths relative to the reference root); the Python host layer
+ * in hl-vae_b200/ mirrors those interfaces and calls these functions through ctypes.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and integer sizes only; no torch types.
+ *  - Every pointer is a DEVICE pointer owned by the caller for the duration of the call
+ *    (the library allocates nothing and keeps no pointer after return), except
+ *    `hlvae_kspec_t*`, which is a HOST pointer copied into kernel parameters.
+ *  - `stream` is a cudaStream_t passed as void*.  Calls only enqueue work; no host sync.
+ *  - Return value: 0 on success, negative on argument error (HLVAE_E_*), positive =
+ *    cudaError_t from the launch.  Numerical failures (non positive-definite block,
+ *    subject longer than HLVAE_TMAX) are reported through the device status words
+ *    `status[0..3]` = {code, latent, subject, 0}; the host wrapper reads them.
+ *  - Functions are re-entrant and hold no global mutable state.
+ *  - Floating-point arrays are float64 unless a `dtype` argument says otherwise
+ *    (HLVAE_F32 / HLVAE_F64 select the storage type of streamed arrays; arithmetic is
+ *    float64 inside the kernels either way).
+ */
+#ifndef HLVAE_B200_H
+#define HLVAE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HLVAE_ABI_VERSION 1
+
+#define HLVAE_MAX_COMPS 8   /* additive components per kernel                      */
+#define HLVAE_MAX_DISC 3    /* categorical / binary factors per component          */
+#define HLVAE_MAX_Q 8       /* covariate columns                                   */
+#define HLVAE_TMAX 32       /* rows per subject handled by the per-subject kernels */
+
+#define HLVAE_F32 0
+#define HLVAE_F64 1
+
+#define HLVAE_KIND_CAT 1    /* kernel_spec.py:26-32  CatKernel: x1 == x2           */
+#define HLVAE_KIND_BIN 2    /* kernel_spec.py:9-23   BinKernel: x1 + x2 == 2       */
+
+#define HLVAE_E_ARG (-1)
+#define HLVAE_E_UNSUPPORTED (-2)
+
+#define HLVAE_STATUS_NOT_PD 1
+#define HLVAE_STATUS_T_TOO_LARGE 2
+
+/* One ScaleKernel term of an additive kernel (kernel_gen.py:219-310): outputscale *
+ * [SE(x[se_col]; lengthscale)] * prod_i disc_i.  se_col < 0: no squared-exponential
+ * factor.  Component r uses outputscale[r][l] and lengthscale[r][l]. */
+typedef struct {
+    int32_t se_col;
+    int32_t ndisc;
+    int32_t disc_kind[HLVAE_MAX_DISC];
+    int32_t disc_col[HLVAE_MAX_DISC];
+} hlvae_comp_t;
+
+typedef struct {
+    int32_t ncomp;
+    int32_t reserved;
+    hlvae_comp_t comp[HLVAE_MAX_COMPS];
+} hlvae_kspec_t;
+
+int hlvae_version(void);
+/* sizeof(hlvae_kspec_t) as compiled, so a binding can verify its struct layout. */
+int hlvae_sizeof_kspec(void);
+
+/* ------------------------------------------------------------------------------------
+ * Dense additive-kernel evaluation.  Replaces `covar_module(x1, x2).evaluate()`
+ * (elbo_functions.py:147-148,222-223; utils.py:128-130) for kernel objects built by
+ * kernel_gen.generate_kernel_batched (kernel_gen.py:199-310).
+ *   x1: [n1,Q] (bs1 = 0) or [L,n1,Q] (bs1 = n1*ld1) row-major with leading dim ld1
+ *   out: [L,n1,n2];  outputscale, lengthscale: [ncomp, L] (constrained values)
+ * bwd: g_out [L,n1,n2] -> g_os, g_ls [ncomp,L] (accumulated, caller zero-fills),
+ *   g_x1 / g_x2 [L,n,Q] (nullable, accumulated; squared-exponential columns only).
+ * ---------------------------------------------------------------------------------- */
+int hlvae_kernel_eval_fwd(const hlvae_kspec_t* spec, const double* outputscale, const double* lengthscale,
+                          int L, int Q, const double* x1, int n1, int64_t ld1, int64_t bs1,
+                          const double* x2, int n2, int64_t ld2, int64_t bs2, double* out, void* stream);
+int hlvae_kernel_eval_bwd(const hlvae_kspec_t* spec, const double* outputscale, const double* lengthscale,
+                          int L, int Q, const double* x1, int n1, int64_t ld1, int64_t bs1,
+                          const double* x2, int n2, int64_t ld2, int64_t bs2, const double* g_out,
+                          double* g_os, double* g_ls, double* g_x1, double* g_x2, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Streaming part of the KL upper bound: everything in
+ * elbo_functions.minibatch_KLD_upper_bound (elbo_functions.py:118-193) and
+ * minibatch_KLD_upper_bound_iter (:196-285) that scales with the minibatch.
+ *
+ * Subjects are described in CSR form over a row permutation: subject s owns rows
+ * row_idx[subj_ptr[s] .. subj_ptr[s+1]) of x / mu / log_v; tt_ptr[s] = sum_{s'<s} T_s'^2.
+ *
+ * With J = 1/2 (A + B + C + D + E - F) of elbo_functions.py:166-173 (w = iK m and
+ * G = iK H iK - iK held constant), the two calls produce, per latent dimension l:
+ *   S = sum_s K0xz_s^T B_s^-1 K0xz_s   (:161 / :254,266)      p = sum_s K0xz_s^T B_s^-1 mu_s (:188 / :265)
+ *   gw = dJ/dw = sum_s K0xz_s^T B_s^-1 (K0xz_s w - mu_s)
+ *   scal[0] = A (:166-167), scal[1] = B + sum(iB * K0_st) (:168,170), scal[2] = C (:169), scal[3] = F (:173)
+ * and dJ/d{mu, log_v, Z, outputscale0, lengthscale0, outputscale1, lengthscale1}.
+ *
+ * hlvae_kl_subject : per-(subject, l) warp: B_s = K1(x_s,x_s) + noise I (:150-151 / :249-250),
+ *                    Cholesky, explicit inverse (:156-157 / :251-252), writes binv
+ *                    [L, tt_total] and the terms that do not involve Z.
+ * hlvae_kl_panel   : per-(l, subject chunk) CTA: K0xz rows on the fly, B^-1 K0xz, the
+ *                    sufficient statistics (FP64 tensor-core mma), and the remaining gradients.
+ * `acc` is one float64 buffer the caller zero-fills; hlvae_kl_acc_layout gives offsets
+ * (in doubles) of {S, p, gw, scal, gZ, gos0, gls0, gos1, gls1, total}.  g_mu, g_logv:
+ * [N, L] contiguous, fully overwritten for the rows listed in row_idx.
+ * ---------------------------------------------------------------------------------- */
+#define HLVAE_ACC_S 0
+#define HLVAE_ACC_P 1
+#define HLVAE_ACC_GW 2
+#define HLVAE_ACC_SCAL 3
+#define HLVAE_ACC_GZ 4
+#define HLVAE_ACC_GOS0 5
+#define HLVAE_ACC_GLS0 6
+#define HLVAE_ACC_GOS1 7
+#define HLVAE_ACC_GLS1 8
+#define HLVAE_ACC_TOTAL 9
+#define HLVAE_NSCAL 4
+int hlvae_kl_acc_layout(int L, int M, int Q, int64_t* offsets /* [10] */);
+
+int hlvae_kl_subject(const hlvae_kspec_t* spec0, const double* os0, const double* ls0,
+                     const hlvae_kspec_t* spec1, const double* os1, const double* ls1, const double* noise,
+                     int L, int Q, const double* x, int64_t ldx,
+                     const int32_t* row_idx, const int32_t* subj_ptr, const int32_t* tt_ptr, int n_subj, int t_cap,
+                     const void* log_v, int64_t ld_lv, int dtype,
+                     double* binv, int64_t tt_total, double* acc, int M, double* g_logv,
+                     int32_t* status, void* stream);
+
+int hlvae_kl_panel(const hlvae_kspec_t* spec0, const double* os0, const double* ls0,
+                   const hlvae_kspec_t* spec1, const double* os1, const double* ls1,
+                   int L, int Q, int M, const double* x, int64_t ldx, const double* z,
+                   const int32_t* row_idx, const int32_t* subj_ptr, const int32_t* tt_ptr, int n_subj,
+                   int subj_per_chunk, const void* mu, int64_t ld_mu, int dtype,
+                   const double* w, const double* G, const double* binv, int64_t tt_total,
+                   double* acc, double* g_mu, int32_t* status, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Fused masked heterogeneous log-likelihood.  Replaces HLVAE.loglik_and_reconstruction
+ * (HLVAE.py:381-414) with the per-type functions of HL_VAE/loglik.py:27-213, plus the
+ * per-step monitoring transforms read_functions.statistics (:268-302, incl. the
+ * categorical / ordinal argmax imputation) and discrete_variables_transformation (:221-235).
+ *
+ * Variable d is described by var_kind[d] (HLVAE_VAR_*), var_nclass[d], var_dcol[d] (first
+ * column in data), var_pcol[d] (first column in theta / params); vparam [4, D] float64 holds
+ * per variable {normalisation mean, normalisation variance (already clamped), raw
+ * log-variance parameter, data divisor (255 for conv real data, else 1)}.
+ *   data [N,E_x], theta [N,P_theta], mask [N,D]: storage `dtype`; mask_u8 != 0: mask is uint8.
+ * fwd outputs (nullable): log_p_x, log_p_x_missing [N,D], params [N,P_theta], recon_mean,
+ *   recon_mode, data_tr [N,D] in storage dtype; ll_total[1] float64 += sum(log_p_x).
+ * bwd: g_lp [N,D] upstream gradient of log_p_x (nullable: then g_scalar is used for every
+ *   element) -> g_theta [N,P_theta] (overwritten), g_lvy [D] float64 (accumulated).
+ * ---------------------------------------------------------------------------------- */
+#define HLVAE_VAR_REAL 0
+#define HLVAE_VAR_POS 1
+#define HLVAE_VAR_COUNT 2
+#define HLVAE_VAR_CAT 3
+#define HLVAE_VAR_ORDINAL 4
+#define HLVAE_MAX_CLASS 16
+
+int hlvae_loglik_fwd(int64_t N, int D, int64_t ld_data, int64_t ld_theta,
+                     const int32_t* var_kind, const int32_t* var_nclass, const int32_t* var_dcol,
+                     const int32_t* var_pcol, const double* vparam,
+                     const void* data, const void* theta, const void* mask, int dtype, int mask_u8,
+                     void* log_p_x, void* log_p_x_missing, void* params,
+                     void* recon_mean, void* recon_mode, void* data_tr, double* ll_total, void* stream);
+int hlvae_loglik_bwd(int64_t N, int D, int64_t ld_data, int64_t ld_theta,
+                     const int32_t* var_kind, const int32_t* var_nclass, const int32_t* var_dcol,
+                     const int32_t* var_pcol, const double* vparam,
+                     const void* data, const void* theta, const void* mask, int dtype, int mask_u8,
+                     const void* g_lp, double g_scalar, void* g_theta, double* g_lvy, void* stream);
+
+/* Stand-alone forms of the monitoring transforms for callers that hold only `params` or
+ * `data` (training.py:84-91): read_functions.statistics (:268-302) -> mean, mode [N,D];
+ * read_functions.discrete_variables_transformation (:221-235) -> out [N,D]. */
+int hlvae_statistics(int64_t N, int D, int64_t ld_theta, const int32_t* var_kind, const int32_t* var_nclass,
+                     const int32_t* var_pcol, const double* vparam, const void* params, int dtype,
+                     void* mean, void* mode, void* stream);
+int hlvae_discrete_transform(int64_t N, int D, int64_t ld_data, const int32_t* var_kind, const int32_t* var_nclass,
+                             const int32_t* var_dcol, const void* data, int dtype, void* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HLVAE_B200_H */

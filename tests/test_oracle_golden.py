@@ -1,0 +1,69 @@
+"""CPU: the oracle reproduces every golden fixture (which hold outputs of the unmodified reference,
+written by oracle/make_goldens.py)."""
+import ast
+
+import numpy as np
+import pytest
+import torch
+
+import helpers as h
+from oracle import hlvae_oracle as orc
+
+DT = torch.float64
+
+
+@pytest.mark.parametrize("name", h.KL_CASES)
+def test_oracle_kl_matches_golden(name):
+    g = h.load(name)
+    kargs = ast.literal_eval(str(g["kargs"]))
+    fixed_T = int(g["T"]) if int(g["fixed_T_api"]) else None
+    ref = h.oracle_kl(kargs, int(g["L"]), h.t(g["x"]), h.t(g["mu"]), h.t(g["log_v"]), h.t(g["z"]), h.t(g["m"]),
+                      h.t(g["H"]), h.t(g["ros0"]), h.t(g["rls0"]), h.t(g["ros1"]), h.t(g["rls1"]), h.t(g["noise"]),
+                      int(g["P_tot"]), int(g["n_subj"]), int(g["N_tot"]), float(g["eps"]), fixed_T=fixed_T)
+    # fixtures hold the REFERENCE's outputs; tolerance = the float64 round-off floor between two
+    # evaluation orders at cond(K0zz) ~ 1e7 (see oracle/make_goldens.py)
+    assert h.rel_err(ref["kld"], g["kld"]) < 1e-6
+    for key in ("d_mu", "d_logv", "d_z", "d_m", "d_H"):
+        assert h.rel_err(ref[key], g[key]) < 2e-6, key
+    if int(g["natural_gradient"]):
+        assert h.rel_err(ref["grad_m"], g["grad_m"]) < 2e-6
+        assert h.rel_err(ref["grad_H"], g["grad_H"]) < 2e-6
+    for key in ("d_os0", "d_ls0", "d_os1", "d_ls1"):
+        if g[key].size:
+            assert h.rel_err(ref[key], g[key]) < 1e-4, key
+    for key in ("A", "B", "C", "D", "E", "F", "kld_qu_pu"):
+        assert h.rel_err(ref["terms"][key], g["term_" + key]) < 1e-12, key
+
+
+@pytest.mark.parametrize("name", h.LOGLIK_CASES)
+def test_oracle_loglik_matches_golden(name):
+    g = h.load(name)
+    types = h.parse_types(g)
+    descs, E_x, P_th = orc.build_layout(types)
+    nr, npos = h.golden_norm(g, "cpu")
+    lvr = h.t(g["log_vy_real"]) if g["log_vy_real"].size else None
+    lvp = h.t(g["log_vy_pos"]) if g["log_vy_pos"].size else None
+    theta = h.t(g["theta"]).requires_grad_(True)
+    lpx, lpm, params = orc.loglik_and_reconstruction(descs, h.t(g["data"]), h.t(g["mask"]), theta, lvr, lvp, nr, npos,
+                                                     bool(int(g["conv"])))
+    (lpx * h.t(g["g_up"])).sum().backward()
+    mean, mode = orc.statistics(descs, params.detach(), lvp)
+    dtr = orc.discrete_variables_transformation(descs, h.t(g["data"]))
+    assert h.rel_err(lpx, g["log_p_x"]) < 1e-12
+    assert h.rel_err(lpm, g["log_p_x_missing"]) < 1e-12
+    assert h.rel_err(params, g["params"]) < 1e-12
+    assert h.rel_err(theta.grad, g["d_theta"]) < 1e-12
+    assert np.array_equal(mean.numpy(), g["recon_mean"])
+    assert np.array_equal(mode.numpy(), g["recon_mode"])
+    assert np.array_equal(dtr.numpy(), g["data_transformed"])
+
+
+def test_fixed_T_and_iter_agree():
+    """elbo_functions.py:118-193 and :196-285 are the same mathematics when every subject has T rows."""
+    inp = h.make_kl_inputs(L=3, M=10, n_subj=4, T=5, seed=9)
+    a = h.oracle_kl(inp["kargs"], 3, inp["x"], inp["mu"], inp["lv"], inp["z"], inp["m"], inp["H"], inp["ros0"],
+                    inp["rls0"], inp["ros1"], inp["rls1"], inp["noise"], 200, 4, 200 * 5, 1e-6)
+    b = h.oracle_kl(inp["kargs"], 3, inp["x"], inp["mu"], inp["lv"], inp["z"], inp["m"], inp["H"], inp["ros0"],
+                    inp["rls0"], inp["ros1"], inp["rls1"], inp["noise"], 200, 4, 200 * 5, 1e-6, fixed_T=5)
+    assert h.rel_err(a["kld"], b["kld"]) < 1e-9
+    assert h.rel_err(a["grad_H"], b["grad_H"]) < 1e-9
