@@ -1,0 +1,390 @@
+#!/usr/bin/env python
+"""Benchmark of the HL-VAE per-step ELBO hot path (BASELINE.json metric: ELBO train steps/sec,
+forward + backward).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Workload (BASELINE.json configs[1]): synthetic HealthMNIST-shaped longitudinal minibatch, L=32
+latent dimensions, M=64 inducing points, 800 subjects x T=20 = 16000 rows per step, D4 variable
+layout (324 real + 972 categorical x 5 -> E_x = P_theta = 5184), default additive kernel.
+One step = fused masked log-likelihood forward+backward (theta given) + KL upper bound
+forward+backward (mu, log_v given) + natural-gradient update of (m, H): the part of
+training.py:82-137 this repo owns (the NN trunk stays stock PyTorch and is not timed).
+
+`value`  : steps/s with inputs resident in HBM (CUDA events, max over ranks).
+`e2e`    : steps/s through the same public functions with HOST (pinned) inputs: every step copies
+           data, mask, theta, mu, log_v, covariates host->device and reads the loss back.
+`roofline`: dominant kernel of the step, algorithmic work / CUDA-event time of that kernel measured
+           inside the timed region (events bracket each C-ABI call on the launching stream).
+`cpu_baseline`: the oracle port of the reference path (float64 PyTorch, all host cores) on a bounded
+           sample of the same workload; `--impl reference` runs only that and prints it as the line.
+N > 1: weak scaling, every rank owns 800 subjects of a global N x 800-subject minibatch and the
+per-latent accumulators are all-reduced once per step (NCCL); value counts 16000-row step
+equivalents per second over all ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics as pystat
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+L, M, Q, T = 32, 64, 6, 20
+SUBJ_PER_RANK = 800
+P_TOTAL, N_TOTAL = 5000, 100000            # ~100k-sample dataset of configs[1]
+EPS, NG_LR = 1e-6, 0.01
+WORKLOAD = "configs[1]: synthetic HealthMNIST-shaped, L=32, M=64, 800 subjects x T=20 = 16000 rows/step, D4 (324 real + 972 cat x5)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--subjects", type=int, default=SUBJ_PER_RANK)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: oracle port of the reference path on the host cores
+# ------------------------------------------------------------------------------------------
+def cpu_reference_arm(steps, warmup, sample_subjects=20, budget_s=25.0):
+    """Times oracle.elbo_path_step (float64 PyTorch restatement of training.py:82-137 for this path)
+    on a bounded sample: `sample_subjects` x T rows of the same workload.  Returns steps/s scaled
+    to the 16000-row step (cost is linear in rows; the replicated M x M part is not scaled down, so
+    the scaled figure slightly flatters the CPU)."""
+    from hlvae_b200 import synth
+    from oracle import hlvae_oracle as orc
+    torch.set_num_threads(os.cpu_count() or 1)
+    rng = np.random.default_rng(0)
+    gen = torch.Generator().manual_seed(0)
+    x, lens = synth.covariates(sample_subjects, T, rng)
+    pool, _ = synth.covariates(200, T, rng)
+    z = synth.inducing_points(pool, L, M, rng).requires_grad_(True)
+    N_b = x.shape[0]
+    types = synth.HEALTHMNIST_D4_TYPES
+    descs, E_x, P_th = orc.build_layout(types)
+    data, mask = synth.likelihood_batch(types, N_b, rng, observed=0.75, pixel_like=True)
+    spec0, spec1 = orc.compile_spec(**synth.DEFAULT_KERNEL_ARGS)
+    prm0 = orc.KernelParams.default(spec0, L).requires_grad_()
+    prm1 = orc.KernelParams.default(spec1, L).requires_grad_()
+    m, H = synth.variational_state(L, M, gen)
+    theta = torch.randn(N_b, P_th, generator=gen, dtype=torch.float64).requires_grad_(True)
+    mu = torch.randn(N_b, L, generator=gen, dtype=torch.float64).requires_grad_(True)
+    lv = (-3.0 * torch.rand(N_b, L, generator=gen, dtype=torch.float64)).requires_grad_(True)
+    lvr = torch.zeros(324, dtype=torch.float64, requires_grad=True)
+    state = dict(descs=descs, data=data, mask=mask, theta=theta, log_vy_real=lvr, conv=True, spec0=spec0, prm0=prm0,
+                 spec1=spec1, prm1=prm1, noise=torch.ones(L, dtype=torch.float64), m=m, H=H, x=x, mu=mu, log_v=lv,
+                 z=z, P=P_TOTAL, P_b=sample_subjects, N=N_TOTAL, id_covariate=2, eps=EPS,
+                 leaves=[theta, mu, lv, z, lvr, prm0.raw_outputscale, prm0.raw_lengthscale, prm1.raw_outputscale,
+                         prm1.raw_lengthscale])
+    times = []
+    t_start = time.perf_counter()
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        out = orc.elbo_path_step(state, NG_LR)
+        state["m"], state["H"] = out["m"], out["H"]
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+        if time.perf_counter() - t_start > budget_s and len(times) >= 2:
+            break
+    ms = 1e3 * pystat.median(times)
+    scale = (SUBJ_PER_RANK * T) / N_b
+    return dict(value=1e3 / (ms * scale), ms_sample_step=ms, steps_timed=len(times), cores=torch.get_num_threads(),
+                sample=f"{N_b} rows ({sample_subjects} subjects x T={T}) of the same workload per step, float64 oracle port; "
+                       f"scaled x{scale:.0f} in rows to the 16000-row step")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference_arm(max(args.steps, 2), max(args.warmup, 1))
+    line = dict(metric="ELBO train steps/sec (fwd+bwd)", value=r["value"], unit="steps/s", impl="reference",
+                n_gpus=args.gpus, steps=r["steps_timed"], warmup=max(args.warmup, 1),
+                ms_per_step=1e3 / r["value"], higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
+                data="synthetic", config=dict(workload=WORKLOAD, arm="oracle port of the reference CPU path "
+                                              "(the shipped reference needs gpytorch, absent on the box)"),
+                cpu_baseline=dict(value=r["value"], unit="steps/s", cores=r["cores"], kind="port", sample=r["sample"]),
+                e2e=dict(value=r["value"], unit="steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        return dict(sm_mhz=(pystat.median(sm) if sm else None), sm_max_mhz=(mx or None), reasons=sorted(reasons),
+                    samples=len(sm))
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def measure_fp64_peak(dev):
+    """FP64 GEMM throughput of this GPU (cuBLAS DGEMM 4096^3, best of 5): the denominator for the
+    FP64-tensor-pipe kernel.  MEASURED_PEAKS.json only has bf16 and HBM."""
+    n = 4096
+    a = torch.randn(n, n, dtype=torch.float64, device=dev)
+    b = torch.randn(n, n, dtype=torch.float64, device=dev)
+    torch.matmul(a, b)
+    best = 1e9
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+
+
+def build_gpu_state(dev, n_subj, rank, seed=0):
+    from hlvae_b200 import kernels, likelihoods, loglik, subjects, synth
+    rng = np.random.default_rng(seed + rank)
+    gen_cpu = torch.Generator().manual_seed(seed)               # replicated state: same on every rank
+    gen_dev = torch.Generator(device=dev).manual_seed(seed + rank)
+    x, lens = synth.covariates(n_subj, T, rng, first_id=rank * n_subj)
+    pool, _ = synth.covariates(400, T, np.random.default_rng(seed))
+    z = synth.inducing_points(pool, L, M, np.random.default_rng(seed)).to(dev).requires_grad_(True)
+    m, H = synth.variational_state(L, M, gen_cpu)
+    k0, k1 = kernels.generate_kernel_batched(L, **synth.DEFAULT_KERNEL_ARGS)
+    k0, k1 = k0.to(dev).double(), k1.to(dev).double()
+    lik = likelihoods.GaussianLikelihood(batch_shape=torch.Size([L]), noise_constraint=likelihoods.GreaterThan(1e-8))
+    lik.noise = 1
+    lik = lik.to(dev).double()
+    lik.raw_noise.requires_grad = False
+    lay = loglik.VarLayout(synth.HEALTHMNIST_D4_TYPES, dev)
+    N_b = x.shape[0]
+    data, mask = synth.device_likelihood_batch(lay, N_b, dev, gen_dev, dtype=torch.float32)
+    theta = torch.randn(N_b, lay.P_theta, device=dev, generator=gen_dev, dtype=torch.float32)
+    mu = torch.randn(N_b, L, device=dev, generator=gen_dev, dtype=torch.float32)
+    lv = -3.0 * torch.rand(N_b, L, device=dev, generator=gen_dev, dtype=torch.float32)
+    log_vy_real = torch.zeros(324, dtype=torch.float64, device=dev, requires_grad=True)
+    return dict(k0=k0, k1=k1, lik=lik, z=z, m=m.to(dev), H=H.to(dev), lay=lay, x=x.to(dev), data=data, mask=mask,
+                theta=theta.requires_grad_(True), mu=mu.requires_grad_(True), lv=lv.requires_grad_(True),
+                log_vy_real=log_vy_real, layout=subjects.SubjectLayout.from_lengths(lens, dev), n_subj=n_subj, N_b=N_b)
+
+
+def elbo_step(s, world, host=None):
+    """One ELBO-path step through the public (reference-shaped) functions.  With `host`, the step's
+    inputs first travel from pinned host memory and the loss is read back."""
+    from hlvae_b200 import elbo, loglik
+    if host is not None:
+        dev = s["x"].device
+        for k in ("data", "mask", "x"):
+            s[k] = host[k].to(dev, non_blocking=True)
+        for k in ("theta", "mu", "lv"):
+            s[k] = host[k].to(dev, non_blocking=True).requires_grad_(True)
+    for t_ in (s["theta"], s["mu"], s["lv"], s["z"], s["log_vy_real"], *s["k0"].parameters(), *s["k1"].parameters()):
+        t_.grad = None
+    P_b = s["n_subj"] * world
+    vparam = s["lay"].vparam(log_vy_real=s["log_vy_real"], conv=True)
+    out = loglik.fused_loglik(s["lay"], s["data"], s["mask"], s["theta"], vparam, monitor=True)
+    nll = -out["log_p_x"].sum(dtype=torch.float64) * (P_TOTAL / P_b)                        # training.py:83,104,122
+    kld, gm, gH = elbo.minibatch_KLD_upper_bound_iter(s["k0"], s["k1"], s["lik"], L, s["m"], s["H"], s["x"], s["mu"],
+                                                      s["lv"], s["z"], P_TOTAL, P_b, N_TOTAL, True, 2, EPS,
+                                                      layout=s["layout"])                     # training.py:110-113
+    loss = nll + kld                                                                           # :124
+    loss.backward()                                                                            # :127
+    s["m"], s["H"] = elbo.natural_gradient_update(s["m"], s["H"], gm, gH, NG_LR)               # :130-137
+    if host is not None:
+        return float(loss.item())
+    return loss
+
+
+ALGO = {}
+
+
+def algorithmic_work(n_rows, n_subj):
+    """Algorithmic work per launch (DESIGN.md section 'Kernels and rooflines')."""
+    E_x = P_th = 5184
+    D = 1296
+    sz = 4                                   # float32 storage of streamed arrays
+    ALGO["hlvae_loglik_fwd"] = ("hbm", n_rows * (sz * (E_x + P_th) + D + sz * (5 * D + P_th)))
+    ALGO["hlvae_loglik_bwd"] = ("hbm", n_rows * (sz * (E_x + P_th) + D + sz * D + sz * P_th))
+    # FP64 contraction flops: S = K^T V and W = V G (2 L N M^2 each) + B^-1 K and W V^T (2 L N T M each)
+    ALGO["hlvae_kl_panel"] = ("tensor", 2.0 * L * n_rows * M * M * 2 + 2.0 * L * n_rows * T * M * 2)
+    ALGO["hlvae_kl_subject"] = ("fp64", L * n_subj * (T ** 3 / 3 + T ** 3 / 3 + T ** 3 / 3 + 2 * 2.0 * T ** 3))
+
+
+def run_gpu(args):
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    import __graft_entry__ as g
+    if rank == 0:
+        g.build()
+    from hlvae_b200 import _lib, config, parallel
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        dist.barrier()
+        parallel.enable()
+    _lib.lib()
+    config.check_errors = False              # keep the timed step free of host syncs
+    s = build_gpu_state(dev, args.subjects, rank)
+    n_rows = s["N_b"]
+    algorithmic_work(n_rows, args.subjects)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        elbo_step(s, world)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    _lib.PROFILE = []
+    launches0 = _lib.LAUNCHES
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        elbo_step(s, world)
+    e1.record()
+    barrier()
+    sampler.stop_flag = True
+    total_ms = e0.elapsed_time(e1)
+    prof = _lib.PROFILE
+    _lib.PROFILE = None
+    launches = _lib.LAUNCHES - launches0
+    if world > 1:
+        tt = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        total_ms = float(tt.item())
+    ms_per_step = total_ms / args.steps
+    value = world * (n_rows / (SUBJ_PER_RANK * T)) * 1e3 / ms_per_step
+
+    # per-kernel device time inside the timed region
+    per = {}
+    for name, a, b in prof:
+        per.setdefault(name, []).append(a.elapsed_time(b))
+    kern = {k: dict(ms_avg=float(np.mean(v)), launches_per_step=len(v) / args.steps) for k, v in per.items()}
+    hbm_peak, peak_src = measured_peaks()
+    fp64_peak = measure_fp64_peak(dev)
+    for k, d in kern.items():
+        if k in ALGO:
+            bound, work = ALGO[k]
+            d["bound"] = bound
+            if bound == "hbm":
+                d["achieved"] = work / (d["ms_avg"] * 1e-3) / 1e9
+                d["peak"], d["unit"] = hbm_peak, "GB/s"
+            else:
+                d["achieved"] = work / (d["ms_avg"] * 1e-3) / 1e12
+                d["peak"], d["unit"] = fp64_peak, "TFLOP/s"
+            d["frac"] = d["achieved"] / d["peak"]
+        d["share_of_step"] = d["ms_avg"] * d["launches_per_step"] / ms_per_step
+    top = max((k for k in kern if k in ALGO and ALGO[k][0] in ("hbm", "tensor")), key=lambda k: kern[k]["share_of_step"])
+    roof = dict(kernel=top, bound=kern[top]["bound"], achieved=kern[top]["achieved"], peak=kern[top]["peak"],
+                unit=kern[top]["unit"], frac=kern[top]["frac"], traffic=None,
+                peak_source=(peak_src if kern[top]["bound"] == "hbm" else
+                             "FP64 DGEMM 4096^3 measured in this run (cuBLAS; MEASURED_PEAKS.json has no FP64 entry)"),
+                ms_avg=kern[top]["ms_avg"])
+
+    # end to end: host (pinned) inputs, H2D every step, loss read back
+    e2e = None
+    if not args.no_e2e:
+        host = {k: s[k].detach().cpu().pin_memory() for k in ("data", "mask", "x", "theta", "mu", "lv")}
+        h2d = sum(v.numel() * v.element_size() for v in host.values())
+        for _ in range(2):
+            elbo_step(s, world, host)
+        barrier()
+        t0 = time.perf_counter()
+        n_e2e = max(3, min(args.steps, 10))
+        for _ in range(n_e2e):
+            elbo_step(s, world, host)
+        barrier()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            tt = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+        e2e = dict(value=world * (n_rows / (SUBJ_PER_RANK * T)) * n_e2e / dt, unit="steps/s", h2d_bytes_per_step=h2d,
+                   d2h_bytes_per_step=8, steps=n_e2e)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference_arm(steps=8, warmup=1, budget_s=20.0)
+        cpu = dict(value=r["value"], unit="steps/s", cores=r["cores"], kind="port", sample=r["sample"])
+
+    if rank == 0:
+        line = dict(metric="ELBO train steps/sec (fwd+bwd)", value=value, unit="steps/s", n_gpus=world,
+                    steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms_per_step, higher_is_better=True,
+                    scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+                    config=dict(workload=WORKLOAD, rows_per_rank=n_rows, global_rows_per_step=n_rows * world,
+                                storage="f32 streamed arrays (data, theta, mu, log_v), f64 arithmetic and M x M stage",
+                                l2="inputs larger than L2 (data + theta = 664 MB per step)",
+                                parallelism=f"dp{world}: subjects sharded, one all-reduce of accumulators" if world > 1 else "single GPU"),
+                    clocks=sampler.summary(), e2e=e2e, gpu_launches=launches, roofline=roof, cpu_baseline=cpu,
+                    kernels=kern, fp64_peak_tflops=fp64_peak)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -72,6 +72,27 @@ def lib():
     return _lib
 
 
+# Optional per-call device timing: when PROFILE is a list, every C-ABI call is bracketed by CUDA
+# events on the launching stream (no sync); bench.py reads them after the timed region.
+PROFILE = None
+LAUNCHES = 0
+
+
+def call(name, *args):
+    """Invoke C-ABI entry point `name` (each one enqueues exactly one kernel) and check its result."""
+    global LAUNCHES
+    fn = getattr(lib(), name)
+    LAUNCHES += 1
+    if PROFILE is None:
+        return check(fn(*args), name)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    rc = fn(*args)
+    e1.record()
+    PROFILE.append((name, e0, e1))
+    return check(rc, name)
+
+
 def check(rc: int, what: str):
     if rc != 0:
         raise RuntimeError(f"hlvae_b200: {what} failed with code {rc}" +

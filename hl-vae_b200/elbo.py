@@ -83,20 +83,20 @@ class _KLD(torch.autograd.Function):
         os1c, ls1c = os1.detach().contiguous(), ls1.detach().contiguous()
         lib, st = _lib.lib(), _lib.stream_ptr()
         if layout.n_subj > 0:
-            _lib.check(lib.hlvae_kl_subject(fs0.cspec, _lib.ptr(os0c), _lib.ptr(ls0c), fs1.cspec, _lib.ptr(os1c),
+            _lib.call("hlvae_kl_subject", fs0.cspec, _lib.ptr(os0c), _lib.ptr(ls0c), fs1.cspec, _lib.ptr(os1c),
                                             _lib.ptr(ls1c), _lib.ptr(noise), L, Q, _lib.ptr(x_c), Q,
                                             _lib.ptr(layout.row_idx), _lib.ptr(layout.subj_ptr),
                                             _lib.ptr(layout.tt_ptr), layout.n_subj, max(layout.t_max, 1),
                                             _lib.ptr(lv_c), L, dcode, _lib.ptr(binv), binv.shape[1], _lib.ptr(acc), M,
-                                            _lib.ptr(g_lv), _lib.ptr(status), st), "hlvae_kl_subject")
+                                            _lib.ptr(g_lv), _lib.ptr(status), st)
             n_chunks = max(1, min((N_SM * 8 + L - 1) // L, (layout.n_subj + 2) // 3))
             spc = (layout.n_subj + n_chunks - 1) // n_chunks
-            _lib.check(lib.hlvae_kl_panel(fs0.cspec, _lib.ptr(os0c), _lib.ptr(ls0c), fs1.cspec, _lib.ptr(os1c),
+            _lib.call("hlvae_kl_panel", fs0.cspec, _lib.ptr(os0c), _lib.ptr(ls0c), fs1.cspec, _lib.ptr(os1c),
                                           _lib.ptr(ls1c), L, Q, M, _lib.ptr(x_c), Q, _lib.ptr(zl.detach()),
                                           _lib.ptr(layout.row_idx), _lib.ptr(layout.subj_ptr),
                                           _lib.ptr(layout.tt_ptr), layout.n_subj, spc, _lib.ptr(mu_c), L, dcode,
                                           _lib.ptr(wd), _lib.ptr(Gs), _lib.ptr(binv), binv.shape[1], _lib.ptr(acc),
-                                          _lib.ptr(g_mu), _lib.ptr(status), st), "hlvae_kl_panel")
+                                          _lib.ptr(g_mu), _lib.ptr(status), st)
         # ---- 3. data parallel: one all-reduce of every accumulator (S, p, scalars, replicated-parameter grads)
         if config.process_group is not None:
             torch.distributed.all_reduce(acc, group=config.process_group)

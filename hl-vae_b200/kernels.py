@@ -258,12 +258,13 @@ class _KernelEval(torch.autograd.Function):
         os_c, ls_c = os_.detach().contiguous(), ls_.detach().contiguous()
         bs1 = n1 * Q if x1c.dim() == 3 else 0
         bs2 = n2 * Q if x2c.dim() == 3 else 0
-        _lib.check(_lib.lib().hlvae_kernel_eval_fwd(fs.cspec, _lib.ptr(os_c), _lib.ptr(ls_c), L, Q, _lib.ptr(x1c), n1,
-                                                    Q, bs1, _lib.ptr(x2c), n2, Q, bs2, _lib.ptr(out),
-                                                    _lib.stream_ptr()), "hlvae_kernel_eval_fwd")
         ctx.fs = fs
         ctx.save_for_backward(os_c, ls_c, x1c, x2c)
-        ctx.same = x1 is x2
+        if n1 == 0 or n2 == 0:
+            return out
+        _lib.call("hlvae_kernel_eval_fwd", fs.cspec, _lib.ptr(os_c), _lib.ptr(ls_c), L, Q, _lib.ptr(x1c), n1,
+                                                    Q, bs1, _lib.ptr(x2c), n2, Q, bs2, _lib.ptr(out),
+                                                    _lib.stream_ptr())
         return out
 
     @staticmethod
@@ -280,10 +281,11 @@ class _KernelEval(torch.autograd.Function):
         g_x2 = torch.zeros(L, n2, Q, dtype=torch.float64, device=g.device) if need2 else None
         bs1 = n1 * Q if x1c.dim() == 3 else 0
         bs2 = n2 * Q if x2c.dim() == 3 else 0
-        _lib.check(_lib.lib().hlvae_kernel_eval_bwd(fs.cspec, _lib.ptr(os_c), _lib.ptr(ls_c), L, Q, _lib.ptr(x1c), n1,
-                                                    Q, bs1, _lib.ptr(x2c), n2, Q, bs2, _lib.ptr(g), _lib.ptr(g_os),
-                                                    _lib.ptr(g_ls), _lib.ptr(g_x1), _lib.ptr(g_x2),
-                                                    _lib.stream_ptr()), "hlvae_kernel_eval_bwd")
+        if n1 > 0 and n2 > 0:
+            _lib.call("hlvae_kernel_eval_bwd", fs.cspec, _lib.ptr(os_c), _lib.ptr(ls_c), L, Q, _lib.ptr(x1c),
+                                                        n1, Q, bs1, _lib.ptr(x2c), n2, Q, bs2, _lib.ptr(g),
+                                                        _lib.ptr(g_os), _lib.ptr(g_ls), _lib.ptr(g_x1),
+                                                        _lib.ptr(g_x2), _lib.stream_ptr())
         if g_x1 is not None and x1c.dim() == 2:
             g_x1 = g_x1.sum(0)
         if g_x2 is not None and x2c.dim() == 2:

@@ -115,12 +115,13 @@ class _FusedLoglik(torch.autograd.Function):
         rmean = new(N, D) if monitor else None
         rmode = new(N, D) if monitor else None
         dtr = new(N, D) if monitor else None
-        _lib.check(_lib.lib().hlvae_loglik_fwd(N, D, layout.E_x, layout.P_theta, _lib.ptr(layout.var_kind),
+        if N > 0:
+          _lib.call("hlvae_loglik_fwd", N, D, layout.E_x, layout.P_theta, _lib.ptr(layout.var_kind),
                                                _lib.ptr(layout.var_nclass), _lib.ptr(layout.var_dcol),
                                                _lib.ptr(layout.var_pcol), _lib.ptr(vp), _lib.ptr(da), _lib.ptr(th),
                                                _lib.ptr(mk), dcode, int(mask_u8), _lib.ptr(lpx), _lib.ptr(lpm),
                                                _lib.ptr(prm), _lib.ptr(rmean), _lib.ptr(rmode), _lib.ptr(dtr), None,
-                                               _lib.stream_ptr()), "hlvae_loglik_fwd")
+                                               _lib.stream_ptr())
         ctx.layout, ctx.mask_u8, ctx.dcode = layout, mask_u8, dcode
         ctx.save_for_backward(th, vp, da, mk)
         outs = (lpx, lpm, prm) + ((rmean, rmode, dtr) if monitor else ())
@@ -135,12 +136,12 @@ class _FusedLoglik(torch.autograd.Function):
         g = g_lpx.to(th.dtype).contiguous()
         g_theta = torch.empty_like(th)
         g_lvy = torch.zeros(D, dtype=torch.float64, device=th.device)
-        _lib.check(_lib.lib().hlvae_loglik_bwd(N, D, layout.E_x, layout.P_theta, _lib.ptr(layout.var_kind),
+        if N > 0:
+          _lib.call("hlvae_loglik_bwd", N, D, layout.E_x, layout.P_theta, _lib.ptr(layout.var_kind),
                                                _lib.ptr(layout.var_nclass), _lib.ptr(layout.var_dcol),
                                                _lib.ptr(layout.var_pcol), _lib.ptr(vp), _lib.ptr(da), _lib.ptr(th),
                                                _lib.ptr(mk), ctx.dcode, int(ctx.mask_u8), _lib.ptr(g), 0.0,
-                                               _lib.ptr(g_theta), _lib.ptr(g_lvy), _lib.stream_ptr()),
-                   "hlvae_loglik_bwd")
+                                               _lib.ptr(g_theta), _lib.ptr(g_lvy), _lib.stream_ptr())
         g_vp = torch.zeros_like(vp)
         g_vp[2] = g_lvy
         return g_theta, g_vp, None, None, None, None
@@ -298,10 +299,10 @@ def statistics(layout, params, vparam):
     mean, mode = torch.empty(N, layout.D, dtype=prm.dtype, device=prm.device), \
         torch.empty(N, layout.D, dtype=prm.dtype, device=prm.device)
     vp = vparam.detach().to(torch.float64).contiguous()
-    _lib.check(_lib.lib().hlvae_statistics(N, layout.D, layout.P_theta, _lib.ptr(layout.var_kind),
+    _lib.call("hlvae_statistics", N, layout.D, layout.P_theta, _lib.ptr(layout.var_kind),
                                            _lib.ptr(layout.var_nclass), _lib.ptr(layout.var_pcol), _lib.ptr(vp),
                                            _lib.ptr(prm), _lib.dtype_code(prm), _lib.ptr(mean), _lib.ptr(mode),
-                                           _lib.stream_ptr()), "hlvae_statistics")
+                                           _lib.stream_ptr())
     return mean, mode
 
 
@@ -310,8 +311,8 @@ def discrete_variables_transformation(layout, data):
     N = data.shape[0]
     da = data.detach().contiguous()
     out = torch.empty(N, layout.D, dtype=da.dtype, device=da.device)
-    _lib.check(_lib.lib().hlvae_discrete_transform(N, layout.D, layout.E_x, _lib.ptr(layout.var_kind),
+    _lib.call("hlvae_discrete_transform", N, layout.D, layout.E_x, _lib.ptr(layout.var_kind),
                                                    _lib.ptr(layout.var_nclass), _lib.ptr(layout.var_dcol),
                                                    _lib.ptr(da), _lib.dtype_code(da), _lib.ptr(out),
-                                                   _lib.stream_ptr()), "hlvae_discrete_transform")
+                                                   _lib.stream_ptr())
     return out

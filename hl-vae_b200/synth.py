@@ -100,3 +100,42 @@ def likelihood_batch(types, N, rng, observed=0.7, pixel_like=False):
     data = np.concatenate(cols, 1)
     mask = (rng.random((N, len(types))) < observed).astype(np.float64)
     return torch.from_numpy(data), torch.from_numpy(mask)
+
+
+def device_likelihood_batch(layout, N, device, gen, dtype=torch.float32, observed=0.75, pixel_like=True):
+    """Same encodings as likelihood_batch, generated directly on `device` for large N (bench sizes).
+    `layout` is a hlvae_b200.loglik.VarLayout; returns (data [N,E_x] dtype, mask [N,D] uint8)."""
+    D = layout.D
+    data = torch.zeros(N, layout.E_x, dtype=dtype, device=device)
+    kinds = layout.var_kind.tolist()
+    ncls = layout.var_nclass.to(device)
+    dcol = layout.var_dcol.to(device).long()
+    u = torch.rand(N, D, device=device, generator=gen)
+    cls = (u * ncls[None, :]).floor().long().clamp_(min=0)
+    cls = torch.minimum(cls, (ncls[None, :] - 1).long())
+    kind_t = torch.tensor(kinds, device=device)
+    for name, code in (("cat", 3), ("ordinal", 4)):
+        idx = torch.nonzero(kind_t == code).squeeze(1)
+        if idx.numel() == 0:
+            continue
+        if name == "cat":
+            data.scatter_(1, dcol[idx][None, :] + cls[:, idx], 1.0)
+        else:
+            cmax = int(ncls[idx].max())
+            for c in range(cmax):
+                sel = idx[ncls[idx] > c]
+                data[:, dcol[sel] + c] = (cls[:, sel] >= c).to(dtype)
+    idx = torch.nonzero(kind_t == 0).squeeze(1)
+    if idx.numel():
+        v = (torch.rand(N, idx.numel(), device=device, generator=gen) * 256).floor() if pixel_like else \
+            torch.randn(N, idx.numel(), device=device, generator=gen)
+        data[:, dcol[idx]] = v.to(dtype)
+    idx = torch.nonzero(kind_t == 1).squeeze(1)
+    if idx.numel():
+        data[:, dcol[idx]] = torch.exp(torch.randn(N, idx.numel(), device=device, generator=gen)).to(dtype)
+    idx = torch.nonzero(kind_t == 2).squeeze(1)
+    if idx.numel():
+        lam = torch.full((N, idx.numel()), 3.0, device=device)
+        data[:, dcol[idx]] = (torch.poisson(lam, generator=gen) + 1).to(dtype)
+    mask = (torch.rand(N, D, device=device, generator=gen) < observed).to(torch.uint8)
+    return data, mask
