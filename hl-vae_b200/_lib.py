@@ -42,9 +42,13 @@ _SIGS = {
     "hlvae_kernel_eval_bwd": ([C.POINTER(KSpec), _P, _P, _I, _I, _P, _I, _L, _L, _P, _I, _L, _L, _P, _P, _P, _P, _P, _P], _I),
     "hlvae_kl_acc_layout": ([_I, _I, _I, C.POINTER(_L)], _I),
     "hlvae_kl_subject": ([C.POINTER(KSpec), _P, _P, C.POINTER(KSpec), _P, _P, _P, _I, _I, _P, _L, _P, _P, _P, _I, _I,
-                          _P, _L, _I, _P, _L, _P, _I, _P, _P, _P], _I),
+                          _P, _L, _I, _P, _L, _P, _I, _P, _D, _P, _P], _I),
     "hlvae_kl_panel": ([C.POINTER(KSpec), _P, _P, C.POINTER(KSpec), _P, _P, _I, _I, _I, _P, _L, _P, _P, _P, _P, _I, _I,
-                        _P, _L, _I, _P, _P, _P, _L, _P, _P, _P, _P], _I),
+                        _P, _L, _I, _P, _P, _P, _L, _P, _P, _D, _P, _P], _I),
+    "hlvae_mxm_workspace_doubles": ([_I, _I], _L),
+    "hlvae_mxm_pre": ([C.POINTER(KSpec), _P, _P, _I, _I, _I, _P, _D, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P], _I),
+    "hlvae_mxm_post": ([_I, _I, _D, _D, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P], _I),
+    "hlvae_natgrad_update": ([_I, _I, _D, _P, _P, _P, _P, _P, _P, _P, _P, _P], _I),
     "hlvae_loglik_fwd": ([_L, _I, _L, _L, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P], _I),
     "hlvae_loglik_bwd": ([_L, _I, _L, _L, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _D, _P, _P, _P], _I),
     "hlvae_statistics": ([_L, _I, _L, _P, _P, _P, _P, _P, _I, _P, _P, _P], _I),
@@ -76,6 +80,11 @@ def lib():
 # events on the launching stream (no sync); bench.py reads them after the timed region.
 PROFILE = None
 LAUNCHES = 0
+
+
+def workspace(L, M, device):
+    n = int(lib().hlvae_mxm_workspace_doubles(L, M))
+    return torch.empty(n, dtype=torch.float64, device=device) if n else None
 
 
 def call(name, *args):

@@ -33,7 +33,7 @@ kl_subject_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict
              const int32_t* __restrict__ row_idx, const int32_t* __restrict__ subj_ptr,
              const int32_t* __restrict__ tt_ptr, int n_subj, int tcap, const TS* __restrict__ log_v, int64_t ld_lv,
              double* __restrict__ binv, int64_t tt_total, double* __restrict__ acc, const AccOff off,
-             double* __restrict__ g_logv, int32_t* __restrict__ status) {
+             TS* __restrict__ g_logv, double gscale, int32_t* __restrict__ status) {
     extern __shared__ double smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ldt = tcap | 1;
@@ -134,7 +134,7 @@ kl_subject_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict
         bout[e] = bij;
         accum_grads<false>(sp0, kp0, xs + i * Q, xs + j * Q, 0.5 * bij, gos0, gls0, dummy);
     }
-    if (lane < T) g_logv[(int64_t)g * L + l] = 0.5 * (Bw[lane * ldt + lane] * ev - 1.0);
+    if (lane < T) g_logv[(int64_t)g * L + l] = (TS)(gscale * 0.5 * (Bw[lane * ldt + lane] * ev - 1.0));
     // X = Ktil B^-1 -> Bi
     for (int e = lane; e < T * T; e += 32) {
         int i = e / T, j = e % T;
@@ -205,7 +205,7 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
            const int32_t* __restrict__ tt_ptr, int n_subj, int subj_per_chunk, const TS* __restrict__ mu,
            int64_t ld_mu, const double* __restrict__ w, const double* __restrict__ G,
            const double* __restrict__ binv, int64_t tt_total, double* __restrict__ acc, const AccOff off,
-           double* __restrict__ g_mu, int32_t* __restrict__ status) {
+           TS* __restrict__ g_mu, double gscale, int32_t* __restrict__ status) {
     using SM = PanelSmem<MP, RP, G_SMEM>;
     constexpr int LD = SM::LD;
     constexpr int SI = MP / 32;   // S tiles (8x8) per warp per dim; 16 warps as 4 x 4
@@ -350,7 +350,7 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
             for (int t = 0; t < T; t++) a = fma(brow[t], rv[rs + t], a);
             rho[tid] = a;
             a_acc = fma(rv[tid], a, a_acc);
-            g_mu[(int64_t)grow[tid] * L + l] = -a;
+            g_mu[(int64_t)grow[tid] * L + l] = (TS)(-a * gscale);
         }
         __syncthreads();
 
@@ -535,8 +535,8 @@ int launch_panel(const hlvae_kspec_t* spec0, const double* os0, const double* ls
                  const double* os1, const double* ls1, int L, int Q, int M, const double* x, int64_t ldx,
                  const double* z, const int32_t* row_idx, const int32_t* subj_ptr, const int32_t* tt_ptr, int n_subj,
                  int subj_per_chunk, const void* mu, int64_t ld_mu, const double* w, const double* G,
-                 const double* binv, int64_t tt_total, double* acc, const AccOff& off, double* g_mu, int32_t* status,
-                 cudaStream_t st) {
+                 const double* binv, int64_t tt_total, double* acc, const AccOff& off, void* g_mu, double gscale,
+                 int32_t* status, cudaStream_t st) {
     using SM = PanelSmem<MP, RP, G_SMEM>;
     auto kern = kl_panel_k<MP, RP, G_SMEM, TS>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::bytes);
@@ -545,7 +545,7 @@ int launch_panel(const hlvae_kspec_t* spec0, const double* os0, const double* ls
     dim3 grid(n_chunks, L);
     kern<<<grid, PN_THREADS, SM::bytes, st>>>(*spec0, os0, ls0, *spec1, os1, ls1, L, Q, M, x, ldx, z, row_idx,
                                               subj_ptr, tt_ptr, n_subj, subj_per_chunk, (const TS*)mu, ld_mu, w, G,
-                                              binv, tt_total, acc, off, g_mu, status);
+                                              binv, tt_total, acc, off, (TS*)g_mu, gscale, status);
     HLVAE_CHECK_LAUNCH();
     return 0;
 }
@@ -556,11 +556,11 @@ int dispatch_panel(int M, const hlvae_kspec_t* spec0, const double* os0, const d
                    int64_t ldx, const double* z, const int32_t* row_idx, const int32_t* subj_ptr,
                    const int32_t* tt_ptr, int n_subj, int subj_per_chunk, const void* mu, int64_t ld_mu,
                    const double* w, const double* G, const double* binv, int64_t tt_total, double* acc,
-                   const AccOff& off, double* g_mu, int32_t* status, cudaStream_t st) {
+                   const AccOff& off, void* g_mu, double gscale, int32_t* status, cudaStream_t st) {
 #define HLVAE_PANEL(MP, RP, GS)                                                                                       \
     return launch_panel<MP, RP, GS, TS>(spec0, os0, ls0, spec1, os1, ls1, L, Q, M, x, ldx, z, row_idx, subj_ptr,     \
                                         tt_ptr, n_subj, subj_per_chunk, mu, ld_mu, w, G, binv, tt_total, acc, off,   \
-                                        g_mu, status, st)
+                                        g_mu, gscale, status, st)
     if (M <= 32) { HLVAE_PANEL(32, 64, true); }
     if (M <= 64) { HLVAE_PANEL(64, 64, true); }
     if (M <= 128) { HLVAE_PANEL(128, 32, false); }
@@ -595,7 +595,7 @@ extern "C" int hlvae_kl_subject(const hlvae_kspec_t* spec0, const double* os0, c
                                 int L, int Q, const double* x, int64_t ldx, const int32_t* row_idx,
                                 const int32_t* subj_ptr, const int32_t* tt_ptr, int n_subj, int t_cap,
                                 const void* log_v, int64_t ld_lv, int dtype, double* binv, int64_t tt_total,
-                                double* acc, int M, double* g_logv, int32_t* status, void* stream) {
+                                double* acc, int M, void* g_logv, double gscale, int32_t* status, void* stream) {
     if (!hlvae::spec_valid(spec0, Q) || !hlvae::spec_valid(spec1, Q) || L <= 0 || Q <= 0 || Q > HLVAE_MAX_Q ||
         M <= 0 || n_subj < 0 || t_cap <= 0 || t_cap > HLVAE_TMAX || !x || !row_idx || !subj_ptr || !tt_ptr || !log_v ||
         !binv || !acc || !g_logv || !noise)
@@ -616,14 +616,14 @@ extern "C" int hlvae_kl_subject(const hlvae_kspec_t* spec0, const double* os0, c
         if (e != cudaSuccess) return (int)e;
         kern<<<grid, SJ_WARPS * 32, smem, st>>>(*spec0, os0, ls0, *spec1, os1, ls1, noise, L, Q, x, ldx, row_idx,
                                                 subj_ptr, tt_ptr, n_subj, t_cap, (const double*)log_v, ld_lv, binv,
-                                                tt_total, acc, off, g_logv, status);
+                                                tt_total, acc, off, (double*)g_logv, gscale, status);
     } else {
         auto kern = kl_subject_k<float>;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         kern<<<grid, SJ_WARPS * 32, smem, st>>>(*spec0, os0, ls0, *spec1, os1, ls1, noise, L, Q, x, ldx, row_idx,
                                                 subj_ptr, tt_ptr, n_subj, t_cap, (const float*)log_v, ld_lv, binv,
-                                                tt_total, acc, off, g_logv, status);
+                                                tt_total, acc, off, (float*)g_logv, gscale, status);
     }
     HLVAE_CHECK_LAUNCH();
     return 0;
@@ -634,8 +634,8 @@ extern "C" int hlvae_kl_panel(const hlvae_kspec_t* spec0, const double* os0, con
                               const double* x, int64_t ldx, const double* z, const int32_t* row_idx,
                               const int32_t* subj_ptr, const int32_t* tt_ptr, int n_subj, int subj_per_chunk,
                               const void* mu, int64_t ld_mu, int dtype, const double* w, const double* G,
-                              const double* binv, int64_t tt_total, double* acc, double* g_mu, int32_t* status,
-                              void* stream) {
+                              const double* binv, int64_t tt_total, double* acc, void* g_mu, double gscale,
+                              int32_t* status, void* stream) {
     if (!hlvae::spec_valid(spec0, Q) || !hlvae::spec_valid(spec1, Q) || L <= 0 || Q <= 0 || Q > HLVAE_MAX_Q ||
         M <= 0 || n_subj < 0 || subj_per_chunk <= 0 || !x || !z || !row_idx || !subj_ptr || !tt_ptr || !mu || !w ||
         !G || !binv || !acc || !g_mu)
@@ -647,11 +647,11 @@ extern "C" int hlvae_kl_panel(const hlvae_kspec_t* spec0, const double* os0, con
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == HLVAE_F64)
         return dispatch_panel<double>(M, spec0, os0, ls0, spec1, os1, ls1, L, Q, x, ldx, z, row_idx, subj_ptr, tt_ptr,
-                                      n_subj, subj_per_chunk, mu, ld_mu, w, G, binv, tt_total, acc, off, g_mu, status,
-                                      st);
+                                      n_subj, subj_per_chunk, mu, ld_mu, w, G, binv, tt_total, acc, off, g_mu, gscale,
+                                      status, st);
     if (dtype == HLVAE_F32)
         return dispatch_panel<float>(M, spec0, os0, ls0, spec1, os1, ls1, L, Q, x, ldx, z, row_idx, subj_ptr, tt_ptr,
-                                     n_subj, subj_per_chunk, mu, ld_mu, w, G, binv, tt_total, acc, off, g_mu, status,
-                                     st);
+                                     n_subj, subj_per_chunk, mu, ld_mu, w, G, binv, tt_total, acc, off, g_mu, gscale,
+                                     status, st);
     return HLVAE_E_ARG;
 }

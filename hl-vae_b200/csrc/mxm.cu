@@ -1,0 +1,434 @@
+// Replicated M x M stage of the KL upper bound, float64, one CTA per latent dimension:
+//   hlvae_mxm_pre   : K0zz + eps I, Cholesky, explicit inverses iK, iH, w = iK m, G = iK H iK - iK
+//                     (elbo_functions.py:148,153-157,162-163,171 / :223-231)
+//   hlvae_mxm_post  : D, E, kld_qu_pu, kld_total (:170-181 / :259-277), the natural-gradient pieces
+//                     (:186-191 / :279-283) and d kld / d{K0zz, m, H} in closed form
+//   hlvae_natgrad_update : training.py:130-137
+// Small dense algebra is done CTA-wide on matrices held in shared memory (M <= 64) or in a
+// caller-provided global workspace (64 < M <= 128; L2 resident).
+#include "common.cuh"
+
+using namespace hlvae;
+
+namespace hlvae {
+bool spec_valid(const hlvae_kspec_t* sp, int Q);
+}
+
+namespace {
+
+constexpr int MX_THREADS = 256;
+constexpr int MX_NBUF = 5;
+
+struct Mat {
+    double* p;
+    int ld;
+    __device__ __forceinline__ double& operator()(int i, int j) const { return p[i * ld + j]; }
+};
+
+// C = X Y (TRANSX = false) or X^T Y (TRANSX = true); all M x M.  C must not alias X or Y.
+template <bool TRANSX>
+__device__ void mm(Mat C, Mat X, Mat Y, int M) {
+    const int n = M * M;
+    for (int e0 = threadIdx.x; e0 < n; e0 += 4 * MX_THREADS) {
+        int e[4], i[4], j[4];
+        double a[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            e[u] = e0 + u * MX_THREADS;
+            int ee = e[u] < n ? e[u] : 0;
+            i[u] = ee / M;
+            j[u] = ee % M;
+            a[u] = 0.0;
+        }
+        for (int k = 0; k < M; k++) {
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                double x = TRANSX ? X(k, i[u]) : X(i[u], k);
+                a[u] = fma(x, Y(k, j[u]), a[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            if (e[u] < n) C(i[u], j[u]) = a[u];
+    }
+    __syncthreads();
+}
+
+// In-place lower Cholesky of A (column by column, thread i owns row i).  Returns false when a
+// pivot is not positive.  logdet = 2 sum log L_jj.  `tmp` holds M doubles in shared memory.
+__device__ bool chol(Mat A, int M, double* tmp, double& logdet) {
+    const int i = threadIdx.x;
+    double ld = 0.0;
+    for (int j = 0; j < M; j++) {
+        if (i >= j && i < M) {
+            double s0 = A(i, j), s1 = 0.0;
+            int k = 0;
+            for (; k + 1 < j; k += 2) {
+                s0 = fma(-A(i, k), A(j, k), s0);
+                s1 = fma(-A(i, k + 1), A(j, k + 1), s1);
+            }
+            if (k < j) s0 = fma(-A(i, k), A(j, k), s0);
+            tmp[i] = s0 + s1;
+        }
+        __syncthreads();
+        const double djj = tmp[j];
+        if (!(djj > 0.0)) return false;       // uniform: every thread reads the same value
+        const double d = sqrt(djj);
+        ld += 2.0 * log(d);
+        if (i >= j && i < M) A(i, j) = (i == j) ? d : tmp[i] / d;
+        __syncthreads();
+    }
+    logdet = ld;
+    return true;
+}
+
+// B = L^-1 for lower-triangular L (thread c solves L y = e_c).  B must not alias L.
+__device__ void tri_inv(Mat B, Mat Lm, int M) {
+    const int c = threadIdx.x;
+    if (c < M) {
+        for (int i = 0; i < c; i++) B(i, c) = 0.0;
+        B(c, c) = 1.0 / Lm(c, c);
+        for (int i = c + 1; i < M; i++) {
+            double s0 = 0.0, s1 = 0.0;
+            int k = c;
+            for (; k + 1 < i; k += 2) {
+                s0 = fma(Lm(i, k), B(k, c), s0);
+                s1 = fma(Lm(i, k + 1), B(k + 1, c), s1);
+            }
+            if (k < i) s0 = fma(Lm(i, k), B(k, c), s0);
+            B(i, c) = -(s0 + s1) / Lm(i, i);
+        }
+    }
+    __syncthreads();
+}
+
+// C = B^T B for lower-triangular B (so the sum starts at max(i, j)); optional copy to global.
+__device__ void ata_lower(Mat C, Mat B, int M, double* __restrict__ gout) {
+    for (int e = threadIdx.x; e < M * M; e += MX_THREADS) {
+        int i = e / M, j = e % M;
+        double a = 0.0;
+        for (int k = max(i, j); k < M; k++) a = fma(B(k, i), B(k, j), a);
+        C(i, j) = a;
+        if (gout) gout[e] = a;
+    }
+    __syncthreads();
+}
+
+__device__ void load(Mat A, const double* __restrict__ g, int M) {
+    for (int e = threadIdx.x; e < M * M; e += MX_THREADS) A(e / M, e % M) = g[e];
+    __syncthreads();
+}
+
+__device__ double block_sum(double v, double* red) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double s = 0.0;
+    for (int w = 0; w < MX_THREADS / 32; w++) s += red[w];
+    __syncthreads();
+    return s;
+}
+
+// Buffers: M <= 64 -> all MX_NBUF in shared memory; otherwise buffer 0 in shared memory and the
+// rest in the global workspace ws[l][MX_NBUF-1][M][M].
+struct Bufs {
+    Mat b[MX_NBUF];
+    double* vec;   // 4 * M + 16 doubles of shared scratch
+};
+
+__device__ Bufs carve(double* smem, int M, double* ws, int l) {
+    Bufs B;
+    const int ld = M + 1;
+    const bool all_smem = (M <= 64);
+    B.b[0] = Mat{smem, ld};
+    double* p = smem + (size_t)M * ld;
+    for (int u = 1; u < MX_NBUF; u++) {
+        if (all_smem) {
+            B.b[u] = Mat{p, ld};
+            p += (size_t)M * ld;
+        } else {
+            B.b[u] = Mat{ws + ((size_t)l * (MX_NBUF - 1) + (u - 1)) * M * M, M};
+        }
+    }
+    B.vec = p;
+    return B;
+}
+
+size_t mx_smem_bytes(int M) {
+    size_t mats = (M <= 64) ? MX_NBUF : 1;
+    return (mats * (size_t)M * (M + 1) + 4 * (size_t)M + 16) * sizeof(double);
+}
+
+// =====================================================================================
+__global__ void __launch_bounds__(MX_THREADS)
+mxm_pre_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__ os0, const double* __restrict__ ls0,
+          int L, int Q, int M, const double* __restrict__ z, double eps, const double* __restrict__ m,
+          const double* __restrict__ H, double* __restrict__ iK, double* __restrict__ iH, double* __restrict__ w,
+          double* __restrict__ G, double* __restrict__ pre, double* __restrict__ ws, int32_t* __restrict__ status) {
+    extern __shared__ double smem[];
+    const int l = blockIdx.x, tid = threadIdx.x;
+    Bufs B = carve(smem, M, ws, l);
+    double* tmp = B.vec;            // [M]
+    double* mv = B.vec + M;         // [M] m
+    double* wv = B.vec + 2 * M;     // [M] w
+    double* red = B.vec + 4 * M;    // [8]
+    const size_t mm_off = (size_t)l * M * M;
+    KParams kp;
+    load_kparams(kp, sp0, os0, ls0, L, l);
+    const double* zl = z + (size_t)l * M * Q;
+    Mat A = B.b[0], P1 = B.b[1], P2 = B.b[2];
+    // K0zz + eps I (elbo_functions.py:148,153 / :223-224)
+    for (int e = tid; e < M * M; e += MX_THREADS) {
+        int i = e / M, j = e % M;
+        A(i, j) = eval_additive(sp0, kp, zl + i * Q, zl + j * Q) + (i == j ? eps : 0.0);
+    }
+    for (int i = tid; i < M; i += MX_THREADS) mv[i] = m[(size_t)l * M + i];
+    __syncthreads();
+    double logdetK = 0.0, logdetH = 0.0;
+    if (!chol(A, M, tmp, logdetK)) {                                   // :154 / :225
+        if (tid == 0) report_status(status, HLVAE_STATUS_NOT_PD, l, -1);
+        return;
+    }
+    tri_inv(P1, A, M);
+    ata_lower(A, P1, M, iK + mm_off);                                  // iK (:155 / :226), kept in A
+    // w = iK m, qf1 = m^T iK m (:177 / :272)
+    for (int i = tid; i < M; i += MX_THREADS) {
+        double a = 0.0;
+        for (int k = 0; k < M; k++) a = fma(A(i, k), mv[k], a);
+        wv[i] = a;
+        w[(size_t)l * M + i] = a;
+    }
+    __syncthreads();
+    double qf = 0.0;
+    for (int i = tid; i < M; i += MX_THREADS) qf += mv[i] * wv[i];
+    qf = block_sum(qf, red);
+    // P2 = H iK ; tr1 = trace(H iK) (:176 / :271)
+    load(P1, H + mm_off, M);
+    mm<false>(P2, P1, A, M);
+    double tr1 = 0.0;
+    for (int i = tid; i < M; i += MX_THREADS) tr1 += P2(i, i);
+    tr1 = block_sum(tr1, red);
+    // G = sym(iK H iK) - iK   (:171 / :231 minus the iK of :170)
+    mm<false>(P1, A, P2, M);
+    for (int e = tid; e < M * M; e += MX_THREADS) {
+        int i = e / M, j = e % M;
+        G[mm_off + e] = 0.5 * (P1(i, j) + P1(j, i)) - A(i, j);
+    }
+    __syncthreads();
+    // iH (:162-163 / :227-228)
+    load(A, H + mm_off, M);
+    if (!chol(A, M, tmp, logdetH)) {
+        if (tid == 0) report_status(status, HLVAE_STATUS_NOT_PD, l, -2);
+        return;
+    }
+    tri_inv(P1, A, M);
+    ata_lower(A, P1, M, iH + mm_off);
+    if (tid == 0) {
+        pre[l * 4 + 0] = logdetK;
+        pre[l * 4 + 1] = logdetH;
+        pre[l * 4 + 2] = tr1;
+        pre[l * 4 + 3] = qf;
+    }
+}
+
+// =====================================================================================
+// f = c0 (1/2 tr(G S) + w^T gw) + kld_qu_pu with G = iK H iK - iK, w = iK m:
+//   Gamma = df/d(iK) = c0/2 (Ss iK H + H iK Ss - Ss) + c0/2 (gw m^T + m gw^T) + 1/2 (H + m m^T)
+//   df/dK = -iK Gamma iK + 1/2 iK          df/dH = c0/2 iK Ss iK + 1/2 iK - 1/2 iH
+//   df/dm = c0 iK gw + iK m
+__global__ void __launch_bounds__(MX_THREADS)
+mxm_post_k(int L, int M, double c0, double constant, const double* __restrict__ iK, const double* __restrict__ iH,
+           const double* __restrict__ H, const double* __restrict__ m, const double* __restrict__ w,
+           const double* __restrict__ G, const double* __restrict__ pre, const double* __restrict__ S,
+           const double* __restrict__ p, const double* __restrict__ gw, const double* __restrict__ scal,
+           double* __restrict__ kld, double* __restrict__ gK_over_c0, double* __restrict__ gH, double* __restrict__ gm,
+           double* __restrict__ ng_m, double* __restrict__ ng_H, double* __restrict__ ws) {
+    extern __shared__ double smem[];
+    const int l = blockIdx.x, tid = threadIdx.x;
+    Bufs B = carve(smem, M, ws, l);
+    double* mv = B.vec;             // m
+    double* gv = B.vec + M;         // gw
+    double* pv = B.vec + 2 * M;     // p
+    double* wv = B.vec + 3 * M;     // w
+    double* red = B.vec + 4 * M;
+    const size_t mm_off = (size_t)l * M * M;
+    Mat Q0 = B.b[0], Q1 = B.b[1], Q2 = B.b[2], Q3 = B.b[3], Q4 = B.b[4];
+    double js = 0.0;
+    for (int e = tid; e < M * M; e += MX_THREADS) {
+        int i = e / M, j = e % M;
+        double ss = 0.5 * (S[mm_off + e] + S[mm_off + (size_t)j * M + i]);
+        Q0(i, j) = ss;                                                 // Ss
+        js = fma(G[mm_off + e], ss, js);
+        Q1(i, j) = iK[mm_off + e];
+        Q2(i, j) = H[mm_off + e];
+    }
+    for (int i = tid; i < M; i += MX_THREADS) {
+        mv[i] = m[(size_t)l * M + i];
+        gv[i] = gw[(size_t)l * M + i];
+        pv[i] = p[(size_t)l * M + i];
+        wv[i] = w[(size_t)l * M + i];
+    }
+    __syncthreads();
+    js = 0.5 * block_sum(js, red);                                     // S parts of D (:170) and E (:172)
+    mm<false>(Q3, Q1, Q0, M);                                          // U = iK Ss
+    mm<false>(Q4, Q3, Q1, M);                                          // iK Ss iK  (:189 / :281)
+    for (int e = tid; e < M * M; e += MX_THREADS) {
+        int i = e / M, j = e % M;
+        double bm = Q4(i, j), ik = Q1(i, j), ih = iH[mm_off + e];
+        if (ng_H) ng_H[mm_off + e] = 0.5 * (-ih + bm + ik);           // grad_H (:191 / :283)
+        gH[mm_off + e] = 0.5 * c0 * bm + 0.5 * ik - 0.5 * ih;
+    }
+    for (int i = tid; i < M; i += MX_THREADS) {
+        double a = 0.0, b = 0.0, c = 0.0;
+        for (int k = 0; k < M; k++) {
+            a = fma(Q1(i, k), pv[k], a);                               // iK p
+            b = fma(Q4(i, k) + Q1(i, k), mv[k], b);                    // (iK S iK + iK) m
+            c = fma(Q1(i, k), gv[k], c);                               // iK gw
+        }
+        if (ng_m) ng_m[(size_t)l * M + i] = -a + b;                    // grad_m (:190 / :282)
+        gm[(size_t)l * M + i] = c0 * c + wv[i];
+    }
+    __syncthreads();
+    mm<true>(Q4, Q3, Q2, M);                                           // V1 = U^T H = Ss iK H
+    for (int e = tid; e < M * M; e += MX_THREADS) {
+        int i = e / M, j = e % M;
+        if (i <= j) {
+            double g = 0.5 * c0 * (Q4(i, j) + Q4(j, i) - Q0(i, j)) + 0.5 * c0 * (gv[i] * mv[j] + mv[i] * gv[j]) +
+                       0.5 * (Q2(i, j) + mv[i] * mv[j]);
+            Q0(i, j) = g;                                              // Gamma (symmetric)
+            Q0(j, i) = g;
+        }
+    }
+    __syncthreads();
+    mm<false>(Q3, Q1, Q0, M);                                          // iK Gamma
+    mm<false>(Q4, Q3, Q1, M);                                          // iK Gamma iK
+    const double ic0 = 1.0 / c0;
+    for (int e = tid; e < M * M; e += MX_THREADS) {
+        int i = e / M, j = e % M;
+        gK_over_c0[mm_off + e] = (-Q4(i, j) + 0.5 * Q1(i, j)) * ic0;
+    }
+    if (tid == 0) {
+        const double* sc = scal + (size_t)l * HLVAE_NSCAL;
+        const double* pr = pre + (size_t)l * 4;
+        double kq = 0.5 * (pr[2] + pr[3] - (double)M + pr[0] - pr[1]);                     // :180 / :275
+        double v = c0 * (0.5 * (sc[0] + sc[1] + sc[2] - sc[3]) + js) + kq;               // :181 / :277
+        if (l == 0) v -= constant;
+        atomicAdd(kld, v);
+    }
+}
+
+// =====================================================================================
+// training.py:130-137
+__global__ void __launch_bounds__(MX_THREADS)
+natgrad_k(int L, int M, double lr, const double* __restrict__ m, const double* __restrict__ H,
+          const double* __restrict__ grad_m, const double* __restrict__ grad_H, double* __restrict__ m_out,
+          double* __restrict__ H_out, double* __restrict__ ws, int32_t* __restrict__ status) {
+    extern __shared__ double smem[];
+    const int l = blockIdx.x, tid = threadIdx.x;
+    Bufs B = carve(smem, M, ws, l);
+    double* tmp = B.vec;
+    double* mv = B.vec + M;
+    double* v = B.vec + 2 * M;
+    const size_t mm_off = (size_t)l * M * M;
+    Mat A = B.b[0], P1 = B.b[1], P2 = B.b[2], P3 = B.b[3];
+    load(A, H + mm_off, M);
+    for (int i = tid; i < M; i += MX_THREADS) mv[i] = m[(size_t)l * M + i];
+    __syncthreads();
+    double ldet;
+    if (!chol(A, M, tmp, ldet)) {                                      // :131
+        if (tid == 0) report_status(status, HLVAE_STATUS_NOT_PD, l, -3);
+        return;
+    }
+    tri_inv(P1, A, M);
+    ata_lower(P2, P1, M, nullptr);                                     // iH (:132)
+    // v = iH m - lr (grad_m - 2 grad_H m)   (:136-137)
+    for (int i = tid; i < M; i += MX_THREADS) {
+        double a = 0.0, b = 0.0;
+        for (int k = 0; k < M; k++) {
+            a = fma(P2(i, k), mv[k], a);
+            b = fma(grad_H[mm_off + (size_t)i * M + k], mv[k], b);
+        }
+        v[i] = a - lr * (grad_m[(size_t)l * M + i] - 2.0 * b);
+    }
+    // iH_new = iH + lr (grad_H + grad_H^T)   (:133)
+    for (int e = tid; e < M * M; e += MX_THREADS) {
+        int i = e / M, j = e % M;
+        A(i, j) = P2(i, j) + lr * (grad_H[mm_off + e] + grad_H[mm_off + (size_t)j * M + i]);
+    }
+    __syncthreads();
+    if (!chol(A, M, tmp, ldet)) {                                      // :134
+        if (tid == 0) report_status(status, HLVAE_STATUS_NOT_PD, l, -4);
+        return;
+    }
+    tri_inv(P1, A, M);
+    ata_lower(P3, P1, M, H_out + mm_off);                              // H_new (:135)
+    for (int i = tid; i < M; i += MX_THREADS) {
+        double a = 0.0;
+        for (int k = 0; k < M; k++) a = fma(P3(i, k), v[k], a);
+        m_out[(size_t)l * M + i] = a;                                  // m_new (:136)
+    }
+}
+
+template <typename K>
+int set_smem(K kern, size_t bytes) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    return e == cudaSuccess ? 0 : (int)e;
+}
+
+}  // namespace
+
+extern "C" int64_t hlvae_mxm_workspace_doubles(int L, int M) {
+    return (M <= 64) ? 0 : (int64_t)L * (MX_NBUF - 1) * M * M;
+}
+
+extern "C" int hlvae_mxm_pre(const hlvae_kspec_t* spec0, const double* os0, const double* ls0, int L, int Q, int M,
+                             const double* z, double eps, const double* m, const double* H, double* iK, double* iH,
+                             double* w, double* G, double* pre, double* ws, int32_t* status, void* stream) {
+    if (!hlvae::spec_valid(spec0, Q) || L <= 0 || Q <= 0 || Q > HLVAE_MAX_Q || M <= 0 || !z || !m || !H || !iK ||
+        !iH || !w || !G || !pre)
+        return HLVAE_E_ARG;
+    if (M > 128) return HLVAE_E_UNSUPPORTED;
+    if (M > 64 && !ws) return HLVAE_E_ARG;
+    size_t smem = mx_smem_bytes(M);
+    int rc = set_smem(mxm_pre_k, smem);
+    if (rc) return rc;
+    mxm_pre_k<<<L, MX_THREADS, smem, (cudaStream_t)stream>>>(*spec0, os0, ls0, L, Q, M, z, eps, m, H, iK, iH, w, G,
+                                                             pre, ws, status);
+    HLVAE_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int hlvae_mxm_post(int L, int M, double c0, double constant, const double* iK, const double* iH,
+                              const double* H, const double* m, const double* w, const double* G, const double* pre,
+                              const double* S, const double* p, const double* gw, const double* scal, double* kld,
+                              double* gK_over_c0, double* gH, double* gm, double* ng_m, double* ng_H, double* ws,
+                              void* stream) {
+    if (L <= 0 || M <= 0 || !(c0 > 0.0) || !iK || !iH || !H || !m || !w || !G || !pre || !S || !p || !gw || !scal ||
+        !kld || !gK_over_c0 || !gH || !gm)
+        return HLVAE_E_ARG;
+    if (M > 128) return HLVAE_E_UNSUPPORTED;
+    if (M > 64 && !ws) return HLVAE_E_ARG;
+    size_t smem = mx_smem_bytes(M);
+    int rc = set_smem(mxm_post_k, smem);
+    if (rc) return rc;
+    mxm_post_k<<<L, MX_THREADS, smem, (cudaStream_t)stream>>>(L, M, c0, constant, iK, iH, H, m, w, G, pre, S, p, gw,
+                                                              scal, kld, gK_over_c0, gH, gm, ng_m, ng_H, ws);
+    HLVAE_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int hlvae_natgrad_update(int L, int M, double lr, const double* m, const double* H, const double* grad_m,
+                                    const double* grad_H, double* m_out, double* H_out, double* ws, int32_t* status,
+                                    void* stream) {
+    if (L <= 0 || M <= 0 || !m || !H || !grad_m || !grad_H || !m_out || !H_out) return HLVAE_E_ARG;
+    if (M > 128) return HLVAE_E_UNSUPPORTED;
+    if (M > 64 && !ws) return HLVAE_E_ARG;
+    size_t smem = mx_smem_bytes(M);
+    int rc = set_smem(natgrad_k, smem);
+    if (rc) return rc;
+    natgrad_k<<<L, MX_THREADS, smem, (cudaStream_t)stream>>>(L, M, lr, m, H, grad_m, grad_H, m_out, H_out, ws,
+                                                             status);
+    HLVAE_CHECK_LAUNCH();
+    return 0;
+}

@@ -17,7 +17,7 @@ from __future__ import annotations
 import torch
 
 from . import _lib, config
-from .kernels import _KernelEval, compile_spec
+from .kernels import compile_spec
 from .subjects import SubjectLayout
 
 N_SM = 148
@@ -31,8 +31,9 @@ def _noise_vector(likelihood, L, device):
 def _raise_status(status, info):
     st = status.tolist()
     if st[0] == _lib.STATUS_NOT_PD:
-        raise RuntimeError(f"hlvae_b200: cholesky: B_s of subject {st[2]} (latent dim {st[1]}) is not "
-                           "positive-definite")
+        what = {-1: "K0zz + eps I", -2: "H", -3: "H", -4: "H^-1 + lr (grad_H + grad_H^T)"}.get(
+            st[2], f"B_s of subject {st[2]}")
+        raise RuntimeError(f"hlvae_b200: cholesky: {what} (latent dim {st[1]}) is not positive-definite")
     if st[0] == _lib.STATUS_T_TOO_LARGE:
         raise RuntimeError(f"hlvae_b200: subject {st[2]} has more than {_lib.TMAX} rows")
     if info is not None and bool((info != 0).any()):
@@ -40,6 +41,11 @@ def _raise_status(status, info):
 
 
 class _KLD(torch.autograd.Function):
+    """(mu, log_v, z, m, H, constrained hyper-parameters) -> kld_total, grad_m, grad_H.
+
+    Every gradient is produced in the forward pass (the streaming kernels need only quantities
+    of the M x M pre-stage, see DESIGN.md "single-pass gradient"), so backward is a scaling."""
+
     @staticmethod
     def forward(ctx, mu, log_v, z, m, H, os0, ls0, os1, ls1, noise, x, fs0, fs1, layout, scale, const, eps,
                 natural_gradient, out_shape):
@@ -49,101 +55,103 @@ class _KLD(torch.autograd.Function):
         if mu.dtype != log_v.dtype:
             raise TypeError("mu and log_v must share a dtype")
         dcode = _lib.dtype_code(mu)
+        f64 = dict(dtype=torch.float64, device=dev)
         mu_c, lv_c = mu.detach().contiguous(), log_v.detach().contiguous()
         x_c = x.detach().to(torch.float64).contiguous()
-        f64 = dict(dtype=torch.float64, device=dev)
+        z_c = z.detach().to(torch.float64).contiguous()
+        m_c = m.detach().to(torch.float64).reshape(L, M).contiguous()
+        H_c = H.detach().to(torch.float64).contiguous()
+        os0c, ls0c = os0.detach().contiguous(), ls0.detach().contiguous()
+        os1c, ls1c = os1.detach().contiguous(), ls1.detach().contiguous()
+        st = _lib.stream_ptr()
+        ws = _lib.workspace(L, M, dev)
+        status = torch.zeros(4, dtype=torch.int32, device=dev)
 
-        # ---- 1. M x M pre-stage on a private graph (its gradient is taken below, inside forward)
-        with torch.enable_grad():
-            zl = z.detach().to(torch.float64).contiguous().requires_grad_(True)
-            os0l = os0.detach().requires_grad_(True)
-            ls0l = ls0.detach().requires_grad_(True)
-            ml = m.detach().to(torch.float64).requires_grad_(True)
-            Hl = H.detach().to(torch.float64).requires_grad_(True)
-            eye = torch.eye(M, **f64)
-            eyeL = eye.expand(L, M, M).contiguous()
-            K0zz = _KernelEval.apply(fs0, os0l, ls0l, zl, zl) + eps * eye                 # :148,153 / :223-224
-            LK, infoK = torch.linalg.cholesky_ex(K0zz)                                     # :154 / :225
-            iK = torch.cholesky_solve(eyeL, LK)                            # :155 / :226
-            LH, infoH = torch.linalg.cholesky_ex(Hl)                                       # :162 / :227
-            iH = torch.cholesky_solve(eyeL, LH)                            # :163 / :228
-            w = iK @ ml                                                                    # iK m in :166 / :230
-            G = iK @ Hl @ iK - iK                                                          # :171 / :231 minus :170
-        Gs = (0.5 * (G + G.transpose(-1, -2))).detach().contiguous()
-        wd = w.detach().reshape(L, M).contiguous()
+        # ---- 1. M x M pre-stage (replicated): iK, iH, w = iK m, G = iK H iK - iK
+        mats = torch.empty(4, L, M, M, **f64)          # iK, iH, G, (later) dkld/dK0zz / c0
+        iK, iH, G, gK = mats[0], mats[1], mats[2], mats[3]
+        vecs = torch.empty(2, L, M, **f64)             # w, dkld/dm
+        w, gm = vecs[0], vecs[1]
+        pre = torch.empty(L, 4, **f64)
+        _lib.call("hlvae_mxm_pre", fs0.cspec, _lib.ptr(os0c), _lib.ptr(ls0c), L, Q, M, _lib.ptr(z_c), eps,
+                  _lib.ptr(m_c), _lib.ptr(H_c), _lib.ptr(iK), _lib.ptr(iH), _lib.ptr(w), _lib.ptr(G), _lib.ptr(pre),
+                  _lib.ptr(ws), _lib.ptr(status), st)
 
         # ---- 2. streaming stage
         off = _lib.acc_layout(L, M, Q)
-        acc = torch.zeros(off["total"], **f64)
-        g_mu = torch.zeros(N, L, **f64)
-        g_lv = torch.zeros(N, L, **f64)
+        acc = torch.zeros(off["total"] + 1, **f64)     # last element: kld_total
+        full = layout.n_rows == N
+        g_mu = torch.empty_like(mu_c) if full else torch.zeros_like(mu_c)
+        g_lv = torch.empty_like(lv_c) if full else torch.zeros_like(lv_c)
         binv = torch.empty(L, max(layout.tt_total, 1), **f64)
-        status = torch.zeros(4, dtype=torch.int32, device=dev)
-        os0c, ls0c = os0.detach().contiguous(), ls0.detach().contiguous()
-        os1c, ls1c = os1.detach().contiguous(), ls1.detach().contiguous()
-        lib, st = _lib.lib(), _lib.stream_ptr()
         if layout.n_subj > 0:
             _lib.call("hlvae_kl_subject", fs0.cspec, _lib.ptr(os0c), _lib.ptr(ls0c), fs1.cspec, _lib.ptr(os1c),
-                                            _lib.ptr(ls1c), _lib.ptr(noise), L, Q, _lib.ptr(x_c), Q,
-                                            _lib.ptr(layout.row_idx), _lib.ptr(layout.subj_ptr),
-                                            _lib.ptr(layout.tt_ptr), layout.n_subj, max(layout.t_max, 1),
-                                            _lib.ptr(lv_c), L, dcode, _lib.ptr(binv), binv.shape[1], _lib.ptr(acc), M,
-                                            _lib.ptr(g_lv), _lib.ptr(status), st)
+                      _lib.ptr(ls1c), _lib.ptr(noise), L, Q, _lib.ptr(x_c), Q, _lib.ptr(layout.row_idx),
+                      _lib.ptr(layout.subj_ptr), _lib.ptr(layout.tt_ptr), layout.n_subj, max(layout.t_max, 1),
+                      _lib.ptr(lv_c), L, dcode, _lib.ptr(binv), binv.shape[1], _lib.ptr(acc), M, _lib.ptr(g_lv),
+                      scale, _lib.ptr(status), st)
             n_chunks = max(1, min((N_SM * 8 + L - 1) // L, (layout.n_subj + 2) // 3))
             spc = (layout.n_subj + n_chunks - 1) // n_chunks
             _lib.call("hlvae_kl_panel", fs0.cspec, _lib.ptr(os0c), _lib.ptr(ls0c), fs1.cspec, _lib.ptr(os1c),
-                                          _lib.ptr(ls1c), L, Q, M, _lib.ptr(x_c), Q, _lib.ptr(zl.detach()),
-                                          _lib.ptr(layout.row_idx), _lib.ptr(layout.subj_ptr),
-                                          _lib.ptr(layout.tt_ptr), layout.n_subj, spc, _lib.ptr(mu_c), L, dcode,
-                                          _lib.ptr(wd), _lib.ptr(Gs), _lib.ptr(binv), binv.shape[1], _lib.ptr(acc),
-                                          _lib.ptr(g_mu), _lib.ptr(status), st)
+                      _lib.ptr(ls1c), L, Q, M, _lib.ptr(x_c), Q, _lib.ptr(z_c), _lib.ptr(layout.row_idx),
+                      _lib.ptr(layout.subj_ptr), _lib.ptr(layout.tt_ptr), layout.n_subj, spc, _lib.ptr(mu_c), L,
+                      dcode, _lib.ptr(w), _lib.ptr(G), _lib.ptr(binv), binv.shape[1], _lib.ptr(acc), _lib.ptr(g_mu),
+                      scale, _lib.ptr(status), st)
         # ---- 3. data parallel: one all-reduce of every accumulator (S, p, scalars, replicated-parameter grads)
         if config.process_group is not None:
             torch.distributed.all_reduce(acc, group=config.process_group)
-        if config.check_errors:
-            _raise_status(status, torch.cat([infoK, infoH]))
 
         def view(name, *shape):
             n = 1
-            for s in shape:
-                n *= s
+            for s_ in shape:
+                n *= s_
             return acc[off[name]:off[name] + n].view(*shape)
 
-        S, p, gw = view("S", L, M, M), view("p", L, M, 1), view("gw", L, M, 1)
-        scal = view("scal", L, _lib.NSCAL).sum(0)
-        nc0, nc1 = fs0.ncomp, fs1.ncomp
+        S, p, gw, scal = view("S", L, M, M), view("p", L, M), view("gw", L, M), view("scal", L, _lib.NSCAL)
+        kld = acc[off["total"]:]
+        # ---- 4. M x M post-stage: kld_total, natural-gradient pieces, d kld / d{K0zz, m, H}
+        gH = torch.empty(L, M, M, **f64)
+        if natural_gradient:
+            ng_H_c = torch.empty(L, M, M, **f64)
+            ng_m_c = torch.empty(L, M, 1, **f64)
+        _lib.call("hlvae_mxm_post", L, M, scale, const, _lib.ptr(iK), _lib.ptr(iH), _lib.ptr(H_c), _lib.ptr(m_c),
+                  _lib.ptr(w), _lib.ptr(G), _lib.ptr(pre), _lib.ptr(S), _lib.ptr(p), _lib.ptr(gw), _lib.ptr(scal),
+                  _lib.ptr(kld), _lib.ptr(gK), _lib.ptr(gH), _lib.ptr(gm),
+                  _lib.ptr(ng_m_c) if natural_gradient else None, _lib.ptr(ng_H_c) if natural_gradient else None,
+                  _lib.ptr(ws), st)
+        # d kld / dK0zz -> Z and the K0 hyper-parameters, accumulated (over c0) onto the streaming gradients
         gZ = view("gZ", L, M, Q)
-        gos0, gls0 = view("gos0", _lib.MAX_COMPS, L)[:nc0], view("gls0", _lib.MAX_COMPS, L)[:nc0]
-        gos1, gls1 = view("gos1", _lib.MAX_COMPS, L)[:nc1], view("gls1", _lib.MAX_COMPS, L)[:nc1]
+        _lib.call("hlvae_kernel_eval_bwd", fs0.cspec, _lib.ptr(os0c), _lib.ptr(ls0c), L, Q, _lib.ptr(z_c), M, Q,
+                  M * Q, _lib.ptr(z_c), M, Q, M * Q, _lib.ptr(gK), _lib.ptr(view("gos0", _lib.MAX_COMPS, L)),
+                  _lib.ptr(view("gls0", _lib.MAX_COMPS, L)), _lib.ptr(gZ), _lib.ptr(gZ), st)
+        if config.check_errors:
+            _raise_status(status, None)
+        nc0, nc1 = fs0.ncomp, fs1.ncomp
+        grads = acc[off["gZ"]:off["total"]] * scale          # one launch for every replicated-parameter gradient
+        o0 = off["gZ"]
 
-        # ---- 4. M x M post-stage
-        with torch.enable_grad():
-            J_S = 0.5 * (G * S).sum()                                                      # S parts of D (:170) and E (:172)
-            tr1 = (iK * Hl.transpose(-1, -2)).sum()                                        # :176 / :271
-            qf1 = (ml * (iK @ ml)).sum()                                                   # :177 / :272
-            logdetK = 2 * torch.log(torch.diagonal(LK, dim1=-1, dim2=-2)).sum()            # :178 / :273
-            logdetH = 2 * torch.log(torch.diagonal(LH, dim1=-1, dim2=-2)).sum()            # :179 / :274
-            kq = 0.5 * (tr1 + qf1 - L * M + logdetK - logdetH)                             # :180 / :275
-            local = scale * (J_S + (w * gw).sum()) + kq
-            gz_l, gos0_l, gls0_l, gm_l, gH_l = torch.autograd.grad(local, [zl, os0l, ls0l, ml, Hl])
-        kld = scale * (0.5 * (scal[0] + scal[1] + scal[2] - scal[3]) + J_S.detach()) + kq.detach() - const  # :181 / :277
+        def gview(name, *shape):
+            n = 1
+            for s_ in shape:
+                n *= s_
+            return grads[off[name] - o0:off[name] - o0 + n].view(*shape)
 
-        grad_m = grad_H = None
-        if natural_gradient:                                                               # :186-191 / :279-283
-            iKd = iK.detach()
-            Bm = iKd @ S @ iKd + iKd
-            grad_m = -(iKd @ p) + Bm @ ml.detach()
-            grad_H = 0.5 * (-iH.detach() + Bm)
-
-        ctx.save_for_backward((scale * g_mu).to(mu.dtype), (scale * g_lv).to(log_v.dtype), gz_l + scale * gZ, gm_l,
-                              gH_l, gos0_l + scale * gos0, gls0_l + scale * gls0, scale * gos1, scale * gls1)
+        ctx.save_for_backward(g_mu, g_lv, gview("gZ", L, M, Q).to(z.dtype), gm.reshape(m.shape).to(m.dtype),
+                              gH.to(H.dtype), gview("gos0", _lib.MAX_COMPS, L)[:nc0],
+                              gview("gls0", _lib.MAX_COMPS, L)[:nc0], gview("gos1", _lib.MAX_COMPS, L)[:nc1],
+                              gview("gls1", _lib.MAX_COMPS, L)[:nc1])
+        grad_m = ng_m_c if natural_gradient else None
+        grad_H = ng_H_c if natural_gradient else None
         ctx.mark_non_differentiable(*[t for t in (grad_m, grad_H) if t is not None])
-        return kld.reshape(out_shape), grad_m, grad_H
+        return kld.clone().reshape(out_shape), grad_m, grad_H
 
     @staticmethod
     def backward(ctx, g_kld, g_gm, g_gH):
         g = g_kld.reshape(())
-        return tuple(g * t for t in ctx.saved_tensors) + (None,) * 10
+        out = []
+        for t in ctx.saved_tensors:
+            out.append((g * t).to(t.dtype) if t.numel() else t)
+        return tuple(out) + (None,) * 10
 
 
 def _kld(covar_module0, covar_module1, likelihood, latent_dim, m, H, train_xt, mu, log_v, z, layout, scale, const,
@@ -179,10 +187,18 @@ def minibatch_KLD_upper_bound_iter(covar_module0, covar_module1, likelihood, lat
 
 
 def natural_gradient_update(m, H, grad_m, grad_H, lr):
-    """training.py:130-137 (kept here so callers outside training.py can reuse it)."""
-    eye = torch.eye(H.shape[-1], dtype=H.dtype, device=H.device).expand_as(H)
-    iH = torch.cholesky_solve(eye, torch.linalg.cholesky(H))
-    iH_new = iH + lr * (grad_H + grad_H.transpose(-1, -2))
-    H_new = torch.cholesky_solve(eye, torch.linalg.cholesky(iH_new)).detach()
-    m_new = (H_new @ (iH @ m - lr * (grad_m - 2 * (grad_H @ m)))).detach()
-    return m_new, H_new
+    """training.py:130-137 as one kernel (hlvae_natgrad_update): returns detached (m_new, H_new)."""
+    L, M = H.shape[0], H.shape[-1]
+    dev = H.device
+    m_c = m.detach().to(torch.float64).reshape(L, M).contiguous()
+    H_c = H.detach().to(torch.float64).contiguous()
+    gm = grad_m.detach().to(torch.float64).reshape(L, M).contiguous()
+    gH = grad_H.detach().to(torch.float64).contiguous()
+    m_new, H_new = torch.empty_like(m_c), torch.empty_like(H_c)
+    status = torch.zeros(4, dtype=torch.int32, device=dev)
+    ws = _lib.workspace(L, M, dev)
+    _lib.call("hlvae_natgrad_update", L, M, float(lr), _lib.ptr(m_c), _lib.ptr(H_c), _lib.ptr(gm), _lib.ptr(gH),
+              _lib.ptr(m_new), _lib.ptr(H_new), _lib.ptr(ws), _lib.ptr(status), _lib.stream_ptr())
+    if config.check_errors:
+        _raise_status(status, None)
+    return m_new.reshape(m.shape).to(m.dtype), H_new.to(H.dtype)

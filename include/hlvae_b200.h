@@ -108,7 +108,8 @@ int hlvae_kernel_eval_bwd(const hlvae_kspec_t* spec, const double* outputscale, 
  *                    sufficient statistics (FP64 tensor-core mma), and the remaining gradients.
  * `acc` is one float64 buffer the caller zero-fills; hlvae_kl_acc_layout gives offsets
  * (in doubles) of {S, p, gw, scal, gZ, gos0, gls0, gos1, gls1, total}.  g_mu, g_logv:
- * [N, L] contiguous, fully overwritten for the rows listed in row_idx.
+ * [N, L] contiguous in the storage `dtype`, overwritten for the rows listed in row_idx with
+ * gscale * dJ/dmu and gscale * dJ/dlog_v (gscale = P / P_batch of elbo_functions.py:181,277).
  * ---------------------------------------------------------------------------------- */
 #define HLVAE_ACC_S 0
 #define HLVAE_ACC_P 1
@@ -128,7 +129,7 @@ int hlvae_kl_subject(const hlvae_kspec_t* spec0, const double* os0, const double
                      int L, int Q, const double* x, int64_t ldx,
                      const int32_t* row_idx, const int32_t* subj_ptr, const int32_t* tt_ptr, int n_subj, int t_cap,
                      const void* log_v, int64_t ld_lv, int dtype,
-                     double* binv, int64_t tt_total, double* acc, int M, double* g_logv,
+                     double* binv, int64_t tt_total, double* acc, int M, void* g_logv, double gscale,
                      int32_t* status, void* stream);
 
 int hlvae_kl_panel(const hlvae_kspec_t* spec0, const double* os0, const double* ls0,
@@ -137,7 +138,32 @@ int hlvae_kl_panel(const hlvae_kspec_t* spec0, const double* os0, const double* 
                    const int32_t* row_idx, const int32_t* subj_ptr, const int32_t* tt_ptr, int n_subj,
                    int subj_per_chunk, const void* mu, int64_t ld_mu, int dtype,
                    const double* w, const double* G, const double* binv, int64_t tt_total,
-                   double* acc, double* g_mu, int32_t* status, void* stream);
+                   double* acc, void* g_mu, double gscale, int32_t* status, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Replicated M x M stage (float64, one CTA per latent dimension, M <= 128).
+ * hlvae_mxm_pre : K0zz = K0(Z,Z) + eps I (:148,153 / :223-224), Cholesky and explicit inverses
+ *   iK, iH (:154-157,162-163 / :225-228), w = iK m, G = sym(iK H iK) - iK; pre[l] =
+ *   {logdet K, logdet H, tr(iK H), m^T iK m} (:176-179 / :271-274).  All outputs [L,...] float64.
+ * hlvae_mxm_post: from the (all-reduced) accumulators S, p, gw, scal: kld[0] += kld_total
+ *   (:181 / :277, `constant` = L * N / 2 subtracted once), the natural-gradient pieces ng_m, ng_H
+ *   (:186-191 / :279-283; nullable) and, with f = c0 (tr(G S)/2 + w^T gw) + kld_qu_pu,
+ *   gK_over_c0 = (df/dK0zz) / c0, gH = df/dH, gm = df/dm.  c0 = P / P_batch.
+ * hlvae_natgrad_update: training.py:130-137, (m, H, grad_m, grad_H, lr) -> (m_out, H_out).
+ * `ws`: global workspace of hlvae_mxm_workspace_doubles(L, M) doubles (0 when M <= 64).
+ * ---------------------------------------------------------------------------------- */
+int64_t hlvae_mxm_workspace_doubles(int L, int M);
+int hlvae_mxm_pre(const hlvae_kspec_t* spec0, const double* os0, const double* ls0, int L, int Q, int M,
+                  const double* z, double eps, const double* m, const double* H, double* iK, double* iH,
+                  double* w, double* G, double* pre, double* ws, int32_t* status, void* stream);
+int hlvae_mxm_post(int L, int M, double c0, double constant, const double* iK, const double* iH,
+                   const double* H, const double* m, const double* w, const double* G, const double* pre,
+                   const double* S, const double* p, const double* gw, const double* scal, double* kld,
+                   double* gK_over_c0, double* gH, double* gm, double* ng_m, double* ng_H, double* ws,
+                   void* stream);
+int hlvae_natgrad_update(int L, int M, double lr, const double* m, const double* H, const double* grad_m,
+                         const double* grad_H, double* m_out, double* H_out, double* ws, int32_t* status,
+                         void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Fused masked heterogeneous log-likelihood.  Replaces HLVAE.loglik_and_reconstruction

@@ -19,13 +19,13 @@ DT = torch.float64
 @pytest.mark.parametrize("name", h.KL_CASES)
 def test_golden(name, device):
     r = h.run_kl_golden(name, device)
-    errs = h.assert_kl_close(r, tol=1e-6, hyper_tol=1e-4, label=name)
+    errs = h.assert_kl_close(r, tol=5e-6, hyper_tol=1e-4, label=name)
     print(name, {k: f"{v:.1e}" for k, v in errs.items()})
 
 
 def test_golden_with_host_known_lengths(device):
     r = h.run_kl_golden("kl_default_ragged", device, layout="lengths")
-    h.assert_kl_close(r, tol=1e-6, hyper_tol=1e-4)
+    h.assert_kl_close(r, tol=5e-6, hyper_tol=1e-4)
 
 
 def test_golden_float32_storage(device):

@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_library_exports_every_declared_symbol(built_lib):
     hdr = open(os.path.join(ROOT, "include", "hlvae_b200.h")).read()
-    declared = set(re.findall(r"^int\s+(hlvae_\w+)\s*\(", hdr, flags=re.M))
+    declared = set(re.findall(r"^(?:int|int64_t)\s+(hlvae_\w+)\s*\(", hdr, flags=re.M))
     assert declared, "no declarations parsed"
     assert declared == set(_lib.EXPORTED), declared ^ set(_lib.EXPORTED)
     for name in declared:
