@@ -25,8 +25,36 @@ struct AccOff {
 // =====================================================================================
 constexpr int SJ_WARPS = 4;
 
+// lower-triangle walk: element t = i (i + 1) / 2 + j, advanced by 32 per step without divisions
+struct TriIdx {
+    int i, j;
+    __device__ __forceinline__ void init(int t) {
+        i = 0;
+        j = t;
+        while (j > i) { j -= i + 1; i++; }
+    }
+    __device__ __forceinline__ void advance32() {
+        j += 32;
+        while (j > i) { j -= i + 1; i++; }
+    }
+};
+
+// square walk: element e = i T + j, advanced by 32 per step without divisions
+struct SqIdx {
+    int i, j;
+    __device__ __forceinline__ void init(int e, int T) {
+        i = 0;
+        j = e;
+        while (j >= T) { j -= T; i++; }
+    }
+    __device__ __forceinline__ void advance32(int T) {
+        j += 32;
+        while (j >= T) { j -= T; i++; }
+    }
+};
+
 template <typename TS>
-__global__ void __launch_bounds__(SJ_WARPS * 32)
+__global__ void __launch_bounds__(SJ_WARPS * 32, 4)
 kl_subject_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__ os0, const double* __restrict__ ls0,
              const __grid_constant__ hlvae_kspec_t sp1, const double* __restrict__ os1, const double* __restrict__ ls1,
              const double* __restrict__ noise, int L, int Q, const double* __restrict__ x, int64_t ldx,
@@ -53,6 +81,7 @@ kl_subject_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict
         if (lane == 0) report_status(status, HLVAE_STATUS_T_TOO_LARGE, l, s);
         return;
     }
+    const int TL = T * (T + 1) / 2;
     KParams kp0, kp1;
     load_kparams(kp0, sp0, os0, ls0, L, l);
     load_kparams(kp1, sp1, os1, ls1, L, l);
@@ -67,13 +96,21 @@ kl_subject_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict
     }
     __syncwarp();
     const double nz = noise[l];
-    // B_s = K1(x_s, x_s) + noise I (elbo_functions.py:249-250); Ks = K0(x_s, x_s) (:248) + diag(exp(log_v))
-    for (int e = lane; e < T * T; e += 32) {
-        int i = e / T, j = e % T;
-        double k1 = eval_additive(sp1, kp1, xs + i * Q, xs + j * Q);
-        double k0 = eval_additive(sp0, kp0, xs + i * Q, xs + j * Q);
-        Bw[i * ldt + j] = k1 + (i == j ? nz : 0.0);
-        Ks[i * ldt + j] = k0;
+    // B_s = K1(x_s, x_s) + noise I (elbo_functions.py:249-250); Ks = K0(x_s, x_s) (:248) + diag(exp(log_v)).
+    // Both are symmetric: evaluate the lower triangle and mirror.
+    {
+        TriIdx ix;
+        ix.init(lane);
+        for (int t = lane; t < TL; t += 32, ix.advance32()) {
+            const int i = ix.i, j = ix.j;
+            double k1 = eval_additive(sp1, kp1, xs + i * Q, xs + j * Q);
+            double k0 = eval_additive(sp0, kp0, xs + i * Q, xs + j * Q);
+            if (i == j) k1 += nz;
+            Bw[i * ldt + j] = k1;
+            Bw[j * ldt + i] = k1;
+            Ks[i * ldt + j] = k0;
+            Ks[j * ldt + i] = k0;
+        }
     }
     __syncwarp();
     if (lane < T) Ks[lane * ldt + lane] += ev;
@@ -82,11 +119,19 @@ kl_subject_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict
     double logdet = 0.0;
     bool bad = false;
     for (int j = 0; j < T; j++) {
-        double sum = 0.0;
+        double s0 = 0.0, s1 = 0.0;
         if (lane >= j && lane < T) {
-            sum = Bw[lane * ldt + j];
-            for (int k = 0; k < j; k++) sum = fma(-Bw[lane * ldt + k], Bw[j * ldt + k], sum);
+            const double* ri = Bw + lane * ldt;
+            const double* rj = Bw + j * ldt;
+            s0 = ri[j];
+            int k = 0;
+            for (; k + 1 < j; k += 2) {
+                s0 = fma(-ri[k], rj[k], s0);
+                s1 = fma(-ri[k + 1], rj[k + 1], s1);
+            }
+            if (k < j) s0 = fma(-ri[k], rj[k], s0);
         }
+        const double sum = s0 + s1;
         double djj = __shfl_sync(0xffffffffu, sum, j);
         if (!(djj > 0.0)) { bad = true; break; }
         double d = sqrt(djj);
@@ -104,18 +149,28 @@ kl_subject_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict
         for (int i = 0; i < c; i++) Bi[i * ldt + c] = 0.0;
         Bi[c * ldt + c] = 1.0 / Bw[c * ldt + c];
         for (int i = c + 1; i < T; i++) {
-            double a = 0.0;
-            for (int k = c; k < i; k++) a = fma(Bw[i * ldt + k], Bi[k * ldt + c], a);
-            Bi[i * ldt + c] = -a / Bw[i * ldt + i];
+            double a0 = 0.0, a1 = 0.0;
+            int k = c;
+            for (; k + 1 < i; k += 2) {
+                a0 = fma(Bw[i * ldt + k], Bi[k * ldt + c], a0);
+                a1 = fma(Bw[i * ldt + k + 1], Bi[(k + 1) * ldt + c], a1);
+            }
+            if (k < i) a0 = fma(Bw[i * ldt + k], Bi[k * ldt + c], a0);
+            Bi[i * ldt + c] = -(a0 + a1) / Bw[i * ldt + i];
         }
     }
     __syncwarp();
-    // B^-1 = L^-T L^-1 into Bw (explicit inverse, as :252)
-    for (int e = lane; e < T * T; e += 32) {
-        int i = e / T, j = e % T;
-        double a = 0.0;
-        for (int k = max(i, j); k < T; k++) a = fma(Bi[k * ldt + i], Bi[k * ldt + j], a);
-        Bw[i * ldt + j] = a;
+    // B^-1 = L^-T L^-1 into Bw (explicit inverse, as :252); symmetric: lower triangle + mirror
+    {
+        TriIdx ix;
+        ix.init(lane);
+        for (int t = lane; t < TL; t += 32, ix.advance32()) {
+            const int i = ix.i, j = ix.j;      // i >= j
+            double a = 0.0;
+            for (int k = i; k < T; k++) a = fma(Bi[k * ldt + i], Bi[k * ldt + j], a);
+            Bw[i * ldt + j] = a;
+            Bw[j * ldt + i] = a;
+        }
     }
     __syncwarp();
 
@@ -124,32 +179,58 @@ kl_subject_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict
 #pragma unroll
     for (int r = 0; r < HLVAE_MAX_COMPS; r++) { gos0[r] = gls0[r] = gos1[r] = gls1[r] = dummy[r] = 0.0; }
 
-    // B + D1 terms: sum(B^-1 * (K0ss + diag e^logv)) (:257,259); dJ/dK0ss = 1/2 B^-1; write B^-1.
+    // B + D1 terms: sum(B^-1 * (K0ss + diag e^logv)) (:257,259); dJ/dK0ss = 1/2 B^-1 (off-diagonal
+    // entries counted twice through the mirror); write B^-1.
     double bd = 0.0;
     double* bout = binv + (int64_t)l * tt_total + tt_ptr[s];
-    for (int e = lane; e < T * T; e += 32) {
-        int i = e / T, j = e % T;
-        double bij = Bw[i * ldt + j];
-        bd = fma(bij, Ks[i * ldt + j], bd);
-        bout[e] = bij;
-        accum_grads<false>(sp0, kp0, xs + i * Q, xs + j * Q, 0.5 * bij, gos0, gls0, dummy);
+    {
+        TriIdx ix;
+        ix.init(lane);
+        for (int t = lane; t < TL; t += 32, ix.advance32()) {
+            const int i = ix.i, j = ix.j;
+            const double bij = Bw[i * ldt + j];
+            const double wgt = (i == j) ? 1.0 : 2.0;
+            bd = fma(wgt * bij, Ks[i * ldt + j], bd);
+            bout[i * T + j] = bij;
+            bout[j * T + i] = bij;
+            accum_grads<false>(sp0, kp0, xs + i * Q, xs + j * Q, 0.5 * wgt * bij, gos0, gls0, dummy);
+        }
     }
     if (lane < T) g_logv[(int64_t)g * L + l] = (TS)(gscale * 0.5 * (Bw[lane * ldt + lane] * ev - 1.0));
     // X = Ktil B^-1 -> Bi
-    for (int e = lane; e < T * T; e += 32) {
-        int i = e / T, j = e % T;
-        double a = 0.0;
-        for (int k = 0; k < T; k++) a = fma(Ks[i * ldt + k], Bw[k * ldt + j], a);
-        Bi[i * ldt + j] = a;
+    {
+        SqIdx ix;
+        ix.init(lane, T);
+        for (int e = lane; e < T * T; e += 32, ix.advance32(T)) {
+            const int i = ix.i, j = ix.j;
+            double a0 = 0.0, a1 = 0.0;
+            int k = 0;
+            for (; k + 1 < T; k += 2) {
+                a0 = fma(Ks[i * ldt + k], Bw[k * ldt + j], a0);
+                a1 = fma(Ks[i * ldt + k + 1], Bw[(k + 1) * ldt + j], a1);
+            }
+            if (k < T) a0 = fma(Ks[i * ldt + k], Bw[k * ldt + j], a0);
+            Bi[i * ldt + j] = a0 + a1;
+        }
     }
     __syncwarp();
-    // dJ/dB_s (part without K0xz) = 1/2 (B^-1 - B^-1 Ktil B^-1), contracted with dB/d(theta1)
-    for (int e = lane; e < T * T; e += 32) {
-        int i = e / T, j = e % T;
-        double a = 0.0;
-        for (int k = 0; k < T; k++) a = fma(Bw[i * ldt + k], Bi[k * ldt + j], a);
-        double gb = 0.5 * (Bw[i * ldt + j] - a);
-        accum_grads<false>(sp1, kp1, xs + i * Q, xs + j * Q, gb, gos1, gls1, dummy);
+    // dJ/dB_s (part without K0xz) = 1/2 (B^-1 - B^-1 Ktil B^-1) (symmetric), contracted with dB/d(theta1)
+    {
+        TriIdx ix;
+        ix.init(lane);
+        for (int t = lane; t < TL; t += 32, ix.advance32()) {
+            const int i = ix.i, j = ix.j;
+            double a0 = 0.0, a1 = 0.0;
+            int k = 0;
+            for (; k + 1 < T; k += 2) {
+                a0 = fma(Bw[i * ldt + k], Bi[k * ldt + j], a0);
+                a1 = fma(Bw[i * ldt + k + 1], Bi[(k + 1) * ldt + j], a1);
+            }
+            if (k < T) a0 = fma(Bw[i * ldt + k], Bi[k * ldt + j], a0);
+            const double wgt = (i == j) ? 0.5 : 1.0;
+            const double gb = wgt * (Bw[i * ldt + j] - (a0 + a1));
+            accum_grads<false>(sp1, kp1, xs + i * Q, xs + j * Q, gb, gos1, gls1, dummy);
+        }
     }
     bd = warp_sum(bd);
     double fsum = warp_sum(lv);
@@ -184,14 +265,31 @@ kl_subject_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict
 constexpr int PN_THREADS = 512;
 constexpr int PN_SMAX = 16;   // subjects per panel
 
+// One component's descriptor pulled into registers field by field (a struct copy indexed by a
+// run-time component number would be placed in local memory).
+struct CompRegs {
+    int se_col, ndisc;
+    int disc_kind[HLVAE_MAX_DISC], disc_col[HLVAE_MAX_DISC];
+    __device__ __forceinline__ void load(const hlvae_kspec_t& sp, int r) {
+        se_col = sp.comp[r].se_col;
+        ndisc = sp.comp[r].ndisc;
+#pragma unroll
+        for (int f = 0; f < HLVAE_MAX_DISC; f++) {
+            disc_kind[f] = sp.comp[r].disc_kind[f];
+            disc_col[f] = sp.comp[r].disc_col[f];
+        }
+    }
+};
+
 template <int MP, int RP, bool G_SMEM>
 struct PanelSmem {
     static constexpr int LD = MP + 4;          // leading dim of row panels: conflict-free DMMA fragment loads
-    static constexpr int BCAP = RP * HLVAE_TMAX;
+    static constexpr int LDB = RP + 4;         // leading dim of the dense block-diagonal B^-1 panel
     static constexpr size_t doubles = (size_t)HLVAE_MAX_Q * MP /*Zs*/ + MP /*ws*/ + (G_SMEM ? (size_t)MP * LD : 0) +
-                                      2 * (size_t)RP * LD /*Kb,Vb*/ + BCAP /*Bs*/ + (size_t)RP * HLVAE_MAX_Q /*xs*/ +
-                                      3 * RP /*mus, rv, rho*/ + (size_t)MP * HLVAE_MAX_COMPS /*zacc*/ +
-                                      4 * HLVAE_MAX_COMPS + 8 /*hyper acc + A*/;
+                                      2 * (size_t)RP * LD /*Kb,Vb*/ + (size_t)RP * LDB /*Bp*/ +
+                                      (size_t)RP * HLVAE_MAX_Q /*xs*/ + 3 * RP /*mus, rv, rho*/ +
+                                      (size_t)MP * HLVAE_MAX_COMPS /*zacc*/ + 4 * HLVAE_MAX_COMPS + 8 /*hyper acc + A*/ +
+                                      4 * HLVAE_MAX_COMPS /*kps*/;
     static constexpr size_t ints = 2 * RP + 2 * (PN_SMAX + 1) + 8;
     static constexpr size_t bytes = doubles * 8 + ints * 4;
 };
@@ -208,23 +306,27 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
            TS* __restrict__ g_mu, double gscale, int32_t* __restrict__ status) {
     using SM = PanelSmem<MP, RP, G_SMEM>;
     constexpr int LD = SM::LD;
-    constexpr int SI = MP / 32;   // S tiles (8x8) per warp per dim; 16 warps as 4 x 4
-    constexpr int WR = RP / 32;   // W tile rows per warp
-    constexpr int WC = MP / 32;   // W tile cols per warp
+    constexpr int LDB = SM::LDB;
+    constexpr int SI = MP / 32;                 // S tiles (8x8) per warp per dim; 16 warps as 4 x 4
+    constexpr int WR = RP / 32;                 // row tiles per warp for [RP x MP] outputs
+    constexpr int WC = MP / 32;                 // col tiles per warp for [RP x MP] outputs
+    constexpr int NGRP = PN_THREADS / MP;       // row groups in the element-wise phases
+    constexpr int RPT = RP / NGRP;              // rows per thread in the element-wise phases
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* Zs = reinterpret_cast<double*>(smem_raw);          // [Q][MP] transposed
     double* ws = Zs + HLVAE_MAX_Q * MP;
     double* Gs = ws + MP;                                      // [MP][LD] if G_SMEM
     double* Kb = Gs + (G_SMEM ? MP * LD : 0);                  // [RP][LD]  K0xz, later W = V G
     double* Vb = Kb + RP * LD;                                 // [RP][LD]  B^-1 K0xz
-    double* Bs = Vb + RP * LD;                                 // B^-1 blocks (compact), later dJ/dB blocks
-    double* xs = Bs + SM::BCAP;                                // [RP][Q]
+    double* Bp = Vb + RP * LD;                                 // [RP][LDB] dense block-diagonal B^-1, later dJ/dB
+    double* xs = Bp + RP * LDB;                                // [RP][Q]
     double* mus = xs + RP * HLVAE_MAX_Q;
     double* rv = mus + RP;
     double* rho = rv + RP;
     double* zacc = rho + RP;                                   // [MP][MAX_COMPS]
     double* hyp = zacc + MP * HLVAE_MAX_COMPS;                 // gos0, gls0, gos1, gls1, A
-    int* grow = reinterpret_cast<int*>(hyp + 4 * HLVAE_MAX_COMPS + 8);
+    double* kps = hyp + 4 * HLVAE_MAX_COMPS + 8;               // K0 hyper-parameters by component: os, hil2, il2, il3
+    int* grow = reinterpret_cast<int*>(kps + 4 * HLVAE_MAX_COMPS);
     int* sub_of_row = grow + RP;
     int* sub_r0 = sub_of_row + RP;                             // [PN_SMAX+1]
     int* sub_b0 = sub_r0 + PN_SMAX + 1;                        // [PN_SMAX+1]
@@ -235,6 +337,8 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
     const int l = blockIdx.y;
     const int s_begin = blockIdx.x * subj_per_chunk;
     const int s_end = min(n_subj, s_begin + subj_per_chunk);
+    const int em = tid % MP;                                   // this thread's inducing point in element-wise phases
+    const int eg = tid / MP;                                   // and its row group
 
     KParams kp0, kp1;
     load_kparams(kp0, sp0, os0, ls0, L, l);
@@ -253,6 +357,20 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
         }
     }
     for (int e = tid; e < MP * HLVAE_MAX_COMPS + 4 * HLVAE_MAX_COMPS + 8; e += PN_THREADS) zacc[e] = 0.0;
+    if (tid < HLVAE_MAX_COMPS) {
+        double o = 0.0, h = 0.0, i2 = 0.0, i3 = 0.0;
+        if (tid < sp0.ncomp) {
+            o = os0[(int64_t)tid * L + l];
+            const double e_ = ls0[(int64_t)tid * L + l];
+            i2 = 1.0 / (e_ * e_);
+            h = 0.5 * i2;
+            i3 = i2 / e_;
+        }
+        kps[tid] = o;
+        kps[HLVAE_MAX_COMPS + tid] = h;
+        kps[2 * HLVAE_MAX_COMPS + tid] = i2;
+        kps[3 * HLVAE_MAX_COMPS + tid] = i3;
+    }
     const double* Gl = G + (int64_t)l * M * M;
 
     double sacc[SI][SI][2];
@@ -264,6 +382,7 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
 
     if (tid == 0) meta[2] = s_begin;
     __syncthreads();
+    const double wm = ws[em];
 
     while (true) {
         // ---- P0: pack whole subjects into a panel of at most RP rows
@@ -289,6 +408,8 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
             meta[0] = ns;
             meta[2] = s;
         }
+        // clear the dense B^-1 panel while thread 0 packs
+        for (int e = tid; e < RP * LDB; e += PN_THREADS) Bp[e] = 0.0;
         __syncthreads();
         const int nsub = meta[0];
         if (nsub == 0) break;
@@ -304,34 +425,101 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
             grow[tid] = g;
             for (int q = 0; q < Q; q++) xs[tid * Q + q] = x[(int64_t)g * ldx + q];
             mus[tid] = (double)mu[(int64_t)g * ld_mu + l];
+        } else if (tid < RP) {
+            sub_of_row[tid] = -1;
         }
-        {
+        {   // scatter the subjects' B^-1 blocks (contiguous in global memory) onto the block diagonal
             const double* bsrc = binv + (int64_t)l * tt_total + tt_ptr[s_first];
             const int nb = sub_b0[nsub];
-            for (int e = tid; e < nb; e += PN_THREADS) Bs[e] = bsrc[e];
-        }
-        __syncthreads();
-
-        // ---- P1: K0xz rows (elbo_functions.py:147 / :222), zero padded to [R8][MP]
-        for (int e = tid; e < R8 * MP; e += PN_THREADS) {
-            int r = e / MP, m = e % MP;
-            double v = 0.0;
-            if (r < R && m < M) v = eval_additive(sp0, kp0, xs + r * Q, Zs + m, 1, MP);
-            Kb[r * LD + m] = v;
-        }
-        __syncthreads();
-
-        // ---- P2: V = B^-1 K0xz (block diagonal, :160 / :254); r = K0xz w - mu (:166 / :230)
-        for (int e = tid; e < R8 * MP; e += PN_THREADS) {
-            int r = e / MP, m = e % MP;
-            double v = 0.0;
-            if (r < R) {
-                int k = sub_of_row[r];
-                int rs = sub_r0[k], T = sub_r0[k + 1] - rs;
-                const double* brow = Bs + sub_b0[k] + (r - rs) * T;
-                for (int t = 0; t < T; t++) v = fma(brow[t], Kb[(rs + t) * LD + m], v);
+            int k = 0;
+            for (int e = tid; e < nb; e += PN_THREADS) {
+                while (e >= sub_b0[k + 1]) k++;
+                const int rs = sub_r0[k], T = sub_r0[k + 1] - rs;
+                const int le = e - sub_b0[k];
+                const int i = le / T, j = le - i * T;
+                Bp[(rs + i) * LDB + rs + j] = bsrc[e];
             }
-            Vb[r * LD + m] = v;
+        }
+        __syncthreads();
+
+        // ---- P1: K0xz rows (elbo_functions.py:147 / :222), zero padded to [R8][MP].
+        // Thread = (inducing point em, row group eg); components outermost so that the spec and the
+        // inducing point's covariates stay in registers and row covariates are warp broadcasts.
+        {
+            double kacc[RPT];
+#pragma unroll
+            for (int k = 0; k < RPT; k++) kacc[k] = 0.0;
+            if (em < M) {
+                for (int r = 0; r < sp0.ncomp; r++) {
+                    CompRegs c;
+                    c.load(sp0, r);
+                    const double zse = (c.se_col >= 0) ? Zs[c.se_col * MP + em] : 0.0;
+                    double zd[HLVAE_MAX_DISC];
+#pragma unroll
+                    for (int f = 0; f < HLVAE_MAX_DISC; f++) zd[f] = (f < c.ndisc) ? Zs[c.disc_col[f] * MP + em] : 0.0;
+                    const double hil2 = kps[HLVAE_MAX_COMPS + r], osr = kps[r];
+#pragma unroll
+                    for (int k = 0; k < RPT; k++) {
+                        const int row = eg + k * NGRP;
+                        if (row < R) {
+                            const double* xr = xs + row * Q;
+                            bool ok = true;
+#pragma unroll
+                            for (int f = 0; f < HLVAE_MAX_DISC; f++)
+                                if (f < c.ndisc) {
+                                    const double a = xr[c.disc_col[f]];
+                                    ok = ok && ((c.disc_kind[f] == HLVAE_KIND_CAT) ? (a == zd[f]) : (a + zd[f] == 2.0));
+                                }
+                            if (ok) {
+                                double v = 1.0;
+                                if (c.se_col >= 0) {
+                                    const double d = xr[c.se_col] - zse;
+                                    v = exp(-(d * d) * hil2);
+                                }
+                                kacc[k] = fma(osr, v, kacc[k]);
+                            }
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < RPT; k++) {
+                const int row = eg + k * NGRP;
+                if (row < R8) Kb[row * LD + em] = (row < R) ? kacc[k] : 0.0;
+            }
+        }
+        __syncthreads();
+
+        // ---- P2: V = B^-1 K0xz (block diagonal, :160 / :254) on the FP64 tensor pipe, k-range
+        // limited to the subjects a row tile touches; r = K0xz w - mu (:166 / :230)
+        {
+            const int ar = lane >> 2, ac = lane & 3;
+#pragma unroll
+            for (int tr = 0; tr < WR; tr++) {
+                const int rt = wi * WR + tr;
+                if (rt * 8 < R8) {
+                    double c[WC][2];
+#pragma unroll
+                    for (int t = 0; t < WC; t++) c[t][0] = c[t][1] = 0.0;
+                    if (rt * 8 < R) {
+                        const int rlast = min(rt * 8 + 7, R - 1);
+                        const int klo = sub_r0[sub_of_row[rt * 8]] & ~3;
+                        const int khi = (sub_r0[sub_of_row[rlast] + 1] + 3) & ~3;
+                        for (int k0 = klo; k0 < khi; k0 += 4) {
+                            const double a = Bp[(rt * 8 + ar) * LDB + k0 + ac];
+#pragma unroll
+                            for (int t = 0; t < WC; t++) {
+                                const double b = Kb[(k0 + ac) * LD + (wj * WC + t) * 8 + ar];
+                                dmma884(c[t][0], c[t][1], a, b);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int t = 0; t < WC; t++)
+                        *reinterpret_cast<double2*>(&Vb[(rt * 8 + ar) * LD + (wj * WC + t) * 8 + 2 * ac]) =
+                            make_double2(c[t][0], c[t][1]);
+                }
+            }
         }
         for (int r = warp; r < R; r += PN_THREADS / 32) {
             double a = 0.0;
@@ -343,18 +531,16 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
 
         // ---- P3a: rho = B^-1 r; A += r . rho (:167 / :256); dJ/dmu = -rho
         if (tid < R) {
-            int k = sub_of_row[tid];
-            int rs = sub_r0[k], T = sub_r0[k + 1] - rs;
-            const double* brow = Bs + sub_b0[k] + (tid - rs) * T;
+            const int k = sub_of_row[tid];
+            const int rs = sub_r0[k], re = sub_r0[k + 1];
+            const double* brow = Bp + tid * LDB;
             double a = 0.0;
-            for (int t = 0; t < T; t++) a = fma(brow[t], rv[rs + t], a);
+            for (int t = rs; t < re; t++) a = fma(brow[t], rv[t], a);
             rho[tid] = a;
             a_acc = fma(rv[tid], a, a_acc);
             g_mu[(int64_t)grow[tid] * L + l] = (TS)(-a * gscale);
         }
-        __syncthreads();
-
-        // ---- P3b: S += K0xz^T V on the FP64 tensor pipe (:161 / :254,266); p, gw
+        // ---- P3b: S += K0xz^T V on the FP64 tensor pipe (:161 / :254,266)
         {
             const int R4 = (R + 3) & ~3;
             const int kr = lane & 3, kc = lane >> 2;
@@ -370,19 +556,21 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
 #pragma unroll
                     for (int b = 0; b < SI; b++) dmma884(sacc[a][b][0], sacc[a][b][1], af[a], bf[b]);
             }
-            if (tid < MP) {
-                double pa = 0.0, ga = 0.0;
-                for (int r = 0; r < R; r++) {
-                    pa = fma(Vb[r * LD + tid], mus[r], pa);      // p (:188 / :265)
-                    ga = fma(Kb[r * LD + tid], rho[r], ga);      // dJ/dw
-                }
-                p_acc += pa;
-                gw_acc += ga;
+        }
+        __syncthreads();
+        // p (:188 / :265) and dJ/dw need rho: column sums over the panel rows
+        if (tid < MP) {
+            double pa = 0.0, ga = 0.0;
+            for (int r = 0; r < R; r++) {
+                pa = fma(Vb[r * LD + tid], mus[r], pa);
+                ga = fma(Kb[r * LD + tid], rho[r], ga);
             }
+            p_acc += pa;
+            gw_acc += ga;
         }
         __syncthreads();
 
-        // ---- P4: W = V G  (dJ/dS = G / 2 applied on both sides -> dJ/dK0xz = W + rho w^T)
+        // ---- P4: W = V G  (dJ/dS = G / 2 applied on both sides -> dJ/dK0xz = W + rho w^T), into Kb
         {
             const int ar = lane >> 2, ac = lane & 3;
 #pragma unroll
@@ -393,7 +581,7 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
 #pragma unroll
                     for (int t = 0; t < WC; t++) c[t][0] = c[t][1] = 0.0;
                     for (int k0 = 0; k0 < MP; k0 += 4) {
-                        double a = Vb[(rt * 8 + ar) * LD + k0 + ac];
+                        const double a = Vb[(rt * 8 + ar) * LD + k0 + ac];
 #pragma unroll
                         for (int t = 0; t < WC; t++) {
                             const int col = (wj * WC + t) * 8 + ar;   // B frag: row = k0 + lane%4, col = lane/4
@@ -406,52 +594,94 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
                             dmma884(c[t][0], c[t][1], a, b);
                         }
                     }
-                    // all warps finished reading Kb as K0xz at the barrier above
 #pragma unroll
-                    for (int t = 0; t < WC; t++) {
-                        double2 v2 = make_double2(c[t][0], c[t][1]);
-                        *reinterpret_cast<double2*>(&Kb[(rt * 8 + ar) * LD + (wj * WC + t) * 8 + 2 * ac]) = v2;
-                    }
+                    for (int t = 0; t < WC; t++)
+                        *reinterpret_cast<double2*>(&Kb[(rt * 8 + ar) * LD + (wj * WC + t) * 8 + 2 * ac]) =
+                            make_double2(c[t][0], c[t][1]);
                 }
             }
         }
         __syncthreads();
 
-        // ---- P5: dJ/dB_s (K0xz part) = -1/2 (rho rho^T + W V^T) -> Bs ; dJ/dK0xz -> hyper-parameters and Z
+        // ---- P5a: dJ/dB_s (K0xz part) = -1/2 (rho rho^T + W V^T) for the 8x8 tiles that meet the block
+        // diagonal, on the FP64 tensor pipe, written over the dense panel Bp
         {
-            const int nb = sub_b0[nsub];
-            for (int e = tid; e < nb; e += PN_THREADS) {
-                int k = 0;
-                while (e >= sub_b0[k + 1]) k++;
-                int rs = sub_r0[k], T = sub_r0[k + 1] - rs;
-                int le = e - sub_b0[k];
-                int i = le / T, j = le % T;
-                double a = rho[rs + i] * rho[rs + j];
-                const double* wr = Kb + (rs + i) * LD;
-                const double* vr = Vb + (rs + j) * LD;
-                for (int m = 0; m < MP; m++) a = fma(wr[m], vr[m], a);
-                Bs[e] = -0.5 * a;
-            }
-            double gos[HLVAE_MAX_COMPS], gls[HLVAE_MAX_COMPS], gxb[HLVAE_MAX_COMPS];
-#pragma unroll
-            for (int r = 0; r < HLVAE_MAX_COMPS; r++) gos[r] = gls[r] = gxb[r] = 0.0;
-            const int m = tid % MP;   // PN_THREADS is a multiple of MP: one column per thread
-            if (m < M) {
-                for (int r = tid / MP; r < R; r += PN_THREADS / MP) {
-                    double g = Kb[r * LD + m] + rho[r] * ws[m];
-                    accum_grads<true>(sp0, kp0, xs + r * Q, Zs + m, g, gos, gls, gxb, 1, MP);
-                }
-            }
-#pragma unroll
-            for (int r = 0; r < HLVAE_MAX_COMPS; r++) {
-                if (r < sp0.ncomp) {
-                    double a = warp_sum(gos[r]), b = warp_sum(gls[r]);
-                    if (lane == 0) {
-                        atomicAdd(&hyp[r], a);
-                        atomicAdd(&hyp[HLVAE_MAX_COMPS + r], b);
+            const int nrt = R8 / 8;
+            const int ar = lane >> 2, ac = lane & 3;
+            for (int tp = warp; tp < nrt * nrt; tp += PN_THREADS / 32) {
+                const int rt = tp / nrt, ct = tp - rt * nrt;
+                const int rl = min(rt * 8 + 7, R - 1), cl = min(ct * 8 + 7, R - 1);
+                const int s_r0 = sub_of_row[rt * 8], s_r1 = sub_of_row[rl];
+                const int s_c0 = sub_of_row[ct * 8], s_c1 = sub_of_row[cl];
+                if (s_r0 <= s_c1 && s_c0 <= s_r1) {
+                    double c0 = 0.0, c1 = 0.0;
+                    for (int m0 = 0; m0 < MP; m0 += 4) {
+                        const double a = Kb[(rt * 8 + ar) * LD + m0 + ac];
+                        const double b = Vb[(ct * 8 + ar) * LD + m0 + ac];
+                        dmma884(c0, c1, a, b);
                     }
-                    if (m < M && sp0.comp[r].se_col >= 0 && gxb[r] != 0.0) atomicAdd(&zacc[m * HLVAE_MAX_COMPS + r], gxb[r]);
+                    const int i = rt * 8 + ar, j = ct * 8 + 2 * ac;
+                    if (i < R) {
+                        const double ri = rho[i];
+                        if (j < R) Bp[i * LDB + j] = -0.5 * (c0 + ri * rho[j]);
+                        if (j + 1 < R) Bp[i * LDB + j + 1] = -0.5 * (c1 + ri * rho[j + 1]);
+                    }
                 }
+            }
+        }
+        // ---- P5b: dJ/dK0xz = W + rho w^T, contracted with dK0xz/d{outputscale, lengthscale, Z}
+        {
+            double gk[RPT];
+#pragma unroll
+            for (int k = 0; k < RPT; k++) {
+                const int row = eg + k * NGRP;
+                gk[k] = (row < R && em < M) ? Kb[row * LD + em] + rho[row] * wm : 0.0;
+            }
+            for (int r = 0; r < sp0.ncomp; r++) {
+                CompRegs c;
+                c.load(sp0, r);
+                const double zse = (c.se_col >= 0) ? Zs[c.se_col * MP + em] : 0.0;
+                double zd[HLVAE_MAX_DISC];
+#pragma unroll
+                for (int f = 0; f < HLVAE_MAX_DISC; f++) zd[f] = (f < c.ndisc) ? Zs[c.disc_col[f] * MP + em] : 0.0;
+                const double osr = kps[r], hil2 = kps[HLVAE_MAX_COMPS + r], il2 = kps[2 * HLVAE_MAX_COMPS + r],
+                             il3 = kps[3 * HLVAE_MAX_COMPS + r];
+                double gos = 0.0, gls = 0.0, gz = 0.0;
+                if (em < M) {
+#pragma unroll
+                    for (int k = 0; k < RPT; k++) {
+                        const int row = eg + k * NGRP;
+                        if (row < R) {
+                            const double* xr = xs + row * Q;
+                            bool ok = true;
+#pragma unroll
+                            for (int f = 0; f < HLVAE_MAX_DISC; f++)
+                                if (f < c.ndisc) {
+                                    const double a = xr[c.disc_col[f]];
+                                    ok = ok && ((c.disc_kind[f] == HLVAE_KIND_CAT) ? (a == zd[f]) : (a + zd[f] == 2.0));
+                                }
+                            if (ok) {
+                                double v = 1.0, d = 0.0;
+                                if (c.se_col >= 0) {
+                                    d = xr[c.se_col] - zse;
+                                    v = exp(-(d * d) * hil2);
+                                }
+                                const double gkv = gk[k] * v;
+                                gos += gkv;
+                                const double t = gkv * osr * d;
+                                gls = fma(t * d, il3, gls);
+                                gz = fma(t, il2, gz);
+                            }
+                        }
+                    }
+                }
+                gos = warp_sum(gos);
+                gls = warp_sum(gls);
+                if (lane == 0) {
+                    atomicAdd(&hyp[r], gos);
+                    atomicAdd(&hyp[HLVAE_MAX_COMPS + r], gls);
+                }
+                if (c.se_col >= 0 && gz != 0.0) atomicAdd(&zacc[em * HLVAE_MAX_COMPS + r], gz);
             }
         }
         __syncthreads();
@@ -462,13 +692,14 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
 #pragma unroll
             for (int r = 0; r < HLVAE_MAX_COMPS; r++) gos[r] = gls[r] = dummy[r] = 0.0;
             const int nb = sub_b0[nsub];
+            int k = 0;
             for (int e = tid; e < nb; e += PN_THREADS) {
-                int k = 0;
                 while (e >= sub_b0[k + 1]) k++;
-                int rs = sub_r0[k], T = sub_r0[k + 1] - rs;
-                int le = e - sub_b0[k];
-                int i = le / T, j = le % T;
-                accum_grads<false>(sp1, kp1, xs + (rs + i) * Q, xs + (rs + j) * Q, Bs[e], gos, gls, dummy);
+                const int rs = sub_r0[k], T = sub_r0[k + 1] - rs;
+                const int le = e - sub_b0[k];
+                const int i = le / T, j = le - i * T;
+                accum_grads<false>(sp1, kp1, xs + (rs + i) * Q, xs + (rs + j) * Q, Bp[(rs + i) * LDB + rs + j], gos, gls,
+                                   dummy);
             }
 #pragma unroll
             for (int r = 0; r < HLVAE_MAX_COMPS; r++) {
