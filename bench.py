@@ -61,7 +61,7 @@ def parse():
 # ------------------------------------------------------------------------------------------
 # CPU arm: oracle port of the reference path on the host cores
 # ------------------------------------------------------------------------------------------
-def cpu_reference_arm(steps, warmup, sample_subjects=20, budget_s=25.0):
+def cpu_reference_arm(steps, warmup, sample_subjects=100, budget_s=25.0):
     """Times oracle.elbo_path_step (float64 PyTorch restatement of training.py:82-137 for this path)
     on a bounded sample: `sample_subjects` x T rows of the same workload.  Returns steps/s scaled
     to the 16000-row step (cost is linear in rows; the replicated M x M part is not scaled down, so
@@ -128,38 +128,38 @@ def run_reference(args):
 # GPU arm
 # ------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons DURING the timed region, through NVML (10 ms period; an
+    nvidia-smi subprocess per sample would be slower than the whole timed region)."""
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.sm, self.mx, self.reasons, self.stop_flag, self.err = index, [], None, set(), False, None
 
     def run(self):
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([c.strip() for c in out.strip().split(",")])
-            except Exception:
-                pass
-            time.sleep(0.1)
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.index]) if vis and vis.split(",")[0].isdigit() else self.index
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            while not self.stop_flag:
+                self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                bits = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                for n, b in self.REASONS.items():
+                    if bits & b:
+                        self.reasons.add(n)
+                time.sleep(0.01)
+        except Exception as e:      # keep the benchmark alive; the JSON line then shows samples = 0
+            self.err = repr(e)
 
     def summary(self):
-        sm, mx, reasons = [], 0.0, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                mx = max(mx, float(r[1]))
-                for n, v in zip(names, r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
-            except Exception:
-                continue
-        return dict(sm_mhz=(pystat.median(sm) if sm else None), sm_max_mhz=(mx or None), reasons=sorted(reasons),
-                    samples=len(sm))
+        d = dict(sm_mhz=(pystat.median(self.sm) if self.sm else None), sm_max_mhz=self.mx, reasons=sorted(self.reasons),
+                 samples=len(self.sm))
+        if self.err:
+            d["error"] = self.err
+        return d
 
 
 def measured_peaks():
@@ -205,7 +205,7 @@ def build_gpu_state(dev, n_subj, rank, seed=0):
     lik.raw_noise.requires_grad = False
     lay = loglik.VarLayout(synth.HEALTHMNIST_D4_TYPES, dev)
     N_b = x.shape[0]
-    data, mask = synth.device_likelihood_batch(lay, N_b, dev, gen_dev, dtype=torch.float32)
+    data, mask = synth.device_likelihood_batch(lay, N_b, dev, gen_dev, dtype=torch.uint8)   # pixel values / one-hot codes: exact in uint8
     theta = torch.randn(N_b, lay.P_theta, device=dev, generator=gen_dev, dtype=torch.float32)
     mu = torch.randn(N_b, L, device=dev, generator=gen_dev, dtype=torch.float32)
     lv = -3.0 * torch.rand(N_b, L, device=dev, generator=gen_dev, dtype=torch.float32)
@@ -230,7 +230,7 @@ def elbo_step(s, world, host=None):
     P_b = s["n_subj"] * world
     vparam = s["lay"].vparam(log_vy_real=s["log_vy_real"], conv=True)
     out = loglik.fused_loglik(s["lay"], s["data"], s["mask"], s["theta"], vparam, monitor=True)
-    nll = -out["log_p_x"].sum(dtype=torch.float64) * (P_TOTAL / P_b)                        # training.py:83,104,122
+    nll = -out["log_p_x_sum"] * (P_TOTAL / P_b)                                             # training.py:83,104,122
     kld, gm, gH = elbo.minibatch_KLD_upper_bound_iter(s["k0"], s["k1"], s["lik"], L, s["m"], s["H"], s["x"], s["mu"],
                                                       s["lv"], s["z"], P_TOTAL, P_b, N_TOTAL, True, 2, EPS,
                                                       layout=s["layout"])                     # training.py:110-113
@@ -249,9 +249,9 @@ def algorithmic_work(n_rows, n_subj):
     """Algorithmic work per launch (DESIGN.md section 'Kernels and rooflines')."""
     E_x = P_th = 5184
     D = 1296
-    sz = 4                                   # float32 storage of streamed arrays
-    ALGO["hlvae_loglik_fwd"] = ("hbm", n_rows * (sz * (E_x + P_th) + D + sz * (5 * D + P_th)))
-    ALGO["hlvae_loglik_bwd"] = ("hbm", n_rows * (sz * (E_x + P_th) + D + sz * D + sz * P_th))
+    sz = 4                                   # float32 storage of theta and outputs; data and mask are uint8
+    ALGO["hlvae_loglik_fwd"] = ("hbm", n_rows * (E_x + sz * P_th + D + sz * (5 * D + P_th)))
+    ALGO["hlvae_loglik_bwd"] = ("hbm", n_rows * (E_x + sz * P_th + D + sz * P_th))   # upstream gradient is a device scalar
     # FP64 contraction flops: S = K^T V and W = V G (2 L N M^2 each) + B^-1 K and W V^T (2 L N T M each)
     ALGO["hlvae_kl_panel"] = ("tensor", 2.0 * L * n_rows * M * M * 2 + 2.0 * L * n_rows * T * M * 2)
     ALGO["hlvae_kl_subject"] = ("fp64", L * n_subj * (T ** 3 / 3 + T ** 3 / 3 + T ** 3 / 3 + 2 * 2.0 * T ** 3))
@@ -360,16 +360,16 @@ def run_gpu(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference_arm(steps=8, warmup=1, budget_s=20.0)
+        r = cpu_reference_arm(steps=10, warmup=1, budget_s=20.0)
         cpu = dict(value=r["value"], unit="steps/s", cores=r["cores"], kind="port", sample=r["sample"])
 
     if rank == 0:
         line = dict(metric="ELBO train steps/sec (fwd+bwd)", value=value, unit="steps/s", n_gpus=world,
                     steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms_per_step, higher_is_better=True,
-                    scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+                    scaling="weak", vs_baseline=None, dtype="f64 (KL bound) + f32 (likelihoods)", data="synthetic",
                     config=dict(workload=WORKLOAD, rows_per_rank=n_rows, global_rows_per_step=n_rows * world,
-                                storage="f32 streamed arrays (data, theta, mu, log_v), f64 arithmetic and M x M stage",
-                                l2="inputs larger than L2 (data + theta = 664 MB per step)",
+                                storage="theta, mu, log_v and outputs f32; data and mask u8; likelihood arithmetic f32 (SFU) with exact f64 argmax re-evaluation; KL stream and M x M stage f64",
+                                l2="inputs larger than L2 (data + theta = 415 MB per step, 126 MB L2)",
                                 parallelism=f"dp{world}: subjects sharded, one all-reduce of accumulators" if world > 1 else "single GPU"),
                     clocks=sampler.summary(), e2e=e2e, gpu_launches=launches, roofline=roof, cpu_baseline=cpu,
                     kernels=kern, fp64_peak_tflops=fp64_peak)

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libhlvae_b200.so")
 
 MAX_COMPS, MAX_DISC, MAX_Q, TMAX, MAX_CLASS = 8, 3, 8, 32, 16
-F32, F64 = 0, 1
+F32, F64, U8 = 0, 1, 2
 KIND_CAT, KIND_BIN = 1, 2
 VAR_KINDS = {"real": 0, "pos": 1, "count": 2, "cat": 3, "ordinal": 4}
 ACC_NAMES = ("S", "p", "gw", "scal", "gZ", "gos0", "gls0", "gos1", "gls1", "total")
@@ -49,8 +49,8 @@ _SIGS = {
     "hlvae_mxm_pre": ([C.POINTER(KSpec), _P, _P, _I, _I, _I, _P, _D, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P], _I),
     "hlvae_mxm_post": ([_I, _I, _D, _D, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P], _I),
     "hlvae_natgrad_update": ([_I, _I, _D, _P, _P, _P, _P, _P, _P, _P, _P, _P], _I),
-    "hlvae_loglik_fwd": ([_L, _I, _L, _L, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P], _I),
-    "hlvae_loglik_bwd": ([_L, _I, _L, _L, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _D, _P, _P, _P], _I),
+    "hlvae_loglik_fwd": ([_L, _I, _L, _L, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P], _I),
+    "hlvae_loglik_bwd": ([_L, _I, _L, _L, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P], _I),
     "hlvae_statistics": ([_L, _I, _L, _P, _P, _P, _P, _P, _I, _P, _P, _P], _I),
     "hlvae_discrete_transform": ([_L, _I, _L, _P, _P, _P, _P, _I, _P, _P], _I),
 }

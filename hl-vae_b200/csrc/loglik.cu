@@ -1,359 +1,729 @@
 // Fused masked heterogeneous log-likelihood: HLVAE.loglik_and_reconstruction
 // (HLVAE.py:381-414) over the per-type functions of HL_VAE/loglik.py:27-213, plus
 // read_functions.statistics (:268-302) and discrete_variables_transformation (:221-235).
-// One thread per (row, variable); consecutive threads take consecutive variables of a row, so
-// a warp touches one contiguous span of data / theta / params.  Arithmetic is float64 whatever
-// the storage type, which also makes the categorical / ordinal argmax decisions reproduce the
-// float64 reference (first index wins ties, as torch.argmax).
+//
+// Layout of the work: a CTA owns a TILE of consecutive variables (<= LL_THREADS, one per
+// thread) and walks a stripe of row batches (LL_ROWS rows at a time).  Per batch it stages the
+// tile's contiguous span of `theta` (cp.async, no register round trip) and `data` of every row
+// of the batch into shared memory - one coalesced burst that keeps tens of KB in flight per CTA -
+// then every thread evaluates its variable for each row from shared memory, the per-class
+// outputs (params / g_theta) go back through shared memory as coalesced spans, and the [N, D]
+// outputs are written directly (consecutive threads = consecutive columns).  Per-variable
+// constants (variances, normalisation) are computed once per thread in float64 and reused for
+// every row of the stripe.
+//
+// Arithmetic type R follows the storage type of theta: float64 storage -> float64 math (the
+// drop-in case, reference tensors are float64); float32 storage -> float32 math on the SFU
+// (ex2/lg2.approx), which makes the kernel HBM-bound.  In the float32 path the categorical /
+// ordinal argmax imputations (which must be bit-exact against the float64 reference) re-evaluate
+// the variable in float64 whenever the float32 decision is not provably the float64 one.
 #include "common.cuh"
 
 using namespace hlvae;
 
 namespace {
 
-constexpr int LL_THREADS = 256;
+constexpr int LL_THREADS = 128;                          // threads per CTA = max variables per tile
+constexpr int LL_ROWS = 8;                               // rows staged per batch
 constexpr double LOG_2PI = 1.8378770664093454835606594728112;
 
-__device__ __forceinline__ double softplus_d(double x) {
-    // torch.nn.functional.softplus (beta=1, threshold=20)
-    return x > 20.0 ? x : log1p(exp(x));
-}
-__device__ __forceinline__ double sigmoid_d(double x) { return 1.0 / (1.0 + exp(-x)); }
-// derivative of softplus_d (1 above the linear threshold, as torch's softplus backward)
-__device__ __forceinline__ double dsoftplus_d(double x) { return x > 20.0 ? 1.0 : sigmoid_d(x); }
+// ------------------------------------------------------------------------------------
+template <typename R> struct Mth;
+template <> struct Mth<double> {
+    static __device__ __forceinline__ double ex(double x) { return exp(x); }
+    static __device__ __forceinline__ double lg(double x) { return log(x); }
+    static __device__ __forceinline__ double lg1p(double x) { return log1p(x); }
+    static __device__ __forceinline__ double exm1(double x) { return expm1(x); }
+    static __device__ __forceinline__ double lgam(double x) { return lgamma(x); }
+    static __device__ __forceinline__ double rcp(double x) { return 1.0 / x; }
+};
+template <> struct Mth<float> {
+    static __device__ __forceinline__ float ex(float x) { return __expf(x); }
+    static __device__ __forceinline__ float lg(float x) { return __logf(x); }
+    static __device__ __forceinline__ float lg1p(float x) { return log1pf(x); }
+    static __device__ __forceinline__ float exm1(float x) { return expm1f(x); }
+    static __device__ __forceinline__ float lgam(float x) { return lgammaf(x); }
+    static __device__ __forceinline__ float rcp(float x) { return __fdividef(1.0f, x); }
+};
 
-template <typename TM>
-__device__ __forceinline__ double load_mask(const void* mask, int64_t i) {
-    return (double)reinterpret_cast<const TM*>(mask)[i];
+// torch.nn.functional.softplus (beta = 1, threshold = 20) and its derivative
+template <typename R> __device__ __forceinline__ R softplus_(R x) {
+    return x > R(20) ? x : Mth<R>::lg1p(Mth<R>::ex(x));
 }
+template <typename R> __device__ __forceinline__ R sigmoid_(R x) { return Mth<R>::rcp(R(1) + Mth<R>::ex(-x)); }
+template <typename R> __device__ __forceinline__ R dsoftplus_(R x) { return x > R(20) ? R(1) : sigmoid_<R>(x); }
+template <typename R> __device__ __forceinline__ R clamp_(R x, R lo, R hi) { return fmin(fmax(x, lo), hi); }
 
-template <typename TS>
-__device__ __forceinline__ void st(void* p, int64_t i, double v) {
+template <typename T> __device__ __forceinline__ double ldd(const void* p, int64_t i) {
+    return (double)reinterpret_cast<const T*>(p)[i];
+}
+template <typename TS> __device__ __forceinline__ void st(void* p, int64_t i, double v) {
     if (p) reinterpret_cast<TS*>(p)[i] = (TS)v;
 }
 
+// Per-variable constants, computed once per thread (float64, then rounded to R).
+template <typename R> struct VarC {
+    int kind, C, xo, po;      // type, classes, offsets of the variable inside the staged spans
+    R nm, snv, ivar, lconst, idiv, ev, sg8;
+    bool ok;
+};
+
+template <typename R>
+__device__ __forceinline__ VarC<R> load_var(int d, int D, bool active, const int32_t* __restrict__ var_kind,
+                                            const int32_t* __restrict__ var_nclass,
+                                            const int32_t* __restrict__ var_dcol,
+                                            const int32_t* __restrict__ var_pcol, const double* __restrict__ vparam,
+                                            int xs0, int ps0, int cap) {
+    VarC<R> v;
+    v.kind = -1; v.C = 1; v.xo = 0; v.po = 0; v.ok = false;
+    v.nm = v.snv = v.ivar = v.lconst = v.idiv = v.ev = v.sg8 = R(0);
+    if (!active) return v;
+    v.kind = var_kind[d];
+    v.C = var_nclass[d];
+    v.xo = var_dcol[d] - xs0;
+    v.po = var_pcol[d] - ps0;
+    // variables of a tile must be packed in order (header: "packed layout"); otherwise flag it
+    v.ok = v.C >= 1 && v.C <= HLVAE_MAX_CLASS && v.xo >= 0 && v.po >= 0 && v.xo + v.C <= cap && v.po + v.C <= cap;
+    const double nm = vparam[d], nv = vparam[D + d], e = vparam[2 * D + d], div = vparam[3 * D + d];
+    v.nm = (R)nm;
+    v.snv = (R)sqrt(nv);
+    v.idiv = (R)(1.0 / div);
+    if (v.kind == HLVAE_VAR_REAL) {
+        const double t8 = e + 8.0;
+        const double sp = t8 > 20.0 ? t8 : log1p(exp(t8));
+        const double var = nv * exp(-8.0 + sp);                              // loglik.py:51-52,56
+        v.ivar = (R)(1.0 / var);
+        v.lconst = (R)(0.5 * LOG_2PI + 0.5 * log(var));                      // :58
+        v.sg8 = (R)(t8 > 20.0 ? 1.0 : 1.0 / (1.0 + exp(-t8)));
+    } else if (v.kind == HLVAE_VAR_POS) {
+        const double var = nv * exp(e);                                      // :100
+        v.ivar = (R)(1.0 / var);
+        v.lconst = (R)(0.5 * log(2.0 * 3.14159265358979323846 * var));       // :102
+        v.ev = (R)exp(e);                                                    // read_functions.py:284
+    }
+    return v;
+}
+
 // ------------------------------------------------------------------------------------
-template <typename TS, typename TM>
-__global__ void __launch_bounds__(LL_THREADS)
-loglik_fwd_k(int64_t N, int D, int64_t ld_data, int64_t ld_theta, const int32_t* __restrict__ var_kind,
-             const int32_t* __restrict__ var_nclass, const int32_t* __restrict__ var_dcol,
-             const int32_t* __restrict__ var_pcol, const double* __restrict__ vparam, const TS* __restrict__ data,
-             const TS* __restrict__ theta, const void* __restrict__ mask, void* __restrict__ log_p_x,
-             void* __restrict__ log_p_x_missing, void* __restrict__ params, void* __restrict__ recon_mean,
-             void* __restrict__ recon_mode, void* __restrict__ data_tr, double* __restrict__ ll_total) {
-    __shared__ double red[LL_THREADS / 32];
-    const int64_t idx = (int64_t)blockIdx.x * LL_THREADS + threadIdx.x;
-    double lp_obs = 0.0;
-    if (idx < N * D) {
-        const int64_t n = idx / D;
-        const int d = (int)(idx % D);
-        const int kind = var_kind[d];
-        const int C = var_nclass[d];
-        const TS* x = data + n * ld_data + var_dcol[d];
-        const TS* th = theta + n * ld_theta + var_pcol[d];
-        const int64_t pbase = n * ld_theta + var_pcol[d];
-        const double m = load_mask<TM>(mask, n * D + d);
-        double lp = 0.0, rmean = 0.0, rmode = 0.0, dtr = 0.0;
-        if (kind == HLVAE_VAR_REAL) {
-            // loglik.py:27-70 (extra_params path)
-            const double nm = vparam[d], nv = vparam[D + d], e = vparam[2 * D + d], div = vparam[3 * D + d];
-            const double xv = (double)x[0] / div;                       // HLVAE.py:393-394
-            const double lvy = -8.0 + softplus_d(e + 8.0);              // :51
-            const double var = nv * exp(lvy);                            // :52,56
-            const double mean = sqrt(nv) * (double)th[0] + nm;           // :55
-            const double r = xv - mean;
-            lp = -0.5 * r * r / var - 0.5 * LOG_2PI - 0.5 * log(var);    // :58
-            st<TS>(params, pbase, mean);
-            rmean = mean; rmode = mean;                                  // read_functions.py:275-278
-            dtr = (double)x[0];                                          // read_functions.py:233
-        } else if (kind == HLVAE_VAR_POS) {
-            // loglik.py:73-121
-            const double nm = vparam[d], nv = vparam[D + d], e = vparam[2 * D + d];
-            const double ld = log(1.0 + (double)x[0]);                   // :84
-            const double mean = sqrt(nv) * (double)th[0] + nm;           // :96
-            const double var = nv * exp(e);                              // :100
-            const double r = ld - mean;
-            lp = -0.5 * r * r / var - 0.5 * log(2.0 * 3.14159265358979323846 * var) - ld;   // :102
-            st<TS>(params, pbase, mean);
-            const double v = exp(e);                                     // read_functions.py:284
-            rmean = exp(mean + 0.5 * v) - 1.0;                           // :287
-            rmode = exp(mean - v) - 1.0;                                 // :289
-            dtr = (double)x[0];
-        } else if (kind == HLVAE_VAR_COUNT) {
-            // loglik.py:191-213
-            double lam = softplus_d((double)th[0]);
-            lam = fmin(fmax(lam, 1e-6), 1e20);                           // :203
-            const double xv = (double)x[0];
-            lp = xv * log(lam) - lam - lgamma(xv + 1.0);                 // Poisson.log_prob
-            st<TS>(params, pbase, lam);
-            rmean = lam; rmode = floor(lam);                             // read_functions.py:293-295
-            dtr = xv;
-        } else if (kind == HLVAE_VAR_CAT) {
-            // loglik.py:124-146
-            double t[HLVAE_MAX_CLASS];
-            double mx = -INFINITY;
-#pragma unroll 4
-            for (int c = 0; c < C; c++) { t[c] = (double)th[c]; mx = fmax(mx, t[c]); }
-            double se = 0.0;
-            for (int c = 0; c < C; c++) se += exp(t[c] - mx);
-            const double lse = mx + log(se);                             // torch.logsumexp
-            // params = theta - lse (:134); log_p_x uses log_softmax of that again (:135)
-            double se2 = 0.0, mx2 = -INFINITY;
-            for (int c = 0; c < C; c++) { t[c] = t[c] - lse; mx2 = fmax(mx2, t[c]); }
-            for (int c = 0; c < C; c++) se2 += exp(t[c] - mx2);
-            const double lse2 = mx2 + log(se2);
-            int am = 0, dam = 0;
-            double best = t[0], dbest = (double)x[0];
-            for (int c = 0; c < C; c++) {
-                const double xv = (double)x[c];
-                lp += xv * (t[c] - lse2);
-                st<TS>(params, pbase + c, t[c]);
-                if (t[c] > best) { best = t[c]; am = c; }                // argmax, first index on ties
-                if (xv > dbest) { dbest = xv; dam = c; }
-            }
-            rmean = am; rmode = am;                                      // read_functions.py:296-302
-            dtr = dam;                                                   // read_functions.py:226-227
+// Exact (float64) argmax decisions for the float32 path: same operation order as the float64
+// reference (torch.logsumexp, then theta - lse; first index wins ties).
+__device__ __noinline__ int cat_argmax_f64(const float* t, int C) {
+    double mx = -INFINITY;
+    for (int c = 0; c < C; c++) mx = fmax(mx, (double)t[c]);
+    double se = 0.0;
+    for (int c = 0; c < C; c++) se += exp((double)t[c] - mx);
+    const double lse = mx + log(se);
+    int am = 0;
+    double best = (double)t[0] - lse;
+    for (int c = 1; c < C; c++) {
+        const double v = (double)t[c] - lse;
+        if (v > best) { best = v; am = c; }
+    }
+    return am;
+}
+
+__device__ __forceinline__ double softplus_d(double x) { return x > 20.0 ? x : log1p(exp(x)); }
+
+// ordinal class probabilities exactly as loglik.py:163-178 (float64); returns the argmax
+template <typename TI>
+__device__ __forceinline__ int ordinal_probs_f64(const TI* th, int C, double* p, double& tot_out) {
+    const double eps = 1e-6;
+    const double loc = softplus_d((double)th[C - 1]);                        // :163
+    double cum = 0.0, prev = 0.0, tot = 0.0;
+    for (int c = 0; c < C; c++) {
+        double sg = 1.0;
+        if (c < C - 1) {
+            cum += fmin(fmax(softplus_d((double)th[c]), eps), 1e20);         // :164
+            sg = 1.0 / (1.0 + exp(-(cum - loc)));                            // :165
+        }
+        p[c] = fmin(fmax(sg - prev, eps), 1.0);                              // :166-169
+        prev = sg;
+        tot += p[c];
+    }
+    int am = 0;
+    double best = -1.0;
+    for (int c = 0; c < C; c++) {
+        const double ph = p[c] / tot;                                        // :178
+        if (ph > best) { best = ph; am = c; }
+    }
+    tot_out = tot;
+    return am;
+}
+
+__device__ __noinline__ int ord_argmax_f64(const float* th, int C) {
+    double p[HLVAE_MAX_CLASS], tot;
+    return ordinal_probs_f64<float>(th, C, p, tot);
+}
+
+// ------------------------------------------------------------------------------------
+// One variable, forward.  x / t point into the staged spans (t is overwritten with `params`).
+template <typename R, typename XT>
+__device__ __forceinline__ void var_forward(const VarC<R>& v, const XT* __restrict__ x_, R* __restrict__ t, bool observed,
+                                            R& lp, R& rmean, R& rmode, R& dtr) {
+    struct { const XT* p; __device__ __forceinline__ R operator[](int c) const { return (R)p[c]; } } x{x_};
+    const int C = v.C;
+    if (v.kind == HLVAE_VAR_REAL) {                                          // loglik.py:27-70
+        const R xv = x[0] * v.idiv;                                          // HLVAE.py:393-394
+        const R mean = v.snv * t[0] + v.nm;                                  // :55
+        const R r = xv - mean;
+        lp = R(-0.5) * r * r * v.ivar - v.lconst;                            // :58
+        t[0] = mean;
+        rmean = mean; rmode = mean;                                          // read_functions.py:275-278
+        dtr = x[0];                                                          // read_functions.py:233
+    } else if (v.kind == HLVAE_VAR_POS) {                                    // loglik.py:73-121
+        const R ld = Mth<R>::lg1p(x[0]);                                     // :84
+        const R mean = v.snv * t[0] + v.nm;                                  // :96
+        const R r = ld - mean;
+        lp = R(-0.5) * r * r * v.ivar - v.lconst - ld;                       // :102
+        t[0] = mean;
+        rmean = Mth<R>::ex(mean + R(0.5) * v.ev) - R(1);                     // read_functions.py:287
+        rmode = Mth<R>::ex(mean - v.ev) - R(1);                              // :289
+        dtr = x[0];
+    } else if (v.kind == HLVAE_VAR_COUNT) {                                  // loglik.py:191-213
+        const R lam = clamp_<R>(softplus_<R>(t[0]), R(1e-6), R(1e20));       // :203
+        const R xv = x[0];
+        lp = xv * Mth<R>::lg(lam) - lam - Mth<R>::lgam(xv + R(1));           // Poisson.log_prob
+        t[0] = lam;
+        rmean = lam; rmode = floor(lam);                                     // read_functions.py:293-295
+        dtr = xv;
+    } else if (v.kind == HLVAE_VAR_CAT) {                                    // loglik.py:124-146
+        R mx = t[0], second = -INFINITY;                                     // second: largest logit strictly below mx
+        int am = 0;
+        for (int c = 1; c < C; c++) {
+            const R tc = t[c];
+            if (tc > mx) { second = mx; mx = tc; am = c; }                   // first index wins ties
+            else if (tc < mx) second = fmax(second, tc);
+        }
+        R se = R(0);
+        for (int c = 0; c < C; c++) se += Mth<R>::ex(t[c] - mx);
+        const R lse = mx + Mth<R>::lg(se);                                   // torch.logsumexp
+        if constexpr (sizeof(R) == 4) {
+            // The reference takes argmax of fl64(theta_c - lse); it can differ from argmax(theta) only when
+            // two DISTINCT logits collapse onto one double after the subtraction.
+            const R gap = mx - second;
+            if (gap > R(0) && gap < R(1e-13) * (fabs(mx) + fabs(lse)) + R(1e-37))
+                am = cat_argmax_f64(reinterpret_cast<const float*>(t), C);
         } else {
-            // ordinal, loglik.py:149-188
-            const double eps = 1e-6;
-            const double loc = softplus_d((double)th[C - 1]);            // :163
-            double p[HLVAE_MAX_CLASS];
-            double cum = 0.0, prev = 0.0, tot = 0.0;
-            int vals = 0;
-            for (int c = 0; c < C; c++) {
-                double sg = 1.0;
-                if (c < C - 1) {
-                    cum += fmin(fmax(softplus_d((double)th[c]), eps), 1e20);   // :164
-                    sg = sigmoid_d(cum - loc);                                    // :165
-                }
-                p[c] = fmin(fmax(sg - prev, eps), 1.0);                          // :166-169
-                prev = sg;
-                tot += p[c];
-                vals += (int)(double)x[c];                                       // :172
+            am = 0;
+            R best = t[0] - lse;
+            for (int c = 1; c < C; c++) {
+                const R val = t[c] - lse;
+                if (val > best) { best = val; am = c; }
             }
-            if (m == 0.0) vals = 1;                                              // :173
-            int am = 0;
-            double best = -1.0, lsum = 0.0, py = 0.0;
+        }
+        // params = theta - lse (:134).  log_p_x = sum_c x_c log_softmax(params)_c (:135); the second
+        // normalisation is the identity up to 1 ulp (logsumexp(params) = O(1e-16)) and is dropped.
+        R acc = R(0), dbest = x[0];
+        int dam = 0;
+        for (int c = 0; c < C; c++) {
+            const R pc = t[c] - lse;
+            const R xv = x[c];
+            acc += xv * pc;
+            t[c] = pc;
+            if (xv > dbest) { dbest = xv; dam = c; }
+        }
+        lp = acc;
+        rmean = (R)am; rmode = (R)am;                                        // read_functions.py:296-302
+        dtr = (R)dam;                                                        // read_functions.py:226-227
+    } else {                                                                 // ordinal, loglik.py:149-188
+        int vals = 0;
+        R sx = R(0);
+        for (int c = 0; c < C; c++) { vals += (int)x[c]; sx += x[c]; }       // :172
+        if (!observed) vals = 1;                                             // :173
+        int am = 0;
+        R py = R(1), lsum = R(1);
+        if constexpr (sizeof(R) == 8) {
+            double p[HLVAE_MAX_CLASS], tot;
+            am = ordinal_probs_f64<R>(t, C, p, tot);
+            double ls = 0.0;
             for (int c = 0; c < C; c++) {
-                const double ph = p[c] / tot;                                    // :178
-                st<TS>(params, pbase + c, ph);
-                if (ph > best) { best = ph; am = c; }
-                lsum += ph;
+                const double ph = p[c] / tot;                                // :178
+                t[c] = (R)ph;
+                ls += ph;
+                if (c == vals - 1) py = (R)ph;
+            }
+            lsum = (R)ls;
+        } else {
+            // float32: class probabilities as products of factors in (0, 1] so that small differences of
+            // sigmoids keep their relative accuracy:
+            //   sigma(u_c) - sigma(u_{c-1}) = sigma(u_c) sigma(-u_{c-1}) (1 - exp(-(u_c - u_{c-1})))
+            // The unnormalised p_c overwrite theta_c in place (theta_c is consumed first; theta_{C-1} is `loc`).
+            const R eps = R(1e-6);
+            const R loc = softplus_<R>(t[C - 1]);
+            R cum = R(0), sneg_prev = R(1), tot = R(0);
+            for (int c = 0; c < C; c++) {
+                R pc;
+                if (c < C - 1) {
+                    const R delta = clamp_<R>(softplus_<R>(t[c]), eps, R(1e20));
+                    cum += delta;
+                    const R e = Mth<R>::ex(loc - cum);                       // exp(-u_c)
+                    const R sg = Mth<R>::rcp(R(1) + e);                      // sigma(u_c)
+                    pc = (c == 0) ? sg : sg * sneg_prev * (-Mth<R>::exm1(-delta));
+                    sneg_prev = (e > R(1e30)) ? R(1) : e * sg;               // sigma(-u_c)
+                } else {
+                    pc = sneg_prev;                                          // 1 - sigma(u_{C-2})
+                }
+                pc = clamp_<R>(pc, eps, R(1));
+                tot += pc;
+                t[c] = pc;
+            }
+            const R itot = Mth<R>::rcp(tot);
+            R best = R(-1), second = R(-1), ls = R(0);
+            for (int c = 0; c < C; c++) {
+                const R ph = t[c] * itot;
+                t[c] = ph;
+                ls += ph;
+                if (ph > best) { second = best; best = ph; am = c; }
+                else second = fmax(second, ph);
                 if (c == vals - 1) py = ph;
             }
-            lp = log(py) - log(lsum);                                            // :179 log_softmax(log p)
-            rmean = am; rmode = am;
-            double sx = 0.0;
-            for (int c = 0; c < C; c++) sx += (double)x[c];
-            dtr = sx - 1.0;                                                      // read_functions.py:229-230
+            lsum = ls;
+            // not provably the float64 decision -> the caller redoes this variable in float64 (rare)
+            if (best - second < R(4e-6) * (R(4) + cum + loc) * best) am = -1;
         }
-        lp_obs = lp * m;
-        st<TS>(log_p_x, n * D + d, lp_obs);
-        st<TS>(log_p_x_missing, n * D + d, lp * (1.0 - m));
-        st<TS>(recon_mean, n * D + d, rmean);
-        st<TS>(recon_mode, n * D + d, rmode);
-        st<TS>(data_tr, n * D + d, dtr);
+        lp = Mth<R>::lg(py) - Mth<R>::lg(lsum);                              // :179 log_softmax(log p)
+        rmean = (R)am; rmode = (R)am;
+        dtr = sx - R(1);                                                     // read_functions.py:229-230
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// Staging helpers.  cp.async moves 4 / 8-byte elements global -> shared without a register round
+// trip, so a CTA can put a whole row batch in flight before it waits.
+template <int BYTES>
+__device__ __forceinline__ void cp_async_elem(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(d), "l"(gsrc), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+// Stage `span` elements of one row.  Same-width elements go through cp.async one by one (coalesced
+// across the warp).  uint8 codes are fetched as aligned 4-byte words: the copy starts at the
+// 4-byte boundary below `src` (`shift` bytes early; the caller reads element j at dst[shift + j]),
+// which stays inside the array as long as its end is 4-byte aligned (`word_ok`).
+template <typename T>
+__device__ __forceinline__ int stage_row(T* __restrict__ dst, const T* __restrict__ src, int span, int tid, bool word_ok) {
+    if constexpr (sizeof(T) >= 4) {
+        for (int i = tid; i < span; i += LL_THREADS) cp_async_elem<sizeof(T)>(dst + i, src + i);
+        return 0;
+    } else {
+        const int shift = word_ok ? (int)(reinterpret_cast<uintptr_t>(src) & 3) : 0;
+        if (word_ok) {
+            const T* s0 = src - shift;
+            const int words = (shift + span + 3) >> 2;
+            for (int i = tid; i < words; i += LL_THREADS) cp_async_elem<4>(dst + 4 * i, s0 + 4 * i);
+        } else {
+            for (int i = tid; i < span; i += LL_THREADS) dst[i] = src[i];
+        }
+        return shift;
+    }
+}
+
+// grid: (variable tiles, row stripes); dynamic smem: 2 * LL_ROWS * cap elements of R
+template <typename TS, typename TD, typename TM>
+__global__ void __launch_bounds__(LL_THREADS, sizeof(TS) == 4 ? 6 : 3)
+loglik_fwd_k(int64_t N, int D, int tile_vars, int cap, int64_t ld_data, int64_t ld_theta,
+             const int32_t* __restrict__ var_kind, const int32_t* __restrict__ var_nclass,
+             const int32_t* __restrict__ var_dcol, const int32_t* __restrict__ var_pcol,
+             const double* __restrict__ vparam, const TD* __restrict__ data, const TS* __restrict__ theta,
+             const TM* __restrict__ mask, TS* __restrict__ log_p_x, TS* __restrict__ log_p_x_missing,
+             TS* __restrict__ params, TS* __restrict__ recon_mean, TS* __restrict__ recon_mode,
+             TS* __restrict__ data_tr, double* __restrict__ ll_total) {
+    using R = TS;
+    extern __shared__ __align__(16) unsigned char ll_smem[];
+    R* sT = reinterpret_cast<R*>(ll_smem);       // [LL_ROWS][cap]   theta, overwritten with params
+    R* sM = sT + LL_ROWS * cap;                  // [LL_ROWS][LL_THREADS] mask of (row, this thread's variable)
+    TD* sX = reinterpret_cast<TD*>(sM + LL_ROWS * LL_THREADS);   // [LL_ROWS][capx]  data in its storage type
+    const int capx = cap + 8;
+    __shared__ int sShift[LL_ROWS];
+    const bool word_ok = (((uintptr_t)data | (uintptr_t)(N * ld_data)) & 3) == 0;
+    __shared__ double red[LL_THREADS / 32];
+    const int tid = threadIdx.x;
+    const int d0 = blockIdx.x * tile_vars;
+    const int d1 = min(D, d0 + tile_vars);
+    const int d = d0 + tid;
+    const bool active = d < d1;
+    const int xs0 = var_dcol[d0], ps0 = var_pcol[d0];
+    const int span_x = max(0, min(cap, var_dcol[d1 - 1] + var_nclass[d1 - 1] - xs0));
+    const int span_p = max(0, min(cap, var_pcol[d1 - 1] + var_nclass[d1 - 1] - ps0));
+    const VarC<R> v = load_var<R>(d, D, active, var_kind, var_nclass, var_dcol, var_pcol, vparam, xs0, ps0, cap);
+    double ll = 0.0;
+    for (int64_t n0 = (int64_t)blockIdx.y * LL_ROWS; n0 < N; n0 += (int64_t)gridDim.y * LL_ROWS) {
+        const int nr = (int)min((int64_t)LL_ROWS, N - n0);
+        for (int r = 0; r < nr; r++) {
+            stage_row<TS>(sT + r * cap, theta + (n0 + r) * ld_theta + ps0, span_p, tid, true);
+            const int sh = stage_row<TD>(sX + r * capx, data + (n0 + r) * ld_data + xs0, span_x, tid, word_ok);
+            if (tid == 0) sShift[r] = sh;
+        }
+#pragma unroll
+        for (int r = 0; r < LL_ROWS; r++) sM[r * LL_THREADS + tid] = (active && r < nr) ? (R)mask[(n0 + r) * D + d] : R(0);
+        cp_async_wait_all();
+        __syncthreads();
+        if (active) {
+#pragma unroll 1
+            for (int r = 0; r < nr; r++) {
+                R lp = R(0), rmean = R(0), rmode = R(0), dtr = R(0);
+                const R m_ = sM[r * LL_THREADS + tid];
+                if (v.ok) {
+                    var_forward<R, TD>(v, sX + r * capx + sShift[r] + v.xo, sT + r * cap + v.po, m_ != R(0), lp, rmean,
+                                       rmode, dtr);
+                    if constexpr (sizeof(R) == 4) {
+                        if (v.kind == HLVAE_VAR_ORDINAL && rmean < R(0)) {      // ordinal decision float32 could not prove: redo from the original theta
+                            const R am = (R)ord_argmax_f64(reinterpret_cast<const float*>(theta) +
+                                                           (n0 + r) * ld_theta + ps0 + v.po, v.C);
+                            rmean = am; rmode = am;
+                        }
+                    }
+                } else {
+                    lp = rmean = rmode = dtr = (R)NAN;
+                }
+                const R lpo = lp * m_;
+                ll += (double)lpo;
+                const int64_t o = (n0 + r) * D + d;
+                if (log_p_x) log_p_x[o] = lpo;
+                if (log_p_x_missing) log_p_x_missing[o] = lp * (R(1) - m_);
+                if (recon_mean) recon_mean[o] = rmean;
+                if (recon_mode) recon_mode[o] = rmode;
+                if (data_tr) data_tr[o] = dtr;
+            }
+        }
+        __syncthreads();
+        if (params) {
+            for (int r = 0; r < nr; r++) {
+                TS* prow = params + (n0 + r) * ld_theta + ps0;
+                const R* src = sT + r * cap;
+                for (int i = tid; i < span_p; i += LL_THREADS) prow[i] = src[i];
+            }
+        }
+        __syncthreads();
     }
     if (ll_total) {
-        lp_obs = warp_sum(lp_obs);
-        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = lp_obs;
+        ll = warp_sum(ll);
+        if ((tid & 31) == 0) red[tid >> 5] = ll;
         __syncthreads();
-        if (threadIdx.x == 0) {
+        if (tid == 0) {
             double s = 0.0;
             for (int w = 0; w < LL_THREADS / 32; w++) s += red[w];
-            atomicAdd(ll_total, s);
+            if (s != 0.0) atomicAdd(ll_total, s);
         }
     }
 }
 
 // ------------------------------------------------------------------------------------
-template <typename TS, typename TM>
-__global__ void __launch_bounds__(LL_THREADS)
-loglik_bwd_k(int64_t N, int D, int64_t ld_data, int64_t ld_theta, const int32_t* __restrict__ var_kind,
-             const int32_t* __restrict__ var_nclass, const int32_t* __restrict__ var_dcol,
-             const int32_t* __restrict__ var_pcol, const double* __restrict__ vparam, const TS* __restrict__ data,
-             const TS* __restrict__ theta, const void* __restrict__ mask, const TS* __restrict__ g_lp, double g_scalar,
-             TS* __restrict__ g_theta, double* __restrict__ g_lvy) {
-    // grid: (ceil(D / LL_THREADS), row blocks); thread owns one variable, loops over a stripe of rows,
-    // so the per-variable log-variance gradient reduces in a register.
-    const int d = blockIdx.x * LL_THREADS + threadIdx.x;
-    if (d >= D) return;
-    const int kind = var_kind[d];
-    const int C = var_nclass[d];
-    const int dcol = var_dcol[d], pcol = var_pcol[d];
-    const double nm = vparam[d], nv = vparam[D + d], e = vparam[2 * D + d], div = vparam[3 * D + d];
-    const double snv = sqrt(nv);
-    double ge = 0.0;
-    double var = 1.0, sg8 = 0.0;
-    if (kind == HLVAE_VAR_REAL) {
-        var = nv * exp(-8.0 + softplus_d(e + 8.0));
-        sg8 = dsoftplus_d(e + 8.0);
-    } else if (kind == HLVAE_VAR_POS) {
-        var = nv * exp(e);
-    }
-    for (int64_t n = blockIdx.y; n < N; n += gridDim.y) {
-        const double m = load_mask<TM>(mask, n * D + d);
-        const double g = (g_lp ? (double)g_lp[n * D + d] : g_scalar) * m;
-        const TS* x = data + n * ld_data + dcol;
-        const TS* th = theta + n * ld_theta + pcol;
-        TS* gt = g_theta + n * ld_theta + pcol;
-        if (kind == HLVAE_VAR_REAL) {
-            const double r = (double)x[0] / div - (snv * (double)th[0] + nm);
-            gt[0] = (TS)(g * snv * r / var);
-            ge += g * (0.5 * r * r / var - 0.5) * sg8;
-        } else if (kind == HLVAE_VAR_POS) {
-            const double r = log(1.0 + (double)x[0]) - (snv * (double)th[0] + nm);
-            gt[0] = (TS)(g * snv * r / var);
-            ge += g * (0.5 * r * r / var - 0.5);
-        } else if (kind == HLVAE_VAR_COUNT) {
-            const double t0 = (double)th[0];
-            const double sp = softplus_d(t0);
-            double gl = 0.0;
-            if (sp >= 1e-6 && sp <= 1e20) gl = ((double)x[0] / sp - 1.0) * dsoftplus_d(t0);
-            gt[0] = (TS)(g * gl);
-        } else if (kind == HLVAE_VAR_CAT) {
-            double t[HLVAE_MAX_CLASS];
-            double mx = -INFINITY, sx = 0.0;
-            for (int c = 0; c < C; c++) { t[c] = (double)th[c]; mx = fmax(mx, t[c]); sx += (double)x[c]; }
-            double se = 0.0;
-            for (int c = 0; c < C; c++) { t[c] = exp(t[c] - mx); se += t[c]; }
-            for (int c = 0; c < C; c++) gt[c] = (TS)(g * ((double)x[c] - t[c] / se * sx));
-        } else {
-            const double eps = 1e-6;
-            const double t_loc = (double)th[C - 1];
-            const double loc = softplus_d(t_loc);
-            double sgm[HLVAE_MAX_CLASS], p[HLVAE_MAX_CLASS], q[HLVAE_MAX_CLASS];
-            double cum = 0.0, prev = 0.0, tot = 0.0;
-            int vals = 0;
-            for (int c = 0; c < C; c++) {
-                double sg = 1.0;
+// One variable, backward: d log_p_x / d theta (times g) into t (in place of theta), and the
+// derivative w.r.t. the raw log-variance parameter (real / pos).
+template <typename R, typename XT>
+__device__ __forceinline__ void var_backward(const VarC<R>& v, const XT* __restrict__ x_, R* __restrict__ t, bool observed,
+                                             R g, R& ge) {
+    struct { const XT* p; __device__ __forceinline__ R operator[](int c) const { return (R)p[c]; } } x{x_};
+    const int C = v.C;
+    if (v.kind == HLVAE_VAR_REAL) {
+        const R r = x[0] * v.idiv - (v.snv * t[0] + v.nm);
+        t[0] = g * v.snv * r * v.ivar;
+        ge = g * (R(0.5) * r * r * v.ivar - R(0.5)) * v.sg8;
+    } else if (v.kind == HLVAE_VAR_POS) {
+        const R r = Mth<R>::lg1p(x[0]) - (v.snv * t[0] + v.nm);
+        t[0] = g * v.snv * r * v.ivar;
+        ge = g * (R(0.5) * r * r * v.ivar - R(0.5));
+    } else if (v.kind == HLVAE_VAR_COUNT) {
+        const R t0 = t[0];
+        const R sp = softplus_<R>(t0);
+        R gl = R(0);
+        if (sp >= R(1e-6) && sp <= R(1e20)) gl = (x[0] * Mth<R>::rcp(sp) - R(1)) * dsoftplus_<R>(t0);
+        t[0] = g * gl;
+    } else if (v.kind == HLVAE_VAR_CAT) {
+        R mx = -INFINITY, sx = R(0);
+        for (int c = 0; c < C; c++) { mx = fmax(mx, t[c]); sx += x[c]; }
+        R se = R(0);
+        for (int c = 0; c < C; c++) { const R e = Mth<R>::ex(t[c] - mx); t[c] = e; se += e; }
+        const R k = sx * Mth<R>::rcp(se);
+        for (int c = 0; c < C; c++) t[c] = g * (x[c] - t[c] * k);
+    } else {
+        const R eps = R(1e-6);
+        const R t_loc = t[C - 1];
+        const R loc = softplus_<R>(t_loc);
+        R dsg[HLVAE_MAX_CLASS], q[HLVAE_MAX_CLASS];      // dsg_c = sigma'(u_c) = sigma(u_c) sigma(-u_c)
+        R cum = R(0), prev = R(0), tot = R(0), sneg_prev = R(1);
+        int vals = 0;
+#pragma unroll
+        for (int c = 0; c < HLVAE_MAX_CLASS; c++) {
+            if (c < C) {
+                R sg = R(1), qc, ds = R(0);
                 if (c < C - 1) {
-                    cum += fmin(fmax(softplus_d((double)th[c]), eps), 1e20);
-                    sg = sigmoid_d(cum - loc);
+                    const R delta = clamp_<R>(softplus_<R>(t[c]), eps, R(1e20));
+                    cum += delta;
+                    const R e = Mth<R>::ex(loc - cum);                      // exp(-u_c)
+                    sg = Mth<R>::rcp(R(1) + e);
+                    const R sneg = (e > R(1e30)) ? R(1) : e * sg;           // sigma(-u_c), no cancellation
+                    ds = sg * sneg;
+                    if constexpr (sizeof(R) == 4) {
+                        qc = (c == 0) ? sg : sg * sneg_prev * (-Mth<R>::exm1(-delta));
+                    } else {
+                        qc = sg - prev;
+                    }
+                    sneg_prev = sneg;
+                } else {
+                    if constexpr (sizeof(R) == 4) qc = sneg_prev; else qc = sg - prev;
                 }
-                sgm[c] = sg;
-                q[c] = sg - prev;
-                p[c] = fmin(fmax(q[c], eps), 1.0);
+                dsg[c] = ds;
+                q[c] = qc;
                 prev = sg;
-                tot += p[c];
-                vals += (int)(double)x[c];
+                tot += clamp_<R>(qc, eps, R(1));
+                vals += (int)x[c];
             }
-            if (m == 0.0) vals = 1;
-            const int y = vals - 1;
-            // lp = log p_y - log tot ; clamp passes gradient inside [eps, 1]
-            double gq[HLVAE_MAX_CLASS];
-            for (int c = 0; c < C; c++) {
-                double gp = ((c == y) ? 1.0 / p[c] : 0.0) - 1.0 / tot;
-                gq[c] = (q[c] >= eps && q[c] <= 1.0) ? gp : 0.0;
-            }
-            // q_c = sg_c - sg_{c-1}: d/dsg_c = gq_c - gq_{c+1}, c < C-1; u_c = cum_c - loc
-            double g_loc = 0.0, run = 0.0;
-            for (int c = C - 2; c >= 0; c--) {
-                const double gu = (gq[c] - gq[c + 1]) * sgm[c] * (1.0 - sgm[c]);
-                g_loc -= gu;
-                run += gu;                                   // reverse cumulative sum -> d/da_c
-                const double tc = (double)th[c];
-                const double sp = softplus_d(tc);
-                const double ga = (sp >= eps && sp <= 1e20) ? run * dsoftplus_d(tc) : 0.0;
-                gt[c] = (TS)(g * ga);
-            }
-            gt[C - 1] = (TS)(g * g_loc * dsoftplus_d(t_loc));
         }
+        if (!observed) vals = 1;
+        const int y = vals - 1;
+        // lp = log p_y - log tot ; the clamp passes gradient inside [eps, 1]
+        // q_c = sg_c - sg_{c-1}: d/dsg_c = gq_c - gq_{c+1}, c < C-1; u_c = cum_c - loc
+        const R itot = Mth<R>::rcp(tot);
+        R g_loc = R(0), run = R(0), gq_next = R(0);
+        {
+            const R qc = q[C - 1];
+            const R pc = clamp_<R>(qc, eps, R(1));
+            const R gp = ((C - 1 == y) ? Mth<R>::rcp(pc) : R(0)) - itot;
+            gq_next = (qc >= eps && qc <= R(1)) ? gp : R(0);
+        }
+#pragma unroll
+        for (int c = HLVAE_MAX_CLASS - 2; c >= 0; c--) {
+            if (c <= C - 2) {
+                const R qc = q[c];
+                const R pc = clamp_<R>(qc, eps, R(1));
+                const R gp = ((c == y) ? Mth<R>::rcp(pc) : R(0)) - itot;
+                const R gqc = (qc >= eps && qc <= R(1)) ? gp : R(0);
+                const R gu = (gqc - gq_next) * dsg[c];
+                gq_next = gqc;
+                g_loc -= gu;
+                run += gu;                                   // reverse cumulative sum -> d/d delta_c
+                const R tc = t[c];
+                const R sp = softplus_<R>(tc);
+                const R ga = (sp >= eps && sp <= R(1e20)) ? run * dsoftplus_<R>(tc) : R(0);
+                t[c] = g * ga;
+            }
+        }
+        t[C - 1] = g * g_loc * dsoftplus_<R>(t_loc);
     }
-    if (g_lvy && (kind == HLVAE_VAR_REAL || kind == HLVAE_VAR_POS) && ge != 0.0) atomicAdd(g_lvy + d, ge);
+}
+
+template <typename TS, typename TD, typename TM>
+__global__ void __launch_bounds__(LL_THREADS, sizeof(TS) == 4 ? 6 : 3)
+loglik_bwd_k(int64_t N, int D, int tile_vars, int cap, int64_t ld_data, int64_t ld_theta,
+             const int32_t* __restrict__ var_kind, const int32_t* __restrict__ var_nclass,
+             const int32_t* __restrict__ var_dcol, const int32_t* __restrict__ var_pcol,
+             const double* __restrict__ vparam, const TD* __restrict__ data, const TS* __restrict__ theta,
+             const TM* __restrict__ mask, const TS* __restrict__ g_lp, const double* __restrict__ g_scalar,
+             TS* __restrict__ g_theta, double* __restrict__ g_lvy) {
+    using R = TS;
+    extern __shared__ __align__(16) unsigned char ll_smem[];
+    R* sT = reinterpret_cast<R*>(ll_smem);
+    R* sM = sT + LL_ROWS * cap;                  // mask and upstream gradient per (row, variable)
+    R* sG = sM + LL_ROWS * LL_THREADS;
+    TD* sX = reinterpret_cast<TD*>(sG + LL_ROWS * LL_THREADS);
+    const int capx = cap + 8;
+    __shared__ int sShift[LL_ROWS];
+    const bool word_ok = (((uintptr_t)data | (uintptr_t)(N * ld_data)) & 3) == 0;
+    const int tid = threadIdx.x;
+    const int d0 = blockIdx.x * tile_vars;
+    const int d1 = min(D, d0 + tile_vars);
+    const int d = d0 + tid;
+    const bool active = d < d1;
+    const int xs0 = var_dcol[d0], ps0 = var_pcol[d0];
+    const int span_x = max(0, min(cap, var_dcol[d1 - 1] + var_nclass[d1 - 1] - xs0));
+    const int span_p = max(0, min(cap, var_pcol[d1 - 1] + var_nclass[d1 - 1] - ps0));
+    const VarC<R> v = load_var<R>(d, D, active, var_kind, var_nclass, var_dcol, var_pcol, vparam, xs0, ps0, cap);
+    const R gs = g_scalar ? (R)(*g_scalar) : R(0);
+    double ge_acc = 0.0;
+    for (int64_t n0 = (int64_t)blockIdx.y * LL_ROWS; n0 < N; n0 += (int64_t)gridDim.y * LL_ROWS) {
+        const int nr = (int)min((int64_t)LL_ROWS, N - n0);
+        for (int r = 0; r < nr; r++) {
+            stage_row<TS>(sT + r * cap, theta + (n0 + r) * ld_theta + ps0, span_p, tid, true);
+            const int sh = stage_row<TD>(sX + r * capx, data + (n0 + r) * ld_data + xs0, span_x, tid, word_ok);
+            if (tid == 0) sShift[r] = sh;
+        }
+#pragma unroll
+        for (int r = 0; r < LL_ROWS; r++) {
+            const bool on = active && r < nr;
+            sM[r * LL_THREADS + tid] = on ? (R)mask[(n0 + r) * D + d] : R(0);
+            sG[r * LL_THREADS + tid] = gs + ((on && g_lp) ? (R)g_lp[(n0 + r) * D + d] : R(0));
+        }
+        cp_async_wait_all();
+        __syncthreads();
+        if (active) {
+#pragma unroll 1
+            for (int r = 0; r < nr; r++) {
+                if (v.ok) {
+                    R ge = R(0);
+                    const R m_ = sM[r * LL_THREADS + tid];
+                    var_backward<R, TD>(v, sX + r * capx + sShift[r] + v.xo, sT + r * cap + v.po, m_ != R(0),
+                                        sG[r * LL_THREADS + tid] * m_, ge);
+                    ge_acc += (double)ge;
+                } else {
+                    for (int c = 0; c < v.C && v.po >= 0 && v.po + c < cap; c++) sT[r * cap + v.po + c] = (R)NAN;
+                }
+            }
+        }
+        __syncthreads();
+        for (int r = 0; r < nr; r++) {
+            TS* grow = g_theta + (n0 + r) * ld_theta + ps0;
+            const R* src = sT + r * cap;
+            for (int i = tid; i < span_p; i += LL_THREADS) grow[i] = src[i];
+        }
+        __syncthreads();
+    }
+    if (g_lvy && active && (v.kind == HLVAE_VAR_REAL || v.kind == HLVAE_VAR_POS) && ge_acc != 0.0)
+        atomicAdd(g_lvy + d, ge_acc);
 }
 
 // ------------------------------------------------------------------------------------
 // Stand-alone monitoring transforms for callers that hold `params` / `data` only
 // (training.py:84-91 calls them separately from the likelihood).
 template <typename TS>
-__global__ void __launch_bounds__(LL_THREADS)
+__global__ void __launch_bounds__(256)
 statistics_k(int64_t N, int D, int64_t ld_theta, const int32_t* __restrict__ var_kind,
              const int32_t* __restrict__ var_nclass, const int32_t* __restrict__ var_pcol,
              const double* __restrict__ vparam, const TS* __restrict__ params, TS* __restrict__ mean,
              TS* __restrict__ mode) {
-    const int64_t idx = (int64_t)blockIdx.x * LL_THREADS + threadIdx.x;
-    if (idx >= N * D) return;
-    const int64_t n = idx / D;
-    const int d = (int)(idx % D);
-    const int kind = var_kind[d], C = var_nclass[d];
-    const TS* p = params + n * ld_theta + var_pcol[d];
-    double a, b;
-    if (kind == HLVAE_VAR_REAL) {
-        a = b = (double)p[0];                                            // read_functions.py:275-278
-    } else if (kind == HLVAE_VAR_POS) {
-        const double v = exp(vparam[2 * D + d]);                         // :284
-        a = exp((double)p[0] + 0.5 * v) - 1.0;                           // :287
-        b = exp((double)p[0] - v) - 1.0;                                 // :289
-    } else if (kind == HLVAE_VAR_COUNT) {
-        a = (double)p[0];
-        b = floor(a);                                                    // :293-295
-    } else {
-        int am = 0;
-        TS best = p[0];
-        for (int c = 1; c < C; c++)
-            if (p[c] > best) { best = p[c]; am = c; }                    // :296-302, first index on ties
-        a = b = am;
+    const int d = blockIdx.x * 256 + threadIdx.x;
+    if (d >= D) return;
+    const int kind = var_kind[d], C = var_nclass[d], pcol = var_pcol[d];
+    const double v = exp(vparam[2 * D + d]);                                 // read_functions.py:284
+    for (int64_t n = blockIdx.y; n < N; n += gridDim.y) {
+        const TS* p = params + n * ld_theta + pcol;
+        double a, b;
+        if (kind == HLVAE_VAR_REAL) {
+            a = b = (double)p[0];                                            // :275-278
+        } else if (kind == HLVAE_VAR_POS) {
+            a = exp((double)p[0] + 0.5 * v) - 1.0;                           // :287
+            b = exp((double)p[0] - v) - 1.0;                                 // :289
+        } else if (kind == HLVAE_VAR_COUNT) {
+            a = (double)p[0];
+            b = floor(a);                                                    // :293-295
+        } else {
+            int am = 0;
+            TS best = p[0];
+            for (int c = 1; c < C; c++)
+                if (p[c] > best) { best = p[c]; am = c; }                    // :296-302, first index on ties
+            a = b = am;
+        }
+        mean[n * D + d] = (TS)a;
+        mode[n * D + d] = (TS)b;
     }
-    mean[idx] = (TS)a;
-    mode[idx] = (TS)b;
 }
 
 template <typename TS>
-__global__ void __launch_bounds__(LL_THREADS)
+__global__ void __launch_bounds__(256)
 discrete_transform_k(int64_t N, int D, int64_t ld_data, const int32_t* __restrict__ var_kind,
                      const int32_t* __restrict__ var_nclass, const int32_t* __restrict__ var_dcol,
                      const TS* __restrict__ data, TS* __restrict__ out) {
-    const int64_t idx = (int64_t)blockIdx.x * LL_THREADS + threadIdx.x;
-    if (idx >= N * D) return;
-    const int64_t n = idx / D;
-    const int d = (int)(idx % D);
-    const int kind = var_kind[d], C = var_nclass[d];
-    const TS* x = data + n * ld_data + var_dcol[d];
-    double r;
-    if (kind == HLVAE_VAR_CAT) {                                         // read_functions.py:224-227
-        int am = 0;
-        TS best = x[0];
-        for (int c = 1; c < C; c++)
-            if (x[c] > best) { best = x[c]; am = c; }
-        r = am;
-    } else if (kind == HLVAE_VAR_ORDINAL) {                              // :228-230
-        double s = 0.0;
-        for (int c = 0; c < C; c++) s += (double)x[c];
-        r = s - 1.0;
-    } else {
-        r = (double)x[0];                                                // :233
+    const int d = blockIdx.x * 256 + threadIdx.x;
+    if (d >= D) return;
+    const int kind = var_kind[d], C = var_nclass[d], dcol = var_dcol[d];
+    for (int64_t n = blockIdx.y; n < N; n += gridDim.y) {
+        const TS* x = data + n * ld_data + dcol;
+        double r;
+        if (kind == HLVAE_VAR_CAT) {                                         // read_functions.py:224-227
+            int am = 0;
+            TS best = x[0];
+            for (int c = 1; c < C; c++)
+                if (x[c] > best) { best = x[c]; am = c; }
+            r = am;
+        } else if (kind == HLVAE_VAR_ORDINAL) {                              // :228-230
+            double s = 0.0;
+            for (int c = 0; c < C; c++) s += (double)x[c];
+            r = s - 1.0;
+        } else {
+            r = (double)x[0];                                                // :233
+        }
+        out[n * D + d] = (TS)r;
     }
-    out[idx] = (TS)r;
 }
 
 bool args_ok(int64_t N, int D, const int32_t* a, const int32_t* b, const int32_t* c, const int32_t* d,
-             const double* vp, const void* data, const void* theta, const void* mask, int dtype) {
-    return N >= 0 && D > 0 && a && b && c && d && vp && data && theta && mask && (dtype == HLVAE_F32 || dtype == HLVAE_F64);
+             const double* vp, const void* data, const void* theta, const void* mask, int dtype, int data_dtype,
+             int mask_dtype) {
+    if (!(N >= 0 && D > 0 && a && b && c && d && vp && data && theta && mask)) return false;
+    if (dtype != HLVAE_F32 && dtype != HLVAE_F64) return false;
+    if (data_dtype != dtype && data_dtype != HLVAE_U8) return false;
+    if (mask_dtype != dtype && mask_dtype != HLVAE_U8) return false;
+    return true;
+}
+
+struct Tiling {
+    int tile_vars, n_tiles;
+    unsigned rows;
+};
+
+// Variable tiles of equal size (<= LL_THREADS) and as many row stripes as stay resident at once
+// (one wave: every CTA walks the same number of row batches, +-1).
+Tiling make_tiling(int64_t N, int D, int ctas_per_sm) {
+    N = (N + LL_ROWS - 1) / LL_ROWS;            // row batches
+    Tiling t;
+    t.n_tiles = (D + LL_THREADS - 1) / LL_THREADS;
+    t.tile_vars = (D + t.n_tiles - 1) / t.n_tiles;
+    t.n_tiles = (D + t.tile_vars - 1) / t.tile_vars;
+    int64_t want = ((int64_t)148 * ctas_per_sm) / t.n_tiles;
+    if (want > N) want = N;
+    if (want > 65535) want = 65535;
+    if (want < 1) want = 1;
+    t.rows = (unsigned)want;
+    return t;
+}
+
+template <typename K>
+int set_smem(K kern, size_t bytes) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    return e == cudaSuccess ? 0 : (int)e;
 }
 
 }  // namespace
 
+#define HLVAE_LL_DISPATCH(CALL)                                                                      \
+    if (dtype == HLVAE_F64) {                                                                        \
+        if (data_dtype == HLVAE_U8) {                                                                \
+            if (mask_dtype == HLVAE_U8) { CALL(double, uint8_t, uint8_t); } else { CALL(double, uint8_t, double); } \
+        } else {                                                                                     \
+            if (mask_dtype == HLVAE_U8) { CALL(double, double, uint8_t); } else { CALL(double, double, double); }   \
+        }                                                                                            \
+    } else {                                                                                         \
+        if (data_dtype == HLVAE_U8) {                                                                \
+            if (mask_dtype == HLVAE_U8) { CALL(float, uint8_t, uint8_t); } else { CALL(float, uint8_t, float); }    \
+        } else {                                                                                     \
+            if (mask_dtype == HLVAE_U8) { CALL(float, float, uint8_t); } else { CALL(float, float, float); }        \
+        }                                                                                            \
+    }
+
 extern "C" int hlvae_loglik_fwd(int64_t N, int D, int64_t ld_data, int64_t ld_theta, const int32_t* var_kind,
                                 const int32_t* var_nclass, const int32_t* var_dcol, const int32_t* var_pcol,
                                 const double* vparam, const void* data, const void* theta, const void* mask,
-                                int dtype, int mask_u8, void* log_p_x, void* log_p_x_missing, void* params,
-                                void* recon_mean, void* recon_mode, void* data_tr, double* ll_total, void* stream) {
-    if (!args_ok(N, D, var_kind, var_nclass, var_dcol, var_pcol, vparam, data, theta, mask, dtype)) return HLVAE_E_ARG;
+                                int dtype, int data_dtype, int mask_dtype, int max_class, void* log_p_x,
+                                void* log_p_x_missing, void* params, void* recon_mean, void* recon_mode,
+                                void* data_tr, double* ll_total, void* stream) {
+    if (!args_ok(N, D, var_kind, var_nclass, var_dcol, var_pcol, vparam, data, theta, mask, dtype, data_dtype,
+                 mask_dtype))
+        return HLVAE_E_ARG;
     if (N == 0) return 0;
-    const int64_t total = N * D;
-    const unsigned grid = (unsigned)((total + LL_THREADS - 1) / LL_THREADS);
     cudaStream_t st = (cudaStream_t)stream;
-#define HLVAE_LL_FWD(TS, TM)                                                                                         \
-    loglik_fwd_k<TS, TM><<<grid, LL_THREADS, 0, st>>>(N, D, ld_data, ld_theta, var_kind, var_nclass, var_dcol,       \
-                                                      var_pcol, vparam, (const TS*)data, (const TS*)theta, mask,     \
-                                                      log_p_x, log_p_x_missing, params, recon_mean, recon_mode,      \
-                                                      data_tr, ll_total)
-    if (dtype == HLVAE_F64) {
-        if (mask_u8) HLVAE_LL_FWD(double, uint8_t); else HLVAE_LL_FWD(double, double);
-    } else {
-        if (mask_u8) HLVAE_LL_FWD(float, uint8_t); else HLVAE_LL_FWD(float, float);
+    if (max_class < 1 || max_class > HLVAE_MAX_CLASS) return HLVAE_E_ARG;
+    const size_t esz = dtype == HLVAE_F64 ? 8 : 4;
+    const size_t xsz = data_dtype == HLVAE_U8 ? 1 : esz;
+    Tiling tl = make_tiling(N, D, 1);
+    const int cap = (tl.tile_vars * max_class + 3) & ~3;
+    const size_t smem = (size_t)LL_ROWS * ((cap + LL_THREADS) * esz + (cap + 8) * xsz);
+#define HLVAE_LL_FWD(TS, TD, TM)                                                                                     \
+    {                                                                                                                \
+        auto kern = loglik_fwd_k<TS, TD, TM>;                                                                        \
+        int rc = set_smem(kern, smem);                                                                               \
+        if (rc) return rc;                                                                                           \
+        int nb = 1;                                                                                                  \
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, LL_THREADS, smem);                                  \
+        tl = make_tiling(N, D, nb < 1 ? 1 : nb);                                                                     \
+        dim3 grid(tl.n_tiles, tl.rows);                                                                              \
+        kern<<<grid, LL_THREADS, smem, st>>>(N, D, tl.tile_vars, cap, ld_data, ld_theta, var_kind, var_nclass,       \
+                                             var_dcol, var_pcol, vparam, (const TD*)data, (const TS*)theta,          \
+                                             (const TM*)mask, (TS*)log_p_x, (TS*)log_p_x_missing, (TS*)params, (TS*)recon_mean,       \
+                                             (TS*)recon_mode, (TS*)data_tr, ll_total);                               \
     }
+    HLVAE_LL_DISPATCH(HLVAE_LL_FWD)
 #undef HLVAE_LL_FWD
     HLVAE_CHECK_LAUNCH();
     return 0;
@@ -362,26 +732,34 @@ extern "C" int hlvae_loglik_fwd(int64_t N, int D, int64_t ld_data, int64_t ld_th
 extern "C" int hlvae_loglik_bwd(int64_t N, int D, int64_t ld_data, int64_t ld_theta, const int32_t* var_kind,
                                 const int32_t* var_nclass, const int32_t* var_dcol, const int32_t* var_pcol,
                                 const double* vparam, const void* data, const void* theta, const void* mask,
-                                int dtype, int mask_u8, const void* g_lp, double g_scalar, void* g_theta,
-                                double* g_lvy, void* stream) {
-    if (!args_ok(N, D, var_kind, var_nclass, var_dcol, var_pcol, vparam, data, theta, mask, dtype) || !g_theta)
+                                int dtype, int data_dtype, int mask_dtype, int max_class, const void* g_lp,
+                                const double* g_scalar, void* g_theta, double* g_lvy, void* stream) {
+    if (!args_ok(N, D, var_kind, var_nclass, var_dcol, var_pcol, vparam, data, theta, mask, dtype, data_dtype,
+                 mask_dtype) ||
+        !g_theta || (!g_lp && !g_scalar))
         return HLVAE_E_ARG;
     if (N == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    // enough row stripes to fill the machine: 148 SMs x 8 resident CTAs, capped by N
-    const unsigned gx = (unsigned)((D + LL_THREADS - 1) / LL_THREADS);
-    unsigned gy = (unsigned)((148 * 8 + gx - 1) / gx);
-    if ((int64_t)gy > N) gy = (unsigned)N;
-    dim3 grid(gx, gy);
-#define HLVAE_LL_BWD(TS, TM)                                                                                         \
-    loglik_bwd_k<TS, TM><<<grid, LL_THREADS, 0, st>>>(N, D, ld_data, ld_theta, var_kind, var_nclass, var_dcol,       \
-                                                      var_pcol, vparam, (const TS*)data, (const TS*)theta, mask,     \
-                                                      (const TS*)g_lp, g_scalar, (TS*)g_theta, g_lvy)
-    if (dtype == HLVAE_F64) {
-        if (mask_u8) HLVAE_LL_BWD(double, uint8_t); else HLVAE_LL_BWD(double, double);
-    } else {
-        if (mask_u8) HLVAE_LL_BWD(float, uint8_t); else HLVAE_LL_BWD(float, float);
+    if (max_class < 1 || max_class > HLVAE_MAX_CLASS) return HLVAE_E_ARG;
+    const size_t esz = dtype == HLVAE_F64 ? 8 : 4;
+    const size_t xsz = data_dtype == HLVAE_U8 ? 1 : esz;
+    Tiling tl = make_tiling(N, D, 1);
+    const int cap = (tl.tile_vars * max_class + 3) & ~3;
+    const size_t smem = (size_t)LL_ROWS * ((cap + 2 * LL_THREADS) * esz + (cap + 8) * xsz);
+#define HLVAE_LL_BWD(TS, TD, TM)                                                                                     \
+    {                                                                                                                \
+        auto kern = loglik_bwd_k<TS, TD, TM>;                                                                        \
+        int rc = set_smem(kern, smem);                                                                               \
+        if (rc) return rc;                                                                                           \
+        int nb = 1;                                                                                                  \
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, LL_THREADS, smem);                                  \
+        tl = make_tiling(N, D, nb < 1 ? 1 : nb);                                                                     \
+        dim3 grid(tl.n_tiles, tl.rows);                                                                              \
+        kern<<<grid, LL_THREADS, smem, st>>>(N, D, tl.tile_vars, cap, ld_data, ld_theta, var_kind, var_nclass,       \
+                                             var_dcol, var_pcol, vparam, (const TD*)data, (const TS*)theta,          \
+                                             (const TM*)mask, (const TS*)g_lp, g_scalar, (TS*)g_theta, g_lvy);                        \
     }
+    HLVAE_LL_DISPATCH(HLVAE_LL_BWD)
 #undef HLVAE_LL_BWD
     HLVAE_CHECK_LAUNCH();
     return 0;
@@ -394,14 +772,17 @@ extern "C" int hlvae_statistics(int64_t N, int D, int64_t ld_theta, const int32_
         (dtype != HLVAE_F32 && dtype != HLVAE_F64))
         return HLVAE_E_ARG;
     if (N == 0) return 0;
-    const unsigned grid = (unsigned)((N * D + LL_THREADS - 1) / LL_THREADS);
+    const unsigned gx = (unsigned)((D + 255) / 256);
+    unsigned gy = (unsigned)((148 * 8 + gx - 1) / gx);
+    if ((int64_t)gy > N) gy = (unsigned)N;
+    dim3 grid(gx, gy);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == HLVAE_F64)
-        statistics_k<double><<<grid, LL_THREADS, 0, st>>>(N, D, ld_theta, var_kind, var_nclass, var_pcol, vparam,
-                                                          (const double*)params, (double*)mean, (double*)mode);
+        statistics_k<double><<<grid, 256, 0, st>>>(N, D, ld_theta, var_kind, var_nclass, var_pcol, vparam,
+                                                   (const double*)params, (double*)mean, (double*)mode);
     else
-        statistics_k<float><<<grid, LL_THREADS, 0, st>>>(N, D, ld_theta, var_kind, var_nclass, var_pcol, vparam,
-                                                         (const float*)params, (float*)mean, (float*)mode);
+        statistics_k<float><<<grid, 256, 0, st>>>(N, D, ld_theta, var_kind, var_nclass, var_pcol, vparam,
+                                                  (const float*)params, (float*)mean, (float*)mode);
     HLVAE_CHECK_LAUNCH();
     return 0;
 }
@@ -413,14 +794,17 @@ extern "C" int hlvae_discrete_transform(int64_t N, int D, int64_t ld_data, const
         (dtype != HLVAE_F32 && dtype != HLVAE_F64))
         return HLVAE_E_ARG;
     if (N == 0) return 0;
-    const unsigned grid = (unsigned)((N * D + LL_THREADS - 1) / LL_THREADS);
+    const unsigned gx = (unsigned)((D + 255) / 256);
+    unsigned gy = (unsigned)((148 * 8 + gx - 1) / gx);
+    if ((int64_t)gy > N) gy = (unsigned)N;
+    dim3 grid(gx, gy);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == HLVAE_F64)
-        discrete_transform_k<double><<<grid, LL_THREADS, 0, st>>>(N, D, ld_data, var_kind, var_nclass, var_dcol,
-                                                                  (const double*)data, (double*)out);
+        discrete_transform_k<double><<<grid, 256, 0, st>>>(N, D, ld_data, var_kind, var_nclass, var_dcol,
+                                                           (const double*)data, (double*)out);
     else
-        discrete_transform_k<float><<<grid, LL_THREADS, 0, st>>>(N, D, ld_data, var_kind, var_nclass, var_dcol,
-                                                                 (const float*)data, (float*)out);
+        discrete_transform_k<float><<<grid, 256, 0, st>>>(N, D, ld_data, var_kind, var_nclass, var_dcol,
+                                                          (const float*)data, (float*)out);
     HLVAE_CHECK_LAUNCH();
     return 0;
 }

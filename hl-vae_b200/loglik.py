@@ -43,6 +43,7 @@ class VarLayout:
             p += C
         self.types = [(k, int(c)) for k, c in types]
         self.D, self.E_x, self.P_theta = len(kinds), e, p
+        self.max_class = max(ncls) if ncls else 1
         self.device = device
         i32 = dict(dtype=torch.int32, device=device)
         self.var_kind = torch.tensor(kinds, **i32)
@@ -92,8 +93,20 @@ class VarLayout:
         return torch.stack([nm, nv, lvy, div])
 
 
+def _storage_code(t, base_dtype, what):
+    """Storage code of `data` / `mask`: uint8 (bool) travels as is, anything else is brought to the
+    storage dtype of theta."""
+    if t.dtype in (torch.uint8, torch.bool):
+        t = t.detach().contiguous()
+        return (t.view(torch.uint8) if t.dtype == torch.bool else t), _lib.U8
+    return t.detach().to(base_dtype).contiguous(), (_lib.F64 if base_dtype == torch.float64 else _lib.F32)
+
+
 class _FusedLoglik(torch.autograd.Function):
-    """(theta, vparam) -> log_p_x, log_p_x_missing, params, recon_mean, recon_mode, data_tr."""
+    """(theta, vparam) -> log_p_x, log_p_x_missing, params, log_p_x_sum[, recon_mean, recon_mode, data_tr].
+
+    log_p_x_sum (float64 scalar) is accumulated inside the forward kernel; when a loss uses only
+    the sum (training.py:83,104: -sum(log_p_x)), backward never materialises an [N, D] gradient."""
 
     @staticmethod
     def forward(ctx, theta, vparam, data, mask, layout, monitor):
@@ -104,44 +117,46 @@ class _FusedLoglik(torch.autograd.Function):
         dt = theta.dtype
         dcode = _lib.dtype_code(theta)
         th = theta.detach().contiguous()
-        da = data.detach().to(dt).contiguous()
-        mask_u8 = mask.dtype in (torch.uint8, torch.bool)
-        mk = mask.detach().contiguous() if mask_u8 else mask.detach().to(dt).contiguous()
-        if mk.dtype == torch.bool:
-            mk = mk.view(torch.uint8)
+        da, da_code = _storage_code(data, dt, "data")
+        mk, mk_code = _storage_code(mask, dt, "mask")
         vp = vparam.detach().to(torch.float64).contiguous()
         new = lambda *s: torch.empty(*s, dtype=dt, device=th.device)
         lpx, lpm, prm = new(N, D), new(N, D), new(N, layout.P_theta)
         rmean = new(N, D) if monitor else None
         rmode = new(N, D) if monitor else None
         dtr = new(N, D) if monitor else None
+        total = torch.zeros((), dtype=torch.float64, device=th.device)
         if N > 0:
-          _lib.call("hlvae_loglik_fwd", N, D, layout.E_x, layout.P_theta, _lib.ptr(layout.var_kind),
-                                               _lib.ptr(layout.var_nclass), _lib.ptr(layout.var_dcol),
-                                               _lib.ptr(layout.var_pcol), _lib.ptr(vp), _lib.ptr(da), _lib.ptr(th),
-                                               _lib.ptr(mk), dcode, int(mask_u8), _lib.ptr(lpx), _lib.ptr(lpm),
-                                               _lib.ptr(prm), _lib.ptr(rmean), _lib.ptr(rmode), _lib.ptr(dtr), None,
-                                               _lib.stream_ptr())
-        ctx.layout, ctx.mask_u8, ctx.dcode = layout, mask_u8, dcode
+            _lib.call("hlvae_loglik_fwd", N, D, layout.E_x, layout.P_theta, _lib.ptr(layout.var_kind),
+                      _lib.ptr(layout.var_nclass), _lib.ptr(layout.var_dcol), _lib.ptr(layout.var_pcol), _lib.ptr(vp),
+                      _lib.ptr(da), _lib.ptr(th), _lib.ptr(mk), dcode, da_code, mk_code, layout.max_class, _lib.ptr(lpx), _lib.ptr(lpm),
+                      _lib.ptr(prm), _lib.ptr(rmean), _lib.ptr(rmode), _lib.ptr(dtr), _lib.ptr(total),
+                      _lib.stream_ptr())
+        ctx.layout, ctx.codes = layout, (dcode, da_code, mk_code)
         ctx.save_for_backward(th, vp, da, mk)
-        outs = (lpx, lpm, prm) + ((rmean, rmode, dtr) if monitor else ())
-        ctx.mark_non_differentiable(*outs[1:])
+        ctx.set_materialize_grads(False)
+        outs = (lpx, lpm, prm, total) + ((rmean, rmode, dtr) if monitor else ())
+        ctx.mark_non_differentiable(lpm, prm, *outs[4:])
         return outs
 
     @staticmethod
-    def backward(ctx, g_lpx, *unused):
+    def backward(ctx, g_lpx, g_lpm, g_prm, g_total, *unused):
         th, vp, da, mk = ctx.saved_tensors
         layout = ctx.layout
+        dcode, da_code, mk_code = ctx.codes
         N, D = th.shape[0], layout.D
-        g = g_lpx.to(th.dtype).contiguous()
         g_theta = torch.empty_like(th)
         g_lvy = torch.zeros(D, dtype=torch.float64, device=th.device)
+        if g_lpx is None and g_total is None:
+            return torch.zeros_like(th), torch.zeros_like(vp), None, None, None, None
+        g = g_lpx.to(th.dtype).contiguous() if g_lpx is not None else None
+        gs = g_total.detach().to(torch.float64).reshape(1).contiguous() if g_total is not None else None
         if N > 0:
-          _lib.call("hlvae_loglik_bwd", N, D, layout.E_x, layout.P_theta, _lib.ptr(layout.var_kind),
-                                               _lib.ptr(layout.var_nclass), _lib.ptr(layout.var_dcol),
-                                               _lib.ptr(layout.var_pcol), _lib.ptr(vp), _lib.ptr(da), _lib.ptr(th),
-                                               _lib.ptr(mk), ctx.dcode, int(ctx.mask_u8), _lib.ptr(g), 0.0,
-                                               _lib.ptr(g_theta), _lib.ptr(g_lvy), _lib.stream_ptr())
+            _lib.call("hlvae_loglik_bwd", N, D, layout.E_x, layout.P_theta, _lib.ptr(layout.var_kind),
+                      _lib.ptr(layout.var_nclass), _lib.ptr(layout.var_dcol), _lib.ptr(layout.var_pcol), _lib.ptr(vp),
+                      _lib.ptr(da), _lib.ptr(th), _lib.ptr(mk), dcode, da_code, mk_code, layout.max_class, _lib.ptr(g),
+                      _lib.ptr(gs),
+                      _lib.ptr(g_theta), _lib.ptr(g_lvy), _lib.stream_ptr())
         g_vp = torch.zeros_like(vp)
         g_vp[2] = g_lvy
         return g_theta, g_vp, None, None, None, None
@@ -149,9 +164,10 @@ class _FusedLoglik(torch.autograd.Function):
 
 def fused_loglik(layout, data, mask, theta, vparam, monitor=True):
     """All type groups in one launch.  Returns a dict with log_p_x, log_p_x_missing [N,D], params
-    [N,P_theta] and (monitor=True) recon_mean, recon_mode, data_transformed [N,D]."""
+    [N,P_theta], log_p_x_sum (float64 scalar = log_p_x.sum(), differentiable) and (monitor=True)
+    recon_mean, recon_mode, data_transformed [N,D].  `data` and `mask` may be uint8."""
     outs = _FusedLoglik.apply(theta, vparam, data, mask, layout, monitor)
-    names = ("log_p_x", "log_p_x_missing", "params", "recon_mean", "recon_mode", "data_transformed")
+    names = ("log_p_x", "log_p_x_missing", "params", "log_p_x_sum", "recon_mean", "recon_mode", "data_transformed")
     return dict(zip(names, outs))
 
 

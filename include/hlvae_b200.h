@@ -39,6 +39,7 @@ extern "C" {
 
 #define HLVAE_F32 0
 #define HLVAE_F64 1
+#define HLVAE_U8 2          /* exact small integers: masks, one-hot / thermometer codes, pixel values */
 
 #define HLVAE_KIND_CAT 1    /* kernel_spec.py:26-32  CatKernel: x1 == x2           */
 #define HLVAE_KIND_BIN 2    /* kernel_spec.py:9-23   BinKernel: x1 + x2 == 2       */
@@ -175,11 +176,18 @@ int hlvae_natgrad_update(int L, int M, double lr, const double* m, const double*
  * column in data), var_pcol[d] (first column in theta / params); vparam [4, D] float64 holds
  * per variable {normalisation mean, normalisation variance (already clamped), raw
  * log-variance parameter, data divisor (255 for conv real data, else 1)}.
- *   data [N,E_x], theta [N,P_theta], mask [N,D]: storage `dtype`; mask_u8 != 0: mask is uint8.
+ * Packed layout: variable d occupies columns [var_dcol[d], var_dcol[d] + nclass[d]) of data and
+ * [var_pcol[d], ...) of theta, and var_dcol / var_pcol increase with d (read_functions.py:144-173
+ * builds exactly this); a CTA stages the contiguous span of a tile of <= 128 variables.
+ *   theta [N,P_theta] and every output: storage `dtype` (HLVAE_F32 / HLVAE_F64), which also selects
+ *   the arithmetic: float64 storage -> float64 math; float32 storage -> float32 SFU math with exact
+ *   float64 re-evaluation of categorical / ordinal argmax decisions that float32 cannot prove.
+ *   data [N,E_x]: `data_dtype` = dtype or HLVAE_U8;  mask [N,D]: `mask_dtype` = dtype or HLVAE_U8.
+ *   max_class = max_d nclass[d] (sizes the shared-memory staging of a row batch).
  * fwd outputs (nullable): log_p_x, log_p_x_missing [N,D], params [N,P_theta], recon_mean,
- *   recon_mode, data_tr [N,D] in storage dtype; ll_total[1] float64 += sum(log_p_x).
- * bwd: g_lp [N,D] upstream gradient of log_p_x (nullable: then g_scalar is used for every
- *   element) -> g_theta [N,P_theta] (overwritten), g_lvy [D] float64 (accumulated).
+ *   recon_mode, data_tr [N,D]; ll_total[1] float64 += sum(log_p_x)  (HLVAE.py:377-379 summed).
+ * bwd: upstream gradient of log_p_x = g_lp[n,d] (nullable) + *g_scalar (device scalar, nullable:
+ *   the gradient of ll_total) -> g_theta [N,P_theta] (overwritten), g_lvy [D] float64 (accumulated).
  * ---------------------------------------------------------------------------------- */
 #define HLVAE_VAR_REAL 0
 #define HLVAE_VAR_POS 1
@@ -191,14 +199,15 @@ int hlvae_natgrad_update(int L, int M, double lr, const double* m, const double*
 int hlvae_loglik_fwd(int64_t N, int D, int64_t ld_data, int64_t ld_theta,
                      const int32_t* var_kind, const int32_t* var_nclass, const int32_t* var_dcol,
                      const int32_t* var_pcol, const double* vparam,
-                     const void* data, const void* theta, const void* mask, int dtype, int mask_u8,
-                     void* log_p_x, void* log_p_x_missing, void* params,
+                     const void* data, const void* theta, const void* mask, int dtype, int data_dtype,
+                     int mask_dtype, int max_class, void* log_p_x, void* log_p_x_missing, void* params,
                      void* recon_mean, void* recon_mode, void* data_tr, double* ll_total, void* stream);
 int hlvae_loglik_bwd(int64_t N, int D, int64_t ld_data, int64_t ld_theta,
                      const int32_t* var_kind, const int32_t* var_nclass, const int32_t* var_dcol,
                      const int32_t* var_pcol, const double* vparam,
-                     const void* data, const void* theta, const void* mask, int dtype, int mask_u8,
-                     const void* g_lp, double g_scalar, void* g_theta, double* g_lvy, void* stream);
+                     const void* data, const void* theta, const void* mask, int dtype, int data_dtype,
+                     int mask_dtype, int max_class, const void* g_lp, const double* g_scalar, void* g_theta,
+                     double* g_lvy, void* stream);
 
 /* Stand-alone forms of the monitoring transforms for callers that hold only `params` or
  * `data` (training.py:84-91): read_functions.statistics (:268-302) -> mean, mode [N,D];

@@ -3,7 +3,7 @@ rows = list(csv.reader(open(sys.argv[1])))
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 cur = None; hdr = None; data = []
 for r in rows:
-    if r and r[0] == 'File Name':
+    if r and r[0] in ('File Name','File Path'):
         cur = r[1].split('/')[-1]; continue
     if r and r[0] == 'Line No':
         hdr = r; continue
