@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--subjects", type=int, default=SUBJ_PER_RANK)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="time eager launches instead of CUDA-graph replay")
     return ap.parse_args()
 
 
@@ -215,31 +216,32 @@ def build_gpu_state(dev, n_subj, rank, seed=0):
                 log_vy_real=log_vy_real, layout=subjects.SubjectLayout.from_lengths(lens, dev), n_subj=n_subj, N_b=N_b)
 
 
-def elbo_step(s, world, host=None):
-    """One ELBO-path step through the public (reference-shaped) functions.  With `host`, the step's
-    inputs first travel from pinned host memory and the loss is read back."""
+INPUT_KEYS = ("data", "mask", "x", "theta", "mu", "lv")
+
+
+def elbo_step(s, world, inp=None):
+    """One ELBO-path step through the public (reference-shaped) functions: training.py:82-137 minus the
+    NN trunk and Adam.  `inp` (default: s) holds the step's inputs data / mask / x / theta / mu / lv; the
+    replicated state (kernels, Z, m, H, log-variances) lives in `s` and is updated in place, so the
+    function can be captured into a CUDA graph (hlvae_b200.graph.StepGraph)."""
     from hlvae_b200 import elbo, loglik
-    if host is not None:
-        dev = s["x"].device
-        for k in ("data", "mask", "x"):
-            s[k] = host[k].to(dev, non_blocking=True)
-        for k in ("theta", "mu", "lv"):
-            s[k] = host[k].to(dev, non_blocking=True).requires_grad_(True)
-    for t_ in (s["theta"], s["mu"], s["lv"], s["z"], s["log_vy_real"], *s["k0"].parameters(), *s["k1"].parameters()):
+    inp = s if inp is None else inp
+    for t_ in (inp["theta"], inp["mu"], inp["lv"], s["z"], s["log_vy_real"], *s["k0"].parameters(),
+               *s["k1"].parameters()):
         t_.grad = None
     P_b = s["n_subj"] * world
     vparam = s["lay"].vparam(log_vy_real=s["log_vy_real"], conv=True)
-    out = loglik.fused_loglik(s["lay"], s["data"], s["mask"], s["theta"], vparam, monitor=True)
+    out = loglik.fused_loglik(s["lay"], inp["data"], inp["mask"], inp["theta"], vparam, monitor=True)
     nll = -out["log_p_x_sum"] * (P_TOTAL / P_b)                                             # training.py:83,104,122
-    kld, gm, gH = elbo.minibatch_KLD_upper_bound_iter(s["k0"], s["k1"], s["lik"], L, s["m"], s["H"], s["x"], s["mu"],
-                                                      s["lv"], s["z"], P_TOTAL, P_b, N_TOTAL, True, 2, EPS,
-                                                      layout=s["layout"])                     # training.py:110-113
+    kld, gm, gH = elbo.minibatch_KLD_upper_bound_iter(s["k0"], s["k1"], s["lik"], L, s["m"], s["H"], inp["x"],
+                                                      inp["mu"], inp["lv"], s["z"], P_TOTAL, P_b, N_TOTAL, True, 2,
+                                                      EPS, layout=s["layout"])                # training.py:110-113
     loss = nll + kld                                                                           # :124
     loss.backward()                                                                            # :127
-    s["m"], s["H"] = elbo.natural_gradient_update(s["m"], s["H"], gm, gH, NG_LR)               # :130-137
-    if host is not None:
-        return float(loss.item())
-    return loss
+    m_new, H_new = elbo.natural_gradient_update(s["m"], s["H"], gm, gH, NG_LR)                 # :130-137
+    s["m"].copy_(m_new)
+    s["H"].copy_(H_new)
+    return loss.detach()
 
 
 ALGO = {}
@@ -279,31 +281,45 @@ def run_gpu(args):
     s = build_gpu_state(dev, args.subjects, rank)
     n_rows = s["N_b"]
     algorithmic_work(n_rows, args.subjects)
+    fp64_peak = measure_fp64_peak(dev)       # before any graph capture (uses the RNG)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        elbo_step(s, world)
+    from hlvae_b200.graph import StepGraph
+    m0, H0 = s["m"].clone(), s["H"].clone()
+
+    def reset_state():
+        s["m"].copy_(m0)
+        s["H"].copy_(H0)
+
+    # ---- timed region: the step captured once into a CUDA graph and replayed (hlvae_b200.graph)
+    warm = max(args.warmup, 3)
+    use_graph = not args.eager
+    graph = None
+    if use_graph:
+        try:
+            graph = StepGraph(lambda: elbo_step(s, world), warmup=warm)
+        except Exception as e:                    # report, then measure the eager path instead
+            print(f"[bench] CUDA-graph capture failed ({e!r}); timing the eager path", file=sys.stderr, flush=True)
+            use_graph = False
+    run_step = (graph.replay if use_graph else (lambda: elbo_step(s, world)))
+    for _ in range(warm):
+        run_step()
     barrier()
+    reset_state()
     sampler = ClockSampler(local)
     sampler.start()
-    _lib.PROFILE = []
-    launches0 = _lib.LAUNCHES
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
     for _ in range(args.steps):
-        elbo_step(s, world)
+        run_step()
     e1.record()
     barrier()
-    sampler.stop_flag = True
     total_ms = e0.elapsed_time(e1)
-    prof = _lib.PROFILE
-    _lib.PROFILE = None
-    launches = _lib.LAUNCHES - launches0
     if world > 1:
         tt = torch.tensor([total_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -311,13 +327,34 @@ def run_gpu(args):
     ms_per_step = total_ms / args.steps
     value = world * (n_rows / (SUBJ_PER_RANK * T)) * 1e3 / ms_per_step
 
+    # ---- the same step launched eagerly, every C-ABI call bracketed by CUDA events on its stream
+    # (events cannot be read back from inside a replayed graph): per-kernel durations + eager step time
+    reset_state()
+    n_prof = max(3, min(args.steps, 20))
+    for _ in range(2):
+        elbo_step(s, world)
+    barrier()
+    _lib.PROFILE = []
+    launches0 = _lib.LAUNCHES
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for _ in range(n_prof):
+        elbo_step(s, world)
+    p1.record()
+    barrier()
+    sampler.stop_flag = True
+    eager_ms = p0.elapsed_time(p1) / n_prof
+    prof = _lib.PROFILE
+    _lib.PROFILE = None
+    launches_per_step = (_lib.LAUNCHES - launches0) // n_prof
+    launches = launches_per_step * args.steps
+
     # per-kernel device time inside the timed region
     per = {}
     for name, a, b in prof:
         per.setdefault(name, []).append(a.elapsed_time(b))
-    kern = {k: dict(ms_avg=float(np.mean(v)), launches_per_step=len(v) / args.steps) for k, v in per.items()}
+    kern = {k: dict(ms_avg=float(np.mean(v)), launches_per_step=len(v) / n_prof) for k, v in per.items()}
     hbm_peak, peak_src = measured_peaks()
-    fp64_peak = measure_fp64_peak(dev)
     for k, d in kern.items():
         if k in ALGO:
             bound, work = ALGO[k]
@@ -337,26 +374,77 @@ def run_gpu(args):
                              "FP64 DGEMM 4096^3 measured in this run (cuBLAS; MEASURED_PEAKS.json has no FP64 entry)"),
                 ms_avg=kern[top]["ms_avg"])
 
-    # end to end: host (pinned) inputs, H2D every step, loss read back
+    # ---- end to end: every step's inputs travel from pinned host memory and its loss is read back.
+    # Two device input sets: the copy stream fills one while the graph of the other runs.
     e2e = None
     if not args.no_e2e:
-        host = {k: s[k].detach().cpu().pin_memory() for k in ("data", "mask", "x", "theta", "mu", "lv")}
+        reset_state()
+        host = {k: s[k].detach().cpu().pin_memory() for k in INPUT_KEYS}
         h2d = sum(v.numel() * v.element_size() for v in host.values())
+        sets = []
         for _ in range(2):
-            elbo_step(s, world, host)
+            d = {k: torch.empty_like(s[k]) for k in ("data", "mask", "x")}
+            d.update({k: torch.empty_like(s[k]).requires_grad_(True) for k in ("theta", "mu", "lv")})
+            sets.append(d)
+        copy_stream = torch.cuda.Stream()
+        loss_host = [torch.zeros(1, dtype=torch.float64).pin_memory() for _ in range(2)]
+
+        def upload(b):
+            with torch.no_grad():
+                for k in INPUT_KEYS:
+                    sets[b][k].copy_(host[k], non_blocking=True)
+
+        upload(0), upload(1)
+        torch.cuda.synchronize()
+        steps_e = []
+        for b in range(2):
+            fn = (lambda bb: (lambda: elbo_step(s, world, sets[bb])))(b)
+            steps_e.append(StepGraph(fn, warmup=1).replay if use_graph else fn)
+        n_e2e = max(4, min(args.steps, 20))
+        copied = [torch.cuda.Event() for _ in range(2)]
+        done = [torch.cuda.Event() for _ in range(2)]
+        losses = []
+
+        def e2e_loop(n):
+            cur = torch.cuda.current_stream()
+            with torch.cuda.stream(copy_stream):
+                upload(0)
+                copied[0].record(copy_stream)
+            for i in range(n):
+                b = i & 1
+                cur.wait_event(copied[b])
+                loss = steps_e[b]()
+                loss_host[b].copy_(loss.reshape(1), non_blocking=True)
+                done[b].record(cur)
+                if i + 1 < n:
+                    with torch.cuda.stream(copy_stream):
+                        if i >= 1:
+                            copy_stream.wait_event(done[1 - b])       # that buffer's previous step has finished
+                        upload(1 - b)
+                        copied[1 - b].record(copy_stream)
+                if i >= 1:                                            # read the previous step's loss (host side)
+                    done[1 - b].synchronize()
+                    losses.append(float(loss_host[1 - b]))
+            done[(n - 1) & 1].synchronize()
+            losses.append(float(loss_host[(n - 1) & 1]))
+
+        e2e_loop(3)
         barrier()
+        x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
-        n_e2e = max(3, min(args.steps, 10))
-        for _ in range(n_e2e):
-            elbo_step(s, world, host)
+        x0.record()
+        e2e_loop(n_e2e)
+        x1.record()
         barrier()
-        dt = time.perf_counter() - t0
+        dt = max(time.perf_counter() - t0, x0.elapsed_time(x1) * 1e-3)
         if world > 1:
             tt = torch.tensor([dt], device=dev, dtype=torch.float64)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             dt = float(tt.item())
         e2e = dict(value=world * (n_rows / (SUBJ_PER_RANK * T)) * n_e2e / dt, unit="steps/s", h2d_bytes_per_step=h2d,
-                   d2h_bytes_per_step=8, steps=n_e2e)
+                   d2h_bytes_per_step=8, steps=n_e2e,
+                   how="pinned host -> device copy of data, mask, covariates, theta, mu, log_v every step on a copy "
+                       "stream (double-buffered against the running step), loss copied back and read every step")
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -372,7 +460,9 @@ def run_gpu(args):
                                 l2="inputs larger than L2 (data + theta = 415 MB per step, 126 MB L2)",
                                 parallelism=f"dp{world}: subjects sharded, one all-reduce of accumulators" if world > 1 else "single GPU"),
                     clocks=sampler.summary(), e2e=e2e, gpu_launches=launches, roofline=roof, cpu_baseline=cpu,
-                    kernels=kern, fp64_peak_tflops=fp64_peak)
+                    kernels=kern, fp64_peak_tflops=fp64_peak, cuda_graph=use_graph, eager_ms_per_step=eager_ms,
+                    kernel_timing="CUDA events around every C-ABI call in an eager pass of the same step run right "
+                                  "after the timed region (events are not readable inside a replayed graph)")
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -63,6 +63,8 @@ class Kernel(nn.Module):
         if active_dims is not None and not torch.is_tensor(active_dims):
             active_dims = torch.tensor(active_dims, dtype=torch.long)
         self.register_buffer("active_dims", active_dims)
+        # host copy of the covariate column: compile_spec runs every step and must not read the device
+        self._columns = None if active_dims is None else [int(v) for v in active_dims.reshape(-1).tolist()]
         if has_lengthscale is None:
             has_lengthscale = type(self).has_lengthscale
         if has_lengthscale:
@@ -88,10 +90,9 @@ class Kernel(nn.Module):
     def _column(self):
         if self.active_dims is None:
             raise ValueError(f"{type(self).__name__} needs active_dims (a covariate column)")
-        a = self.active_dims.reshape(-1)
-        if a.numel() != 1:
+        if len(self._columns) != 1:
             raise ValueError("only one covariate column per base kernel is supported")
-        return int(a[0])
+        return self._columns[0]
 
     def __call__(self, x1, x2=None, **params):
         return _LazyKernelTensor(self, x1, x1 if x2 is None else x2)
