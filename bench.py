@@ -465,7 +465,12 @@ def run_gpu(args):
                                   "after the timed region (events are not readable inside a replayed graph)")
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Tearing down a NCCL communicator whose collectives were captured into still-live CUDA graphs can
+        # block; the result line is out, so synchronise, meet the other ranks and leave.
+        sys.stdout.flush()
+        torch.cuda.synchronize()
+        dist.barrier()
+        os._exit(0)
 
 
 def main():

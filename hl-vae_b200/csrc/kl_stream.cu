@@ -264,6 +264,7 @@ kl_subject_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict
 // =====================================================================================
 constexpr int PN_THREADS = 512;
 constexpr int PN_SMAX = 16;   // subjects per panel
+constexpr int PN_NCACHE = 3;  // K0 components whose unscaled values are kept from the K0xz pass to the gradient pass
 
 // One component's descriptor pulled into registers field by field (a struct copy indexed by a
 // run-time component number would be placed in local memory).
@@ -289,8 +290,8 @@ struct PanelSmem {
                                       2 * (size_t)RP * LD /*Kb,Vb*/ + (size_t)RP * LDB /*Bp*/ +
                                       (size_t)RP * HLVAE_MAX_Q /*xs*/ + 3 * RP /*mus, rv, rho*/ +
                                       (size_t)MP * HLVAE_MAX_COMPS /*zacc*/ + 4 * HLVAE_MAX_COMPS + 8 /*hyper acc + A*/ +
-                                      4 * HLVAE_MAX_COMPS /*kps*/;
-    static constexpr size_t ints = 2 * RP + 2 * (PN_SMAX + 1) + 8;
+                                      8 * HLVAE_MAX_COMPS /*kps, kps1*/ + (size_t)PN_NCACHE * RP * MP /*vc*/;
+    static constexpr size_t ints = 2 * RP + 3 * (PN_SMAX + 1) + 8;
     static constexpr size_t bytes = doubles * 8 + ints * 4;
 };
 
@@ -326,11 +327,14 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
     double* zacc = rho + RP;                                   // [MP][MAX_COMPS]
     double* hyp = zacc + MP * HLVAE_MAX_COMPS;                 // gos0, gls0, gos1, gls1, A
     double* kps = hyp + 4 * HLVAE_MAX_COMPS + 8;               // K0 hyper-parameters by component: os, hil2, il2, il3
-    int* grow = reinterpret_cast<int*>(kps + 4 * HLVAE_MAX_COMPS);
+    double* kps1 = kps + 4 * HLVAE_MAX_COMPS;                  // same for K1
+    double* vc = kps1 + 4 * HLVAE_MAX_COMPS;                   // [PN_NCACHE][RP][MP] unscaled component values (0 = no match)
+    int* grow = reinterpret_cast<int*>(vc + PN_NCACHE * RP * MP);
     int* sub_of_row = grow + RP;
     int* sub_r0 = sub_of_row + RP;                             // [PN_SMAX+1]
-    int* sub_b0 = sub_r0 + PN_SMAX + 1;                        // [PN_SMAX+1]
-    int* meta = sub_b0 + PN_SMAX + 1;                          // nsub, first subject, next subject
+    int* sub_b0 = sub_r0 + PN_SMAX + 1;                        // [PN_SMAX+1] offsets of the T x T blocks
+    int* sub_t0 = sub_b0 + PN_SMAX + 1;                        // [PN_SMAX+1] offsets of the lower triangles
+    int* meta = sub_t0 + PN_SMAX + 1;                          // nsub, first subject, next subject
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wi = warp >> 2, wj = warp & 3;
@@ -339,10 +343,6 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
     const int s_end = min(n_subj, s_begin + subj_per_chunk);
     const int em = tid % MP;                                   // this thread's inducing point in element-wise phases
     const int eg = tid / MP;                                   // and its row group
-
-    KParams kp0, kp1;
-    load_kparams(kp0, sp0, os0, ls0, L, l);
-    load_kparams(kp1, sp1, os1, ls1, L, l);
 
     // ---- per-CTA setup: inducing points of this latent dim (transposed), w, G
     for (int e = tid; e < HLVAE_MAX_Q * MP; e += PN_THREADS) {
@@ -370,6 +370,20 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
         kps[HLVAE_MAX_COMPS + tid] = h;
         kps[2 * HLVAE_MAX_COMPS + tid] = i2;
         kps[3 * HLVAE_MAX_COMPS + tid] = i3;
+    } else if (tid < 2 * HLVAE_MAX_COMPS) {
+        const int r = tid - HLVAE_MAX_COMPS;
+        double o = 0.0, h = 0.0, i2 = 0.0, i3 = 0.0;
+        if (r < sp1.ncomp) {
+            o = os1[(int64_t)r * L + l];
+            const double e_ = ls1[(int64_t)r * L + l];
+            i2 = 1.0 / (e_ * e_);
+            h = 0.5 * i2;
+            i3 = i2 / e_;
+        }
+        kps1[r] = o;
+        kps1[HLVAE_MAX_COMPS + r] = h;
+        kps1[2 * HLVAE_MAX_COMPS + r] = i2;
+        kps1[3 * HLVAE_MAX_COMPS + r] = i3;
     }
     const double* Gl = G + (int64_t)l * M * M;
 
@@ -387,10 +401,11 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
     while (true) {
         // ---- P0: pack whole subjects into a panel of at most RP rows
         if (tid == 0) {
-            int s = meta[2], ns = 0, rows = 0, bsz = 0;
+            int s = meta[2], ns = 0, rows = 0, bsz = 0, tsz = 0;
             meta[1] = s;
             sub_r0[0] = 0;
             sub_b0[0] = 0;
+            sub_t0[0] = 0;
             while (s < s_end && ns < PN_SMAX) {
                 int T = subj_ptr[s + 1] - subj_ptr[s];
                 if (T > HLVAE_TMAX) {   // reported by kl_subject_k as well; skip here
@@ -400,10 +415,12 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
                 if (rows + T > RP) break;
                 rows += T;
                 bsz += T * T;
+                tsz += T * (T + 1) / 2;
                 ns++;
                 s++;
                 sub_r0[ns] = rows;
                 sub_b0[ns] = bsz;
+                sub_t0[ns] = tsz;
             }
             meta[0] = ns;
             meta[2] = s;
@@ -470,14 +487,16 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
                                     const double a = xr[c.disc_col[f]];
                                     ok = ok && ((c.disc_kind[f] == HLVAE_KIND_CAT) ? (a == zd[f]) : (a + zd[f] == 2.0));
                                 }
+                            double v = 0.0;
                             if (ok) {
-                                double v = 1.0;
+                                v = 1.0;
                                 if (c.se_col >= 0) {
                                     const double d = xr[c.se_col] - zse;
                                     v = exp(-(d * d) * hil2);
                                 }
                                 kacc[k] = fma(osr, v, kacc[k]);
                             }
+                            if (r < PN_NCACHE) vc[(r * RP + row) * MP + em] = v;
                         }
                     }
                 }
@@ -603,8 +622,8 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
         }
         __syncthreads();
 
-        // ---- P5a: dJ/dB_s (K0xz part) = -1/2 (rho rho^T + W V^T) for the 8x8 tiles that meet the block
-        // diagonal, on the FP64 tensor pipe, written over the dense panel Bp
+        // ---- P5a: dJ/dB_s (K0xz part) = -1/2 (rho rho^T + W V^T), symmetric: only the 8x8 tiles on or below
+        // the diagonal that meet the block diagonal, on the FP64 tensor pipe, written over the dense panel Bp
         {
             const int nrt = R8 / 8;
             const int ar = lane >> 2, ac = lane & 3;
@@ -613,7 +632,7 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
                 const int rl = min(rt * 8 + 7, R - 1), cl = min(ct * 8 + 7, R - 1);
                 const int s_r0 = sub_of_row[rt * 8], s_r1 = sub_of_row[rl];
                 const int s_c0 = sub_of_row[ct * 8], s_c1 = sub_of_row[cl];
-                if (s_r0 <= s_c1 && s_c0 <= s_r1) {
+                if (ct <= rt && s_r0 <= s_c1 && s_c0 <= s_r1) {
                     double c0 = 0.0, c1 = 0.0;
                     for (int m0 = 0; m0 < MP; m0 += 4) {
                         const double a = Kb[(rt * 8 + ar) * LD + m0 + ac];
@@ -641,74 +660,120 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
                 CompRegs c;
                 c.load(sp0, r);
                 const double zse = (c.se_col >= 0) ? Zs[c.se_col * MP + em] : 0.0;
-                double zd[HLVAE_MAX_DISC];
-#pragma unroll
-                for (int f = 0; f < HLVAE_MAX_DISC; f++) zd[f] = (f < c.ndisc) ? Zs[c.disc_col[f] * MP + em] : 0.0;
                 const double osr = kps[r], hil2 = kps[HLVAE_MAX_COMPS + r], il2 = kps[2 * HLVAE_MAX_COMPS + r],
                              il3 = kps[3 * HLVAE_MAX_COMPS + r];
-                double gos = 0.0, gls = 0.0, gz = 0.0;
+                // sums of g v, g v d, g v d^2 over this thread's rows (d = x - z); outputscale and lengthscale
+                // factors are applied once at the end
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0;
                 if (em < M) {
+                    if (r < PN_NCACHE) {
+                        const double* vr = vc + (size_t)r * RP * MP + em;
+                        if (c.se_col >= 0) {
 #pragma unroll
-                    for (int k = 0; k < RPT; k++) {
-                        const int row = eg + k * NGRP;
-                        if (row < R) {
-                            const double* xr = xs + row * Q;
-                            bool ok = true;
+                            for (int k = 0; k < RPT; k++) {
+                                const int row = eg + k * NGRP;
+                                if (row < R) {
+                                    const double gkv = gk[k] * vr[row * MP];
+                                    const double d = xs[row * Q + c.se_col] - zse;
+                                    const double t = gkv * d;
+                                    s0 += gkv;
+                                    s1 += t;
+                                    s2 = fma(t, d, s2);
+                                }
+                            }
+                        } else {
 #pragma unroll
-                            for (int f = 0; f < HLVAE_MAX_DISC; f++)
-                                if (f < c.ndisc) {
-                                    const double a = xr[c.disc_col[f]];
-                                    ok = ok && ((c.disc_kind[f] == HLVAE_KIND_CAT) ? (a == zd[f]) : (a + zd[f] == 2.0));
+                            for (int k = 0; k < RPT; k++) {
+                                const int row = eg + k * NGRP;
+                                if (row < R) s0 = fma(gk[k], vr[row * MP], s0);
+                            }
+                        }
+                    } else {
+                        double zd[HLVAE_MAX_DISC];
+#pragma unroll
+                        for (int f = 0; f < HLVAE_MAX_DISC; f++) zd[f] = (f < c.ndisc) ? Zs[c.disc_col[f] * MP + em] : 0.0;
+#pragma unroll
+                        for (int k = 0; k < RPT; k++) {
+                            const int row = eg + k * NGRP;
+                            if (row < R) {
+                                const double* xr = xs + row * Q;
+                                bool ok = true;
+#pragma unroll
+                                for (int f = 0; f < HLVAE_MAX_DISC; f++)
+                                    if (f < c.ndisc) {
+                                        const double a = xr[c.disc_col[f]];
+                                        ok = ok && ((c.disc_kind[f] == HLVAE_KIND_CAT) ? (a == zd[f]) : (a + zd[f] == 2.0));
+                                    }
+                                if (ok) {
+                                    double v = 1.0, d = 0.0;
+                                    if (c.se_col >= 0) {
+                                        d = xr[c.se_col] - zse;
+                                        v = exp(-(d * d) * hil2);
+                                    }
+                                    const double gkv = gk[k] * v;
+                                    const double t = gkv * d;
+                                    s0 += gkv;
+                                    s1 += t;
+                                    s2 = fma(t, d, s2);
                                 }
-                            if (ok) {
-                                double v = 1.0, d = 0.0;
-                                if (c.se_col >= 0) {
-                                    d = xr[c.se_col] - zse;
-                                    v = exp(-(d * d) * hil2);
-                                }
-                                const double gkv = gk[k] * v;
-                                gos += gkv;
-                                const double t = gkv * osr * d;
-                                gls = fma(t * d, il3, gls);
-                                gz = fma(t, il2, gz);
                             }
                         }
                     }
                 }
-                gos = warp_sum(gos);
-                gls = warp_sum(gls);
+                const double gos = warp_sum(s0);
+                const double gls = warp_sum(s2) * osr * il3;
                 if (lane == 0) {
                     atomicAdd(&hyp[r], gos);
                     atomicAdd(&hyp[HLVAE_MAX_COMPS + r], gls);
                 }
-                if (c.se_col >= 0 && gz != 0.0) atomicAdd(&zacc[em * HLVAE_MAX_COMPS + r], gz);
+                if (c.se_col >= 0 && s1 != 0.0) atomicAdd(&zacc[em * HLVAE_MAX_COMPS + r], s1 * osr * il2);
             }
         }
         __syncthreads();
 
-        // ---- P6: contract dJ/dB_s with dB_s/d(theta1)
+        // ---- P6: contract dJ/dB_s (symmetric: lower triangle, off-diagonal entries twice) with dB_s/d(theta1)
         {
-            double gos[HLVAE_MAX_COMPS], gls[HLVAE_MAX_COMPS], dummy[HLVAE_MAX_COMPS];
+            const int nt = sub_t0[nsub];
+            for (int r = 0; r < sp1.ncomp; r++) {
+                CompRegs c;
+                c.load(sp1, r);
+                const double osr = kps1[r], hil2 = kps1[HLVAE_MAX_COMPS + r], il3 = kps1[3 * HLVAE_MAX_COMPS + r];
+                double gos = 0.0, gls = 0.0;
+                int k = 0;
+                for (int e = tid; e < nt; e += PN_THREADS) {
+                    while (e >= sub_t0[k + 1]) k++;
+                    const int rs = sub_r0[k];
+                    const int le = e - sub_t0[k];
+                    int i = (int)((sqrtf(8.0f * (float)le + 1.0f) - 1.0f) * 0.5f);
+                    while (i * (i + 1) / 2 > le) i--;
+                    while ((i + 1) * (i + 2) / 2 <= le) i++;
+                    const int j = le - i * (i + 1) / 2;
+                    const double* xi = xs + (rs + i) * Q;
+                    const double* xj = xs + (rs + j) * Q;
+                    bool ok = true;
 #pragma unroll
-            for (int r = 0; r < HLVAE_MAX_COMPS; r++) gos[r] = gls[r] = dummy[r] = 0.0;
-            const int nb = sub_b0[nsub];
-            int k = 0;
-            for (int e = tid; e < nb; e += PN_THREADS) {
-                while (e >= sub_b0[k + 1]) k++;
-                const int rs = sub_r0[k], T = sub_r0[k + 1] - rs;
-                const int le = e - sub_b0[k];
-                const int i = le / T, j = le - i * T;
-                accum_grads<false>(sp1, kp1, xs + (rs + i) * Q, xs + (rs + j) * Q, Bp[(rs + i) * LDB + rs + j], gos, gls,
-                                   dummy);
-            }
-#pragma unroll
-            for (int r = 0; r < HLVAE_MAX_COMPS; r++) {
-                if (r < sp1.ncomp) {
-                    double a = warp_sum(gos[r]), b = warp_sum(gls[r]);
-                    if (lane == 0) {
-                        atomicAdd(&hyp[2 * HLVAE_MAX_COMPS + r], a);
-                        atomicAdd(&hyp[3 * HLVAE_MAX_COMPS + r], b);
+                    for (int f = 0; f < HLVAE_MAX_DISC; f++)
+                        if (f < c.ndisc) {
+                            const double a = xi[c.disc_col[f]], b2 = xj[c.disc_col[f]];
+                            ok = ok && ((c.disc_kind[f] == HLVAE_KIND_CAT) ? (a - b2 == 0.0) : (a + b2 == 2.0));
+                        }
+                    if (ok) {
+                        const double g = Bp[(rs + i) * LDB + rs + j] * (i == j ? 1.0 : 2.0);
+                        double v = 1.0, d = 0.0;
+                        if (c.se_col >= 0) {
+                            d = xi[c.se_col] - xj[c.se_col];
+                            v = exp(-(d * d) * hil2);
+                        }
+                        const double gv = g * v;
+                        gos += gv;
+                        gls = fma(gv * d, d, gls);
                     }
+                }
+                gos = warp_sum(gos);
+                gls = warp_sum(gls) * osr * il3;
+                if (lane == 0) {
+                    atomicAdd(&hyp[2 * HLVAE_MAX_COMPS + r], gos);
+                    atomicAdd(&hyp[3 * HLVAE_MAX_COMPS + r], gls);
                 }
             }
         }
@@ -793,7 +858,7 @@ int dispatch_panel(int M, const hlvae_kspec_t* spec0, const double* os0, const d
                                         tt_ptr, n_subj, subj_per_chunk, mu, ld_mu, w, G, binv, tt_total, acc, off,   \
                                         g_mu, gscale, status, st)
     if (M <= 32) { HLVAE_PANEL(32, 64, true); }
-    if (M <= 64) { HLVAE_PANEL(64, 64, true); }
+    if (M <= 64) { HLVAE_PANEL(64, 64, false); }
     if (M <= 128) { HLVAE_PANEL(128, 32, false); }
 #undef HLVAE_PANEL
     return HLVAE_E_UNSUPPORTED;
