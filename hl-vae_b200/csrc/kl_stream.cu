@@ -23,7 +23,7 @@ struct AccOff {
 // =====================================================================================
 // kl_subject_k
 // =====================================================================================
-constexpr int SJ_WARPS = 4;
+constexpr int SJ_WARPS = 2;
 
 // lower-triangle walk: element t = i (i + 1) / 2 + j, advanced by 32 per step without divisions
 struct TriIdx {
@@ -53,8 +53,44 @@ struct SqIdx {
     }
 };
 
+// One component's descriptor pulled into registers field by field (a struct copy indexed by a
+// run-time component number would be placed in local memory).
+struct CompRegs {
+    int se_col, ndisc;
+    int disc_kind[HLVAE_MAX_DISC], disc_col[HLVAE_MAX_DISC];
+    __device__ __forceinline__ void load(const hlvae_kspec_t& sp, int r) {
+        se_col = sp.comp[r].se_col;
+        ndisc = sp.comp[r].ndisc;
+#pragma unroll
+        for (int f = 0; f < HLVAE_MAX_DISC; f++) {
+            disc_kind[f] = sp.comp[r].disc_kind[f];
+            disc_col[f] = sp.comp[r].disc_col[f];
+        }
+    }
+    // unscaled value of the component at rows (xa, xb) of one covariate matrix; d = xa - xb on its SE column
+    __device__ __forceinline__ double value(const double* __restrict__ xa, const double* __restrict__ xb, double hil2,
+                                            double& d) const {
+        d = 0.0;
+        bool ok = true;
+#pragma unroll
+        for (int f = 0; f < HLVAE_MAX_DISC; f++)
+            if (f < ndisc) {
+                const double a = xa[disc_col[f]], b = xb[disc_col[f]];
+                ok = ok && ((disc_kind[f] == HLVAE_KIND_CAT) ? (a - b == 0.0) : (a + b == 2.0));
+            }
+        if (!ok) return 0.0;
+        if (se_col < 0) return 1.0;
+        d = xa[se_col] - xb[se_col];
+        return exp_nonpos(-(d * d) * hil2);
+    }
+};
+
+// Per-warp shared memory: covariate rows, three T x T matrices, and the hyper-parameters of this
+// latent dimension by component ({outputscale, 1/(2 l^2), 1/l^3} x {K0, K1}).
+constexpr int SJ_KP = 6 * HLVAE_MAX_COMPS;
+
 template <typename TS>
-__global__ void __launch_bounds__(SJ_WARPS * 32, 4)
+__global__ void __launch_bounds__(SJ_WARPS * 32, 9)
 kl_subject_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__ os0, const double* __restrict__ ls0,
              const __grid_constant__ hlvae_kspec_t sp1, const double* __restrict__ os1, const double* __restrict__ ls1,
              const double* __restrict__ noise, int L, int Q, const double* __restrict__ x, int64_t ldx,
@@ -65,11 +101,12 @@ kl_subject_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict
     extern __shared__ double smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ldt = tcap | 1;
-    const int per_warp = tcap * Q + 3 * tcap * ldt;
+    const int per_warp = tcap * Q + 3 * tcap * ldt + SJ_KP;
     double* xs = smem + (size_t)warp * per_warp;
     double* Bw = xs + tcap * Q;
     double* Bi = Bw + tcap * ldt;
     double* Ks = Bi + tcap * ldt;
+    double* kp = Ks + tcap * ldt;           // [0..8) os0, [8..16) hil2_0, [16..24) il3_0, [24..48) same for K1
 
     const int64_t pair = (int64_t)blockIdx.x * SJ_WARPS + warp;
     if (pair >= (int64_t)n_subj * L) return;
@@ -82,9 +119,6 @@ kl_subject_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict
         return;
     }
     const int TL = T * (T + 1) / 2;
-    KParams kp0, kp1;
-    load_kparams(kp0, sp0, os0, ls0, L, l);
-    load_kparams(kp1, sp1, os1, ls1, L, l);
 
     int g = -1;
     double ev = 0.0, lv = 0.0;
@@ -94,29 +128,43 @@ kl_subject_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict
         lv = (double)log_v[(int64_t)g * ld_lv + l];
         ev = exp(lv);
     }
+    if (lane < 2 * HLVAE_MAX_COMPS) {
+        const int which = lane >> 3, r = lane & 7;
+        const int nc = which ? sp1.ncomp : sp0.ncomp;
+        double o = 0.0, h = 0.0, i3 = 0.0;
+        if (r < nc) {
+            o = (which ? os1 : os0)[(int64_t)r * L + l];
+            const double e_ = (which ? ls1 : ls0)[(int64_t)r * L + l];
+            const double i2 = 1.0 / (e_ * e_);
+            h = 0.5 * i2;
+            i3 = i2 / e_;
+        }
+        kp[which * 24 + r] = o;
+        kp[which * 24 + 8 + r] = h;
+        kp[which * 24 + 16 + r] = i3;
+    }
     __syncwarp();
     const double nz = noise[l];
-    // B_s = K1(x_s, x_s) + noise I (elbo_functions.py:249-250); Ks = K0(x_s, x_s) (:248) + diag(exp(log_v)).
-    // Both are symmetric: evaluate the lower triangle and mirror.
+    // B_s = K1(x_s, x_s) + noise I (elbo_functions.py:249-250): lower triangle, mirrored
     {
         TriIdx ix;
         ix.init(lane);
         for (int t = lane; t < TL; t += 32, ix.advance32()) {
             const int i = ix.i, j = ix.j;
-            double k1 = eval_additive(sp1, kp1, xs + i * Q, xs + j * Q);
-            double k0 = eval_additive(sp0, kp0, xs + i * Q, xs + j * Q);
-            if (i == j) k1 += nz;
+            double k1 = (i == j) ? nz : 0.0;
+            for (int r = 0; r < sp1.ncomp; r++) {
+                CompRegs c;
+                c.load(sp1, r);
+                double d;
+                k1 = fma(kp[24 + r], c.value(xs + i * Q, xs + j * Q, kp[32 + r], d), k1);
+            }
             Bw[i * ldt + j] = k1;
             Bw[j * ldt + i] = k1;
-            Ks[i * ldt + j] = k0;
-            Ks[j * ldt + i] = k0;
         }
     }
     __syncwarp();
-    if (lane < T) Ks[lane * ldt + lane] += ev;
 
     // Cholesky, lower, left-looking; lane i owns row i.  (:251)
-    double logdet = 0.0;
     bool bad = false;
     for (int j = 0; j < T; j++) {
         double s0 = 0.0, s1 = 0.0;
@@ -132,17 +180,18 @@ kl_subject_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict
             if (k < j) s0 = fma(-ri[k], rj[k], s0);
         }
         const double sum = s0 + s1;
-        double djj = __shfl_sync(0xffffffffu, sum, j);
+        const double djj = __shfl_sync(0xffffffffu, sum, j);
         if (!(djj > 0.0)) { bad = true; break; }
-        double d = sqrt(djj);
-        if (lane >= j && lane < T) Bw[lane * ldt + j] = (lane == j) ? d : sum / d;
-        logdet += 2.0 * log(d);                                  // C term (:258)
+        const double rd = rsqrt(djj);
+        if (lane >= j && lane < T) Bw[lane * ldt + j] = (lane == j) ? djj * rd : sum * rd;
         __syncwarp();
     }
     if (bad) {
         if (lane == 0) report_status(status, HLVAE_STATUS_NOT_PD, l, s);
         return;
     }
+    // C term (:258): log det B = 2 sum log L_ii, one logarithm per lane
+    const double logdet = warp_sum(lane < T ? 2.0 * log(Bw[lane * ldt + lane]) : 0.0);
     // L^-1 column by column: lane c solves L y = e_c, stored in Bi[:, c].
     if (lane < T) {
         const int c = lane;
@@ -160,102 +209,148 @@ kl_subject_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict
         }
     }
     __syncwarp();
-    // B^-1 = L^-T L^-1 into Bw (explicit inverse, as :252); symmetric: lower triangle + mirror
-    {
-        TriIdx ix;
-        ix.init(lane);
-        for (int t = lane; t < TL; t += 32, ix.advance32()) {
-            const int i = ix.i, j = ix.j;      // i >= j
-            double a = 0.0;
-            for (int k = i; k < T; k++) a = fma(Bi[k * ldt + i], Bi[k * ldt + j], a);
-            Bw[i * ldt + j] = a;
-            Bw[j * ldt + i] = a;
-        }
-    }
-    __syncwarp();
-
-    double gos0[HLVAE_MAX_COMPS], gls0[HLVAE_MAX_COMPS], gos1[HLVAE_MAX_COMPS], gls1[HLVAE_MAX_COMPS],
-        dummy[HLVAE_MAX_COMPS];
-#pragma unroll
-    for (int r = 0; r < HLVAE_MAX_COMPS; r++) { gos0[r] = gls0[r] = gos1[r] = gls1[r] = dummy[r] = 0.0; }
-
-    // B + D1 terms: sum(B^-1 * (K0ss + diag e^logv)) (:257,259); dJ/dK0ss = 1/2 B^-1 (off-diagonal
-    // entries counted twice through the mirror); write B^-1.
-    double bd = 0.0;
+    // B^-1 = L^-T L^-1 into Bw (explicit inverse, as :252), written to global for the panel kernel
     double* bout = binv + (int64_t)l * tt_total + tt_ptr[s];
     {
         TriIdx ix;
         ix.init(lane);
         for (int t = lane; t < TL; t += 32, ix.advance32()) {
-            const int i = ix.i, j = ix.j;
-            const double bij = Bw[i * ldt + j];
-            const double wgt = (i == j) ? 1.0 : 2.0;
-            bd = fma(wgt * bij, Ks[i * ldt + j], bd);
-            bout[i * T + j] = bij;
-            bout[j * T + i] = bij;
-            accum_grads<false>(sp0, kp0, xs + i * Q, xs + j * Q, 0.5 * wgt * bij, gos0, gls0, dummy);
+            const int i = ix.i, j = ix.j;      // i >= j
+            double a0 = 0.0, a1 = 0.0;
+            int k = i;
+            for (; k + 1 < T; k += 2) {
+                a0 = fma(Bi[k * ldt + i], Bi[k * ldt + j], a0);
+                a1 = fma(Bi[(k + 1) * ldt + i], Bi[(k + 1) * ldt + j], a1);
+            }
+            if (k < T) a0 = fma(Bi[k * ldt + i], Bi[k * ldt + j], a0);
+            const double a = a0 + a1;
+            Bw[i * ldt + j] = a;
+            Bw[j * ldt + i] = a;
+            bout[i * T + j] = a;
+            bout[j * T + i] = a;
         }
     }
-    if (lane < T) g_logv[(int64_t)g * L + l] = (TS)(gscale * 0.5 * (Bw[lane * ldt + lane] * ev - 1.0));
+    __syncwarp();
+
+    // K0(x_s, x_s) (:248), one evaluation per component and entry.  With wgt = B^-1_ij (x2 off the diagonal):
+    //   B + D1 terms (:257,259) = sum_r os_r sum wgt v_r + sum_i B^-1_ii e^logv_i,   dJ/dK0ss = B^-1 / 2.
+    double bd = 0.0;
+    for (int r = 0; r < sp0.ncomp; r++) {
+        CompRegs c;
+        c.load(sp0, r);
+        const double osr = kp[r], hil2 = kp[8 + r], il3 = kp[16 + r];
+        double gos = 0.0, gls = 0.0;
+        TriIdx ix;
+        ix.init(lane);
+        for (int t = lane; t < TL; t += 32, ix.advance32()) {
+            const int i = ix.i, j = ix.j;
+            double d;
+            const double v = c.value(xs + i * Q, xs + j * Q, hil2, d);
+            const double wv = ((i == j) ? 1.0 : 2.0) * Bw[i * ldt + j] * v;
+            gos += wv;
+            gls = fma(wv * d, d, gls);
+            const double kv = osr * v;
+            Ks[i * ldt + j] = (r == 0) ? kv : Ks[i * ldt + j] + kv;
+        }
+        gos = warp_sum(gos);
+        gls = warp_sum(gls);
+        bd = fma(osr, gos, bd);
+        if (lane == 0) {
+            atomicAdd(acc + off.o[HLVAE_ACC_GOS0] + (int64_t)r * L + l, 0.5 * gos);
+            if (c.se_col >= 0) atomicAdd(acc + off.o[HLVAE_ACC_GLS0] + (int64_t)r * L + l, 0.5 * gls * osr * il3);
+        }
+    }
+    __syncwarp();
+    {   // mirror K0ss
+        TriIdx ix;
+        ix.init(lane);
+        for (int t = lane; t < TL; t += 32, ix.advance32()) {
+            const int i = ix.i, j = ix.j;
+            const double kv = (sp0.ncomp > 0) ? Ks[i * ldt + j] : 0.0;
+            Ks[i * ldt + j] = kv;
+            Ks[j * ldt + i] = kv;
+        }
+    }
+    __syncwarp();
+    double bdiag = 0.0;
+    if (lane < T) {   // Ktil = K0ss + diag(e^logv); its B term and the log-variance gradient
+        const double bii = Bw[lane * ldt + lane];
+        Ks[lane * ldt + lane] += ev;
+        bdiag = bii * ev;
+        g_logv[(int64_t)g * L + l] = (TS)(gscale * 0.5 * (bii * ev - 1.0));
+    }
+    bd += warp_sum(bdiag);
+    __syncwarp();
     // X = Ktil B^-1 -> Bi
     {
         SqIdx ix;
         ix.init(lane, T);
         for (int e = lane; e < T * T; e += 32, ix.advance32(T)) {
             const int i = ix.i, j = ix.j;
-            double a0 = 0.0, a1 = 0.0;
+            const double* kr = Ks + i * ldt;
+            const double* bc = Bw + j * ldt;           // B^-1 is symmetric: column j = row j (contiguous)
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
             int k = 0;
-            for (; k + 1 < T; k += 2) {
-                a0 = fma(Ks[i * ldt + k], Bw[k * ldt + j], a0);
-                a1 = fma(Ks[i * ldt + k + 1], Bw[(k + 1) * ldt + j], a1);
+            for (; k + 3 < T; k += 4) {
+                a0 = fma(kr[k], bc[k], a0);
+                a1 = fma(kr[k + 1], bc[k + 1], a1);
+                a2 = fma(kr[k + 2], bc[k + 2], a2);
+                a3 = fma(kr[k + 3], bc[k + 3], a3);
             }
-            if (k < T) a0 = fma(Ks[i * ldt + k], Bw[k * ldt + j], a0);
-            Bi[i * ldt + j] = a0 + a1;
+            for (; k < T; k++) a0 = fma(kr[k], bc[k], a0);
+            Bi[i * ldt + j] = (a0 + a1) + (a2 + a3);
         }
     }
     __syncwarp();
-    // dJ/dB_s (part without K0xz) = 1/2 (B^-1 - B^-1 Ktil B^-1) (symmetric), contracted with dB/d(theta1)
+    // dJ/dB_s (part without K0xz) = 1/2 (B^-1 - B^-1 Ktil B^-1) (symmetric; off-diagonal entries count twice)
+    // -> lower triangle of Ks (Ktil is no longer needed)
     {
         TriIdx ix;
         ix.init(lane);
         for (int t = lane; t < TL; t += 32, ix.advance32()) {
             const int i = ix.i, j = ix.j;
-            double a0 = 0.0, a1 = 0.0;
+            const double* br = Bw + i * ldt;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
             int k = 0;
-            for (; k + 1 < T; k += 2) {
-                a0 = fma(Bw[i * ldt + k], Bi[k * ldt + j], a0);
-                a1 = fma(Bw[i * ldt + k + 1], Bi[(k + 1) * ldt + j], a1);
+            for (; k + 3 < T; k += 4) {
+                a0 = fma(br[k], Bi[k * ldt + j], a0);
+                a1 = fma(br[k + 1], Bi[(k + 1) * ldt + j], a1);
+                a2 = fma(br[k + 2], Bi[(k + 2) * ldt + j], a2);
+                a3 = fma(br[k + 3], Bi[(k + 3) * ldt + j], a3);
             }
-            if (k < T) a0 = fma(Bw[i * ldt + k], Bi[k * ldt + j], a0);
-            const double wgt = (i == j) ? 0.5 : 1.0;
-            const double gb = wgt * (Bw[i * ldt + j] - (a0 + a1));
-            accum_grads<false>(sp1, kp1, xs + i * Q, xs + j * Q, gb, gos1, gls1, dummy);
+            for (; k < T; k++) a0 = fma(br[k], Bi[k * ldt + j], a0);
+            Ks[i * ldt + j] = ((i == j) ? 0.5 : 1.0) * (br[j] - ((a0 + a1) + (a2 + a3)));
         }
     }
-    bd = warp_sum(bd);
-    double fsum = warp_sum(lv);
-    double* scal = acc + off.o[HLVAE_ACC_SCAL] + (int64_t)l * HLVAE_NSCAL;
+    __syncwarp();
+    // contracted with dB/d(theta1), one component at a time
+    for (int r = 0; r < sp1.ncomp; r++) {
+        CompRegs c;
+        c.load(sp1, r);
+        const double osr = kp[24 + r], hil2 = kp[32 + r], il3 = kp[40 + r];
+        double gos = 0.0, gls = 0.0;
+        TriIdx ix;
+        ix.init(lane);
+        for (int t = lane; t < TL; t += 32, ix.advance32()) {
+            const int i = ix.i, j = ix.j;
+            double d;
+            const double gv = Ks[i * ldt + j] * c.value(xs + i * Q, xs + j * Q, hil2, d);
+            gos += gv;
+            gls = fma(gv * d, d, gls);
+        }
+        gos = warp_sum(gos);
+        gls = warp_sum(gls);
+        if (lane == 0) {
+            atomicAdd(acc + off.o[HLVAE_ACC_GOS1] + (int64_t)r * L + l, gos);
+            if (c.se_col >= 0) atomicAdd(acc + off.o[HLVAE_ACC_GLS1] + (int64_t)r * L + l, gls * osr * il3);
+        }
+    }
+    const double fsum = warp_sum(lv);
     if (lane == 0) {
+        double* scal = acc + off.o[HLVAE_ACC_SCAL] + (int64_t)l * HLVAE_NSCAL;
         atomicAdd(scal + 1, bd);
         atomicAdd(scal + 2, logdet);
         atomicAdd(scal + 3, fsum);
-    }
-#pragma unroll
-    for (int r = 0; r < HLVAE_MAX_COMPS; r++) {
-        if (r < sp0.ncomp) {
-            double a = warp_sum(gos0[r]), b = warp_sum(gls0[r]);
-            if (lane == 0) {
-                atomicAdd(acc + off.o[HLVAE_ACC_GOS0] + (int64_t)r * L + l, a);
-                if (sp0.comp[r].se_col >= 0) atomicAdd(acc + off.o[HLVAE_ACC_GLS0] + (int64_t)r * L + l, b);
-            }
-        }
-        if (r < sp1.ncomp) {
-            double a = warp_sum(gos1[r]), b = warp_sum(gls1[r]);
-            if (lane == 0) {
-                atomicAdd(acc + off.o[HLVAE_ACC_GOS1] + (int64_t)r * L + l, a);
-                if (sp1.comp[r].se_col >= 0) atomicAdd(acc + off.o[HLVAE_ACC_GLS1] + (int64_t)r * L + l, b);
-            }
-        }
     }
 }
 
@@ -265,22 +360,6 @@ kl_subject_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict
 constexpr int PN_THREADS = 512;
 constexpr int PN_SMAX = 16;   // subjects per panel
 constexpr int PN_NCACHE = 3;  // K0 components whose unscaled values are kept from the K0xz pass to the gradient pass
-
-// One component's descriptor pulled into registers field by field (a struct copy indexed by a
-// run-time component number would be placed in local memory).
-struct CompRegs {
-    int se_col, ndisc;
-    int disc_kind[HLVAE_MAX_DISC], disc_col[HLVAE_MAX_DISC];
-    __device__ __forceinline__ void load(const hlvae_kspec_t& sp, int r) {
-        se_col = sp.comp[r].se_col;
-        ndisc = sp.comp[r].ndisc;
-#pragma unroll
-        for (int f = 0; f < HLVAE_MAX_DISC; f++) {
-            disc_kind[f] = sp.comp[r].disc_kind[f];
-            disc_col[f] = sp.comp[r].disc_col[f];
-        }
-    }
-};
 
 template <int MP, int RP, bool G_SMEM>
 struct PanelSmem {
@@ -492,7 +571,7 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
                                 v = 1.0;
                                 if (c.se_col >= 0) {
                                     const double d = xr[c.se_col] - zse;
-                                    v = exp(-(d * d) * hil2);
+                                    v = exp_nonpos(-(d * d) * hil2);
                                 }
                                 kacc[k] = fma(osr, v, kacc[k]);
                             }
@@ -589,34 +668,48 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
         }
         __syncthreads();
 
-        // ---- P4: W = V G  (dJ/dS = G / 2 applied on both sides -> dJ/dK0xz = W + rho w^T), into Kb
+        // ---- P4: W = V G  (dJ/dS = G / 2 applied on both sides -> dJ/dK0xz = W + rho w^T), into Kb.
+        // One G fragment per k-step serves all of the warp's row tiles.
         {
             const int ar = lane >> 2, ac = lane & 3;
+            double c[WR][WC][2];
+            bool live[WR];
 #pragma unroll
             for (int tr = 0; tr < WR; tr++) {
-                const int rt = wi * WR + tr;
-                if (rt * 8 < R) {
-                    double c[WC][2];
+                live[tr] = (wi * WR + tr) * 8 < R;
 #pragma unroll
-                    for (int t = 0; t < WC; t++) c[t][0] = c[t][1] = 0.0;
-                    for (int k0 = 0; k0 < MP; k0 += 4) {
-                        const double a = Vb[(rt * 8 + ar) * LD + k0 + ac];
+                for (int t = 0; t < WC; t++) c[tr][t][0] = c[tr][t][1] = 0.0;
+            }
+            if (live[0]) {
+#pragma unroll 4
+                for (int k0 = 0; k0 < MP; k0 += 4) {
+                    double bfr[WC];
 #pragma unroll
-                        for (int t = 0; t < WC; t++) {
-                            const int col = (wj * WC + t) * 8 + ar;   // B frag: row = k0 + lane%4, col = lane/4
-                            double b;
-                            if (G_SMEM) {
-                                b = Gs[(k0 + ac) * LD + col];
-                            } else {
-                                b = (k0 + ac < M && col < M) ? Gl[(int64_t)(k0 + ac) * M + col] : 0.0;
-                            }
-                            dmma884(c[t][0], c[t][1], a, b);
+                    for (int t = 0; t < WC; t++) {
+                        const int col = (wj * WC + t) * 8 + ar;       // B frag: row = k0 + lane%4, col = lane/4
+                        if (G_SMEM) {
+                            bfr[t] = Gs[(k0 + ac) * LD + col];
+                        } else {
+                            bfr[t] = (k0 + ac < M && col < M) ? __ldg(Gl + (int64_t)(k0 + ac) * M + col) : 0.0;
                         }
                     }
 #pragma unroll
+                    for (int tr = 0; tr < WR; tr++) {
+                        if (live[tr]) {
+                            const double a = Vb[((wi * WR + tr) * 8 + ar) * LD + k0 + ac];
+#pragma unroll
+                            for (int t = 0; t < WC; t++) dmma884(c[tr][t][0], c[tr][t][1], a, bfr[t]);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int tr = 0; tr < WR; tr++) {
+                if (live[tr]) {
+#pragma unroll
                     for (int t = 0; t < WC; t++)
-                        *reinterpret_cast<double2*>(&Kb[(rt * 8 + ar) * LD + (wj * WC + t) * 8 + 2 * ac]) =
-                            make_double2(c[t][0], c[t][1]);
+                        *reinterpret_cast<double2*>(&Kb[((wi * WR + tr) * 8 + ar) * LD + (wj * WC + t) * 8 + 2 * ac]) =
+                            make_double2(c[tr][t][0], c[tr][t][1]);
                 }
             }
         }
@@ -708,7 +801,7 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
                                     double v = 1.0, d = 0.0;
                                     if (c.se_col >= 0) {
                                         d = xr[c.se_col] - zse;
-                                        v = exp(-(d * d) * hil2);
+                                        v = exp_nonpos(-(d * d) * hil2);
                                     }
                                     const double gkv = gk[k] * v;
                                     const double t = gkv * d;
@@ -762,7 +855,7 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
                         double v = 1.0, d = 0.0;
                         if (c.se_col >= 0) {
                             d = xi[c.se_col] - xj[c.se_col];
-                            v = exp(-(d * d) * hil2);
+                            v = exp_nonpos(-(d * d) * hil2);
                         }
                         const double gv = g * v;
                         gos += gv;
@@ -901,7 +994,7 @@ extern "C" int hlvae_kl_subject(const hlvae_kspec_t* spec0, const double* os0, c
     AccOff off;
     fill_offsets(L, M, Q, off.o);
     const int ldt = t_cap | 1;
-    size_t smem = (size_t)SJ_WARPS * ((size_t)t_cap * Q + 3 * (size_t)t_cap * ldt) * sizeof(double);
+    size_t smem = (size_t)SJ_WARPS * ((size_t)t_cap * Q + 3 * (size_t)t_cap * ldt + SJ_KP) * sizeof(double);
     int64_t pairs = (int64_t)n_subj * L;
     unsigned grid = (unsigned)((pairs + SJ_WARPS - 1) / SJ_WARPS);
     cudaStream_t st = (cudaStream_t)stream;
