@@ -56,6 +56,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--eager", action="store_true", help="time eager launches instead of CUDA-graph replay")
+    ap.add_argument("--no-overlap", action="store_true", help="single stream: no likelihood / KL overlap")
     return ap.parse_args()
 
 
@@ -230,15 +231,26 @@ def elbo_step(s, world, inp=None):
                *s["k1"].parameters()):
         t_.grad = None
     P_b = s["n_subj"] * world
+    # The KL branch (and the natural-gradient update, which needs only its forward outputs) runs on a second
+    # stream next to the HBM-bound likelihood kernels; autograd replays each branch on its own stream.
+    cur = torch.cuda.current_stream()
+    side = s.get("side")
+    if side is not None:
+        side.wait_stream(cur)
+    with torch.cuda.stream(side if side is not None else cur):
+        kld, gm, gH = elbo.minibatch_KLD_upper_bound_iter(s["k0"], s["k1"], s["lik"], L, s["m"], s["H"], inp["x"],
+                                                          inp["mu"], inp["lv"], s["z"], P_TOTAL, P_b, N_TOTAL, True,
+                                                          2, EPS, layout=s["layout"])            # training.py:110-113
+        m_new, H_new = elbo.natural_gradient_update(s["m"], s["H"], gm, gH, NG_LR)             # :130-137
     vparam = s["lay"].vparam(log_vy_real=s["log_vy_real"], conv=True)
     out = loglik.fused_loglik(s["lay"], inp["data"], inp["mask"], inp["theta"], vparam, monitor=True)
     nll = -out["log_p_x_sum"] * (P_TOTAL / P_b)                                             # training.py:83,104,122
-    kld, gm, gH = elbo.minibatch_KLD_upper_bound_iter(s["k0"], s["k1"], s["lik"], L, s["m"], s["H"], inp["x"],
-                                                      inp["mu"], inp["lv"], s["z"], P_TOTAL, P_b, N_TOTAL, True, 2,
-                                                      EPS, layout=s["layout"])                # training.py:110-113
+    if side is not None:
+        cur.wait_stream(side)
+        for t_ in (kld, m_new, H_new):      # allocated on the side stream, consumed on this one
+            t_.record_stream(cur)
     loss = nll + kld                                                                           # :124
     loss.backward()                                                                            # :127
-    m_new, H_new = elbo.natural_gradient_update(s["m"], s["H"], gm, gH, NG_LR)                 # :130-137
     s["m"].copy_(m_new)
     s["H"].copy_(H_new)
     return loss.detach()
@@ -279,6 +291,8 @@ def run_gpu(args):
     _lib.lib()
     config.check_errors = False              # keep the timed step free of host syncs
     s = build_gpu_state(dev, args.subjects, rank)
+    s["side"] = None if args.no_overlap else torch.cuda.Stream()
+    config.overlap = not args.no_overlap
     n_rows = s["N_b"]
     algorithmic_work(n_rows, args.subjects)
     fp64_peak = measure_fp64_peak(dev)       # before any graph capture (uses the RNG)
@@ -331,6 +345,7 @@ def run_gpu(args):
     # (events cannot be read back from inside a replayed graph): per-kernel durations + eager step time
     reset_state()
     n_prof = max(3, min(args.steps, 20))
+    side_saved, s["side"], config.overlap = s["side"], None, False      # one stream: kernels timed one at a time
     for _ in range(2):
         elbo_step(s, world)
     barrier()
@@ -346,6 +361,7 @@ def run_gpu(args):
     eager_ms = p0.elapsed_time(p1) / n_prof
     prof = _lib.PROFILE
     _lib.PROFILE = None
+    s["side"], config.overlap = side_saved, not args.no_overlap
     launches_per_step = (_lib.LAUNCHES - launches0) // n_prof
     launches = launches_per_step * args.steps
 
@@ -461,8 +477,10 @@ def run_gpu(args):
                                 parallelism=f"dp{world}: subjects sharded, one all-reduce of accumulators" if world > 1 else "single GPU"),
                     clocks=sampler.summary(), e2e=e2e, gpu_launches=launches, roofline=roof, cpu_baseline=cpu,
                     kernels=kern, fp64_peak_tflops=fp64_peak, cuda_graph=use_graph, eager_ms_per_step=eager_ms,
-                    kernel_timing="CUDA events around every C-ABI call in an eager pass of the same step run right "
-                                  "after the timed region (events are not readable inside a replayed graph)")
+                    overlap=not args.no_overlap,
+                    kernel_timing="CUDA events around every C-ABI call in an eager, single-stream pass of the same "
+                                  "step run right after the timed region (events are not readable inside a replayed "
+                                  "graph; the timed region overlaps the KL branch with the likelihood kernels)")
         print(json.dumps(line), flush=True)
     if world > 1:
         # Tearing down a NCCL communicator whose collectives were captured into still-live CUDA graphs can

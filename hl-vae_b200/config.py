@@ -8,3 +8,7 @@ check_errors = True
 # torch.distributed process group over which the per-latent accumulators are all-reduced
 # (None: single process).  Set by hlvae_b200.parallel.enable().
 process_group = None
+
+# Run independent kernels of one KL call on two CUDA streams (per-subject T x T stage next to the
+# M x M pre-stage).  Pure scheduling: results are identical either way.
+overlap = True

@@ -168,12 +168,27 @@ mxm_pre_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__ 
           double* __restrict__ G, double* __restrict__ pre, double* __restrict__ ws, int32_t* __restrict__ status) {
     extern __shared__ double smem[];
     const int l = blockIdx.x, tid = threadIdx.x;
-    Bufs B = carve(smem, M, ws, l);
+    // grid (L, 2): the K0zz factorisation and the H factorisation are independent, one CTA each
+    const bool h_role = blockIdx.y == 1;
+    Bufs B = carve(smem, M, ws, (int)(blockIdx.y * gridDim.x) + l);
     double* tmp = B.vec;            // [M]
     double* mv = B.vec + M;         // [M] m
     double* wv = B.vec + 2 * M;     // [M] w
     double* red = B.vec + 4 * M;    // [8]
     const size_t mm_off = (size_t)l * M * M;
+    if (h_role) {                                                      // iH, log det H (:162-163 / :227-228)
+        Mat A = B.b[0], P1 = B.b[1];
+        double logdetH = 0.0;
+        load(A, H + mm_off, M);
+        if (!chol(A, M, tmp, logdetH)) {
+            if (tid == 0) report_status(status, HLVAE_STATUS_NOT_PD, l, -2);
+            return;
+        }
+        tri_inv(P1, A, M);
+        ata_lower(A, P1, M, iH + mm_off);
+        if (tid == 0) pre[l * 4 + 1] = logdetH;
+        return;
+    }
     KParams kp;
     load_kparams(kp, sp0, os0, ls0, L, l);
     const double* zl = z + (size_t)l * M * Q;
@@ -185,7 +200,7 @@ mxm_pre_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__ 
     }
     for (int i = tid; i < M; i += MX_THREADS) mv[i] = m[(size_t)l * M + i];
     __syncthreads();
-    double logdetK = 0.0, logdetH = 0.0;
+    double logdetK = 0.0;
     if (!chol(A, M, tmp, logdetK)) {                                   // :154 / :225
         if (tid == 0) report_status(status, HLVAE_STATUS_NOT_PD, l, -1);
         return;
@@ -215,18 +230,8 @@ mxm_pre_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__ 
         int i = e / M, j = e % M;
         G[mm_off + e] = 0.5 * (P1(i, j) + P1(j, i)) - A(i, j);
     }
-    __syncthreads();
-    // iH (:162-163 / :227-228)
-    load(A, H + mm_off, M);
-    if (!chol(A, M, tmp, logdetH)) {
-        if (tid == 0) report_status(status, HLVAE_STATUS_NOT_PD, l, -2);
-        return;
-    }
-    tri_inv(P1, A, M);
-    ata_lower(A, P1, M, iH + mm_off);
     if (tid == 0) {
         pre[l * 4 + 0] = logdetK;
-        pre[l * 4 + 1] = logdetH;
         pre[l * 4 + 2] = tr1;
         pre[l * 4 + 3] = qf;
     }
@@ -322,8 +327,9 @@ mxm_post_k(int L, int M, double c0, double constant, const double* __restrict__ 
 // training.py:130-137
 __global__ void __launch_bounds__(MX_THREADS)
 natgrad_k(int L, int M, double lr, const double* __restrict__ m, const double* __restrict__ H,
-          const double* __restrict__ grad_m, const double* __restrict__ grad_H, double* __restrict__ m_out,
-          double* __restrict__ H_out, double* __restrict__ ws, int32_t* __restrict__ status) {
+          const double* __restrict__ iH_in, const double* __restrict__ grad_m, const double* __restrict__ grad_H,
+          double* __restrict__ m_out, double* __restrict__ H_out, double* __restrict__ ws,
+          int32_t* __restrict__ status) {
     extern __shared__ double smem[];
     const int l = blockIdx.x, tid = threadIdx.x;
     Bufs B = carve(smem, M, ws, l);
@@ -332,16 +338,19 @@ natgrad_k(int L, int M, double lr, const double* __restrict__ m, const double* _
     double* v = B.vec + 2 * M;
     const size_t mm_off = (size_t)l * M * M;
     Mat A = B.b[0], P1 = B.b[1], P2 = B.b[2], P3 = B.b[3];
-    load(A, H + mm_off, M);
     for (int i = tid; i < M; i += MX_THREADS) mv[i] = m[(size_t)l * M + i];
-    __syncthreads();
     double ldet;
-    if (!chol(A, M, tmp, ldet)) {                                      // :131
-        if (tid == 0) report_status(status, HLVAE_STATUS_NOT_PD, l, -3);
-        return;
+    if (iH_in) {                                                       // H^-1 already known (hlvae_mxm_pre)
+        load(P2, iH_in + mm_off, M);
+    } else {
+        load(A, H + mm_off, M);
+        if (!chol(A, M, tmp, ldet)) {                                  // :131
+            if (tid == 0) report_status(status, HLVAE_STATUS_NOT_PD, l, -3);
+            return;
+        }
+        tri_inv(P1, A, M);
+        ata_lower(P2, P1, M, nullptr);                                 // iH (:132)
     }
-    tri_inv(P1, A, M);
-    ata_lower(P2, P1, M, nullptr);                                     // iH (:132)
     // v = iH m - lr (grad_m - 2 grad_H m)   (:136-137)
     for (int i = tid; i < M; i += MX_THREADS) {
         double a = 0.0, b = 0.0;
@@ -379,7 +388,7 @@ int set_smem(K kern, size_t bytes) {
 }  // namespace
 
 extern "C" int64_t hlvae_mxm_workspace_doubles(int L, int M) {
-    return (M <= 64) ? 0 : (int64_t)L * (MX_NBUF - 1) * M * M;
+    return (M <= 64) ? 0 : (int64_t)2 * L * (MX_NBUF - 1) * M * M;      // hlvae_mxm_pre runs 2 CTAs per latent dim
 }
 
 extern "C" int hlvae_mxm_pre(const hlvae_kspec_t* spec0, const double* os0, const double* ls0, int L, int Q, int M,
@@ -393,7 +402,7 @@ extern "C" int hlvae_mxm_pre(const hlvae_kspec_t* spec0, const double* os0, cons
     size_t smem = mx_smem_bytes(M);
     int rc = set_smem(mxm_pre_k, smem);
     if (rc) return rc;
-    mxm_pre_k<<<L, MX_THREADS, smem, (cudaStream_t)stream>>>(*spec0, os0, ls0, L, Q, M, z, eps, m, H, iK, iH, w, G,
+    mxm_pre_k<<<dim3(L, 2), MX_THREADS, smem, (cudaStream_t)stream>>>(*spec0, os0, ls0, L, Q, M, z, eps, m, H, iK, iH, w, G,
                                                              pre, ws, status);
     HLVAE_CHECK_LAUNCH();
     return 0;
@@ -418,16 +427,16 @@ extern "C" int hlvae_mxm_post(int L, int M, double c0, double constant, const do
     return 0;
 }
 
-extern "C" int hlvae_natgrad_update(int L, int M, double lr, const double* m, const double* H, const double* grad_m,
-                                    const double* grad_H, double* m_out, double* H_out, double* ws, int32_t* status,
-                                    void* stream) {
+extern "C" int hlvae_natgrad_update(int L, int M, double lr, const double* m, const double* H, const double* iH,
+                                    const double* grad_m, const double* grad_H, double* m_out, double* H_out,
+                                    double* ws, int32_t* status, void* stream) {
     if (L <= 0 || M <= 0 || !m || !H || !grad_m || !grad_H || !m_out || !H_out) return HLVAE_E_ARG;
     if (M > 128) return HLVAE_E_UNSUPPORTED;
     if (M > 64 && !ws) return HLVAE_E_ARG;
     size_t smem = mx_smem_bytes(M);
     int rc = set_smem(natgrad_k, smem);
     if (rc) return rc;
-    natgrad_k<<<L, MX_THREADS, smem, (cudaStream_t)stream>>>(L, M, lr, m, H, grad_m, grad_H, m_out, H_out, ws,
+    natgrad_k<<<L, MX_THREADS, smem, (cudaStream_t)stream>>>(L, M, lr, m, H, iH, grad_m, grad_H, m_out, H_out, ws,
                                                              status);
     HLVAE_CHECK_LAUNCH();
     return 0;

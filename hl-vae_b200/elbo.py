@@ -22,6 +22,16 @@ from .subjects import SubjectLayout
 
 N_SM = 148
 
+_side_streams = {}
+
+
+def _side_stream(device):
+    """A stream other than the current one, on which hlvae_kl_subject (T x T work, needs nothing from
+    the M x M pre-stage) runs next to hlvae_mxm_pre (2 L CTAs only)."""
+    cur = torch.cuda.current_stream(device)
+    pool = _side_streams.setdefault(str(device), [torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)])
+    return pool[0] if pool[0] != cur else pool[1]
+
 
 def _noise_vector(likelihood, L, device):
     nz = likelihood.noise_covar.noise if hasattr(likelihood, "noise_covar") else likelihood.noise
@@ -67,29 +77,39 @@ class _KLD(torch.autograd.Function):
         ws = _lib.workspace(L, M, dev)
         status = torch.zeros(4, dtype=torch.int32, device=dev)
 
-        # ---- 1. M x M pre-stage (replicated): iK, iH, w = iK m, G = iK H iK - iK
+        # ---- buffers
         mats = torch.empty(4, L, M, M, **f64)          # iK, iH, G, (later) dkld/dK0zz / c0
         iK, iH, G, gK = mats[0], mats[1], mats[2], mats[3]
         vecs = torch.empty(2, L, M, **f64)             # w, dkld/dm
         w, gm = vecs[0], vecs[1]
         pre = torch.empty(L, 4, **f64)
-        _lib.call("hlvae_mxm_pre", fs0.cspec, _lib.ptr(os0c), _lib.ptr(ls0c), L, Q, M, _lib.ptr(z_c), eps,
-                  _lib.ptr(m_c), _lib.ptr(H_c), _lib.ptr(iK), _lib.ptr(iH), _lib.ptr(w), _lib.ptr(G), _lib.ptr(pre),
-                  _lib.ptr(ws), _lib.ptr(status), st)
-
-        # ---- 2. streaming stage
         off = _lib.acc_layout(L, M, Q)
         acc = torch.zeros(off["total"] + 1, **f64)     # last element: kld_total
         full = layout.n_rows == N
         g_mu = torch.empty_like(mu_c) if full else torch.zeros_like(mu_c)
         g_lv = torch.empty_like(lv_c) if full else torch.zeros_like(lv_c)
         binv = torch.empty(L, max(layout.tt_total, 1), **f64)
+
+        # ---- 2a. per-subject T x T stage on a side stream (independent of the M x M pre-stage)
+        cur = torch.cuda.current_stream(dev)
+        side = _side_stream(dev) if (config.overlap and layout.n_subj > 0) else None
         if layout.n_subj > 0:
-            _lib.call("hlvae_kl_subject", fs0.cspec, _lib.ptr(os0c), _lib.ptr(ls0c), fs1.cspec, _lib.ptr(os1c),
-                      _lib.ptr(ls1c), _lib.ptr(noise), L, Q, _lib.ptr(x_c), Q, _lib.ptr(layout.row_idx),
-                      _lib.ptr(layout.subj_ptr), _lib.ptr(layout.tt_ptr), layout.n_subj, max(layout.t_max, 1),
-                      _lib.ptr(lv_c), L, dcode, _lib.ptr(binv), binv.shape[1], _lib.ptr(acc), M, _lib.ptr(g_lv),
-                      scale, _lib.ptr(status), st)
+            if side is not None:
+                side.wait_stream(cur)
+            with torch.cuda.stream(side if side is not None else cur):
+                _lib.call("hlvae_kl_subject", fs0.cspec, _lib.ptr(os0c), _lib.ptr(ls0c), fs1.cspec, _lib.ptr(os1c),
+                          _lib.ptr(ls1c), _lib.ptr(noise), L, Q, _lib.ptr(x_c), Q, _lib.ptr(layout.row_idx),
+                          _lib.ptr(layout.subj_ptr), _lib.ptr(layout.tt_ptr), layout.n_subj, max(layout.t_max, 1),
+                          _lib.ptr(lv_c), L, dcode, _lib.ptr(binv), binv.shape[1], _lib.ptr(acc), M, _lib.ptr(g_lv),
+                          scale, _lib.ptr(status), _lib.stream_ptr())
+        # ---- 1. M x M pre-stage (replicated): iK, iH, w = iK m, G = iK H iK - iK
+        _lib.call("hlvae_mxm_pre", fs0.cspec, _lib.ptr(os0c), _lib.ptr(ls0c), L, Q, M, _lib.ptr(z_c), eps,
+                  _lib.ptr(m_c), _lib.ptr(H_c), _lib.ptr(iK), _lib.ptr(iH), _lib.ptr(w), _lib.ptr(G), _lib.ptr(pre),
+                  _lib.ptr(ws), _lib.ptr(status), st)
+        if side is not None:
+            cur.wait_stream(side)
+        # ---- 2b. streaming stage over the minibatch rows
+        if layout.n_subj > 0:
             n_chunks = max(1, min((N_SM * 8 + L - 1) // L, (layout.n_subj + 2) // 3))
             spc = (layout.n_subj + n_chunks - 1) // n_chunks
             _lib.call("hlvae_kl_panel", fs0.cspec, _lib.ptr(os0c), _lib.ptr(ls0c), fs1.cspec, _lib.ptr(os1c),
@@ -142,11 +162,11 @@ class _KLD(torch.autograd.Function):
                               gview("gls1", _lib.MAX_COMPS, L)[:nc1])
         grad_m = ng_m_c if natural_gradient else None
         grad_H = ng_H_c if natural_gradient else None
-        ctx.mark_non_differentiable(*[t for t in (grad_m, grad_H) if t is not None])
-        return kld.clone().reshape(out_shape), grad_m, grad_H
+        ctx.mark_non_differentiable(iH, *[t for t in (grad_m, grad_H) if t is not None])
+        return kld.clone().reshape(out_shape), grad_m, grad_H, iH
 
     @staticmethod
-    def backward(ctx, g_kld, g_gm, g_gH):
+    def backward(ctx, g_kld, g_gm, g_gH, g_iH):
         g = g_kld.reshape(())
         out = []
         for t in ctx.saved_tensors:
@@ -163,8 +183,13 @@ def _kld(covar_module0, covar_module1, likelihood, latent_dim, m, H, train_xt, m
     os0, ls0 = fs0.constrained(L, train_xt.device)
     os1, ls1 = fs1.constrained(L, train_xt.device)
     noise = _noise_vector(likelihood, L, train_xt.device)
-    return _KLD.apply(mu, log_v, z, m, H, os0, ls0, os1, ls1, noise, train_xt, fs0, fs1, layout, float(scale),
-                      float(const), float(eps), bool(natural_gradient), out_shape)
+    kld, grad_m, grad_H, iH = _KLD.apply(mu, log_v, z, m, H, os0, ls0, os1, ls1, noise, train_xt, fs0, fs1, layout,
+                                         float(scale), float(const), float(eps), bool(natural_gradient), out_shape)
+    if grad_H is not None:
+        # H^-1 of this step rides along with grad_H so that natural_gradient_update (training.py:131-132) need
+        # not factorise the same H again; valid only while H is unchanged (checked there)
+        grad_H._hlvae_iH = (iH, H.data_ptr(), H._version)
+    return kld, grad_m, grad_H
 
 
 def minibatch_KLD_upper_bound(covar_module0, covar_module1, likelihood, latent_dim, m, H, train_xt, mu, log_v, z,
@@ -197,7 +222,11 @@ def natural_gradient_update(m, H, grad_m, grad_H, lr):
     m_new, H_new = torch.empty_like(m_c), torch.empty_like(H_c)
     status = torch.zeros(4, dtype=torch.int32, device=dev)
     ws = _lib.workspace(L, M, dev)
-    _lib.call("hlvae_natgrad_update", L, M, float(lr), _lib.ptr(m_c), _lib.ptr(H_c), _lib.ptr(gm), _lib.ptr(gH),
+    iH = None
+    stash = getattr(grad_H, "_hlvae_iH", None)
+    if stash is not None and stash[1] == H.data_ptr() and stash[2] == H._version and H.dtype == torch.float64:
+        iH = stash[0]
+    _lib.call("hlvae_natgrad_update", L, M, float(lr), _lib.ptr(m_c), _lib.ptr(H_c), _lib.ptr(iH), _lib.ptr(gm), _lib.ptr(gH),
               _lib.ptr(m_new), _lib.ptr(H_new), _lib.ptr(ws), _lib.ptr(status), _lib.stream_ptr())
     if config.check_errors:
         _raise_status(status, None)

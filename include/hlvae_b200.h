@@ -150,7 +150,9 @@ int hlvae_kl_panel(const hlvae_kspec_t* spec0, const double* os0, const double* 
  *   (:181 / :277, `constant` = L * N / 2 subtracted once), the natural-gradient pieces ng_m, ng_H
  *   (:186-191 / :279-283; nullable) and, with f = c0 (tr(G S)/2 + w^T gw) + kld_qu_pu,
  *   gK_over_c0 = (df/dK0zz) / c0, gH = df/dH, gm = df/dm.  c0 = P / P_batch.
- * hlvae_natgrad_update: training.py:130-137, (m, H, grad_m, grad_H, lr) -> (m_out, H_out).
+ * hlvae_natgrad_update: training.py:130-137, (m, H, grad_m, grad_H, lr) -> (m_out, H_out); `iH` (nullable) is
+ *   H^-1 when the caller already has it from hlvae_mxm_pre of the same step (skips :131-132).
+ * hlvae_mxm_pre launches 2 CTAs per latent dimension (K0zz path and H path are independent).
  * `ws`: global workspace of hlvae_mxm_workspace_doubles(L, M) doubles (0 when M <= 64).
  * ---------------------------------------------------------------------------------- */
 int64_t hlvae_mxm_workspace_doubles(int L, int M);
@@ -162,9 +164,9 @@ int hlvae_mxm_post(int L, int M, double c0, double constant, const double* iK, c
                    const double* S, const double* p, const double* gw, const double* scal, double* kld,
                    double* gK_over_c0, double* gH, double* gm, double* ng_m, double* ng_H, double* ws,
                    void* stream);
-int hlvae_natgrad_update(int L, int M, double lr, const double* m, const double* H, const double* grad_m,
-                         const double* grad_H, double* m_out, double* H_out, double* ws, int32_t* status,
-                         void* stream);
+int hlvae_natgrad_update(int L, int M, double lr, const double* m, const double* H, const double* iH,
+                         const double* grad_m, const double* grad_H, double* m_out, double* H_out, double* ws,
+                         int32_t* status, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Fused masked heterogeneous log-likelihood.  Replaces HLVAE.loglik_and_reconstruction
