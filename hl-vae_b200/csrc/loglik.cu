@@ -25,6 +25,9 @@ namespace {
 
 constexpr int LL_THREADS = 128;                          // threads per CTA = max variables per tile
 constexpr int LL_ROWS = 8;                               // rows staged per batch
+constexpr int LL_CAPM = LL_THREADS + 16;                  // staged mask / upstream-gradient row (with alignment shift)
+constexpr int LL_STAGES = 1;                             // 2: prefetch the next row batch while this one is evaluated (measured: no gain,
+                                                         // the resident CTAs of an SM already cover each other's loads)
 constexpr double LOG_2PI = 1.8378770664093454835606594728112;
 
 // ------------------------------------------------------------------------------------
@@ -60,6 +63,8 @@ template <typename T> __device__ __forceinline__ double ldd(const void* p, int64
 template <typename TS> __device__ __forceinline__ void st(void* p, int64_t i, double v) {
     if (p) reinterpret_cast<TS*>(p)[i] = (TS)v;
 }
+
+__device__ __forceinline__ int d0_(int tile, int tile_vars) { return tile * tile_vars; }
 
 // Per-variable constants, computed once per thread (float64, then rounded to R).
 template <typename R> struct VarC {
@@ -156,6 +161,82 @@ __device__ __noinline__ int ord_argmax_f64(const float* th, int C) {
 }
 
 // ------------------------------------------------------------------------------------
+// Categorical variable, forward (loglik.py:124-146): params = theta - logsumexp(theta) written over
+// theta, log_p_x = sum_c x_c params_c (the reference's second log_softmax of the already normalised
+// params is the identity up to 1 ulp and is dropped), argmax of params (read_functions.py:296-302)
+// and of the one-hot data (:226-227).  CMAX is the unroll bound: when it equals C the loops are
+// straight-line code on registers.
+template <typename R, typename XT, int CMAX>
+__device__ __forceinline__ void cat_forward(const XT* __restrict__ x, R* __restrict__ t, int C, R& lp, R& rmean, R& dtr) {
+    R tv[CMAX];
+#pragma unroll
+    for (int c = 0; c < CMAX; c++) tv[c] = (c < C) ? t[c] : R(-INFINITY);
+    R mx = tv[0], second = -INFINITY;                                        // second: largest logit strictly below mx
+    int am = 0;
+#pragma unroll
+    for (int c = 1; c < CMAX; c++) {
+        const R tc = tv[c];
+        if (tc > mx) { second = mx; mx = tc; am = c; }                       // first index wins ties
+        else if (tc < mx) second = fmax(second, tc);
+    }
+    R se = R(0);
+#pragma unroll
+    for (int c = 0; c < CMAX; c++) se += Mth<R>::ex(tv[c] - mx);             // padded logits are -inf: exp = 0
+    const R lse = mx + Mth<R>::lg(se);                                       // torch.logsumexp
+    if constexpr (sizeof(R) == 4) {
+        // The reference takes argmax of fl64(theta_c - lse); it can differ from argmax(theta) only when two
+        // DISTINCT logits collapse onto one double after the subtraction.
+        const R gap = mx - second;
+        if (gap > R(0) && gap < R(1e-13) * (fabs(mx) + fabs(lse)) + R(1e-37))
+            am = cat_argmax_f64(reinterpret_cast<const float*>(t), C);
+    } else {
+        am = 0;
+        R best = tv[0] - lse;
+#pragma unroll
+        for (int c = 1; c < CMAX; c++) {
+            const R val = tv[c] - lse;
+            if (c < C && val > best) { best = val; am = c; }
+        }
+    }
+    R acc = R(0), dbest = (R)x[0];
+    int dam = 0;
+#pragma unroll
+    for (int c = 0; c < CMAX; c++) {
+        if (c < C) {
+            const R pc = tv[c] - lse;
+            const R xv = (R)x[c];
+            acc += xv * pc;
+            t[c] = pc;
+            if (xv > dbest) { dbest = xv; dam = c; }
+        }
+    }
+    lp = acc;
+    rmean = (R)am;
+    dtr = (R)dam;
+}
+
+// Categorical variable, backward: g (x_c - softmax(theta)_c sum(x)) over theta.
+template <typename R, typename XT, int CMAX>
+__device__ __forceinline__ void cat_backward(const XT* __restrict__ x, R* __restrict__ t, int C, R g) {
+    R tv[CMAX], xv[CMAX];
+    R mx = -INFINITY, sx = R(0);
+#pragma unroll
+    for (int c = 0; c < CMAX; c++) {
+        tv[c] = (c < C) ? t[c] : R(-INFINITY);
+        xv[c] = (c < C) ? (R)x[c] : R(0);
+        mx = fmax(mx, tv[c]);
+        sx += xv[c];
+    }
+    R se = R(0);
+#pragma unroll
+    for (int c = 0; c < CMAX; c++) { tv[c] = Mth<R>::ex(tv[c] - mx); se += tv[c]; }
+    const R k = sx * Mth<R>::rcp(se);
+#pragma unroll
+    for (int c = 0; c < CMAX; c++)
+        if (c < C) t[c] = g * (xv[c] - tv[c] * k);
+}
+
+// ------------------------------------------------------------------------------------
 // One variable, forward.  x / t point into the staged spans (t is overwritten with `params`).
 template <typename R, typename XT>
 __device__ __forceinline__ void var_forward(const VarC<R>& v, const XT* __restrict__ x_, R* __restrict__ t, bool observed,
@@ -187,44 +268,17 @@ __device__ __forceinline__ void var_forward(const VarC<R>& v, const XT* __restri
         rmean = lam; rmode = floor(lam);                                     // read_functions.py:293-295
         dtr = xv;
     } else if (v.kind == HLVAE_VAR_CAT) {                                    // loglik.py:124-146
-        R mx = t[0], second = -INFINITY;                                     // second: largest logit strictly below mx
-        int am = 0;
-        for (int c = 1; c < C; c++) {
-            const R tc = t[c];
-            if (tc > mx) { second = mx; mx = tc; am = c; }                   // first index wins ties
-            else if (tc < mx) second = fmax(second, tc);
+        switch (C) {     // common class counts run fully unrolled from registers
+            case 2: cat_forward<R, XT, 2>(x_, t, 2, lp, rmean, dtr); break;
+            case 3: cat_forward<R, XT, 3>(x_, t, 3, lp, rmean, dtr); break;
+            case 4: cat_forward<R, XT, 4>(x_, t, 4, lp, rmean, dtr); break;
+            case 5: cat_forward<R, XT, 5>(x_, t, 5, lp, rmean, dtr); break;
+            case 6: cat_forward<R, XT, 6>(x_, t, 6, lp, rmean, dtr); break;
+            case 8: cat_forward<R, XT, 8>(x_, t, 8, lp, rmean, dtr); break;
+            case 10: cat_forward<R, XT, 10>(x_, t, 10, lp, rmean, dtr); break;
+            default: cat_forward<R, XT, HLVAE_MAX_CLASS>(x_, t, C, lp, rmean, dtr); break;
         }
-        R se = R(0);
-        for (int c = 0; c < C; c++) se += Mth<R>::ex(t[c] - mx);
-        const R lse = mx + Mth<R>::lg(se);                                   // torch.logsumexp
-        if constexpr (sizeof(R) == 4) {
-            // The reference takes argmax of fl64(theta_c - lse); it can differ from argmax(theta) only when
-            // two DISTINCT logits collapse onto one double after the subtraction.
-            const R gap = mx - second;
-            if (gap > R(0) && gap < R(1e-13) * (fabs(mx) + fabs(lse)) + R(1e-37))
-                am = cat_argmax_f64(reinterpret_cast<const float*>(t), C);
-        } else {
-            am = 0;
-            R best = t[0] - lse;
-            for (int c = 1; c < C; c++) {
-                const R val = t[c] - lse;
-                if (val > best) { best = val; am = c; }
-            }
-        }
-        // params = theta - lse (:134).  log_p_x = sum_c x_c log_softmax(params)_c (:135); the second
-        // normalisation is the identity up to 1 ulp (logsumexp(params) = O(1e-16)) and is dropped.
-        R acc = R(0), dbest = x[0];
-        int dam = 0;
-        for (int c = 0; c < C; c++) {
-            const R pc = t[c] - lse;
-            const R xv = x[c];
-            acc += xv * pc;
-            t[c] = pc;
-            if (xv > dbest) { dbest = xv; dam = c; }
-        }
-        lp = acc;
-        rmean = (R)am; rmode = (R)am;                                        // read_functions.py:296-302
-        dtr = (R)dam;                                                        // read_functions.py:226-227
+        rmode = rmean;                                                       // read_functions.py:296-302
     } else {                                                                 // ordinal, loglik.py:149-188
         int vals = 0;
         R sx = R(0);
@@ -296,26 +350,52 @@ __device__ __forceinline__ void cp_async_elem(void* smem_dst, const void* gsrc) 
     asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(d), "l"(gsrc), "n"(BYTES) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N_>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N_) : "memory"); }
 
-// Stage `span` elements of one row.  Same-width elements go through cp.async one by one (coalesced
-// across the warp).  uint8 codes are fetched as aligned 4-byte words: the copy starts at the
-// 4-byte boundary below `src` (`shift` bytes early; the caller reads element j at dst[shift + j]),
-// which stays inside the array as long as its end is 4-byte aligned (`word_ok`).
+// Stage `span` elements of one row as aligned 16-byte chunks: the copy starts at the 16-byte boundary
+// below `src` (`shift` elements early; the caller finds element j at dst[shift + j]) and ends at the
+// boundary above the last element.  The over-read stays inside the array as long as the array itself
+// starts and ends on 16-byte boundaries (`vec_ok`); otherwise elements are copied one by one.
 template <typename T>
-__device__ __forceinline__ int stage_row(T* __restrict__ dst, const T* __restrict__ src, int span, int tid, bool word_ok) {
+__device__ __forceinline__ int stage_row(T* __restrict__ dst, const T* __restrict__ src, int span, int tid, bool vec_ok) {
+    constexpr int E = 16 / (int)sizeof(T);
+    if (vec_ok) {
+        const int shift = (int)((reinterpret_cast<uintptr_t>(src) & 15) / sizeof(T));
+        const T* s0 = src - shift;
+        const int chunks = (shift + span + E - 1) / E;
+        for (int i = tid; i < chunks; i += LL_THREADS) cp_async_elem<16>(dst + E * i, s0 + E * i);
+        return shift;
+    }
     if constexpr (sizeof(T) >= 4) {
         for (int i = tid; i < span; i += LL_THREADS) cp_async_elem<sizeof(T)>(dst + i, src + i);
-        return 0;
     } else {
-        const int shift = word_ok ? (int)(reinterpret_cast<uintptr_t>(src) & 3) : 0;
-        if (word_ok) {
-            const T* s0 = src - shift;
-            const int words = (shift + span + 3) >> 2;
-            for (int i = tid; i < words; i += LL_THREADS) cp_async_elem<4>(dst + 4 * i, s0 + 4 * i);
-        } else {
-            for (int i = tid; i < span; i += LL_THREADS) dst[i] = src[i];
+        for (int i = tid; i < span; i += LL_THREADS) dst[i] = src[i];
+    }
+    return 0;
+}
+
+// Write `span` elements staged at src[shift + j] to dst[j]; dst has the same 16-byte phase as the staged
+// row (same column offset, same leading dimension), so whole chunks go out as 16-byte stores.
+template <typename T>
+__device__ __forceinline__ void unstage_row(T* __restrict__ dst, const T* __restrict__ src, int shift, int span,
+                                            int tid, bool vec_ok) {
+    constexpr int E = 16 / (int)sizeof(T);
+    if (vec_ok && (int)((reinterpret_cast<uintptr_t>(dst) & 15) / sizeof(T)) == shift) {
+        const int chunks = (shift + span + E - 1) / E;
+        for (int i = tid; i < chunks; i += LL_THREADS) {
+            const int j0 = E * i - shift;                    // first element of the chunk, in span coordinates
+            if (j0 >= 0 && j0 + E <= span) {
+                *reinterpret_cast<int4*>(dst + j0) = *reinterpret_cast<const int4*>(src + E * i);
+            } else {
+#pragma unroll
+                for (int e = 0; e < E; e++)
+                    if (j0 + e >= 0 && j0 + e < span) dst[j0 + e] = src[E * i + e];
+            }
         }
-        return shift;
+    } else {
+        for (int i = tid; i < span; i += LL_THREADS) dst[i] = src[shift + i];
     }
 }
 
@@ -331,12 +411,15 @@ loglik_fwd_k(int64_t N, int D, int tile_vars, int cap, int64_t ld_data, int64_t 
              TS* __restrict__ data_tr, double* __restrict__ ll_total) {
     using R = TS;
     extern __shared__ __align__(16) unsigned char ll_smem[];
-    R* sT = reinterpret_cast<R*>(ll_smem);       // [LL_ROWS][cap]   theta, overwritten with params
-    R* sM = sT + LL_ROWS * cap;                  // [LL_ROWS][LL_THREADS] mask of (row, this thread's variable)
-    TD* sX = reinterpret_cast<TD*>(sM + LL_ROWS * LL_THREADS);   // [LL_ROWS][capx]  data in its storage type
-    const int capx = cap + 8;
-    __shared__ int sShift[LL_ROWS];
-    const bool word_ok = (((uintptr_t)data | (uintptr_t)(N * ld_data)) & 3) == 0;
+    const int capt = cap + 8, capx = cap + 16;   // row strides: room for the alignment shift, multiples of 16 bytes
+    // per stage: sT [LL_ROWS][capt] theta (overwritten with params), sX [LL_ROWS][capx] data and
+    // sK [LL_ROWS][LL_CAPM] mask of the tile's variables, both in their storage types
+    const size_t stage_bytes = (size_t)LL_ROWS * (capt * sizeof(R) + capx * sizeof(TD) + LL_CAPM * sizeof(TM));
+    __shared__ int sShift[LL_STAGES][LL_ROWS], sShiftT[LL_STAGES][LL_ROWS], sShiftM[LL_STAGES][LL_ROWS];
+    const bool m_ok = (((uintptr_t)mask | (uintptr_t)(N * D * (int64_t)sizeof(TM))) & 15) == 0;
+    const int span_m = min(D, d0_(blockIdx.x, tile_vars) + tile_vars) - d0_(blockIdx.x, tile_vars);
+    const bool x_ok = (((uintptr_t)data | (uintptr_t)(N * ld_data * (int64_t)sizeof(TD))) & 15) == 0;
+    const bool t_ok = (((uintptr_t)theta | (uintptr_t)params | (uintptr_t)(N * ld_theta * (int64_t)sizeof(TS))) & 15) == 0;
     __shared__ double red[LL_THREADS / 32];
     const int tid = threadIdx.x;
     const int d0 = blockIdx.x * tile_vars;
@@ -347,28 +430,50 @@ loglik_fwd_k(int64_t N, int D, int tile_vars, int cap, int64_t ld_data, int64_t 
     const int span_x = max(0, min(cap, var_dcol[d1 - 1] + var_nclass[d1 - 1] - xs0));
     const int span_p = max(0, min(cap, var_pcol[d1 - 1] + var_nclass[d1 - 1] - ps0));
     const VarC<R> v = load_var<R>(d, D, active, var_kind, var_nclass, var_dcol, var_pcol, vparam, xs0, ps0, cap);
-    double ll = 0.0;
-    for (int64_t n0 = (int64_t)blockIdx.y * LL_ROWS; n0 < N; n0 += (int64_t)gridDim.y * LL_ROWS) {
-        const int nr = (int)min((int64_t)LL_ROWS, N - n0);
-        for (int r = 0; r < nr; r++) {
-            stage_row<TS>(sT + r * cap, theta + (n0 + r) * ld_theta + ps0, span_p, tid, true);
-            const int sh = stage_row<TD>(sX + r * capx, data + (n0 + r) * ld_data + xs0, span_x, tid, word_ok);
-            if (tid == 0) sShift[r] = sh;
+    const int64_t stride = (int64_t)gridDim.y * LL_ROWS;
+
+    auto prefetch = [&](int64_t n0, int stg) {   // put one row batch in flight (nothing if n0 is past the end)
+        if (n0 < N) {
+            R* sT = reinterpret_cast<R*>(ll_smem + stg * stage_bytes);
+            TD* sX = reinterpret_cast<TD*>(sT + LL_ROWS * capt);
+            TM* sK = reinterpret_cast<TM*>(sX + LL_ROWS * capx);
+            const int nr = (int)min((int64_t)LL_ROWS, N - n0);
+            for (int r = 0; r < nr; r++) {
+                const int st_ = stage_row<TS>(sT + r * capt, theta + (n0 + r) * ld_theta + ps0, span_p, tid, t_ok);
+                const int sh = stage_row<TD>(sX + r * capx, data + (n0 + r) * ld_data + xs0, span_x, tid, x_ok);
+                const int sm = stage_row<TM>(sK + r * LL_CAPM, mask + (n0 + r) * D + d0, span_m, tid, m_ok);
+                if (tid == 0) { sShift[stg][r] = sh; sShiftT[stg][r] = st_; sShiftM[stg][r] = sm; }
+            }
         }
-#pragma unroll
-        for (int r = 0; r < LL_ROWS; r++) sM[r * LL_THREADS + tid] = (active && r < nr) ? (R)mask[(n0 + r) * D + d] : R(0);
-        cp_async_wait_all();
+        cp_async_commit();
+    };
+
+    double ll = 0.0;
+    int stg = 0;
+    if (LL_STAGES == 2) prefetch((int64_t)blockIdx.y * LL_ROWS, 0);
+    for (int64_t n0 = (int64_t)blockIdx.y * LL_ROWS; n0 < N; n0 += stride, stg ^= (LL_STAGES - 1)) {
+        if (LL_STAGES == 2) {
+            prefetch(n0 + stride, stg ^ 1);      // next batch travels while this one is evaluated
+            cp_async_wait_group<1>();
+        } else {
+            prefetch(n0, 0);
+            cp_async_wait_all();
+        }
         __syncthreads();
+        R* sT = reinterpret_cast<R*>(ll_smem + stg * stage_bytes);
+        TD* sX = reinterpret_cast<TD*>(sT + LL_ROWS * capt);
+        TM* sK = reinterpret_cast<TM*>(sX + LL_ROWS * capx);
+        const int nr = (int)min((int64_t)LL_ROWS, N - n0);
         if (active) {
 #pragma unroll 1
             for (int r = 0; r < nr; r++) {
                 R lp = R(0), rmean = R(0), rmode = R(0), dtr = R(0);
-                const R m_ = sM[r * LL_THREADS + tid];
+                const R m_ = (R)sK[r * LL_CAPM + sShiftM[stg][r] + tid];
                 if (v.ok) {
-                    var_forward<R, TD>(v, sX + r * capx + sShift[r] + v.xo, sT + r * cap + v.po, m_ != R(0), lp, rmean,
-                                       rmode, dtr);
+                    var_forward<R, TD>(v, sX + r * capx + sShift[stg][r] + v.xo, sT + r * capt + sShiftT[stg][r] + v.po,
+                                       m_ != R(0), lp, rmean, rmode, dtr);
                     if constexpr (sizeof(R) == 4) {
-                        if (v.kind == HLVAE_VAR_ORDINAL && rmean < R(0)) {      // ordinal decision float32 could not prove: redo from the original theta
+                        if (v.kind == HLVAE_VAR_ORDINAL && rmean < R(0)) {   // float32 could not prove the argmax: redo from theta
                             const R am = (R)ord_argmax_f64(reinterpret_cast<const float*>(theta) +
                                                            (n0 + r) * ld_theta + ps0 + v.po, v.C);
                             rmean = am; rmode = am;
@@ -389,14 +494,12 @@ loglik_fwd_k(int64_t N, int D, int tile_vars, int cap, int64_t ld_data, int64_t 
         }
         __syncthreads();
         if (params) {
-            for (int r = 0; r < nr; r++) {
-                TS* prow = params + (n0 + r) * ld_theta + ps0;
-                const R* src = sT + r * cap;
-                for (int i = tid; i < span_p; i += LL_THREADS) prow[i] = src[i];
-            }
+            for (int r = 0; r < nr; r++)
+                unstage_row<TS>(params + (n0 + r) * ld_theta + ps0, sT + r * capt, sShiftT[stg][r], span_p, tid, t_ok);
         }
-        __syncthreads();
+        __syncthreads();                         // this stage is refilled by the prefetch of the next iteration
     }
+    cp_async_wait_all();
     if (ll_total) {
         ll = warp_sum(ll);
         if ((tid & 31) == 0) red[tid >> 5] = ll;
@@ -432,12 +535,16 @@ __device__ __forceinline__ void var_backward(const VarC<R>& v, const XT* __restr
         if (sp >= R(1e-6) && sp <= R(1e20)) gl = (x[0] * Mth<R>::rcp(sp) - R(1)) * dsoftplus_<R>(t0);
         t[0] = g * gl;
     } else if (v.kind == HLVAE_VAR_CAT) {
-        R mx = -INFINITY, sx = R(0);
-        for (int c = 0; c < C; c++) { mx = fmax(mx, t[c]); sx += x[c]; }
-        R se = R(0);
-        for (int c = 0; c < C; c++) { const R e = Mth<R>::ex(t[c] - mx); t[c] = e; se += e; }
-        const R k = sx * Mth<R>::rcp(se);
-        for (int c = 0; c < C; c++) t[c] = g * (x[c] - t[c] * k);
+        switch (C) {
+            case 2: cat_backward<R, XT, 2>(x_, t, 2, g); break;
+            case 3: cat_backward<R, XT, 3>(x_, t, 3, g); break;
+            case 4: cat_backward<R, XT, 4>(x_, t, 4, g); break;
+            case 5: cat_backward<R, XT, 5>(x_, t, 5, g); break;
+            case 6: cat_backward<R, XT, 6>(x_, t, 6, g); break;
+            case 8: cat_backward<R, XT, 8>(x_, t, 8, g); break;
+            case 10: cat_backward<R, XT, 10>(x_, t, 10, g); break;
+            default: cat_backward<R, XT, HLVAE_MAX_CLASS>(x_, t, C, g); break;
+        }
     } else {
         const R eps = R(1e-6);
         const R t_loc = t[C - 1];
@@ -515,13 +622,17 @@ loglik_bwd_k(int64_t N, int D, int tile_vars, int cap, int64_t ld_data, int64_t 
              TS* __restrict__ g_theta, double* __restrict__ g_lvy) {
     using R = TS;
     extern __shared__ __align__(16) unsigned char ll_smem[];
-    R* sT = reinterpret_cast<R*>(ll_smem);
-    R* sM = sT + LL_ROWS * cap;                  // mask and upstream gradient per (row, variable)
-    R* sG = sM + LL_ROWS * LL_THREADS;
-    TD* sX = reinterpret_cast<TD*>(sG + LL_ROWS * LL_THREADS);
-    const int capx = cap + 8;
-    __shared__ int sShift[LL_ROWS];
-    const bool word_ok = (((uintptr_t)data | (uintptr_t)(N * ld_data)) & 3) == 0;
+    const int capt = cap + 8, capx = cap + 16;
+    // per stage: sT [LL_ROWS][capt] theta (overwritten with g_theta), sG [LL_ROWS][LL_CAPM] upstream gradient,
+    // sX [LL_ROWS][capx] data, sK [LL_ROWS][LL_CAPM] mask
+    const size_t stage_bytes = (size_t)LL_ROWS * ((capt + LL_CAPM) * sizeof(R) + capx * sizeof(TD) + LL_CAPM * sizeof(TM));
+    __shared__ int sShift[LL_STAGES][LL_ROWS], sShiftT[LL_STAGES][LL_ROWS], sShiftM[LL_STAGES][LL_ROWS],
+        sShiftG[LL_STAGES][LL_ROWS];
+    const bool m_ok = (((uintptr_t)mask | (uintptr_t)(N * D * (int64_t)sizeof(TM))) & 15) == 0;
+    const bool g_ok = (((uintptr_t)g_lp | (uintptr_t)(N * D * (int64_t)sizeof(TS))) & 15) == 0;
+    const int span_m = min(D, d0_(blockIdx.x, tile_vars) + tile_vars) - d0_(blockIdx.x, tile_vars);
+    const bool x_ok = (((uintptr_t)data | (uintptr_t)(N * ld_data * (int64_t)sizeof(TD))) & 15) == 0;
+    const bool t_ok = (((uintptr_t)theta | (uintptr_t)g_theta | (uintptr_t)(N * ld_theta * (int64_t)sizeof(TS))) & 15) == 0;
     const int tid = threadIdx.x;
     const int d0 = blockIdx.x * tile_vars;
     const int d1 = min(D, d0 + tile_vars);
@@ -532,44 +643,66 @@ loglik_bwd_k(int64_t N, int D, int tile_vars, int cap, int64_t ld_data, int64_t 
     const int span_p = max(0, min(cap, var_pcol[d1 - 1] + var_nclass[d1 - 1] - ps0));
     const VarC<R> v = load_var<R>(d, D, active, var_kind, var_nclass, var_dcol, var_pcol, vparam, xs0, ps0, cap);
     const R gs = g_scalar ? (R)(*g_scalar) : R(0);
+    const int64_t stride = (int64_t)gridDim.y * LL_ROWS;
+
+    auto prefetch = [&](int64_t n0, int stg) {
+        if (n0 < N) {
+            R* sT = reinterpret_cast<R*>(ll_smem + stg * stage_bytes);
+            R* sG = sT + LL_ROWS * capt;
+            TD* sX = reinterpret_cast<TD*>(sG + LL_ROWS * LL_CAPM);
+            TM* sK = reinterpret_cast<TM*>(sX + LL_ROWS * capx);
+            const int nr = (int)min((int64_t)LL_ROWS, N - n0);
+            for (int r = 0; r < nr; r++) {
+                const int st_ = stage_row<TS>(sT + r * capt, theta + (n0 + r) * ld_theta + ps0, span_p, tid, t_ok);
+                const int sh = stage_row<TD>(sX + r * capx, data + (n0 + r) * ld_data + xs0, span_x, tid, x_ok);
+                const int sm = stage_row<TM>(sK + r * LL_CAPM, mask + (n0 + r) * D + d0, span_m, tid, m_ok);
+                int sg = 0;
+                if (g_lp) sg = stage_row<TS>(sG + r * LL_CAPM, g_lp + (n0 + r) * D + d0, span_m, tid, g_ok);
+                if (tid == 0) { sShift[stg][r] = sh; sShiftT[stg][r] = st_; sShiftM[stg][r] = sm; sShiftG[stg][r] = sg; }
+            }
+        }
+        cp_async_commit();
+    };
+
     double ge_acc = 0.0;
-    for (int64_t n0 = (int64_t)blockIdx.y * LL_ROWS; n0 < N; n0 += (int64_t)gridDim.y * LL_ROWS) {
-        const int nr = (int)min((int64_t)LL_ROWS, N - n0);
-        for (int r = 0; r < nr; r++) {
-            stage_row<TS>(sT + r * cap, theta + (n0 + r) * ld_theta + ps0, span_p, tid, true);
-            const int sh = stage_row<TD>(sX + r * capx, data + (n0 + r) * ld_data + xs0, span_x, tid, word_ok);
-            if (tid == 0) sShift[r] = sh;
+    int stg = 0;
+    if (LL_STAGES == 2) prefetch((int64_t)blockIdx.y * LL_ROWS, 0);
+    for (int64_t n0 = (int64_t)blockIdx.y * LL_ROWS; n0 < N; n0 += stride, stg ^= (LL_STAGES - 1)) {
+        if (LL_STAGES == 2) {
+            prefetch(n0 + stride, stg ^ 1);
+            cp_async_wait_group<1>();
+        } else {
+            prefetch(n0, 0);
+            cp_async_wait_all();
         }
-#pragma unroll
-        for (int r = 0; r < LL_ROWS; r++) {
-            const bool on = active && r < nr;
-            sM[r * LL_THREADS + tid] = on ? (R)mask[(n0 + r) * D + d] : R(0);
-            sG[r * LL_THREADS + tid] = gs + ((on && g_lp) ? (R)g_lp[(n0 + r) * D + d] : R(0));
-        }
-        cp_async_wait_all();
         __syncthreads();
+        R* sT = reinterpret_cast<R*>(ll_smem + stg * stage_bytes);
+        R* sG = sT + LL_ROWS * capt;
+        TD* sX = reinterpret_cast<TD*>(sG + LL_ROWS * LL_CAPM);
+        TM* sK = reinterpret_cast<TM*>(sX + LL_ROWS * capx);
+        const int nr = (int)min((int64_t)LL_ROWS, N - n0);
         if (active) {
 #pragma unroll 1
             for (int r = 0; r < nr; r++) {
                 if (v.ok) {
                     R ge = R(0);
-                    const R m_ = sM[r * LL_THREADS + tid];
-                    var_backward<R, TD>(v, sX + r * capx + sShift[r] + v.xo, sT + r * cap + v.po, m_ != R(0),
-                                        sG[r * LL_THREADS + tid] * m_, ge);
+                    const R m_ = (R)sK[r * LL_CAPM + sShiftM[stg][r] + tid];
+                    const R g_ = gs + (g_lp ? sG[r * LL_CAPM + sShiftG[stg][r] + tid] : R(0));
+                    var_backward<R, TD>(v, sX + r * capx + sShift[stg][r] + v.xo, sT + r * capt + sShiftT[stg][r] + v.po,
+                                        m_ != R(0), g_ * m_, ge);
                     ge_acc += (double)ge;
                 } else {
-                    for (int c = 0; c < v.C && v.po >= 0 && v.po + c < cap; c++) sT[r * cap + v.po + c] = (R)NAN;
+                    for (int c = 0; c < v.C && v.po >= 0 && v.po + c < cap; c++)
+                        sT[r * capt + sShiftT[stg][r] + v.po + c] = (R)NAN;
                 }
             }
         }
         __syncthreads();
-        for (int r = 0; r < nr; r++) {
-            TS* grow = g_theta + (n0 + r) * ld_theta + ps0;
-            const R* src = sT + r * cap;
-            for (int i = tid; i < span_p; i += LL_THREADS) grow[i] = src[i];
-        }
+        for (int r = 0; r < nr; r++)
+            unstage_row<TS>(g_theta + (n0 + r) * ld_theta + ps0, sT + r * capt, sShiftT[stg][r], span_p, tid, t_ok);
         __syncthreads();
     }
+    cp_async_wait_all();
     if (g_lvy && active && (v.kind == HLVAE_VAR_REAL || v.kind == HLVAE_VAR_POS) && ge_acc != 0.0)
         atomicAdd(g_lvy + d, ge_acc);
 }
@@ -707,8 +840,9 @@ extern "C" int hlvae_loglik_fwd(int64_t N, int D, int64_t ld_data, int64_t ld_th
     const size_t esz = dtype == HLVAE_F64 ? 8 : 4;
     const size_t xsz = data_dtype == HLVAE_U8 ? 1 : esz;
     Tiling tl = make_tiling(N, D, 1);
-    const int cap = (tl.tile_vars * max_class + 3) & ~3;
-    const size_t smem = (size_t)LL_ROWS * ((cap + LL_THREADS) * esz + (cap + 8) * xsz);
+    const int cap = (tl.tile_vars * max_class + 15) & ~15;
+    const size_t msz = mask_dtype == HLVAE_U8 ? 1 : esz;
+    const size_t smem = (size_t)LL_STAGES * LL_ROWS * ((cap + 8) * esz + (cap + 16) * xsz + LL_CAPM * msz);
 #define HLVAE_LL_FWD(TS, TD, TM)                                                                                     \
     {                                                                                                                \
         auto kern = loglik_fwd_k<TS, TD, TM>;                                                                        \
@@ -744,8 +878,9 @@ extern "C" int hlvae_loglik_bwd(int64_t N, int D, int64_t ld_data, int64_t ld_th
     const size_t esz = dtype == HLVAE_F64 ? 8 : 4;
     const size_t xsz = data_dtype == HLVAE_U8 ? 1 : esz;
     Tiling tl = make_tiling(N, D, 1);
-    const int cap = (tl.tile_vars * max_class + 3) & ~3;
-    const size_t smem = (size_t)LL_ROWS * ((cap + 2 * LL_THREADS) * esz + (cap + 8) * xsz);
+    const int cap = (tl.tile_vars * max_class + 15) & ~15;
+    const size_t msz = mask_dtype == HLVAE_U8 ? 1 : esz;
+    const size_t smem = (size_t)LL_STAGES * LL_ROWS * ((cap + 8 + LL_CAPM) * esz + (cap + 16) * xsz + LL_CAPM * msz);
 #define HLVAE_LL_BWD(TS, TD, TM)                                                                                     \
     {                                                                                                                \
         auto kern = loglik_bwd_k<TS, TD, TM>;                                                                        \
