@@ -384,8 +384,16 @@ def run_gpu(args):
             d["frac"] = d["achieved"] / d["peak"]
         d["share_of_step"] = d["ms_avg"] * d["launches_per_step"] / ms_per_step
     top = max((k for k in kern if k in ALGO and ALGO[k][0] in ("hbm", "tensor")), key=lambda k: kern[k]["share_of_step"])
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", "traffic_r01.json")
+    if os.path.exists(tp) and n_rows == SUBJ_PER_RANK * T:      # captured at this workload size only
+        tj = json.load(open(tp))
+        traffic, traffic_src = tj.get(top), tj.get("source")
+        for k_, d_ in kern.items():
+            if k_ in tj:
+                d_["traffic"] = tj[k_]
     roof = dict(kernel=top, bound=kern[top]["bound"], achieved=kern[top]["achieved"], peak=kern[top]["peak"],
-                unit=kern[top]["unit"], frac=kern[top]["frac"], traffic=None,
+                unit=kern[top]["unit"], frac=kern[top]["frac"], traffic=traffic, traffic_source=traffic_src,
                 peak_source=(peak_src if kern[top]["bound"] == "hbm" else
                              "FP64 DGEMM 4096^3 measured in this run (cuBLAS; MEASURED_PEAKS.json has no FP64 entry)"),
                 ms_avg=kern[top]["ms_avg"])

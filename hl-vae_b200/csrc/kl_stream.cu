@@ -357,7 +357,6 @@ kl_subject_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict
 // =====================================================================================
 // kl_panel_k
 // =====================================================================================
-constexpr int PN_THREADS = 512;
 constexpr int PN_SMAX = 16;   // subjects per panel
 constexpr int PN_NCACHE = 3;  // K0 components whose unscaled values are kept from the K0xz pass to the gradient pass
 
@@ -374,8 +373,10 @@ struct PanelSmem {
     static constexpr size_t bytes = doubles * 8 + ints * 4;
 };
 
-template <int MP, int RP, bool G_SMEM, typename TS>
-__global__ void __launch_bounds__(PN_THREADS, 1)
+// NT threads per CTA: 512 (one CTA per SM) or 256 with RP = 32 (two CTAs per SM whose barrier and
+// latency stalls cover each other; register file: 2 x 256 x 128).  Warps form a (NT / 128) x 4 grid over tiles.
+template <int MP, int RP, bool G_SMEM, int NT, typename TS>
+__global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1)
 kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__ os0, const double* __restrict__ ls0,
            const __grid_constant__ hlvae_kspec_t sp1, const double* __restrict__ os1, const double* __restrict__ ls1,
            int L, int Q, int M, const double* __restrict__ x, int64_t ldx, const double* __restrict__ z,
@@ -387,11 +388,15 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
     using SM = PanelSmem<MP, RP, G_SMEM>;
     constexpr int LD = SM::LD;
     constexpr int LDB = SM::LDB;
-    constexpr int SI = MP / 32;                 // S tiles (8x8) per warp per dim; 16 warps as 4 x 4
-    constexpr int WR = RP / 32;                 // row tiles per warp for [RP x MP] outputs
-    constexpr int WC = MP / 32;                 // col tiles per warp for [RP x MP] outputs
+    constexpr int PN_THREADS = NT;
+    constexpr int WGI = NT / 128;               // warp grid: WGI x 4
+    constexpr int SIR = (MP / 8) / WGI;         // S tiles (8x8) per warp, rows
+    constexpr int SIC = (MP / 8) / 4;           // S tiles per warp, columns
+    constexpr int WR = (RP / 8) / WGI;          // row tiles per warp for [RP x MP] outputs
+    constexpr int WC = (MP / 8) / 4;            // col tiles per warp for [RP x MP] outputs
     constexpr int NGRP = PN_THREADS / MP;       // row groups in the element-wise phases
     constexpr int RPT = RP / NGRP;              // rows per thread in the element-wise phases
+    static_assert(WR >= 1 && WC >= 1 && SIR >= 1 && SIC >= 1 && RPT >= 1, "tile shape");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* Zs = reinterpret_cast<double*>(smem_raw);          // [Q][MP] transposed
     double* ws = Zs + HLVAE_MAX_Q * MP;
@@ -466,11 +471,11 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
     }
     const double* Gl = G + (int64_t)l * M * M;
 
-    double sacc[SI][SI][2];
+    double sacc[SIR][SIC][2];
 #pragma unroll
-    for (int a = 0; a < SI; a++)
+    for (int a = 0; a < SIR; a++)
 #pragma unroll
-        for (int b = 0; b < SI; b++) sacc[a][b][0] = sacc[a][b][1] = 0.0;
+        for (int b = 0; b < SIC; b++) sacc[a][b][0] = sacc[a][b][1] = 0.0;
     double p_acc = 0.0, gw_acc = 0.0, a_acc = 0.0;
 
     if (tid == 0) meta[2] = s_begin;
@@ -643,16 +648,15 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
             const int R4 = (R + 3) & ~3;
             const int kr = lane & 3, kc = lane >> 2;
             for (int k0 = 0; k0 < R4; k0 += 4) {
-                double af[SI], bf[SI];
+                double af[SIR], bf[SIC];
 #pragma unroll
-                for (int t = 0; t < SI; t++) {
-                    af[t] = Kb[(k0 + kr) * LD + (wi * SI + t) * 8 + kc];
-                    bf[t] = Vb[(k0 + kr) * LD + (wj * SI + t) * 8 + kc];
-                }
+                for (int t = 0; t < SIR; t++) af[t] = Kb[(k0 + kr) * LD + (wi * SIR + t) * 8 + kc];
 #pragma unroll
-                for (int a = 0; a < SI; a++)
+                for (int t = 0; t < SIC; t++) bf[t] = Vb[(k0 + kr) * LD + (wj * SIC + t) * 8 + kc];
 #pragma unroll
-                    for (int b = 0; b < SI; b++) dmma884(sacc[a][b][0], sacc[a][b][1], af[a], bf[b]);
+                for (int a = 0; a < SIR; a++)
+#pragma unroll
+                    for (int b = 0; b < SIC; b++) dmma884(sacc[a][b][0], sacc[a][b][1], af[a], bf[b]);
             }
         }
         __syncthreads();
@@ -878,10 +882,10 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
         double* Sg = acc + off.o[HLVAE_ACC_S] + (int64_t)l * M * M;
         const int cr = lane >> 2, cc = 2 * (lane & 3);
 #pragma unroll
-        for (int a = 0; a < SI; a++)
+        for (int a = 0; a < SIR; a++)
 #pragma unroll
-            for (int b = 0; b < SI; b++) {
-                int i = (wi * SI + a) * 8 + cr, j = (wj * SI + b) * 8 + cc;
+            for (int b = 0; b < SIC; b++) {
+                int i = (wi * SIR + a) * 8 + cr, j = (wj * SIC + b) * 8 + cc;
                 if (i < M) {
                     if (j < M) atomicAdd(Sg + (int64_t)i * M + j, sacc[a][b][0]);
                     if (j + 1 < M) atomicAdd(Sg + (int64_t)i * M + j + 1, sacc[a][b][1]);
@@ -919,7 +923,7 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
     }
 }
 
-template <int MP, int RP, bool G_SMEM, typename TS>
+template <int MP, int RP, bool G_SMEM, int NT, typename TS>
 int launch_panel(const hlvae_kspec_t* spec0, const double* os0, const double* ls0, const hlvae_kspec_t* spec1,
                  const double* os1, const double* ls1, int L, int Q, int M, const double* x, int64_t ldx,
                  const double* z, const int32_t* row_idx, const int32_t* subj_ptr, const int32_t* tt_ptr, int n_subj,
@@ -927,12 +931,12 @@ int launch_panel(const hlvae_kspec_t* spec0, const double* os0, const double* ls
                  const double* binv, int64_t tt_total, double* acc, const AccOff& off, void* g_mu, double gscale,
                  int32_t* status, cudaStream_t st) {
     using SM = PanelSmem<MP, RP, G_SMEM>;
-    auto kern = kl_panel_k<MP, RP, G_SMEM, TS>;
+    auto kern = kl_panel_k<MP, RP, G_SMEM, NT, TS>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::bytes);
     if (e != cudaSuccess) return (int)e;
     int n_chunks = (n_subj + subj_per_chunk - 1) / subj_per_chunk;
     dim3 grid(n_chunks, L);
-    kern<<<grid, PN_THREADS, SM::bytes, st>>>(*spec0, os0, ls0, *spec1, os1, ls1, L, Q, M, x, ldx, z, row_idx,
+    kern<<<grid, NT, SM::bytes, st>>>(*spec0, os0, ls0, *spec1, os1, ls1, L, Q, M, x, ldx, z, row_idx,
                                               subj_ptr, tt_ptr, n_subj, subj_per_chunk, (const TS*)mu, ld_mu, w, G,
                                               binv, tt_total, acc, off, (TS*)g_mu, gscale, status);
     HLVAE_CHECK_LAUNCH();
@@ -946,13 +950,15 @@ int dispatch_panel(int M, const hlvae_kspec_t* spec0, const double* os0, const d
                    const int32_t* tt_ptr, int n_subj, int subj_per_chunk, const void* mu, int64_t ld_mu,
                    const double* w, const double* G, const double* binv, int64_t tt_total, double* acc,
                    const AccOff& off, void* g_mu, double gscale, int32_t* status, cudaStream_t st) {
-#define HLVAE_PANEL(MP, RP, GS)                                                                                       \
-    return launch_panel<MP, RP, GS, TS>(spec0, os0, ls0, spec1, os1, ls1, L, Q, M, x, ldx, z, row_idx, subj_ptr,     \
+#define HLVAE_PANEL(MP, RP, GS, NT)                                                                                   \
+    return launch_panel<MP, RP, GS, NT, TS>(spec0, os0, ls0, spec1, os1, ls1, L, Q, M, x, ldx, z, row_idx, subj_ptr,     \
                                         tt_ptr, n_subj, subj_per_chunk, mu, ld_mu, w, G, binv, tt_total, acc, off,   \
                                         g_mu, gscale, status, st)
-    if (M <= 32) { HLVAE_PANEL(32, 64, true); }
-    if (M <= 64) { HLVAE_PANEL(64, 64, false); }
-    if (M <= 128) { HLVAE_PANEL(128, 32, false); }
+    // (a 256-thread, RP = 32, two-CTAs-per-SM shape was measured 9 % slower at M = 64, T = 20: one subject per
+    // panel triples the per-panel fixed cost)
+    if (M <= 32) { HLVAE_PANEL(32, 64, true, 512); }
+    if (M <= 64) { HLVAE_PANEL(64, 64, false, 512); }
+    if (M <= 128) { HLVAE_PANEL(128, 32, false, 512); }
 #undef HLVAE_PANEL
     return HLVAE_E_UNSUPPORTED;
 }
