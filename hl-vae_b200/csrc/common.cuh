@@ -38,9 +38,10 @@ __device__ __forceinline__ void load_kparams(KParams& kp, const hlvae_kspec_t& s
 // exp(x) for x <= 0 (every squared-exponential argument is -(d^2) / (2 l^2)).  About half the
 // instructions of the general library exp: no overflow / NaN handling, one rounding step
 // (x = k ln2 + r, |r| <= ln2 / 2), a degree-13 Taylor polynomial in Estrin form (short dependency
-// chain) and an exponent insert.  Error <= ~1.5 ulp; arguments below -708 (results < 3e-308) give 0.
+// chain) and an exponent insert.  Branch-free.  Error <= ~1.5 ulp; arguments below -708 are clamped
+// (result 3e-308 instead of a denormal or 0).
 __device__ __forceinline__ double exp_nonpos(double x) {
-    if (x < -708.0) return 0.0;
+    x = fmax(x, -708.0);
     const double MAGIC = 6755399441055744.0;                 // 1.5 * 2^52: adding it rounds to nearest integer
     const double t = fma(x, 1.4426950408889634074, MAGIC);
     const int k = __double2loint(t);

@@ -528,6 +528,7 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
             mus[tid] = (double)mu[(int64_t)g * ld_mu + l];
         } else if (tid < RP) {
             sub_of_row[tid] = -1;
+            for (int q = 0; q < Q; q++) xs[tid * Q + q] = 0.0;
         }
         {   // scatter the subjects' B^-1 blocks (contiguous in global memory) onto the block diagonal
             const double* bsrc = binv + (int64_t)l * tt_total + tt_ptr[s_first];
@@ -559,29 +560,34 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
 #pragma unroll
                     for (int f = 0; f < HLVAE_MAX_DISC; f++) zd[f] = (f < c.ndisc) ? Zs[c.disc_col[f] * MP + em] : 0.0;
                     const double hil2 = kps[HLVAE_MAX_COMPS + r], osr = kps[r];
+                    // Straight-line body (no data-dependent branches): the RPT rows of a thread are independent,
+                    // so their exponentials interleave and hide each other's latency.  Rows >= R read the
+                    // zero-filled tail of xs; their values are never used.
+                    const int nd = c.ndisc;
+                    const bool cat0 = c.disc_kind[0] == HLVAE_KIND_CAT, cat1 = c.disc_kind[1] == HLVAE_KIND_CAT,
+                               cat2 = c.disc_kind[2] == HLVAE_KIND_CAT;
+                    const int dc0 = nd > 0 ? c.disc_col[0] : 0, dc1 = nd > 1 ? c.disc_col[1] : 0,
+                              dc2 = nd > 2 ? c.disc_col[2] : 0;
+                    const int sc = c.se_col >= 0 ? c.se_col : 0;
+                    const bool has_se = c.se_col >= 0;
+                    double vv[RPT];
+#pragma unroll
+                    for (int k = 0; k < RPT; k++) {
+                        const double* xr = xs + (eg + k * NGRP) * Q;
+                        const double a0 = xr[dc0], a1 = xr[dc1], a2 = xr[dc2];
+                        bool ok = true;
+                        ok = ok && (nd < 1 || (cat0 ? (a0 == zd[0]) : (a0 + zd[0] == 2.0)));
+                        ok = ok && (nd < 2 || (cat1 ? (a1 == zd[1]) : (a1 + zd[1] == 2.0)));
+                        ok = ok && (nd < 3 || (cat2 ? (a2 == zd[2]) : (a2 + zd[2] == 2.0)));
+                        const double d = xr[sc] - zse;
+                        const double e_ = has_se ? exp_nonpos(-(d * d) * hil2) : 1.0;
+                        vv[k] = ok ? e_ : 0.0;
+                    }
 #pragma unroll
                     for (int k = 0; k < RPT; k++) {
                         const int row = eg + k * NGRP;
-                        if (row < R) {
-                            const double* xr = xs + row * Q;
-                            bool ok = true;
-#pragma unroll
-                            for (int f = 0; f < HLVAE_MAX_DISC; f++)
-                                if (f < c.ndisc) {
-                                    const double a = xr[c.disc_col[f]];
-                                    ok = ok && ((c.disc_kind[f] == HLVAE_KIND_CAT) ? (a == zd[f]) : (a + zd[f] == 2.0));
-                                }
-                            double v = 0.0;
-                            if (ok) {
-                                v = 1.0;
-                                if (c.se_col >= 0) {
-                                    const double d = xr[c.se_col] - zse;
-                                    v = exp_nonpos(-(d * d) * hil2);
-                                }
-                                kacc[k] = fma(osr, v, kacc[k]);
-                            }
-                            if (r < PN_NCACHE) vc[(r * RP + row) * MP + em] = v;
-                        }
+                        kacc[k] = fma(osr, vv[k], kacc[k]);
+                        if (r < PN_NCACHE) vc[(r * RP + row) * MP + em] = vv[k];
                     }
                 }
             }

@@ -104,3 +104,52 @@ def test_natural_gradient_step_matches_oracle(device):
                       inp["rls0"], inp["ros1"], inp["rls1"], inp["noise"], 200, 6, 200 * 8, 1e-6)
     m3, H3 = orc.natural_gradient_update(inp["m"], inp["H"], ref["grad_m"], ref["grad_H"], 0.01)
     assert h.rel_err(m2, m3) < 1e-6 and h.rel_err(H2, H3) < 1e-6
+
+
+@pytest.mark.parametrize("M", [32, 64, 128])
+def test_kernel_sweep_config(M, device):
+    """BASELINE.json configs[2]: SE(time) + CA(id) + SE(age) x CA(sex), continuous ages, ragged T_s,
+    M in {32, 64, 128} (each M selects a different panel-kernel shape), against the oracle."""
+    errs = h.check_kl_vs_oracle(device, 4, M, 24, 20, seed=300 + M, tol=1e-6, hyper_tol=1e-4, ragged=True,
+                                kargs=h.synth.SWEEP_KERNEL_ARGS, continuous_age=True)
+    print(M, {k: f"{v:.1e}" for k, v in errs.items()})
+
+
+def test_masked_bin_spec_against_oracle(device):
+    """BinKernel factors, missing-covariate masks and bin x SE interactions (5 components in K0, two
+    beyond the cached three) on fresh seeded inputs."""
+    errs = h.check_kl_vs_oracle(device, 3, 40, 16, 12, seed=77, tol=1e-6, hyper_tol=1e-4, ragged=True,
+                                kargs=h.synth.MASKED_KERNEL_ARGS)
+    print({k: f"{v:.1e}" for k, v in errs.items()})
+
+
+def test_full_size_minibatch_properties(device):
+    """BASELINE.json configs[2] upper size: 64 000 rows (3200 subjects x T = 20), L = 32, M = 64, float32
+    storage.  Size-independent checks: (i) kld and every replicated gradient are additive over a
+    partition of the subjects for fixed (m, H, Z, hyper-parameters) - the streaming part is a sum over
+    subjects and kld_qu_pu a constant; (ii) gradients w.r.t. mu / log_v of a subject do not depend on
+    which other subjects are in the batch."""
+    L, M, P_b, T = 32, 64, 3200, 20
+    inp = h.make_kl_inputs(L, M, P_b, T, seed=13)
+    lay = subjects.SubjectLayout.from_lengths(inp["lens"], device)
+    parts = [lay.shard(r, 4) for r in range(4)]
+    kw = dict(storage=torch.float32, P_tot=P_b)          # scale P / P_b = 1 for every run
+    full = h.run_kl_product(inp, device, layout=lay, **kw)
+    outs = []
+    for part in parts:
+        inp_p = dict(inp)
+        inp_p["n_subj"] = P_b                             # keep the P / P_b scale of the full batch
+        outs.append(h.run_kl_product(inp_p, device, layout=part, **kw))
+    # kld(part) = J(part) + kq - const ; kld(full) = sum J(part) + kq - const
+    empty = subjects.SubjectLayout.from_lengths([], device)
+    inp_e = dict(inp)
+    base = h.run_kl_product(inp_e, device, layout=empty, **kw)       # kq - const (no subjects)
+    total = sum(o["kld"] - base["kld"] for o in outs) + base["kld"]
+    # tr(G S) with |G| ~ |iK|^2 ~ 1e12 amplifies the float64 summation-order difference of S (measured 1e-7)
+    assert h.rel_err(total, full["kld"]) < 1e-6
+    d_mu = sum(o["d_mu"] for o in outs)
+    assert h.rel_err(d_mu, full["d_mu"]) < 1e-5           # float32 storage of the gradient
+    d_z = sum(o["d_z"] - base["d_z"] for o in outs) + base["d_z"]
+    assert h.rel_err(d_z, full["d_z"]) < 1e-5
+    gH = sum(o["grad_H"] - base["grad_H"] for o in outs) + base["grad_H"]
+    assert h.rel_err(gH, full["grad_H"]) < 1e-6
