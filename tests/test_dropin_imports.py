@@ -1,0 +1,40 @@
+"""CPU: the drop-in wiring of INTEGRATION.md section 4.  With `hl-vae_b200/dropin` ahead of the reference
+checkout on sys.path, the reference's own unmodified `training.py` / `HLVAE.py` must import and their
+hot-path names must resolve to this repo's functions.  Needs /root/reference (build container only; the
+GPU box skips it) and uses the test-only stand-ins for gpytorch / matplotlib, which are absent here."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get("HLVAE_REFERENCE", "/root/reference")
+
+SCRIPT = r'''
+import sys
+root, ref = sys.argv[1], sys.argv[2]
+sys.path[:0] = [root, root + "/hl-vae_b200/dropin", root + "/oracle/standins", ref]
+import hlvae_b200
+import training, HLVAE, validation, kernel_gen, kernel_spec, elbo_functions
+from HL_VAE import loglik, read_functions
+from hlvae_b200 import elbo as E, kernels as K, loglik as LL
+assert training.__file__.startswith(ref) and HLVAE.__file__.startswith(ref)          # the reference's own files
+assert training.minibatch_KLD_upper_bound is E.minibatch_KLD_upper_bound
+assert training.minibatch_KLD_upper_bound_iter is E.minibatch_KLD_upper_bound_iter
+assert kernel_gen.generate_kernel_batched is K.generate_kernel_batched
+assert kernel_spec.CatKernel is K.CatKernel and kernel_spec.BinKernel is K.BinKernel
+assert HLVAE.loglik is loglik and loglik.loglik_cat is LL.loglik_cat and loglik.loglik_ordinal is LL.loglik_ordinal
+assert callable(validation.deviance_upper_bound) and callable(elbo_functions.elbo)    # passed through from the reference
+assert training.read_functions is read_functions and hasattr(read_functions, "read_data")
+assert read_functions.statistics.__module__.endswith("read_functions") and "hl-vae_b200" in read_functions.__file__
+import HL_VAE.utils as U
+assert U.__file__.startswith(ref)                                                     # everything else: reference
+print("dropin ok")
+'''
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present")
+def test_reference_training_imports_resolve_to_dropins():
+    r = subprocess.run([sys.executable, "-c", SCRIPT, ROOT, REF], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "dropin ok" in r.stdout, r.stdout + r.stderr
