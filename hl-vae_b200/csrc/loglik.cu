@@ -354,6 +354,60 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N_>
 __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N_) : "memory"); }
 
+// ---- TMA (bulk asynchronous copy) versions of the same staging: ONE thread issues one
+// cp.async.bulk per row and array (16-byte aligned start, size a multiple of 16 bytes - exactly the
+// aligned chunk ranges used below), completion is counted on an mbarrier; the other 127 threads issue
+// nothing.  Results go back the same way (cp.async.bulk shared -> global) for the whole chunks of a row.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned done;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n"
+                 ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+// One row of one array by TMA (called by a single thread): returns the alignment shift, adds the bytes to `tx`.
+template <typename T>
+__device__ __forceinline__ int tma_row_bytes(const T* src, int span, unsigned& bytes) {
+    constexpr int E = 16 / (int)sizeof(T);
+    const int shift = (int)((reinterpret_cast<uintptr_t>(src) & 15) / sizeof(T));
+    bytes = (unsigned)(((shift + span + E - 1) / E) * 16);
+    return shift;
+}
+
+// Whole 16-byte chunks of a staged row go out as one bulk store (single thread); the partial chunks at the
+// two ends are written element-wise by the first threads of the CTA.
+template <typename T>
+__device__ __forceinline__ void tma_unstage_row(T* __restrict__ dst, const T* __restrict__ src, int shift, int span, int tid) {
+    constexpr int E = 16 / (int)sizeof(T);
+    const int i0 = shift > 0 ? 1 : 0;                         // first whole chunk
+    const int i1 = (shift + span) / E;                        // one past the last whole chunk
+    const int head = min(span, E * i0 - shift);               // elements before the first whole chunk
+    const int tail0 = max(head, E * i1 - shift);              // first element after the last whole chunk
+    if (tid == 0 && i1 > i0) bulk_s2g(dst + (E * i0 - shift), src + E * i0, (unsigned)((i1 - i0) * 16));
+    if (tid < head) dst[tid] = src[shift + tid];
+    if (tid >= E && tid - E < span - tail0) dst[tail0 + tid - E] = src[shift + tail0 + tid - E];
+}
+
 // Stage `span` elements of one row as aligned 16-byte chunks: the copy starts at the 16-byte boundary
 // below `src` (`shift` elements early; the caller finds element j at dst[shift + j]) and ends at the
 // boundary above the last element.  The over-read stays inside the array as long as the array itself
@@ -431,9 +485,39 @@ loglik_fwd_k(int64_t N, int D, int tile_vars, int cap, int64_t ld_data, int64_t 
     const int span_p = max(0, min(cap, var_pcol[d1 - 1] + var_nclass[d1 - 1] - ps0));
     const VarC<R> v = load_var<R>(d, D, active, var_kind, var_nclass, var_dcol, var_pcol, vparam, xs0, ps0, cap);
     const int64_t stride = (int64_t)gridDim.y * LL_ROWS;
+    __shared__ __align__(8) unsigned long long mbar[LL_STAGES];
+    const bool use_tma = x_ok && t_ok && m_ok;   // every staged array starts and ends on a 16-byte boundary
+    unsigned phase[LL_STAGES];
+#pragma unroll
+    for (int i = 0; i < LL_STAGES; i++) phase[i] = 0;
+    if (use_tma) {
+        if (tid == 0)
+            for (int i = 0; i < LL_STAGES; i++) mbar_init(&mbar[i], 1);
+        __syncthreads();
+    }
 
     auto prefetch = [&](int64_t n0, int stg) {   // put one row batch in flight (nothing if n0 is past the end)
-        if (n0 < N) {
+        if (n0 < N && use_tma) {
+            if (tid == 0) {
+                R* sT = reinterpret_cast<R*>(ll_smem + stg * stage_bytes);
+                TD* sX = reinterpret_cast<TD*>(sT + LL_ROWS * capt);
+                TM* sK = reinterpret_cast<TM*>(sX + LL_ROWS * capx);
+                const int nr = (int)min((int64_t)LL_ROWS, N - n0);
+                unsigned bt[LL_ROWS], bx[LL_ROWS], bm[LL_ROWS], total = 0;
+                for (int r = 0; r < nr; r++) {
+                    sShiftT[stg][r] = tma_row_bytes<TS>(theta + (n0 + r) * ld_theta + ps0, span_p, bt[r]);
+                    sShift[stg][r] = tma_row_bytes<TD>(data + (n0 + r) * ld_data + xs0, span_x, bx[r]);
+                    sShiftM[stg][r] = tma_row_bytes<TM>(mask + (n0 + r) * D + d0, span_m, bm[r]);
+                    total += bt[r] + bx[r] + bm[r];
+                }
+                mbar_expect_tx(&mbar[stg], total);
+                for (int r = 0; r < nr; r++) {
+                    bulk_g2s(sT + r * capt, theta + (n0 + r) * ld_theta + ps0 - sShiftT[stg][r], bt[r], &mbar[stg]);
+                    bulk_g2s(sX + r * capx, data + (n0 + r) * ld_data + xs0 - sShift[stg][r], bx[r], &mbar[stg]);
+                    bulk_g2s(sK + r * LL_CAPM, mask + (n0 + r) * D + d0 - sShiftM[stg][r], bm[r], &mbar[stg]);
+                }
+            }
+        } else if (n0 < N) {
             R* sT = reinterpret_cast<R*>(ll_smem + stg * stage_bytes);
             TD* sX = reinterpret_cast<TD*>(sT + LL_ROWS * capt);
             TM* sK = reinterpret_cast<TM*>(sX + LL_ROWS * capx);
@@ -459,7 +543,11 @@ loglik_fwd_k(int64_t N, int D, int tile_vars, int cap, int64_t ld_data, int64_t 
             prefetch(n0, 0);
             cp_async_wait_all();
         }
-        __syncthreads();
+        __syncthreads();                         // shifts written by thread 0 / cp.async data of all threads
+        if (use_tma) {
+            mbar_wait(&mbar[stg], phase[stg]);
+            phase[stg] ^= 1;
+        }
         R* sT = reinterpret_cast<R*>(ll_smem + stg * stage_bytes);
         TD* sX = reinterpret_cast<TD*>(sT + LL_ROWS * capt);
         TM* sK = reinterpret_cast<TM*>(sX + LL_ROWS * capx);
@@ -492,10 +580,20 @@ loglik_fwd_k(int64_t N, int D, int tile_vars, int cap, int64_t ld_data, int64_t 
                 if (data_tr) data_tr[o] = dtr;
             }
         }
+        if (use_tma) fence_async_smem();         // params written through the generic proxy, read by the bulk store
         __syncthreads();
         if (params) {
-            for (int r = 0; r < nr; r++)
-                unstage_row<TS>(params + (n0 + r) * ld_theta + ps0, sT + r * capt, sShiftT[stg][r], span_p, tid, t_ok);
+            if (use_tma) {
+                for (int r = 0; r < nr; r++)
+                    tma_unstage_row<TS>(params + (n0 + r) * ld_theta + ps0, sT + r * capt, sShiftT[stg][r], span_p, tid);
+                if (tid == 0) {
+                    bulk_commit();
+                    bulk_wait_read();            // the staged rows have been read; the stage may be refilled
+                }
+            } else {
+                for (int r = 0; r < nr; r++)
+                    unstage_row<TS>(params + (n0 + r) * ld_theta + ps0, sT + r * capt, sShiftT[stg][r], span_p, tid, t_ok);
+            }
         }
         __syncthreads();                         // this stage is refilled by the prefetch of the next iteration
     }
@@ -644,9 +742,43 @@ loglik_bwd_k(int64_t N, int D, int tile_vars, int cap, int64_t ld_data, int64_t 
     const VarC<R> v = load_var<R>(d, D, active, var_kind, var_nclass, var_dcol, var_pcol, vparam, xs0, ps0, cap);
     const R gs = g_scalar ? (R)(*g_scalar) : R(0);
     const int64_t stride = (int64_t)gridDim.y * LL_ROWS;
+    __shared__ __align__(8) unsigned long long mbar[LL_STAGES];
+    const bool use_tma = x_ok && t_ok && m_ok && (!g_lp || g_ok);
+    unsigned phase[LL_STAGES];
+#pragma unroll
+    for (int i = 0; i < LL_STAGES; i++) phase[i] = 0;
+    if (use_tma) {
+        if (tid == 0)
+            for (int i = 0; i < LL_STAGES; i++) mbar_init(&mbar[i], 1);
+        __syncthreads();
+    }
 
     auto prefetch = [&](int64_t n0, int stg) {
-        if (n0 < N) {
+        if (n0 < N && use_tma) {
+            if (tid == 0) {
+                R* sT = reinterpret_cast<R*>(ll_smem + stg * stage_bytes);
+                R* sG = sT + LL_ROWS * capt;
+                TD* sX = reinterpret_cast<TD*>(sG + LL_ROWS * LL_CAPM);
+                TM* sK = reinterpret_cast<TM*>(sX + LL_ROWS * capx);
+                const int nr = (int)min((int64_t)LL_ROWS, N - n0);
+                unsigned bt[LL_ROWS], bx[LL_ROWS], bm[LL_ROWS], bg[LL_ROWS], total = 0;
+                for (int r = 0; r < nr; r++) {
+                    sShiftT[stg][r] = tma_row_bytes<TS>(theta + (n0 + r) * ld_theta + ps0, span_p, bt[r]);
+                    sShift[stg][r] = tma_row_bytes<TD>(data + (n0 + r) * ld_data + xs0, span_x, bx[r]);
+                    sShiftM[stg][r] = tma_row_bytes<TM>(mask + (n0 + r) * D + d0, span_m, bm[r]);
+                    bg[r] = 0;
+                    sShiftG[stg][r] = g_lp ? tma_row_bytes<TS>(g_lp + (n0 + r) * D + d0, span_m, bg[r]) : 0;
+                    total += bt[r] + bx[r] + bm[r] + bg[r];
+                }
+                mbar_expect_tx(&mbar[stg], total);
+                for (int r = 0; r < nr; r++) {
+                    bulk_g2s(sT + r * capt, theta + (n0 + r) * ld_theta + ps0 - sShiftT[stg][r], bt[r], &mbar[stg]);
+                    bulk_g2s(sX + r * capx, data + (n0 + r) * ld_data + xs0 - sShift[stg][r], bx[r], &mbar[stg]);
+                    bulk_g2s(sK + r * LL_CAPM, mask + (n0 + r) * D + d0 - sShiftM[stg][r], bm[r], &mbar[stg]);
+                    if (g_lp) bulk_g2s(sG + r * LL_CAPM, g_lp + (n0 + r) * D + d0 - sShiftG[stg][r], bg[r], &mbar[stg]);
+                }
+            }
+        } else if (n0 < N) {
             R* sT = reinterpret_cast<R*>(ll_smem + stg * stage_bytes);
             R* sG = sT + LL_ROWS * capt;
             TD* sX = reinterpret_cast<TD*>(sG + LL_ROWS * LL_CAPM);
@@ -676,6 +808,10 @@ loglik_bwd_k(int64_t N, int D, int tile_vars, int cap, int64_t ld_data, int64_t 
             cp_async_wait_all();
         }
         __syncthreads();
+        if (use_tma) {
+            mbar_wait(&mbar[stg], phase[stg]);
+            phase[stg] ^= 1;
+        }
         R* sT = reinterpret_cast<R*>(ll_smem + stg * stage_bytes);
         R* sG = sT + LL_ROWS * capt;
         TD* sX = reinterpret_cast<TD*>(sG + LL_ROWS * LL_CAPM);
@@ -697,9 +833,19 @@ loglik_bwd_k(int64_t N, int D, int tile_vars, int cap, int64_t ld_data, int64_t 
                 }
             }
         }
+        if (use_tma) fence_async_smem();
         __syncthreads();
-        for (int r = 0; r < nr; r++)
-            unstage_row<TS>(g_theta + (n0 + r) * ld_theta + ps0, sT + r * capt, sShiftT[stg][r], span_p, tid, t_ok);
+        if (use_tma) {
+            for (int r = 0; r < nr; r++)
+                tma_unstage_row<TS>(g_theta + (n0 + r) * ld_theta + ps0, sT + r * capt, sShiftT[stg][r], span_p, tid);
+            if (tid == 0) {
+                bulk_commit();
+                bulk_wait_read();
+            }
+        } else {
+            for (int r = 0; r < nr; r++)
+                unstage_row<TS>(g_theta + (n0 + r) * ld_theta + ps0, sT + r * capt, sShiftT[stg][r], span_p, tid, t_ok);
+        }
         __syncthreads();
     }
     cp_async_wait_all();
