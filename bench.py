@@ -49,7 +49,7 @@ WORKLOAD = "configs[1]: synthetic HealthMNIST-shaped, L=32, M=64, 800 subjects x
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--subjects", type=int, default=SUBJ_PER_RANK)
