@@ -35,11 +35,10 @@ __device__ __forceinline__ void load_kparams(KParams& kp, const hlvae_kspec_t& s
     }
 }
 
-// exp(x) for x <= 0 (every squared-exponential argument is -(d^2) / (2 l^2)).  About half the
+// exp(x) for x <= 0 (every squared-exponential argument is -(d^2) / (2 l^2)).  Under half the
 // instructions of the general library exp: no overflow / NaN handling, one rounding step
-// (x = k ln2 + r, |r| <= ln2 / 2), a degree-13 Taylor polynomial in Estrin form (short dependency
-// chain) and an exponent insert.  Branch-free.  Error <= ~1.5 ulp; arguments below -708 are clamped
-// (result 3e-308 instead of a denormal or 0).
+// (x = k ln2 + r, |r| <= ln2 / 2), a degree-13 Taylor polynomial and an exponent insert.
+// Branch-free.  Error <= ~1.5 ulp; arguments below -708 are clamped (3e-308 instead of a denormal or 0).
 __device__ __forceinline__ double exp_nonpos(double x) {
     x = fmax(x, -708.0);
     const double MAGIC = 6755399441055744.0;                 // 1.5 * 2^52: adding it rounds to nearest integer
@@ -48,21 +47,25 @@ __device__ __forceinline__ double exp_nonpos(double x) {
     const double kf = t - MAGIC;
     double r = fma(kf, -6.93147180369123816490e-01, x);      // ln2 high part
     r = fma(kf, -1.90821492927058770002e-10, r);             // ln2 low part
-    const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
-    // 1/n!, n = 0..13, paired
-    const double p01 = 1.0 + r;
-    const double p23 = fma(r, 1.0 / 6.0, 0.5);
-    const double p45 = fma(r, 1.0 / 120.0, 1.0 / 24.0);
-    const double p67 = fma(r, 1.0 / 5040.0, 1.0 / 720.0);
-    const double p89 = fma(r, 1.0 / 362880.0, 1.0 / 40320.0);
-    const double pab = fma(r, 1.0 / 39916800.0, 1.0 / 3628800.0);
-    const double pcd = fma(r, 1.0 / 6227020800.0, 1.0 / 479001600.0);
-    const double q0 = fma(r2, p23, p01);                     // terms 0..3
-    const double q1 = fma(r2, p67, p45);                     // terms 4..7
-    const double q2 = fma(r2, pab, p89);                     // terms 8..11
-    const double lo = fma(r4, q1, q0);                       // terms 0..7
-    const double hi = fma(r4, pcd, q2);                      // terms 8..13
-    const double p = fma(r8, hi, lo);
+    // even and odd halves as two independent Horner chains in r^2: every DFMA takes its single new constant
+    // straight from the constant bank (Estrin pairs need two 64-bit constants per DFMA and spend more
+    // instructions moving them into registers than they save); dependency depth 8
+    const double s = r * r;
+    double pe = 1.0 / 479001600.0;                           // 1/12!
+    double po = 1.0 / 6227020800.0;                          // 1/13!
+    pe = fma(pe, s, 1.0 / 3628800.0);
+    po = fma(po, s, 1.0 / 39916800.0);
+    pe = fma(pe, s, 1.0 / 40320.0);
+    po = fma(po, s, 1.0 / 362880.0);
+    pe = fma(pe, s, 1.0 / 720.0);
+    po = fma(po, s, 1.0 / 5040.0);
+    pe = fma(pe, s, 1.0 / 24.0);
+    po = fma(po, s, 1.0 / 120.0);
+    pe = fma(pe, s, 0.5);
+    po = fma(po, s, 1.0 / 6.0);
+    pe = fma(pe, s, 1.0);
+    po = fma(po, s, 1.0);
+    const double p = fma(r, po, pe);
     return p * __hiloint2double((k + 1023) << 20, 0);        // k >= -1022 here
 }
 

@@ -477,6 +477,10 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
 #pragma unroll
         for (int b = 0; b < SIC; b++) sacc[a][b][0] = sacc[a][b][1] = 0.0;
     double p_acc = 0.0, gw_acc = 0.0, a_acc = 0.0;
+    // gradient sums of the cached K0 components, kept per thread over the CTA's whole chunk (reduced once at the end)
+    double hg0[PN_NCACHE], hg1[PN_NCACHE], hg2[PN_NCACHE];
+#pragma unroll
+    for (int r = 0; r < PN_NCACHE; r++) hg0[r] = hg1[r] = hg2[r] = 0.0;
 
     if (tid == 0) meta[2] = s_begin;
     __syncthreads();
@@ -823,13 +827,19 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
                         }
                     }
                 }
-                const double gos = warp_sum(s0);
-                const double gls = warp_sum(s2) * osr * il3;
-                if (lane == 0) {
-                    atomicAdd(&hyp[r], gos);
-                    atomicAdd(&hyp[HLVAE_MAX_COMPS + r], gls);
+                if (r < PN_NCACHE) {
+#pragma unroll
+                    for (int q = 0; q < PN_NCACHE; q++)
+                        if (q == r) { hg0[q] += s0; hg1[q] += s1; hg2[q] += s2; }
+                } else {
+                    const double gos = warp_sum(s0);
+                    const double gls = warp_sum(s2) * osr * il3;
+                    if (lane == 0) {
+                        atomicAdd(&hyp[r], gos);
+                        atomicAdd(&hyp[HLVAE_MAX_COMPS + r], gls);
+                    }
+                    if (c.se_col >= 0 && s1 != 0.0) atomicAdd(&zacc[em * HLVAE_MAX_COMPS + r], s1 * osr * il2);
                 }
-                if (c.se_col >= 0 && s1 != 0.0) atomicAdd(&zacc[em * HLVAE_MAX_COMPS + r], s1 * osr * il2);
             }
         }
         __syncthreads();
@@ -883,6 +893,21 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
         __syncthreads();
     }
 
+    // ---- cached components: reduce the per-thread gradient sums into hyp / zacc
+#pragma unroll
+    for (int r = 0; r < PN_NCACHE; r++) {
+        if (r < sp0.ncomp) {
+            const double osr = kps[r], il2 = kps[2 * HLVAE_MAX_COMPS + r], il3 = kps[3 * HLVAE_MAX_COMPS + r];
+            const double gos = warp_sum(hg0[r]);
+            const double gls = warp_sum(hg2[r]) * osr * il3;
+            if (lane == 0) {
+                atomicAdd(&hyp[r], gos);
+                atomicAdd(&hyp[HLVAE_MAX_COMPS + r], gls);
+            }
+            if (sp0.comp[r].se_col >= 0 && hg1[r] != 0.0) atomicAdd(&zacc[em * HLVAE_MAX_COMPS + r], hg1[r] * osr * il2);
+        }
+    }
+    __syncthreads();
     // ---- flush CTA accumulators
     {
         double* Sg = acc + off.o[HLVAE_ACC_S] + (int64_t)l * M * M;
