@@ -57,6 +57,9 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--eager", action="store_true", help="time eager launches instead of CUDA-graph replay")
     ap.add_argument("--no-overlap", action="store_true", help="single stream: no likelihood / KL overlap")
+    ap.add_argument("--workload", default="elbo", choices=["elbo", "predict"],
+                    help="elbo: the BASELINE.json metric (default); predict: SURVEY 8(f) row 1, GP posterior-mean "
+                         "prediction (utils.batch_predict_varying_T), its own JSON line")
     return ap.parse_args()
 
 
@@ -499,8 +502,72 @@ def run_gpu(args):
         os._exit(0)
 
 
+def run_predict(args):
+    """utils.batch_predict_varying_T (utils.py:99-191) at the configs[1] shape:
+    16000 conditioning rows (800 subjects x T=20), 4000 test rows, L=32, M=64.  One call = one "step"."""
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    import __graft_entry__ as g
+    g.build()
+    from hlvae_b200 import kernels, likelihoods, predict, synth
+    from oracle import hlvae_oracle as orc
+    rng = np.random.default_rng(0)
+    gen = torch.Generator().manual_seed(0)
+    x, lens = synth.covariates(args.subjects, T, rng)
+    pool, _ = synth.covariates(400, T, np.random.default_rng(1))
+    z = synth.inducing_points(pool, L, M, np.random.default_rng(1))
+    sel = torch.from_numpy(rng.choice(x.shape[0], x.shape[0] // 4, replace=False))
+    test_x = x[sel].clone()
+    test_x[:, 0] += 0.5
+    mu = torch.randn(x.shape[0], L, generator=gen, dtype=torch.float64)
+    k0, k1 = kernels.generate_kernel_batched(L, **synth.DEFAULT_KERNEL_ARGS)
+    k0, k1 = k0.to(dev).double().eval(), k1.to(dev).double().eval()
+    lik = likelihoods.GaussianLikelihood(batch_shape=torch.Size([L]), noise_constraint=likelihoods.GreaterThan(1e-8))
+    lik.noise = 1
+    lik = lik.to(dev).double().eval()
+    xd, xtd, mud, zd = x.to(dev), test_x.to(dev), mu.to(dev), z.to(dev)
+    call = lambda: predict.batch_predict_varying_T(L, k0, k1, lik, xd, xtd, mud, zd, 2, EPS)
+    for _ in range(max(args.warmup, 3)):
+        call()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = call()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    # CPU arm: the oracle restatement on a bounded sample (100 subjects, 500 test rows), scaled in rows
+    ns = 100
+    xs_, ls_ = synth.covariates(ns, T, np.random.default_rng(0))
+    ts_ = xs_[:500].clone()
+    ts_[:, 0] += 0.5
+    spec0, spec1 = orc.compile_spec(**synth.DEFAULT_KERNEL_ARGS)
+    p0, p1 = orc.KernelParams.default(spec0, L), orc.KernelParams.default(spec1, L)
+    torch.set_num_threads(os.cpu_count() or 1)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        orc.batch_predict(spec0, p0, spec1, p1, torch.ones(L, dtype=torch.float64), xs_, ts_, mu[:xs_.shape[0]], z,
+                          orc.split_subjects_by_id(xs_, 2), 2, EPS)
+    cpu_s = (time.perf_counter() - t0) * (args.subjects / ns)
+    line = dict(metric="GP posterior-mean prediction calls/sec (utils.batch_predict_varying_T)", value=1e3 / ms,
+                unit="calls/s", n_gpus=1, steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms,
+                higher_is_better=True, dtype="f64", data="synthetic",
+                config=dict(workload=f"SURVEY 8(f).1: {x.shape[0]} conditioning rows ({args.subjects} subjects x T={T}), "
+                                     f"{test_x.shape[0]} test rows, L={L}, M={M}, default kernel"),
+                cpu_baseline=dict(value=1.0 / cpu_s, unit="calls/s", cores=torch.get_num_threads(), kind="port",
+                                  sample=f"{ns} subjects / 500 test rows, float64 oracle port, scaled x{args.subjects / ns:.0f} in rows"),
+                checksum=float(out.abs().sum()))
+    print(json.dumps(line), flush=True)
+
+
 def main():
     args = parse()
+    if args.workload == "predict" and args.impl != "reference":
+        run_predict(args)
+        return
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -264,6 +264,51 @@ def natural_gradient_update(m, H, grad_m, grad_H, lr):
     return m_new.detach(), H_new.detach()
 
 
+def batch_predict(spec0, prm0, spec1, prm1, noise, prediction_x, test_x, mu, z, subjects: List[torch.Tensor],
+                  id_covariate: int, eps: float) -> torch.Tensor:
+    """GP posterior-mean prediction of the latent variables at `test_x`: utils.batch_predict_varying_T
+    (utils.py:99-191; with every subject T rows long it equals utils.batch_predict, :193-271).  The
+    reference's `torch.solve(B, A)` (removed from torch) is `torch.linalg.solve(A, B)`.
+
+    prediction_x [N, Q] / mu [N, L]: covariates and encoder means of the conditioning rows; `subjects`:
+    row-index tensors of prediction_x, one per subject; returns Z_pred [N_test, L]."""
+    L, M = z.shape[0], z.shape[1]
+    N = prediction_x.shape[0]
+    K0xz = eval_additive(spec0, prm0, prediction_x, z)                        # :128 / :229
+    K0zz = eval_additive(spec0, prm0, z, z) + eps * torch.eye(M, dtype=DT)    # :129,132 / :230,234
+    K0Xz = eval_additive(spec0, prm0, test_x, z)                              # :130 / :232
+    K0zx = K0xz.transpose(-1, -2)
+    Hm = K0zz.clone()
+    iB_mu = torch.zeros(L, N, 1, dtype=DT)
+    iBs = []
+    for idx in subjects:                                                      # :139-160
+        xs = prediction_x[idx]
+        T = xs.shape[0]
+        xs_l = xs.unsqueeze(0).expand(L, T, xs.shape[1])
+        Bs = eval_additive(spec1, prm1, xs_l, xs_l) + torch.eye(T, dtype=DT) * noise.reshape(L, 1, 1)   # :149-150
+        _, iB = _chol_inv(Bs)                                                 # :152-153
+        Ks = K0xz[:, idx]
+        Hm = Hm + Ks.transpose(1, 2) @ iB @ Ks                                # :156-158
+        iB_mu[:, idx] = iB @ mu[idx].T.unsqueeze(2)                           # :159
+        iBs.append(iB)
+    t = K0xz @ torch.linalg.solve(Hm, K0zx @ iB_mu)                           # :162
+    corr = torch.zeros(L, N, 1, dtype=DT)
+    for idx, iB in zip(subjects, iBs):                                        # :164-166
+        corr[:, idx] = iB @ t[:, idx]
+    mu_tilde = iB_mu - corr                                                   # :167
+    first = K0Xz @ torch.linalg.solve(K0zz, K0zx @ mu_tilde)                  # :169
+    test_ids = torch.unique(test_x[:, id_covariate])                          # :171-172
+    mask = torch.isin(prediction_x[:, id_covariate], test_ids)
+    second = torch.zeros(L, test_x.shape[0], 1, dtype=DT)
+    xm = prediction_x[mask]
+    for sid in test_ids:                                                      # :175-186
+        sel = test_x[:, id_covariate] == sid
+        xt = test_x[sel]
+        K1Xx = eval_additive(spec1, prm1, xt.unsqueeze(0).expand(L, *xt.shape), xm.unsqueeze(0).expand(L, *xm.shape))
+        second[:, sel] = K1Xx @ mu_tilde[:, mask]
+    return (first + second).squeeze(2).T                                      # :188
+
+
 # --------------------------------------------------------------------------------------
 # Heterogeneous likelihoods (HL_VAE/loglik.py) on the packed [N, E_x] / [N, P_theta] layout
 # --------------------------------------------------------------------------------------

@@ -272,8 +272,77 @@ def loglik_case(name, types, N, seed, conv=False, observed=0.7):
     print(f"  {name}: N={N} D={D} E_x={E_x} worst rel diff {max(w):.2e}")
 
 
+# ------------------------------------------------------------------ GP posterior-mean prediction
+def predict_case(name, kargs, L, M, n_subj, T, ragged, seed, n_test_subj=3, continuous_age=False):
+    """utils.batch_predict_varying_T (and, with equal T, utils.batch_predict) of the unmodified reference.
+    Both call `torch.solve(B, A)`, which current torch no longer has: it is shimmed as
+    (torch.linalg.solve(A, B), None) for the duration of the call - the reference file itself is untouched."""
+    import utils as ref_utils                                # reference (needs the matplotlib stand-in)
+    rng = np.random.default_rng(seed)
+    gen = torch.Generator().manual_seed(seed)
+    x, lens = synth.covariates(n_subj, T, rng, ragged=ragged, t_min=3, continuous_age=continuous_age)
+    pool, _ = synth.covariates(40, T, rng, continuous_age=continuous_age)
+    z = synth.inducing_points(torch.cat([x, pool]), L, M, rng)
+    N = x.shape[0]
+    mu = torch.randn(N, L, generator=gen, dtype=DT)
+    k0, k1, lik = ref_modules(L, kargs, gen)
+    k0.eval(); k1.eval(); lik.eval()
+    idc = kargs['id_covariate']
+    # test rows: unseen time points of the first n_test_subj subjects plus one subject absent from prediction_x
+    starts = np.concatenate([[0], np.cumsum(lens)])
+    rows = []
+    for s_ in range(n_test_subj):
+        xr = x[starts[s_]:starts[s_ + 1]].clone()
+        xr[:, 0] += 0.5
+        rows.append(xr[: max(2, len(xr) // 2)])
+    extra, _ = synth.covariates(1, T, rng, first_id=10_000, continuous_age=continuous_age)
+    rows.append(extra[:4])
+    test_x = torch.cat(rows)
+    eps = 1e-6
+    had = hasattr(torch, "solve")
+    old = getattr(torch, "solve", None)
+    torch.solve = lambda B, A: (torch.linalg.solve(A, B), None)
+    try:
+        with torch.no_grad():
+            zp = ref_utils.batch_predict_varying_T(L, k0, k1, lik, x, test_x, mu, z, idc, eps)
+            zp_fixed = None
+            if not ragged:
+                zp_fixed = ref_utils.batch_predict(L, k0, k1, lik, x, test_x, mu, z, n_subj, T, idc, eps)
+    finally:
+        if had:
+            torch.solve = old
+        else:
+            del torch.solve
+    spec0, spec1 = orc.compile_spec(**kargs)
+    ros0, rls0 = extract_params(k0)
+    ros1, rls1 = extract_params(k1)
+    noise = lik.noise_covar.noise.detach().reshape(-1).clone()
+    prm0, prm1 = orc.KernelParams(ros0.clone(), rls0.clone()), orc.KernelParams(ros1.clone(), rls1.clone())
+    with torch.no_grad():
+        ozp = orc.batch_predict(spec0, prm0, spec1, prm1, noise, x, test_x, mu, z, orc.split_subjects_by_id(x, idc), idc, eps)
+    w = [check(name + ".Z_pred", ozp, zp, 1e-7)]
+    if zp_fixed is not None:
+        w.append(check(name + ".Z_pred_fixedT", ozp, zp_fixed, 1e-7))
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), kargs=repr(kargs), L=L, M=M, T=T, n_subj=n_subj, eps=eps,
+                        ragged=int(ragged), x=x.numpy(), lens=np.array(lens), test_x=test_x.numpy(), mu=mu.numpy(),
+                        z=z.numpy(), noise=noise.numpy(), ros0=ros0.numpy(), rls0=rls0.numpy(), ros1=ros1.numpy(),
+                        rls1=rls1.numpy(), Z_pred=zp.numpy())
+    print(f"  {name}: N={N} N_test={test_x.shape[0]} worst rel diff {max(w):.2e}")
+
+
+def predict_cases():
+    print("GP posterior-mean prediction: oracle vs unmodified reference (torch.solve shimmed)")
+    predict_case("predict_default_ragged", synth.DEFAULT_KERNEL_ARGS, L=4, M=12, n_subj=6, T=8, ragged=True, seed=21)
+    predict_case("predict_default_fixedT", synth.DEFAULT_KERNEL_ARGS, L=3, M=10, n_subj=5, T=6, ragged=False, seed=22)
+    predict_case("predict_sweep_ragged", synth.SWEEP_KERNEL_ARGS, L=3, M=16, n_subj=7, T=10, ragged=True, seed=23,
+                 continuous_age=True)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "predict":      # only the prediction fixtures
+        predict_cases()
+        return
     print("KL upper bound: oracle vs unmodified reference (gpytorch stand-in)")
     kl_case("kl_default_ragged", synth.DEFAULT_KERNEL_ARGS, L=4, M=12, n_subj=6, T=8, ragged=True, fixed_T_api=False, seed=1)
     kl_case("kl_default_fixedT", synth.DEFAULT_KERNEL_ARGS, L=3, M=10, n_subj=5, T=6, ragged=False, fixed_T_api=True, seed=2)
@@ -293,6 +362,7 @@ def main():
     loglik_case("loglik_tabular_small", [('count', 1)] * 3 + [('ordinal', 5)] * 3 + [('cat', 5)] * 3 + [('real', 1)] * 2 + [('pos', 1)] * 2,
                 N=16, seed=12)
     loglik_case("loglik_conv_d4", synth.HEALTHMNIST_D4_TYPES, N=3, seed=13, conv=True, observed=0.75)
+    predict_cases()
     print("all oracle-vs-reference checks passed; goldens written to", GOLD)
 
 

@@ -28,6 +28,10 @@ assert HLVAE.loglik is loglik and loglik.loglik_cat is LL.loglik_cat and loglik.
 assert callable(validation.deviance_upper_bound) and callable(elbo_functions.elbo)    # passed through from the reference
 assert training.read_functions is read_functions and hasattr(read_functions, "read_data")
 assert read_functions.statistics.__module__.endswith("read_functions") and "hl-vae_b200" in read_functions.__file__
+import utils as RU, model_test
+from hlvae_b200 import predict as PR
+assert RU.batch_predict_varying_T is PR.batch_predict_varying_T and model_test.batch_predict is PR.batch_predict
+assert RU.HensmanDataLoader.__module__ == "_hlvae_reference_utils" and training.SubjectSampler is RU.SubjectSampler
 import HL_VAE.utils as U
 assert U.__file__.startswith(ref)                                                     # everything else: reference
 print("dropin ok")

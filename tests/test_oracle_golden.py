@@ -67,3 +67,19 @@ def test_fixed_T_and_iter_agree():
                     inp["rls0"], inp["ros1"], inp["rls1"], inp["noise"], 200, 4, 200 * 5, 1e-6, fixed_T=5)
     assert h.rel_err(a["kld"], b["kld"]) < 1e-9
     assert h.rel_err(a["grad_H"], b["grad_H"]) < 1e-9
+
+
+@pytest.mark.parametrize("name", ["predict_default_ragged", "predict_default_fixedT", "predict_sweep_ragged"])
+def test_oracle_predict_matches_reference_goldens(name):
+    """GP posterior-mean prediction (utils.py:99-271): the oracle restatement against the frozen outputs of the
+    unmodified reference functions."""
+    import ast
+    g = h.load(name)
+    kargs = ast.literal_eval(str(g["kargs"]))
+    spec0, spec1 = orc.compile_spec(**kargs)
+    prm0 = orc.KernelParams(h.t(g["ros0"]), h.t(g["rls0"]))
+    prm1 = orc.KernelParams(h.t(g["ros1"]), h.t(g["rls1"]))
+    x = h.t(g["x"])
+    zp = orc.batch_predict(spec0, prm0, spec1, prm1, h.t(g["noise"]), x, h.t(g["test_x"]), h.t(g["mu"]), h.t(g["z"]),
+                           orc.split_subjects_by_id(x, kargs["id_covariate"]), kargs["id_covariate"], float(g["eps"]))
+    assert h.rel_err(zp, g["Z_pred"]) < 1e-9
