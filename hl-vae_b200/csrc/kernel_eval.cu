@@ -90,6 +90,33 @@ bool spec_ok(const hlvae_kspec_t* sp, int Q) {
     return true;
 }
 
+
+// out[i, l] = sum_{j in subject sid[i]} K_l(xt[i], x[row_idx[j]]) * v[row_idx[j], l]
+// (utils.py:175-186: K1(X*, x) mu_tilde; every K1 term carries the id kernel, so only the rows of the test
+// row's own subject contribute).  grid: (ceil(Nt / 256), L); sid[i] < 0: subject absent -> 0.
+__global__ void __launch_bounds__(EV_THREADS)
+subject_matvec_k(const __grid_constant__ hlvae_kspec_t sp, const double* __restrict__ os,
+                 const double* __restrict__ ls, int L, int Q, const double* __restrict__ xt, int nt,
+                 const double* __restrict__ x, const int32_t* __restrict__ row_idx,
+                 const int32_t* __restrict__ subj_ptr, const int32_t* __restrict__ sid,
+                 const double* __restrict__ v, double* __restrict__ out) {
+    const int l = blockIdx.y;
+    KParams kp;
+    load_kparams(kp, sp, os, ls, L, l);
+    const int i = blockIdx.x * EV_THREADS + threadIdx.x;
+    if (i >= nt) return;
+    const int s = sid[i];
+    double acc = 0.0;
+    if (s >= 0) {
+        const double* xa = xt + (int64_t)i * Q;
+        for (int j = subj_ptr[s]; j < subj_ptr[s + 1]; j++) {
+            const int g = row_idx[j];
+            acc = fma(eval_additive(sp, kp, xa, x + (int64_t)g * Q), v[(int64_t)g * L + l], acc);
+        }
+    }
+    out[(int64_t)i * L + l] = acc;
+}
+
 }  // namespace
 
 namespace hlvae {
@@ -126,6 +153,21 @@ extern "C" int hlvae_kernel_eval_bwd(const hlvae_kspec_t* spec, const double* ou
     kernel_eval_bwd_k<<<grid, EV_THREADS, 0, (cudaStream_t)stream>>>(*spec, outputscale, lengthscale, L, Q, x1, n1,
                                                                      ld1, bs1, x2, n2, ld2, bs2, g_out, g_os, g_ls,
                                                                      g_x1, g_x2);
+    HLVAE_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int hlvae_subject_matvec(const hlvae_kspec_t* spec, const double* outputscale, const double* lengthscale,
+                                    int L, int Q, const double* xt, int nt, const double* x, const int32_t* row_idx,
+                                    const int32_t* subj_ptr, const int32_t* sid, const double* v, double* out,
+                                    void* stream) {
+    if (!hlvae::spec_valid(spec, Q) || L <= 0 || Q <= 0 || Q > HLVAE_MAX_Q || nt < 0 || !xt || !x || !row_idx ||
+        !subj_ptr || !sid || !v || !out)
+        return HLVAE_E_ARG;
+    if (nt == 0) return 0;
+    dim3 grid((unsigned)((nt + EV_THREADS - 1) / EV_THREADS), (unsigned)L);
+    subject_matvec_k<<<grid, EV_THREADS, 0, (cudaStream_t)stream>>>(*spec, outputscale, lengthscale, L, Q, xt, nt, x,
+                                                                    row_idx, subj_ptr, sid, v, out);
     HLVAE_CHECK_LAUNCH();
     return 0;
 }

@@ -90,8 +90,23 @@ def _predict(latent_dim, covar_module0, covar_module1, likelihoods, prediction_x
         K0xz = evaluate_dense(covar_module0, x, z)                                          # [L, N, M]
         rhs = torch.bmm(K0xz.transpose(1, 2), mu_tilde.T.unsqueeze(2))                      # K0zx mu_tilde
         first = torch.bmm(evaluate_dense(covar_module0, xt, z), torch.linalg.solve(K0zz, rhs))   # :169 / :249
-        # K1(X*, x) mu_tilde over the conditioning rows whose subject appears in test_x (:171-186 / :251-267);
-        # every K1 term carries the id kernel, so the per-subject loop of the reference is one dense product
+        # K1(X*, x) mu_tilde over the conditioning rows whose subject appears in test_x (:171-186 / :251-267)
+        id_rows = all(any(fs1.cspec.comp[r].disc_kind[f] == _lib.KIND_CAT and fs1.cspec.comp[r].disc_col[f] == id_covariate
+                          for f in range(fs1.cspec.comp[r].ndisc)) for r in range(fs1.ncomp))
+        if id_rows and layout.n_subj > 0:
+            # every K1 term carries the id kernel (kernel_gen.py:225-242,269-289 route exactly those terms to K1):
+            # only the rows of a test row's own subject contribute -> one pass over [N_test, L], no dense block
+            first_rows = layout.row_idx[layout.subj_ptr[:-1].long()].long()
+            ids_sorted, perm = torch.sort(x[first_rows, id_covariate])     # id value of every subject of the layout
+            tid = xt[:, id_covariate].contiguous()
+            pos = torch.searchsorted(ids_sorted, tid).clamp_(max=ids_sorted.numel() - 1)
+            sid = torch.where(ids_sorted[pos] == tid, perm[pos], torch.full_like(pos, -1)).to(torch.int32)
+            out2 = torch.empty(xt.shape[0], L, dtype=torch.float64, device=dev)
+            mt = mu_tilde.contiguous()
+            _lib.call("hlvae_subject_matvec", fs1.cspec, _lib.ptr(hp[2]), _lib.ptr(hp[3]), L, Q, _lib.ptr(xt), xt.shape[0],
+                      _lib.ptr(x), _lib.ptr(layout.row_idx), _lib.ptr(layout.subj_ptr), _lib.ptr(sid), _lib.ptr(mt),
+                      _lib.ptr(out2), _lib.stream_ptr())
+            return (first.squeeze(2).T + out2).contiguous()                                 # :188 / :269
         test_ids = torch.unique(xt[:, id_covariate])
         mask = torch.isin(x[:, id_covariate], test_ids)
         second = torch.zeros_like(first)

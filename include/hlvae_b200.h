@@ -87,6 +87,14 @@ int hlvae_kernel_eval_bwd(const hlvae_kspec_t* spec, const double* outputscale, 
                           const double* x2, int n2, int64_t ld2, int64_t bs2, const double* g_out,
                           double* g_os, double* g_ls, double* g_x1, double* g_x2, void* stream);
 
+/* K1(X*, x) v restricted to same-subject pairs, the last term of the GP posterior-mean predictors
+ * (utils.py:175-186 / :255-267): out[i, l] = sum over the rows j of subject sid[i] of
+ * K_l(xt[i], x[row_idx[j]]) v[row_idx[j], l];  sid[i] < 0 (subject not among the conditioning rows) -> 0.
+ * xt [nt,Q], x [N,Q], v [N,L], out [nt,L] float64 row-major; (row_idx, subj_ptr) as in hlvae_kl_subject. */
+int hlvae_subject_matvec(const hlvae_kspec_t* spec, const double* outputscale, const double* lengthscale,
+                         int L, int Q, const double* xt, int nt, const double* x, const int32_t* row_idx,
+                         const int32_t* subj_ptr, const int32_t* sid, const double* v, double* out, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * Streaming part of the KL upper bound: everything in
  * elbo_functions.minibatch_KLD_upper_bound (elbo_functions.py:118-193) and
