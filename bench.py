@@ -57,7 +57,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--eager", action="store_true", help="time eager launches instead of CUDA-graph replay")
     ap.add_argument("--no-overlap", action="store_true", help="single stream: no likelihood / KL overlap")
-    ap.add_argument("--workload", default="elbo", choices=["elbo", "predict"],
+    ap.add_argument("--workload", default="elbo", choices=["elbo", "predict", "sweep"],
                     help="elbo: the BASELINE.json metric (default); predict: SURVEY 8(f) row 1, GP posterior-mean "
                          "prediction (utils.batch_predict_varying_T), its own JSON line")
     return ap.parse_args()
@@ -563,10 +563,120 @@ def run_predict(args):
     print(json.dumps(line), flush=True)
 
 
+def run_sweep(args):
+    """BASELINE.json configs[2] and configs[3] as tables (not the headline line):
+    (a) additive-kernel sweep - SE(time) + CA(id) + SE(age) x CA(sex), M in {32, 64, 128}, minibatch 4k / 16k / 64k
+        rows (T = 20; plus a ragged 16k case), L = 32: device time of one KL forward + backward
+        (hlvae_mxm_pre, hlvae_kl_subject, hlvae_kl_panel, hlvae_mxm_post, hlvae_kernel_eval_bwd) and of its
+        streaming kernels alone;
+    (b) likelihood-heavy tabular batch - 64 count + 64 ordinal(5) + 64 cat(5) + 32 real + 32 pos, 30 % missing,
+        16k / 64k rows, float32 storage: fused likelihood forward / backward time and GB/s of algorithmic bytes."""
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    import __graft_entry__ as g
+    g.build()
+    from hlvae_b200 import _lib, config, elbo, kernels, likelihoods, loglik, subjects, synth
+    from oracle import hlvae_oracle as orc
+    config.check_errors = False
+    config.overlap = False
+    hbm_peak, _ = measured_peaks()
+    reps = max(args.steps, 5)
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        _lib.PROFILE = []
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        per = {}
+        for name, a, b in _lib.PROFILE:
+            per.setdefault(name, []).append(a.elapsed_time(b))
+        _lib.PROFILE = None
+        return e0.elapsed_time(e1) / reps, {k: float(np.mean(v)) for k, v in per.items()}
+
+    kl_rows = []
+    for Mx in (32, 64, 128):
+        for n_subj, ragged in ((200, False), (800, False), (800, True), (3200, False)):
+            rng = np.random.default_rng(7)
+            gen = torch.Generator().manual_seed(7)
+            x, lens = synth.covariates(n_subj, T, rng, ragged=ragged, t_min=5, continuous_age=True)
+            pool, _ = synth.covariates(400, T, np.random.default_rng(8), continuous_age=True)
+            z = synth.inducing_points(pool, L, Mx, np.random.default_rng(8)).to(dev).requires_grad_(True)
+            m, H = synth.variational_state(L, Mx, gen)
+            k0, k1 = kernels.generate_kernel_batched(L, **synth.SWEEP_KERNEL_ARGS)
+            k0, k1 = k0.to(dev).double(), k1.to(dev).double()
+            lik = likelihoods.GaussianLikelihood(batch_shape=torch.Size([L]), noise_constraint=likelihoods.GreaterThan(1e-8))
+            lik.noise = 1
+            lik = lik.to(dev).double()
+            N_b = x.shape[0]
+            mu = torch.randn(N_b, L, generator=gen).to(dev).requires_grad_(True)
+            lv = (-3.0 * torch.rand(N_b, L, generator=gen)).to(dev).requires_grad_(True)
+            lay = subjects.SubjectLayout.from_lengths(lens, dev)
+            xd, md, Hd = x.to(dev), m.to(dev), H.to(dev)
+
+            def step():
+                for t_ in (mu, lv, z, *k0.parameters(), *k1.parameters()):
+                    t_.grad = None
+                kld, gm, gH = elbo.minibatch_KLD_upper_bound_iter(k0, k1, lik, L, md, Hd, xd, mu, lv, z, P_TOTAL, n_subj,
+                                                                  N_TOTAL, True, 2, EPS, layout=lay)
+                kld.sum().backward()
+
+            ms, per = timed(step)
+            stream = per.get("hlvae_kl_subject", 0.0) + per.get("hlvae_kl_panel", 0.0)
+            flops = 2.0 * L * N_b * Mx * Mx * 2 + 2.0 * L * N_b * T * Mx * 2
+            kl_rows.append(dict(M=Mx, rows=N_b, subjects=n_subj, ragged=ragged, kl_fwd_bwd_ms=round(ms, 3),
+                                kl_subject_ms=round(per.get("hlvae_kl_subject", 0.0), 3),
+                                kl_panel_ms=round(per.get("hlvae_kl_panel", 0.0), 3),
+                                panel_tflops=round(flops / (per["hlvae_kl_panel"] * 1e-3) / 1e12, 2),
+                                rows_per_s=round(N_b / (stream * 1e-3))))
+    ll_rows = []
+    types = synth.TABULAR_TYPES
+    layt = loglik.VarLayout(types, dev)
+    descs, E_x, P_th = orc.build_layout(types)
+    for N_b in (16000, 64000):
+        rng = np.random.default_rng(9)
+        gen = torch.Generator(device=dev).manual_seed(9)
+        data, mask = synth.likelihood_batch(types, 4000, rng)
+        reps_ = N_b // 4000
+        data = data.float().repeat(reps_, 1).to(dev)
+        mask = mask.to(torch.uint8).repeat(reps_, 1).to(dev)
+        theta = torch.randn(N_b, P_th, device=dev, generator=gen).requires_grad_(True)
+        z32 = torch.zeros(32, dtype=torch.float64, device=dev)
+        lvr, lvp = z32.clone().requires_grad_(True), z32.clone().requires_grad_(True)
+
+        def step():
+            theta.grad = lvr.grad = lvp.grad = None
+            vparam = layt.vparam(lvr, lvp, [z32, torch.ones_like(z32)], [z32, torch.ones_like(z32)])
+            out = loglik.fused_loglik(layt, data, mask, theta, vparam, monitor=True)
+            (-out["log_p_x_sum"]).backward()
+
+        ms, per = timed(step)
+        D = len(types)
+        bf = N_b * (4 * E_x + 4 * P_th + D + 4 * (5 * D + P_th))
+        bb = N_b * (4 * E_x + 4 * P_th + D + 4 * P_th)
+        ll_rows.append(dict(rows=N_b, D=D, fwd_ms=round(per["hlvae_loglik_fwd"], 3), bwd_ms=round(per["hlvae_loglik_bwd"], 3),
+                            fwd_gbs=round(bf / (per["hlvae_loglik_fwd"] * 1e-3) / 1e9), fwd_frac=round(bf / (per["hlvae_loglik_fwd"] * 1e-3) / 1e9 / hbm_peak, 3),
+                            bwd_gbs=round(bb / (per["hlvae_loglik_bwd"] * 1e-3) / 1e9), bwd_frac=round(bb / (per["hlvae_loglik_bwd"] * 1e-3) / 1e9 / hbm_peak, 3)))
+    print(json.dumps(dict(workload="sweep: BASELINE.json configs[2] (kernel sweep, L=32, T=20, SE(time)+CA(id)+SE(age)xCA(sex)) "
+                                   "and configs[3] (tabular likelihoods, 30 % missing, f32 storage)",
+                          timing="CUDA events, eager single-stream launches, 3 warm-ups", kernel_sweep=kl_rows,
+                          tabular_loglik=ll_rows, hbm_peak_gbs=hbm_peak)), flush=True)
+
+
 def main():
     args = parse()
     if args.workload == "predict" and args.impl != "reference":
         run_predict(args)
+        return
+    if args.workload == "sweep" and args.impl != "reference":
+        run_sweep(args)
         return
     if args.impl == "reference":
         run_reference(args)

@@ -610,6 +610,77 @@ loglik_fwd_k(int64_t N, int D, int tile_vars, int cap, int64_t ld_data, int64_t 
     }
 }
 
+// Ordinal variable, backward (loglik.py:149-188 differentiated): theta is overwritten with
+// g * d log_p_x / d theta.  CMAX is the unroll bound; when it equals C everything stays in registers.
+template <typename R, typename XT, int CMAX>
+__device__ __forceinline__ void ord_backward(const XT* __restrict__ x_, R* __restrict__ t, int C, bool observed, R g) {
+    struct { const XT* p; __device__ __forceinline__ R operator[](int c) const { return (R)p[c]; } } x{x_};
+    const R eps = R(1e-6);
+    const R t_loc = t[C - 1];
+    const R loc = softplus_<R>(t_loc);
+    R dsg[CMAX], q[CMAX];      // dsg_c = sigma'(u_c) = sigma(u_c) sigma(-u_c)
+    R cum = R(0), prev = R(0), tot = R(0), sneg_prev = R(1);
+    int vals = 0;
+#pragma unroll
+    for (int c = 0; c < CMAX; c++) {
+        if (c < C) {
+            R sg = R(1), qc, ds = R(0);
+            if (c < C - 1) {
+                const R delta = clamp_<R>(softplus_<R>(t[c]), eps, R(1e20));
+                cum += delta;
+                const R e = Mth<R>::ex(loc - cum);                      // exp(-u_c)
+                sg = Mth<R>::rcp(R(1) + e);
+                const R sneg = (e > R(1e30)) ? R(1) : e * sg;           // sigma(-u_c), no cancellation
+                ds = sg * sneg;
+                if constexpr (sizeof(R) == 4) {
+                    qc = (c == 0) ? sg : sg * sneg_prev * (-Mth<R>::exm1(-delta));
+                } else {
+                    qc = sg - prev;
+                }
+                sneg_prev = sneg;
+            } else {
+                if constexpr (sizeof(R) == 4) qc = sneg_prev; else qc = sg - prev;
+            }
+            dsg[c] = ds;
+            q[c] = qc;
+            prev = sg;
+            tot += clamp_<R>(qc, eps, R(1));
+            vals += (int)x[c];
+        }
+    }
+    if (!observed) vals = 1;
+    const int y = vals - 1;
+    // lp = log p_y - log tot ; the clamp passes gradient inside [eps, 1]
+    // q_c = sg_c - sg_{c-1}: d/dsg_c = gq_c - gq_{c+1}, c < C-1; u_c = cum_c - loc
+    const R itot = Mth<R>::rcp(tot);
+    R g_loc = R(0), run = R(0), gq_next = R(0);
+    {
+        const R qc = q[C - 1];
+        const R pc = clamp_<R>(qc, eps, R(1));
+        const R gp = ((C - 1 == y) ? Mth<R>::rcp(pc) : R(0)) - itot;
+        gq_next = (qc >= eps && qc <= R(1)) ? gp : R(0);
+    }
+#pragma unroll
+    for (int c = CMAX - 2; c >= 0; c--) {
+        if (c <= C - 2) {
+            const R qc = q[c];
+            const R pc = clamp_<R>(qc, eps, R(1));
+            const R gp = ((c == y) ? Mth<R>::rcp(pc) : R(0)) - itot;
+            const R gqc = (qc >= eps && qc <= R(1)) ? gp : R(0);
+            const R gu = (gqc - gq_next) * dsg[c];
+            gq_next = gqc;
+            g_loc -= gu;
+            run += gu;                                   // reverse cumulative sum -> d/d delta_c
+            const R tc = t[c];
+            const R sp = softplus_<R>(tc);
+            const R ga = (sp >= eps && sp <= R(1e20)) ? run * dsoftplus_<R>(tc) : R(0);
+            t[c] = g * ga;
+        }
+    }
+    t[C - 1] = g * g_loc * dsoftplus_<R>(t_loc);
+
+}
+
 // ------------------------------------------------------------------------------------
 // One variable, backward: d log_p_x / d theta (times g) into t (in place of theta), and the
 // derivative w.r.t. the raw log-variance parameter (real / pos).
@@ -644,69 +715,16 @@ __device__ __forceinline__ void var_backward(const VarC<R>& v, const XT* __restr
             default: cat_backward<R, XT, HLVAE_MAX_CLASS>(x_, t, C, g); break;
         }
     } else {
-        const R eps = R(1e-6);
-        const R t_loc = t[C - 1];
-        const R loc = softplus_<R>(t_loc);
-        R dsg[HLVAE_MAX_CLASS], q[HLVAE_MAX_CLASS];      // dsg_c = sigma'(u_c) = sigma(u_c) sigma(-u_c)
-        R cum = R(0), prev = R(0), tot = R(0), sneg_prev = R(1);
-        int vals = 0;
-#pragma unroll
-        for (int c = 0; c < HLVAE_MAX_CLASS; c++) {
-            if (c < C) {
-                R sg = R(1), qc, ds = R(0);
-                if (c < C - 1) {
-                    const R delta = clamp_<R>(softplus_<R>(t[c]), eps, R(1e20));
-                    cum += delta;
-                    const R e = Mth<R>::ex(loc - cum);                      // exp(-u_c)
-                    sg = Mth<R>::rcp(R(1) + e);
-                    const R sneg = (e > R(1e30)) ? R(1) : e * sg;           // sigma(-u_c), no cancellation
-                    ds = sg * sneg;
-                    if constexpr (sizeof(R) == 4) {
-                        qc = (c == 0) ? sg : sg * sneg_prev * (-Mth<R>::exm1(-delta));
-                    } else {
-                        qc = sg - prev;
-                    }
-                    sneg_prev = sneg;
-                } else {
-                    if constexpr (sizeof(R) == 4) qc = sneg_prev; else qc = sg - prev;
-                }
-                dsg[c] = ds;
-                q[c] = qc;
-                prev = sg;
-                tot += clamp_<R>(qc, eps, R(1));
-                vals += (int)x[c];
-            }
+        switch (C) {
+            case 2: ord_backward<R, XT, 2>(x_, t, 2, observed, g); break;
+            case 3: ord_backward<R, XT, 3>(x_, t, 3, observed, g); break;
+            case 4: ord_backward<R, XT, 4>(x_, t, 4, observed, g); break;
+            case 5: ord_backward<R, XT, 5>(x_, t, 5, observed, g); break;
+            case 6: ord_backward<R, XT, 6>(x_, t, 6, observed, g); break;
+            case 8: ord_backward<R, XT, 8>(x_, t, 8, observed, g); break;
+            case 10: ord_backward<R, XT, 10>(x_, t, 10, observed, g); break;
+            default: ord_backward<R, XT, HLVAE_MAX_CLASS>(x_, t, C, observed, g); break;
         }
-        if (!observed) vals = 1;
-        const int y = vals - 1;
-        // lp = log p_y - log tot ; the clamp passes gradient inside [eps, 1]
-        // q_c = sg_c - sg_{c-1}: d/dsg_c = gq_c - gq_{c+1}, c < C-1; u_c = cum_c - loc
-        const R itot = Mth<R>::rcp(tot);
-        R g_loc = R(0), run = R(0), gq_next = R(0);
-        {
-            const R qc = q[C - 1];
-            const R pc = clamp_<R>(qc, eps, R(1));
-            const R gp = ((C - 1 == y) ? Mth<R>::rcp(pc) : R(0)) - itot;
-            gq_next = (qc >= eps && qc <= R(1)) ? gp : R(0);
-        }
-#pragma unroll
-        for (int c = HLVAE_MAX_CLASS - 2; c >= 0; c--) {
-            if (c <= C - 2) {
-                const R qc = q[c];
-                const R pc = clamp_<R>(qc, eps, R(1));
-                const R gp = ((c == y) ? Mth<R>::rcp(pc) : R(0)) - itot;
-                const R gqc = (qc >= eps && qc <= R(1)) ? gp : R(0);
-                const R gu = (gqc - gq_next) * dsg[c];
-                gq_next = gqc;
-                g_loc -= gu;
-                run += gu;                                   // reverse cumulative sum -> d/d delta_c
-                const R tc = t[c];
-                const R sp = softplus_<R>(tc);
-                const R ga = (sp >= eps && sp <= R(1e20)) ? run * dsoftplus_<R>(tc) : R(0);
-                t[c] = g * ga;
-            }
-        }
-        t[C - 1] = g * g_loc * dsoftplus_<R>(t_loc);
     }
 }
 

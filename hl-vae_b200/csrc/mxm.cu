@@ -26,30 +26,46 @@ struct Mat {
 };
 
 // C = X Y (TRANSX = false) or X^T Y (TRANSX = true); all M x M.  C must not alias X or Y.
-template <bool TRANSX>
-__device__ void mm(Mat C, Mat X, Mat Y, int M) {
-    const int n = M * M;
-    for (int e0 = threadIdx.x; e0 < n; e0 += 4 * MX_THREADS) {
-        int e[4], i[4], j[4];
-        double a[4];
+// Each thread owns a 4 x 4 register tile whose rows / columns are interleaved with stride nt = ceil(M / 4)
+// (rows ic + a nt, columns jc + b nt): per k it loads 4 + 4 operands for 16 FMAs, consecutive threads read
+// consecutive columns of Y (conflict-free in shared memory, coalesced in the global workspace) and share
+// the X operands (broadcast).  `k_from_diag`: X^T Y with X, Y lower triangular - the sum may start at
+// max(ic, jc) because rows above the diagonal hold zeros.
+template <bool TRANSX, bool K_FROM_DIAG = false>
+__device__ void mm(Mat C, Mat X, Mat Y, int M, double* __restrict__ gout = nullptr) {
+    const int nt = (M + 3) >> 2;
+    for (int t = threadIdx.x; t < nt * nt; t += MX_THREADS) {
+        const int ic = t / nt, jc = t - ic * nt;
+        double acc[4][4];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            e[u] = e0 + u * MX_THREADS;
-            int ee = e[u] < n ? e[u] : 0;
-            i[u] = ee / M;
-            j[u] = ee % M;
-            a[u] = 0.0;
-        }
-        for (int k = 0; k < M; k++) {
+        for (int a = 0; a < 4; a++)
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                double x = TRANSX ? X(k, i[u]) : X(i[u], k);
-                a[u] = fma(x, Y(k, j[u]), a[u]);
+            for (int b2 = 0; b2 < 4; b2++) acc[a][b2] = 0.0;
+        bool iv[4], jv[4];
+#pragma unroll
+        for (int a = 0; a < 4; a++) { iv[a] = ic + a * nt < M; jv[a] = jc + a * nt < M; }
+        for (int k = K_FROM_DIAG ? max(ic, jc) : 0; k < M; k++) {
+            double xv[4], yv[4];
+#pragma unroll
+            for (int a = 0; a < 4; a++) {
+                const int i = ic + a * nt;
+                xv[a] = iv[a] ? (TRANSX ? X(k, i) : X(i, k)) : 0.0;
+                yv[a] = jv[a] ? Y(k, jc + a * nt) : 0.0;
             }
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int b2 = 0; b2 < 4; b2++) acc[a][b2] = fma(xv[a], yv[b2], acc[a][b2]);
         }
 #pragma unroll
-        for (int u = 0; u < 4; u++)
-            if (e[u] < n) C(i[u], j[u]) = a[u];
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int b2 = 0; b2 < 4; b2++)
+                if (iv[a] && jv[b2]) {
+                    const int i = ic + a * nt, j = jc + b2 * nt;
+                    C(i, j) = acc[a][b2];
+                    if (gout) gout[i * M + j] = acc[a][b2];
+                }
     }
     __syncthreads();
 }
@@ -102,17 +118,8 @@ __device__ void tri_inv(Mat B, Mat Lm, int M) {
     __syncthreads();
 }
 
-// C = B^T B for lower-triangular B (so the sum starts at max(i, j)); optional copy to global.
-__device__ void ata_lower(Mat C, Mat B, int M, double* __restrict__ gout) {
-    for (int e = threadIdx.x; e < M * M; e += MX_THREADS) {
-        int i = e / M, j = e % M;
-        double a = 0.0;
-        for (int k = max(i, j); k < M; k++) a = fma(B(k, i), B(k, j), a);
-        C(i, j) = a;
-        if (gout) gout[e] = a;
-    }
-    __syncthreads();
-}
+// C = B^T B for lower-triangular B (rows above the diagonal are zero); optional copy to global.
+__device__ void ata_lower(Mat C, Mat B, int M, double* __restrict__ gout) { mm<true, true>(C, B, B, M, gout); }
 
 __device__ void load(Mat A, const double* __restrict__ g, int M) {
     for (int e = threadIdx.x; e < M * M; e += MX_THREADS) A(e / M, e % M) = g[e];
