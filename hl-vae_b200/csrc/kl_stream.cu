@@ -384,7 +384,7 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
            const int32_t* __restrict__ tt_ptr, int n_subj, int subj_per_chunk, const TS* __restrict__ mu,
            int64_t ld_mu, const double* __restrict__ w, const double* __restrict__ G,
            const double* __restrict__ binv, int64_t tt_total, double* __restrict__ acc, const AccOff off,
-           TS* __restrict__ g_mu, double gscale, int32_t* __restrict__ status) {
+           TS* __restrict__ g_mu, TS* __restrict__ qdiag, double gscale, int32_t* __restrict__ status) {
     using SM = PanelSmem<MP, RP, G_SMEM>;
     constexpr int LD = SM::LD;
     constexpr int LDB = SM::LDB;
@@ -729,6 +729,15 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
         }
         __syncthreads();
 
+        // optional output: diag(W V^T)_r = V_r G V_r^T per row (validation.py:69-72 with G = W^-1)
+        if (qdiag) {
+            for (int r = warp; r < R; r += PN_THREADS / 32) {
+                double a = 0.0;
+                for (int m = lane; m < MP; m += 32) a = fma(Kb[r * LD + m], Vb[r * LD + m], a);
+                a = warp_sum(a);
+                if (lane == 0) qdiag[(int64_t)grow[r] * L + l] = (TS)a;
+            }
+        }
         // ---- P5a: dJ/dB_s (K0xz part) = -1/2 (rho rho^T + W V^T), symmetric: only the 8x8 tiles on or below
         // the diagonal that meet the block diagonal, on the FP64 tensor pipe, written over the dense panel Bp
         {
@@ -959,8 +968,8 @@ int launch_panel(const hlvae_kspec_t* spec0, const double* os0, const double* ls
                  const double* os1, const double* ls1, int L, int Q, int M, const double* x, int64_t ldx,
                  const double* z, const int32_t* row_idx, const int32_t* subj_ptr, const int32_t* tt_ptr, int n_subj,
                  int subj_per_chunk, const void* mu, int64_t ld_mu, const double* w, const double* G,
-                 const double* binv, int64_t tt_total, double* acc, const AccOff& off, void* g_mu, double gscale,
-                 int32_t* status, cudaStream_t st) {
+                 const double* binv, int64_t tt_total, double* acc, const AccOff& off, void* g_mu, void* qdiag,
+                 double gscale, int32_t* status, cudaStream_t st) {
     using SM = PanelSmem<MP, RP, G_SMEM>;
     auto kern = kl_panel_k<MP, RP, G_SMEM, NT, TS>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::bytes);
@@ -969,7 +978,7 @@ int launch_panel(const hlvae_kspec_t* spec0, const double* os0, const double* ls
     dim3 grid(n_chunks, L);
     kern<<<grid, NT, SM::bytes, st>>>(*spec0, os0, ls0, *spec1, os1, ls1, L, Q, M, x, ldx, z, row_idx,
                                               subj_ptr, tt_ptr, n_subj, subj_per_chunk, (const TS*)mu, ld_mu, w, G,
-                                              binv, tt_total, acc, off, (TS*)g_mu, gscale, status);
+                                              binv, tt_total, acc, off, (TS*)g_mu, (TS*)qdiag, gscale, status);
     HLVAE_CHECK_LAUNCH();
     return 0;
 }
@@ -980,11 +989,11 @@ int dispatch_panel(int M, const hlvae_kspec_t* spec0, const double* os0, const d
                    int64_t ldx, const double* z, const int32_t* row_idx, const int32_t* subj_ptr,
                    const int32_t* tt_ptr, int n_subj, int subj_per_chunk, const void* mu, int64_t ld_mu,
                    const double* w, const double* G, const double* binv, int64_t tt_total, double* acc,
-                   const AccOff& off, void* g_mu, double gscale, int32_t* status, cudaStream_t st) {
+                   const AccOff& off, void* g_mu, void* qdiag, double gscale, int32_t* status, cudaStream_t st) {
 #define HLVAE_PANEL(MP, RP, GS, NT)                                                                                   \
     return launch_panel<MP, RP, GS, NT, TS>(spec0, os0, ls0, spec1, os1, ls1, L, Q, M, x, ldx, z, row_idx, subj_ptr,     \
                                         tt_ptr, n_subj, subj_per_chunk, mu, ld_mu, w, G, binv, tt_total, acc, off,   \
-                                        g_mu, gscale, status, st)
+                                        g_mu, qdiag, gscale, status, st)
     // (a 256-thread, RP = 32, two-CTAs-per-SM shape was measured 9 % slower at M = 64, T = 20: one subject per
     // panel triples the per-panel fixed cost)
     if (M <= 32) { HLVAE_PANEL(32, 64, true, 512); }
@@ -1060,8 +1069,8 @@ extern "C" int hlvae_kl_panel(const hlvae_kspec_t* spec0, const double* os0, con
                               const double* x, int64_t ldx, const double* z, const int32_t* row_idx,
                               const int32_t* subj_ptr, const int32_t* tt_ptr, int n_subj, int subj_per_chunk,
                               const void* mu, int64_t ld_mu, int dtype, const double* w, const double* G,
-                              const double* binv, int64_t tt_total, double* acc, void* g_mu, double gscale,
-                              int32_t* status, void* stream) {
+                              const double* binv, int64_t tt_total, double* acc, void* g_mu, void* qdiag,
+                              double gscale, int32_t* status, void* stream) {
     if (!hlvae::spec_valid(spec0, Q) || !hlvae::spec_valid(spec1, Q) || L <= 0 || Q <= 0 || Q > HLVAE_MAX_Q ||
         M <= 0 || n_subj < 0 || subj_per_chunk <= 0 || !x || !z || !row_idx || !subj_ptr || !tt_ptr || !mu || !w ||
         !G || !binv || !acc || !g_mu)
@@ -1073,11 +1082,11 @@ extern "C" int hlvae_kl_panel(const hlvae_kspec_t* spec0, const double* os0, con
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == HLVAE_F64)
         return dispatch_panel<double>(M, spec0, os0, ls0, spec1, os1, ls1, L, Q, x, ldx, z, row_idx, subj_ptr, tt_ptr,
-                                      n_subj, subj_per_chunk, mu, ld_mu, w, G, binv, tt_total, acc, off, g_mu, gscale,
-                                      status, st);
+                                      n_subj, subj_per_chunk, mu, ld_mu, w, G, binv, tt_total, acc, off, g_mu, qdiag,
+                                      gscale, status, st);
     if (dtype == HLVAE_F32)
         return dispatch_panel<float>(M, spec0, os0, ls0, spec1, os1, ls1, L, Q, x, ldx, z, row_idx, subj_ptr, tt_ptr,
-                                     n_subj, subj_per_chunk, mu, ld_mu, w, G, binv, tt_total, acc, off, g_mu, gscale,
-                                     status, st);
+                                     n_subj, subj_per_chunk, mu, ld_mu, w, G, binv, tt_total, acc, off, g_mu, qdiag,
+                                     gscale, status, st);
     return HLVAE_E_ARG;
 }

@@ -116,7 +116,7 @@ class _KLD(torch.autograd.Function):
                       _lib.ptr(ls1c), L, Q, M, _lib.ptr(x_c), Q, _lib.ptr(z_c), _lib.ptr(layout.row_idx),
                       _lib.ptr(layout.subj_ptr), _lib.ptr(layout.tt_ptr), layout.n_subj, spc, _lib.ptr(mu_c), L,
                       dcode, _lib.ptr(w), _lib.ptr(G), _lib.ptr(binv), binv.shape[1], _lib.ptr(acc), _lib.ptr(g_mu),
-                      scale, _lib.ptr(status), st)
+                      None, scale, _lib.ptr(status), st)
         # ---- 3. data parallel: one all-reduce of every accumulator (S, p, scalars, replicated-parameter grads)
         if config.process_group is not None:
             torch.distributed.all_reduce(acc, group=config.process_group)

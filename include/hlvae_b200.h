@@ -119,6 +119,8 @@ int hlvae_subject_matvec(const hlvae_kspec_t* spec, const double* outputscale, c
  * (in doubles) of {S, p, gw, scal, gZ, gos0, gls0, gos1, gls1, total}.  g_mu, g_logv:
  * [N, L] contiguous in the storage `dtype`, overwritten for the rows listed in row_idx with
  * gscale * dJ/dmu and gscale * dJ/dlog_v (gscale = P / P_batch of elbo_functions.py:181,277).
+ * qdiag (nullable, [N, L], storage dtype): per row r the quadratic form (B^-1 K0xz)_r G (B^-1 K0xz)_r^T, the
+ * diagonal that validation.validation_dubo needs with G = W^-1 (validation.py:69-72).
  * ---------------------------------------------------------------------------------- */
 #define HLVAE_ACC_S 0
 #define HLVAE_ACC_P 1
@@ -147,7 +149,7 @@ int hlvae_kl_panel(const hlvae_kspec_t* spec0, const double* os0, const double* 
                    const int32_t* row_idx, const int32_t* subj_ptr, const int32_t* tt_ptr, int n_subj,
                    int subj_per_chunk, const void* mu, int64_t ld_mu, int dtype,
                    const double* w, const double* G, const double* binv, int64_t tt_total,
-                   double* acc, void* g_mu, double gscale, int32_t* status, void* stream);
+                   double* acc, void* g_mu, void* qdiag, double gscale, int32_t* status, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Replicated M x M stage (float64, one CTA per latent dimension, M <= 128).

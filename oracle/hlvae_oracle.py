@@ -309,6 +309,48 @@ def batch_predict(spec0, prm0, spec1, prm1, noise, prediction_x, test_x, mu, z, 
     return (first + second).squeeze(2).T                                      # :188
 
 
+def validation_dubo(spec0, prm0, spec1, prm1, noise, x, m, log_v, z, P: int, T: int, eps: float) -> torch.Tensor:
+    """Deviance upper bound of the validation pass, validation.validation_dubo (validation.py:16-76): fixed T,
+    summed over the latent dimensions.  m, log_v [N, L] (encoder means / log-variances of the validation rows);
+    `torch.solve(m_st, B_st)` (:59) is B_st^-1 m_st."""
+    L, M = z.shape[0], z.shape[1]
+    v = torch.exp(log_v)                                                      # :34
+    xs = x.reshape(P, T, -1)
+    K0xz = eval_additive(spec0, prm0, x, z)                                   # :38
+    K0zz = eval_additive(spec0, prm0, z, z) + eps * torch.eye(M, dtype=DT)    # :39
+    LK = torch.linalg.cholesky(K0zz)
+    iK = torch.cholesky_inverse(LK)                                           # :40-41
+    X4 = xs.unsqueeze(1).expand(P, L, T, xs.shape[-1])                        # :37 stacked_x_st
+    K0_all = eval_additive(spec0, prm0, X4, X4)                               # :42  [P, L, T, T]
+    B_all = eval_additive(spec1, prm1, X4, X4) + torch.eye(T, dtype=DT) * noise.reshape(1, L, 1, 1)   # :43
+    total = torch.zeros((), dtype=DT)
+    for l in range(L):                                                        # :48-75
+        K0_st, B_st = K0_all[:, l], B_all[:, l]
+        LB = torch.linalg.cholesky(B_st)
+        iB = torch.cholesky_inverse(LB)                                       # :44-45
+        m_st = m[:, l].reshape(P, T, 1)
+        v_st = v[:, l].reshape(P, T)
+        K_st = K0xz[l].reshape(P, T, M)
+        iB_K = iB @ K_st                                                      # :52
+        S = K0xz[l].T @ iB_K.reshape(P * T, M)                                # :53
+        W = K0zz[l] + S
+        W = (W + W.T) / 2                                                     # :54-55
+        LW = torch.linalg.cholesky(W)
+        logdet = -2 * torch.log(torch.diagonal(LK[l])).sum() + 2 * torch.log(torch.diagonal(LB, dim1=-2, dim2=-1)).sum() \
+            + 2 * torch.log(torch.diagonal(LW)).sum()                         # :57-60
+        iB_m = iB @ m_st                                                      # :61
+        qF1 = (m_st * iB_m).sum()
+        p = K0xz[l].T @ iB_m.reshape(P * T)
+        qF2 = (torch.linalg.solve_triangular(LW, p[:, None], upper=False) ** 2).sum()    # :64
+        tr = (iB * K0_st).sum() - (S * iK[l]).sum()                           # :66
+        logDetD = torch.log(v[:, l]).sum()
+        tr_iB_D = (torch.diagonal(iB, dim1=-2, dim2=-1) * v_st).sum()         # :68
+        Dh = (iB_K * torch.sqrt(v_st)[:, :, None]).reshape(P * T, M)
+        tr2 = torch.diagonal(torch.cholesky_solve(Dh.T @ Dh, LW)).sum()       # :69-71
+        total = total + 0.5 * ((tr_iB_D - tr2) + (qF1 - qF2) - P * T + logdet - logDetD + tr)   # :72-74
+    return total.reshape(1)
+
+
 # --------------------------------------------------------------------------------------
 # Heterogeneous likelihoods (HL_VAE/loglik.py) on the packed [N, E_x] / [N, P_theta] layout
 # --------------------------------------------------------------------------------------

@@ -330,12 +330,53 @@ def predict_case(name, kargs, L, M, n_subj, T, ragged, seed, n_test_subj=3, cont
     print(f"  {name}: N={N} N_test={test_x.shape[0]} worst rel diff {max(w):.2e}")
 
 
+def dubo_case(name, kargs, L, M, n_subj, T, seed, continuous_age=False):
+    """validation.validation_dubo (validation.py:16-76) of the unmodified reference, `torch.solve` shimmed."""
+    import validation as ref_validation                      # reference
+    rng = np.random.default_rng(seed)
+    gen = torch.Generator().manual_seed(seed)
+    x, lens = synth.covariates(n_subj, T, rng, continuous_age=continuous_age)
+    pool, _ = synth.covariates(40, T, rng, continuous_age=continuous_age)
+    z = synth.inducing_points(torch.cat([x, pool]), L, M, rng)
+    N = x.shape[0]
+    mu = torch.randn(N, L, generator=gen, dtype=DT)
+    lv = -3.0 * torch.rand(N, L, generator=gen, dtype=DT)
+    k0, k1, lik = ref_modules(L, kargs, gen)
+    k0.eval(); k1.eval(); lik.eval()
+    eps = 1e-6
+    had, old = hasattr(torch, "solve"), getattr(torch, "solve", None)
+    torch.solve = lambda B, A: (torch.linalg.solve(A, B), None)
+    try:
+        with torch.no_grad():
+            d = ref_validation.validation_dubo(L, k0, k1, lik, x, mu, lv, z, n_subj, T, eps)
+    finally:
+        if had:
+            torch.solve = old
+        else:
+            del torch.solve
+    spec0, spec1 = orc.compile_spec(**kargs)
+    ros0, rls0 = extract_params(k0)
+    ros1, rls1 = extract_params(k1)
+    noise = lik.noise_covar.noise.detach().reshape(-1).clone()
+    prm0, prm1 = orc.KernelParams(ros0.clone(), rls0.clone()), orc.KernelParams(ros1.clone(), rls1.clone())
+    with torch.no_grad():
+        od = orc.validation_dubo(spec0, prm0, spec1, prm1, noise, x, mu, lv, z, n_subj, T, eps)
+    w = check(name + ".dubo", od, d, 1e-8)
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), kargs=repr(kargs), L=L, M=M, T=T, n_subj=n_subj, eps=eps,
+                        x=x.numpy(), mu=mu.numpy(), log_v=lv.numpy(), z=z.numpy(), noise=noise.numpy(), ros0=ros0.numpy(),
+                        rls0=rls0.numpy(), ros1=ros1.numpy(), rls1=rls1.numpy(), dubo=d.numpy())
+    print(f"  {name}: N={N} dubo={float(d):.6e} rel diff {w:.2e}")
+
+
 def predict_cases():
     print("GP posterior-mean prediction: oracle vs unmodified reference (torch.solve shimmed)")
     predict_case("predict_default_ragged", synth.DEFAULT_KERNEL_ARGS, L=4, M=12, n_subj=6, T=8, ragged=True, seed=21)
     predict_case("predict_default_fixedT", synth.DEFAULT_KERNEL_ARGS, L=3, M=10, n_subj=5, T=6, ragged=False, seed=22)
     predict_case("predict_sweep_ragged", synth.SWEEP_KERNEL_ARGS, L=3, M=16, n_subj=7, T=10, ragged=True, seed=23,
                  continuous_age=True)
+    print("validation deviance upper bound: oracle vs unmodified reference (torch.solve shimmed)")
+    dubo_case("dubo_default", synth.DEFAULT_KERNEL_ARGS, L=4, M=12, n_subj=6, T=8, seed=31)
+    dubo_case("dubo_sweep", synth.SWEEP_KERNEL_ARGS, L=3, M=16, n_subj=5, T=10, seed=32, continuous_age=True)
 
 
 def main():

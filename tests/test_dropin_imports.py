@@ -32,6 +32,9 @@ import utils as RU, model_test
 from hlvae_b200 import predict as PR
 assert RU.batch_predict_varying_T is PR.batch_predict_varying_T and model_test.batch_predict is PR.batch_predict
 assert RU.HensmanDataLoader.__module__ == "_hlvae_reference_utils" and training.SubjectSampler is RU.SubjectSampler
+from hlvae_b200 import validation as VA
+assert validation.validation_dubo is VA.validation_dubo and validation.validate.__globals__["validation_dubo"] is VA.validation_dubo
+assert training.validate is validation.validate
 import HL_VAE.utils as U
 assert U.__file__.startswith(ref)                                                     # everything else: reference
 print("dropin ok")

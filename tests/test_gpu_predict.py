@@ -7,7 +7,7 @@ import pytest
 import torch
 
 import helpers as h
-from hlvae_b200 import predict, synth
+from hlvae_b200 import predict, synth, validation
 from oracle import hlvae_oracle as orc
 
 pytestmark = pytest.mark.gpu
@@ -67,3 +67,27 @@ def test_cpu_tensors_fail_loudly():
     with pytest.raises((RuntimeError, NotImplementedError)):
         predict.batch_predict_varying_T(2, None, None, None, torch.zeros(4, 6, dtype=DT), torch.zeros(2, 6, dtype=DT),
                                         torch.zeros(4, 2, dtype=DT), torch.zeros(2, 3, 6, dtype=DT), 2, 1e-6)
+
+
+@pytest.mark.parametrize("name", ["dubo_default", "dubo_sweep"])
+def test_dubo_golden(name, device):
+    """validation.validation_dubo (validation.py:16-76) against the unmodified reference's frozen output."""
+    g = h.load(name)
+    kargs, L, k0, k1, lik = _modules(g, device)
+    d = validation.validation_dubo(L, k0, k1, lik, h.t(g["x"], device), h.t(g["mu"], device), h.t(g["log_v"], device),
+                                   h.t(g["z"], device), int(g["n_subj"]), int(g["T"]), float(g["eps"]))
+    assert d.shape == (1,) and h.rel_err(d, g["dubo"]) < 1e-7
+
+
+def test_dubo_against_oracle_larger(device):
+    L, M, n_subj, T = 6, 64, 50, 20
+    inp = h.make_kl_inputs(L, M, n_subj, T, seed=611, ragged=False)
+    k0, k1, lik = h.build_product_kernels(inp["kargs"], L, device, inp["ros0"], inp["rls0"], inp["ros1"], inp["rls1"],
+                                          inp["noise"])
+    spec0, spec1 = orc.compile_spec(**inp["kargs"])
+    prm0, prm1 = orc.KernelParams(inp["ros0"], inp["rls0"]), orc.KernelParams(inp["ros1"], inp["rls1"])
+    ref = orc.validation_dubo(spec0, prm0, spec1, prm1, inp["noise"], inp["x"], inp["mu"], inp["lv"], inp["z"], n_subj, T,
+                              1e-6)
+    got = validation.validation_dubo(L, k0.eval(), k1.eval(), lik.eval(), inp["x"].to(device), inp["mu"].to(device),
+                                     inp["lv"].to(device), inp["z"].to(device), n_subj, T, 1e-6)
+    assert h.rel_err(got, ref) < 1e-6

@@ -83,3 +83,17 @@ def test_oracle_predict_matches_reference_goldens(name):
     zp = orc.batch_predict(spec0, prm0, spec1, prm1, h.t(g["noise"]), x, h.t(g["test_x"]), h.t(g["mu"]), h.t(g["z"]),
                            orc.split_subjects_by_id(x, kargs["id_covariate"]), kargs["id_covariate"], float(g["eps"]))
     assert h.rel_err(zp, g["Z_pred"]) < 1e-9
+
+
+@pytest.mark.parametrize("name", ["dubo_default", "dubo_sweep"])
+def test_oracle_dubo_matches_reference_goldens(name):
+    """validation.validation_dubo (validation.py:16-76): oracle restatement vs the unmodified reference."""
+    import ast
+    g = h.load(name)
+    kargs = ast.literal_eval(str(g["kargs"]))
+    spec0, spec1 = orc.compile_spec(**kargs)
+    prm0 = orc.KernelParams(h.t(g["ros0"]), h.t(g["rls0"]))
+    prm1 = orc.KernelParams(h.t(g["ros1"]), h.t(g["rls1"]))
+    d = orc.validation_dubo(spec0, prm0, spec1, prm1, h.t(g["noise"]), h.t(g["x"]), h.t(g["mu"]), h.t(g["log_v"]),
+                            h.t(g["z"]), int(g["n_subj"]), int(g["T"]), float(g["eps"]))
+    assert h.rel_err(d, g["dubo"]) < 1e-9
