@@ -104,6 +104,11 @@ def test_natural_gradient_step_matches_oracle(device):
                       inp["rls0"], inp["ros1"], inp["rls1"], inp["noise"], 200, 6, 200 * 8, 1e-6)
     m3, H3 = orc.natural_gradient_update(inp["m"], inp["H"], ref["grad_m"], ref["grad_H"], 0.01)
     assert h.rel_err(m2, m3) < 1e-6 and h.rel_err(H2, H3) < 1e-6
+    # the update normally reuses H^-1 of the KL call that produced grad_H; plain tensors (no such record) make it
+    # factorise H itself (training.py:131-132) - same result
+    m4, H4 = elbo.natural_gradient_update(inp["m"].to(device), inp["H"].to(device), got["grad_m"].clone(),
+                                          got["grad_H"].clone(), 0.01)
+    assert h.rel_err(m4, m2) < 1e-9 and h.rel_err(H4, H2) < 1e-9
 
 
 @pytest.mark.parametrize("M", [32, 64, 128])
