@@ -283,6 +283,17 @@ def run_gpu(args):
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    if world > 1:
+        # keep this rank's threads (and therefore its pinned host buffers, first-touch) on the NUMA node next to
+        # its GPU: with 8 ranks the e2e host->device copies otherwise cross sockets
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[local]) if vis and vis.split(",")[0].isdigit() else local
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(idx))
+        except Exception as e:
+            print(f"[bench] rank {rank}: NUMA affinity not set ({e!r})", file=sys.stderr, flush=True)
     import __graft_entry__ as g
     if rank == 0:
         g.build()
