@@ -26,6 +26,7 @@ namespace {
 constexpr int LL_THREADS = 128;                          // threads per CTA = max variables per tile
 constexpr int LL_ROWS = 8;                               // rows staged per batch
 constexpr int LL_CAPM = LL_THREADS + 16;                  // staged mask / upstream-gradient row (with alignment shift)
+static_assert(4 * LL_ROWS <= 32, "one warp issues every bulk copy of a row batch");
 constexpr int LL_STAGES = 1;                             // 2: prefetch the next row batch while this one is evaluated (measured: no gain,
                                                          // the resident CTAs of an SM already cover each other's loads)
 constexpr double LOG_2PI = 1.8378770664093454835606594728112;
@@ -394,16 +395,18 @@ __device__ __forceinline__ int tma_row_bytes(const T* src, int span, unsigned& b
     return shift;
 }
 
-// Whole 16-byte chunks of a staged row go out as one bulk store (single thread); the partial chunks at the
-// two ends are written element-wise by the first threads of the CTA.
+// Whole 16-byte chunks of a staged row go out as one bulk store issued by thread `issuer` (one row per thread,
+// so the rows of a batch are issued in parallel); the partial chunks at the two ends are written element-wise
+// by the first threads of the CTA.
 template <typename T>
-__device__ __forceinline__ void tma_unstage_row(T* __restrict__ dst, const T* __restrict__ src, int shift, int span, int tid) {
+__device__ __forceinline__ void tma_unstage_row(T* __restrict__ dst, const T* __restrict__ src, int shift, int span, int tid,
+                                                int issuer) {
     constexpr int E = 16 / (int)sizeof(T);
     const int i0 = shift > 0 ? 1 : 0;                         // first whole chunk
     const int i1 = (shift + span) / E;                        // one past the last whole chunk
     const int head = min(span, E * i0 - shift);               // elements before the first whole chunk
     const int tail0 = max(head, E * i1 - shift);              // first element after the last whole chunk
-    if (tid == 0 && i1 > i0) bulk_s2g(dst + (E * i0 - shift), src + E * i0, (unsigned)((i1 - i0) * 16));
+    if (tid == issuer && i1 > i0) bulk_s2g(dst + (E * i0 - shift), src + E * i0, (unsigned)((i1 - i0) * 16));
     if (tid < head) dst[tid] = src[shift + tid];
     if (tid >= E && tid - E < span - tail0) dst[tail0 + tid - E] = src[shift + tail0 + tid - E];
 }
@@ -498,24 +501,36 @@ loglik_fwd_k(int64_t N, int D, int tile_vars, int cap, int64_t ld_data, int64_t 
 
     auto prefetch = [&](int64_t n0, int stg) {   // put one row batch in flight (nothing if n0 is past the end)
         if (n0 < N && use_tma) {
-            if (tid == 0) {
+            if (tid < 32) {        // warp 0: lane = (array, row); every lane issues its own bulk copy
                 R* sT = reinterpret_cast<R*>(ll_smem + stg * stage_bytes);
                 TD* sX = reinterpret_cast<TD*>(sT + LL_ROWS * capt);
                 TM* sK = reinterpret_cast<TM*>(sX + LL_ROWS * capx);
                 const int nr = (int)min((int64_t)LL_ROWS, N - n0);
-                unsigned bt[LL_ROWS], bx[LL_ROWS], bm[LL_ROWS], total = 0;
-                for (int r = 0; r < nr; r++) {
-                    sShiftT[stg][r] = tma_row_bytes<TS>(theta + (n0 + r) * ld_theta + ps0, span_p, bt[r]);
-                    sShift[stg][r] = tma_row_bytes<TD>(data + (n0 + r) * ld_data + xs0, span_x, bx[r]);
-                    sShiftM[stg][r] = tma_row_bytes<TM>(mask + (n0 + r) * D + d0, span_m, bm[r]);
-                    total += bt[r] + bx[r] + bm[r];
+                const int r = tid % LL_ROWS, arr = tid / LL_ROWS;
+                const bool job = r < nr && arr < 3;
+                unsigned bytes = 0;
+                int shift = 0;
+                const void* src = nullptr;
+                void* dst = nullptr;
+                if (job) {
+                    if (arr == 0) {
+                        const TS* p_ = theta + (n0 + r) * ld_theta + ps0;
+                        shift = tma_row_bytes<TS>(p_, span_p, bytes);
+                        src = p_ - shift; dst = sT + r * capt; sShiftT[stg][r] = shift;
+                    } else if (arr == 1) {
+                        const TD* p_ = data + (n0 + r) * ld_data + xs0;
+                        shift = tma_row_bytes<TD>(p_, span_x, bytes);
+                        src = p_ - shift; dst = sX + r * capx; sShift[stg][r] = shift;
+                    } else {
+                        const TM* p_ = mask + (n0 + r) * D + d0;
+                        shift = tma_row_bytes<TM>(p_, span_m, bytes);
+                        src = p_ - shift; dst = sK + r * LL_CAPM; sShiftM[stg][r] = shift;
+                    }
                 }
-                mbar_expect_tx(&mbar[stg], total);
-                for (int r = 0; r < nr; r++) {
-                    bulk_g2s(sT + r * capt, theta + (n0 + r) * ld_theta + ps0 - sShiftT[stg][r], bt[r], &mbar[stg]);
-                    bulk_g2s(sX + r * capx, data + (n0 + r) * ld_data + xs0 - sShift[stg][r], bx[r], &mbar[stg]);
-                    bulk_g2s(sK + r * LL_CAPM, mask + (n0 + r) * D + d0 - sShiftM[stg][r], bm[r], &mbar[stg]);
-                }
+                const unsigned total = __reduce_add_sync(0xffffffffu, bytes);
+                if (tid == 0) mbar_expect_tx(&mbar[stg], total);
+                __syncwarp();
+                if (job) bulk_g2s(dst, src, bytes, &mbar[stg]);
             }
         } else if (n0 < N) {
             R* sT = reinterpret_cast<R*>(ll_smem + stg * stage_bytes);
@@ -585,8 +600,8 @@ loglik_fwd_k(int64_t N, int D, int tile_vars, int cap, int64_t ld_data, int64_t 
         if (params) {
             if (use_tma) {
                 for (int r = 0; r < nr; r++)
-                    tma_unstage_row<TS>(params + (n0 + r) * ld_theta + ps0, sT + r * capt, sShiftT[stg][r], span_p, tid);
-                if (tid == 0) {
+                    tma_unstage_row<TS>(params + (n0 + r) * ld_theta + ps0, sT + r * capt, sShiftT[stg][r], span_p, tid, r);
+                if (tid < nr) {                  // thread r issued row r
                     bulk_commit();
                     bulk_wait_read();            // the staged rows have been read; the stage may be refilled
                 }
@@ -773,28 +788,42 @@ loglik_bwd_k(int64_t N, int D, int tile_vars, int cap, int64_t ld_data, int64_t 
 
     auto prefetch = [&](int64_t n0, int stg) {
         if (n0 < N && use_tma) {
-            if (tid == 0) {
+            if (tid < 32) {        // warp 0: lane = (array, row); every lane issues its own bulk copy
                 R* sT = reinterpret_cast<R*>(ll_smem + stg * stage_bytes);
                 R* sG = sT + LL_ROWS * capt;
                 TD* sX = reinterpret_cast<TD*>(sG + LL_ROWS * LL_CAPM);
                 TM* sK = reinterpret_cast<TM*>(sX + LL_ROWS * capx);
                 const int nr = (int)min((int64_t)LL_ROWS, N - n0);
-                unsigned bt[LL_ROWS], bx[LL_ROWS], bm[LL_ROWS], bg[LL_ROWS], total = 0;
-                for (int r = 0; r < nr; r++) {
-                    sShiftT[stg][r] = tma_row_bytes<TS>(theta + (n0 + r) * ld_theta + ps0, span_p, bt[r]);
-                    sShift[stg][r] = tma_row_bytes<TD>(data + (n0 + r) * ld_data + xs0, span_x, bx[r]);
-                    sShiftM[stg][r] = tma_row_bytes<TM>(mask + (n0 + r) * D + d0, span_m, bm[r]);
-                    bg[r] = 0;
-                    sShiftG[stg][r] = g_lp ? tma_row_bytes<TS>(g_lp + (n0 + r) * D + d0, span_m, bg[r]) : 0;
-                    total += bt[r] + bx[r] + bm[r] + bg[r];
+                const int r = tid % LL_ROWS, arr = tid / LL_ROWS;
+                const bool job = r < nr && (arr < 3 || (arr == 3 && g_lp != nullptr));
+                unsigned bytes = 0;
+                int shift = 0;
+                const void* src = nullptr;
+                void* dst = nullptr;
+                if (r < nr && arr == 3 && !g_lp) sShiftG[stg][r] = 0;
+                if (job) {
+                    if (arr == 0) {
+                        const TS* p_ = theta + (n0 + r) * ld_theta + ps0;
+                        shift = tma_row_bytes<TS>(p_, span_p, bytes);
+                        src = p_ - shift; dst = sT + r * capt; sShiftT[stg][r] = shift;
+                    } else if (arr == 1) {
+                        const TD* p_ = data + (n0 + r) * ld_data + xs0;
+                        shift = tma_row_bytes<TD>(p_, span_x, bytes);
+                        src = p_ - shift; dst = sX + r * capx; sShift[stg][r] = shift;
+                    } else if (arr == 2) {
+                        const TM* p_ = mask + (n0 + r) * D + d0;
+                        shift = tma_row_bytes<TM>(p_, span_m, bytes);
+                        src = p_ - shift; dst = sK + r * LL_CAPM; sShiftM[stg][r] = shift;
+                    } else {
+                        const TS* p_ = g_lp + (n0 + r) * D + d0;
+                        shift = tma_row_bytes<TS>(p_, span_m, bytes);
+                        src = p_ - shift; dst = sG + r * LL_CAPM; sShiftG[stg][r] = shift;
+                    }
                 }
-                mbar_expect_tx(&mbar[stg], total);
-                for (int r = 0; r < nr; r++) {
-                    bulk_g2s(sT + r * capt, theta + (n0 + r) * ld_theta + ps0 - sShiftT[stg][r], bt[r], &mbar[stg]);
-                    bulk_g2s(sX + r * capx, data + (n0 + r) * ld_data + xs0 - sShift[stg][r], bx[r], &mbar[stg]);
-                    bulk_g2s(sK + r * LL_CAPM, mask + (n0 + r) * D + d0 - sShiftM[stg][r], bm[r], &mbar[stg]);
-                    if (g_lp) bulk_g2s(sG + r * LL_CAPM, g_lp + (n0 + r) * D + d0 - sShiftG[stg][r], bg[r], &mbar[stg]);
-                }
+                const unsigned total = __reduce_add_sync(0xffffffffu, bytes);
+                if (tid == 0) mbar_expect_tx(&mbar[stg], total);
+                __syncwarp();
+                if (job) bulk_g2s(dst, src, bytes, &mbar[stg]);
             }
         } else if (n0 < N) {
             R* sT = reinterpret_cast<R*>(ll_smem + stg * stage_bytes);
@@ -855,8 +884,8 @@ loglik_bwd_k(int64_t N, int D, int tile_vars, int cap, int64_t ld_data, int64_t 
         __syncthreads();
         if (use_tma) {
             for (int r = 0; r < nr; r++)
-                tma_unstage_row<TS>(g_theta + (n0 + r) * ld_theta + ps0, sT + r * capt, sShiftT[stg][r], span_p, tid);
-            if (tid == 0) {
+                tma_unstage_row<TS>(g_theta + (n0 + r) * ld_theta + ps0, sT + r * capt, sShiftT[stg][r], span_p, tid, r);
+            if (tid < nr) {
                 bulk_commit();
                 bulk_wait_read();
             }
