@@ -57,7 +57,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--eager", action="store_true", help="time eager launches instead of CUDA-graph replay")
     ap.add_argument("--no-overlap", action="store_true", help="single stream: no likelihood / KL overlap")
-    ap.add_argument("--workload", default="elbo", choices=["elbo", "predict", "sweep"],
+    ap.add_argument("--workload", default="elbo", choices=["elbo", "predict", "sweep", "theta"],
                     help="elbo: the BASELINE.json metric (default); predict: SURVEY 8(f) row 1, GP posterior-mean "
                          "prediction (utils.batch_predict_varying_T), its own JSON line")
     return ap.parse_args()
@@ -574,6 +574,98 @@ def run_predict(args):
     print(json.dumps(line), flush=True)
 
 
+def run_theta(args):
+    """HLVAE.theta_estimation (HLVAE.py:416-453) at the configs[1] batch: 16000 rows, D4
+    (324 real + 972 cat x5 -> P_theta = 5184), y_dim = 5, convolutional layout (y_grouped = permuted view of
+    [N, y_dim, D]), float32 storage, uint8 mask.  One forward + backward = one "step"; inputs (y 415 MB, upstream
+    gradient 332 MB) exceed the 126 MB L2."""
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    import __graft_entry__ as g
+    g.build()
+    from hlvae_b200 import _lib, synth, theta as th
+    from oracle import hlvae_oracle as orc
+    hbm_peak, _ = measured_peaks()
+    types = synth.HEALTHMNIST_D4_TYPES
+    N, Y, D = args.subjects * T, 5, len(types)
+    gen = torch.Generator(device=dev).manual_seed(0)
+    lay = th.HeadLayout(types, True, dev)
+    P = lay.P
+    y = torch.randn(N, Y, D, generator=gen, device=dev, dtype=torch.float32).permute(0, 2, 1)
+    mask = (torch.rand(N, D, generator=gen, device=dev) < 0.75).to(torch.uint8)
+    W = torch.randn(P, Y, generator=gen, device=dev, dtype=torch.float64) * 0.3
+    b = torch.randn(P, generator=gen, device=dev, dtype=torch.float64) * 0.3
+    g_up = torch.randn(N, P, generator=gen, device=dev, dtype=torch.float32)
+    yq = y.detach().requires_grad_(True)
+    Wq, bq = W.requires_grad_(True), b.requires_grad_(True)
+    _lib.PROFILE = []
+
+    def step():
+        yq.grad = Wq.grad = bq.grad = None
+        theta = th.theta_heads(lay, yq, mask, Wq, bq)
+        theta.backward(g_up)
+        return theta
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    _lib.PROFILE.clear()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    tc0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = step()
+    enqueue_ms = (time.perf_counter() - tc0) * 1e3 / args.steps
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    per = {}
+    for name, a, c in _lib.PROFILE:
+        per.setdefault(name, []).append(a.elapsed_time(c))
+    _lib.PROFILE = None
+    bytes_fwd = N * (4 * D * Y + 4 * P)
+    bytes_bwd = N * (4 * D * Y + D + 4 * P + 4 * D * Y)
+    kern = {}
+    for name, nbytes in (("hlvae_theta_fwd", bytes_fwd), ("hlvae_theta_bwd", bytes_bwd)):
+        t_ms = float(np.mean(per[name]))
+        kern[name] = dict(ms_avg=t_ms, bound="hbm", achieved=nbytes / t_ms / 1e6, peak=hbm_peak, unit="GB/s",
+                          frac=nbytes / t_ms / 1e6 / hbm_peak, algorithmic_bytes=nbytes)
+    # CPU arm: the oracle restatement of the reference method on a bounded row sample, scaled in rows
+    ns = 400
+    cg = torch.Generator().manual_seed(0)
+    ti = orc.types_info_from_layout(types, conv=True)
+    heads = []
+    for i, tpl in enumerate(ti['set_of_types']):
+        n, C = int((ti['data_types_indexes'] == i).sum()), int(tpl[1])
+        r = lambda *s_: (torch.randn(*s_, generator=cg, dtype=torch.float64) * 0.3).requires_grad_(True)
+        heads.append(dict(weight=r(n, Y, C - 1), bias=r(n, C - 1)) if tpl[0] == 'cat' else
+                     dict(weight_mean=r(n, Y, 1), bias_mean=r(n, 1)))
+    yc = torch.randn(ns, D, Y, generator=cg, dtype=torch.float64).requires_grad_(True)
+    mc = (torch.rand(ns, D, generator=cg) < 0.75).double()
+    gc = torch.randn(ns, P, generator=cg, dtype=torch.float64)
+    torch.set_num_threads(os.cpu_count() or 1)
+    orc.theta_estimation(types, heads, yc, mc, conv=True).backward(gc)
+    t0 = time.perf_counter()
+    reps_c = 3
+    for _ in range(reps_c):
+        orc.theta_estimation(types, heads, yc, mc, conv=True).backward(gc)
+    cpu_s = (time.perf_counter() - t0) / reps_c * (N / ns)
+    line = dict(metric="observation-head (theta_estimation) fwd+bwd passes/sec", value=1e3 / ms, unit="steps/s", n_gpus=1,
+                steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms, higher_is_better=True, dtype="f32",
+                data="synthetic",
+                config=dict(workload=f"SURVEY 8(f).2: {N} rows, D4 (324 real + 972 cat x5), y_dim={Y}, conv layout, "
+                                     "float32 storage, uint8 mask", l2="inputs larger than L2 (y 415 MB + upstream 332 MB)"),
+                gpu_launches=2 * args.steps, kernels=kern, host_enqueue_ms_per_step=enqueue_ms,
+                roofline=dict(kernel="hlvae_theta_bwd", bound="hbm", achieved=kern["hlvae_theta_bwd"]["achieved"],
+                              peak=hbm_peak, unit="GB/s", frac=kern["hlvae_theta_bwd"]["frac"], traffic=None),
+                cpu_baseline=dict(value=1.0 / cpu_s, unit="steps/s", cores=torch.get_num_threads(), kind="port",
+                                  sample=f"{ns} rows of the same workload, float64 oracle port, scaled x{N / ns:.0f} in rows"),
+                checksum=float(out.double().abs().sum()))
+    print(json.dumps(line), flush=True)
+
+
 def run_sweep(args):
     """BASELINE.json configs[2] and configs[3] as tables (not the headline line):
     (a) additive-kernel sweep - SE(time) + CA(id) + SE(age) x CA(sex), M in {32, 64, 128}, minibatch 4k / 16k / 64k
@@ -685,6 +777,9 @@ def main():
     args = parse()
     if args.workload == "predict" and args.impl != "reference":
         run_predict(args)
+        return
+    if args.workload == "theta" and args.impl != "reference":
+        run_theta(args)
         return
     if args.workload == "sweep" and args.impl != "reference":
         run_sweep(args)

@@ -14,7 +14,8 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libhlvae_b200.so")
 
-MAX_COMPS, MAX_DISC, MAX_Q, TMAX, MAX_CLASS = 8, 3, 8, 32, 16
+MAX_COMPS, MAX_DISC, MAX_Q, TMAX, MAX_CLASS, MAX_Y = 8, 3, 8, 32, 16, 16
+HEAD_AFFINE, HEAD_SIGMOID, HEAD_ZERO, HEAD_BIAS = 0, 1, 2, 3
 F32, F64, U8 = 0, 1, 2
 KIND_CAT, KIND_BIN = 1, 2
 VAR_KINDS = {"real": 0, "pos": 1, "count": 2, "cat": 3, "ordinal": 4}
@@ -54,6 +55,8 @@ _SIGS = {
     "hlvae_loglik_bwd": ([_L, _I, _L, _L, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P], _I),
     "hlvae_statistics": ([_L, _I, _L, _P, _P, _P, _P, _P, _I, _P, _P, _P], _I),
     "hlvae_discrete_transform": ([_L, _I, _L, _P, _P, _P, _P, _I, _P, _P], _I),
+    "hlvae_theta_fwd": ([_L, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _L, _L, _L, _I, _P, _L, _P], _I),
+    "hlvae_theta_bwd": ([_L, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _L, _L, _L, _I, _P, _I, _P, _L, _P, _P, _P, _P], _I),
 }
 EXPORTED = tuple(_SIGS)
 

@@ -1,0 +1,301 @@
+// Per-variable observation heads: HLVAE.theta_estimation (HLVAE.py:416-453) over the Observation_*
+// modules (HLVAE.py:11-89) as ONE streaming pass.  The reference evaluates every head twice (observed and,
+// under no_grad, missing entries), multiplies by masks and scatters through boolean indices; for 0/1 masks that
+// is  theta[n, p] = act_p(bias[p] + sum_k weight[p, k] y[n, var(p), k])  in the forward direction, with the
+// gradient flowing only through observed (mask = 1) entries.
+//
+// CTA = tile of whole variables covering <= 256 theta columns x a stripe of rows, thread = theta column with
+// its weights in registers.  y is read straight from global memory: the lanes of a warp own the columns of
+// adjacent variables, so for either layout of y (conv: [N, Y, D] viewed as [N, D, Y]; dense: [N, D, Y]) a warp's
+// loads fall into one or two sectors per k and the y_dim loads of RB rows are all in flight together - no
+// staging, no barrier; theta rows are written coalesced (thread = column).  Backward: thread = column
+// accumulates d/d{weight, bias} in float64 registers over the whole stripe (one atomic per column and CTA at the
+// end) and leaves its masked upstream gradient in (double-buffered) shared memory; after ONE barrier per row
+// batch, thread = (variable, k) forms d/dy from the <= 16 columns of the variable, decoded so that consecutive
+// threads write consecutive addresses of the caller's layout.  HBM-bound: y and theta cross once.
+#include "common.cuh"
+
+namespace {
+
+constexpr int TH_THREADS = 256;   // = max theta columns and max variables per tile
+// rows in flight per thread: about 40 registers of y values (y_dim = 5: 8 rows in float32, 4 in float64)
+template <typename TS, int YP, bool BWD = false>
+struct ThRows {
+    static constexpr int raw = (BWD ? 80 : 160) / (YP * (int)sizeof(TS));
+    static constexpr int value = raw < 1 ? 1 : (raw > 8 ? 8 : raw);
+};
+
+template <typename TS>
+__device__ __forceinline__ TS sigmoid_t(TS z);
+template <>
+__device__ __forceinline__ double sigmoid_t<double>(double z) { return 1.0 / (1.0 + exp(-z)); }
+template <>
+__device__ __forceinline__ float sigmoid_t<float>(float z) { return 1.0f / (1.0f + expf(-z)); }
+
+struct ThTile {
+    int d0, nv, p0, ncols;
+    int64_t r_begin, r_end;
+};
+
+__device__ __forceinline__ ThTile th_tile(const int32_t* __restrict__ tile_var, const int32_t* __restrict__ var_pcol,
+                                          int64_t N, int TH_RB) {
+    ThTile t;
+    t.d0 = tile_var[blockIdx.x];
+    const int d1 = tile_var[blockIdx.x + 1];
+    t.nv = d1 - t.d0;
+    t.p0 = var_pcol[t.d0];
+    t.ncols = var_pcol[d1] - t.p0;
+    const int64_t batches = (N + TH_RB - 1) / TH_RB;
+    const int64_t per = (batches + gridDim.y - 1) / gridDim.y;
+    t.r_begin = (int64_t)blockIdx.y * per * TH_RB;
+    t.r_end = t.r_begin + per * TH_RB;
+    if (t.r_end > N) t.r_end = N;
+    return t;
+}
+
+template <typename TS, int YP>
+__global__ void __launch_bounds__(TH_THREADS, 3)
+theta_fwd_k(int64_t N, int Y, const int32_t* __restrict__ col_var, const int32_t* __restrict__ col_mode,
+            const int32_t* __restrict__ var_pcol, const int32_t* __restrict__ tile_var,
+            const double* __restrict__ weight, const double* __restrict__ bias, const TS* __restrict__ y, int64_t sn,
+            int64_t sd, int64_t sk, TS* __restrict__ theta, int64_t ld_theta) {
+    constexpr int TH_RB = ThRows<TS, YP>::value;
+    const int tid = threadIdx.x;
+    const ThTile t = th_tile(tile_var, var_pcol, N, TH_RB);
+    if (tid >= t.ncols || t.r_begin >= t.r_end) return;
+    const int p = t.p0 + tid;
+    const int mode = col_mode[p];
+    const bool ydep = (mode == HLVAE_HEAD_AFFINE || mode == HLVAE_HEAD_SIGMOID);
+    const TS b = (mode == HLVAE_HEAD_ZERO) ? (TS)0 : (TS)bias[p];
+    TS wk[YP];
+#pragma unroll
+    for (int k = 0; k < YP; k++) wk[k] = (ydep && k < Y) ? (TS)weight[(int64_t)p * Y + k] : (TS)0;
+    const TS* yv = y + (int64_t)col_var[p] * sd;
+    TS* out = theta + p;
+    for (int64_t n0 = t.r_begin; n0 < t.r_end; n0 += TH_RB) {
+        TS yk[TH_RB][YP];
+#pragma unroll
+        for (int r = 0; r < TH_RB; r++) {
+            const int64_t n = (n0 + r < t.r_end) ? n0 + r : t.r_end - 1;      // clamped: the tail re-reads the last row
+#pragma unroll
+            for (int k = 0; k < YP; k++) yk[r][k] = (ydep && k < Y) ? yv[n * sn + k * sk] : (TS)0;
+        }
+#pragma unroll
+        for (int r = 0; r < TH_RB; r++) {
+            TS z = b;
+#pragma unroll
+            for (int k = 0; k < YP; k++) z = fma(wk[k], yk[r][k], z);
+            if (mode == HLVAE_HEAD_SIGMOID) z = sigmoid_t<TS>(z);
+            if (n0 + r < t.r_end) out[(n0 + r) * ld_theta] = z;
+        }
+    }
+}
+
+template <typename TS, typename TM, int YP>
+__global__ void __launch_bounds__(TH_THREADS, 3)
+theta_bwd_k(int64_t N, int D, int Y, const int32_t* __restrict__ col_var, const int32_t* __restrict__ col_mode,
+            const int32_t* __restrict__ var_pcol, const int32_t* __restrict__ tile_var,
+            const double* __restrict__ weight, const double* __restrict__ bias, const TS* __restrict__ y, int64_t sn,
+            int64_t sd, int64_t sk, const TM* __restrict__ mask, const TS* __restrict__ g_theta, int64_t ld_theta,
+            TS* __restrict__ g_y, double* __restrict__ g_weight, double* __restrict__ g_bias) {
+    constexpr int TH_RB = ThRows<TS, YP, true>::value;
+    extern __shared__ __align__(16) unsigned char th_smem[];
+    TS* gs = reinterpret_cast<TS*>(th_smem);                  // [2][RB][256] masked upstream gradient per column
+    TS* Ws = gs + 2 * TH_RB * TH_THREADS;                     // [256][Y] weights of the tile's y-dependent columns
+    int* vlp = reinterpret_cast<int*>(Ws + (size_t)TH_THREADS * Y);   // [256] first tile-local column of a variable
+    int* vnc = vlp + TH_THREADS;                              // [256] its column count
+    const int tid = threadIdx.x;
+    const ThTile t = th_tile(tile_var, var_pcol, N, TH_RB);
+    if (t.r_begin >= t.r_end) return;
+
+    const bool live = tid < t.ncols;
+    const int p = t.p0 + (live ? tid : 0);
+    const int mode = live ? col_mode[p] : HLVAE_HEAD_ZERO;
+    const bool ydep = (mode == HLVAE_HEAD_AFFINE || mode == HLVAE_HEAD_SIGMOID);
+    const int dvar = col_var[p];
+    const TS b = (TS)bias[p];
+    TS wk[YP];
+    double gw[YP], gb = 0.0;
+#pragma unroll
+    for (int k = 0; k < YP; k++) {
+        wk[k] = (ydep && k < Y) ? (TS)weight[(int64_t)p * Y + k] : (TS)0;
+        gw[k] = 0.0;
+    }
+    for (int k = 0; k < Y; k++) Ws[tid * Y + k] = ydep ? (TS)weight[(int64_t)p * Y + k] : (TS)0;
+    if (tid < t.nv) {
+        vlp[tid] = var_pcol[t.d0 + tid] - t.p0;
+        vnc[tid] = var_pcol[t.d0 + tid + 1] - var_pcol[t.d0 + tid];
+    }
+    const TS* yv = y + (int64_t)dvar * sd;
+    const TM* mv = mask + dvar;
+    const TS* gin = g_theta + p;
+    // (variable, k) pairs of the d/dy phase, consecutive threads -> consecutive addresses of the caller's layout
+    const bool v_fastest = sd < sk;
+    const int npairs = t.nv * Y;
+    int buf = 0;
+    for (int64_t n0 = t.r_begin; n0 < t.r_end; n0 += TH_RB, buf ^= 1) {
+        TS* gsb = gs + buf * TH_RB * TH_THREADS;
+        // ---- thread = column: masked upstream gradient, d/d{weight, bias}
+        if (live) {
+            TS yk[TH_RB][YP], g[TH_RB];
+#pragma unroll
+            for (int r = 0; r < TH_RB; r++) {
+                const bool in = n0 + r < t.r_end;
+                const int64_t n = in ? n0 + r : t.r_end - 1;
+                const bool obs = in && mode != HLVAE_HEAD_ZERO && (mv[n * D] != (TM)0);
+                g[r] = obs ? gin[n * ld_theta] : (TS)0;
+#pragma unroll
+                for (int k = 0; k < YP; k++) yk[r][k] = (ydep && k < Y) ? yv[n * sn + k * sk] : (TS)0;
+            }
+            // sums over the batch's rows in the storage type, one float64 accumulation per batch (conversions to
+            // float64 run at a fraction of the FMA rate)
+            TS gwb[YP], gbb = (TS)0;
+#pragma unroll
+            for (int k = 0; k < YP; k++) gwb[k] = (TS)0;
+#pragma unroll
+            for (int r = 0; r < TH_RB; r++) {
+                TS gr = g[r];
+                if (mode == HLVAE_HEAD_SIGMOID) {
+                    TS z = b;
+#pragma unroll
+                    for (int k = 0; k < YP; k++) z = fma(wk[k], yk[r][k], z);
+                    const TS sg = sigmoid_t<TS>(z);
+                    gr *= sg * ((TS)1 - sg);
+                }
+#pragma unroll
+                for (int k = 0; k < YP; k++) gwb[k] = fma(gr, yk[r][k], gwb[k]);
+                gbb += gr;
+                gsb[r * TH_THREADS + tid] = ydep ? gr : (TS)0;
+            }
+#pragma unroll
+            for (int k = 0; k < YP; k++) gw[k] += (double)gwb[k];
+            gb += (double)gbb;
+        }
+        __syncthreads();
+        // ---- thread = (variable, k): d/dy[n, d, k] = sum over the variable's columns of g * weight[col, k]
+        for (int q = tid; q < npairs; q += TH_THREADS) {
+            int v, k;
+            if (v_fastest) { k = q / t.nv; v = q - k * t.nv; } else { v = q / Y; k = q - v * Y; }
+            const int lp = vlp[v], nc = vnc[v];
+            TS a[TH_RB];
+#pragma unroll
+            for (int r = 0; r < TH_RB; r++) a[r] = (TS)0;
+            for (int c = 0; c < nc; c++) {
+                const TS wv = Ws[(lp + c) * Y + k];
+#pragma unroll
+                for (int r = 0; r < TH_RB; r++) a[r] = fma(gsb[r * TH_THREADS + lp + c], wv, a[r]);
+            }
+            TS* dst = g_y + (int64_t)(t.d0 + v) * sd + (int64_t)k * sk;
+#pragma unroll
+            for (int r = 0; r < TH_RB; r++)
+                if (n0 + r < t.r_end) dst[(n0 + r) * sn] = a[r];
+        }
+    }
+    if (live && mode != HLVAE_HEAD_ZERO) {
+        if (gb != 0.0) atomicAdd(g_bias + p, gb);
+        if (ydep) {
+#pragma unroll
+            for (int k = 0; k < YP; k++)
+                if (k < Y && gw[k] != 0.0) atomicAdd(g_weight + (int64_t)p * Y + k, gw[k]);
+        }
+    }
+}
+
+int grid_stripes(int64_t N, int n_tiles, int RB, int ctas_per_sm) {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t batches = (N + RB - 1) / RB;
+    int64_t want = ((int64_t)sms * ctas_per_sm + n_tiles - 1) / n_tiles;
+    if (want > batches) want = batches;
+    if (want < 1) want = 1;
+    if (want > 65535) want = 65535;
+    return (int)want;
+}
+
+template <typename TS, int YP>
+int launch_fwd(int64_t N, int Y, int n_tiles, const int32_t* col_var, const int32_t* col_mode, const int32_t* var_pcol,
+               const int32_t* tile_var, const double* weight, const double* bias, const void* y, int64_t sn, int64_t sd,
+               int64_t sk, void* theta, int64_t ld_theta, cudaStream_t st) {
+    auto kern = theta_fwd_k<TS, YP>;
+    dim3 grid(n_tiles, grid_stripes(N, n_tiles, ThRows<TS, YP>::value, 16));
+    kern<<<grid, TH_THREADS, 0, st>>>(N, Y, col_var, col_mode, var_pcol, tile_var, weight, bias, (const TS*)y, sn, sd,
+                                         sk, (TS*)theta, ld_theta);
+    HLVAE_CHECK_LAUNCH();
+    return 0;
+}
+
+template <typename TS, typename TM, int YP>
+int launch_bwd(int64_t N, int D, int Y, int n_tiles, const int32_t* col_var, const int32_t* col_mode,
+               const int32_t* var_pcol, const int32_t* tile_var, const double* weight, const double* bias, const void* y,
+               int64_t sn, int64_t sd, int64_t sk, const void* mask, const void* g_theta, int64_t ld_theta, void* g_y,
+               double* g_weight, double* g_bias, cudaStream_t st) {
+    auto kern = theta_bwd_k<TS, TM, YP>;
+    constexpr int RB = ThRows<TS, YP, true>::value;
+    const size_t smem = ((size_t)2 * RB * TH_THREADS + (size_t)TH_THREADS * Y) * sizeof(TS) + 2 * TH_THREADS * sizeof(int);
+    dim3 grid(n_tiles, grid_stripes(N, n_tiles, RB, 9));
+    kern<<<grid, TH_THREADS, smem, st>>>(N, D, Y, col_var, col_mode, var_pcol, tile_var, weight, bias, (const TS*)y, sn,
+                                         sd, sk, (const TM*)mask, (const TS*)g_theta, ld_theta, (TS*)g_y, g_weight,
+                                         g_bias);
+    HLVAE_CHECK_LAUNCH();
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int hlvae_theta_fwd(int64_t N, int D, int P, int Y, int n_tiles, const int32_t* col_var,
+                               const int32_t* col_mode, const int32_t* var_pcol, const int32_t* tile_var,
+                               const double* weight, const double* bias, const void* y, int64_t sn, int64_t sd,
+                               int64_t sk, int dtype, void* theta, int64_t ld_theta, void* stream) {
+    if (N < 0 || D <= 0 || P <= 0 || Y <= 0 || n_tiles <= 0 || !col_var || !col_mode || !var_pcol || !tile_var ||
+        !weight || !bias || !y || !theta || ld_theta < P)
+        return HLVAE_E_ARG;
+    if (Y > HLVAE_MAX_Y) return HLVAE_E_UNSUPPORTED;
+    if (dtype != HLVAE_F32 && dtype != HLVAE_F64) return HLVAE_E_ARG;
+    if (N == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+#define HLVAE_TH_FWD(TS, YP) \
+    return launch_fwd<TS, YP>(N, Y, n_tiles, col_var, col_mode, var_pcol, tile_var, weight, bias, y, sn, sd, sk, theta, ld_theta, st)
+#define HLVAE_TH_FWD_Y(TS)                                                                                             \
+    switch (Y) {                                                                                                       \
+        case 1: HLVAE_TH_FWD(TS, 1); case 2: HLVAE_TH_FWD(TS, 2); case 3: HLVAE_TH_FWD(TS, 3); case 4: HLVAE_TH_FWD(TS, 4); \
+        case 5: HLVAE_TH_FWD(TS, 5); case 6: HLVAE_TH_FWD(TS, 6); case 7: HLVAE_TH_FWD(TS, 7); case 8: HLVAE_TH_FWD(TS, 8); \
+        default: HLVAE_TH_FWD(TS, 16);                                                                                 \
+    }
+    if (dtype == HLVAE_F32) { HLVAE_TH_FWD_Y(float) }
+    HLVAE_TH_FWD_Y(double)
+#undef HLVAE_TH_FWD_Y
+#undef HLVAE_TH_FWD
+}
+
+extern "C" int hlvae_theta_bwd(int64_t N, int D, int P, int Y, int n_tiles, const int32_t* col_var,
+                               const int32_t* col_mode, const int32_t* var_pcol, const int32_t* tile_var,
+                               const double* weight, const double* bias, const void* y, int64_t sn, int64_t sd,
+                               int64_t sk, int dtype, const void* mask, int mask_dtype, const void* g_theta,
+                               int64_t ld_theta, void* g_y, double* g_weight, double* g_bias, void* stream) {
+    if (N < 0 || D <= 0 || P <= 0 || Y <= 0 || n_tiles <= 0 || !col_var || !col_mode || !var_pcol || !tile_var ||
+        !weight || !bias || !y || !mask || !g_theta || !g_y || !g_weight || !g_bias || ld_theta < P)
+        return HLVAE_E_ARG;
+    if (Y > HLVAE_MAX_Y) return HLVAE_E_UNSUPPORTED;
+    if (dtype != HLVAE_F32 && dtype != HLVAE_F64) return HLVAE_E_ARG;
+    if (mask_dtype != dtype && mask_dtype != HLVAE_U8) return HLVAE_E_ARG;
+    if (N == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+#define HLVAE_TH_BWD(TS, TM, YP)                                                                                       \
+    return launch_bwd<TS, TM, YP>(N, D, Y, n_tiles, col_var, col_mode, var_pcol, tile_var, weight, bias, y, sn, sd, sk, \
+                                  mask, g_theta, ld_theta, g_y, g_weight, g_bias, st)
+#define HLVAE_TH_BWD_Y(TS, TM)                                                                                         \
+    switch (Y) {                                                                                                       \
+        case 1: HLVAE_TH_BWD(TS, TM, 1); case 2: HLVAE_TH_BWD(TS, TM, 2); case 3: HLVAE_TH_BWD(TS, TM, 3);             \
+        case 4: HLVAE_TH_BWD(TS, TM, 4); case 5: HLVAE_TH_BWD(TS, TM, 5); case 6: HLVAE_TH_BWD(TS, TM, 6);             \
+        case 7: HLVAE_TH_BWD(TS, TM, 7); case 8: HLVAE_TH_BWD(TS, TM, 8);                                              \
+        default: HLVAE_TH_BWD(TS, TM, 16);                                                                             \
+    }
+    if (dtype == HLVAE_F32) {
+        if (mask_dtype == HLVAE_U8) { HLVAE_TH_BWD_Y(float, unsigned char) }
+        HLVAE_TH_BWD_Y(float, float)
+    }
+    if (mask_dtype == HLVAE_U8) { HLVAE_TH_BWD_Y(double, unsigned char) }
+    HLVAE_TH_BWD_Y(double, double)
+#undef HLVAE_TH_BWD_Y
+#undef HLVAE_TH_BWD
+}

@@ -230,6 +230,42 @@ int hlvae_statistics(int64_t N, int D, int64_t ld_theta, const int32_t* var_kind
 int hlvae_discrete_transform(int64_t N, int D, int64_t ld_data, const int32_t* var_kind, const int32_t* var_nclass,
                              const int32_t* var_dcol, const void* data, int dtype, void* out, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * Per-variable observation heads.  Replaces HLVAE.theta_estimation
+ * (HLVAE.py:416-453) over the Observation_Count / _Real_Pos_Beta / _Cat / _Ordinal modules
+ * (HLVAE.py:11-89) and the real-valued Sigmoid layer of the convolutional model (:292-295), logvar_network=False.
+ * The reference evaluates each head on y * mask and, under no_grad, on y * (1 - mask), and merges the two
+ * through boolean indexing; for 0/1 masks that is, per theta column p of variable d = col_var[p],
+ *     theta[n, p] = act_p(bias[p] + sum_k weight[p, k] * y[n, d, k])
+ * with gradients flowing through observed entries (mask[n, d] != 0) only.  col_mode[p]:
+ *   HLVAE_HEAD_AFFINE   count / pos / real mean, categorical logits 1..C-1, ordinal region (:22,51,65,87)
+ *   HLVAE_HEAD_SIGMOID  real mean of the convolutional model (affine, then Sigmoid)
+ *   HLVAE_HEAD_ZERO     first categorical logit, fixed to 0 (:66-67)
+ *   HLVAE_HEAD_BIAS     ordinal thresholds: bias[p] = weight_thresholds, independent of y (:85)
+ * Packed layout as in hlvae_loglik_*: var_pcol[d] = first theta column of variable d, var_pcol[D] = P;
+ * tile_var[0..n_tiles] = variable boundaries of tiles covering <= 256 theta columns and <= 256 variables each.
+ *   y [N, D, Y] addressed with ELEMENT strides (sn, sd, sk): the convolutional decoder's y_grouped is a
+ *   permuted view of [N, Y, D] (HLVAE.py:341-342, sd = 1, sk = D), the dense one is contiguous (:344).
+ *   weight [P, Y], bias [P] float64 (rows of constant columns are ignored).  Y <= HLVAE_MAX_Y.
+ *   y, theta, g_theta, g_y: storage `dtype` (HLVAE_F32 / HLVAE_F64), arithmetic in that type;
+ *   mask [N, D] contiguous, `mask_dtype` = dtype or HLVAE_U8.
+ * bwd: g_theta [N, ld_theta] -> g_y (same strides as y, overwritten), g_weight [P, Y], g_bias [P]
+ *   float64 (accumulated, caller zero-fills).
+ * ---------------------------------------------------------------------------------- */
+#define HLVAE_MAX_Y 16
+#define HLVAE_HEAD_AFFINE 0
+#define HLVAE_HEAD_SIGMOID 1
+#define HLVAE_HEAD_ZERO 2
+#define HLVAE_HEAD_BIAS 3
+int hlvae_theta_fwd(int64_t N, int D, int P, int Y, int n_tiles, const int32_t* col_var, const int32_t* col_mode,
+                    const int32_t* var_pcol, const int32_t* tile_var, const double* weight, const double* bias,
+                    const void* y, int64_t sn, int64_t sd, int64_t sk, int dtype, void* theta, int64_t ld_theta,
+                    void* stream);
+int hlvae_theta_bwd(int64_t N, int D, int P, int Y, int n_tiles, const int32_t* col_var, const int32_t* col_mode,
+                    const int32_t* var_pcol, const int32_t* tile_var, const double* weight, const double* bias,
+                    const void* y, int64_t sn, int64_t sd, int64_t sk, int dtype, const void* mask, int mask_dtype,
+                    const void* g_theta, int64_t ld_theta, void* g_y, double* g_weight, double* g_bias, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -567,6 +567,62 @@ def batch_norm_params(descs: List[VarDesc], data, mask):
 # --------------------------------------------------------------------------------------
 # One ELBO-path step (training.py:83,104-137): used by the CPU baseline in bench.py
 # --------------------------------------------------------------------------------------
+# --------------------------------------------------------------------------------------
+# Observation heads: y -> theta (HLVAE.py:11-89, 416-453), SURVEY.md 8(f) row 2
+# --------------------------------------------------------------------------------------
+def head_forward(kind: str, prm: Dict[str, torch.Tensor], gamma: torch.Tensor) -> torch.Tensor:
+    """One Observation_* module on gamma [N, d, Y] -> [N, d, dim] (logvar_network=False).
+    count: HLVAE.py:21-23; real / pos: :42-52 (mean head only, the empty logvar block adds nothing);
+    cat: :63-68 (a zero logit in front); ordinal: :84-89 (thresholds repeated over the batch, then the region)."""
+    lin = lambda w, b: torch.einsum("bdy,dya->bda", gamma, w) + b
+    if kind == 'count':
+        return lin(prm['weight'], prm['bias'])
+    if kind in ('real', 'pos'):
+        return lin(prm['weight_mean'], prm['bias_mean'])
+    if kind == 'cat':
+        th = lin(prm['weight'], prm['bias'])
+        zero = torch.zeros(th.shape[0], th.shape[1], 1, dtype=DT)
+        return torch.cat((zero, th), dim=-1)
+    if kind == 'ordinal':
+        thr = prm['weight_thresholds'].repeat((gamma.shape[0], 1, 1))
+        return torch.cat((thr, lin(prm['weight_region'], prm['bias_region'])), dim=-1)
+    raise NotImplementedError(kind)
+
+
+def theta_estimation(types: Sequence[Tuple[str, int]], heads: List[Dict[str, torch.Tensor]], y: torch.Tensor,
+                     mask: torch.Tensor, conv: bool = False) -> torch.Tensor:
+    """HLVAE.theta_estimation (HLVAE.py:416-453).  `heads[i]` holds the parameters of the i-th type group's
+    module, groups ordered as types_info['set_of_types'].  Follows the reference literally: heads on y * mask
+    (:419,424-427), Sigmoid on the real group of the convolutional model (:429-431), times the parameter mask
+    (:433-434); the same on y * (1 - mask) under no_grad (:436-446); missing entries overwrite (:449-453)."""
+    ti = types_info_from_layout(types, conv=conv)
+    descs, _, P = build_layout(types)
+    N = y.shape[0]
+    pm = torch.zeros(N, P, dtype=DT)                        # read_functions.py:147,172-175: mask per parameter column
+    for d, v in enumerate(descs):
+        pm[:, v.theta_col:v.theta_col + v.nclass] = mask[:, d:d + 1]
+    theta = torch.zeros(N, P, dtype=DT)
+    observed_y = y * mask[:, :, None]
+    missing_y = y * (1 - mask)[:, :, None]
+    for i, tpl in enumerate(ti['set_of_types']):
+        vsel = torch.tensor(ti['data_types_indexes'] == i)
+        psel = torch.tensor(ti['param_indexes'] == i)
+        dim = int(tpl[1])
+        pmi = pm[:, psel].reshape(N, -1, dim)
+        obs = head_forward(tpl[0], heads[i], observed_y[:, vsel, :])
+        if tpl[0] == 'real' and conv:
+            obs = torch.sigmoid(obs)
+        obs = obs * pmi
+        with torch.no_grad():
+            mis = head_forward(tpl[0], heads[i], missing_y[:, vsel, :])
+            if tpl[0] == 'real' and conv:
+                mis = torch.sigmoid(mis)
+            mis = mis * (1 - pmi)
+        merged = torch.where(pmi == 0, mis, obs).reshape(N, -1)
+        theta = theta.index_put((torch.arange(N)[:, None], torch.nonzero(psel)[:, 0][None, :]), merged)
+    return theta
+
+
 def elbo_path_step(state: dict, natural_gradient_lr=0.01) -> Dict[str, torch.Tensor]:
     """nll + KL forward, backward to (theta, mu, log_v, Z, kernel raw parameters, log_vy),
     natural-gradient update of (m, H).  `state` holds every tensor of one minibatch."""

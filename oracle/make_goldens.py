@@ -272,6 +272,75 @@ def loglik_case(name, types, N, seed, conv=False, observed=0.7):
     print(f"  {name}: N={N} D={D} E_x={E_x} worst rel diff {max(w):.2e}")
 
 
+# ------------------------------------------------------------------ observation heads (y -> theta)
+HEAD_PARAM_NAMES = {'count': ('weight', 'bias'), 'real': ('weight_mean', 'bias_mean'), 'pos': ('weight_mean', 'bias_mean'),
+                    'cat': ('weight', 'bias'), 'ordinal': ('weight_thresholds', 'weight_region', 'bias_region')}
+
+
+def theta_case(name, types, N, seed, conv=False, observed=0.7):
+    """HLVAE.theta_estimation of the unmodified reference (HLVAE.py:416-453) on a seeded y, with an arbitrary
+    upstream gradient: theta, d/dy and the gradient of every Observation_* parameter."""
+    import HLVAE as ref_hlvae                               # reference
+    gen = torch.Generator().manual_seed(seed)
+    torch.manual_seed(seed)
+    tinfo = orc.types_info_from_layout(types, conv=conv)
+    descs, E_x, P_th = orc.build_layout(types)
+    D = len(types)
+    dims = [D, [16], 4, [16], 5] if conv else [E_x, [16], 4, [16], 3]
+    Y = dims[4]
+    model = ref_hlvae.HLVAE(dims, tinfo, D, vy_init=[1., .5], vy_fixed=False, logvar_network=False, conv=conv).double()
+    with torch.no_grad():                                   # move the heads away from their near-zero initial state
+        for prm in model.obs_layer.parameters():
+            prm.add_(0.4 * torch.randn(prm.shape, generator=gen, dtype=DT))
+    if conv:                                                # y_grouped is a permuted view of [N, Y, D] (:341-342)
+        y0 = (torch.randn(N, Y, D, generator=gen, dtype=DT) * 1.5).permute(0, 2, 1)
+    else:
+        y0 = torch.randn(N, D, Y, generator=gen, dtype=DT) * 1.5
+    mask = (torch.rand(N, D, generator=gen, dtype=DT) < observed).to(DT)
+    pm = torch.zeros(N, P_th, dtype=DT)
+    for d, v in enumerate(descs):
+        pm[:, v.theta_col:v.theta_col + v.nclass] = mask[:, d:d + 1]
+    g_up = torch.randn(N, P_th, generator=gen, dtype=DT)
+    y = y0.clone().requires_grad_(True)
+    theta = model.theta_estimation(y, mask, pm)
+    (theta * g_up).sum().backward()
+
+    # ---- oracle
+    heads, layer = [], 0
+    for i, tpl in enumerate(tinfo['set_of_types']):
+        mod = model.obs_layer[layer]
+        heads.append({n: getattr(mod, n).detach().clone().requires_grad_(True) for n in HEAD_PARAM_NAMES[tpl[0]]})
+        layer += 2 if (tpl[0] == 'real' and conv) else 1
+    y_o = y0.clone().requires_grad_(True)
+    th_o = orc.theta_estimation(types, heads, y_o, mask, conv=conv)
+    (th_o * g_up).sum().backward()
+    w = [check(name + ".theta", th_o, theta, 1e-13), check(name + ".d_y", y_o.grad, y.grad, 1e-12)]
+    out = dict(types=np.array([f"{k}:{c}" for k, c in types]), conv=int(conv), y=y0.contiguous().numpy(),
+               mask=mask.numpy(), g_up=g_up.numpy(), theta=theta.detach().numpy(), d_y=y.grad.contiguous().numpy(),
+               n_groups=len(heads))
+    layer = 0
+    for i, tpl in enumerate(tinfo['set_of_types']):
+        mod = model.obs_layer[layer]
+        for n in HEAD_PARAM_NAMES[tpl[0]]:
+            gref = getattr(mod, n).grad
+            w.append(check(f"{name}.d_{tpl[0]}{tpl[1]}.{n}", heads[i][n].grad, gref, 1e-11))
+            out[f"g{i}_{n}"] = getattr(mod, n).detach().numpy()
+            out[f"d_g{i}_{n}"] = gref.numpy()
+        out[f"g{i}_kind"] = np.array(f"{tpl[0]}:{tpl[1]}")
+        layer += 2 if (tpl[0] == 'real' and conv) else 1
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print(f"  {name}: N={N} D={D} P_theta={P_th} worst rel diff {max(w):.2e}")
+
+
+def theta_cases():
+    print("observation heads (theta_estimation): oracle vs unmodified reference")
+    rng = np.random.default_rng(21)
+    theta_case("theta_mixed", synth.mixed_types(rng, 24), N=24, seed=21)
+    theta_case("theta_tabular_small", [('count', 1)] * 3 + [('ordinal', 5)] * 3 + [('cat', 5)] * 3 + [('real', 1)] * 2 +
+               [('pos', 1)] * 2, N=16, seed=22)
+    theta_case("theta_conv_d4", synth.HEALTHMNIST_D4_TYPES, N=3, seed=23, conv=True, observed=0.75)
+
+
 # ------------------------------------------------------------------ GP posterior-mean prediction
 def predict_case(name, kargs, L, M, n_subj, T, ragged, seed, n_test_subj=3, continuous_age=False):
     """utils.batch_predict_varying_T (and, with equal T, utils.batch_predict) of the unmodified reference.
@@ -384,6 +453,9 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "predict":      # only the prediction fixtures
         predict_cases()
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "theta":        # only the observation-head fixtures
+        theta_cases()
+        return
     print("KL upper bound: oracle vs unmodified reference (gpytorch stand-in)")
     kl_case("kl_default_ragged", synth.DEFAULT_KERNEL_ARGS, L=4, M=12, n_subj=6, T=8, ragged=True, fixed_T_api=False, seed=1)
     kl_case("kl_default_fixedT", synth.DEFAULT_KERNEL_ARGS, L=3, M=10, n_subj=5, T=6, ragged=False, fixed_T_api=True, seed=2)
@@ -404,6 +476,7 @@ def main():
                 N=16, seed=12)
     loglik_case("loglik_conv_d4", synth.HEALTHMNIST_D4_TYPES, N=3, seed=13, conv=True, observed=0.75)
     predict_cases()
+    theta_cases()
     print("all oracle-vs-reference checks passed; goldens written to", GOLD)
 
 

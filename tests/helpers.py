@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 import hlvae_b200  # noqa: F401
-from hlvae_b200 import elbo, kernels, likelihoods, loglik, subjects, synth
+from hlvae_b200 import elbo, kernels, likelihoods, loglik, subjects, synth, theta as theta_mod
 from oracle import hlvae_oracle as orc
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -21,6 +21,7 @@ DT = torch.float64
 KL_CASES = ["kl_default_ragged", "kl_default_fixedT", "kl_sweep_ragged", "kl_masked_bin", "kl_trained_like",
             "kl_not_natgrad", "kl_shuffled_rows", "kl_T32_M40"]
 LOGLIK_CASES = ["loglik_mixed", "loglik_tabular_small", "loglik_conv_d4"]
+THETA_CASES = ["theta_mixed", "theta_tabular_small", "theta_conv_d4"]
 
 
 def load(name):
@@ -268,4 +269,60 @@ def assert_loglik_close(r, tol=1e-9, label=""):
     assert np.array_equal(gm[:, disc], g["recon_mean"][:, disc]), f"{label} categorical/ordinal argmax differs"
     assert np.array_equal(got["data_transformed"].detach().cpu().numpy(), g["data_transformed"]), \
         f"{label} discrete transform differs"
+    return errs
+
+
+# ---------------------------------------------------------------------------- observation heads
+class _Head(torch.nn.Module):
+    """Stand-in for one Observation_* module (HLVAE.py:11-89): same parameter names, no forward."""
+
+    def __init__(self, params):
+        super().__init__()
+        for n, v in params.items():
+            setattr(self, n, torch.nn.Parameter(v))
+
+
+def golden_heads(g, dev, conv):
+    """(obs_layer ModuleList as HLVAE.py:276-299 builds it, per-group oracle head dicts, group kinds)."""
+    layers, heads, kinds = [], [], []
+    for i in range(int(g["n_groups"])):
+        kind = str(g[f"g{i}_kind"]).split(":")[0]
+        names = [k[len(f"g{i}_"):] for k in g if k.startswith(f"g{i}_") and k != f"g{i}_kind"]
+        layers.append(_Head({n: t(g[f"g{i}_{n}"], dev) for n in names}))
+        heads.append({n: t(g[f"g{i}_{n}"]).requires_grad_(True) for n in names})
+        kinds.append(kind)
+        if kind == "real" and conv:
+            layers.append(torch.nn.Sigmoid())
+    return torch.nn.ModuleList(layers), heads, kinds
+
+
+def run_theta_golden(name, dev, storage=torch.float64, mask_u8=False):
+    g = load(name)
+    types, conv = parse_types(g), bool(int(g["conv"]))
+    obs_layer, _, kinds = golden_heads(g, dev, conv)
+    lay = theta_mod.HeadLayout(types, conv, dev)
+    y0 = t(g["y"], dev).to(storage)
+    if conv:                                    # the convolutional decoder hands over a permuted view (HLVAE.py:341-342)
+        y0 = y0.permute(0, 2, 1).contiguous().permute(0, 2, 1)
+    y = y0.clone(memory_format=torch.preserve_format).requires_grad_(True)
+    mask = t(g["mask"], dev)
+    mask = mask.to(torch.uint8) if mask_u8 else mask.to(storage)
+    W, b = theta_mod.pack_heads(obs_layer, lay, y.shape[2])
+    theta = theta_mod.theta_heads(lay, y, mask, W, b)
+    (theta.double() * t(g["g_up"], dev)).sum().backward()
+    grads, layer = {}, 0
+    for i, kind in enumerate(kinds):
+        for n, prm in obs_layer[layer].named_parameters():
+            grads[f"d_g{i}_{n}"] = prm.grad
+        layer += 2 if (kind == "real" and conv) else 1
+    return dict(g=g, theta=theta.detach(), d_y=y.grad, grads=grads)
+
+
+def assert_theta_close(r, tol, label=""):
+    g = r["g"]
+    errs = {"theta": rel_err(r["theta"], g["theta"]), "d_y": rel_err(r["d_y"], g["d_y"])}
+    for k, v in r["grads"].items():
+        errs[k] = rel_err(v, g[k])
+    bad = {k: v for k, v in errs.items() if not v < tol}
+    assert not bad, f"{label}: {bad}"
     return errs

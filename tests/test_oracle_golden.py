@@ -97,3 +97,42 @@ def test_oracle_dubo_matches_reference_goldens(name):
     d = orc.validation_dubo(spec0, prm0, spec1, prm1, h.t(g["noise"]), h.t(g["x"]), h.t(g["mu"]), h.t(g["log_v"]),
                             h.t(g["z"]), int(g["n_subj"]), int(g["T"]), float(g["eps"]))
     assert h.rel_err(d, g["dubo"]) < 1e-9
+
+
+@pytest.mark.parametrize("name", h.THETA_CASES)
+def test_oracle_theta_matches_reference_goldens(name):
+    """HLVAE.theta_estimation (HLVAE.py:416-453): oracle restatement vs the unmodified reference's outputs."""
+    g = h.load(name)
+    types, conv = h.parse_types(g), bool(int(g["conv"]))
+    _, heads, kinds = h.golden_heads(g, "cpu", conv)
+    y = h.t(g["y"]).requires_grad_(True)
+    theta = orc.theta_estimation(types, heads, y, h.t(g["mask"]), conv=conv)
+    (theta * h.t(g["g_up"])).sum().backward()
+    assert h.rel_err(theta, g["theta"]) < 1e-13
+    assert h.rel_err(y.grad, g["d_y"]) < 1e-12
+    for i, hd in enumerate(heads):
+        for n, prm in hd.items():
+            assert h.rel_err(prm.grad, g[f"d_g{i}_{n}"]) < 1e-11, (i, n)
+
+
+@pytest.mark.parametrize("name", h.THETA_CASES)
+def test_packed_head_form_equals_reference(name):
+    """Host logic of hl-vae_b200/theta.py on CPU (no kernel): the per-column (weight, bias, mode) form that
+    `pack_heads` builds reproduces the reference's theta when evaluated with plain torch ops."""
+    from hlvae_b200 import theta as th, _lib
+    g = h.load(name)
+    types, conv = h.parse_types(g), bool(int(g["conv"]))
+    obs_layer, _, _ = h.golden_heads(g, "cpu", conv)
+    lay = th.HeadLayout(types, conv, "cpu")
+    y = h.t(g["y"])
+    W, b = th.pack_heads(obs_layer, lay, y.shape[2])
+    z = b[None, :] + torch.einsum("npk,pk->np", y[:, lay.col_var.long(), :], W)
+    mode = lay.col_mode
+    z = torch.where(mode == _lib.HEAD_SIGMOID, torch.sigmoid(z), z)
+    z = torch.where(mode == _lib.HEAD_ZERO, torch.zeros_like(z), z)
+    z = torch.where(mode == _lib.HEAD_BIAS, b[None, :].expand_as(z), z)
+    assert h.rel_err(z, g["theta"]) < 1e-13
+    tv = lay.tile_var.tolist()
+    vp = lay.var_pcol.tolist()
+    assert tv[0] == 0 and tv[-1] == lay.D and all(a < c for a, c in zip(tv, tv[1:]))
+    assert all(vp[c] - vp[a] <= th.MAX_TILE and c - a <= th.MAX_TILE for a, c in zip(tv, tv[1:]))
