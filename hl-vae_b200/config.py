@@ -12,3 +12,7 @@ process_group = None
 # Run independent kernels of one KL call on two CUDA streams (per-subject T x T stage next to the
 # M x M pre-stage).  Pure scheduling: results are identical either way.
 overlap = True
+
+# Drop-in HLVAE module (hl-vae_b200/dropin/HLVAE.py): also replace HLVAE.loglik_and_reconstruction
+# (HLVAE.py:381-414) by the fused method, which returns no `samples`.  Read when the drop-in is imported.
+fused_loglik_method = False

@@ -22,7 +22,13 @@ constexpr int TH_THREADS = 256;   // = max theta columns and max variables per t
 template <typename TS, int YP, bool BWD = false>
 struct ThRows {
     static constexpr int raw = (BWD ? 80 : 160) / (YP * (int)sizeof(TS));
-    static constexpr int value = raw < 1 ? 1 : (raw > 8 ? 8 : raw);
+    // backward: a power of two, the rows of a column travel through shared memory as one vector
+    static constexpr int value = BWD ? (raw >= 8 ? 8 : raw >= 4 ? 4 : raw >= 2 ? 2 : 1) : (raw < 1 ? 1 : (raw > 8 ? 8 : raw));
+};
+
+template <typename TS, int RB>
+struct alignas(sizeof(TS) * RB > 16 ? 16 : sizeof(TS) * RB) ThRowVec {
+    TS v[RB];
 };
 
 template <typename TS>
@@ -53,6 +59,37 @@ __device__ __forceinline__ ThTile th_tile(const int32_t* __restrict__ tile_var, 
     return t;
 }
 
+// R rows of one theta column.  yb / ob point at the first row; the row and k offsets are 32-bit and uniform over
+// the CTA (r and k are compile-time), so each access costs one wide multiply-add on top of the memory instruction.
+template <typename TS, int YP, int R>
+__device__ __forceinline__ void th_fwd_rows(const TS* __restrict__ yb, TS* __restrict__ ob, int sn, int sk, int ld, int Y,
+                                            const TS (&wk)[YP], TS b, int mode, bool ydep) {
+    // keep the strides opaque per call: otherwise the compiler hoists all R x y_dim 64-bit offsets out of the
+    // row loop as loop invariants (80 registers of addresses, spills, ~9 integer instructions per load)
+    asm volatile("" : "+r"(sn), "+r"(sk), "+r"(ld));
+    TS z[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) z[r] = b;
+    if (ydep) {
+        TS yk[R][YP];
+        const TS* pr = yb;                       // one pointer per row, k offsets shared by all rows
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+#pragma unroll
+            for (int k = 0; k < YP; k++) yk[r][k] = (k < Y) ? pr[k * sk] : (TS)0;
+            pr += sn;
+        }
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+#pragma unroll
+            for (int k = 0; k < YP; k++) z[r] = fma(wk[k], yk[r][k], z[r]);
+            if (mode == HLVAE_HEAD_SIGMOID) z[r] = sigmoid_t<TS>(z[r]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; r++) ob[r * ld] = z[r];
+}
+
 template <typename TS, int YP>
 __global__ void __launch_bounds__(TH_THREADS, 3)
 theta_fwd_k(int64_t N, int Y, const int32_t* __restrict__ col_var, const int32_t* __restrict__ col_mode,
@@ -72,22 +109,101 @@ theta_fwd_k(int64_t N, int Y, const int32_t* __restrict__ col_var, const int32_t
     for (int k = 0; k < YP; k++) wk[k] = (ydep && k < Y) ? (TS)weight[(int64_t)p * Y + k] : (TS)0;
     const TS* yv = y + (int64_t)col_var[p] * sd;
     TS* out = theta + p;
-    for (int64_t n0 = t.r_begin; n0 < t.r_end; n0 += TH_RB) {
-        TS yk[TH_RB][YP];
+    const int sn32 = (int)sn, sk32 = (int)sk, ld32 = (int)ld_theta;
+    int64_t n0 = t.r_begin;
+    for (; n0 + TH_RB <= t.r_end; n0 += TH_RB)
+        th_fwd_rows<TS, YP, TH_RB>(yv + n0 * sn, out + n0 * ld_theta, sn32, sk32, ld32, Y, wk, b, mode, ydep);
+    for (; n0 < t.r_end; n0++)
+        th_fwd_rows<TS, YP, 1>(yv + n0 * sn, out + n0 * ld_theta, sn32, sk32, ld32, Y, wk, b, mode, ydep);
+}
+
+// One batch of R rows of the backward pass (see the kernel comment); called with R = RB for full batches and
+// R = 1 for the tail rows of a stripe.  All threads of the CTA call it (it contains the barrier).
+template <typename TS, typename TM, int YP, int R>
+__device__ __forceinline__ void th_bwd_rows(bool live, bool ydep, int mode, TS b, const TS (&wk)[YP], double (&gw)[YP],
+                                            double& gb, const TS* __restrict__ yb, const TM* __restrict__ mb,
+                                            const TS* __restrict__ gb_in, TS* __restrict__ gyb, int sn, int sd, int sk,
+                                            int D, int ld, int Y, TS* __restrict__ gsb, const TS* __restrict__ Ws,
+                                            const int* __restrict__ vlp, const int* __restrict__ vnc, int nv,
+                                            bool v_fastest) {
+    const int tid = threadIdx.x;
+    asm volatile("" : "+r"(sn), "+r"(sk), "+r"(ld), "+r"(D));      // see th_fwd_rows
+    // ---- thread = column: masked upstream gradient, d/d{weight, bias}
+    if (live) {
+        ThRowVec<TS, R> gout;
+        if (mode == HLVAE_HEAD_ZERO) {
 #pragma unroll
-        for (int r = 0; r < TH_RB; r++) {
-            const int64_t n = (n0 + r < t.r_end) ? n0 + r : t.r_end - 1;      // clamped: the tail re-reads the last row
+            for (int r = 0; r < R; r++) gout.v[r] = (TS)0;
+        } else {
+            TS g[R];
 #pragma unroll
-            for (int k = 0; k < YP; k++) yk[r][k] = (ydep && k < Y) ? yv[n * sn + k * sk] : (TS)0;
+            for (int r = 0; r < R; r++) g[r] = gb_in[r * ld];
+            TM m[R];
+#pragma unroll
+            for (int r = 0; r < R; r++) m[r] = mb[r * D];
+            if (ydep) {
+                TS yk[R][YP];
+                const TS* pr = yb;
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+#pragma unroll
+                    for (int k = 0; k < YP; k++) yk[r][k] = (k < Y) ? pr[k * sk] : (TS)0;
+                    pr += sn;
+                }
+                // sums over the batch's rows in the storage type, one float64 accumulation per batch (conversions
+                // to float64 run at a fraction of the FMA rate)
+                TS gwb[YP], gbb = (TS)0;
+#pragma unroll
+                for (int k = 0; k < YP; k++) gwb[k] = (TS)0;
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    TS gr = (m[r] != (TM)0) ? g[r] : (TS)0;
+                    if (mode == HLVAE_HEAD_SIGMOID) {
+                        TS z = b;
+#pragma unroll
+                        for (int k = 0; k < YP; k++) z = fma(wk[k], yk[r][k], z);
+                        const TS sg = sigmoid_t<TS>(z);
+                        gr *= sg * ((TS)1 - sg);
+                    }
+#pragma unroll
+                    for (int k = 0; k < YP; k++) gwb[k] = fma(gr, yk[r][k], gwb[k]);
+                    gbb += gr;
+                    gout.v[r] = gr;
+                }
+#pragma unroll
+                for (int k = 0; k < YP; k++) gw[k] += (double)gwb[k];
+                gb += (double)gbb;
+            } else {   // HLVAE_HEAD_BIAS: the column is its bias
+                TS gbb = (TS)0;
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    gbb += (m[r] != (TM)0) ? g[r] : (TS)0;
+                    gout.v[r] = (TS)0;
+                }
+                gb += (double)gbb;
+            }
         }
+        *reinterpret_cast<ThRowVec<TS, R>*>(gsb + tid * R) = gout;
+    }
+    __syncthreads();
+    // ---- thread = (variable, k): d/dy[n, d, k] = sum over the variable's columns of g * weight[col, k]
+    const int npairs = nv * Y;
+    for (int q = tid; q < npairs; q += TH_THREADS) {
+        int v, k;
+        if (v_fastest) { k = q / nv; v = q - k * nv; } else { v = q / Y; k = q - v * Y; }
+        const int lp = vlp[v], nc = vnc[v];
+        TS a[R];
 #pragma unroll
-        for (int r = 0; r < TH_RB; r++) {
-            TS z = b;
+        for (int r = 0; r < R; r++) a[r] = (TS)0;
+        for (int c = 0; c < nc; c++) {
+            const TS wv = Ws[(lp + c) * Y + k];
+            const ThRowVec<TS, R> gv = *reinterpret_cast<const ThRowVec<TS, R>*>(gsb + (lp + c) * R);
 #pragma unroll
-            for (int k = 0; k < YP; k++) z = fma(wk[k], yk[r][k], z);
-            if (mode == HLVAE_HEAD_SIGMOID) z = sigmoid_t<TS>(z);
-            if (n0 + r < t.r_end) out[(n0 + r) * ld_theta] = z;
+            for (int r = 0; r < R; r++) a[r] = fma(gv.v[r], wv, a[r]);
         }
+        TS* dst = gyb + v * sd + k * sk;
+#pragma unroll
+        for (int r = 0; r < R; r++) dst[r * sn] = a[r];
     }
 }
 
@@ -100,7 +216,7 @@ theta_bwd_k(int64_t N, int D, int Y, const int32_t* __restrict__ col_var, const 
             TS* __restrict__ g_y, double* __restrict__ g_weight, double* __restrict__ g_bias) {
     constexpr int TH_RB = ThRows<TS, YP, true>::value;
     extern __shared__ __align__(16) unsigned char th_smem[];
-    TS* gs = reinterpret_cast<TS*>(th_smem);                  // [2][RB][256] masked upstream gradient per column
+    TS* gs = reinterpret_cast<TS*>(th_smem);                  // [2][256][RB] masked upstream gradient per column
     TS* Ws = gs + 2 * TH_RB * TH_THREADS;                     // [256][Y] weights of the tile's y-dependent columns
     int* vlp = reinterpret_cast<int*>(Ws + (size_t)TH_THREADS * Y);   // [256] first tile-local column of a variable
     int* vnc = vlp + TH_THREADS;                              // [256] its column count
@@ -126,71 +242,23 @@ theta_bwd_k(int64_t N, int D, int Y, const int32_t* __restrict__ col_var, const 
         vlp[tid] = var_pcol[t.d0 + tid] - t.p0;
         vnc[tid] = var_pcol[t.d0 + tid + 1] - var_pcol[t.d0 + tid];
     }
+    __syncthreads();
     const TS* yv = y + (int64_t)dvar * sd;
     const TM* mv = mask + dvar;
     const TS* gin = g_theta + p;
-    // (variable, k) pairs of the d/dy phase, consecutive threads -> consecutive addresses of the caller's layout
-    const bool v_fastest = sd < sk;
-    const int npairs = t.nv * Y;
+    TS* gyt = g_y + (int64_t)t.d0 * sd;
+    const bool v_fastest = sd < sk;       // consecutive threads of the d/dy phase -> consecutive addresses of the layout
+    const int sn32 = (int)sn, sd32 = (int)sd, sk32 = (int)sk, ld32 = (int)ld_theta;
     int buf = 0;
-    for (int64_t n0 = t.r_begin; n0 < t.r_end; n0 += TH_RB, buf ^= 1) {
-        TS* gsb = gs + buf * TH_RB * TH_THREADS;
-        // ---- thread = column: masked upstream gradient, d/d{weight, bias}
-        if (live) {
-            TS yk[TH_RB][YP], g[TH_RB];
-#pragma unroll
-            for (int r = 0; r < TH_RB; r++) {
-                const bool in = n0 + r < t.r_end;
-                const int64_t n = in ? n0 + r : t.r_end - 1;
-                const bool obs = in && mode != HLVAE_HEAD_ZERO && (mv[n * D] != (TM)0);
-                g[r] = obs ? gin[n * ld_theta] : (TS)0;
-#pragma unroll
-                for (int k = 0; k < YP; k++) yk[r][k] = (ydep && k < Y) ? yv[n * sn + k * sk] : (TS)0;
-            }
-            // sums over the batch's rows in the storage type, one float64 accumulation per batch (conversions to
-            // float64 run at a fraction of the FMA rate)
-            TS gwb[YP], gbb = (TS)0;
-#pragma unroll
-            for (int k = 0; k < YP; k++) gwb[k] = (TS)0;
-#pragma unroll
-            for (int r = 0; r < TH_RB; r++) {
-                TS gr = g[r];
-                if (mode == HLVAE_HEAD_SIGMOID) {
-                    TS z = b;
-#pragma unroll
-                    for (int k = 0; k < YP; k++) z = fma(wk[k], yk[r][k], z);
-                    const TS sg = sigmoid_t<TS>(z);
-                    gr *= sg * ((TS)1 - sg);
-                }
-#pragma unroll
-                for (int k = 0; k < YP; k++) gwb[k] = fma(gr, yk[r][k], gwb[k]);
-                gbb += gr;
-                gsb[r * TH_THREADS + tid] = ydep ? gr : (TS)0;
-            }
-#pragma unroll
-            for (int k = 0; k < YP; k++) gw[k] += (double)gwb[k];
-            gb += (double)gbb;
-        }
-        __syncthreads();
-        // ---- thread = (variable, k): d/dy[n, d, k] = sum over the variable's columns of g * weight[col, k]
-        for (int q = tid; q < npairs; q += TH_THREADS) {
-            int v, k;
-            if (v_fastest) { k = q / t.nv; v = q - k * t.nv; } else { v = q / Y; k = q - v * Y; }
-            const int lp = vlp[v], nc = vnc[v];
-            TS a[TH_RB];
-#pragma unroll
-            for (int r = 0; r < TH_RB; r++) a[r] = (TS)0;
-            for (int c = 0; c < nc; c++) {
-                const TS wv = Ws[(lp + c) * Y + k];
-#pragma unroll
-                for (int r = 0; r < TH_RB; r++) a[r] = fma(gsb[r * TH_THREADS + lp + c], wv, a[r]);
-            }
-            TS* dst = g_y + (int64_t)(t.d0 + v) * sd + (int64_t)k * sk;
-#pragma unroll
-            for (int r = 0; r < TH_RB; r++)
-                if (n0 + r < t.r_end) dst[(n0 + r) * sn] = a[r];
-        }
-    }
+    int64_t n0 = t.r_begin;
+    for (; n0 + TH_RB <= t.r_end; n0 += TH_RB, buf ^= 1)
+        th_bwd_rows<TS, TM, YP, TH_RB>(live, ydep, mode, b, wk, gw, gb, yv + n0 * sn, mv + n0 * D, gin + n0 * ld_theta,
+                                       gyt + n0 * sn, sn32, sd32, sk32, D, ld32, Y, gs + buf * TH_RB * TH_THREADS, Ws, vlp,
+                                       vnc, t.nv, v_fastest);
+    for (; n0 < t.r_end; n0++, buf ^= 1)
+        th_bwd_rows<TS, TM, YP, 1>(live, ydep, mode, b, wk, gw, gb, yv + n0 * sn, mv + n0 * D, gin + n0 * ld_theta,
+                                   gyt + n0 * sn, sn32, sd32, sk32, D, ld32, Y, gs + buf * TH_RB * TH_THREADS, Ws, vlp, vnc,
+                                   t.nv, v_fastest);
     if (live && mode != HLVAE_HEAD_ZERO) {
         if (gb != 0.0) atomicAdd(g_bias + p, gb);
         if (ydep) {
@@ -199,6 +267,12 @@ theta_bwd_k(int64_t N, int D, int Y, const int32_t* __restrict__ col_var, const 
                 if (k < Y && gw[k] != 0.0) atomicAdd(g_weight + (int64_t)p * Y + k, gw[k]);
         }
     }
+}
+
+// 32-bit in-batch offsets: (rows in flight) * row stride + y_dim * k stride must fit in an int
+bool th_offsets_fit(int64_t sn, int64_t sd, int64_t sk, int64_t ld, int Y) {
+    const int64_t lim = (int64_t)1 << 31;
+    return sn >= 0 && sd >= 0 && sk >= 0 && 8 * sn + Y * sk + 256 * sd < lim && 8 * ld < lim;
 }
 
 int grid_stripes(int64_t N, int n_tiles, int RB, int ctas_per_sm) {
@@ -249,7 +323,7 @@ extern "C" int hlvae_theta_fwd(int64_t N, int D, int P, int Y, int n_tiles, cons
     if (N < 0 || D <= 0 || P <= 0 || Y <= 0 || n_tiles <= 0 || !col_var || !col_mode || !var_pcol || !tile_var ||
         !weight || !bias || !y || !theta || ld_theta < P)
         return HLVAE_E_ARG;
-    if (Y > HLVAE_MAX_Y) return HLVAE_E_UNSUPPORTED;
+    if (Y > HLVAE_MAX_Y || !th_offsets_fit(sn, sd, sk, ld_theta, Y)) return HLVAE_E_UNSUPPORTED;
     if (dtype != HLVAE_F32 && dtype != HLVAE_F64) return HLVAE_E_ARG;
     if (N == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
@@ -275,7 +349,7 @@ extern "C" int hlvae_theta_bwd(int64_t N, int D, int P, int Y, int n_tiles, cons
     if (N < 0 || D <= 0 || P <= 0 || Y <= 0 || n_tiles <= 0 || !col_var || !col_mode || !var_pcol || !tile_var ||
         !weight || !bias || !y || !mask || !g_theta || !g_y || !g_weight || !g_bias || ld_theta < P)
         return HLVAE_E_ARG;
-    if (Y > HLVAE_MAX_Y) return HLVAE_E_UNSUPPORTED;
+    if (Y > HLVAE_MAX_Y || !th_offsets_fit(sn, sd, sk, ld_theta, Y)) return HLVAE_E_UNSUPPORTED;
     if (dtype != HLVAE_F32 && dtype != HLVAE_F64) return HLVAE_E_ARG;
     if (mask_dtype != dtype && mask_dtype != HLVAE_U8) return HLVAE_E_ARG;
     if (N == 0) return 0;

@@ -19,7 +19,11 @@ import hlvae_b200
 import training, HLVAE, validation, kernel_gen, kernel_spec, elbo_functions
 from HL_VAE import loglik, read_functions
 from hlvae_b200 import elbo as E, kernels as K, loglik as LL
-assert training.__file__.startswith(ref) and HLVAE.__file__.startswith(ref)          # the reference's own files
+assert training.__file__.startswith(ref)                                             # the reference's own file
+from hlvae_b200 import theta as TH
+assert "dropin" in HLVAE.__file__ and HLVAE.HLVAE.__module__ == "_hlvae_reference_HLVAE"   # reference class, passed through
+assert HLVAE.HLVAE.theta_estimation is TH.theta_estimation and HLVAE.Observation_Cat.__module__ == "_hlvae_reference_HLVAE"
+assert HLVAE.HLVAE.encode.__module__ == "_hlvae_reference_HLVAE" and callable(HLVAE.HLVAE.reference_theta_estimation)
 assert training.minibatch_KLD_upper_bound is E.minibatch_KLD_upper_bound
 assert training.minibatch_KLD_upper_bound_iter is E.minibatch_KLD_upper_bound_iter
 assert kernel_gen.generate_kernel_batched is K.generate_kernel_batched
