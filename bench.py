@@ -57,7 +57,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--eager", action="store_true", help="time eager launches instead of CUDA-graph replay")
     ap.add_argument("--no-overlap", action="store_true", help="single stream: no likelihood / KL overlap")
-    ap.add_argument("--workload", default="elbo", choices=["elbo", "predict", "sweep", "theta"],
+    ap.add_argument("--workload", default="elbo", choices=["elbo", "predict", "sweep", "theta", "full"],
                     help="elbo: the BASELINE.json metric (default); predict: SURVEY 8(f) row 1, GP posterior-mean "
                          "prediction (utils.batch_predict_varying_T), its own JSON line")
     return ap.parse_args()
@@ -666,6 +666,121 @@ def run_theta(args):
     print(json.dumps(line), flush=True)
 
 
+def run_full(args):
+    """SURVEY.md 8(d) step rate (ii): the FULL training step of training.py:78-137 at the configs[1] batch - the
+    stock-PyTorch NN trunk (convolutional encoder / decoder with the shapes of HLVAE.py:146-165, 244-275, hidden [500],
+    y_dim 5; cuDNN / cuBLAS, float32 - the reference runs it in float64), then this repo's path: observation heads
+    (hlvae_theta_*), fused likelihoods (hlvae_loglik_*), KL upper bound + natural-gradient update (hlvae_kl_*,
+    hlvae_mxm_*), backward through everything, and one torch.optim.Adam step over trunk, heads, kernel
+    hyper-parameters, inducing points and log-variances.  Eager launches, CUDA events."""
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    import __graft_entry__ as g
+    g.build()
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from hlvae_b200 import _lib, config, elbo, loglik, synth, theta as th
+    config.check_errors = False
+    torch.manual_seed(0)
+    s = build_gpu_state(dev, args.subjects, 0)
+    lay, N_b, Y, H1 = s["lay"], s["N_b"], 5, 500
+    hlay = th.HeadLayout(synth.HEALTHMNIST_D4_TYPES, True, dev)
+    real_d, cat_d = lay.idx["real"], lay.idx["cat"]
+    real_col = lay.var_dcol.long()[real_d]
+    cat_col = (lay.var_dcol.long()[cat_d][:, None] + torch.arange(5, device=dev)[None, :]).reshape(-1)
+
+    class Head(nn.Module):
+        def __init__(self, **shapes):
+            super().__init__()
+            for n, shp in shapes.items():
+                setattr(self, n, nn.Parameter(torch.randn(*shp, dtype=torch.float64) * 0.05))
+
+    class Trunk(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.rep_w = nn.Parameter(torch.randn(cat_d.numel(), 5) * 0.05)        # Representation_One_Hot, HLVAE.py:91-102
+            self.rep_b = nn.Parameter(torch.randn(cat_d.numel()) * 0.05)
+            self.conv1, self.conv2 = nn.Conv2d(1, 16, 3, 1, 1), nn.Conv2d(16, 32, 3, 1, 1)   # :146-152
+            self.enc = nn.Linear(32 * 9 * 9, H1)
+            self.mean, self.logvar = nn.Linear(H1, L), nn.Linear(H1, L)            # :167-177
+            self.dec, self.y_layer = nn.Linear(L, H1), nn.Linear(H1, 32 * 9 * 9)   # :244-266
+            self.deconv = nn.Sequential(nn.ConvTranspose2d(32, 16, 4, 2, 1), nn.ReLU(), nn.ConvTranspose2d(16, Y, 4, 2, 1))
+            # obs_layer as HLVAE.py:276-299 builds it for the sorted type groups [('cat','5'), ('real','1')]
+            self.obs_layer = nn.ModuleList([Head(weight=(cat_d.numel(), Y, 4), bias=(cat_d.numel(), 4)),
+                                            Head(weight_mean=(real_d.numel(), Y, 1), bias_mean=(real_d.numel(), 1)),
+                                            nn.Sigmoid()])
+
+        def encode(self, data, mask):                                              # :302-335
+            n = data.shape[0]
+            img = torch.zeros(n, lay.D, device=dev)
+            img[:, real_d] = data[:, real_col].float() / 255
+            img[:, cat_d] = torch.einsum("bdc,dc->bd", data[:, cat_col].float().view(n, -1, 5), self.rep_w) + self.rep_b
+            h = (img * mask.float()).view(n, 1, 36, 36)
+            h = F.max_pool2d(F.relu(self.conv1(h)), 2)
+            h = F.max_pool2d(F.relu(self.conv2(h)), 2).reshape(n, -1)
+            h = F.relu(self.enc(h))
+            return self.mean(h), torch.clamp(self.logvar(h), -15.0, 15.0)
+
+        def decode(self, z):                                                       # :337-343
+            yv = self.deconv(self.y_layer(F.relu(self.dec(z))).view(-1, 32, 9, 9))
+            return yv.view(yv.shape[0], Y, -1).permute(0, 2, 1)                     # y_grouped: permuted view
+
+    net = Trunk().to(dev)
+    params = list(net.parameters()) + [s["z"], s["log_vy_real"]] + list(s["k0"].parameters()) + list(s["k1"].parameters())
+    opt = torch.optim.Adam(params, lr=1e-3)
+    P_b = s["n_subj"]
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        mu, lv = net.encode(s["data"], s["mask"])
+        zs = mu + torch.randn_like(mu) * torch.exp(0.5 * lv)                        # HLVAE.py:360-365
+        y = net.decode(zs)
+        W, b = th.pack_heads(net.obs_layer, hlay, Y)
+        theta = th.theta_heads(hlay, y, s["mask"], W, b)                            # HLVAE.py:344
+        vparam = lay.vparam(log_vy_real=s["log_vy_real"], conv=True)
+        out = loglik.fused_loglik(lay, s["data"], s["mask"], theta, vparam, monitor=True)
+        nll = -out["log_p_x_sum"] * (P_TOTAL / P_b)
+        kld, gm, gH = elbo.minibatch_KLD_upper_bound_iter(s["k0"], s["k1"], s["lik"], L, s["m"], s["H"], s["x"], mu, lv,
+                                                          s["z"], P_TOTAL, P_b, N_TOTAL, True, 2, EPS, layout=s["layout"])
+        loss = nll + kld
+        loss.backward()
+        opt.step()
+        m_new, H_new = elbo.natural_gradient_update(s["m"], s["H"], gm, gH, NG_LR)
+        s["m"].copy_(m_new)
+        s["H"].copy_(H_new)
+        return loss.detach()
+
+    for _ in range(max(args.warmup, 3)):
+        l0 = step()
+    torch.cuda.synchronize()
+    _lib.PROFILE = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    tc0 = time.perf_counter()
+    for _ in range(args.steps):
+        l1 = step()
+    enqueue_ms = (time.perf_counter() - tc0) * 1e3 / args.steps
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    per = {}
+    for name, a, c in _lib.PROFILE:
+        per[name] = per.get(name, 0.0) + a.elapsed_time(c) / args.steps
+    _lib.PROFILE = None
+    own = sum(per.values())
+    line = dict(metric="full train steps/sec (NN trunk + ELBO path + Adam)", value=1e3 / ms, unit="steps/s", n_gpus=1,
+                steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms, higher_is_better=True,
+                dtype="f32 trunk (stock PyTorch) + f64 KL + f32 likelihoods / heads", data="synthetic",
+                config=dict(workload=WORKLOAD + "; SURVEY 8(d) step rate (ii): conv encoder/decoder trunk (hidden 500, y_dim 5), "
+                                                "observation heads, fused likelihoods, KL + natural gradient, Adam; eager launches",
+                            rows_per_step=N_b),
+                host_enqueue_ms_per_step=enqueue_ms, own_kernels_ms_per_step=own, own_kernels_share=own / ms,
+                kernels_ms={k: round(v, 4) for k, v in per.items()}, loss_first=float(l0), loss_last=float(l1))
+    print(json.dumps(line), flush=True)
+
+
 def run_sweep(args):
     """BASELINE.json configs[2] and configs[3] as tables (not the headline line):
     (a) additive-kernel sweep - SE(time) + CA(id) + SE(age) x CA(sex), M in {32, 64, 128}, minibatch 4k / 16k / 64k
@@ -777,6 +892,9 @@ def main():
     args = parse()
     if args.workload == "predict" and args.impl != "reference":
         run_predict(args)
+        return
+    if args.workload == "full" and args.impl != "reference":
+        run_full(args)
         return
     if args.workload == "theta" and args.impl != "reference":
         run_theta(args)
