@@ -57,7 +57,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--eager", action="store_true", help="time eager launches instead of CUDA-graph replay")
     ap.add_argument("--no-overlap", action="store_true", help="single stream: no likelihood / KL overlap")
-    ap.add_argument("--workload", default="elbo", choices=["elbo", "predict", "sweep", "theta", "full"],
+    ap.add_argument("--workload", default="elbo", choices=["elbo", "predict", "sweep", "theta", "full", "norm"],
                     help="elbo: the BASELINE.json metric (default); predict: SURVEY 8(f) row 1, GP posterior-mean "
                          "prediction (utils.batch_predict_varying_T), its own JSON line")
     return ap.parse_args()
@@ -781,6 +781,53 @@ def run_full(args):
     print(json.dumps(line), flush=True)
 
 
+def run_norm(args):
+    """HL_VAE.utils.batch_normalization (HL_VAE/utils.py:88-143) on (a) the configs[3]
+    likelihood-heavy tabular batch (64 count + 64 ordinal(5) + 64 cat(5) + 32 real + 32 pos, 64 000 rows, float32 data,
+    uint8 mask) and (b) the configs[1] batch (16 000 rows, D4, convolutional: uint8 data and mask).  Device time of
+    the three launches and GB/s of algorithmic bytes (apply: data + mask in, X out; stats: the real / positive
+    columns + their mask columns, twice)."""
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    import __graft_entry__ as g
+    g.build()
+    from hlvae_b200 import _lib, normalize as nz, synth
+    hbm_peak, _ = measured_peaks()
+    rows = []
+    for tag, types, conv, N, ddt in (("configs[3] tabular", synth.TABULAR_TYPES, False, 64000, torch.float32),
+                                     ("configs[1] D4 conv", synth.HEALTHMNIST_D4_TYPES, True, 16000, torch.uint8)):
+        lay = nz.NormLayout(types, conv, dev)
+        gen = torch.Generator(device=dev).manual_seed(0)
+        data, mask = synth.device_likelihood_batch(lay.var, N, dev, gen, dtype=ddt, observed=0.7, pixel_like=conv)
+        for _ in range(max(args.warmup, 3)):
+            nz.normalize(lay, data, mask)
+        torch.cuda.synchronize()
+        _lib.PROFILE = []
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            X, mean, var = nz.normalize(lay, data, mask)
+        e1.record()
+        torch.cuda.synchronize()
+        per = {}
+        for name, a, c in _lib.PROFILE:
+            per.setdefault(name, []).append(a.elapsed_time(c))
+        _lib.PROFILE = None
+        dsz = data.element_size()
+        apply_bytes = N * (lay.var.E_x * dsz + lay.var.D + lay.var.E_x * 4)
+        stats_bytes = 2 * N * lay.n_stat * (dsz + 1)
+        t_apply = float(np.mean(per["hlvae_batch_norm_apply"]))
+        t_stats = float(np.sum(per.get("hlvae_batch_norm_stats", [0.0]))) / args.steps
+        rows.append(dict(case=tag, rows=N, E_x=lay.var.E_x, stat_vars=lay.n_stat, call_ms=e0.elapsed_time(e1) / args.steps,
+                         apply_ms=t_apply, apply_gbs=apply_bytes / t_apply / 1e6, apply_frac=apply_bytes / t_apply / 1e6 / hbm_peak,
+                         stats_ms_both_passes=t_stats, stats_gbs=(stats_bytes / t_stats / 1e6) if t_stats else None,
+                         checksum=float(torch.nan_to_num(X.double()).abs().sum())))
+    print(json.dumps(dict(workload="SURVEY 8(f).4: HL_VAE.utils.batch_normalization (hlvae_batch_norm_stats x2 + hlvae_batch_norm_apply)",
+                          hbm_peak_gbs=hbm_peak, steps=args.steps, cases=rows)), flush=True)
+
+
 def run_sweep(args):
     """BASELINE.json configs[2] and configs[3] as tables (not the headline line):
     (a) additive-kernel sweep - SE(time) + CA(id) + SE(age) x CA(sex), M in {32, 64, 128}, minibatch 4k / 16k / 64k
@@ -892,6 +939,9 @@ def main():
     args = parse()
     if args.workload == "predict" and args.impl != "reference":
         run_predict(args)
+        return
+    if args.workload == "norm" and args.impl != "reference":
+        run_norm(args)
         return
     if args.workload == "full" and args.impl != "reference":
         run_full(args)

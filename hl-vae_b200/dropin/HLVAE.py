@@ -5,6 +5,8 @@ resolves to the CUDA per-type likelihoods) and every name is passed through; the
   * `HLVAE.theta_estimation` (HLVAE.py:416-453)  -> hlvae_b200.theta.theta_estimation (one head kernel per
     direction instead of two einsum passes per type group + boolean-index scatters; same values and gradients
     for 0/1 masks), and
+  * the module-level `batch_normalization` the methods call (HLVAE.py:7,303,330,370; HL_VAE/utils.py:88-143)
+    -> hlvae_b200.normalize.batch_normalization (three streaming launches), and
   * `HLVAE.loglik_and_reconstruction` (HLVAE.py:381-414) -> hlvae_b200.loglik.loglik_and_reconstruction (all type
     groups in one launch) when `hlvae_b200.config.fused_loglik_method` is set - off by default because the fused
     method returns no `samples` (training.py never reads them; predict / test scripts may).
@@ -15,6 +17,7 @@ import sys
 
 from hlvae_b200 import config as _config
 from hlvae_b200.loglik import loglik_and_reconstruction as _fused_loglik_method
+from hlvae_b200.normalize import batch_normalization as _batch_normalization
 from hlvae_b200.theta import theta_estimation as _theta_estimation
 
 _here = os.path.dirname(os.path.abspath(__file__))
@@ -27,6 +30,9 @@ for _p in sys.path:
         for _k, _v in vars(_ref).items():
             if not _k.startswith("__"):
                 globals().setdefault(_k, _v)
+        # `from HL_VAE.utils import batch_normalization` (HLVAE.py:7) -> the module global the methods call
+        _ref.reference_batch_normalization = _ref.batch_normalization
+        _ref.batch_normalization = batch_normalization = _batch_normalization
         _ref.HLVAE.reference_theta_estimation = _ref.HLVAE.theta_estimation
         _ref.HLVAE.theta_estimation = _theta_estimation
         if getattr(_config, "fused_loglik_method", False):

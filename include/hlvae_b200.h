@@ -266,6 +266,29 @@ int hlvae_theta_bwd(int64_t N, int D, int P, int Y, int n_tiles, const int32_t* 
                     const void* y, int64_t sn, int64_t sd, int64_t sk, int dtype, const void* mask, int mask_dtype,
                     const void* g_theta, int64_t ld_theta, void* g_y, double* g_weight, double* g_bias, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * Batch normalisation of the data batch.  Replaces HL_VAE/utils.py:88-143
+ * `batch_normalization`: the encoder input X_list [N, E_x] and the normalisation parameters
+ * [mean, var] of the real (non-convolutional) and positive variables that loglik_real / loglik_pos take.
+ *   real, conv: observed / 255 (:99-103); real: (observed - mean) / sqrt(var + 1e-5) * mask with the masked
+ *   two-pass mean / variance (:104-108); count: log(observed), 0 where missing (:113-119); pos: the same
+ *   standardisation on log(1 + observed) (:120-131; the caller clamps the variance, :127); cat / ordinal /
+ *   other: data * mask (:132-140).
+ * hlvae_batch_norm_stats: pass 0 accumulates stats[0][d] += sum_n mask, stats[1][d] += sum_n value * mask;
+ *   pass 1 (after pass 0 of ALL rows) stats[2][d] += sum_n ((value - mean) * mask)^2, for the variables listed
+ *   in stat_vars[n_stat].  stats [3, D] float64, caller zero-fills.
+ * hlvae_batch_norm_apply: out [N, E_x] (storage `dtype`) from data, mask and meanvar [2, D] float64
+ *   (mean; variance as used at :108 / :128, i.e. already clamped for positive variables);
+ *   dcol_var [E_x] = variable of each data column.
+ * data [N, E_x]: `data_dtype` = dtype or HLVAE_U8; mask [N, D]: `mask_dtype` = dtype or HLVAE_U8.
+ * ---------------------------------------------------------------------------------- */
+int hlvae_batch_norm_stats(int64_t N, int D, int64_t ld_data, const int32_t* var_kind, const int32_t* var_dcol,
+                           const int32_t* stat_vars, int n_stat, const void* data, const void* mask, int dtype,
+                           int data_dtype, int mask_dtype, int pass, double* stats, void* stream);
+int hlvae_batch_norm_apply(int64_t N, int D, int64_t ld_data, const int32_t* var_kind, const int32_t* dcol_var,
+                           const void* data, const void* mask, int dtype, int data_dtype, int mask_dtype, int conv,
+                           const double* meanvar, void* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

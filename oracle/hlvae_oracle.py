@@ -565,9 +565,6 @@ def batch_norm_params(descs: List[VarDesc], data, mask):
 
 
 # --------------------------------------------------------------------------------------
-# One ELBO-path step (training.py:83,104-137): used by the CPU baseline in bench.py
-# --------------------------------------------------------------------------------------
-# --------------------------------------------------------------------------------------
 # Observation heads: y -> theta (HLVAE.py:11-89, 416-453), SURVEY.md 8(f) row 2
 # --------------------------------------------------------------------------------------
 def head_forward(kind: str, prm: Dict[str, torch.Tensor], gamma: torch.Tensor) -> torch.Tensor:
@@ -623,6 +620,46 @@ def theta_estimation(types: Sequence[Tuple[str, int]], heads: List[Dict[str, tor
     return theta
 
 
+def batch_normalization(descs: List[VarDesc], data, mask, conv=False):
+    """HL_VAE/utils.py:88-143 on the packed layout: the encoder's input X_list [N, E_x] and the normalisation
+    parameters (norm_real, norm_pos), each (mean [D_g], var [D_g]) or None.
+    real: conv -> observed / 255, no parameters (:99-103); else masked mean / variance and
+    (observed - mean) / sqrt(var + 1e-5) * mask (:104-108).  count: log of the observed value, 0 where missing
+    (:113-119).  pos: the same standardisation on log(1 + observed), variance clamped to [1e-6, 1e20] (:120-131).
+    cat / ordinal: data times the mask repeated per class (:132-138)."""
+    out = torch.zeros_like(data)
+    params = {'real': None, 'pos': None}
+    for kind in ('real', 'pos'):
+        js = [j for j, v in enumerate(descs) if v.kind == kind]
+        if not js:
+            continue
+        dc = [descs[j].data_col for j in js]
+        mk = mask[:, js]
+        obs = data[:, dc] * mk
+        if kind == 'real' and conv:
+            out[:, dc] = obs / 255
+            continue
+        if kind == 'pos':
+            obs = torch.log(1.0 + obs)
+        mean = (obs * mk).sum(0) / mk.sum(0)
+        var = (((obs - mean) * mk) ** 2).sum(0) / mk.sum(0)
+        if kind == 'pos':
+            var = torch.clamp(var, 1e-6, 1e20)
+        out[:, dc] = (obs - mean[None, :]) / torch.sqrt(var + 1e-5) * mk
+        params[kind] = (mean, var)
+    for j, v in enumerate(descs):
+        c0 = v.data_col
+        if v.kind == 'count':
+            aux = torch.log(data[:, c0] * mask[:, j])
+            out[:, c0] = torch.where(mask[:, j] == 0, torch.zeros_like(aux), aux)
+        elif v.kind in ('cat', 'ordinal'):
+            out[:, c0:c0 + v.nclass] = data[:, c0:c0 + v.nclass] * mask[:, j:j + 1]
+    return out, params['real'], params['pos']
+
+
+# --------------------------------------------------------------------------------------
+# One ELBO-path step (training.py:83,104-137): used by the CPU baseline in bench.py
+# --------------------------------------------------------------------------------------
 def elbo_path_step(state: dict, natural_gradient_lr=0.01) -> Dict[str, torch.Tensor]:
     """nll + KL forward, backward to (theta, mu, log_v, Z, kernel raw parameters, log_vy),
     natural-gradient update of (m, H).  `state` holds every tensor of one minibatch."""

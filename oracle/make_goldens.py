@@ -341,6 +341,39 @@ def theta_cases():
     theta_case("theta_conv_d4", synth.HEALTHMNIST_D4_TYPES, N=3, seed=23, conv=True, observed=0.75)
 
 
+# ------------------------------------------------------------------ batch normalisation
+def norm_case(name, types, N, seed, conv=False, observed=0.7):
+    """HL_VAE.utils.batch_normalization of the unmodified reference (HL_VAE/utils.py:88-143)."""
+    from HL_VAE.utils import batch_normalization as ref_bn  # reference
+    rng = np.random.default_rng(seed)
+    data, mask = synth.likelihood_batch(types, N, rng, observed=observed, pixel_like=conv)
+    tinfo = orc.types_info_from_layout(types, conv=conv)
+    descs, E_x, P_th = orc.build_layout(types)
+    X, norm = ref_bn(data, mask, torch.ones(N, P_th, dtype=DT), tinfo)
+    Xo, nr, npos = orc.batch_normalization(descs, data, mask, conv)
+    w = [check(name + ".X", Xo, X, 1e-14)]
+    for tag, mine, ref in (("real", nr, norm[0]), ("pos", npos, norm[1])):
+        assert (mine is None) == (ref == []), name + ": parameter presence differs for " + tag
+        if mine is not None:
+            w.append(check(f"{name}.{tag}_mean", mine[0], ref[0], 1e-14))
+            w.append(check(f"{name}.{tag}_var", mine[1], ref[1], 1e-14))
+    z = lambda t: np.zeros(0) if t is None else t.detach().numpy()
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), types=np.array([f"{k}:{c}" for k, c in types]), conv=int(conv),
+                        data=data.numpy(), mask=mask.numpy(), X=X.numpy(),
+                        real_mean=z(nr[0] if nr else None), real_var=z(nr[1] if nr else None),
+                        pos_mean=z(npos[0] if npos else None), pos_var=z(npos[1] if npos else None))
+    print(f"  {name}: N={N} D={len(types)} E_x={E_x} worst rel diff {max(w):.2e}")
+
+
+def norm_cases():
+    print("batch normalisation: oracle vs unmodified reference")
+    rng = np.random.default_rng(31)
+    norm_case("norm_mixed", synth.mixed_types(rng, 24), N=40, seed=31)
+    norm_case("norm_tabular_small", [('count', 1)] * 3 + [('ordinal', 5)] * 3 + [('cat', 5)] * 3 + [('real', 1)] * 2 +
+              [('pos', 1)] * 2, N=16, seed=32)
+    norm_case("norm_conv_d4", synth.HEALTHMNIST_D4_TYPES, N=3, seed=33, conv=True, observed=0.75)
+
+
 # ------------------------------------------------------------------ GP posterior-mean prediction
 def predict_case(name, kargs, L, M, n_subj, T, ragged, seed, n_test_subj=3, continuous_age=False):
     """utils.batch_predict_varying_T (and, with equal T, utils.batch_predict) of the unmodified reference.
@@ -453,6 +486,9 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "predict":      # only the prediction fixtures
         predict_cases()
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "norm":         # only the batch-normalisation fixtures
+        norm_cases()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "theta":        # only the observation-head fixtures
         theta_cases()
         return
@@ -477,6 +513,7 @@ def main():
     loglik_case("loglik_conv_d4", synth.HEALTHMNIST_D4_TYPES, N=3, seed=13, conv=True, observed=0.75)
     predict_cases()
     theta_cases()
+    norm_cases()
     print("all oracle-vs-reference checks passed; goldens written to", GOLD)
 
 

@@ -22,6 +22,7 @@ KL_CASES = ["kl_default_ragged", "kl_default_fixedT", "kl_sweep_ragged", "kl_mas
             "kl_not_natgrad", "kl_shuffled_rows", "kl_T32_M40"]
 LOGLIK_CASES = ["loglik_mixed", "loglik_tabular_small", "loglik_conv_d4"]
 THETA_CASES = ["theta_mixed", "theta_tabular_small", "theta_conv_d4"]
+NORM_CASES = ["norm_mixed", "norm_tabular_small", "norm_conv_d4"]
 
 
 def load(name):

@@ -23,6 +23,8 @@ assert training.__file__.startswith(ref)                                        
 from hlvae_b200 import theta as TH
 assert "dropin" in HLVAE.__file__ and HLVAE.HLVAE.__module__ == "_hlvae_reference_HLVAE"   # reference class, passed through
 assert HLVAE.HLVAE.theta_estimation is TH.theta_estimation and HLVAE.Observation_Cat.__module__ == "_hlvae_reference_HLVAE"
+from hlvae_b200 import normalize as NZ
+assert HLVAE.HLVAE.forward.__globals__["batch_normalization"] is NZ.batch_normalization
 assert HLVAE.HLVAE.encode.__module__ == "_hlvae_reference_HLVAE" and callable(HLVAE.HLVAE.reference_theta_estimation)
 assert training.minibatch_KLD_upper_bound is E.minibatch_KLD_upper_bound
 assert training.minibatch_KLD_upper_bound_iter is E.minibatch_KLD_upper_bound_iter

@@ -136,3 +136,17 @@ def test_packed_head_form_equals_reference(name):
     vp = lay.var_pcol.tolist()
     assert tv[0] == 0 and tv[-1] == lay.D and all(a < c for a, c in zip(tv, tv[1:]))
     assert all(vp[c] - vp[a] <= th.MAX_TILE and c - a <= th.MAX_TILE for a, c in zip(tv, tv[1:]))
+
+
+@pytest.mark.parametrize("name", h.NORM_CASES)
+def test_oracle_batch_normalization_matches_reference_goldens(name):
+    """HL_VAE.utils.batch_normalization (HL_VAE/utils.py:88-143): oracle restatement vs the unmodified reference."""
+    g = h.load(name)
+    types, conv = h.parse_types(g), bool(int(g["conv"]))
+    descs, _, _ = orc.build_layout(types)
+    X, nr, npos = orc.batch_normalization(descs, h.t(g["data"]), h.t(g["mask"]), conv)
+    assert h.rel_err(X, g["X"]) < 1e-14
+    for tag, mine in (("real", nr), ("pos", npos)):
+        assert (mine is None) == (g[tag + "_mean"].size == 0)
+        if mine is not None:
+            assert h.rel_err(mine[0], g[tag + "_mean"]) < 1e-14 and h.rel_err(mine[1], g[tag + "_var"]) < 1e-14
