@@ -149,6 +149,10 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                  : "d"(a), "d"(b));
 }
 
+__device__ __forceinline__ void prefetch_l1(const void* p) {
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
+
 template <typename T>
 __device__ __forceinline__ double ld_as_double(const void* p, int64_t i) {
     return (double)reinterpret_cast<const T*>(p)[i];

@@ -485,6 +485,8 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
     if (tid == 0) meta[2] = s_begin;
     __syncthreads();
     const double wm = ws[em];
+    const int chunk_row_end = subj_ptr[s_end];
+    const int chunk_tt_end = tt_ptr[s_end];
 
     while (true) {
         // ---- P0: pack whole subjects into a panel of at most RP rows
@@ -522,6 +524,18 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
         const int R = sub_r0[nsub];
         const int R8 = (R + 7) & ~7;
         const int pr0 = subj_ptr[s_first];
+        // look-ahead: the rows and B^-1 blocks the NEXT panel will gather (about the same amount as this one) are
+        // pulled into L1 while this panel computes, so that the set-up above stops waiting on L2 / HBM
+        int pf_g = -1, pf_b = -1;
+        {
+            const int s_next = meta[2];
+            if (s_next < s_end) {
+                const int prn = subj_ptr[s_next];
+                if (tid < RP && prn + tid < chunk_row_end) pf_g = row_idx[prn + tid];
+                const int b0 = tt_ptr[s_next] + tid * 16;          // one 128-byte line per thread
+                if (tid < RP * HLVAE_TMAX / 16 && b0 < chunk_tt_end) pf_b = b0;
+            }
+        }
         if (tid < R) {
             int k = 0;
             while (tid >= sub_r0[k + 1]) k++;
@@ -601,6 +615,11 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
                 if (row < R8) Kb[row * LD + em] = (row < R) ? kacc[k] : 0.0;
             }
         }
+        if (pf_g >= 0) {
+            prefetch_l1(x + (int64_t)pf_g * ldx);
+            prefetch_l1(mu + (int64_t)pf_g * ld_mu + l);
+        }
+        if (pf_b >= 0) prefetch_l1(binv + (int64_t)l * tt_total + pf_b);
         __syncthreads();
 
         // ---- P2: V = B^-1 K0xz (block diagonal, :160 / :254) on the FP64 tensor pipe, k-range
@@ -653,6 +672,20 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
             a_acc = fma(rv[tid], a, a_acc);
             g_mu[(int64_t)grow[tid] * L + l] = (TS)(-a * gscale);
         }
+        // p = sum_r V[r] mu_r (:188 / :265) and dJ/dw = K0xz^T rho = V^T r (B^-1 is symmetric): per-thread partial
+        // sums over this thread's rows, kept over the CTA's whole chunk; they need only V, mu and r, so they share this
+        // barrier interval with rho and the S update instead of a serial two-warp phase of their own
+        if (em < M) {
+#pragma unroll
+            for (int k = 0; k < RPT; k++) {
+                const int row = eg + k * NGRP;
+                if (row < R) {
+                    const double v = Vb[row * LD + em];
+                    p_acc = fma(v, mus[row], p_acc);
+                    gw_acc = fma(v, rv[row], gw_acc);
+                }
+            }
+        }
         // ---- P3b: S += K0xz^T V on the FP64 tensor pipe (:161 / :254,266)
         {
             const int R4 = (R + 3) & ~3;
@@ -668,17 +701,6 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
 #pragma unroll
                     for (int b = 0; b < SIC; b++) dmma884(sacc[a][b][0], sacc[a][b][1], af[a], bf[b]);
             }
-        }
-        __syncthreads();
-        // p (:188 / :265) and dJ/dw need rho: column sums over the panel rows
-        if (tid < MP) {
-            double pa = 0.0, ga = 0.0;
-            for (int r = 0; r < R; r++) {
-                pa = fma(Vb[r * LD + tid], mus[r], pa);
-                ga = fma(Kb[r * LD + tid], rho[r], ga);
-            }
-            p_acc += pa;
-            gw_acc += ga;
         }
         __syncthreads();
 
@@ -931,9 +953,20 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
                     if (j + 1 < M) atomicAdd(Sg + (int64_t)i * M + j + 1, sacc[a][b][1]);
                 }
             }
+        // every row group holds a partial sum of its inducing point: summed in a fixed order through shared memory
+        // (the row panels are free by now), then one atomic per inducing point and CTA
+        Kb[eg * MP + em] = p_acc;
+        Vb[eg * MP + em] = gw_acc;
+        __syncthreads();
         if (tid < M) {
-            atomicAdd(acc + off.o[HLVAE_ACC_P] + (int64_t)l * M + tid, p_acc);
-            atomicAdd(acc + off.o[HLVAE_ACC_GW] + (int64_t)l * M + tid, gw_acc);
+            double pa = 0.0, ga = 0.0;
+#pragma unroll
+            for (int g2 = 0; g2 < NGRP; g2++) {
+                pa += Kb[g2 * MP + tid];
+                ga += Vb[g2 * MP + tid];
+            }
+            atomicAdd(acc + off.o[HLVAE_ACC_P] + (int64_t)l * M + tid, pa);
+            atomicAdd(acc + off.o[HLVAE_ACC_GW] + (int64_t)l * M + tid, ga);
         }
         a_acc = warp_sum(a_acc);
         if (lane == 0 && a_acc != 0.0) atomicAdd(&hyp[4 * HLVAE_MAX_COMPS], a_acc);
