@@ -32,6 +32,7 @@ class _Positive(nn.Module):
 
     def __init__(self, lower_bound=0.0):
         super().__init__()
+        self.lower_bound_value = float(lower_bound)      # host copy: the per-step path must not read the device
         self.register_buffer("lower_bound", torch.as_tensor(float(lower_bound)))
         self.register_buffer("upper_bound", torch.as_tensor(math.inf))
 
@@ -168,6 +169,7 @@ class FlatSpec:
 
     def __init__(self):
         self.cspec = _lib.KSpec()
+        self.lb_cache = {}        # device copies of non-zero constraint lower bounds (owned by the kernel module)
         self.scale_mods = []      # ScaleKernel or None (unit scale)
         self.rbf_mods = []        # RBFKernel or None
 
@@ -191,16 +193,32 @@ class FlatSpec:
         return L
 
     def constrained(self, L, device, dtype=torch.float64):
-        """(outputscale, lengthscale) each [ncomp, L], attached to autograd."""
-        os_rows, ls_rows = [], []
-        one = torch.ones(L, dtype=dtype, device=device)
-        for sm, rm in zip(self.scale_mods, self.rbf_mods):
-            os_rows.append(one if sm is None else sm.outputscale.to(dtype).reshape(-1).expand(L))
-            ls_rows.append(one if rm is None else rm.lengthscale.to(dtype).reshape(-1).expand(L))
-        if not os_rows:
+        """(outputscale, lengthscale) each [ncomp, L], attached to autograd.  The raw parameters of all components
+        go through ONE softplus per kind (stack -> softplus -> + lower bounds) instead of one per module: the same
+        values bit for bit, a dozen fewer launches per step in front of the KL kernels."""
+        if not self.scale_mods:
             z = torch.zeros(0, L, dtype=dtype, device=device)
             return z, z
-        return torch.stack(os_rows).contiguous(), torch.stack(ls_rows).contiguous()
+        return (self._constrained_rows(self.scale_mods, "raw_outputscale", L, device, dtype),
+                self._constrained_rows(self.rbf_mods, "raw_lengthscale", L, device, dtype))
+
+    def _constrained_rows(self, mods, raw_name, L, device, dtype):
+        live = [i for i, m in enumerate(mods) if m is not None]
+        if not live:
+            return torch.ones(len(mods), L, dtype=dtype, device=device)
+        raws = torch.stack([getattr(mods[i], raw_name).to(dtype).reshape(-1).expand(L) for i in live])
+        vals = F.softplus(raws)
+        lbs = [getattr(mods[i], raw_name + "_constraint").lower_bound_value for i in live]   # fixed at construction
+        if any(v != 0.0 for v in lbs):
+            key = (raw_name, str(device), dtype, tuple(lbs))
+            if key not in self.lb_cache:
+                self.lb_cache[key] = torch.tensor(lbs, dtype=dtype, device=device).reshape(-1, 1)
+            vals = vals + self.lb_cache[key]
+        if len(live) == len(mods):
+            return vals.contiguous()
+        one = torch.ones(L, dtype=dtype, device=device)       # components without this parameter: unit rows
+        pos = {i: j for j, i in enumerate(live)}              # (no device index tensors: the step is graph-captured)
+        return torch.stack([vals[pos[i]] if i in pos else one for i in range(len(mods))]).contiguous()
 
 
 def _flatten_product(k, factors):
@@ -240,6 +258,7 @@ def compile_spec(kernel) -> FlatSpec:
         fs.scale_mods.append(scale)
         fs.rbf_mods.append(rbf)
     fs.cspec.ncomp = len(terms)
+    fs.lb_cache = kernel.__dict__.setdefault("_hlvae_lb_cache", {})
     return fs
 
 
