@@ -69,6 +69,35 @@ __device__ __forceinline__ double exp_nonpos(double x) {
     return p * __hiloint2double((k + 1023) << 20, 0);        // k >= -1022 here
 }
 
+// Table-driven variant for the kernels that can afford 512 bytes of shared memory: x = (64 k + j) ln2 / 64 + r with
+// |r| <= ln2 / 128, exp(x) = 2^k * T[j] * (1 + r + r^2/2 + ... + r^5/120), T[j] = 2^(j/64) from `tab` (filled by
+// exp2_table_fill).  The series needs 5 dependent DFMAs instead of 2 x 7 and the table entry is only needed by the
+// last operation, so its shared-memory latency hides behind the polynomial.  Truncation r^6/720 < 4e-17 relative;
+// error <= ~1.5 ulp like exp_nonpos.
+constexpr int HLVAE_EXP_TAB = 64;
+
+__device__ __forceinline__ void exp2_table_fill(double* __restrict__ tab, int tid, int nthreads) {
+    for (int j = tid; j < HLVAE_EXP_TAB; j += nthreads) tab[j] = exp2((double)j / HLVAE_EXP_TAB);
+}
+
+__device__ __forceinline__ double exp_nonpos_tab(double x, const double* __restrict__ tab) {
+    x = fmax(x, -708.0);
+    const double MAGIC = 6755399441055744.0;                 // 1.5 * 2^52
+    const double t = fma(x, 64.0 * 1.4426950408889634074, MAGIC);
+    const int n = __double2loint(t);                         // round(x * 64 / ln2) = 64 k + j
+    const double nf = t - MAGIC;
+    double r = fma(nf, -6.93147180369123816490e-01 / 64.0, x);       // (ln2 high part) / 64: exact scaling
+    r = fma(nf, -1.90821492927058770002e-10 / 64.0, r);
+    const double s = tab[n & (HLVAE_EXP_TAB - 1)];
+    const int k = n >> 6;                                    // arithmetic shift = floor(n / 64)
+    double p = fma(r, 1.0 / 120.0, 1.0 / 24.0);
+    p = fma(p, r, 1.0 / 6.0);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p *= r;                                                  // exp(r) - 1
+    return fma(s, p, s) * __hiloint2double((k + 1023) << 20, 0);     // k >= -1022 here
+}
+
 // Discrete factors of one component: CatKernel (kernel_spec.py:26-32) and BinKernel
 // (kernel_spec.py:9-23); true when every factor equals 1.
 __device__ __forceinline__ bool disc_match(const hlvae_comp_t& c, const double* __restrict__ xa,

@@ -69,7 +69,7 @@ struct CompRegs {
     }
     // unscaled value of the component at rows (xa, xb) of one covariate matrix; d = xa - xb on its SE column
     __device__ __forceinline__ double value(const double* __restrict__ xa, const double* __restrict__ xb, double hil2,
-                                            double& d) const {
+                                            double& d, const double* __restrict__ etab) const {
         d = 0.0;
         bool ok = true;
 #pragma unroll
@@ -81,7 +81,7 @@ struct CompRegs {
         if (!ok) return 0.0;
         if (se_col < 0) return 1.0;
         d = xa[se_col] - xb[se_col];
-        return exp_nonpos(-(d * d) * hil2);
+        return exp_nonpos_tab(-(d * d) * hil2, etab);
     }
 };
 
@@ -102,12 +102,15 @@ kl_subject_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ldt = tcap | 1;
     const int per_warp = tcap * Q + 3 * tcap * ldt + SJ_KP;
-    double* xs = smem + (size_t)warp * per_warp;
+    double* etab = smem;                                   // 2^(j/64), shared by the CTA's warps
+    double* xs = smem + HLVAE_EXP_TAB + (size_t)warp * per_warp;
     double* Bw = xs + tcap * Q;
     double* Bi = Bw + tcap * ldt;
     double* Ks = Bi + tcap * ldt;
     double* kp = Ks + tcap * ldt;           // [0..8) os0, [8..16) hil2_0, [16..24) il3_0, [24..48) same for K1
 
+    exp2_table_fill(etab, threadIdx.x, SJ_WARPS * 32);
+    __syncthreads();
     const int64_t pair = (int64_t)blockIdx.x * SJ_WARPS + warp;
     if (pair >= (int64_t)n_subj * L) return;
     const int s = (int)(pair / L), l = (int)(pair % L);
@@ -156,7 +159,7 @@ kl_subject_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict
                 CompRegs c;
                 c.load(sp1, r);
                 double d;
-                k1 = fma(kp[24 + r], c.value(xs + i * Q, xs + j * Q, kp[32 + r], d), k1);
+                k1 = fma(kp[24 + r], c.value(xs + i * Q, xs + j * Q, kp[32 + r], d, etab), k1);
             }
             Bw[i * ldt + j] = k1;
             Bw[j * ldt + i] = k1;
@@ -245,7 +248,7 @@ kl_subject_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict
         for (int t = lane; t < TL; t += 32, ix.advance32()) {
             const int i = ix.i, j = ix.j;
             double d;
-            const double v = c.value(xs + i * Q, xs + j * Q, hil2, d);
+            const double v = c.value(xs + i * Q, xs + j * Q, hil2, d, etab);
             const double wv = ((i == j) ? 1.0 : 2.0) * Bw[i * ldt + j] * v;
             gos += wv;
             gls = fma(wv * d, d, gls);
@@ -334,7 +337,7 @@ kl_subject_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict
         for (int t = lane; t < TL; t += 32, ix.advance32()) {
             const int i = ix.i, j = ix.j;
             double d;
-            const double gv = Ks[i * ldt + j] * c.value(xs + i * Q, xs + j * Q, hil2, d);
+            const double gv = Ks[i * ldt + j] * c.value(xs + i * Q, xs + j * Q, hil2, d, etab);
             gos += gv;
             gls = fma(gv * d, d, gls);
         }
@@ -368,7 +371,8 @@ struct PanelSmem {
                                       2 * (size_t)RP * LD /*Kb,Vb*/ + (size_t)RP * LDB /*Bp*/ +
                                       (size_t)RP * HLVAE_MAX_Q /*xs*/ + 3 * RP /*mus, rv, rho*/ +
                                       (size_t)MP * HLVAE_MAX_COMPS /*zacc*/ + 4 * HLVAE_MAX_COMPS + 8 /*hyper acc + A*/ +
-                                      8 * HLVAE_MAX_COMPS /*kps, kps1*/ + (size_t)PN_NCACHE * RP * MP /*vc*/;
+                                      8 * HLVAE_MAX_COMPS /*kps, kps1*/ + (size_t)PN_NCACHE * RP * MP /*vc*/ +
+                                      HLVAE_EXP_TAB /*etab*/;
     static constexpr size_t ints = 2 * RP + 3 * (PN_SMAX + 1) + 8;
     static constexpr size_t bytes = doubles * 8 + ints * 4;
 };
@@ -413,7 +417,8 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
     double* kps = hyp + 4 * HLVAE_MAX_COMPS + 8;               // K0 hyper-parameters by component: os, hil2, il2, il3
     double* kps1 = kps + 4 * HLVAE_MAX_COMPS;                  // same for K1
     double* vc = kps1 + 4 * HLVAE_MAX_COMPS;                   // [PN_NCACHE][RP][MP] unscaled component values (0 = no match)
-    int* grow = reinterpret_cast<int*>(vc + PN_NCACHE * RP * MP);
+    double* etab = vc + PN_NCACHE * RP * MP;                   // 2^(j/64) for exp_nonpos_tab
+    int* grow = reinterpret_cast<int*>(etab + HLVAE_EXP_TAB);
     int* sub_of_row = grow + RP;
     int* sub_r0 = sub_of_row + RP;                             // [PN_SMAX+1]
     int* sub_b0 = sub_r0 + PN_SMAX + 1;                        // [PN_SMAX+1] offsets of the T x T blocks
@@ -434,6 +439,7 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
         Zs[e] = (q < Q && m < M) ? z[((int64_t)l * M + m) * Q + q] : 0.0;
     }
     for (int m = tid; m < MP; m += PN_THREADS) ws[m] = (m < M) ? w[(int64_t)l * M + m] : 0.0;
+    exp2_table_fill(etab, tid, PN_THREADS);
     if (G_SMEM) {
         for (int e = tid; e < MP * LD; e += PN_THREADS) {
             int i = e / LD, j = e % LD;
@@ -598,7 +604,7 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
                         ok = ok && (nd < 2 || (cat1 ? (a1 == zd[1]) : (a1 + zd[1] == 2.0)));
                         ok = ok && (nd < 3 || (cat2 ? (a2 == zd[2]) : (a2 + zd[2] == 2.0)));
                         const double d = xr[sc] - zse;
-                        const double e_ = has_se ? exp_nonpos(-(d * d) * hil2) : 1.0;
+                        const double e_ = has_se ? exp_nonpos_tab(-(d * d) * hil2, etab) : 1.0;
                         vv[k] = ok ? e_ : 0.0;
                     }
 #pragma unroll
@@ -846,7 +852,7 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
                                     double v = 1.0, d = 0.0;
                                     if (c.se_col >= 0) {
                                         d = xr[c.se_col] - zse;
-                                        v = exp_nonpos(-(d * d) * hil2);
+                                        v = exp_nonpos_tab(-(d * d) * hil2, etab);
                                     }
                                     const double gkv = gk[k] * v;
                                     const double t = gkv * d;
@@ -906,7 +912,7 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
                         double v = 1.0, d = 0.0;
                         if (c.se_col >= 0) {
                             d = xi[c.se_col] - xj[c.se_col];
-                            v = exp_nonpos(-(d * d) * hil2);
+                            v = exp_nonpos_tab(-(d * d) * hil2, etab);
                         }
                         const double gv = g * v;
                         gos += gv;
@@ -1073,7 +1079,7 @@ extern "C" int hlvae_kl_subject(const hlvae_kspec_t* spec0, const double* os0, c
     AccOff off;
     fill_offsets(L, M, Q, off.o);
     const int ldt = t_cap | 1;
-    size_t smem = (size_t)SJ_WARPS * ((size_t)t_cap * Q + 3 * (size_t)t_cap * ldt + SJ_KP) * sizeof(double);
+    size_t smem = ((size_t)SJ_WARPS * ((size_t)t_cap * Q + 3 * (size_t)t_cap * ldt + SJ_KP) + HLVAE_EXP_TAB) * sizeof(double);
     int64_t pairs = (int64_t)n_subj * L;
     unsigned grid = (unsigned)((pairs + SJ_WARPS - 1) / SJ_WARPS);
     cudaStream_t st = (cudaStream_t)stream;
