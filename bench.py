@@ -41,6 +41,7 @@ sys.path.insert(0, ROOT)
 
 L, M, Q, T = 32, 64, 6, 20
 SUBJ_PER_RANK = 800
+SUBJECT_CTAS_PER_SM = 0
 P_TOTAL, N_TOTAL = 5000, 100000            # ~100k-sample dataset of configs[1]
 EPS, NG_LR = 1e-6, 0.01
 WORKLOAD = "configs[1]: synthetic HealthMNIST-shaped, L=32, M=64, 800 subjects x T=20 = 16000 rows/step, D4 (324 real + 972 cat x5)"
@@ -57,6 +58,9 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--eager", action="store_true", help="time eager launches instead of CUDA-graph replay")
     ap.add_argument("--no-overlap", action="store_true", help="single stream: no likelihood / KL overlap")
+    ap.add_argument("--no-split-backward", action="store_true", help="one backward() of nll + kld instead of one per branch")
+    ap.add_argument("--subject-ctas", type=int, default=SUBJECT_CTAS_PER_SM,
+                    help="resident hlvae_kl_subject CTAs per SM (0: unlimited); leaves room for the likelihood kernels")
     ap.add_argument("--workload", default="elbo", choices=["elbo", "predict", "sweep", "theta", "full", "norm"],
                     help="elbo: the BASELINE.json metric (default); predict: SURVEY 8(f) row 1, GP posterior-mean "
                          "prediction (utils.batch_predict_varying_T), its own JSON line")
@@ -238,6 +242,9 @@ def elbo_step(s, world, inp=None):
     # stream next to the HBM-bound likelihood kernels; autograd replays each branch on its own stream.
     cur = torch.cuda.current_stream()
     side = s.get("side")
+    # net_loss = nll + kld (training.py:124) has two branches with disjoint leaves: backward() per branch gives the same
+    # gradients and lets the likelihood backward kernel run next to the KL forward kernels instead of after them
+    split = side is not None and s.get("split_backward", True)
     if side is not None:
         side.wait_stream(cur)
     with torch.cuda.stream(side if side is not None else cur):
@@ -245,15 +252,20 @@ def elbo_step(s, world, inp=None):
                                                           inp["mu"], inp["lv"], s["z"], P_TOTAL, P_b, N_TOTAL, True,
                                                           2, EPS, layout=s["layout"])            # training.py:110-113
         m_new, H_new = elbo.natural_gradient_update(s["m"], s["H"], gm, gH, NG_LR)             # :130-137
+        if split:
+            kld.backward()
     vparam = s["lay"].vparam(log_vy_real=s["log_vy_real"], conv=True)
     out = loglik.fused_loglik(s["lay"], inp["data"], inp["mask"], inp["theta"], vparam, monitor=True)
     nll = -out["log_p_x_sum"] * (P_TOTAL / P_b)                                             # training.py:83,104,122
+    if split:
+        nll.backward()
     if side is not None:
         cur.wait_stream(side)
         for t_ in (kld, m_new, H_new):      # allocated on the side stream, consumed on this one
             t_.record_stream(cur)
     loss = nll + kld                                                                           # :124
-    loss.backward()                                                                            # :127
+    if not split:
+        loss.backward()                                                                        # :127
     s["m"].copy_(m_new)
     s["H"].copy_(H_new)
     return loss.detach()
@@ -306,7 +318,10 @@ def run_gpu(args):
     config.check_errors = False              # keep the timed step free of host syncs
     s = build_gpu_state(dev, args.subjects, rank)
     s["side"] = None if args.no_overlap else torch.cuda.Stream()
+    s["split_backward"] = not args.no_split_backward
     config.overlap = not args.no_overlap
+    from hlvae_b200 import _lib as _l
+    _l.check(_l.lib().hlvae_set_subject_ctas_per_sm(int(args.subject_ctas)), "hlvae_set_subject_ctas_per_sm")
     n_rows = s["N_b"]
     algorithmic_work(n_rows, args.subjects)
     fp64_peak = measure_fp64_peak(dev)       # before any graph capture (uses the RNG)
@@ -499,7 +514,8 @@ def run_gpu(args):
                                 parallelism=f"dp{world}: subjects sharded, one all-reduce of accumulators" if world > 1 else "single GPU"),
                     clocks=sampler.summary(), e2e=e2e, gpu_launches=launches, roofline=roof, cpu_baseline=cpu,
                     kernels=kern, fp64_peak_tflops=fp64_peak, cuda_graph=use_graph, eager_ms_per_step=eager_ms,
-                    overlap=not args.no_overlap,
+                    overlap=not args.no_overlap, split_backward=not args.no_split_backward,
+                    subject_ctas_per_sm=int(args.subject_ctas),
                     kernel_timing="CUDA events around every C-ABI call in an eager, single-stream pass of the same "
                                   "step run right after the timed region (events are not readable inside a replayed "
                                   "graph; the timed region overlaps the KL branch with the likelihood kernels)")

@@ -43,6 +43,7 @@ _SIGS = {
     "hlvae_kernel_eval_bwd": ([C.POINTER(KSpec), _P, _P, _I, _I, _P, _I, _L, _L, _P, _I, _L, _L, _P, _P, _P, _P, _P, _P], _I),
     "hlvae_subject_matvec": ([C.POINTER(KSpec), _P, _P, _I, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P], _I),
     "hlvae_kl_acc_layout": ([_I, _I, _I, C.POINTER(_L)], _I),
+    "hlvae_set_subject_ctas_per_sm": ([_I], _I),
     "hlvae_kl_subject": ([C.POINTER(KSpec), _P, _P, C.POINTER(KSpec), _P, _P, _P, _I, _I, _P, _L, _P, _P, _P, _I, _I,
                           _P, _L, _I, _P, _L, _P, _I, _P, _D, _P, _P], _I),
     "hlvae_kl_panel": ([C.POINTER(KSpec), _P, _P, C.POINTER(KSpec), _P, _P, _I, _I, _I, _P, _L, _P, _P, _P, _P, _I, _I,

@@ -111,15 +111,17 @@ kl_subject_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict
 
     exp2_table_fill(etab, threadIdx.x, SJ_WARPS * 32);
     __syncthreads();
-    const int64_t pair = (int64_t)blockIdx.x * SJ_WARPS + warp;
-    if (pair >= (int64_t)n_subj * L) return;
+    // grid = one warp per (subject, latent dim) pair, or - when the host caps the CTAs per SM so that the HBM-bound
+    // likelihood kernels can share the SMs with this latency-bound one - a persistent grid striding over the pairs
+    const int64_t n_pairs = (int64_t)n_subj * L;
+    for (int64_t pair = (int64_t)blockIdx.x * SJ_WARPS + warp; pair < n_pairs; pair += (int64_t)gridDim.x * SJ_WARPS) {
     const int s = (int)(pair / L), l = (int)(pair % L);
     const int r0 = subj_ptr[s];
     const int T = subj_ptr[s + 1] - r0;
-    if (T <= 0) return;
+    if (T <= 0) continue;
     if (T > tcap || T > HLVAE_TMAX) {
         if (lane == 0) report_status(status, HLVAE_STATUS_T_TOO_LARGE, l, s);
-        return;
+        continue;
     }
     const int TL = T * (T + 1) / 2;
 
@@ -191,7 +193,7 @@ kl_subject_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict
     }
     if (bad) {
         if (lane == 0) report_status(status, HLVAE_STATUS_NOT_PD, l, s);
-        return;
+        continue;
     }
     // C term (:258): log det B = 2 sum log L_ii, one logarithm per lane
     const double logdet = warp_sum(lane < T ? 2.0 * log(Bw[lane * ldt + lane]) : 0.0);
@@ -355,6 +357,8 @@ kl_subject_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict
         atomicAdd(scal + 2, logdet);
         atomicAdd(scal + 3, fsum);
     }
+    __syncwarp();
+    }   // pairs
 }
 
 // =====================================================================================
@@ -1058,6 +1062,14 @@ void fill_offsets(int L, int M, int Q, int64_t* o) {
 
 }  // namespace
 
+// Scheduling knob (not state of the computation): resident kl_subject CTAs per SM; 0 = one warp per pair.
+static int g_subject_ctas_per_sm = 0;
+extern "C" int hlvae_set_subject_ctas_per_sm(int n) {
+    if (n < 0 || n > 32) return HLVAE_E_ARG;
+    g_subject_ctas_per_sm = n;
+    return 0;
+}
+
 extern "C" int hlvae_kl_acc_layout(int L, int M, int Q, int64_t* offsets) {
     if (L <= 0 || M <= 0 || Q <= 0 || !offsets) return HLVAE_E_ARG;
     fill_offsets(L, M, Q, offsets);
@@ -1082,6 +1094,12 @@ extern "C" int hlvae_kl_subject(const hlvae_kspec_t* spec0, const double* os0, c
     size_t smem = ((size_t)SJ_WARPS * ((size_t)t_cap * Q + 3 * (size_t)t_cap * ldt + SJ_KP) + HLVAE_EXP_TAB) * sizeof(double);
     int64_t pairs = (int64_t)n_subj * L;
     unsigned grid = (unsigned)((pairs + SJ_WARPS - 1) / SJ_WARPS);
+    if (g_subject_ctas_per_sm > 0) {
+        int dev = 0, sms = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const unsigned cap = (unsigned)(sms * g_subject_ctas_per_sm);
+        if (grid > cap) grid = cap;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e;
     if (dtype == HLVAE_F64) {
