@@ -658,6 +658,44 @@ def batch_normalization(descs: List[VarDesc], data, mask, conv=False):
 
 
 # --------------------------------------------------------------------------------------
+# Minibatch composition of the reference's samplers (utils.py:36-97, training.py:38-47)
+# --------------------------------------------------------------------------------------
+def fixed_T_batches(P: int, T: int, batch_size: int) -> List[List[int]]:
+    """BatchSampler(SubjectSampler(dataset, P, T), batch_size, drop_last=False): a np.random.shuffle permutation of
+    the subjects, rows T s .. T (s+1) - 1 of each in turn (utils.py:43-48), cut into batches of `batch_size` rows."""
+    import itertools
+    r = np.arange(P)
+    np.random.shuffle(r)
+    order = list(itertools.chain.from_iterable([list(range(T * x, T * (x + 1))) for x in r]))
+    return [order[b:b + batch_size] for b in range(0, len(order), batch_size)]
+
+
+def varying_T_batches(subject_ids: Sequence[int], subjects_per_batch: int) -> List[List[int]]:
+    """VaryingLengthBatchSampler(VaryingLengthSubjectSampler(dataset, id_covariate), subjects_per_batch): subjects own
+    the rows from their first occurrence to the next subject's first occurrence (utils.py:63-65), permuted with
+    np.random.shuffle (:68-69); a batch closes when a new subject arrives and it already holds
+    `subjects_per_batch` subjects (:86-96)."""
+    from collections import OrderedDict
+    l = [int(v) for v in subject_ids]
+    uniq = list(OrderedDict.fromkeys(l))
+    starts = [l.index(x) for x in uniq]
+    ends = starts[1:] + [len(l)]
+    r = np.arange(len(uniq))
+    np.random.shuffle(r)
+    batches, batch, seen = [], [], set()
+    for x in r:
+        for i in range(starts[x], ends[x]):
+            if x not in seen:
+                if len(seen) == subjects_per_batch:
+                    batches.append(batch)
+                    batch, seen = [], set()
+                seen.add(x)
+            batch.append(i)
+    batches.append(batch)
+    return batches
+
+
+# --------------------------------------------------------------------------------------
 # One ELBO-path step (training.py:83,104-137): used by the CPU baseline in bench.py
 # --------------------------------------------------------------------------------------
 def elbo_path_step(state: dict, natural_gradient_lr=0.01) -> Dict[str, torch.Tensor]:

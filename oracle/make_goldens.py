@@ -374,6 +374,40 @@ def norm_cases():
     norm_case("norm_conv_d4", synth.HEALTHMNIST_D4_TYPES, N=3, seed=33, conv=True, observed=0.75)
 
 
+# ------------------------------------------------------------------ minibatch composition (samplers)
+def sampler_cases():
+    """Row indices of every minibatch of one epoch from the reference's own sampler classes (utils.py:36-97) under a
+    fixed np.random seed.  torch >= 2.2 dropped Sampler.__init__(data_source): shimmed as in SURVEY.md 8(b)."""
+    import torch.utils.data as tud
+    from torch.utils.data import BatchSampler
+    orig = tud.Sampler.__init__
+    tud.Sampler.__init__ = lambda self, data_source=None: None
+    try:
+        import utils as ref_utils                               # reference
+        print("samplers: oracle vs unmodified reference")
+        flat = lambda bb: (np.concatenate([np.asarray(b, dtype=np.int64) for b in bb]),
+                           np.cumsum([0] + [len(b) for b in bb]))
+        P, T, bs, seed = 9, 5, 12, 41
+        ds = [{'label': torch.tensor([0., 0., float(s), 0.])} for s in range(P) for _ in range(T)]
+        np.random.seed(seed)
+        ref = [list(b) for b in BatchSampler(ref_utils.SubjectSampler(ds, P, T), bs, False)]
+        np.random.seed(seed)
+        assert orc.fixed_T_batches(P, T, bs) == ref
+        ids = [3] * 2 + [9] * 5 + [1] * 3 + [4] * 1 + [7] * 4 + [2] * 3 + [8] * 6
+        ds2 = [{'label': torch.tensor([0., 0., float(s), 0.])} for s in ids]
+        np.random.seed(seed + 1)
+        ref2 = [list(b) for b in ref_utils.VaryingLengthBatchSampler(ref_utils.VaryingLengthSubjectSampler(ds2, 2), 3)]
+        np.random.seed(seed + 1)
+        assert orc.varying_T_batches(ids, 3) == ref2
+        f1, f2 = flat(ref), flat(ref2)
+        np.savez_compressed(os.path.join(GOLD, "samplers.npz"), fixed_P=P, fixed_T=T, fixed_batch=bs, fixed_seed=seed,
+                            fixed_rows=f1[0], fixed_ptr=f1[1], var_ids=np.asarray(ids), var_batch=3, var_seed=seed + 1,
+                            var_rows=f2[0], var_ptr=f2[1])
+        print(f"  samplers: {len(ref)} fixed-T batches, {len(ref2)} varying-T batches identical")
+    finally:
+        tud.Sampler.__init__ = orig
+
+
 # ------------------------------------------------------------------ GP posterior-mean prediction
 def predict_case(name, kargs, L, M, n_subj, T, ragged, seed, n_test_subj=3, continuous_age=False):
     """utils.batch_predict_varying_T (and, with equal T, utils.batch_predict) of the unmodified reference.
@@ -486,6 +520,9 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "predict":      # only the prediction fixtures
         predict_cases()
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "samplers":
+        sampler_cases()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "norm":         # only the batch-normalisation fixtures
         norm_cases()
         return
@@ -514,6 +551,7 @@ def main():
     predict_cases()
     theta_cases()
     norm_cases()
+    sampler_cases()
     print("all oracle-vs-reference checks passed; goldens written to", GOLD)
 
 
