@@ -15,13 +15,20 @@
 // threads write consecutive addresses of the caller's layout.  HBM-bound: y and theta cross once.
 #include "common.cuh"
 
+#ifndef HLVAE_TH_BWD_BYTES
+#define HLVAE_TH_BWD_BYTES 80      // bytes of y values in flight per thread in the backward kernel
+#endif
+#ifndef HLVAE_TH_BWD_CTAS
+#define HLVAE_TH_BWD_CTAS 3
+#endif
+
 namespace {
 
 constexpr int TH_THREADS = 256;   // = max theta columns and max variables per tile
 // rows in flight per thread: about 40 registers of y values (y_dim = 5: 8 rows in float32, 4 in float64)
 template <typename TS, int YP, bool BWD = false>
 struct ThRows {
-    static constexpr int raw = (BWD ? 80 : 160) / (YP * (int)sizeof(TS));
+    static constexpr int raw = (BWD ? HLVAE_TH_BWD_BYTES : 160) / (YP * (int)sizeof(TS));
     // backward: a power of two, the rows of a column travel through shared memory as one vector
     static constexpr int value = BWD ? (raw >= 8 ? 8 : raw >= 4 ? 4 : raw >= 2 ? 2 : 1) : (raw < 1 ? 1 : (raw > 8 ? 8 : raw));
 };
@@ -97,6 +104,7 @@ theta_fwd_k(int64_t N, int Y, const int32_t* __restrict__ col_var, const int32_t
             const double* __restrict__ weight, const double* __restrict__ bias, const TS* __restrict__ y, int64_t sn,
             int64_t sd, int64_t sk, TS* __restrict__ theta, int64_t ld_theta) {
     constexpr int TH_RB = ThRows<TS, YP>::value;
+    Y = (YP == 16) ? Y : YP;      // exact instantiations (y_dim <= 8): y_dim is a compile-time constant from here on
     const int tid = threadIdx.x;
     const ThTile t = th_tile(tile_var, var_pcol, N, TH_RB);
     if (tid >= t.ncols || t.r_begin >= t.r_end) return;
@@ -124,8 +132,7 @@ __device__ __forceinline__ void th_bwd_rows(bool live, bool ydep, int mode, TS b
                                             double& gb, const TS* __restrict__ yb, const TM* __restrict__ mb,
                                             const TS* __restrict__ gb_in, TS* __restrict__ gyb, int sn, int sd, int sk,
                                             int D, int ld, int Y, TS* __restrict__ gsb, const TS* __restrict__ Ws,
-                                            const int* __restrict__ vlp, const int* __restrict__ vnc, int nv,
-                                            bool v_fastest) {
+                                            const int* __restrict__ pairs, int npairs) {
     const int tid = threadIdx.x;
     asm volatile("" : "+r"(sn), "+r"(sk), "+r"(ld), "+r"(D));      // see th_fwd_rows
     // ---- thread = column: masked upstream gradient, d/d{weight, bias}
@@ -187,11 +194,9 @@ __device__ __forceinline__ void th_bwd_rows(bool live, bool ydep, int mode, TS b
     }
     __syncthreads();
     // ---- thread = (variable, k): d/dy[n, d, k] = sum over the variable's columns of g * weight[col, k]
-    const int npairs = nv * Y;
     for (int q = tid; q < npairs; q += TH_THREADS) {
-        int v, k;
-        if (v_fastest) { k = q / nv; v = q - k * nv; } else { v = q / Y; k = q - v * Y; }
-        const int lp = vlp[v], nc = vnc[v];
+        const int pq = pairs[q];                 // (variable, k, first column, column count), tabulated per tile
+        const int v = pq & 255, k = (pq >> 8) & 31, lp = (pq >> 13) & 511, nc = pq >> 22;
         TS a[R];
 #pragma unroll
         for (int r = 0; r < R; r++) a[r] = (TS)0;
@@ -208,18 +213,19 @@ __device__ __forceinline__ void th_bwd_rows(bool live, bool ydep, int mode, TS b
 }
 
 template <typename TS, typename TM, int YP>
-__global__ void __launch_bounds__(TH_THREADS, 3)
+__global__ void __launch_bounds__(TH_THREADS, HLVAE_TH_BWD_CTAS)
 theta_bwd_k(int64_t N, int D, int Y, const int32_t* __restrict__ col_var, const int32_t* __restrict__ col_mode,
             const int32_t* __restrict__ var_pcol, const int32_t* __restrict__ tile_var,
             const double* __restrict__ weight, const double* __restrict__ bias, const TS* __restrict__ y, int64_t sn,
             int64_t sd, int64_t sk, const TM* __restrict__ mask, const TS* __restrict__ g_theta, int64_t ld_theta,
             TS* __restrict__ g_y, double* __restrict__ g_weight, double* __restrict__ g_bias) {
     constexpr int TH_RB = ThRows<TS, YP, true>::value;
+    // (y_dim stays a run-time value here: making it a compile-time constant as in the forward kernel was measured
+    // 5 % slower - 0.547 vs 0.519 ms - the fully unrolled d/dy phase schedules worse)
     extern __shared__ __align__(16) unsigned char th_smem[];
     TS* gs = reinterpret_cast<TS*>(th_smem);                  // [2][256][RB] masked upstream gradient per column
     TS* Ws = gs + 2 * TH_RB * TH_THREADS;                     // [256][Y] weights of the tile's y-dependent columns
-    int* vlp = reinterpret_cast<int*>(Ws + (size_t)TH_THREADS * Y);   // [256] first tile-local column of a variable
-    int* vnc = vlp + TH_THREADS;                              // [256] its column count
+    int* pairs = reinterpret_cast<int*>(Ws + (size_t)TH_THREADS * Y);   // [nv * Y] packed (v, k, first column, #columns)
     const int tid = threadIdx.x;
     const ThTile t = th_tile(tile_var, var_pcol, N, TH_RB);
     if (t.r_begin >= t.r_end) return;
@@ -238,27 +244,31 @@ theta_bwd_k(int64_t N, int D, int Y, const int32_t* __restrict__ col_var, const 
         gw[k] = 0.0;
     }
     for (int k = 0; k < Y; k++) Ws[tid * Y + k] = ydep ? (TS)weight[(int64_t)p * Y + k] : (TS)0;
-    if (tid < t.nv) {
-        vlp[tid] = var_pcol[t.d0 + tid] - t.p0;
-        vnc[tid] = var_pcol[t.d0 + tid + 1] - var_pcol[t.d0 + tid];
+    // (variable, k) pairs of the d/dy phase, ordered so that consecutive threads write consecutive addresses of the
+    // caller's layout (variable-fastest when y is [N, Y, D] viewed as [N, D, Y])
+    const int npairs = t.nv * Y;
+    const bool v_fastest = sd < sk;
+    for (int q = tid; q < npairs; q += TH_THREADS) {
+        int v, k;
+        if (v_fastest) { k = q / t.nv; v = q - k * t.nv; } else { v = q / Y; k = q - v * Y; }
+        const int lp = var_pcol[t.d0 + v] - t.p0, nc = var_pcol[t.d0 + v + 1] - var_pcol[t.d0 + v];
+        pairs[q] = v | (k << 8) | (lp << 13) | (nc << 22);
     }
     __syncthreads();
     const TS* yv = y + (int64_t)dvar * sd;
     const TM* mv = mask + dvar;
     const TS* gin = g_theta + p;
     TS* gyt = g_y + (int64_t)t.d0 * sd;
-    const bool v_fastest = sd < sk;       // consecutive threads of the d/dy phase -> consecutive addresses of the layout
     const int sn32 = (int)sn, sd32 = (int)sd, sk32 = (int)sk, ld32 = (int)ld_theta;
     int buf = 0;
     int64_t n0 = t.r_begin;
     for (; n0 + TH_RB <= t.r_end; n0 += TH_RB, buf ^= 1)
         th_bwd_rows<TS, TM, YP, TH_RB>(live, ydep, mode, b, wk, gw, gb, yv + n0 * sn, mv + n0 * D, gin + n0 * ld_theta,
-                                       gyt + n0 * sn, sn32, sd32, sk32, D, ld32, Y, gs + buf * TH_RB * TH_THREADS, Ws, vlp,
-                                       vnc, t.nv, v_fastest);
+                                       gyt + n0 * sn, sn32, sd32, sk32, D, ld32, Y, gs + buf * TH_RB * TH_THREADS, Ws, pairs,
+                                       npairs);
     for (; n0 < t.r_end; n0++, buf ^= 1)
         th_bwd_rows<TS, TM, YP, 1>(live, ydep, mode, b, wk, gw, gb, yv + n0 * sn, mv + n0 * D, gin + n0 * ld_theta,
-                                   gyt + n0 * sn, sn32, sd32, sk32, D, ld32, Y, gs + buf * TH_RB * TH_THREADS, Ws, vlp, vnc,
-                                   t.nv, v_fastest);
+                                   gyt + n0 * sn, sn32, sd32, sk32, D, ld32, Y, gs + buf * TH_RB * TH_THREADS, Ws, pairs, npairs);
     if (live && mode != HLVAE_HEAD_ZERO) {
         if (gb != 0.0) atomicAdd(g_bias + p, gb);
         if (ydep) {
@@ -305,7 +315,7 @@ int launch_bwd(int64_t N, int D, int Y, int n_tiles, const int32_t* col_var, con
                double* g_weight, double* g_bias, cudaStream_t st) {
     auto kern = theta_bwd_k<TS, TM, YP>;
     constexpr int RB = ThRows<TS, YP, true>::value;
-    const size_t smem = ((size_t)2 * RB * TH_THREADS + (size_t)TH_THREADS * Y) * sizeof(TS) + 2 * TH_THREADS * sizeof(int);
+    const size_t smem = ((size_t)2 * RB * TH_THREADS + (size_t)TH_THREADS * Y) * sizeof(TS) + (size_t)TH_THREADS * Y * sizeof(int);
     dim3 grid(n_tiles, grid_stripes(N, n_tiles, RB, 9));
     kern<<<grid, TH_THREADS, smem, st>>>(N, D, Y, col_var, col_mode, var_pcol, tile_var, weight, bias, (const TS*)y, sn,
                                          sd, sk, (const TM*)mask, (const TS*)g_theta, ld_theta, (TS*)g_y, g_weight,
