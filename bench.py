@@ -59,6 +59,7 @@ def parse():
     ap.add_argument("--eager", action="store_true", help="time eager launches instead of CUDA-graph replay")
     ap.add_argument("--no-overlap", action="store_true", help="single stream: no likelihood / KL overlap")
     ap.add_argument("--no-split-backward", action="store_true", help="one backward() of nll + kld instead of one per branch")
+    ap.add_argument("--no-natgrad-stream", action="store_true", help="natural-gradient update on the KL stream, not its own")
     ap.add_argument("--subject-ctas", type=int, default=SUBJECT_CTAS_PER_SM,
                     help="resident hlvae_kl_subject CTAs per SM (0: unlimited); leaves room for the likelihood kernels")
     ap.add_argument("--workload", default="elbo", choices=["elbo", "predict", "sweep", "theta", "full", "norm"],
@@ -251,7 +252,17 @@ def elbo_step(s, world, inp=None):
         kld, gm, gH = elbo.minibatch_KLD_upper_bound_iter(s["k0"], s["k1"], s["lik"], L, s["m"], s["H"], inp["x"],
                                                           inp["mu"], inp["lv"], s["z"], P_TOTAL, P_b, N_TOTAL, True,
                                                           2, EPS, layout=s["layout"])            # training.py:110-113
-        m_new, H_new = elbo.natural_gradient_update(s["m"], s["H"], gm, gH, NG_LR)             # :130-137
+        side2 = s.get("side2") if split else None
+        if side2 is not None:
+            # the natural-gradient update (32 CTAs, latency-bound) needs only grad_m / grad_H: it runs on a third stream
+            # next to the KL backward (kernel_eval_bwd + the hyper-parameter transforms' backward kernels)
+            side2.wait_stream(side)
+            with torch.cuda.stream(side2):
+                m_new, H_new = elbo.natural_gradient_update(s["m"], s["H"], gm, gH, NG_LR)     # :130-137
+            for t_ in (gm, gH):
+                t_.record_stream(side2)
+        else:
+            m_new, H_new = elbo.natural_gradient_update(s["m"], s["H"], gm, gH, NG_LR)         # :130-137
         if split:
             kld.backward()
     vparam = s["lay"].vparam(log_vy_real=s["log_vy_real"], conv=True)
@@ -261,6 +272,8 @@ def elbo_step(s, world, inp=None):
         nll.backward()
     if side is not None:
         cur.wait_stream(side)
+        if split and s.get("side2") is not None:
+            cur.wait_stream(s["side2"])
         for t_ in (kld, m_new, H_new):      # allocated on the side stream, consumed on this one
             t_.record_stream(cur)
     loss = nll + kld                                                                           # :124
@@ -319,6 +332,7 @@ def run_gpu(args):
     s = build_gpu_state(dev, args.subjects, rank)
     s["side"] = None if args.no_overlap else torch.cuda.Stream()
     s["split_backward"] = not args.no_split_backward
+    s["side2"] = None if (args.no_overlap or args.no_natgrad_stream) else torch.cuda.Stream()
     config.overlap = not args.no_overlap
     from hlvae_b200 import _lib as _l
     _l.check(_l.lib().hlvae_set_subject_ctas_per_sm(int(args.subject_ctas)), "hlvae_set_subject_ctas_per_sm")
