@@ -96,3 +96,10 @@ def test_properties_full_size(device):
     ic = lay.var.idx["cat"]
     c0 = int(lay.var.var_dcol[ic[0]])
     assert torch.equal(X[:, c0:c0 + 5], data[:, c0:c0 + 5] * mask[:, ic[0]].unsqueeze(1).float())
+
+
+def test_empty_batch(device):
+    types = [('real', 1), ('cat', 3), ('pos', 1)]
+    lay = nz.NormLayout(types, False, device)
+    X, mean, var = nz.normalize(lay, torch.zeros(0, 5, dtype=DT, device=device), torch.zeros(0, 3, dtype=DT, device=device))
+    assert X.shape == (0, 5) and mean.shape == (3,)

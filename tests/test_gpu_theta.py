@@ -156,3 +156,30 @@ def test_no_cpu_fallback():
     with pytest.raises(RuntimeError, match="CUDA"):
         th.theta_heads(lay, torch.zeros(2, 2, 3, dtype=DT), torch.ones(2, 2, dtype=DT), torch.zeros(4, 3, dtype=DT),
                        torch.zeros(4, dtype=DT))
+
+
+def test_edge_cases(device):
+    """Empty batch, single row, an all-missing row (no gradient leaves it), a y view that is not dense, y_dim too large."""
+    types = [('real', 1), ('cat', 4), ('ordinal', 3), ('count', 1), ('pos', 1)]
+    gen = torch.Generator().manual_seed(0)
+    ti, heads = _random_heads(types, False, 3, gen)
+    obs_layer = _product_layers(ti, heads, False, device)
+    lay = th.HeadLayout(types, False, device)
+    W, b = th.pack_heads(obs_layer, lay, 3)
+    empty = th.theta_heads(lay, torch.zeros(0, 5, 3, dtype=DT, device=device), torch.zeros(0, 5, dtype=DT, device=device), W, b)
+    assert empty.shape == (0, lay.P)
+    y1 = torch.randn(1, 5, 3, generator=gen, dtype=DT).to(device).requires_grad_(True)
+    m1 = torch.zeros(1, 5, dtype=DT, device=device)
+    t1 = th.theta_heads(lay, y1, m1, W, b)
+    t1.sum().backward()
+    ref = orc.theta_estimation(types, heads, y1.detach().cpu(), m1.cpu())
+    assert h.rel_err(t1, ref) < 1e-12                         # forward does not depend on the mask
+    assert torch.equal(y1.grad, torch.zeros_like(y1))         # nothing observed: no gradient
+    big = torch.randn(6, 5, 8, generator=gen, dtype=DT).to(device)
+    yv = big[:, :, ::2][:, :, :3]                             # gapped strides: made contiguous by the host layer
+    tv = th.theta_heads(lay, yv, torch.ones(6, 5, dtype=DT, device=device), W, b)
+    assert h.rel_err(tv, orc.theta_estimation(types, heads, yv.cpu().contiguous(), torch.ones(6, 5, dtype=DT))) < 1e-12
+    lay17 = th.HeadLayout([('real', 1)], False, device)
+    with pytest.raises(NotImplementedError):
+        th.theta_heads(lay17, torch.zeros(2, 1, 17, dtype=DT, device=device), torch.ones(2, 1, dtype=DT, device=device),
+                       torch.zeros(1, 17, dtype=DT, device=device), torch.zeros(1, dtype=DT, device=device))
