@@ -21,6 +21,7 @@ from .kernels import compile_spec
 from .subjects import SubjectLayout
 
 N_SM = 148
+PANEL_WAVES = 4        # waves of kl_panel CTAs per launch (see _subjects_per_chunk)
 
 _side_streams = {}
 
@@ -110,8 +111,7 @@ class _KLD(torch.autograd.Function):
             cur.wait_stream(side)
         # ---- 2b. streaming stage over the minibatch rows
         if layout.n_subj > 0:
-            n_chunks = max(1, min((N_SM * 8 + L - 1) // L, (layout.n_subj + 2) // 3))
-            spc = (layout.n_subj + n_chunks - 1) // n_chunks
+            spc = _subjects_per_chunk(layout.n_subj, layout.t_max, L, M)
             _lib.call("hlvae_kl_panel", fs0.cspec, _lib.ptr(os0c), _lib.ptr(ls0c), fs1.cspec, _lib.ptr(os1c),
                       _lib.ptr(ls1c), L, Q, M, _lib.ptr(x_c), Q, _lib.ptr(z_c), _lib.ptr(layout.row_idx),
                       _lib.ptr(layout.subj_ptr), _lib.ptr(layout.tt_ptr), layout.n_subj, spc, _lib.ptr(mu_c), L,
@@ -209,6 +209,22 @@ def minibatch_KLD_upper_bound_iter(covar_module0, covar_module1, likelihood, lat
         layout = SubjectLayout.from_ids(train_xt[:, id_covariate])
     return _kld(covar_module0, covar_module1, likelihood, latent_dim, m, H, train_xt, mu, log_v, z, layout,
                 P / P_in_current_batch, latent_dim * N / 2, natural_gradient, eps, (1,))
+
+
+def _subjects_per_chunk(n_subj, t_max, L, M, waves=None):
+    """Subjects per hlvae_kl_panel CTA.  A CTA walks its chunk in row panels of RP rows (64 for M <= 64, else 32) that
+    hold whole subjects, so a chunk should be a whole number of full panels (a trailing panel with one subject costs
+    nearly as much as a full one), and L * n_chunks CTAs should fill a whole number of waves of N_SM CTAs."""
+    import os
+    rp = 64 if M <= 64 else 32
+    spp = max(1, rp // max(int(t_max), 1))                    # subjects per full panel
+    waves = int(os.environ.get("HLVAE_PANEL_WAVES", waves or PANEL_WAVES))
+    n_panels = (n_subj + spp - 1) // spp
+    # at least `waves` waves of CTAs, and no more than ~30 panels per CTA (large batches: more, shorter CTAs balance
+    # the tail better - measured at 64 000 rows)
+    n_chunks = max(1, min(max((N_SM * waves) // L, (n_panels + 29) // 30), n_panels))
+    spc = (n_subj + n_chunks - 1) // n_chunks
+    return ((spc + spp - 1) // spp) * spp
 
 
 def natural_gradient_update(m, H, grad_m, grad_H, lr):
