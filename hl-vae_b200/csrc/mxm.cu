@@ -326,7 +326,17 @@ mxm_post_k(int L, int M, double c0, double constant, const double* __restrict__ 
         double kq = 0.5 * (pr[2] + pr[3] - (double)M + pr[0] - pr[1]);                     // :180 / :275
         double v = c0 * (0.5 * (sc[0] + sc[1] + sc[2] - sc[3]) + js) + kq;               // :181 / :277
         if (l == 0) v -= constant;
-        atomicAdd(kld, v);
+        // deterministic total (the replicated loss must be bit-identical on every data-parallel rank and from launch
+        // to launch): per-l values are parked in kld[2 + l]; the CTA that arrives last adds them up in index order
+        kld[2 + l] = v;
+        __threadfence();
+        const double arrived = atomicAdd(kld + 1, 1.0);
+        if (arrived == (double)(gridDim.x - 1)) {
+            __threadfence();
+            double tot = 0.0;
+            for (int q = 0; q < (int)gridDim.x; q++) tot += __ldcg(kld + 2 + q);
+            kld[0] += tot;
+        }
     }
 }
 

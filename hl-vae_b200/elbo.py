@@ -85,7 +85,7 @@ class _KLD(torch.autograd.Function):
         w, gm = vecs[0], vecs[1]
         pre = torch.empty(L, 4, **f64)
         off = _lib.acc_layout(L, M, Q)
-        acc = torch.zeros(off["total"] + 1, **f64)     # last element: kld_total
+        acc = torch.zeros(off["total"] + 2 + L, **f64) # tail: kld_total, arrival counter, per-latent kld terms
         full = layout.n_rows == N
         g_mu = torch.empty_like(mu_c) if full else torch.zeros_like(mu_c)
         g_lv = torch.empty_like(lv_c) if full else torch.zeros_like(lv_c)
@@ -163,7 +163,7 @@ class _KLD(torch.autograd.Function):
         grad_m = ng_m_c if natural_gradient else None
         grad_H = ng_H_c if natural_gradient else None
         ctx.mark_non_differentiable(iH, *[t for t in (grad_m, grad_H) if t is not None])
-        return kld.clone().reshape(out_shape), grad_m, grad_H, iH
+        return kld[:1].clone().reshape(out_shape), grad_m, grad_H, iH
 
     @staticmethod
     def backward(ctx, g_kld, g_gm, g_gH, g_iH):

@@ -163,7 +163,9 @@ int hlvae_kl_panel(const hlvae_kspec_t* spec0, const double* os0, const double* 
  *   iK, iH (:154-157,162-163 / :225-228), w = iK m, G = sym(iK H iK) - iK; pre[l] =
  *   {logdet K, logdet H, tr(iK H), m^T iK m} (:176-179 / :271-274).  All outputs [L,...] float64.
  * hlvae_mxm_post: from the (all-reduced) accumulators S, p, gw, scal: kld[0] += kld_total
- *   (:181 / :277, `constant` = L * N / 2 subtracted once), the natural-gradient pieces ng_m, ng_H
+ *   (:181 / :277, `constant` = L * N / 2 subtracted once; `kld` is a caller-zeroed float64 [2 + L]: kld[1] counts
+ *   arrived CTAs and kld[2 + l] parks the per-latent terms, summed in index order by the last CTA so that the total
+ *   is bit-identical from launch to launch and across data-parallel ranks), the natural-gradient pieces ng_m, ng_H
  *   (:186-191 / :279-283; nullable) and, with f = c0 (tr(G S)/2 + w^T gw) + kld_qu_pu,
  *   gK_over_c0 = (df/dK0zz) / c0, gH = df/dH, gm = df/dm.  c0 = P / P_batch.
  * hlvae_natgrad_update: training.py:130-137, (m, H, grad_m, grad_H, lr) -> (m_out, H_out); `iH` (nullable) is
