@@ -158,3 +158,24 @@ def test_full_size_minibatch_properties(device):
     assert h.rel_err(d_z, full["d_z"]) < 5e-5
     gH = sum(o["grad_H"] - base["grad_H"] for o in outs) + base["grad_H"]
     assert h.rel_err(gH, full["grad_H"]) < 5e-5
+
+
+def test_device_loader_layout_feeds_the_kl_kernels(device):
+    """A minibatch from hlvae_b200.data.DeviceSubjectLoader (device gathers + CSR from known subject lengths) gives the
+    same KL bound as grouping the same rows by their id column the way the reference does (torch.unique)."""
+    import numpy as np
+    from hlvae_b200 import data as D, subjects
+    inp = h.make_kl_inputs(L=3, M=12, n_subj=9, T=7, seed=21, ragged=True)
+    x = inp["x"]
+    n = x.shape[0]
+    ds = D.DeviceDataset(np.zeros((n, 4)), np.ones((n, 2)), x.numpy(), id_covariate=2, device=device)
+    np.random.seed(3)
+    batch = next(iter(D.DeviceSubjectLoader(ds, 5, varying_T=True)))
+    rows = batch["idx"]
+    assert batch["label"].is_cuda and batch["digit"].dtype == torch.uint8
+    sub = dict(inp)
+    sub["x"], sub["mu"], sub["lv"] = x[rows.cpu()], inp["mu"][rows.cpu()], inp["lv"][rows.cpu()]
+    sub["n_subj"] = batch["layout"].n_subj
+    a = h.run_kl_product(sub, device, layout=batch["layout"])
+    b = h.run_kl_product(sub, device, layout=subjects.SubjectLayout.from_ids(sub["x"][:, 2].to(device)))
+    assert h.rel_err(a["kld"], b["kld"]) < 1e-9 and h.rel_err(a["d_mu"], b["d_mu"]) < 1e-7
