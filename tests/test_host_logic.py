@@ -110,3 +110,18 @@ def test_cpu_tensors_fail_loudly():
     lay = loglik.VarLayout([("real", 1)], "cpu")
     with pytest.raises(RuntimeError, match="CUDA"):
         loglik.fused_loglik(lay, torch.zeros(2, 1), torch.ones(2, 1), torch.zeros(2, 1), torch.zeros(4, 1))
+
+
+def test_panel_chunks_are_whole_panels():
+    """hlvae_kl_panel chunk sizing (elbo._subjects_per_chunk): whole row panels per chunk, every subject covered, at
+    least one chunk, and a bounded number of panels per CTA for large batches."""
+    from hlvae_b200 import elbo
+    for n_subj, t_max, L, M in ((1, 20, 32, 64), (7, 20, 32, 64), (200, 20, 32, 64), (800, 20, 32, 64), (3200, 20, 32, 64),
+                                (800, 5, 8, 32), (800, 32, 32, 128), (513, 13, 4, 64)):
+        spc = elbo._subjects_per_chunk(n_subj, t_max, L, M)
+        rp = 64 if M <= 64 else 32
+        spp = max(1, rp // t_max)
+        assert spc >= 1 and spc % spp == 0
+        n_chunks = (n_subj + spc - 1) // spc
+        assert n_chunks >= 1 and n_chunks * spc >= n_subj
+        assert spc // spp <= max(30, -(-n_subj // spp) // max(1, (148 * elbo.PANEL_WAVES) // L) + 1) + 1
