@@ -873,7 +873,6 @@ def run_sweep(args):
     import __graft_entry__ as g
     g.build()
     from hlvae_b200 import _lib, config, elbo, kernels, likelihoods, loglik, subjects, synth
-    from oracle import hlvae_oracle as orc
     config.check_errors = False
     config.overlap = False
     hbm_peak, _ = measured_peaks()
@@ -934,7 +933,7 @@ def run_sweep(args):
     ll_rows = []
     types = synth.TABULAR_TYPES
     layt = loglik.VarLayout(types, dev)
-    descs, E_x, P_th = orc.build_layout(types)
+    E_x, P_th = layt.E_x, layt.P_theta
     for N_b in (16000, 64000):
         rng = np.random.default_rng(9)
         gen = torch.Generator(device=dev).manual_seed(9)
