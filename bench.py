@@ -41,7 +41,6 @@ sys.path.insert(0, ROOT)
 
 L, M, Q, T = 32, 64, 6, 20
 SUBJ_PER_RANK = 800
-SUBJECT_CTAS_PER_SM = 0
 P_TOTAL, N_TOTAL = 5000, 100000            # ~100k-sample dataset of configs[1]
 EPS, NG_LR = 1e-6, 0.01
 WORKLOAD = "configs[1]: synthetic HealthMNIST-shaped, L=32, M=64, 800 subjects x T=20 = 16000 rows/step, D4 (324 real + 972 cat x5)"
@@ -61,8 +60,6 @@ def parse():
     ap.add_argument("--no-split-backward", action="store_true", help="one backward() of nll + kld instead of one per branch")
     ap.add_argument("--no-natgrad-stream", action="store_true", help="natural-gradient update on the KL stream, not its own")
     ap.add_argument("--no-kl-priority", action="store_true", help="KL stream at default priority")
-    ap.add_argument("--subject-ctas", type=int, default=SUBJECT_CTAS_PER_SM,
-                    help="resident hlvae_kl_subject CTAs per SM (0: unlimited); leaves room for the likelihood kernels")
     ap.add_argument("--workload", default="elbo", choices=["elbo", "predict", "sweep", "theta", "full", "norm"],
                     help="elbo: the BASELINE.json metric (default); predict: SURVEY 8(f) row 1, GP posterior-mean "
                          "prediction (utils.batch_predict_varying_T), its own JSON line")
@@ -338,8 +335,6 @@ def run_gpu(args):
     s["split_backward"] = not args.no_split_backward
     s["side2"] = None if (args.no_overlap or args.no_natgrad_stream) else torch.cuda.Stream()
     config.overlap = not args.no_overlap
-    from hlvae_b200 import _lib as _l
-    _l.check(_l.lib().hlvae_set_subject_ctas_per_sm(int(args.subject_ctas)), "hlvae_set_subject_ctas_per_sm")
     n_rows = s["N_b"]
     algorithmic_work(n_rows, args.subjects)
     fp64_peak = measure_fp64_peak(dev)       # before any graph capture (uses the RNG)
@@ -533,7 +528,7 @@ def run_gpu(args):
                     clocks=sampler.summary(), e2e=e2e, gpu_launches=launches, roofline=roof, cpu_baseline=cpu,
                     kernels=kern, fp64_peak_tflops=fp64_peak, cuda_graph=use_graph, eager_ms_per_step=eager_ms,
                     overlap=not args.no_overlap, split_backward=not args.no_split_backward,
-                    subject_ctas_per_sm=int(args.subject_ctas), kl_stream_priority=not args.no_kl_priority,
+                    kl_stream_priority=not args.no_kl_priority,
                     kernel_timing="CUDA events around every C-ABI call in an eager, single-stream pass of the same "
                                   "step run right after the timed region (events are not readable inside a replayed "
                                   "graph; the timed region overlaps the KL branch with the likelihood kernels)")

@@ -44,7 +44,6 @@ _SIGS = {
     "hlvae_kernel_eval_bwd": ([C.POINTER(KSpec), _P, _P, _I, _I, _P, _I, _L, _L, _P, _I, _L, _L, _P, _P, _P, _P, _P, _P], _I),
     "hlvae_subject_matvec": ([C.POINTER(KSpec), _P, _P, _I, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P], _I),
     "hlvae_kl_acc_layout": ([_I, _I, _I, C.POINTER(_L)], _I),
-    "hlvae_set_subject_ctas_per_sm": ([_I], _I),
     "hlvae_kl_subject": ([C.POINTER(KSpec), _P, _P, C.POINTER(KSpec), _P, _P, _P, _I, _I, _P, _L, _P, _P, _P, _I, _I,
                           _P, _L, _I, _P, _L, _P, _I, _P, _D, _P, _P], _I),
     "hlvae_kl_panel": ([C.POINTER(KSpec), _P, _P, C.POINTER(KSpec), _P, _P, _I, _I, _I, _P, _L, _P, _P, _P, _P, _I, _I,
@@ -95,11 +94,48 @@ def workspace(L, M, device):
     return torch.empty(n, dtype=torch.float64, device=device) if n else None
 
 
+class _DevPtr(C.c_void_p):
+    """Device pointer that remembers which GPU it belongs to (checked / used by `call`)."""
+    dev = None
+
+
+class _CurrentStream:
+    """Placeholder returned by stream_ptr(): resolved by `call` to torch's current stream of the device the
+    call's tensors live on."""
+
+
+CURRENT_STREAM = _CurrentStream()
+
+
 def call(name, *args):
-    """Invoke C-ABI entry point `name` (each one enqueues exactly one kernel) and check its result."""
+    """Invoke C-ABI entry point `name` (each one enqueues exactly one kernel) and check its result.
+
+    The kernel is launched on the device of the tensors passed through `ptr()` (they must share one device), on
+    torch's current stream OF THAT DEVICE, with that device made current for the duration of the call: the C
+    entry points never call cudaSetDevice themselves."""
     global LAUNCHES
     fn = getattr(lib(), name)
+    dev = None
+    for a in args:
+        if isinstance(a, _DevPtr):
+            if dev is None:
+                dev = a.dev
+            elif a.dev != dev:
+                raise RuntimeError(f"hlvae_b200: {name}: tensors live on different CUDA devices ({dev} and {a.dev})")
+    cur = torch.cuda.current_device()
+    if dev is None:
+        dev = cur
+    if any(a is CURRENT_STREAM for a in args):
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        args = tuple(st if a is CURRENT_STREAM else a for a in args)
     LAUNCHES += 1
+    if dev != cur:
+        with torch.cuda.device(dev):
+            return _invoke(fn, name, args)
+    return _invoke(fn, name, args)
+
+
+def _invoke(fn, name, args):
     if PROFILE is None:
         return check(fn(*args), name)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -117,16 +153,19 @@ def check(rc: int, what: str):
 
 
 def ptr(t):
-    """Device pointer of a CUDA tensor (None -> NULL)."""
+    """Device pointer of a CUDA tensor (None -> NULL), tagged with the tensor's device index."""
     if t is None:
         return None
     if not t.is_cuda:
         raise RuntimeError("hlvae_b200: tensors must live on a CUDA device (no CPU fallback)")
-    return C.c_void_p(t.data_ptr())
+    p = _DevPtr(t.data_ptr())
+    p.dev = t.device.index
+    return p
 
 
 def stream_ptr():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    """The launching stream: torch's current stream of the call's device (resolved inside `call`)."""
+    return CURRENT_STREAM
 
 
 def dtype_code(t):

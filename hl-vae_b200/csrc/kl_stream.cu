@@ -1062,14 +1062,6 @@ void fill_offsets(int L, int M, int Q, int64_t* o) {
 
 }  // namespace
 
-// Scheduling knob (not state of the computation): resident kl_subject CTAs per SM; 0 = one warp per pair.
-static int g_subject_ctas_per_sm = 0;
-extern "C" int hlvae_set_subject_ctas_per_sm(int n) {
-    if (n < 0 || n > 32) return HLVAE_E_ARG;
-    g_subject_ctas_per_sm = n;
-    return 0;
-}
-
 extern "C" int hlvae_kl_acc_layout(int L, int M, int Q, int64_t* offsets) {
     if (L <= 0 || M <= 0 || Q <= 0 || !offsets) return HLVAE_E_ARG;
     fill_offsets(L, M, Q, offsets);
@@ -1094,12 +1086,6 @@ extern "C" int hlvae_kl_subject(const hlvae_kspec_t* spec0, const double* os0, c
     size_t smem = ((size_t)SJ_WARPS * ((size_t)t_cap * Q + 3 * (size_t)t_cap * ldt + SJ_KP) + HLVAE_EXP_TAB) * sizeof(double);
     int64_t pairs = (int64_t)n_subj * L;
     unsigned grid = (unsigned)((pairs + SJ_WARPS - 1) / SJ_WARPS);
-    if (g_subject_ctas_per_sm > 0) {
-        int dev = 0, sms = 148;
-        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        const unsigned cap = (unsigned)(sms * g_subject_ctas_per_sm);
-        if (grid > cap) grid = cap;
-    }
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e;
     if (dtype == HLVAE_F64) {

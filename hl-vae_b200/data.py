@@ -95,6 +95,10 @@ class DeviceSubjectLoader:
         else:
             if P is None or T is None:
                 raise ValueError("fixed-T sampling needs P and T (utils.py:37-41)")
+            # batch_size counts ROWS here; when it is not a multiple of T a batch boundary cuts a subject (the
+            # reference's BatchSampler does the same and its minibatch_KLD_upper_bound then fails in
+            # reshape([P_batch, T, Q]), elbo_functions.py:144): such batches carry no subject layout
+            self.whole_subjects = self.batch_size % int(T) == 0
             self.starts = [T * s for s in range(P)]
             self.ends = [T * (s + 1) for s in range(P)]
         self.P = len(self.starts)
@@ -134,5 +138,8 @@ class DeviceSubjectLoader:
     def __iter__(self):
         for rows, lens in self.batches():
             batch = self.ds.rows(rows)
-            batch['layout'] = SubjectLayout.from_lengths(lens, self.ds.device)
+            # fragments of a cut subject must not pass as subjects of their own: no layout -> the fixed-T KL bound
+            # builds SubjectLayout.fixed(N, T), which raises when N is not a whole number of subjects
+            whole = self.varying_T or self.whole_subjects
+            batch['layout'] = SubjectLayout.from_lengths(lens, self.ds.device) if whole else None
             yield batch

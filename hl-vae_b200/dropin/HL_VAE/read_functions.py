@@ -1,7 +1,6 @@
 """Drop-in for HL_VAE/read_functions.py: the reference module (data reading, error metrics, ...)
 with `statistics` (:268-339) and `discrete_variables_transformation` (:221-235) replaced by the
-CUDA kernels for the five hot-path variable types.  Types outside that set (beta) fall through to
-the reference code."""
+CUDA kernels.  There is no CPU path: CPU tensors and variable types the kernels do not know raise."""
 import importlib.util
 import os
 
@@ -29,15 +28,16 @@ def _layout(types_info, device):
     return _layouts[key]
 
 
-def _supported(types_info):
-    return all(t['type'] in ('real', 'pos', 'count', 'cat', 'ordinal') for t in types_info['types_dict'])
+def _require(types_info, tensor, what):
+    bad = sorted({t['type'] for t in types_info['types_dict']} - set(_ll.SUPPORTED_TYPES))
+    if bad:
+        raise NotImplementedError(f"hlvae_b200: {what}: variable types {bad} are not supported by the CUDA kernels")
+    if not tensor.is_cuda:
+        raise RuntimeError(f"hlvae_b200: {what} runs on CUDA tensors only (no CPU fallback)")
 
 
 def statistics(loglik_params, types_info, device, conv=False, log_vy=None):
-    if not _supported(types_info) or not loglik_params.is_cuda:
-        if _ref is None:
-            raise RuntimeError("hlvae_b200: statistics needs CUDA tensors (reference module not found for other cases)")
-        return _ref.statistics(loglik_params, types_info, device, conv, log_vy)
+    _require(types_info, loglik_params, "statistics")
     lay = _layout(types_info, loglik_params.device)
     lv_pos = None
     if log_vy is not None and lay.idx["pos"].numel():
@@ -49,8 +49,5 @@ def statistics(loglik_params, types_info, device, conv=False, log_vy=None):
 
 
 def discrete_variables_transformation(data, types_info):
-    if not _supported(types_info) or not data.is_cuda:
-        if _ref is None:
-            raise RuntimeError("hlvae_b200: discrete_variables_transformation needs CUDA tensors")
-        return _ref.discrete_variables_transformation(data, types_info)
+    _require(types_info, data, "discrete_variables_transformation")
     return _ll.discrete_variables_transformation(_layout(types_info, data.device), data)

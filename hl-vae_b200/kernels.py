@@ -64,8 +64,10 @@ class Kernel(nn.Module):
         if active_dims is not None and not torch.is_tensor(active_dims):
             active_dims = torch.tensor(active_dims, dtype=torch.long)
         self.register_buffer("active_dims", active_dims)
-        # host copy of the covariate column: compile_spec runs every step and must not read the device
-        self._columns = None if active_dims is None else [int(v) for v in active_dims.reshape(-1).tolist()]
+        # host copy of the covariate column: compile_spec runs every step and must not read the device; refreshed
+        # whenever the `active_dims` buffer (the source of truth, as in gpytorch) is replaced or written in place
+        self._columns, self._columns_tag = None, None
+        self._refresh_columns()
         if has_lengthscale is None:
             has_lengthscale = type(self).has_lengthscale
         if has_lengthscale:
@@ -88,9 +90,17 @@ class Kernel(nn.Module):
                 raw.copy_(con.inverse_transform(torch.as_tensor(val).to(raw)).expand_as(raw))
         return self
 
+    def _refresh_columns(self):
+        ad = self.active_dims
+        tag = None if ad is None else (ad.data_ptr(), ad._version, ad.device)
+        if tag != self._columns_tag:
+            self._columns = None if ad is None else [int(v) for v in ad.reshape(-1).tolist()]
+            self._columns_tag = tag
+
     def _column(self):
         if self.active_dims is None:
             raise ValueError(f"{type(self).__name__} needs active_dims (a covariate column)")
+        self._refresh_columns()      # load_state_dict / reassignment of the buffer changes the tag (no device read otherwise)
         if len(self._columns) != 1:
             raise ValueError("only one covariate column per base kernel is supported")
         return self._columns[0]

@@ -21,6 +21,8 @@ from . import _lib
 # RNG stream advances identically (training.py never reads them).  The fused method skips them.
 PRODUCE_SAMPLES = True
 
+SUPPORTED_TYPES = tuple(_lib.VAR_KINDS)        # variable types the fused kernels evaluate
+
 
 class VarLayout:
     """Per-variable descriptors of the packed [N, E_x] data / [N, P_theta] parameter layout

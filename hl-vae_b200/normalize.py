@@ -40,12 +40,18 @@ class NormLayout:
 
 
 _layout_cache = {}
+_LAYOUT_CACHE_MAX = 16
 
 
 def _layout_for(types_info, device):
-    key = (id(types_info), str(device))
+    """Layout descriptors of `types_info`, cached by CONTENT ((type, nclass) per variable, conv flag, device): an
+    id()-keyed cache would hand a stale layout to a dict that was mutated in place or whose id CPython reused."""
+    key = (tuple((t['type'], int(t['nclass'])) for t in types_info['types_dict']), bool(types_info.get('conv', False)),
+           str(device))
     lay = _layout_cache.get(key)
     if lay is None:
+        if len(_layout_cache) >= _LAYOUT_CACHE_MAX:
+            _layout_cache.pop(next(iter(_layout_cache)))
         lay = NormLayout.from_types_info(types_info, device)
         _layout_cache[key] = lay
     return lay
@@ -58,6 +64,9 @@ def normalize(layout: NormLayout, data, mask, out_dtype=None):
         raise RuntimeError("hlvae_b200: batch normalisation runs on CUDA tensors only (no CPU fallback)")
     v = layout.var
     N = data.shape[0]
+    if data.dim() != 2 or data.shape[1] != v.E_x or mask.dim() != 2 or mask.shape[0] != N or mask.shape[1] != v.D:
+        raise ValueError(f"hlvae_b200: batch normalisation expects data [N, {v.E_x}] and mask [N, {v.D}], got "
+                         f"{tuple(data.shape)} and {tuple(mask.shape)}")
     if out_dtype is None:
         out_dtype = data.dtype if data.dtype in (torch.float32, torch.float64) else torch.float32
     dcode = _lib.F64 if out_dtype == torch.float64 else _lib.F32

@@ -37,6 +37,10 @@ class SubjectLayout:
     @staticmethod
     def fixed(n_rows, T, device):
         """Rows are subject-contiguous, T per subject (elbo_functions.py:144)."""
+        if T <= 0 or n_rows % T != 0:
+            # the reference's reshape([P_batch, T, Q]) (elbo_functions.py:144) raises as well; dropping the trailing
+            # rows silently would bias the loss
+            raise ValueError(f"hlvae_b200: {n_rows} rows are not a whole number of subjects of T = {T} rows")
         n_subj = n_rows // T
         return SubjectLayout._finish(torch.arange(n_subj * T), [T] * n_subj, device)
 

@@ -135,12 +135,6 @@ int hlvae_subject_matvec(const hlvae_kspec_t* spec, const double* outputscale, c
 #define HLVAE_NSCAL 4
 int hlvae_kl_acc_layout(int L, int M, int Q, int64_t* offsets /* [10] */);
 
-/* Scheduling hint, process-wide (the one exception to "no global state"; it never changes results): cap the
- * resident hlvae_kl_subject CTAs per SM at n (persistent grid striding over the (subject, l) pairs) so that the
- * HBM-bound likelihood kernels, launched on another stream, can share the SMs with this latency-bound kernel.
- * n = 0 (default): one warp per pair, as many CTAs per SM as fit. */
-int hlvae_set_subject_ctas_per_sm(int n);
-
 int hlvae_kl_subject(const hlvae_kspec_t* spec0, const double* os0, const double* ls0,
                      const hlvae_kspec_t* spec1, const double* os1, const double* ls1, const double* noise,
                      int L, int Q, const double* x, int64_t ldx,
