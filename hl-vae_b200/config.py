@@ -16,3 +16,8 @@ overlap = True
 # Drop-in HLVAE module (hl-vae_b200/dropin/HLVAE.py): also replace HLVAE.loglik_and_reconstruction
 # (HLVAE.py:381-414) by the fused method, which returns no `samples`.  Read when the drop-in is imported.
 fused_loglik_method = False
+
+# Keep the per-term pieces of the last KL call (the scalars A, B + sum(iB*K0), C, F per latent dimension, the
+# M x M pre-stage scalars, S, p, iK, G) on `hlvae_b200.elbo.last_terms` - what tests compare term by term with
+# elbo_functions.py:166-181 / :256-277.  Off by default (a few device copies per call).
+keep_terms = False

@@ -24,6 +24,7 @@ N_SM = 148
 PANEL_WAVES = 4        # waves of kl_panel CTAs per launch (see _subjects_per_chunk)
 
 _side_streams = {}
+last_terms = None      # see config.keep_terms
 
 
 def _side_stream(device):
@@ -146,6 +147,10 @@ class _KLD(torch.autograd.Function):
                   _lib.ptr(view("gls0", _lib.MAX_COMPS, L)), _lib.ptr(gZ), _lib.ptr(gZ), st)
         if config.check_errors:
             _raise_status(status, None)
+        if config.keep_terms:
+            global last_terms
+            last_terms = dict(scal=scal.clone(), pre=pre.clone(), S=S.clone(), p=p.clone(), iK=iK.clone(), G=G.clone(),
+                              H=H_c.clone(), iH=iH.clone(), kld_per_latent=kld[2:2 + L].clone(), scale=scale)
         nc0, nc1 = fs0.ncomp, fs1.ncomp
         grads = acc[off["gZ"]:off["total"]] * scale          # one launch for every replicated-parameter gradient
         o0 = off["gZ"]

@@ -40,7 +40,62 @@ def rel_err(a, b, scale=None):
     return float((a - b).abs().max()) / (den + 1e-300)
 
 
+def elem_err(a, b, rtol, afloor=1e-7):
+    """Element-wise check for per-row gradients (d_mu, d_logv, d_theta): the worst ratio
+    |a_i - b_i| / (rtol |b_i| + afloor max|b|); <= 1 passes.  Unlike rel_err (max-norm over the whole tensor) this
+    constrains the small entries too; the absolute floor only covers entries ~1e7 times smaller than the largest."""
+    a, b = torch.as_tensor(a, dtype=DT).cpu(), torch.as_tensor(b, dtype=DT).cpu()
+    if b.numel() == 0:
+        return 0.0
+    den = rtol * b.abs() + afloor * float(b.abs().max()) + 1e-300
+    return float(((a - b).abs() / den).max())
+
+
 # ---------------------------------------------------------------------------- KL
+def kl_terms_from_product(lt):
+    """ELBO terms of elbo_functions.py:166-181 / :256-277 assembled from what the kernels emit
+    (hlvae_b200.elbo.last_terms, config.keep_terms): per-latent scalars scal = [A, B + sum(iB * K0_st), C, F]
+    (hlvae_kl_subject / hlvae_kl_panel), the M x M pre-stage scalars pre = [log det K, log det H, tr(iK H),
+    m^T iK m] (hlvae_mxm_pre) and the statistics S.  The reference's D is sum(iB * K0_st) - tr(iK S), so B and D are
+    compared as B + D."""
+    scal, pre, S, iK, H = (lt[k].double().cpu() for k in ("scal", "pre", "S", "iK", "H"))
+    L, M = S.shape[0], S.shape[-1]
+    Ss = 0.5 * (S + S.transpose(-1, -2))
+    out = dict(A=scal[:, 0].sum(), C=scal[:, 2].sum(), F=scal[:, 3].sum())
+    out["B+D"] = scal[:, 1].sum() - (iK * Ss).sum()
+    out["E"] = ((iK @ H @ iK) * Ss).sum()
+    out["kld_qu_pu"] = 0.5 * (pre[:, 2].sum() + pre[:, 3].sum() - L * M + pre[:, 0].sum() - pre[:, 1].sum())
+    out["S"], out["p"] = S, lt["p"].double().cpu()
+    return out
+
+
+def trace_scales(iK, H, S):
+    """sum of the absolute addends of tr(iK S) and tr(iK H iK S)"""
+    iK, H, S = (torch.as_tensor(a, dtype=DT) for a in (iK, H, S))
+    return float((iK.abs() * S.abs()).sum()), float(((iK @ H @ iK).abs() * S.abs()).sum())
+
+
+def assert_terms_close(got, ref, tol, label=""):
+    """Per-term gate of BASELINE.md section 4.  |delta| <= tol * max(|term|, |largest ELBO term|) would let the huge
+    kld_qu_pu hide everything at the initial state, so each term is held to tol relative to ITSELF - except the two
+    traces against S, tr(iK S) in D and E = tr(iK H iK S): with cond(K0zz + eps I) ~ 1e7 two float64 inverses of the
+    same K0zz differ by ~1e-9 and the traces are sums of cancelling addends, so those two get the scale-aware bound of
+    SURVEY.md section 7: max(|term|, sum of the absolute addends) (`ref["scale_D"]`, `ref["scale_E"]`)."""
+    errs, bad = {}, {}
+    for k in ("A", "B+D", "C", "E", "F", "kld_qu_pu"):
+        g, r = float(got[k]), float(ref[k])
+        scale = max(abs(r), float(ref.get({"B+D": "scale_D", "E": "scale_E"}.get(k, ""), 0.0)), 1e-300)
+        errs[k] = abs(g - r) / scale
+        if errs[k] > tol:
+            bad[k] = errs[k]
+    for k in ("S", "p"):
+        errs[k] = rel_err(got[k].reshape(-1), torch.as_tensor(ref[k]).reshape(-1))
+        if errs[k] > tol:
+            bad[k] = errs[k]
+    assert not bad, f"{label} ELBO terms outside tolerance: {bad} (all: {errs})"
+    return errs
+
+
 def set_kernel_params(kmod, ros, rls):
     """Write raw_outputscale [ncomp, L] / raw_lengthscale [n_se, L] (depth-first SE order, the
     order the golden generator extracted them in) into a product kernel module."""
@@ -111,6 +166,10 @@ def assert_kl_close(r, tol=5e-6, hyper_tol=1e-4, label=""):
         for key in ("grad_m", "grad_H"):
             errs[key] = rel_err(got[key], g[key])
     bad = {k: v for k, v in errs.items() if v > tol}
+    for key in ("d_mu", "d_logv"):                       # per-row gradients: element-wise as well
+        errs[key + "/elem"] = elem_err(got[key], g[key], rtol=20 * tol)
+        if errs[key + "/elem"] > 1.0:
+            bad[key + "/elem"] = errs[key + "/elem"]
     for key in ("d_os0", "d_ls0", "d_os1", "d_ls1"):
         if g[key].size:
             errs[key] = rel_err(got[key], g[key])
@@ -213,6 +272,10 @@ def compare_kl(got, ref, tol, hyper_tol, label=""):
                 bad[key] = errs[key]
         elif errs[key] > tol:
             bad[key] = errs[key]
+        if key in ("d_mu", "d_logv"):
+            errs[key + "/elem"] = elem_err(got[key], ref[key], rtol=20 * tol)
+            if errs[key + "/elem"] > 1.0:
+                bad[key + "/elem"] = errs[key + "/elem"]
     assert not bad, f"{label} outside tolerance: {bad} (all: {errs})"
     return errs
 
@@ -264,6 +327,9 @@ def assert_loglik_close(r, tol=1e-9, label=""):
         if g[key].size and got[key] is not None:
             errs[key] = rel_err(got[key], g[key])
     bad = {k: v for k, v in errs.items() if v > tol}
+    errs["d_theta/elem"] = elem_err(got["d_theta"], g["d_theta"], rtol=20 * tol)
+    if errs["d_theta/elem"] > 1.0:
+        bad["d_theta/elem"] = errs["d_theta/elem"]
     assert not bad, f"{label} likelihood terms outside tolerance: {bad} (all: {errs})"
     disc = np.array([k in ("cat", "ordinal") for k, _ in r["types"]])
     gm = got["recon_mean"].detach().cpu().numpy()

@@ -23,6 +23,47 @@ def test_golden(name, device):
     print(name, {k: f"{v:.1e}" for k, v in errs.items()})
 
 
+@pytest.mark.parametrize("name", h.KL_CASES)
+def test_every_elbo_term_against_golden(name, device):
+    """BASELINE.md section 4 gate: A, B + D, C, E, F, kld_qu_pu (elbo_functions.py:166-181 / :256-277) and the
+    statistics S, p one by one - not only their sum kld_total - from what the kernels emit (scal, pre, S)."""
+    g = h.load(name)
+    config.keep_terms = True
+    try:
+        h.run_kl_golden(name, device)
+        got = h.kl_terms_from_product(elbo.last_terms)
+    finally:
+        config.keep_terms = False
+    ref = {k: g["term_" + k] for k in ("A", "C", "E", "F", "kld_qu_pu", "S", "p")}
+    ref["B+D"] = g["term_B"] + g["term_D"]
+    iK = torch.linalg.inv(torch.as_tensor(g["K0zz"]) + float(g["eps"]) * torch.eye(int(g["M"]), dtype=DT))
+    ref["scale_D"], ref["scale_E"] = h.trace_scales(iK, g["H"], g["term_S"])
+    errs = h.assert_terms_close(got, ref, tol=5e-6, label=name)
+    print(name, {k: f"{v:.1e}" for k, v in errs.items()})
+
+
+@pytest.mark.parametrize("L,M,n_subj,T,storage,tol", [(8, 64, 40, 20, torch.float64, 1e-6),
+                                                      (8, 64, 40, 20, torch.float32, 1e-4)])
+def test_every_elbo_term_against_oracle(L, M, n_subj, T, storage, tol, device):
+    """Same gate on fresh seeded inputs at M = 64 (the benchmark's M), float64 and float32 storage."""
+    from oracle import hlvae_oracle as orc
+    inp = h.make_kl_inputs(L, M, n_subj, T, seed=41)
+    config.keep_terms = True
+    try:
+        h.run_kl_product(inp, device, storage=storage)
+        got = h.kl_terms_from_product(elbo.last_terms)
+    finally:
+        config.keep_terms = False
+    ref = h.oracle_kl(inp["kargs"], L, inp["x"], inp["mu"].to(storage).to(DT), inp["lv"].to(storage).to(DT), inp["z"],
+                      inp["m"], inp["H"], inp["ros0"], inp["rls0"], inp["ros1"], inp["rls1"], inp["noise"], 200,
+                      n_subj, 200 * T, 1e-6)["terms"]
+    ref = {k: v.detach() for k, v in ref.items()}
+    ref["B+D"] = ref["B"] + ref["D"]
+    ref["scale_D"], ref["scale_E"] = h.trace_scales(ref["iK"], inp["H"], ref["S"])
+    errs = h.assert_terms_close(got, ref, tol=tol, label=f"terms M={M} {storage}")
+    print({k: f"{v:.1e}" for k, v in errs.items()})
+
+
 def test_golden_with_host_known_lengths(device):
     r = h.run_kl_golden("kl_default_ragged", device, layout="lengths")
     h.assert_kl_close(r, tol=5e-6, hyper_tol=1e-4)
