@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--subjects", type=int, default=SUBJ_PER_RANK)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the compact configs[2]/[3]/[4] figures of the default line")
     ap.add_argument("--eager", action="store_true", help="time eager launches instead of CUDA-graph replay")
     ap.add_argument("--no-overlap", action="store_true", help="single stream: no likelihood / KL overlap")
     ap.add_argument("--no-split-backward", action="store_true", help="one backward() of nll + kld instead of one per branch")
@@ -69,66 +70,96 @@ def parse():
 # ------------------------------------------------------------------------------------------
 # CPU arm: oracle port of the reference path on the host cores
 # ------------------------------------------------------------------------------------------
-def cpu_reference_arm(steps, warmup, sample_subjects=100, budget_s=25.0):
-    """Times oracle.elbo_path_step (float64 PyTorch restatement of training.py:82-137 for this path)
-    on a bounded sample: `sample_subjects` x T rows of the same workload.  Returns steps/s scaled
-    to the 16000-row step (cost is linear in rows; the replicated M x M part is not scaled down, so
-    the scaled figure slightly flatters the CPU)."""
+def cpu_sample_state(sample_subjects, Lx=L, Mx=M, Tx=T, types=None, conv=True, seed=0):
+    """One minibatch of the benchmark workload as float64 CPU tensors for oracle.elbo_path_step: `sample_subjects`
+    subjects x Tx rows, default additive kernel, D4 variable layout (or `types`)."""
     from hlvae_b200 import synth
     from oracle import hlvae_oracle as orc
-    torch.set_num_threads(os.cpu_count() or 1)
-    rng = np.random.default_rng(0)
-    gen = torch.Generator().manual_seed(0)
-    x, lens = synth.covariates(sample_subjects, T, rng)
-    pool, _ = synth.covariates(200, T, rng)
-    z = synth.inducing_points(pool, L, M, rng).requires_grad_(True)
+    rng = np.random.default_rng(seed)
+    gen = torch.Generator().manual_seed(seed)
+    x, lens = synth.covariates(sample_subjects, Tx, rng)
+    pool, _ = synth.covariates(200, Tx, rng)
+    z = synth.inducing_points(pool, Lx, Mx, rng).requires_grad_(True)
     N_b = x.shape[0]
-    types = synth.HEALTHMNIST_D4_TYPES
+    types = synth.HEALTHMNIST_D4_TYPES if types is None else types
     descs, E_x, P_th = orc.build_layout(types)
     data, mask = synth.likelihood_batch(types, N_b, rng, observed=0.75, pixel_like=True)
     spec0, spec1 = orc.compile_spec(**synth.DEFAULT_KERNEL_ARGS)
-    prm0 = orc.KernelParams.default(spec0, L).requires_grad_()
-    prm1 = orc.KernelParams.default(spec1, L).requires_grad_()
-    m, H = synth.variational_state(L, M, gen)
-    theta = torch.randn(N_b, P_th, generator=gen, dtype=torch.float64).requires_grad_(True)
-    mu = torch.randn(N_b, L, generator=gen, dtype=torch.float64).requires_grad_(True)
-    lv = (-3.0 * torch.rand(N_b, L, generator=gen, dtype=torch.float64)).requires_grad_(True)
-    lvr = torch.zeros(324, dtype=torch.float64, requires_grad=True)
-    state = dict(descs=descs, data=data, mask=mask, theta=theta, log_vy_real=lvr, conv=True, spec0=spec0, prm0=prm0,
-                 spec1=spec1, prm1=prm1, noise=torch.ones(L, dtype=torch.float64), m=m, H=H, x=x, mu=mu, log_v=lv,
-                 z=z, P=P_TOTAL, P_b=sample_subjects, N=N_TOTAL, id_covariate=2, eps=EPS,
-                 leaves=[theta, mu, lv, z, lvr, prm0.raw_outputscale, prm0.raw_lengthscale, prm1.raw_outputscale,
-                         prm1.raw_lengthscale])
-    times = []
+    prm0 = orc.KernelParams.default(spec0, Lx).requires_grad_()
+    prm1 = orc.KernelParams.default(spec1, Lx).requires_grad_()
+    m, H = synth.variational_state(Lx, Mx, gen)
+    # theta, mu, log_v as the benchmark stores them (float32 values), held in float64 for the oracle
+    f32 = lambda t_: t_.float().double()
+    theta = f32(torch.randn(N_b, P_th, generator=gen, dtype=torch.float64)).requires_grad_(True)
+    mu = f32(torch.randn(N_b, Lx, generator=gen, dtype=torch.float64)).requires_grad_(True)
+    lv = f32(-3.0 * torch.rand(N_b, Lx, generator=gen, dtype=torch.float64)).requires_grad_(True)
+    n_real = sum(1 for k, _ in types if k == "real")
+    lvr = torch.zeros(n_real, dtype=torch.float64, requires_grad=True)
+    return dict(descs=descs, data=data, mask=mask, theta=theta, log_vy_real=lvr, conv=conv, spec0=spec0, prm0=prm0,
+                spec1=spec1, prm1=prm1, noise=torch.ones(Lx, dtype=torch.float64), m=m, H=H, x=x, mu=mu, log_v=lv,
+                z=z, P=P_TOTAL, P_b=sample_subjects, N=N_TOTAL, id_covariate=2, eps=EPS, lens=lens,
+                leaves=[theta, mu, lv, z, lvr, prm0.raw_outputscale, prm0.raw_lengthscale, prm1.raw_outputscale,
+                        prm1.raw_lengthscale])
+
+
+def cpu_reference_arm(steps, warmup, sample_subjects=100, budget_s=25.0, keep_first=False, **kw):
+    """Times oracle.elbo_path_step (float64 PyTorch restatement of training.py:82-137 for this path) on all host
+    cores, on `sample_subjects` x T rows of the benchmark workload.  `value` is the MEASURED rate on that sample
+    converted to 16000-row step equivalents in proportion to the rows; with sample_subjects = 800 (the --impl reference
+    arm) the sample IS the 16000-row step and nothing is scaled.  (Measured: the oracle's cost grows faster than
+    linearly in the rows - 2000 rows x8 under-states the 16000-row step time about 4x - so a scaled small sample
+    flatters the CPU.)  Stops after `steps` timed steps or when `budget_s` is used up (at least one timed step)."""
+    from oracle import hlvae_oracle as orc
+    torch.set_num_threads(os.cpu_count() or 1)
+    state = cpu_sample_state(sample_subjects, **kw)
+    N_b = state["x"].shape[0]
+    times, first = [], None
     t_start = time.perf_counter()
     for i in range(warmup + steps):
         t0 = time.perf_counter()
         out = orc.elbo_path_step(state, NG_LR)
+        if i == 0 and keep_first:
+            first = dict(out, d_theta=state["theta"].grad.clone(), d_mu=state["mu"].grad.clone(),
+                         d_logv=state["log_v"].grad.clone(), d_z=state["z"].grad.clone(), m0=state["m"].clone(),
+                         H0=state["H"].clone())
         state["m"], state["H"] = out["m"], out["H"]
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
-        if time.perf_counter() - t_start > budget_s and len(times) >= 2:
+        if time.perf_counter() - t_start > budget_s and len(times) >= 1:
             break
     ms = 1e3 * pystat.median(times)
     scale = (SUBJ_PER_RANK * T) / N_b
+    note = "" if scale == 1 else f"; rate converted x{scale:.0f} in rows to 16000-row step equivalents"
     return dict(value=1e3 / (ms * scale), ms_sample_step=ms, steps_timed=len(times), cores=torch.get_num_threads(),
-                sample=f"{N_b} rows ({sample_subjects} subjects x T={T}) of the same workload per step, float64 oracle port; "
-                       f"scaled x{scale:.0f} in rows to the 16000-row step")
+                sample=f"{N_b} rows ({sample_subjects} subjects x T={T}) of the same workload per step, float64 oracle "
+                       f"port, {len(times)} timed steps" + note,
+                state=state, first=first)
 
 
 def run_reference(args):
+    """Reference arm: the oracle port of the reference's CPU path at the benchmark's OWN configuration - 16000 rows
+    per step, nothing scaled.  One such step takes tens of seconds on the host cores, so the arm does 1 warm-up step
+    and then as many timed steps as fit a 60 s budget (at least one) and reports the true count."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = cpu_reference_arm(max(args.steps, 2), max(args.warmup, 1))
-    line = dict(metric="ELBO train steps/sec (fwd+bwd)", value=r["value"], unit="steps/s", impl="reference",
-                n_gpus=args.gpus, steps=r["steps_timed"], warmup=max(args.warmup, 1),
-                ms_per_step=1e3 / r["value"], higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
-                data="synthetic", config=dict(workload=WORKLOAD, arm="oracle port of the reference CPU path "
-                                              "(the shipped reference needs gpytorch, absent on the box)"),
-                cpu_baseline=dict(value=r["value"], unit="steps/s", cores=r["cores"], kind="port", sample=r["sample"]),
-                e2e=dict(value=r["value"], unit="steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    r = cpu_reference_arm(max(args.steps, 1), 1, sample_subjects=SUBJ_PER_RANK, budget_s=60.0)
+    ms = r["ms_sample_step"]
+    small = cpu_reference_arm(5, 1, sample_subjects=100, budget_s=15.0)
+    c1 = cpu_reference_arm(5, 1, sample_subjects=20, budget_s=15.0, Mx=120)
+    line = dict(metric="ELBO train steps/sec (fwd+bwd)", value=1e3 / ms, unit="steps/s", impl="reference",
+                n_gpus=args.gpus, steps=r["steps_timed"], warmup=1, ms_per_step=ms, higher_is_better=True,
+                scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+                config=dict(workload=WORKLOAD, rows_per_step=SUBJ_PER_RANK * T,
+                            arm="oracle port of the reference CPU path (the shipped reference needs gpytorch, absent "
+                                "on the box), measured at the full 16000-row step; 1 warm-up, timed steps within a 60 s budget"),
+                cpu_baseline=dict(value=1e3 / ms, unit="steps/s", cores=r["cores"], kind="port", sample=r["sample"],
+                                  small_sample=dict(value=small["value"], sample=small["sample"]),
+                                  config1=dict(value=1e3 / c1["ms_sample_step"], unit="steps/s",
+                                               sample="BASELINE.json configs[0] shape: L=32, M=120, 400 rows (20 subjects x T=20), D4; "
+                                                      f"{c1['steps_timed']} timed steps")),
+                e2e=dict(value=1e3 / ms, unit="steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)
 
 
@@ -279,7 +310,118 @@ def elbo_step(s, world, inp=None):
         loss.backward()                                                                        # :127
     s["m"].copy_(m_new)
     s["H"].copy_(H_new)
+    s["last"] = dict(nll=nll.detach(), kld=kld.detach())
     return loss.detach()
+
+
+def gpu_state_from_cpu(dev, st, m0, H0):
+    """The oracle's sample minibatch (cpu_sample_state) in the benchmark's storage configuration: theta, mu, log_v
+    float32, data and mask uint8, covariates / Z / m / H float64, default kernel parameters."""
+    from hlvae_b200 import kernels, likelihoods, loglik, subjects, synth
+    k0, k1 = kernels.generate_kernel_batched(L, **synth.DEFAULT_KERNEL_ARGS)
+    k0, k1 = k0.to(dev).double(), k1.to(dev).double()
+    lik = likelihoods.GaussianLikelihood(batch_shape=torch.Size([L]), noise_constraint=likelihoods.GreaterThan(1e-8))
+    lik.noise = 1
+    lik = lik.to(dev).double()
+    lik.raw_noise.requires_grad = False
+    lay = loglik.VarLayout(synth.HEALTHMNIST_D4_TYPES, dev)
+    f32 = lambda a: a.detach().float().to(dev).requires_grad_(True)
+    return dict(k0=k0, k1=k1, lik=lik, z=st["z"].detach().to(dev).requires_grad_(True), m=m0.to(dev).clone(),
+                H=H0.to(dev).clone(), lay=lay, x=st["x"].to(dev), data=st["data"].to(torch.uint8).to(dev),
+                mask=st["mask"].to(torch.uint8).to(dev), theta=f32(st["theta"]), mu=f32(st["mu"]), lv=f32(st["log_v"]),
+                log_vy_real=torch.zeros(324, dtype=torch.float64, device=dev, requires_grad=True),
+                layout=subjects.SubjectLayout.from_lengths(st["lens"], dev), n_subj=len(st["lens"]),
+                N_b=st["x"].shape[0], side=None, side2=None)
+
+
+def parity_vs_oracle(dev, r, streams):
+    """The benchmarked step (float32 theta / mu / log_v, uint8 data and mask, the same streams and split backward)
+    against the float64 oracle on the cpu_baseline sample's first step: every value the step produces."""
+    st, first = r["state"], r["first"]
+    g = gpu_state_from_cpu(dev, st, first["m0"], first["H0"])
+    g.update(streams)
+    loss = elbo_step(g, 1)
+    torch.cuda.synchronize()
+    rel = lambda a, b: float((a.double().cpu() - b).abs().max() / (b.abs().max() + 1e-300))
+
+    def elem(a, b, rtol=1e-4, afloor=1e-7):
+        a = a.double().cpu()
+        return float(((a - b).abs() / (rtol * b.abs() + afloor * b.abs().max() + 1e-300)).max())
+
+    errs = dict(loss=rel(loss, first["loss"]), nll=rel(g["last"]["nll"], first["nll"]), kld=rel(g["last"]["kld"], first["kld"]),
+                m_new=rel(g["m"].reshape(-1), first["m"].reshape(-1)), H_new=rel(g["H"], first["H"]),
+                d_theta=rel(g["theta"].grad, first["d_theta"]), d_mu=rel(g["mu"].grad, first["d_mu"]),
+                d_logv=rel(g["lv"].grad, first["d_logv"]), d_z=rel(g["z"].grad, first["d_z"]))
+    worst_elem = dict(d_theta=elem(g["theta"].grad, first["d_theta"]), d_mu=elem(g["mu"].grad, first["d_mu"]),
+                      d_logv=elem(g["lv"].grad, first["d_logv"]))
+    return dict(against="float64 oracle port, first step of the cpu_baseline sample (same seeded inputs, float32-rounded "
+                        "theta / mu / log_v)", rows=int(st["x"].shape[0]), tol=1e-4, rel_err=errs,
+                elementwise_ratio_to_tol=worst_elem,
+                ok=bool(max(errs.values()) <= 1e-4 and max(worst_elem.values()) <= 1.0))
+
+
+def parity_sharded(dev, rank, world, n_subj_rank=64):
+    """Multi-GPU correctness inside the scaling run: the KL bound of a small global minibatch computed sharded over
+    the ranks (one all-reduce of the accumulators) against the same minibatch computed unsharded on rank 0."""
+    import torch.distributed as dist
+    from hlvae_b200 import config, elbo, kernels, likelihoods, subjects, synth
+    rng = np.random.default_rng(123)
+    gen = torch.Generator().manual_seed(123)
+    P_b = n_subj_rank * world
+    x, lens = synth.covariates(P_b, T, rng, ragged=True, t_min=5)
+    pool, _ = synth.covariates(200, T, rng)
+    z = synth.inducing_points(pool, L, M, rng).to(dev)
+    m, H = synth.variational_state(L, M, gen)
+    N_b = x.shape[0]
+    mu = torch.randn(N_b, L, generator=gen, dtype=torch.float64).to(dev)
+    lv = (-3.0 * torch.rand(N_b, L, generator=gen, dtype=torch.float64)).to(dev)
+    k0, k1 = kernels.generate_kernel_batched(L, **synth.DEFAULT_KERNEL_ARGS)
+    k0, k1 = k0.to(dev).double(), k1.to(dev).double()
+    lik = likelihoods.GaussianLikelihood(batch_shape=torch.Size([L]), noise_constraint=likelihoods.GreaterThan(1e-8))
+    lik.noise = 1
+    lik = lik.to(dev).double()
+    full = subjects.SubjectLayout.from_lengths(lens, dev)
+
+    def run(layout):
+        zz = z.clone().requires_grad_(True)
+        mm = mu.clone().requires_grad_(True)
+        kld, gm, gH = elbo.minibatch_KLD_upper_bound_iter(k0, k1, lik, L, m.to(dev), H.to(dev), x.to(dev), mm, lv, zz,
+                                                          P_TOTAL, P_b, N_TOTAL, True, 2, EPS, layout=layout)
+        kld.sum().backward()
+        return kld.detach().reshape(()), gm, gH, zz.grad, mm.grad
+
+    sh = run(full.shard(rank, world))
+    d_mu = sh[4].clone()
+    dist.all_reduce(d_mu)                    # rows are disjoint across ranks: the sum is the full gradient
+    out = None
+    if rank == 0:
+        pg, config.process_group = config.process_group, None
+        un = run(full)
+        config.process_group = pg
+        rel = lambda a, b: float((a - b).abs().max() / (b.abs().max() + 1e-300))
+        errs = dict(kld=rel(sh[0], un[0]), grad_m=rel(sh[1], un[1]), grad_H=rel(sh[2], un[2]), d_z=rel(sh[3], un[3]),
+                    d_mu=rel(d_mu, un[4]))
+        out = dict(against=f"the same {P_b}-subject ({N_b}-row) ragged minibatch unsharded on rank 0", world=world,
+                   rel_err=errs, tol=1e-6, ok=bool(max(errs.values()) <= 1e-6))
+    dist.barrier()
+    return out
+
+
+def allreduce_latency_us(dev, n_doubles, reps=50):
+    """Device time of one NCCL all-reduce of the accumulator buffer (CUDA events, average of `reps` back to back)."""
+    import torch.distributed as dist
+    buf = torch.zeros(n_doubles, dtype=torch.float64, device=dev)
+    for _ in range(5):
+        dist.all_reduce(buf)
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        dist.all_reduce(buf)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e3 / reps
 
 
 ALGO = {}
@@ -369,13 +511,17 @@ def run_gpu(args):
     sampler = ClockSampler(local)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     barrier()
     e0.record()
-    for _ in range(args.steps):
+    for i in range(args.steps):
         run_step()
+        marks[i].record()
     e1.record()
     barrier()
     total_ms = e0.elapsed_time(e1)
+    per_step = [(e0 if i == 0 else marks[i - 1]).elapsed_time(marks[i]) for i in range(args.steps)]
+    spread = dict(min=min(per_step), median=pystat.median(per_step), max=max(per_step))
     if world > 1:
         tt = torch.tensor([total_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -508,14 +654,32 @@ def run_gpu(args):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             dt = float(tt.item())
         e2e = dict(value=world * (n_rows / (SUBJ_PER_RANK * T)) * n_e2e / dt, unit="steps/s", h2d_bytes_per_step=h2d,
-                   d2h_bytes_per_step=8, steps=n_e2e,
+                   d2h_bytes_per_step=8, steps=n_e2e, h2d_gb_per_s_per_rank=h2d * n_e2e / dt / 1e9,
+                   bound="host -> device copies (PCIe 5 x16, ~55 GB/s per GPU; the ranks of one box share the host's "
+                         "memory and PCIe root bandwidth): the step itself needs a third of this time",
                    how="pinned host -> device copy of data, mask, covariates, theta, mu, log_v every step on a copy "
-                       "stream (double-buffered against the running step), loss copied back and read every step")
+                       "stream (double-buffered against the running step), loss copied back and read every step; the "
+                       "step's other products (g_theta, g_mu, g_logv, parameter gradients, m, H) stay on the device "
+                       "for the optimiser, as in training.py - and in training theta, mu, log_v would not come from "
+                       "the host either (the NN trunk produces them on the device): this is the worst case for the path")
 
-    cpu = None
+    cpu, parity = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference_arm(steps=10, warmup=1, budget_s=20.0)
-        cpu = dict(value=r["value"], unit="steps/s", cores=r["cores"], kind="port", sample=r["sample"])
+        r = cpu_reference_arm(steps=10, warmup=1, budget_s=20.0, keep_first=True)
+        cpu = dict(value=r["value"], unit="steps/s", cores=r["cores"], kind="port", sample=r["sample"],
+                   note="bounded sample for the default run; `bench.py --impl reference` measures the full 16000-row step")
+        config.check_errors = True
+        parity = parity_vs_oracle(dev, r, dict(side=s["side"], side2=s["side2"], split_backward=s["split_backward"]))
+        config.check_errors = False
+        del r
+    allreduce_us = None
+    if world > 1:
+        parity = parity_sharded(dev, rank, world)
+        off = _lib.acc_layout(L, M, Q)
+        allreduce_us = allreduce_latency_us(dev, off["total"] + 2 + L)
+    others = None
+    if rank == 0 and world == 1 and not args.no_sweep:
+        others = other_configs(dev, s, fp64_peak, hbm_peak)
 
     if rank == 0:
         line = dict(metric="ELBO train steps/sec (fwd+bwd)", value=value, unit="steps/s", n_gpus=world,
@@ -526,6 +690,7 @@ def run_gpu(args):
                                 l2="inputs larger than L2 (data + theta = 415 MB per step, 126 MB L2)",
                                 parallelism=f"dp{world}: subjects sharded, one all-reduce of accumulators" if world > 1 else "single GPU"),
                     clocks=sampler.summary(), e2e=e2e, gpu_launches=launches, roofline=roof, cpu_baseline=cpu,
+                    parity=parity, step_ms_spread=spread, allreduce_us=allreduce_us, other_configs=others,
                     kernels=kern, fp64_peak_tflops=fp64_peak, cuda_graph=use_graph, eager_ms_per_step=eager_ms,
                     overlap=not args.no_overlap, split_backward=not args.no_split_backward,
                     kl_stream_priority=not args.no_kl_priority,
@@ -857,83 +1022,78 @@ def run_norm(args):
                           hbm_peak_gbs=hbm_peak, steps=args.steps, cases=rows)), flush=True)
 
 
-def run_sweep(args):
-    """BASELINE.json configs[2] and configs[3] as tables (not the headline line):
-    (a) additive-kernel sweep - SE(time) + CA(id) + SE(age) x CA(sex), M in {32, 64, 128}, minibatch 4k / 16k / 64k
-        rows (T = 20; plus a ragged 16k case), L = 32: device time of one KL forward + backward
-        (hlvae_mxm_pre, hlvae_kl_subject, hlvae_kl_panel, hlvae_mxm_post, hlvae_kernel_eval_bwd) and of its
-        streaming kernels alone;
-    (b) likelihood-heavy tabular batch - 64 count + 64 ordinal(5) + 64 cat(5) + 32 real + 32 pos, 30 % missing,
-        16k / 64k rows, float32 storage: fused likelihood forward / backward time and GB/s of algorithmic bytes."""
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
-    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
-    torch.cuda.set_device(dev)
-    import __graft_entry__ as g
-    g.build()
-    from hlvae_b200 import _lib, config, elbo, kernels, likelihoods, loglik, subjects, synth
-    config.check_errors = False
-    config.overlap = False
-    hbm_peak, _ = measured_peaks()
-    reps = max(args.steps, 5)
+def _timed_profile(fn, reps):
+    from hlvae_b200 import _lib
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    _lib.PROFILE = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    per = {}
+    for name, a, b in _lib.PROFILE:
+        per.setdefault(name, []).append(a.elapsed_time(b))
+    _lib.PROFILE = None
+    return e0.elapsed_time(e1) / reps, {k: float(np.mean(v)) for k, v in per.items()}
 
-    def timed(fn):
-        for _ in range(3):
-            fn()
-        torch.cuda.synchronize()
-        _lib.PROFILE = []
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(reps):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        per = {}
-        for name, a, b in _lib.PROFILE:
-            per.setdefault(name, []).append(a.elapsed_time(b))
-        _lib.PROFILE = None
-        return e0.elapsed_time(e1) / reps, {k: float(np.mean(v)) for k, v in per.items()}
 
-    kl_rows = []
-    for Mx in (32, 64, 128):
-        for n_subj, ragged in ((200, False), (800, False), (800, True), (3200, False)):
-            rng = np.random.default_rng(7)
-            gen = torch.Generator().manual_seed(7)
-            x, lens = synth.covariates(n_subj, T, rng, ragged=ragged, t_min=5, continuous_age=True)
-            pool, _ = synth.covariates(400, T, np.random.default_rng(8), continuous_age=True)
-            z = synth.inducing_points(pool, L, Mx, np.random.default_rng(8)).to(dev).requires_grad_(True)
-            m, H = synth.variational_state(L, Mx, gen)
-            k0, k1 = kernels.generate_kernel_batched(L, **synth.SWEEP_KERNEL_ARGS)
-            k0, k1 = k0.to(dev).double(), k1.to(dev).double()
-            lik = likelihoods.GaussianLikelihood(batch_shape=torch.Size([L]), noise_constraint=likelihoods.GreaterThan(1e-8))
-            lik.noise = 1
-            lik = lik.to(dev).double()
-            N_b = x.shape[0]
-            mu = torch.randn(N_b, L, generator=gen).to(dev).requires_grad_(True)
-            lv = (-3.0 * torch.rand(N_b, L, generator=gen)).to(dev).requires_grad_(True)
-            lay = subjects.SubjectLayout.from_lengths(lens, dev)
-            xd, md, Hd = x.to(dev), m.to(dev), H.to(dev)
+def sweep_kl(dev, cases, reps, fp64_peak=None):
+    """BASELINE.json configs[2]: SE(time) + CA(id) + SE(age) x CA(sex), continuous ages, L = 32, T = 20; one row per
+    (M, subjects, ragged): device time of one KL forward + backward (eager, single stream) and of its kernels."""
+    from hlvae_b200 import elbo, kernels, likelihoods, subjects, synth
+    rows = []
+    for Mx, n_subj, ragged in cases:
+        rng = np.random.default_rng(7)
+        gen = torch.Generator().manual_seed(7)
+        x, lens = synth.covariates(n_subj, T, rng, ragged=ragged, t_min=5, continuous_age=True)
+        pool, _ = synth.covariates(400, T, np.random.default_rng(8), continuous_age=True)
+        z = synth.inducing_points(pool, L, Mx, np.random.default_rng(8)).to(dev).requires_grad_(True)
+        m, H = synth.variational_state(L, Mx, gen)
+        k0, k1 = kernels.generate_kernel_batched(L, **synth.SWEEP_KERNEL_ARGS)
+        k0, k1 = k0.to(dev).double(), k1.to(dev).double()
+        lik = likelihoods.GaussianLikelihood(batch_shape=torch.Size([L]), noise_constraint=likelihoods.GreaterThan(1e-8))
+        lik.noise = 1
+        lik = lik.to(dev).double()
+        N_b = x.shape[0]
+        mu = torch.randn(N_b, L, generator=gen).to(dev).requires_grad_(True)
+        lv = (-3.0 * torch.rand(N_b, L, generator=gen)).to(dev).requires_grad_(True)
+        lay = subjects.SubjectLayout.from_lengths(lens, dev)
+        xd, md, Hd = x.to(dev), m.to(dev), H.to(dev)
 
-            def step():
-                for t_ in (mu, lv, z, *k0.parameters(), *k1.parameters()):
-                    t_.grad = None
-                kld, gm, gH = elbo.minibatch_KLD_upper_bound_iter(k0, k1, lik, L, md, Hd, xd, mu, lv, z, P_TOTAL, n_subj,
-                                                                  N_TOTAL, True, 2, EPS, layout=lay)
-                kld.sum().backward()
+        def step():
+            for t_ in (mu, lv, z, *k0.parameters(), *k1.parameters()):
+                t_.grad = None
+            kld, gm, gH = elbo.minibatch_KLD_upper_bound_iter(k0, k1, lik, L, md, Hd, xd, mu, lv, z, P_TOTAL, n_subj,
+                                                              N_TOTAL, True, 2, EPS, layout=lay)
+            kld.sum().backward()
 
-            ms, per = timed(step)
-            stream = per.get("hlvae_kl_subject", 0.0) + per.get("hlvae_kl_panel", 0.0)
-            flops = 2.0 * L * N_b * Mx * Mx * 2 + 2.0 * L * N_b * T * Mx * 2
-            kl_rows.append(dict(M=Mx, rows=N_b, subjects=n_subj, ragged=ragged, kl_fwd_bwd_ms=round(ms, 3),
-                                kl_subject_ms=round(per.get("hlvae_kl_subject", 0.0), 3),
-                                kl_panel_ms=round(per.get("hlvae_kl_panel", 0.0), 3),
-                                panel_tflops=round(flops / (per["hlvae_kl_panel"] * 1e-3) / 1e12, 2),
-                                rows_per_s=round(N_b / (stream * 1e-3))))
-    ll_rows = []
+        ms, per = _timed_profile(step, reps)
+        stream = per.get("hlvae_kl_subject", 0.0) + per.get("hlvae_kl_panel", 0.0)
+        flops = 2.0 * L * N_b * Mx * Mx * 2 + 2.0 * L * N_b * T * Mx * 2
+        row = dict(M=Mx, rows=N_b, subjects=n_subj, ragged=ragged, kl_fwd_bwd_ms=round(ms, 3),
+                   kl_subject_ms=round(per.get("hlvae_kl_subject", 0.0), 3),
+                   kl_panel_ms=round(per.get("hlvae_kl_panel", 0.0), 3),
+                   panel_tflops=round(flops / (per["hlvae_kl_panel"] * 1e-3) / 1e12, 2),
+                   rows_per_s=round(N_b / (stream * 1e-3)))
+        if fp64_peak:
+            row["panel_frac_fp64_peak"] = round(row["panel_tflops"] / fp64_peak, 3)
+        rows.append(row)
+    return rows
+
+
+def sweep_tabular(dev, sizes, reps, hbm_peak):
+    """BASELINE.json configs[3]: 64 count + 64 ordinal(5) + 64 cat(5) + 32 real + 32 pos, 30 % missing, float32
+    storage: fused likelihood forward / backward device time and GB/s of algorithmic bytes."""
+    from hlvae_b200 import loglik, synth
+    rows = []
     types = synth.TABULAR_TYPES
     layt = loglik.VarLayout(types, dev)
     E_x, P_th = layt.E_x, layt.P_theta
-    for N_b in (16000, 64000):
+    for N_b in sizes:
         rng = np.random.default_rng(9)
         gen = torch.Generator(device=dev).manual_seed(9)
         data, mask = synth.likelihood_batch(types, 4000, rng)
@@ -950,17 +1110,82 @@ def run_sweep(args):
             out = loglik.fused_loglik(layt, data, mask, theta, vparam, monitor=True)
             (-out["log_p_x_sum"]).backward()
 
-        ms, per = timed(step)
+        ms, per = _timed_profile(step, reps)
         D = len(types)
         bf = N_b * (4 * E_x + 4 * P_th + D + 4 * (5 * D + P_th))
         bb = N_b * (4 * E_x + 4 * P_th + D + 4 * P_th)
-        ll_rows.append(dict(rows=N_b, D=D, fwd_ms=round(per["hlvae_loglik_fwd"], 3), bwd_ms=round(per["hlvae_loglik_bwd"], 3),
-                            fwd_gbs=round(bf / (per["hlvae_loglik_fwd"] * 1e-3) / 1e9), fwd_frac=round(bf / (per["hlvae_loglik_fwd"] * 1e-3) / 1e9 / hbm_peak, 3),
-                            bwd_gbs=round(bb / (per["hlvae_loglik_bwd"] * 1e-3) / 1e9), bwd_frac=round(bb / (per["hlvae_loglik_bwd"] * 1e-3) / 1e9 / hbm_peak, 3)))
+        rows.append(dict(rows=N_b, D=D, fwd_ms=round(per["hlvae_loglik_fwd"], 3), bwd_ms=round(per["hlvae_loglik_bwd"], 3),
+                         fwd_gbs=round(bf / (per["hlvae_loglik_fwd"] * 1e-3) / 1e9), fwd_frac=round(bf / (per["hlvae_loglik_fwd"] * 1e-3) / 1e9 / hbm_peak, 3),
+                         bwd_gbs=round(bb / (per["hlvae_loglik_bwd"] * 1e-3) / 1e9), bwd_frac=round(bb / (per["hlvae_loglik_bwd"] * 1e-3) / 1e9 / hbm_peak, 3)))
+    return rows
+
+
+def run_sweep(args):
+    """BASELINE.json configs[2] and configs[3] as tables (not the headline line): the kernel sweep at M in
+    {32, 64, 128} x {4k, 16k, 16k ragged, 64k} rows and the tabular likelihood batch at 16k / 64k rows."""
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    import __graft_entry__ as g
+    g.build()
+    from hlvae_b200 import config
+    config.check_errors = False
+    config.overlap = False
+    hbm_peak, _ = measured_peaks()
+    reps = max(args.steps, 5)
+    cases = [(Mx, n, r) for Mx in (32, 64, 128) for n, r in ((200, False), (800, False), (800, True), (3200, False))]
+    kl_rows = sweep_kl(dev, cases, reps)
+    ll_rows = sweep_tabular(dev, (16000, 64000), reps, hbm_peak)
     print(json.dumps(dict(workload="sweep: BASELINE.json configs[2] (kernel sweep, L=32, T=20, SE(time)+CA(id)+SE(age)xCA(sex)) "
                                    "and configs[3] (tabular likelihoods, 30 % missing, f32 storage)",
                           timing="CUDA events, eager single-stream launches, 3 warm-ups", kernel_sweep=kl_rows,
                           tabular_loglik=ll_rows, hbm_peak_gbs=hbm_peak)), flush=True)
+
+
+def other_configs(dev, s_small, fp64_peak, hbm_peak):
+    """Compact, driver-visible figures for the BASELINE.json configurations that are not the headline line
+    (configs[2], [3], [4]) and for float64 storage; eager single-stream launches, CUDA events, 5 repetitions."""
+    from hlvae_b200 import config
+    ov, config.overlap = config.overlap, False
+    out = {}
+    out["configs2_kernel_sweep_16k_rows"] = sweep_kl(dev, [(32, 800, False), (64, 800, False), (128, 800, False)], 5,
+                                                     fp64_peak)
+    out["configs3_tabular_64k_rows"] = sweep_tabular(dev, (64000,), 5, hbm_peak)[0]
+
+    def eager_ms(st, reps=5):
+        for _ in range(2):
+            elbo_step(st, 1)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            elbo_step(st, 1)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    big = build_gpu_state(dev, 3200, 0)
+    big.update(side=None, side2=None)
+    ms_big = eager_ms(big)
+    out["configs4_64000_rows_per_rank_step"] = dict(ms_per_step=round(ms_big, 3), rows=big["N_b"],
+                                                    rows_per_s=round(big["N_b"] / (ms_big * 1e-3)),
+                                                    step_equivalents_per_s=round(big["N_b"] / (SUBJ_PER_RANK * T) * 1e3 / ms_big, 1))
+    del big
+    torch.cuda.empty_cache()
+    f64 = dict(s_small)
+    f64.update(side=None, side2=None)
+    for k in ("theta", "mu", "lv"):
+        f64[k] = s_small[k].detach().double().requires_grad_(True)
+    for k in ("data", "mask"):
+        f64[k] = s_small[k].double()
+    f64["m"], f64["H"] = s_small["m"].clone(), s_small["H"].clone()
+    ms64 = eager_ms(f64)
+    out["float64_storage_step"] = dict(ms_per_step=round(ms64, 3), steps_per_s=round(1e3 / ms64, 1),
+                                       note="configs[1] with theta, mu, log_v, data, mask and every output float64 "
+                                            "(the reference's storage); eager single-stream launches")
+    config.overlap = ov
+    return out
 
 
 def main():
