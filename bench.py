@@ -126,6 +126,8 @@ def cpu_reference_arm(steps, warmup, sample_subjects=100, budget_s=25.0, keep_fi
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
+        else:
+            t_start = time.perf_counter()            # the budget covers the timed steps
         if time.perf_counter() - t_start > budget_s and len(times) >= 1:
             break
     ms = 1e3 * pystat.median(times)

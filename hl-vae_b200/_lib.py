@@ -52,6 +52,8 @@ _SIGS = {
     "hlvae_mxm_pre": ([C.POINTER(KSpec), _P, _P, _I, _I, _I, _P, _D, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P], _I),
     "hlvae_mxm_post": ([_I, _I, _D, _D, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P], _I),
     "hlvae_natgrad_update": ([_I, _I, _D, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P], _I),
+    "hlvae_mxm_aux": ([C.POINTER(KSpec), _P, _P, _I, _I, _I, _P, _D, _P, _P, _P, _P, _P, _P, _P, _P, _P], _I),
+    "hlvae_kernel_matvec": ([C.POINTER(KSpec), _P, _P, _I, _I, _P, _I, _P, _I, _P, _P, _P], _I),
     "hlvae_loglik_fwd": ([_L, _I, _L, _L, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P], _I),
     "hlvae_loglik_bwd": ([_L, _I, _L, _L, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P], _I),
     "hlvae_statistics": ([_L, _I, _L, _P, _P, _P, _P, _P, _I, _P, _P, _P], _I),

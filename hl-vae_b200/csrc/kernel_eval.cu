@@ -117,6 +117,25 @@ subject_matvec_k(const __grid_constant__ hlvae_kspec_t sp, const double* __restr
     out[(int64_t)i * L + l] = acc;
 }
 
+// out[i, l] = sum_j K_l(x1[i], x2[l, j]) v[l, j]: a dense block of the additive kernel applied to one vector per
+// latent dimension without materialising it (utils.py:169 / :249: K0Xz (iK K0zx mu_tilde)).  One warp per (row, l).
+__global__ void __launch_bounds__(EV_THREADS)
+kernel_matvec_k(const __grid_constant__ hlvae_kspec_t sp, const double* __restrict__ os,
+                const double* __restrict__ ls, int L, int Q, const double* __restrict__ x1, int n1,
+                const double* __restrict__ x2, int n2, const double* __restrict__ v, double* __restrict__ out) {
+    const int l = blockIdx.y;
+    KParams kp;
+    load_kparams(kp, sp, os, ls, L, l);
+    const int i = blockIdx.x * (EV_THREADS / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i >= n1) return;
+    const double* xa = x1 + (int64_t)i * Q;
+    double acc = 0.0;
+    for (int j = lane; j < n2; j += 32)
+        acc = fma(eval_additive(sp, kp, xa, x2 + ((int64_t)l * n2 + j) * Q), v[(int64_t)l * n2 + j], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) out[(int64_t)i * L + l] = acc;
+}
+
 }  // namespace
 
 namespace hlvae {
@@ -168,6 +187,19 @@ extern "C" int hlvae_subject_matvec(const hlvae_kspec_t* spec, const double* out
     dim3 grid((unsigned)((nt + EV_THREADS - 1) / EV_THREADS), (unsigned)L);
     subject_matvec_k<<<grid, EV_THREADS, 0, (cudaStream_t)stream>>>(*spec, outputscale, lengthscale, L, Q, xt, nt, x,
                                                                     row_idx, subj_ptr, sid, v, out);
+    HLVAE_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int hlvae_kernel_matvec(const hlvae_kspec_t* spec, const double* outputscale, const double* lengthscale,
+                                   int L, int Q, const double* x1, int n1, const double* x2, int n2, const double* v,
+                                   double* out, void* stream) {
+    if (!spec_ok(spec, Q) || L <= 0 || Q <= 0 || Q > HLVAE_MAX_Q || n1 < 0 || n2 < 0 || !x1 || !x2 || !v || !out)
+        return HLVAE_E_ARG;
+    if (n1 == 0) return 0;
+    dim3 grid((unsigned)((n1 + EV_THREADS / 32 - 1) / (EV_THREADS / 32)), (unsigned)L);
+    kernel_matvec_k<<<grid, EV_THREADS, 0, (cudaStream_t)stream>>>(*spec, outputscale, lengthscale, L, Q, x1, n1, x2,
+                                                                   n2, v, out);
     HLVAE_CHECK_LAUNCH();
     return 0;
 }

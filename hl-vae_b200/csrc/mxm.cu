@@ -396,6 +396,96 @@ natgrad_k(int L, int M, double lr, const double* __restrict__ m, const double* _
     }
 }
 
+// =====================================================================================
+// M x M epilogue shared by the evaluation-time users of the streaming statistics S = K0zx iB K0xz, p = K0zx iB y:
+//   W = K0zz + eps I + sym(S)          (elbo_functions.py:43-45,91-93; validation.py:54-56; utils.py:136,158)
+//   scal = [log det(K0zz + eps I), log det W, |L_W^-1 p|^2, sum(S * iK)]     (:47-53,95-105 / validation.py:57-66)
+//   a = W^-1 p (utils.py:162 / :246),  c = (K0zz + eps I)^-1 (p - S a) = iK K0zx mu_tilde (utils.py:169 / :249),
+//   iW = W^-1 (validation.py:71, elbo_functions.py:111)
+// Cholesky factors + explicit triangular inverses in float64; every output is optional.
+__global__ void __launch_bounds__(MX_THREADS)
+mxm_aux_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__ os0, const double* __restrict__ ls0,
+          int L, int Q, int M, const double* __restrict__ z, double eps, const double* __restrict__ S,
+          const double* __restrict__ p, double* __restrict__ scal, double* __restrict__ a_out,
+          double* __restrict__ c_out, double* __restrict__ iW_out, double* __restrict__ ws,
+          int32_t* __restrict__ status) {
+    extern __shared__ double smem[];
+    const int l = blockIdx.x, tid = threadIdx.x;
+    Bufs B = carve(smem, M, ws, l);
+    double* tmp = B.vec;            // [M]
+    double* pv = B.vec + M;         // [M] p
+    double* yv = B.vec + 2 * M;     // [M] L_W^-1 p, later p - S a
+    double* av = B.vec + 3 * M;     // [M] a
+    double* red = B.vec + 4 * M;
+    const size_t mm_off = (size_t)l * M * M;
+    KParams kp;
+    load_kparams(kp, sp0, os0, ls0, L, l);
+    const double* zl = z + (size_t)l * M * Q;
+    Mat A = B.b[0], P1 = B.b[1], P2 = B.b[2], Wm = B.b[3];
+    for (int e = tid; e < M * M; e += MX_THREADS) {
+        const int i = e / M, j = e % M;
+        const double k = eval_additive(sp0, kp, zl + i * Q, zl + j * Q) + (i == j ? eps : 0.0);
+        A(i, j) = k;
+        const double s = S ? 0.5 * (S[mm_off + e] + S[mm_off + (size_t)j * M + i]) : 0.0;
+        Wm(i, j) = k + s;
+    }
+    for (int i = tid; i < M; i += MX_THREADS) pv[i] = p ? p[(size_t)l * M + i] : 0.0;
+    __syncthreads();
+    double logdetK = 0.0, logdetW = 0.0;
+    if (!chol(A, M, tmp, logdetK)) {
+        if (tid == 0) report_status(status, HLVAE_STATUS_NOT_PD, l, -1);
+        return;
+    }
+    tri_inv(P1, A, M);
+    ata_lower(P2, P1, M, nullptr);                                     // iK
+    double trS = 0.0;
+    if (S)
+        for (int e = tid; e < M * M; e += MX_THREADS) trS = fma(S[mm_off + e], P2(e / M, e % M), trS);
+    trS = block_sum(trS, red);
+    if (!chol(Wm, M, tmp, logdetW)) {
+        if (tid == 0) report_status(status, HLVAE_STATUS_NOT_PD, l, -5);
+        return;
+    }
+    tri_inv(P1, Wm, M);                                                // L_W^-1 (lower)
+    for (int i = tid; i < M; i += MX_THREADS) {
+        double s = 0.0;
+        for (int k = 0; k <= i; k++) s = fma(P1(i, k), pv[k], s);
+        yv[i] = s;
+    }
+    __syncthreads();
+    double qf2 = 0.0;
+    for (int i = tid; i < M; i += MX_THREADS) qf2 = fma(yv[i], yv[i], qf2);
+    qf2 = block_sum(qf2, red);
+    for (int i = tid; i < M; i += MX_THREADS) {                        // a = L_W^-T y
+        double s = 0.0;
+        for (int k = i; k < M; k++) s = fma(P1(k, i), yv[k], s);
+        av[i] = s;
+        if (a_out) a_out[(size_t)l * M + i] = s;
+    }
+    __syncthreads();
+    if (c_out) {
+        for (int i = tid; i < M; i += MX_THREADS) {                    // p - S a  (S as accumulated, not symmetrised)
+            double s = 0.0;
+            if (S)
+                for (int k = 0; k < M; k++) s = fma(S[mm_off + (size_t)i * M + k], av[k], s);
+            yv[i] = pv[i] - s;
+        }
+        __syncthreads();
+        for (int i = tid; i < M; i += MX_THREADS) {
+            double s = 0.0;
+            for (int k = 0; k < M; k++) s = fma(P2(i, k), yv[k], s);
+            c_out[(size_t)l * M + i] = s;
+        }
+    }
+    if (iW_out) ata_lower(A, P1, M, iW_out + mm_off);
+    if (tid == 0 && scal) {
+        scal[l * 4 + 0] = logdetK;
+        scal[l * 4 + 1] = logdetW;
+        scal[l * 4 + 2] = qf2;
+        scal[l * 4 + 3] = trS;
+    }
+}
+
 template <typename K>
 int set_smem(K kern, size_t bytes) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
@@ -454,6 +544,21 @@ extern "C" int hlvae_natgrad_update(int L, int M, double lr, const double* m, co
     int rc = set_smem(natgrad_k, smem);
     if (rc) return rc;
     natgrad_k<<<L, MX_THREADS, smem, (cudaStream_t)stream>>>(L, M, lr, m, H, iH, grad_m, grad_H, m_out, H_out, ws,
+                                                             status);
+    HLVAE_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int hlvae_mxm_aux(const hlvae_kspec_t* spec0, const double* os0, const double* ls0, int L, int Q, int M,
+                             const double* z, double eps, const double* S, const double* p, double* scal, double* a,
+                             double* c, double* iW, double* ws, int32_t* status, void* stream) {
+    if (!hlvae::spec_valid(spec0, Q) || L <= 0 || Q <= 0 || Q > HLVAE_MAX_Q || M <= 0 || !z) return HLVAE_E_ARG;
+    if (M > 128) return HLVAE_E_UNSUPPORTED;
+    if (M > 64 && !ws) return HLVAE_E_ARG;
+    size_t smem = mx_smem_bytes(M);
+    int rc = set_smem(mxm_aux_k, smem);
+    if (rc) return rc;
+    mxm_aux_k<<<L, MX_THREADS, smem, (cudaStream_t)stream>>>(*spec0, os0, ls0, L, Q, M, z, eps, S, p, scal, a, c, iW, ws,
                                                              status);
     HLVAE_CHECK_LAUNCH();
     return 0;

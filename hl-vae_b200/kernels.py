@@ -150,7 +150,7 @@ class ScaleKernel(Kernel):
             kwargs["active_dims"] = base_kernel.active_dims
         super().__init__(batch_shape=batch_shape, **kwargs)
         self.base_kernel = base_kernel
-        self.register_parameter("raw_outputscale", nn.Parameter(torch.zeros(*self.batch_shape)))
+        self.register_parameter("raw_outputscale", nn.Parameter(torch.zeros(self.batch_shape)))
         self.raw_outputscale_constraint = _Positive()
 
     @property
@@ -356,32 +356,62 @@ def evaluate_dense(kernel, x1, x2):
 # --------------------------------------------------------------------------------------
 # kernel_gen.generate_kernel_batched
 # --------------------------------------------------------------------------------------
-def generate_kernel_batched(latent_dim, cat_kernel, bin_kernel, sqexp_kernel, cat_int_kernel, bin_int_kernel,
-                            covariate_missing_val, id_covariate):
-    """Same signature, component order and module structure as kernel_gen.py:199-310:
-    returns (additive kernel without the id covariate, additive kernel with it)."""
-    bs = torch.Size([latent_dim])
+def _build_additive(bs, cat_kernel, bin_kernel, sqexp_kernel, cat_int_kernel, bin_int_kernel, covariate_missing_val,
+                    id_covariate):
+    """The two additive kernels every generator of kernel_gen.py assembles - same component order (categorical,
+    squared-exponential, binary, categorical x continuous, binary x continuous), same masking by BinKernel factors
+    of missing covariates, same module tree; `bs` is the batch shape of the hyper-parameters and `id_covariate`
+    (None: everything goes to the first kernel) routes the terms that carry the id covariate to the second."""
     missing = {d['covariate']: d['mask'] for d in covariate_missing_val}
     k0, k1 = AdditiveKernel(), AdditiveKernel()
+    kw = {} if bs is None else dict(batch_shape=bs)
 
     def with_mask(k, col):
         return k * BinKernel(active_dims=missing[col], value=1) if col in missing else k
 
-    for idx in cat_kernel:                                                   # :225-242
-        (k1 if idx == id_covariate else k0).kernels.append(
-            ScaleKernel(with_mask(CatKernel(active_dims=idx), idx), batch_shape=bs))
-    for idx in sqexp_kernel:                                                 # :245-254
-        k0.kernels.append(ScaleKernel(with_mask(RbfKernel(active_dims=idx, batch_shape=bs), idx), batch_shape=bs))
-    for idx in bin_kernel:                                                   # :257-266
-        k0.kernels.append(ScaleKernel(with_mask(BinKernel(active_dims=idx, value=1), idx), batch_shape=bs))
-    for d in cat_int_kernel:                                                 # :269-289
+    def rbf(col):
+        return RbfKernel(active_dims=col, batch_shape=bs)
+
+    def is_id(col):
+        return id_covariate is not None and col == id_covariate
+
+    for idx in cat_kernel:                                                   # :225-242 / :27-35 / :121-137
+        (k1 if is_id(idx) else k0).kernels.append(ScaleKernel(with_mask(CatKernel(active_dims=idx), idx), **kw))
+    for idx in sqexp_kernel:                                                 # :245-254 / :38-46 / :140-148
+        k0.kernels.append(ScaleKernel(with_mask(rbf(idx), idx), **kw))
+    for idx in bin_kernel:                                                   # :257-266 / :49-57 / :151-159
+        k0.kernels.append(ScaleKernel(with_mask(BinKernel(active_dims=idx, value=1), idx), **kw))
+    for d in cat_int_kernel:                                                 # :269-289 / :60-75 / :162-181
         a = with_mask(CatKernel(active_dims=d['cat_covariate']), d['cat_covariate'])
-        b = with_mask(RbfKernel(active_dims=d['cont_covariate'], batch_shape=bs), d['cont_covariate'])
-        (k1 if d['cat_covariate'] == id_covariate else k0).kernels.append(
-            ScaleKernel(ProductKernel(a, b), batch_shape=bs))
-    for d in bin_int_kernel:                                                 # :292-308
+        b = with_mask(rbf(d['cont_covariate']), d['cont_covariate'])
+        (k1 if is_id(d['cat_covariate']) else k0).kernels.append(ScaleKernel(ProductKernel(a, b), **kw))
+    for d in bin_int_kernel:                                                 # :292-308 / :78-93 / :184-195
         a = with_mask(BinKernel(active_dims=d['bin_covariate'], value=1), d['bin_covariate'])
-        b = with_mask(RbfKernel(active_dims=d['cont_covariate'], batch_shape=bs), d['cont_covariate'])
-        k0.kernels.append(ScaleKernel(ProductKernel(a, b), batch_shape=bs))
+        b = with_mask(rbf(d['cont_covariate']), d['cont_covariate'])
+        k0.kernels.append(ScaleKernel(ProductKernel(a, b), **kw))
+    return k0, k1
+
+
+def generate_kernel_batched(latent_dim, cat_kernel, bin_kernel, sqexp_kernel, cat_int_kernel, bin_int_kernel,
+                            covariate_missing_val, id_covariate):
+    """Same signature, component order and module structure as kernel_gen.py:199-310:
+    returns (additive kernel without the id covariate, additive kernel with it), hyper-parameters batched over the
+    latent dimensions."""
+    k0, k1 = _build_additive(torch.Size([latent_dim]), cat_kernel, bin_kernel, sqexp_kernel, cat_int_kernel,
+                             bin_int_kernel, covariate_missing_val, id_covariate)
     device = torch.device("cuda" if torch.cuda.is_available() else "cpu")    # :219, :310
     return k0.to(device), k1.to(device)
+
+
+def generate_kernel_approx(cat_kernel, bin_kernel, sqexp_kernel, cat_int_kernel, bin_int_kernel, covariate_missing_val,
+                           id_covariate):
+    """kernel_gen.py:97-197: the un-batched pair (one latent dimension per kernel object), as
+    elbo_functions.elbo / deviance_upper_bound take them."""
+    return _build_additive(None, cat_kernel, bin_kernel, sqexp_kernel, cat_int_kernel, bin_int_kernel,
+                           covariate_missing_val, id_covariate)
+
+
+def generate_kernel(cat_kernel, bin_kernel, sqexp_kernel, cat_int_kernel, bin_int_kernel, covariate_missing_val):
+    """kernel_gen.py:9-94: ONE un-batched additive kernel holding every term."""
+    return _build_additive(None, cat_kernel, bin_kernel, sqexp_kernel, cat_int_kernel, bin_int_kernel,
+                           covariate_missing_val, None)[0]

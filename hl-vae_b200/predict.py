@@ -7,8 +7,10 @@ SURVEY.md section 8(f) row 1, built on the kernels of the ELBO path:
                         p = K0zx iB mu and, through its d/dmu output, iB mu itself       (:159 / :245);
                         a second call with w = a, mu = 0 gives -iB K0xz a                (:162-166 / :246-247)
   * hlvae_kernel_eval_fwd - the dense blocks K0zz, K0xz, K0Xz, K1Xx                     (:128-130,169,175-186)
-and float64 torch.linalg solves for the two M x M systems (the reference's `torch.solve` calls at
-:162,169 / :246,249 no longer exist in torch).  Evaluation-time code: no autograd, CUDA tensors only.
+  * hlvae_mxm_aux     - the two M x M solves (the reference's `torch.solve` calls at :162,169 / :246,249 no longer
+                        exist in torch): a = (K0zz + S)^-1 p and c = K0zz^-1 K0zx mu_tilde = K0zz^-1 (p - S a)
+  * hlvae_kernel_matvec - K0Xz c without materialising K0Xz                           (:169 / :249)
+Evaluation-time code: no autograd, CUDA tensors only, no library (cuBLAS / cuSOLVER) call on the path.
 """
 from __future__ import annotations
 
@@ -78,18 +80,25 @@ def _predict(latent_dim, covar_module0, covar_module1, likelihoods, prediction_x
         fs0, fs1 = compile_spec(covar_module0), compile_spec(covar_module1)
         hp = tuple(t.detach().contiguous() for pair in (fs0.constrained(L, dev), fs1.constrained(L, dev)) for t in pair)
         noise = _noise_vector(likelihoods, L, dev)
-        eye = torch.eye(M, dtype=torch.float64, device=dev)
-        K0zz = evaluate_dense(covar_module0, z, z) + eps * eye                             # :129,132 / :230,234
         zero_w = torch.zeros(L, M, dtype=torch.float64, device=dev)
         # S = sum_s K0zx_s iB_s K0xz_s, p = K0zx iB mu, iB mu  (:139-160 / :236-245)
         S, p, iB_mu, binv = _stream_pass(fs0, fs1, hp, L, Q, M, x, z, layout, mu64, zero_w, noise)
-        a = torch.linalg.solve(K0zz + S, p.unsqueeze(2)).squeeze(2).contiguous()            # :162 / :246
+        # a = (K0zz + eps I + S)^-1 p (:162 / :246) and, since K0zx mu_tilde = K0zx iB (mu - K0xz a) = p - S a,
+        # c = (K0zz + eps I)^-1 (p - S a) (:169 / :249) - one launch, no dense K0xz
+        a = torch.empty(L, M, dtype=torch.float64, device=dev)
+        c = torch.empty(L, M, dtype=torch.float64, device=dev)
+        status = torch.zeros(4, dtype=torch.int32, device=dev)
+        _lib.call("hlvae_mxm_aux", fs0.cspec, _lib.ptr(hp[0]), _lib.ptr(hp[1]), L, Q, M, _lib.ptr(z), float(eps),
+                  _lib.ptr(S.contiguous()), _lib.ptr(p.contiguous()), None, _lib.ptr(a), _lib.ptr(c), None,
+                  _lib.ptr(_lib.workspace(L, M, dev)), _lib.ptr(status), _lib.stream_ptr())
+        if int(status[0]) == _lib.STATUS_NOT_PD:
+            raise RuntimeError("hlvae_b200: cholesky: K0zz + eps I (+ K0zx iB K0xz) is not positive-definite")
         # -iB K0xz a  (:162-166 / :246-247)
         _, _, corr, _ = _stream_pass(fs0, fs1, hp, L, Q, M, x, z, layout, torch.zeros_like(mu64), a, noise, binv=binv)
         mu_tilde = iB_mu + corr                                                             # [N, L]  (:167 / :248)
-        K0xz = evaluate_dense(covar_module0, x, z)                                          # [L, N, M]
-        rhs = torch.bmm(K0xz.transpose(1, 2), mu_tilde.T.unsqueeze(2))                      # K0zx mu_tilde
-        first = torch.bmm(evaluate_dense(covar_module0, xt, z), torch.linalg.solve(K0zz, rhs))   # :169 / :249
+        first = torch.empty(xt.shape[0], L, dtype=torch.float64, device=dev)                # K0Xz c  (:169 / :249)
+        _lib.call("hlvae_kernel_matvec", fs0.cspec, _lib.ptr(hp[0]), _lib.ptr(hp[1]), L, Q, _lib.ptr(xt), xt.shape[0],
+                  _lib.ptr(z), M, _lib.ptr(c), _lib.ptr(first), _lib.stream_ptr())
         # K1(X*, x) mu_tilde over the conditioning rows whose subject appears in test_x (:171-186 / :251-267)
         id_rows = all(any(fs1.cspec.comp[r].disc_kind[f] == _lib.KIND_CAT and fs1.cspec.comp[r].disc_col[f] == id_covariate
                           for f in range(fs1.cspec.comp[r].ndisc)) for r in range(fs1.ncomp))
@@ -106,16 +115,17 @@ def _predict(latent_dim, covar_module0, covar_module1, likelihoods, prediction_x
             _lib.call("hlvae_subject_matvec", fs1.cspec, _lib.ptr(hp[2]), _lib.ptr(hp[3]), L, Q, _lib.ptr(xt), xt.shape[0],
                       _lib.ptr(x), _lib.ptr(layout.row_idx), _lib.ptr(layout.subj_ptr), _lib.ptr(sid), _lib.ptr(mt),
                       _lib.ptr(out2), _lib.stream_ptr())
-            return (first.squeeze(2).T + out2).contiguous()                                 # :188 / :269
+            return (first + out2).contiguous()                                              # :188 / :269
         test_ids = torch.unique(xt[:, id_covariate])
         mask = torch.isin(x[:, id_covariate], test_ids)
         second = torch.zeros_like(first)
         if bool(mask.any()):
+            # a K1 term without the id kernel (not produced by kernel_gen.py, kept for API completeness): dense block
             xm = x[mask].contiguous()
             K1Xx = evaluate_dense(covar_module1, xt.unsqueeze(0).expand(L, *xt.shape).contiguous(),
                                   xm.unsqueeze(0).expand(L, *xm.shape).contiguous())
-            second = torch.bmm(K1Xx, mu_tilde[mask].T.unsqueeze(2))
-        return (first + second).squeeze(2).T.contiguous()                                   # :188 / :269
+            second = (K1Xx * mu_tilde[mask].T.unsqueeze(1)).sum(2).T
+        return (first + second).contiguous()                                                # :188 / :269
 
 
 def batch_predict_varying_T(latent_dim, covar_module0, covar_module1, likelihoods, prediction_x, test_x, mu, zt_list,

@@ -95,6 +95,13 @@ int hlvae_subject_matvec(const hlvae_kspec_t* spec, const double* outputscale, c
                          int L, int Q, const double* xt, int nt, const double* x, const int32_t* row_idx,
                          const int32_t* subj_ptr, const int32_t* sid, const double* v, double* out, void* stream);
 
+/* K(x1, x2_l) v_l without materialising the block: out[i, l] = sum_j K_l(x1[i], x2[l, j]) v[l, j], the
+ * K0Xz (iK K0zx mu_tilde) product of the GP posterior-mean predictors (utils.py:169 / :249).
+ * x1 [n1,Q], x2 [L,n2,Q], v [L,n2], out [n1,L] float64 row-major. */
+int hlvae_kernel_matvec(const hlvae_kspec_t* spec, const double* outputscale, const double* lengthscale,
+                        int L, int Q, const double* x1, int n1, const double* x2, int n2, const double* v,
+                        double* out, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * Streaming part of the KL upper bound: everything in
  * elbo_functions.minibatch_KLD_upper_bound (elbo_functions.py:118-193) and
@@ -179,6 +186,18 @@ int hlvae_mxm_post(int L, int M, double c0, double constant, const double* iK, c
 int hlvae_natgrad_update(int L, int M, double lr, const double* m, const double* H, const double* iH,
                          const double* grad_m, const double* grad_H, double* m_out, double* H_out, double* ws,
                          int32_t* status, void* stream);
+
+/* M x M epilogue of the evaluation-time bounds and predictors (one CTA per latent dimension, float64):
+ * from the streaming statistics S = K0zx iB K0xz [L,M,M] and p = K0zx iB y [L,M] (either nullable = 0), with
+ * W = K0zz + eps I + sym(S):
+ *   scal[l] = {log det(K0zz + eps I), log det W, |L_W^-1 p|^2, sum(S * iK)}
+ *             (elbo_functions.py:47-53 / :95-105, validation.py:57-66)
+ *   a = W^-1 p (utils.py:162 / :246), c = (K0zz + eps I)^-1 (p - S a) (utils.py:169 / :249), iW = W^-1
+ *   (validation.py:71, elbo_functions.py:111) - each output nullable.
+ * Replaces the removed torch.solve calls of the reference; `ws` as in hlvae_mxm_pre. */
+int hlvae_mxm_aux(const hlvae_kspec_t* spec0, const double* os0, const double* ls0, int L, int Q, int M,
+                  const double* z, double eps, const double* S, const double* p, double* scal, double* a,
+                  double* c, double* iW, double* ws, int32_t* status, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Fused masked heterogeneous log-likelihood.  Replaces HLVAE.loglik_and_reconstruction

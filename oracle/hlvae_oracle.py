@@ -351,6 +351,46 @@ def validation_dubo(spec0, prm0, spec1, prm1, noise, x, m, log_v, z, P: int, T: 
     return total.reshape(1)
 
 
+def deviance_upper_bound(spec0, prm0, spec1, prm1, noise, x, m, log_v, z, P: int, T: int, eps: float) -> torch.Tensor:
+    """elbo_functions.deviance_upper_bound (elbo_functions.py:60-115): ONE latent dimension (parameters [n, 1], m and
+    log_v [P T], z [M, Q]).  Line for line the l-th summand of validation_dubo above (validation.py:48-75 is the
+    batched copy of :75-114), so it is evaluated through it."""
+    return validation_dubo(spec0, prm0, spec1, prm1, noise, x, m.reshape(-1, 1), log_v.reshape(-1, 1),
+                           z.reshape(1, *z.shape[-2:]), P, T, eps).reshape(())
+
+
+def elbo(spec0, prm0, spec1, prm1, noise, x, y, z, P: int, T: int, eps: float) -> torch.Tensor:
+    """elbo_functions.elbo (elbo_functions.py:9-57): collapsed evidence lower bound of one latent dimension for a
+    sample y [P T] of the latent; parameters [n, 1], z [M, Q]; `torch.solve(y_st, B_st)` (:47) is B_st^-1 y_st."""
+    M = z.shape[-2]
+    z1 = z.reshape(1, M, -1)
+    xs = x.reshape(P, T, -1)
+    K0xz = eval_additive(spec0, prm0, x, z1)[0]                                # :29
+    K0zz = eval_additive(spec0, prm0, z1, z1)[0] + eps * torch.eye(M, dtype=DT)   # :30
+    LK = torch.linalg.cholesky(K0zz)
+    iK = torch.cholesky_inverse(LK)                                           # :31-32
+    X4 = xs.unsqueeze(1)                                                      # [P, 1, T, Q]
+    K0_st = eval_additive(spec0, prm0, X4, X4)[:, 0]                          # :33
+    B_st = eval_additive(spec1, prm1, X4, X4)[:, 0] + torch.eye(T, dtype=DT) * noise.reshape(())   # :34-35
+    LB = torch.linalg.cholesky(B_st)
+    iB = torch.cholesky_inverse(LB)                                           # :36-37
+    iB_K = iB @ K0xz.reshape(P, T, M)                                         # :39
+    S = K0xz.T @ iB_K.reshape(P * T, M)                                       # :40
+    W = K0zz + S
+    W = (W + W.T) / 2                                                         # :41-42
+    LW = torch.linalg.cholesky(W)
+    logdet = -2 * torch.log(torch.diagonal(LK)).sum() + 2 * torch.log(torch.diagonal(LB, dim1=-2, dim2=-1)).sum() \
+        + 2 * torch.log(torch.diagonal(LW)).sum()                             # :44-47
+    y_st = y.reshape(P, T, 1)
+    iB_y = iB @ y_st                                                          # :48
+    qF1 = (y_st * iB_y).sum()
+    p = K0xz.T @ iB_y.reshape(P * T)
+    qF2 = (torch.linalg.solve_triangular(LW, p[:, None], upper=False) ** 2).sum()   # :51
+    tr = (iB * K0_st).sum() - (S * iK).sum()                                  # :53
+    log_like = -0.5 * T * P * math.log(2 * math.pi) - 0.5 * (logdet + qF1 - qF2)    # :54-55
+    return log_like - 0.5 * tr                                                # :56
+
+
 # --------------------------------------------------------------------------------------
 # Heterogeneous likelihoods (HL_VAE/loglik.py) on the packed [N, E_x] / [N, P_theta] layout
 # --------------------------------------------------------------------------------------

@@ -504,6 +504,68 @@ def dubo_case(name, kargs, L, M, n_subj, T, seed, continuous_age=False):
     print(f"  {name}: N={N} dubo={float(d):.6e} rel diff {w:.2e}")
 
 
+def legacy_bound_case(name, kargs, M, n_subj, T, seed, continuous_age=False):
+    """elbo_functions.deviance_upper_bound (:60-115) and elbo_functions.elbo (:9-57) of the unmodified reference on
+    UN-BATCHED kernel objects (kernel_gen.generate_kernel_approx, :97-197), one latent dimension; `torch.solve`
+    shimmed."""
+    rng = np.random.default_rng(seed)
+    gen = torch.Generator().manual_seed(seed)
+    x, lens = synth.covariates(n_subj, T, rng, continuous_age=continuous_age)
+    pool, _ = synth.covariates(40, T, rng, continuous_age=continuous_age)
+    z = synth.inducing_points(torch.cat([x, pool]), 1, M, rng)[0]
+    N = x.shape[0]
+    mu = torch.randn(N, generator=gen, dtype=DT)
+    lv = -3.0 * torch.rand(N, generator=gen, dtype=DT)
+    k0, k1 = ref_kernel_gen.generate_kernel_approx(kargs['cat_kernel'], kargs['bin_kernel'], kargs['sqexp_kernel'],
+                                                   kargs['cat_int_kernel'], kargs['bin_int_kernel'],
+                                                   kargs['covariate_missing_val'], kargs['id_covariate'])
+    lik = gpytorch.likelihoods.GaussianLikelihood(noise_constraint=gpytorch.constraints.GreaterThan(1.0e-8))
+    lik.noise = 1
+    k0.double(); k1.double(); lik.double()
+    with torch.no_grad():
+        for k in (k0, k1):
+            for p in k.parameters():
+                p.add_(0.3 * torch.randn(p.shape, generator=gen, dtype=DT))
+    k0.eval(); k1.eval(); lik.eval()
+    eps = 1e-6
+    had, old = hasattr(torch, "solve"), getattr(torch, "solve", None)
+    torch.solve = lambda B, A: (torch.linalg.solve(A, B), None)
+    try:
+        with torch.no_grad():
+            d = ref_elbo.deviance_upper_bound(k0, k1, lik, x, mu, lv, z, n_subj, T, eps)
+            e = ref_elbo.elbo(k0, k1, lik, x, mu, z, n_subj, T, eps)
+    finally:
+        if had:
+            torch.solve = old
+        else:
+            del torch.solve
+    spec0, spec1 = orc.compile_spec(**kargs)
+    def params_1(kmod):              # raw parameters of un-batched modules as [n, 1] (one latent dimension)
+        ros = torch.stack([k.raw_outputscale.detach().reshape(1).clone() for k in kmod.kernels])
+        rls = [mod.raw_lengthscale.detach().reshape(1).clone() for mod in kmod.modules()
+               if isinstance(mod, gpytorch.kernels.RBFKernel)]
+        return ros, (torch.stack(rls) if rls else torch.zeros(0, 1, dtype=DT))
+
+    ros0, rls0 = params_1(k0)
+    ros1, rls1 = params_1(k1)
+    noise = lik.noise_covar.noise.detach().reshape(-1).clone()
+    prm0, prm1 = orc.KernelParams(ros0.clone(), rls0.clone()), orc.KernelParams(ros1.clone(), rls1.clone())
+    with torch.no_grad():
+        od = orc.deviance_upper_bound(spec0, prm0, spec1, prm1, noise, x, mu, lv, z, n_subj, T, eps)
+        oe = orc.elbo(spec0, prm0, spec1, prm1, noise, x, mu, z, n_subj, T, eps)
+    w = max(check(name + ".dubo", od, d, 1e-8), check(name + ".elbo", oe, e, 1e-8))
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), kargs=repr(kargs), M=M, T=T, n_subj=n_subj, eps=eps,
+                        x=x.numpy(), mu=mu.numpy(), log_v=lv.numpy(), z=z.numpy(), noise=noise.numpy(), ros0=ros0.numpy(),
+                        rls0=rls0.numpy(), ros1=ros1.numpy(), rls1=rls1.numpy(), dubo=d.numpy(), elbo=e.numpy())
+    print(f"  {name}: N={N} dubo={float(d):.6e} elbo={float(e):.6e} rel diff {w:.2e}")
+
+
+def legacy_bound_cases():
+    print("un-batched deviance_upper_bound / elbo: oracle vs unmodified reference (torch.solve shimmed)")
+    legacy_bound_case("legacy_bounds_default", synth.DEFAULT_KERNEL_ARGS, M=12, n_subj=6, T=8, seed=41)
+    legacy_bound_case("legacy_bounds_sweep", synth.SWEEP_KERNEL_ARGS, M=16, n_subj=5, T=10, seed=42, continuous_age=True)
+
+
 def predict_cases():
     print("GP posterior-mean prediction: oracle vs unmodified reference (torch.solve shimmed)")
     predict_case("predict_default_ragged", synth.DEFAULT_KERNEL_ARGS, L=4, M=12, n_subj=6, T=8, ragged=True, seed=21)
@@ -522,6 +584,9 @@ def main():
         return
     if len(sys.argv) > 1 and sys.argv[1] == "samplers":
         sampler_cases()
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "legacy":       # only the un-batched bound fixtures
+        legacy_bound_cases()
         return
     if len(sys.argv) > 1 and sys.argv[1] == "norm":         # only the batch-normalisation fixtures
         norm_cases()
@@ -549,6 +614,7 @@ def main():
                 N=16, seed=12)
     loglik_case("loglik_conv_d4", synth.HEALTHMNIST_D4_TYPES, N=3, seed=13, conv=True, observed=0.75)
     predict_cases()
+    legacy_bound_cases()
     theta_cases()
     norm_cases()
     sampler_cases()

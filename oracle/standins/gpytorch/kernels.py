@@ -104,7 +104,7 @@ class ScaleKernel(Kernel):
             kwargs["active_dims"] = base_kernel.active_dims
         super().__init__(**kwargs)
         self.base_kernel = base_kernel
-        self.register_parameter("raw_outputscale", torch.nn.Parameter(torch.zeros(*self.batch_shape)))
+        self.register_parameter("raw_outputscale", torch.nn.Parameter(torch.zeros(self.batch_shape)))
         self.raw_outputscale_constraint = outputscale_constraint or Positive()
 
     @property

@@ -31,7 +31,9 @@ assert training.minibatch_KLD_upper_bound_iter is E.minibatch_KLD_upper_bound_it
 assert kernel_gen.generate_kernel_batched is K.generate_kernel_batched
 assert kernel_spec.CatKernel is K.CatKernel and kernel_spec.BinKernel is K.BinKernel
 assert HLVAE.loglik is loglik and loglik.loglik_cat is LL.loglik_cat and loglik.loglik_ordinal is LL.loglik_ordinal
-assert callable(validation.deviance_upper_bound) and callable(elbo_functions.elbo)    # passed through from the reference
+from hlvae_b200 import validation as VA0
+assert validation.deviance_upper_bound is VA0.deviance_upper_bound and elbo_functions.elbo is VA0.elbo
+assert kernel_gen.generate_kernel_approx is K.generate_kernel_approx and kernel_gen.generate_kernel is K.generate_kernel
 assert training.read_functions is read_functions and hasattr(read_functions, "read_data")
 assert read_functions.statistics.__module__.endswith("read_functions") and "hl-vae_b200" in read_functions.__file__
 import utils as RU, model_test

@@ -91,3 +91,26 @@ def test_dubo_against_oracle_larger(device):
     got = validation.validation_dubo(L, k0.eval(), k1.eval(), lik.eval(), inp["x"].to(device), inp["mu"].to(device),
                                      inp["lv"].to(device), inp["z"].to(device), n_subj, T, 1e-6)
     assert h.rel_err(got, ref) < 1e-6
+
+
+@pytest.mark.parametrize("name", ["legacy_bounds_default", "legacy_bounds_sweep"])
+def test_unbatched_bounds_golden(name, device):
+    """elbo_functions.deviance_upper_bound (:60-115) and elbo_functions.elbo (:9-57) on UN-BATCHED kernel objects
+    (kernel_gen.generate_kernel_approx, :97-197) against the frozen outputs of the unmodified reference."""
+    from hlvae_b200 import kernels, likelihoods
+    g = h.load(name)
+    kargs = ast.literal_eval(str(g["kargs"]))
+    k0, k1 = kernels.generate_kernel_approx(kargs['cat_kernel'], kargs['bin_kernel'], kargs['sqexp_kernel'],
+                                            kargs['cat_int_kernel'], kargs['bin_int_kernel'],
+                                            kargs['covariate_missing_val'], kargs['id_covariate'])
+    k0, k1 = k0.to(device).double(), k1.to(device).double()
+    h.set_kernel_params(k0, h.t(g["ros0"], device), h.t(g["rls0"], device))
+    h.set_kernel_params(k1, h.t(g["ros1"], device), h.t(g["rls1"], device))
+    lik = likelihoods.GaussianLikelihood(noise_constraint=likelihoods.GreaterThan(1.0e-8)).to(device).double()
+    lik.noise = h.t(g["noise"], device).reshape(1)
+    x, mu, lv, z = (h.t(g[k], device) for k in ("x", "mu", "log_v", "z"))
+    P, T, eps = int(g["n_subj"]), int(g["T"]), float(g["eps"])
+    d = validation.deviance_upper_bound(k0.eval(), k1.eval(), lik.eval(), x, mu, lv, z, P, T, eps)
+    e = validation.elbo(k0, k1, lik, x, mu, z, P, T, eps)
+    assert d.shape == () and e.shape == ()
+    assert h.rel_err(d, g["dubo"]) < 1e-8 and h.rel_err(e, g["elbo"]) < 1e-8

@@ -99,6 +99,23 @@ def test_oracle_dubo_matches_reference_goldens(name):
     assert h.rel_err(d, g["dubo"]) < 1e-9
 
 
+@pytest.mark.parametrize("name", ["legacy_bounds_default", "legacy_bounds_sweep"])
+def test_oracle_unbatched_bounds_match_reference_goldens(name):
+    """elbo_functions.deviance_upper_bound (:60-115) and elbo_functions.elbo (:9-57), one latent dimension,
+    un-batched kernels: oracle restatement vs the unmodified reference."""
+    import ast
+    g = h.load(name)
+    kargs = ast.literal_eval(str(g["kargs"]))
+    spec0, spec1 = orc.compile_spec(**kargs)
+    prm0 = orc.KernelParams(h.t(g["ros0"]), h.t(g["rls0"]))
+    prm1 = orc.KernelParams(h.t(g["ros1"]), h.t(g["rls1"]))
+    args = (spec0, prm0, spec1, prm1, h.t(g["noise"]), h.t(g["x"]))
+    d = orc.deviance_upper_bound(*args, h.t(g["mu"]), h.t(g["log_v"]), h.t(g["z"]), int(g["n_subj"]), int(g["T"]),
+                                 float(g["eps"]))
+    e = orc.elbo(*args, h.t(g["mu"]), h.t(g["z"]), int(g["n_subj"]), int(g["T"]), float(g["eps"]))
+    assert h.rel_err(d, g["dubo"]) < 1e-9 and h.rel_err(e, g["elbo"]) < 1e-9
+
+
 @pytest.mark.parametrize("name", h.THETA_CASES)
 def test_oracle_theta_matches_reference_goldens(name):
     """HLVAE.theta_estimation (HLVAE.py:416-453): oracle restatement vs the unmodified reference's outputs."""
