@@ -19,6 +19,7 @@ MAX_COMPS, MAX_DISC, MAX_Q, TMAX, MAX_CLASS, MAX_Y = 8, 3, 8, 32, 16, 16
 HEAD_AFFINE, HEAD_SIGMOID, HEAD_ZERO, HEAD_BIAS = 0, 1, 2, 3
 F32, F64, U8 = 0, 1, 2
 KIND_CAT, KIND_BIN = 1, 2
+AUX_REAL, AUX_POS, AUX_BETA = 0, 1, 2
 VAR_KINDS = {"real": 0, "pos": 1, "count": 2, "cat": 3, "ordinal": 4}
 ACC_NAMES = ("S", "p", "gw", "scal", "gZ", "gos0", "gls0", "gos1", "gls1", "total")
 NSCAL = 4
@@ -58,6 +59,8 @@ _SIGS = {
     "hlvae_loglik_bwd": ([_L, _I, _L, _L, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P], _I),
     "hlvae_statistics": ([_L, _I, _L, _P, _P, _P, _P, _P, _I, _P, _P, _P], _I),
     "hlvae_discrete_transform": ([_L, _I, _L, _P, _P, _P, _P, _I, _P, _P], _I),
+    "hlvae_loglik_aux_fwd": ([_I, _L, _I, _P, _L, _I, _P, _L, _I, _P, _L, _L, _P, _L, _I, _P, _P, _P, _P, _P, _P, _P], _I),
+    "hlvae_loglik_aux_bwd": ([_I, _L, _I, _P, _L, _I, _P, _L, _I, _P, _L, _L, _P, _L, _I, _P, _P, _P, _P, _P, _P, _P, _P], _I),
     "hlvae_batch_norm_stats": ([_L, _I, _L, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _P, _P], _I),
     "hlvae_batch_norm_apply": ([_L, _I, _L, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P], _I),
     "hlvae_theta_fwd": ([_L, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _L, _L, _L, _I, _P, _L, _P], _I),

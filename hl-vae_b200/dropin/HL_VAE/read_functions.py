@@ -18,36 +18,23 @@ for _p in __import__("HL_VAE").__path__[1:]:
         globals().update({k: v for k, v in vars(_ref).items() if not k.startswith("__")})
         break
 
-_layouts = {}
+_layouts = {}          # content-keyed (types, device), see hlvae_b200.normalize._layout_for
 
 
-def _layout(types_info, device):
-    key = (id(types_info), str(device))
-    if key not in _layouts:
-        _layouts[key] = _ll.VarLayout.from_types_info(types_info, device)
-    return _layouts[key]
-
-
-def _require(types_info, tensor, what):
-    bad = sorted({t['type'] for t in types_info['types_dict']} - set(_ll.SUPPORTED_TYPES))
-    if bad:
-        raise NotImplementedError(f"hlvae_b200: {what}: variable types {bad} are not supported by the CUDA kernels")
+def _require_cuda(tensor, what):
     if not tensor.is_cuda:
         raise RuntimeError(f"hlvae_b200: {what} runs on CUDA tensors only (no CPU fallback)")
 
 
 def statistics(loglik_params, types_info, device, conv=False, log_vy=None):
-    _require(types_info, loglik_params, "statistics")
-    lay = _layout(types_info, loglik_params.device)
-    lv_pos = None
-    if log_vy is not None and lay.idx["pos"].numel():
-        lv_pos = log_vy[1]
-    vparam = torch.zeros(4, lay.D, dtype=torch.float64, device=loglik_params.device)
-    if lv_pos is not None:
-        vparam[2, lay.idx["pos"]] = lv_pos.detach().to(torch.float64)[lay.gpos["pos"]]
-    return _ll.statistics(lay, loglik_params, vparam)
+    _require_cuda(loglik_params, "statistics")
+    return _ll.statistics_general(loglik_params, types_info, conv, log_vy)
 
 
 def discrete_variables_transformation(data, types_info):
-    _require(types_info, data, "discrete_variables_transformation")
-    return _ll.discrete_variables_transformation(_layout(types_info, data.device), data)
+    _require_cuda(data, "discrete_variables_transformation")
+    types = [("real" if t['type'] == "beta" else t['type'], int(t['nclass'])) for t in types_info['types_dict']]
+    key = (tuple(types), str(data.device))
+    if key not in _layouts:
+        _layouts[key] = _ll.VarLayout(types, data.device)
+    return _ll.discrete_variables_transformation(_layouts[key], data)

@@ -207,11 +207,94 @@ def _run_group(kind, C, batch_data, theta, vp_builder):
     return out, N, Dg
 
 
+class _AuxLoglik(torch.autograd.Function):
+    """One type group through hlvae_loglik_aux_fwd / _bwd: (th_a, th_b | raw dispersion) -> log_p_x, log_p_x_missing,
+    prm_a, prm_b, each [N, Dg].  th_a / th_b may be column slices of theta (row stride passed as is); th_a [N, 1]
+    with col_stride_a = 0 is read by every variable of the group."""
+
+    @staticmethod
+    def forward(ctx, th_a, th_b, data, mask, vparam, mode, cs_a):
+        if not th_a.is_cuda:
+            raise RuntimeError("hlvae_b200: likelihoods run on CUDA tensors only (no CPU fallback)")
+        N, Dg = data.shape
+        dt = th_a.dtype
+        dcode = _lib.dtype_code(th_a)
+        ta = th_a.detach()
+        ta = ta if ta.stride(-1) == 1 or ta.shape[1] == 1 else ta.contiguous()
+        beta = mode == _lib.AUX_BETA
+        if beta:
+            tb = th_b.detach().to(torch.float64).reshape(-1)[:1].contiguous()      # extra_params[0], loglik.py:240
+        else:
+            tb = th_b.detach().to(dt)
+            tb = tb if tb.stride(-1) == 1 else tb.contiguous()
+        da, da_code = _storage_code(data, dt, "data")
+        mk, mk_code = _storage_code(mask, dt, "mask")
+        vp = vparam.detach().to(torch.float64).contiguous()
+        new = lambda: torch.empty(N, Dg, dtype=dt, device=ta.device)
+        lpx, lpm, pa, pb = new(), new(), new(), new()
+        ctx.args = (mode, N, Dg, da_code, mk_code, cs_a, dcode)
+        ctx.save_for_backward(ta, tb, da, mk, vp)
+        ctx.shape_b, ctx.dtype_b = th_b.shape, th_b.dtype
+        _lib.call("hlvae_loglik_aux_fwd", mode, N, Dg, _lib.ptr(da), da.stride(0), da_code, _lib.ptr(mk), mk.stride(0),
+                  mk_code, _lib.ptr(ta), ta.stride(0), cs_a, None if beta else _lib.ptr(tb),
+                  0 if beta else tb.stride(0), dcode, _lib.ptr(vp), _lib.ptr(tb) if beta else None, _lib.ptr(lpx),
+                  _lib.ptr(lpm), _lib.ptr(pa), _lib.ptr(pb), _lib.stream_ptr())
+        ctx.mark_non_differentiable(lpm, pa, pb)
+        return lpx, lpm, pa, pb
+
+    @staticmethod
+    def backward(ctx, g_lpx, g_lpm, g_pa, g_pb):
+        ta, tb, da, mk, vp = ctx.saved_tensors
+        mode, N, Dg, da_code, mk_code, cs_a, dcode = ctx.args
+        beta = mode == _lib.AUX_BETA
+        g = g_lpx.to(ta.dtype).contiguous()
+        g_a = torch.empty(N, Dg, dtype=ta.dtype, device=ta.device)
+        g_b = None if beta else torch.empty(N, Dg, dtype=ta.dtype, device=ta.device)
+        g_disp = torch.zeros(1, dtype=torch.float64, device=ta.device) if beta else None
+        _lib.call("hlvae_loglik_aux_bwd", mode, N, Dg, _lib.ptr(da), da.stride(0), da_code, _lib.ptr(mk), mk.stride(0),
+                  mk_code, _lib.ptr(ta), ta.stride(0), cs_a, None if beta else _lib.ptr(tb),
+                  0 if beta else tb.stride(0), dcode, _lib.ptr(vp), _lib.ptr(tb) if beta else None, _lib.ptr(g), None,
+                  _lib.ptr(g_a), _lib.ptr(g_b), _lib.ptr(g_disp), _lib.stream_ptr())
+        if cs_a == 0:
+            g_a = g_a.sum(1, keepdim=True)
+        if beta:
+            g_second = torch.zeros(ctx.shape_b, dtype=torch.float64, device=ta.device).reshape(-1)
+            g_second[0] = g_disp[0]
+            g_second = g_second.reshape(ctx.shape_b).to(ctx.dtype_b)
+        else:
+            g_second = g_b
+        return g_a, g_second, None, None, None, None, None
+
+
+def _aux_vparam(Dg, device, mean=None, var=None, div=None):
+    vp = torch.zeros(4, Dg, dtype=torch.float64, device=device)
+    vp[1] = 1.0
+    vp[3] = 1.0
+    if mean is not None:
+        vp[0] = torch.as_tensor(mean, dtype=torch.float64, device=device).reshape(-1).expand(Dg)
+    if var is not None:
+        vp[1] = torch.as_tensor(var, dtype=torch.float64, device=device).reshape(-1).expand(Dg)
+    if div is not None:
+        vp[3] = div
+    return vp
+
+
 def loglik_real(batch_data, list_type, theta, normalization_params, extra_params=None):
-    """HL_VAE/loglik.py:27-70."""
-    if extra_params is None:
-        raise NotImplementedError("loglik_real with a variance network (extra_params=None) is not supported")
+    """HL_VAE/loglik.py:27-70.  `extra_params` = the per-variable log-variance parameter (logvar_network=False) or
+    None (logvar_network=True, :45-48: theta holds the means followed by per-row raw log-variances)."""
     norm = None if (isinstance(normalization_params, list) and normalization_params == []) else normalization_params
+    if extra_params is None:
+        data, mask = batch_data
+        N, Dg = data.shape
+        if theta.shape[1] < 2 * Dg:
+            raise IndexError("loglik_real without extra_params expects theta = [means, log-variances] (2 D columns)")
+        vp = _aux_vparam(Dg, theta.device, None if norm is None else norm[0],
+                         None if norm is None else torch.clamp(norm[1].to(torch.float64), min=3e-4))       # :36-41
+        lpx, lpm, mean, var = _AuxLoglik.apply(theta[:, :Dg], theta[:, Dg:2 * Dg], data, mask.float(), vp,
+                                               _lib.AUX_REAL, 1)
+        res = {'log_p_x': lpx, 'log_p_x_missing': lpm, 'params': [mean, var]}                                # :64-65
+        res['samples'] = td.Normal(mean, torch.sqrt(var)).rsample() if PRODUCE_SAMPLES else None
+        return res
     out, N, Dg = _run_group("real", 1, batch_data, theta[:, :batch_data[0].shape[1]],
                             lambda lay: lay.vparam(log_vy_real=extra_params, norm_real=norm))
     res = {'log_p_x': out['log_p_x'], 'log_p_x_missing': out['log_p_x_missing'], 'params': out['params']}
@@ -225,15 +308,55 @@ def loglik_real(batch_data, list_type, theta, normalization_params, extra_params
 
 
 def loglik_pos(batch_data, list_type, theta, normalization_params, extra_params=None):
-    """HL_VAE/loglik.py:73-121."""
+    """HL_VAE/loglik.py:73-121; extra_params None -> per-row log-variances from theta (:89,104-108)."""
     if extra_params is None:
-        raise NotImplementedError("loglik_pos with a variance network (extra_params=None) is not supported")
+        data, mask = batch_data
+        N, Dg = data.shape
+        if theta.shape[1] < 2 * Dg:
+            raise UnboundLocalError("loglik_pos without extra_params expects theta = [means, log-variances]")
+        vp = _aux_vparam(Dg, theta.device, normalization_params[0],
+                         torch.clamp(normalization_params[1].to(torch.float64), min=1e-3))                  # :79-80
+        lpx, lpm, mean, var = _AuxLoglik.apply(theta[:, :Dg], theta[:, Dg:2 * Dg], data, mask.float(), vp,
+                                               _lib.AUX_POS, 1)
+        res = {'log_p_x': lpx, 'log_p_x_missing': lpm, 'params': [mean, var]}                                # :114-115
+        res['samples'] = torch.clamp(torch.exp(td.Normal(mean, torch.sqrt(var)).rsample()) - 1.0, 0, 1e20) \
+            if PRODUCE_SAMPLES else None
+        return res
     out, N, Dg = _run_group("pos", 1, batch_data, theta[:, :batch_data[0].shape[1]],
                             lambda lay: lay.vparam(log_vy_pos=extra_params, norm_pos=normalization_params))
     res = {'log_p_x': out['log_p_x'], 'log_p_x_missing': out['log_p_x_missing'], 'params': out['params']}
     if PRODUCE_SAMPLES:
         est_var = torch.clamp(normalization_params[1], 1e-3, np.inf) * torch.exp(extra_params)
         res['samples'] = torch.clamp(torch.exp(td.Normal(out['params'], torch.sqrt(est_var)).rsample()) - 1.0, 0, 1e20)  # :118-119
+    else:
+        res['samples'] = None
+    return res
+
+
+def loglik_beta(batch_data, list_type, theta, normalization_params, extra_params=None):
+    """HL_VAE/loglik.py:216-256.  normalization_params: the concatenated [min, max + 1e-3] ranges of the group
+    (HLVAE.py:400); extra_params: the raw dispersion `_disp_param`.  The reference reads theta[:, :D] and
+    theta[:, D:2D] and, when theta is narrower (it is: beta variables own ONE parameter column each,
+    read_functions.py:164-173), falls back to columns 0 and 1 as [N, 1] tensors (:232-235) - of which only the first
+    is used afterwards (:238-245): every variable of the group then shares theta[:, 0].  Reproduced as is."""
+    data, mask = batch_data
+    N, Dg = data.shape
+    rng = torch.as_tensor(np.asarray(normalization_params.detach().cpu() if torch.is_tensor(normalization_params)
+                                     else normalization_params), dtype=torch.float64).reshape(Dg, -1)       # :222
+    vp = _aux_vparam(Dg, theta.device)
+    vp[0], vp[1] = rng[:, 0].to(theta.device), rng[:, 1].to(theta.device)
+    if theta.shape[1] >= 2 * Dg:
+        th_a, cs = theta[:, :Dg], 1
+    else:
+        if theta.shape[1] < 2:
+            raise IndexError("index 1 is out of bounds for dimension 1 with size 1")       # what :235 raises
+        th_a, cs = theta[:, 0:1], 0
+    lpx, lpm, al, be = _AuxLoglik.apply(th_a, extra_params, data, mask.float(), vp, _lib.AUX_BETA, cs)
+    if cs == 0:
+        al, be = al[:, :1], be[:, :1]
+    res = {'log_p_x': lpx, 'log_p_x_missing': lpm, 'params': [al, be]}                                       # :253
+    if PRODUCE_SAMPLES:
+        res['samples'] = td.Beta(al, be).sample() * (vp[1] - vp[0]).to(al.dtype) + vp[0].to(al.dtype)         # :254
     else:
         res['samples'] = None
     return res
@@ -297,6 +420,8 @@ def loglik_and_reconstruction(self, theta, batch_data_list, miss_list, param_mis
     Returns (log_p_x, log_p_x_missing, samples_x, params_x) with params_x one tensor per type
     group, consumable by read_functions.p_params_concatenation_by_key (:206-218).  The fused
     monitoring outputs are left on `self.hlvae_b200_monitor`."""
+    if getattr(self, "logvar_network", False) or any(t[0] == 'beta' for t in self.types_info['set_of_types']):
+        return _loglik_by_groups(self, theta, batch_data_list, miss_list, normalization_params)
     lay = _model_layout(self, theta.device)
     nr = normalization_params[0] if len(normalization_params) > 0 else []
     npos = normalization_params[1] if len(normalization_params) > 1 else []
@@ -310,6 +435,38 @@ def loglik_and_reconstruction(self, theta, batch_data_list, miss_list, param_mis
     return out['log_p_x'], out['log_p_x_missing'], samples_x, params_x
 
 
+def _loglik_by_groups(model, theta, batch_data_list, miss_list, normalization_params):
+    """HLVAE.loglik_and_reconstruction (HLVAE.py:381-414) for the configurations the single fused launch does not
+    cover (variance network, beta variables): the reference's own loop over the type groups, each group evaluated by
+    this module's loglik_<type> kernels."""
+    ti = model.types_info
+    dev = theta.device
+    log_p_x = torch.zeros(miss_list.shape, dtype=theta.dtype, device=dev)
+    log_p_x_missing = torch.zeros_like(log_p_x)
+    samples_x, params_x = [], []
+    sel = lambda key, i: torch.as_tensor(np.nonzero(np.asarray(ti[key]) == i)[0], dtype=torch.long, device=dev)
+    this = globals()
+    for i, tpl in enumerate(ti['set_of_types']):
+        dcols, vcols, pcols = sel('exp_types_indexes', i), sel('data_types_indexes', i), sel('param_indexes', i)
+        data_g = batch_data_list[:, dcols]
+        extra, norm = None, torch.tensor(0.)
+        if tpl[0] == 'real':
+            norm = normalization_params[0]
+            if model.conv:
+                data_g = data_g / 255                                                          # :393-394
+            extra = model._log_vy_real
+        elif tpl[0] == 'pos':
+            norm, extra = normalization_params[1], model._log_vy_pos
+        elif tpl[0] == 'beta':
+            norm, extra = np.concatenate(ti['beta_ranges']), model._disp_param                   # :399-401
+        out = this['loglik_' + tpl[0]]([data_g, miss_list[:, vcols]], tpl, theta[:, pcols], norm, extra)
+        log_p_x = log_p_x.index_copy(1, vcols, out['log_p_x'].to(log_p_x.dtype))
+        log_p_x_missing = log_p_x_missing.index_copy(1, vcols, out['log_p_x_missing'].to(log_p_x.dtype))
+        samples_x.append(out['samples'])
+        params_x.append(out['params'])
+    return log_p_x, log_p_x_missing, samples_x, params_x
+
+
 def statistics(layout, params, vparam):
     """read_functions.statistics (:268-302) on packed params -> (mean, mode) [N, D]."""
     N = params.shape[0]
@@ -321,6 +478,61 @@ def statistics(layout, params, vparam):
                                            _lib.ptr(layout.var_nclass), _lib.ptr(layout.var_pcol), _lib.ptr(vp),
                                            _lib.ptr(prm), _lib.dtype_code(prm), _lib.ptr(mean), _lib.ptr(mode),
                                            _lib.stream_ptr())
+    return mean, mode
+
+
+def statistics_general(loglik_params, types_info, conv=False, log_vy=None):
+    """read_functions.statistics (:268-339) for any layout of `types_info`: the packed five-type layout goes to the
+    kernel as is; with a variance network (real / positive groups own [means, variances] columns, :276-291) or beta
+    groups (:303-337) the kernel evaluates the gathered mean columns and the few affected groups are finished with
+    element-wise device ops."""
+    ti = types_info
+    dev = loglik_params.device
+    dti, pidx = np.asarray(ti['data_types_indexes']), np.asarray(ti['param_indexes'])
+    types = [(t['type'], int(t['nclass'])) for t in ti['types_dict']]
+    base_types = [("real" if k == "beta" else k, c) for k, c in types]
+    lay = VarLayout(base_types, dev)
+    plain = len(pidx) == lay.P_theta and not any(k == "beta" for k, _ in types)
+    lv_pos = log_vy[1] if (log_vy is not None and len(log_vy) > 1) else None
+    vparam = torch.zeros(4, lay.D, dtype=torch.float64, device=dev)
+    if lv_pos is not None and lay.idx["pos"].numel():
+        vparam[2, lay.idx["pos"]] = lv_pos.detach().to(torch.float64)[lay.gpos["pos"]]
+    if plain:
+        return statistics(lay, loglik_params, vparam)
+    gather = np.zeros(lay.P_theta, dtype=np.int64)
+    fix = []
+    for i, tpl in enumerate(ti['set_of_types']):
+        cols, vars_g = np.nonzero(pidx == i)[0], np.nonzero(dti == i)[0]
+        if tpl[0] in ("real", "pos", "beta"):
+            n = len(vars_g)
+            gather[[lay.pcol_host[d] for d in vars_g]] = cols[:n]
+            if tpl[0] == "beta" or (tpl[0] == "pos" and len(cols) == 2 * n):
+                fix.append((tpl[0], cols, vars_g))
+        else:
+            gather[np.concatenate([np.arange(lay.pcol_host[d], lay.pcol_host[d] + lay.ncls_host[d]) for d in vars_g])] = cols
+    mean, mode = statistics(lay, loglik_params.index_select(1, torch.as_tensor(gather, device=dev)).contiguous(), vparam)
+    for kind, cols, vars_g in fix:
+        c = torch.as_tensor(cols, device=dev)
+        vg = torch.as_tensor(vars_g, device=dev)
+        prm = loglik_params.index_select(1, c)
+        n = len(vars_g)
+        if kind == "pos":                                                   # :283-291 with the per-row variance
+            mu, var = prm[:, :n], prm[:, n:2 * n]
+            mean = mean.index_copy(1, vg, (torch.exp(mu + 0.5 * var) - 1.0).to(mean.dtype))
+            mode = mode.index_copy(1, vg, (torch.exp(mu - var) - 1.0).to(mode.dtype))
+        else:                                                               # beta, :303-337
+            sz = prm.shape[1] // 2
+            al, be = prm[:, :sz], prm[:, sz:2 * sz]
+            rng = torch.as_tensor(np.concatenate(ti['beta_ranges']).reshape(sz, -1), dtype=prm.dtype, device=dev)
+            lo, hi = rng[:, 0], rng[:, 1]
+            m01 = al / (al + be)
+            md = torch.where((al > 1) & (be > 1), (al - 1) / (al + be - 2),
+                             torch.where((al > 1) & (be <= 1), torch.ones_like(al), torch.zeros_like(al)))
+            eq = (al == 1) & (be == 1)
+            if bool(eq.any()):                                              # :333: uniform density, a random mode
+                md = torch.where(eq, torch.rand(al.shape, device=dev).to(md.dtype), md)
+            mean = mean.index_copy(1, vg, (m01 * (hi - lo) + lo).expand(-1, n).to(mean.dtype))
+            mode = mode.index_copy(1, vg, (md * (hi - lo) + lo).expand(-1, n).to(mode.dtype))
     return mean, mode
 
 

@@ -102,8 +102,8 @@ def pack_heads(obs_layer, layout: HeadLayout, y_dim: int):
             W = W.index_put((g["cols"],), mod.weight[:, :, 0].to(torch.float64))
             b = b.index_put((g["cols"],), mod.bias[:, 0].to(torch.float64))
         elif kind in ("real", "pos"):                                # Observation_Real_Pos_Beta, :26-52
-            if getattr(mod, "weight_logvar", None) is not None:
-                raise NotImplementedError("logvar_network=True heads are not supported")
+            # (a variance network adds weight_logvar / bias_logvar, HLVAE.py:30-35: those heads are evaluated by
+            #  _theta_estimation_logvar below; this function packs the mean heads)
             W = W.index_put((g["cols"],), mod.weight_mean[:, :, 0].to(torch.float64))
             b = b.index_put((g["cols"],), mod.bias_mean[:, 0].to(torch.float64))
             if kind == "real" and layout.conv:
@@ -210,10 +210,73 @@ def _model_head_layout(model, device):
     return lay
 
 
+def _logvar_plan(model, lay, device):
+    """Index maps for logvar_network=True (HLVAE.py:30-51, read_functions.py:164-185): every real / positive variable
+    owns TWO theta columns, and inside a type group the columns hold all means first, then all raw log-variances.
+    Returns (variables with a log-variance head, in variable order; gather index into cat([theta_base, theta_lv], 1)
+    that yields theta in the reference's column order; per-group positions of those variables)."""
+    plan = getattr(model, "_hlvae_b200_logvar_plan", None)
+    if plan is not None and plan["device"] == str(device):
+        return plan
+    ti = model.types_info
+    dti, pidx = np.asarray(ti['data_types_indexes']), np.asarray(ti['param_indexes'])
+    v = lay.var
+    rp_vars = [d for d, (k, _) in enumerate(v.types) if k in ("real", "pos")]
+    rp_pos = {d: j for j, d in enumerate(rp_vars)}
+    P_base = v.P_theta
+    gather = np.zeros(len(pidx), dtype=np.int64)
+    for i, tpl in enumerate(ti['set_of_types']):
+        cols = np.nonzero(pidx == i)[0]
+        vars_g = np.nonzero(dti == i)[0]
+        if tpl[0] in ("real", "pos"):
+            n = len(vars_g)
+            gather[cols[:n]] = [v.pcol_host[d] for d in vars_g]                    # means, HLVAE.py:51
+            gather[cols[n:2 * n]] = [P_base + rp_pos[d] for d in vars_g]           # raw log-variances
+        else:
+            base_cols = np.concatenate([np.arange(v.pcol_host[d], v.pcol_host[d] + v.ncls_host[d]) for d in vars_g])
+            gather[cols] = base_cols
+    plan = dict(device=str(device), rp_vars=torch.tensor(rp_vars, dtype=torch.long, device=device),
+                gather=torch.tensor(gather, dtype=torch.long, device=device),
+                sub=HeadLayout([("count", 1)] * len(rp_vars), False, device), rp_list=rp_vars)
+    model._hlvae_b200_logvar_plan = plan
+    return plan
+
+
+def _theta_estimation_logvar(model, y, miss_list):
+    """theta_estimation with the variance network: the mean heads through the packed layout as usual, the
+    log-variance heads (affine, no Sigmoid: HLVAE.py:431-433 applies it to the first cov_dim columns only) as a
+    second launch over the real / positive variables, then one gather into the reference's column order."""
+    lay = _model_head_layout(model, y.device)
+    plan = _logvar_plan(model, lay, y.device)
+    Y = y.shape[2]
+    W, b = pack_heads(model.obs_layer, lay, Y)
+    theta_base = theta_heads(lay, y, miss_list, W, b)
+    n_rp = len(plan["rp_list"])
+    Wl = torch.zeros(n_rp, Y, dtype=torch.float64, device=y.device)
+    bl = torch.zeros(n_rp, dtype=torch.float64, device=y.device)
+    layer = 0
+    rp_pos = {d: j for j, d in enumerate(plan["rp_list"])}
+    dti = np.asarray(model.types_info['data_types_indexes'])
+    for i, tpl in enumerate(model.types_info['set_of_types']):
+        mod = model.obs_layer[layer]
+        if tpl[0] in ("real", "pos"):
+            rows = torch.tensor([rp_pos[d] for d in np.nonzero(dti == i)[0]], dtype=torch.long, device=y.device)
+            Wl = Wl.index_put((rows,), mod.weight_logvar[:, :, 0].to(torch.float64))
+            bl = bl.index_put((rows,), mod.bias_logvar[:, 0].to(torch.float64))
+            if tpl[0] == "real" and lay.conv:
+                layer += 1
+        layer += 1
+    y_sub = y.index_select(1, plan["rp_vars"])
+    theta_lv = theta_heads(plan["sub"], y_sub, miss_list.index_select(1, plan["rp_vars"]), Wl, bl)
+    return torch.cat([theta_base, theta_lv], 1).index_select(1, plan["gather"])
+
+
 def theta_estimation(self, y, miss_list, param_miss_list):
     """Drop-in for HLVAE.theta_estimation (HLVAE.py:416-453); bind with
     `HLVAE.theta_estimation = hlvae_b200.theta.theta_estimation`.  `param_miss_list` (the mask repeated per
     parameter column) is implied by `miss_list` and the layout and is not read.  Masks must be 0/1."""
+    if getattr(self, "logvar_network", False):
+        return _theta_estimation_logvar(self, y, miss_list)
     lay = _model_head_layout(self, y.device)
     W, b = pack_heads(self.obs_layer, lay, y.shape[2])
     return theta_heads(lay, y, miss_list, W, b)

@@ -252,6 +252,32 @@ int hlvae_discrete_transform(int64_t N, int D, int64_t ld_data, const int32_t* v
                              const int32_t* var_dcol, const void* data, int dtype, void* out, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Likelihood branches outside the fused five-type kernel, one type group [N, Dg] per launch:
+ *   HLVAE_AUX_REAL : loglik_real with the variance network (HL_VAE/loglik.py:45-48) - th_a = means, th_b = per-row
+ *                    raw log-variances;  HLVAE_AUX_POS : loglik_pos likewise (:89,104-108);
+ *   HLVAE_AUX_BETA : loglik_beta (:216-256) - th_a = the probit-mean parameter, `disp` = raw dispersion (1 value).
+ * th_a is addressed as th_a[n * ld_a + d * cs_a] (cs_a = 0: every variable of the group reads column 0, which is
+ * what the reference's fallback indexing at loglik.py:232-235 does); th_b, data, mask as [n * ld + d].
+ * vparam [4, Dg] float64: REAL / POS {normalisation mean, clamped normalisation variance, -, data divisor};
+ * BETA {data_min, data_max, -, -}.  Outputs [N, Dg] contiguous in the storage `dtype`: log_p_x, log_p_x_missing,
+ * prm_a / prm_b = (mean, variance) or (alpha, beta).
+ * bwd: upstream g_lpx [N, Dg] (nullable) and / or a device scalar g_scalar (gradient of sum(log_p_x)) ->
+ * g_a, g_b [N, Dg] element-wise gradients w.r.t. th_a, th_b (BETA: g_b unused, g_disp += d/d disp, caller zero-fills).
+ * ---------------------------------------------------------------------------------- */
+#define HLVAE_AUX_REAL 0
+#define HLVAE_AUX_POS 1
+#define HLVAE_AUX_BETA 2
+int hlvae_loglik_aux_fwd(int mode, int64_t N, int Dg, const void* data, int64_t ld_data, int data_dtype,
+                         const void* mask, int64_t ld_mask, int mask_dtype, const void* th_a, int64_t ld_a,
+                         int64_t cs_a, const void* th_b, int64_t ld_b, int dtype, const double* vparam,
+                         const double* disp, void* lpx, void* lpm, void* prm_a, void* prm_b, void* stream);
+int hlvae_loglik_aux_bwd(int mode, int64_t N, int Dg, const void* data, int64_t ld_data, int data_dtype,
+                         const void* mask, int64_t ld_mask, int mask_dtype, const void* th_a, int64_t ld_a,
+                         int64_t cs_a, const void* th_b, int64_t ld_b, int dtype, const double* vparam,
+                         const double* disp, const void* g_lpx, const double* g_scalar, void* g_a, void* g_b,
+                         double* g_disp, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Per-variable observation heads.  Replaces HLVAE.theta_estimation
  * (HLVAE.py:416-453) over the Observation_Count / _Real_Pos_Beta / _Cat / _Ordinal modules
  * (HLVAE.py:11-89) and the real-valued Sigmoid layer of the convolutional model (:292-295), logvar_network=False.

@@ -421,8 +421,9 @@ def build_layout(types: Sequence[Tuple[str, int]]) -> Tuple[List[VarDesc], int, 
     return descs, e, p
 
 
-def types_info_from_layout(types: Sequence[Tuple[str, int]], conv=False) -> dict:
-    """types_info dict as read_functions.py:141-195 builds it (keys used on the hot path)."""
+def types_info_from_layout(types: Sequence[Tuple[str, int]], conv=False, logvar_network=False) -> dict:
+    """types_info dict as read_functions.py:141-195 builds it (keys used on the hot path).  With logvar_network the
+    real / positive variables own two parameter columns each (:164-173)."""
     type_tuple = [(k, str(c if k in ('cat', 'ordinal') else 1)) for k, c in types]
     set_of_types = sorted(set(type_tuple))
     data_idx, exp_idx, par_idx = [], [], []
@@ -431,7 +432,7 @@ def types_info_from_layout(types: Sequence[Tuple[str, int]], conv=False) -> dict
         w = int(c) if k in ('cat', 'ordinal') else 1
         data_idx.append(gid)
         exp_idx += [gid] * w
-        par_idx += [gid] * w
+        par_idx += [gid] * (2 if (logvar_network and k in ('real', 'pos')) else w)
     return dict(types_dict=[dict(type=k, dim=1, nclass=int(c)) for k, c in type_tuple],
                 set_of_types=set_of_types,
                 data_types_indexes=np.array(data_idx, dtype=float),
@@ -462,6 +463,46 @@ def loglik_pos(data, mask, theta, log_vy, norm_mean, norm_var):
     est_var = lvar * torch.exp(log_vy)                                        # :100
     lp = -0.5 * (ld - est_mean) ** 2 / est_var - 0.5 * torch.log(2 * math.pi * est_var) - ld   # :102
     return lp * mask, lp * (1.0 - mask), est_mean
+
+
+def loglik_real_rowvar(data, mask, theta, norm_mean=None, norm_var=None):
+    """loglik.py:27-70 with extra_params = None (variance network, :45-48): theta = [means, raw log-variances]."""
+    D = data.shape[1]
+    dvar = torch.clamp(norm_var, min=3e-4) if norm_var is not None else torch.tensor(1.0, dtype=DT)
+    dmean = norm_mean if norm_mean is not None else torch.tensor(0.0, dtype=DT)
+    est_mean, raw = theta[:, :D], theta[:, D:2 * D]                            # :46
+    est_var = torch.exp(-8.0 + F.softplus(raw + 8.0))                          # :47-48
+    est_mean = torch.sqrt(dvar) * est_mean + dmean                            # :55
+    est_var = dvar * est_var                                                  # :56
+    lp = -0.5 * (data - est_mean) ** 2 / est_var - 0.5 * math.log(2 * math.pi) - 0.5 * torch.log(est_var)   # :58
+    return lp * mask, lp * (1.0 - mask), est_mean, est_var
+
+
+def loglik_pos_rowvar(data, mask, theta, norm_mean, norm_var):
+    """loglik.py:73-121 with extra_params = None (:89,104-108): per-row log-variances from theta."""
+    D = data.shape[1]
+    lvar = torch.clamp(norm_var, min=1e-3)
+    ld = torch.log(1.0 + data)
+    est_mean = torch.sqrt(lvar) * theta[:, :D] + norm_mean
+    est_var = lvar * torch.exp(theta[:, D:2 * D])                             # :108
+    lp = -0.5 * (ld - est_mean) ** 2 / est_var - 0.5 * torch.log(2 * math.pi * est_var) - ld
+    return lp * mask, lp * (1.0 - mask), est_mean, est_var
+
+
+def loglik_beta(data, mask, theta, ranges, disp):
+    """loglik.py:216-256.  ranges [D, 2] = (min, max + 1e-3) per variable, disp the raw dispersion parameter.
+    theta narrower than 2 D columns -> the reference's fallback (:232-235): one [N, 1] parameter, theta[:, 0],
+    shared by the whole group."""
+    D = data.shape[1]
+    dmin, dmax = ranges[:, 0], ranges[:, 1]
+    xc = (data - dmin) / (dmax - dmin) + 1e-6                                  # :224
+    est = theta[:, :D] if theta.shape[1] >= 2 * D else theta[:, 0:1]           # :230-235
+    phi = torch.clamp(F.softplus(disp.reshape(-1)[0]), 1e-6, 1e20)             # :240
+    mean = 0.5 * (1.0 + torch.erf(est / math.sqrt(2.0)))                       # :241-242
+    al, be = phi * mean, phi * (1.0 - mean)                                    # :244-245
+    lp = (al - 1) * torch.log(xc) + (be - 1) * torch.log(1 - xc) - torch.lgamma(al) - torch.lgamma(be) \
+        + torch.lgamma(al + be)                                                # :247-248
+    return lp * mask, lp * (1.0 - mask), al, be
 
 
 def loglik_cat(data, mask, theta, C):
@@ -607,14 +648,17 @@ def batch_norm_params(descs: List[VarDesc], data, mask):
 # --------------------------------------------------------------------------------------
 # Observation heads: y -> theta (HLVAE.py:11-89, 416-453), SURVEY.md 8(f) row 2
 # --------------------------------------------------------------------------------------
-def head_forward(kind: str, prm: Dict[str, torch.Tensor], gamma: torch.Tensor) -> torch.Tensor:
-    """One Observation_* module on gamma [N, d, Y] -> [N, d, dim] (logvar_network=False).
-    count: HLVAE.py:21-23; real / pos: :42-52 (mean head only, the empty logvar block adds nothing);
+def head_forward(kind: str, prm: Dict[str, torch.Tensor], gamma: torch.Tensor, logvar_network=False) -> torch.Tensor:
+    """One Observation_* module on gamma [N, d, Y] -> [N, d, dim].
+    count: HLVAE.py:21-23; real / pos: :42-52 (mean head; with logvar_network the log-variance head's output is
+    appended along the VARIABLE axis, :51, so the group holds all means, then all raw log-variances);
     cat: :63-68 (a zero logit in front); ordinal: :84-89 (thresholds repeated over the batch, then the region)."""
     lin = lambda w, b: torch.einsum("bdy,dya->bda", gamma, w) + b
     if kind == 'count':
         return lin(prm['weight'], prm['bias'])
     if kind in ('real', 'pos'):
+        if logvar_network:
+            return torch.cat([lin(prm['weight_mean'], prm['bias_mean']), lin(prm['weight_logvar'], prm['bias_logvar'])], 1)
         return lin(prm['weight_mean'], prm['bias_mean'])
     if kind == 'cat':
         th = lin(prm['weight'], prm['bias'])
@@ -627,17 +671,23 @@ def head_forward(kind: str, prm: Dict[str, torch.Tensor], gamma: torch.Tensor) -
 
 
 def theta_estimation(types: Sequence[Tuple[str, int]], heads: List[Dict[str, torch.Tensor]], y: torch.Tensor,
-                     mask: torch.Tensor, conv: bool = False) -> torch.Tensor:
+                     mask: torch.Tensor, conv: bool = False, logvar_network: bool = False) -> torch.Tensor:
     """HLVAE.theta_estimation (HLVAE.py:416-453).  `heads[i]` holds the parameters of the i-th type group's
     module, groups ordered as types_info['set_of_types'].  Follows the reference literally: heads on y * mask
     (:419,424-427), Sigmoid on the real group of the convolutional model (:429-431), times the parameter mask
     (:433-434); the same on y * (1 - mask) under no_grad (:436-446); missing entries overwrite (:449-453)."""
-    ti = types_info_from_layout(types, conv=conv)
-    descs, _, P = build_layout(types)
+    ti = types_info_from_layout(types, conv=conv, logvar_network=logvar_network)
     N = y.shape[0]
-    pm = torch.zeros(N, P, dtype=DT)                        # read_functions.py:147,172-175: mask per parameter column
-    for d, v in enumerate(descs):
-        pm[:, v.theta_col:v.theta_col + v.nclass] = mask[:, d:d + 1]
+    P = len(ti['param_indexes'])
+    pm = torch.zeros(N, P, dtype=DT)                        # read_functions.py:147,172-185: mask per parameter column
+    for i, tpl in enumerate(ti['set_of_types']):
+        vsel = torch.tensor(ti['data_types_indexes'] == i)
+        pcols = torch.nonzero(torch.tensor(ti['param_indexes'] == i))[:, 0]
+        mg = mask[:, vsel]
+        if tpl[0] in ('real', 'pos') and logvar_network:
+            pm[:, pcols] = torch.cat([mg, mg], 1)           # :176-180
+        else:
+            pm[:, pcols] = mg.repeat_interleave(int(tpl[1]) if tpl[0] in ('cat', 'ordinal') else 1, dim=1)
     theta = torch.zeros(N, P, dtype=DT)
     observed_y = y * mask[:, :, None]
     missing_y = y * (1 - mask)[:, :, None]
@@ -646,15 +696,14 @@ def theta_estimation(types: Sequence[Tuple[str, int]], heads: List[Dict[str, tor
         psel = torch.tensor(ti['param_indexes'] == i)
         dim = int(tpl[1])
         pmi = pm[:, psel].reshape(N, -1, dim)
-        obs = head_forward(tpl[0], heads[i], observed_y[:, vsel, :])
-        if tpl[0] == 'real' and conv:
-            obs = torch.sigmoid(obs)
-        obs = obs * pmi
+        cov = int(vsel.sum())
+
+        def sig(o):                                         # Sigmoid on the first cov_dim entries only (:429-431)
+            return torch.cat([torch.sigmoid(o[:, :cov]), o[:, cov:]], 1) if (tpl[0] == 'real' and conv) else o
+
+        obs = sig(head_forward(tpl[0], heads[i], observed_y[:, vsel, :], logvar_network)) * pmi
         with torch.no_grad():
-            mis = head_forward(tpl[0], heads[i], missing_y[:, vsel, :])
-            if tpl[0] == 'real' and conv:
-                mis = torch.sigmoid(mis)
-            mis = mis * (1 - pmi)
+            mis = sig(head_forward(tpl[0], heads[i], missing_y[:, vsel, :], logvar_network)) * (1 - pmi)
         merged = torch.where(pmi == 0, mis, obs).reshape(N, -1)
         theta = theta.index_put((torch.arange(N)[:, None], torch.nonzero(psel)[:, 0][None, :]), merged)
     return theta

@@ -272,23 +272,126 @@ def loglik_case(name, types, N, seed, conv=False, observed=0.7):
     print(f"  {name}: N={N} D={D} E_x={E_x} worst rel diff {max(w):.2e}")
 
 
+def loglik_logvar_case(name, types, N, seed, observed=0.7):
+    """HLVAE.loglik_and_reconstruction (HLVAE.py:381-414), p_params_concatenation_by_key and statistics
+    (read_functions.py:206-218,268-302) of the unmodified reference for a model WITH the variance network
+    (logvar_network=True): model-level fixture; the per-type arithmetic is pinned by loglik_aux_cases."""
+    import HLVAE as ref_hlvae                               # reference
+    from HL_VAE import read_functions as ref_rf             # reference
+    from HL_VAE.utils import batch_normalization as ref_bn  # reference
+    rng = np.random.default_rng(seed)
+    gen = torch.Generator().manual_seed(seed)
+    torch.manual_seed(seed)
+    data, mask = synth.likelihood_batch(types, N, rng, observed=observed)
+    tinfo = orc.types_info_from_layout(types, conv=False, logvar_network=True)
+    descs, E_x, _ = orc.build_layout(types)
+    P_th, D = len(tinfo['param_indexes']), len(types)
+    model = ref_hlvae.HLVAE([E_x, [16], 4, [16], 3], tinfo, D, vy_init=[1., .5], vy_fixed=False, logvar_network=True,
+                            conv=False).double()
+    theta0 = torch.randn(N, P_th, generator=gen, dtype=DT) * 1.2
+    param_mask = torch.ones(N, P_th, dtype=DT)
+    _, norm = ref_bn(data, mask, param_mask, tinfo)
+    theta = theta0.clone().requires_grad_(True)
+    lpx, lpm, samples, params = model.loglik_and_reconstruction(theta, data, mask, param_mask, norm)
+    g_up = torch.randn(N, D, generator=gen, dtype=DT)
+    (lpx * g_up).sum().backward()
+    pcat = ref_rf.p_params_concatenation_by_key([{'x': params}], tinfo, N, data.device, 'x').detach()
+    rmean, rmode = ref_rf.statistics(pcat, tinfo, data.device, False, [model._log_vy_real, model._log_vy_pos])
+    z = lambda t: np.zeros(0) if (t is None or t == []) else t.detach().numpy()
+    nr, npos = norm[0], norm[1]
+    np.savez_compressed(
+        os.path.join(GOLD, name + ".npz"), types=np.array([f"{k}:{c}" for k, c in types]), conv=0, logvar_network=1,
+        data=data.numpy(), mask=mask.numpy(), theta=theta0.numpy(), g_up=g_up.numpy(),
+        norm_real_mean=z(nr[0] if nr != [] else None), norm_real_var=z(nr[1] if nr != [] else None),
+        norm_pos_mean=z(npos[0] if npos != [] else None), norm_pos_var=z(npos[1] if npos != [] else None),
+        log_p_x=lpx.detach().numpy(), log_p_x_missing=lpm.detach().numpy(), params=pcat.numpy(),
+        d_theta=theta.grad.numpy(), recon_mean=rmean.detach().numpy(), recon_mode=rmode.detach().numpy())
+    print(f"  {name}: N={N} D={D} P_theta={P_th} (reference outputs frozen)")
+
+
+def loglik_aux_cases():
+    """The likelihood branches outside the default configuration, function level, unmodified reference:
+    loglik_real / loglik_pos with extra_params = None (variance network, HL_VAE/loglik.py:45-48,104-108) and
+    loglik_beta (:216-256, both for a theta wide enough for the first indexing and for the fallback)."""
+    from HL_VAE import loglik as ref_ll                     # reference
+    print("likelihood branches (variance network, beta): oracle vs unmodified reference")
+    gen = torch.Generator().manual_seed(51)
+    torch.manual_seed(51)
+    out, w = {}, []
+    N, D = 14, 5
+    mask = (torch.rand(N, D, generator=gen) < 0.7).to(DT)
+    g_up = torch.randn(N, D, generator=gen, dtype=DT)
+
+    def run(tag, fn, ofn, data, theta0, norm, extra=None, oargs=()):
+        th = theta0.clone().requires_grad_(True)
+        ex = None if extra is None else extra.clone().requires_grad_(True)
+        r = fn([data, mask[:, :data.shape[1]]], (tag.split("_")[0], '1'), th, norm, ex)
+        (r['log_p_x'] * g_up[:, :data.shape[1]]).sum().backward()
+        th_o = theta0.clone().requires_grad_(True)
+        ex_o = None if extra is None else extra.clone().requires_grad_(True)
+        o = ofn(data, mask[:, :data.shape[1]], th_o, *oargs) if extra is None else \
+            ofn(data, mask[:, :data.shape[1]], th_o, *oargs, ex_o)
+        (o[0] * g_up[:, :data.shape[1]]).sum().backward()
+        w.append(check(tag + ".log_p_x", o[0], r['log_p_x'], 1e-12))
+        w.append(check(tag + ".log_p_x_missing", o[1], r['log_p_x_missing'], 1e-12))
+        w.append(check(tag + ".prm_a", o[2], r['params'][0], 1e-12))
+        w.append(check(tag + ".prm_b", o[3], r['params'][1], 1e-12))
+        w.append(check(tag + ".d_theta", th_o.grad, th.grad, 1e-11))
+        out.update({tag + "_data": data.numpy(), tag + "_theta": theta0.numpy(), tag + "_log_p_x": r['log_p_x'].detach().numpy(),
+                    tag + "_log_p_x_missing": r['log_p_x_missing'].detach().numpy(),
+                    tag + "_prm_a": r['params'][0].detach().numpy(), tag + "_prm_b": r['params'][1].detach().numpy(),
+                    tag + "_d_theta": th.grad.numpy()})
+        if extra is not None:
+            w.append(check(tag + ".d_disp", ex_o.grad, ex.grad, 1e-11))
+            out[tag + "_disp"] = extra.numpy()
+            out[tag + "_d_disp"] = ex.grad.numpy()
+
+    data_r = torch.randn(N, D, generator=gen, dtype=DT)
+    th2 = torch.randn(N, 2 * D, generator=gen, dtype=DT)
+    th2[:, D:] = th2[:, D:] * 2.0 - 3.0
+    nm, nv = torch.randn(D, generator=gen, dtype=DT), torch.rand(D, generator=gen, dtype=DT) + 0.2
+    nv[0] = 1e-5                                             # below the clamp
+    run("real_norm", ref_ll.loglik_real, orc.loglik_real_rowvar, data_r, th2, [nm, nv], oargs=(nm, nv))
+    out["real_norm_nm"], out["real_norm_nv"] = nm.numpy(), nv.numpy()
+    run("real_plain", ref_ll.loglik_real, orc.loglik_real_rowvar, data_r, th2, [])
+    data_p = torch.exp(torch.randn(N, D, generator=gen, dtype=DT))
+    run("pos_norm", ref_ll.loglik_pos, orc.loglik_pos_rowvar, data_p, th2, [nm, nv], oargs=(nm, nv))
+    # beta: ranges as read_functions.py:119 builds them ([min, max + 1e-3]); dispersion parameter of HLVAE.py:226
+    for tag, Db, width in (("beta_wide", 3, 6), ("beta_fallback2", 2, 2), ("beta_fallback3", 3, 3)):
+        lo = torch.rand(Db, generator=gen, dtype=DT) * 2 - 1
+        hi = lo + 0.5 + torch.rand(Db, generator=gen, dtype=DT) * 3
+        xb = lo + (hi - lo) * (0.02 + 0.96 * torch.rand(N, Db, generator=gen, dtype=DT))
+        rng_np = np.concatenate([[float(lo[i]), float(hi[i]) + 1e-3] for i in range(Db)])
+        thb = torch.randn(N, width, generator=gen, dtype=DT) * 0.8
+        disp = torch.tensor([1.0 + 0.7 * float(torch.randn((), generator=gen))], dtype=DT)
+        run(tag, ref_ll.loglik_beta, orc.loglik_beta, xb, thb, rng_np, extra=disp,
+            oargs=(torch.as_tensor(rng_np.reshape(Db, 2)),))
+        out[tag + "_ranges"] = rng_np
+    out["mask"], out["g_up"] = mask.numpy(), g_up.numpy()
+    np.savez_compressed(os.path.join(GOLD, "loglik_aux.npz"), **out)
+    print(f"  loglik_aux: worst rel diff {max(w):.2e}")
+    loglik_logvar_case("loglik_logvar_mixed", synth.mixed_types(np.random.default_rng(53), 16), N=18, seed=53)
+
+
 # ------------------------------------------------------------------ observation heads (y -> theta)
 HEAD_PARAM_NAMES = {'count': ('weight', 'bias'), 'real': ('weight_mean', 'bias_mean'), 'pos': ('weight_mean', 'bias_mean'),
                     'cat': ('weight', 'bias'), 'ordinal': ('weight_thresholds', 'weight_region', 'bias_region')}
 
 
-def theta_case(name, types, N, seed, conv=False, observed=0.7):
+def theta_case(name, types, N, seed, conv=False, observed=0.7, logvar_network=False):
     """HLVAE.theta_estimation of the unmodified reference (HLVAE.py:416-453) on a seeded y, with an arbitrary
     upstream gradient: theta, d/dy and the gradient of every Observation_* parameter."""
     import HLVAE as ref_hlvae                               # reference
     gen = torch.Generator().manual_seed(seed)
     torch.manual_seed(seed)
-    tinfo = orc.types_info_from_layout(types, conv=conv)
+    tinfo = orc.types_info_from_layout(types, conv=conv, logvar_network=logvar_network)
     descs, E_x, P_th = orc.build_layout(types)
+    P_th = len(tinfo['param_indexes'])
     D = len(types)
     dims = [D, [16], 4, [16], 5] if conv else [E_x, [16], 4, [16], 3]
     Y = dims[4]
-    model = ref_hlvae.HLVAE(dims, tinfo, D, vy_init=[1., .5], vy_fixed=False, logvar_network=False, conv=conv).double()
+    model = ref_hlvae.HLVAE(dims, tinfo, D, vy_init=[1., .5], vy_fixed=False, logvar_network=logvar_network,
+                            conv=conv).double()
     with torch.no_grad():                                   # move the heads away from their near-zero initial state
         for prm in model.obs_layer.parameters():
             prm.add_(0.4 * torch.randn(prm.shape, generator=gen, dtype=DT))
@@ -298,30 +401,39 @@ def theta_case(name, types, N, seed, conv=False, observed=0.7):
         y0 = torch.randn(N, D, Y, generator=gen, dtype=DT) * 1.5
     mask = (torch.rand(N, D, generator=gen, dtype=DT) < observed).to(DT)
     pm = torch.zeros(N, P_th, dtype=DT)
-    for d, v in enumerate(descs):
-        pm[:, v.theta_col:v.theta_col + v.nclass] = mask[:, d:d + 1]
+    for i, tpl in enumerate(tinfo['set_of_types']):        # read_functions.py:172-185
+        mg = mask[:, torch.tensor(tinfo['data_types_indexes'] == i)]
+        pc = torch.nonzero(torch.tensor(tinfo['param_indexes'] == i))[:, 0]
+        if tpl[0] in ('real', 'pos') and logvar_network:
+            pm[:, pc] = torch.cat([mg, mg], 1)
+        else:
+            pm[:, pc] = mg.repeat_interleave(int(tpl[1]) if tpl[0] in ('cat', 'ordinal') else 1, dim=1)
     g_up = torch.randn(N, P_th, generator=gen, dtype=DT)
     y = y0.clone().requires_grad_(True)
     theta = model.theta_estimation(y, mask, pm)
     (theta * g_up).sum().backward()
 
     # ---- oracle
+    def names_of(kind):
+        extra = ('weight_logvar', 'bias_logvar') if (logvar_network and kind in ('real', 'pos')) else ()
+        return HEAD_PARAM_NAMES[kind] + extra
+
     heads, layer = [], 0
     for i, tpl in enumerate(tinfo['set_of_types']):
         mod = model.obs_layer[layer]
-        heads.append({n: getattr(mod, n).detach().clone().requires_grad_(True) for n in HEAD_PARAM_NAMES[tpl[0]]})
+        heads.append({n: getattr(mod, n).detach().clone().requires_grad_(True) for n in names_of(tpl[0])})
         layer += 2 if (tpl[0] == 'real' and conv) else 1
     y_o = y0.clone().requires_grad_(True)
-    th_o = orc.theta_estimation(types, heads, y_o, mask, conv=conv)
+    th_o = orc.theta_estimation(types, heads, y_o, mask, conv=conv, logvar_network=logvar_network)
     (th_o * g_up).sum().backward()
     w = [check(name + ".theta", th_o, theta, 1e-13), check(name + ".d_y", y_o.grad, y.grad, 1e-12)]
     out = dict(types=np.array([f"{k}:{c}" for k, c in types]), conv=int(conv), y=y0.contiguous().numpy(),
                mask=mask.numpy(), g_up=g_up.numpy(), theta=theta.detach().numpy(), d_y=y.grad.contiguous().numpy(),
-               n_groups=len(heads))
+               n_groups=len(heads), logvar_network=int(logvar_network))
     layer = 0
     for i, tpl in enumerate(tinfo['set_of_types']):
         mod = model.obs_layer[layer]
-        for n in HEAD_PARAM_NAMES[tpl[0]]:
+        for n in names_of(tpl[0]):
             gref = getattr(mod, n).grad
             w.append(check(f"{name}.d_{tpl[0]}{tpl[1]}.{n}", heads[i][n].grad, gref, 1e-11))
             out[f"g{i}_{n}"] = getattr(mod, n).detach().numpy()
@@ -336,6 +448,7 @@ def theta_cases():
     print("observation heads (theta_estimation): oracle vs unmodified reference")
     rng = np.random.default_rng(21)
     theta_case("theta_mixed", synth.mixed_types(rng, 24), N=24, seed=21)
+    theta_case("theta_logvar_mixed", synth.mixed_types(np.random.default_rng(23), 18), N=20, seed=23, logvar_network=True)
     theta_case("theta_tabular_small", [('count', 1)] * 3 + [('ordinal', 5)] * 3 + [('cat', 5)] * 3 + [('real', 1)] * 2 +
                [('pos', 1)] * 2, N=16, seed=22)
     theta_case("theta_conv_d4", synth.HEALTHMNIST_D4_TYPES, N=3, seed=23, conv=True, observed=0.75)
@@ -585,6 +698,9 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "samplers":
         sampler_cases()
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "aux":          # only the variance-network / beta likelihood fixtures
+        loglik_aux_cases()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "legacy":       # only the un-batched bound fixtures
         legacy_bound_cases()
         return
@@ -613,6 +729,7 @@ def main():
     loglik_case("loglik_tabular_small", [('count', 1)] * 3 + [('ordinal', 5)] * 3 + [('cat', 5)] * 3 + [('real', 1)] * 2 + [('pos', 1)] * 2,
                 N=16, seed=12)
     loglik_case("loglik_conv_d4", synth.HEALTHMNIST_D4_TYPES, N=3, seed=13, conv=True, observed=0.75)
+    loglik_aux_cases()
     predict_cases()
     legacy_bound_cases()
     theta_cases()

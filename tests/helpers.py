@@ -35,7 +35,7 @@ def t(a, dev="cpu", dtype=DT):
 
 
 def rel_err(a, b, scale=None):
-    a, b = torch.as_tensor(a, dtype=DT).cpu(), torch.as_tensor(b, dtype=DT).cpu()
+    a, b = torch.as_tensor(a, dtype=DT).detach().cpu(), torch.as_tensor(b, dtype=DT).detach().cpu()
     den = float(b.abs().max()) if scale is None else float(scale)
     return float((a - b).abs().max()) / (den + 1e-300)
 

@@ -294,3 +294,76 @@ def test_staging_paths_agree(device):
         assert torch.equal(outs[0][0][key], outs[1][0][key]), key
     assert torch.equal(outs[0][1], outs[1][1])
     assert h.rel_err(outs[0][2], outs[1][2]) < 1e-12 and h.rel_err(outs[0][0]["log_p_x_sum"], outs[1][0]["log_p_x_sum"]) < 1e-12
+
+
+@pytest.mark.parametrize("storage,tol", [(torch.float64, 1e-11), (torch.float32, 2e-5)])
+def test_variance_network_and_beta_branches_golden(storage, tol, device):
+    """loglik_real / loglik_pos with extra_params = None (logvar_network=True, HL_VAE/loglik.py:45-48,104-108) and
+    loglik_beta (:216-256, incl. the reference's fallback indexing for a narrow theta) through the reference-shaped
+    functions (hlvae_loglik_aux_fwd / _bwd) against the unmodified reference's outputs and gradients."""
+    from hlvae_b200 import loglik as ll
+    g = h.load("loglik_aux")
+    mask, g_up = h.t(g["mask"], device), h.t(g["g_up"], device)
+    nm, nv = h.t(g["real_norm_nm"], device), h.t(g["real_norm_nv"], device)
+    cases = [("real_norm", ll.loglik_real, ('real', '1'), [nm, nv], False), ("real_plain", ll.loglik_real, ('real', '1'), [], False),
+             ("pos_norm", ll.loglik_pos, ('pos', '1'), [nm, nv], False)]
+    for tag in ("beta_wide", "beta_fallback2", "beta_fallback3"):
+        cases.append((tag, ll.loglik_beta, ('beta', '1'), g[tag + "_ranges"], True))
+    old, ll.PRODUCE_SAMPLES = ll.PRODUCE_SAMPLES, True
+    try:
+        for tag, fn, tpl, norm, beta in cases:
+            data = h.t(g[tag + "_data"], device).to(storage)
+            D = data.shape[1]
+            th = h.t(g[tag + "_theta"], device).to(storage).requires_grad_(True)
+            disp = h.t(g[tag + "_disp"], device).requires_grad_(True) if beta else None
+            out = fn([data, mask[:, :D]], tpl, th, norm, disp)
+            (out["log_p_x"].double() * g_up[:, :D]).sum().backward()
+            got = dict(log_p_x=out["log_p_x"], log_p_x_missing=out["log_p_x_missing"], prm_a=out["params"][0],
+                       prm_b=out["params"][1], d_theta=th.grad)
+            for key, val in got.items():
+                assert val.shape == g[f"{tag}_{key}"].shape, (tag, key, val.shape)
+                assert h.rel_err(val, g[f"{tag}_{key}"]) < tol, (tag, key, h.rel_err(val, g[f"{tag}_{key}"]))
+            if beta:
+                assert h.rel_err(disp.grad, g[tag + "_d_disp"]) < tol, tag
+            assert out["samples"].shape[0] == data.shape[0]
+    finally:
+        ll.PRODUCE_SAMPLES = old
+
+
+def test_variance_network_model_level_golden(device):
+    """HLVAE.loglik_and_reconstruction (HLVAE.py:381-414) + p_params_concatenation_by_key + statistics
+    (read_functions.py:206-218,268-302) for a model with logvar_network=True against the unmodified reference:
+    log_p_x, log_p_x_missing, the concatenated parameters, d/dtheta and the imputation statistics (cat / ordinal
+    argmax bit-exact)."""
+    from hlvae_b200 import loglik as ll
+    g = h.load("loglik_logvar_mixed")
+    types = h.parse_types(g)
+    ti = orc.types_info_from_layout(types, conv=False, logvar_network=True)
+
+    class Model:
+        pass
+
+    m = Model()
+    m.types_info, m.conv, m.logvar_network, m._log_vy_real, m._log_vy_pos = ti, False, True, None, None
+    nr = [h.t(g["norm_real_mean"], device), h.t(g["norm_real_var"], device)] if g["norm_real_mean"].size else []
+    npos = [h.t(g["norm_pos_mean"], device), h.t(g["norm_pos_var"], device)] if g["norm_pos_mean"].size else []
+    theta = h.t(g["theta"], device).requires_grad_(True)
+    old, ll.PRODUCE_SAMPLES = ll.PRODUCE_SAMPLES, False
+    try:
+        lpx, lpm, _, params = ll.loglik_and_reconstruction(m, theta, h.t(g["data"], device), h.t(g["mask"], device),
+                                                           None, [nr, npos])
+    finally:
+        ll.PRODUCE_SAMPLES = old
+    (lpx * h.t(g["g_up"], device)).sum().backward()
+    assert h.rel_err(lpx, g["log_p_x"]) < 1e-11 and h.rel_err(lpm, g["log_p_x_missing"]) < 1e-11
+    assert h.rel_err(theta.grad, g["d_theta"]) < 1e-10
+    # p_params_concatenation_by_key (read_functions.py:206-218): lists are concatenated, tensors flattened
+    pcat = torch.zeros(theta.shape[0], len(ti['param_indexes']), dtype=DT, device=device)
+    for i, prm in enumerate(params):
+        flat = torch.cat(prm, 1) if isinstance(prm, list) else prm.reshape(prm.shape[0], -1)
+        pcat[:, torch.as_tensor(np.nonzero(ti['param_indexes'] == i)[0], device=device)] = flat.detach().double()
+    assert h.rel_err(pcat, g["params"]) < 1e-11
+    mean, mode = ll.statistics_general(pcat, ti, False, [None, None])
+    disc = np.array([k in ("cat", "ordinal") for k, _ in types])
+    assert np.array_equal(mean.cpu().numpy()[:, disc], g["recon_mean"][:, disc])
+    assert h.rel_err(mean, g["recon_mean"]) < 1e-11 and h.rel_err(mode, g["recon_mode"]) < 1e-11

@@ -183,3 +183,27 @@ def test_edge_cases(device):
     with pytest.raises(NotImplementedError):
         th.theta_heads(lay17, torch.zeros(2, 1, 17, dtype=DT, device=device), torch.ones(2, 1, dtype=DT, device=device),
                        torch.zeros(1, 17, dtype=DT, device=device), torch.zeros(1, dtype=DT, device=device))
+
+
+def test_variance_network_heads_golden(device):
+    """HLVAE.theta_estimation with logvar_network=True (HLVAE.py:26-57,416-453): every real / positive variable owns
+    a mean and a raw log-variance column, laid out group-wise as [means..., log-variances...], against the
+    unmodified reference's theta, d/dy and head-parameter gradients."""
+    g = h.load("theta_logvar_mixed")
+    types = h.parse_types(g)
+    obs_layer, _, kinds = h.golden_heads(g, device, False)
+    ti = orc.types_info_from_layout(types, conv=False, logvar_network=True)
+
+    class Model:
+        pass
+
+    model = Model()
+    model.obs_layer, model.types_info, model.conv, model.logvar_network = obs_layer, ti, False, True
+    y = h.t(g["y"], device).requires_grad_(True)
+    theta = th.theta_estimation(model, y, h.t(g["mask"], device), None)
+    assert theta.shape == g["theta"].shape
+    (theta * h.t(g["g_up"], device)).sum().backward()
+    assert h.rel_err(theta, g["theta"]) < 1e-12 and h.rel_err(y.grad, g["d_y"]) < 1e-12
+    for i, kind in enumerate(kinds):
+        for n, prm in obs_layer[i].named_parameters():
+            assert h.rel_err(prm.grad, g[f"d_g{i}_{n}"]) < 1e-11, (i, n)

@@ -116,14 +116,41 @@ def test_oracle_unbatched_bounds_match_reference_goldens(name):
     assert h.rel_err(d, g["dubo"]) < 1e-9 and h.rel_err(e, g["elbo"]) < 1e-9
 
 
-@pytest.mark.parametrize("name", h.THETA_CASES)
+def test_oracle_aux_likelihoods_match_reference_goldens():
+    """loglik_real / loglik_pos with the variance network (HL_VAE/loglik.py:45-48,104-108) and loglik_beta
+    (:216-256): oracle restatements vs the unmodified reference's outputs and gradients."""
+    g = h.load("loglik_aux")
+    mask, g_up = h.t(g["mask"]), h.t(g["g_up"])
+    cases = [("real_norm", orc.loglik_real_rowvar, (h.t(g["real_norm_nm"]), h.t(g["real_norm_nv"])), False),
+             ("real_plain", orc.loglik_real_rowvar, (), False),
+             ("pos_norm", orc.loglik_pos_rowvar, (h.t(g["real_norm_nm"]), h.t(g["real_norm_nv"])), False)]
+    for tag in ("beta_wide", "beta_fallback2", "beta_fallback3"):
+        cases.append((tag, orc.loglik_beta, (h.t(g[tag + "_ranges"]).reshape(-1, 2),), True))
+    for tag, fn, extra, beta in cases:
+        data = h.t(g[tag + "_data"])
+        D = data.shape[1]
+        th = h.t(g[tag + "_theta"]).requires_grad_(True)
+        args = list(extra)
+        if beta:
+            disp = h.t(g[tag + "_disp"]).requires_grad_(True)
+            args.append(disp)
+        lpx, lpm, pa, pb = fn(data, mask[:, :D], th, *args)
+        (lpx * g_up[:, :D]).sum().backward()
+        for key, val in (("log_p_x", lpx), ("log_p_x_missing", lpm), ("prm_a", pa), ("prm_b", pb), ("d_theta", th.grad)):
+            assert h.rel_err(val, g[f"{tag}_{key}"]) < 1e-12, (tag, key)
+        if beta:
+            assert h.rel_err(disp.grad, g[tag + "_d_disp"]) < 1e-12, tag
+
+
+@pytest.mark.parametrize("name", h.THETA_CASES + ["theta_logvar_mixed"])
 def test_oracle_theta_matches_reference_goldens(name):
     """HLVAE.theta_estimation (HLVAE.py:416-453): oracle restatement vs the unmodified reference's outputs."""
     g = h.load(name)
     types, conv = h.parse_types(g), bool(int(g["conv"]))
     _, heads, kinds = h.golden_heads(g, "cpu", conv)
     y = h.t(g["y"]).requires_grad_(True)
-    theta = orc.theta_estimation(types, heads, y, h.t(g["mask"]), conv=conv)
+    theta = orc.theta_estimation(types, heads, y, h.t(g["mask"]), conv=conv,
+                                 logvar_network=bool(int(g.get("logvar_network", 0))))
     (theta * h.t(g["g_up"])).sum().backward()
     assert h.rel_err(theta, g["theta"]) < 1e-13
     assert h.rel_err(y.grad, g["d_y"]) < 1e-12
