@@ -6,6 +6,8 @@
 // Forward and backward are produced in one pass: with w = iK m and G = iK H iK - iK held
 // fixed, J = 1/2 (A + B + C + D + E - F) is linear in S, so dJ/d(inputs) needs nothing
 // from a later stage ("single-pass gradient").
+#include <cstdlib>
+
 #include "common.cuh"
 
 using namespace hlvae;
@@ -67,17 +69,24 @@ struct CompRegs {
             disc_col[f] = sp.comp[r].disc_col[f];
         }
     }
-    // unscaled value of the component at rows (xa, xb) of one covariate matrix; d = xa - xb on its SE column
+    // unscaled value of the component at rows (xa, xb) of one covariate matrix; d = xa - xb on its SE column.
+    // ndisc is the same for every lane, so the factor count selects a branch without divergence: components with
+    // no or one discrete factor (all the generators of kernel_gen.py produce) skip the predicated general loop.
+    __device__ __forceinline__ bool match1(const double* __restrict__ xa, const double* __restrict__ xb, int f) const {
+        const double a = xa[disc_col[f]], b = xb[disc_col[f]];
+        return (disc_kind[f] == HLVAE_KIND_CAT) ? (a - b == 0.0) : (a + b == 2.0);
+    }
     __device__ __forceinline__ double value(const double* __restrict__ xa, const double* __restrict__ xb, double hil2,
                                             double& d, const double* __restrict__ etab) const {
         d = 0.0;
         bool ok = true;
+        if (ndisc == 1) {
+            ok = match1(xa, xb, 0);
+        } else if (ndisc > 1) {
 #pragma unroll
-        for (int f = 0; f < HLVAE_MAX_DISC; f++)
-            if (f < ndisc) {
-                const double a = xa[disc_col[f]], b = xb[disc_col[f]];
-                ok = ok && ((disc_kind[f] == HLVAE_KIND_CAT) ? (a - b == 0.0) : (a + b == 2.0));
-            }
+            for (int f = 0; f < HLVAE_MAX_DISC; f++)
+                if (f < ndisc) ok = ok && match1(xa, xb, f);
+        }
         if (!ok) return 0.0;
         if (se_col < 0) return 1.0;
         d = xa[se_col] - xb[se_col];
@@ -359,6 +368,377 @@ kl_subject_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict
     }
     __syncwarp();
     }   // pairs
+}
+
+// =====================================================================================
+// kl_subject2_k: the same per-(subject, latent dim) stage with the T x T algebra restructured around what bounded
+// the first version (ncu r01k: shared-memory bandwidth - two conflicting LDS.64 per DFMA in every product):
+//   * Cholesky and the triangular inverse keep "their" row / column in REGISTERS (loops fully unrolled over the
+//     padded size TP, so every register index is static); the only shared-memory operand left is a row of L that all
+//     lanes read at the same address (broadcast, conflict-free, two entries per LDS.128);
+//   * the three T^3 products - B^-1 = L^-T L^-1, X = Ktil B^-1 and B^-1 X - run on the FP64 tensor pipe
+//     (mma.sync.m8n8k4: one LDS.64 per operand element per 8 x 8 x 4 block instead of two per multiply-add), with the
+//     leading dimension TP + 4 (= 4 or 12 mod 16), for which both fragment shapes are bank-conflict free;
+//   * dJ/dB is contracted with dB/d(theta_1) straight from the accumulator fragments (never stored).
+// Rows T..TP-1 are padded with an identity block (B) / zeros (Ktil), which leaves every result untouched.
+// =====================================================================================
+template <int TP>
+struct Subj2 {
+    static constexpr int LDA = TP + 4;
+    static constexpr int NT = TP / 8;
+    static constexpr int NTRI = TP * (TP + 1) / 2;
+    static constexpr int per_warp = HLVAE_TMAX * HLVAE_MAX_Q + 2 * TP * LDA + TP + SJ_KP;
+    // per CTA: exp table, then the (i, j) pairs of the lower-triangle walk (16 bits each)
+    static constexpr int shared_doubles = (HLVAE_EXP_TAB + (NTRI + 3) / 4 + 1) & ~1;   // even: 16-byte aligned rows
+    static constexpr int min_blocks = TP <= 24 ? 8 : 4;
+};
+
+template <int TP, typename TS>
+__global__ void __launch_bounds__(SJ_WARPS * 32, Subj2<TP>::min_blocks)
+kl_subject2_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__ os0, const double* __restrict__ ls0,
+              const __grid_constant__ hlvae_kspec_t sp1, const double* __restrict__ os1, const double* __restrict__ ls1,
+              const double* __restrict__ noise, int L, int Q, const double* __restrict__ x, int64_t ldx,
+              const int32_t* __restrict__ row_idx, const int32_t* __restrict__ subj_ptr,
+              const int32_t* __restrict__ tt_ptr, int n_subj, const TS* __restrict__ log_v, int64_t ld_lv,
+              double* __restrict__ binv, int64_t tt_total, double* __restrict__ acc, const AccOff off,
+              TS* __restrict__ g_logv, double gscale, int32_t* __restrict__ status) {
+    using S2 = Subj2<TP>;
+    constexpr int LDA = S2::LDA, NT = S2::NT;
+    extern __shared__ __align__(16) double smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* etab = smem;
+    unsigned short* tri = reinterpret_cast<unsigned short*>(smem + HLVAE_EXP_TAB);   // element t -> (i << 8) | j
+    double* xs = smem + S2::shared_doubles + (size_t)warp * S2::per_warp;
+    double* Am = xs + HLVAE_TMAX * HLVAE_MAX_Q;        // B -> L -> B^-1
+    double* Bm = Am + TP * LDA;                         // L^-1 -> K0ss / Ktil -> X
+    double* dinv = Bm + TP * LDA;                       // 1 / L_jj
+    double* kp = dinv + TP;
+    const int ar = lane >> 2, ac = lane & 3;            // fragment coordinates
+
+    exp2_table_fill(etab, threadIdx.x, SJ_WARPS * 32);
+    for (int i = threadIdx.x; i < TP; i += SJ_WARPS * 32)
+        for (int j = 0; j <= i; j++) tri[i * (i + 1) / 2 + j] = (unsigned short)((i << 8) | j);
+    __syncthreads();
+    const int64_t n_pairs = (int64_t)n_subj * L;
+    for (int64_t pair = (int64_t)blockIdx.x * SJ_WARPS + warp; pair < n_pairs; pair += (int64_t)gridDim.x * SJ_WARPS) {
+    const int s = (int)(pair / L), l = (int)(pair % L);
+    const int r0 = subj_ptr[s];
+    const int T = subj_ptr[s + 1] - r0;
+    if (T <= 0) continue;
+    if (T > TP || T > HLVAE_TMAX) {
+        if (lane == 0) report_status(status, HLVAE_STATUS_T_TOO_LARGE, l, s);
+        continue;
+    }
+    const int TL = T * (T + 1) / 2;
+    int g = -1;
+    double ev = 0.0, lv = 0.0;
+    if (lane < T) {
+        g = row_idx[r0 + lane];
+        for (int q = 0; q < Q; q++) xs[lane * Q + q] = x[(int64_t)g * ldx + q];
+        lv = (double)log_v[(int64_t)g * ld_lv + l];
+        ev = exp(lv);
+    }
+    if (lane < 2 * HLVAE_MAX_COMPS) {
+        const int which = lane >> 3, r = lane & 7;
+        const int nc = which ? sp1.ncomp : sp0.ncomp;
+        double o = 0.0, h = 0.0, i3 = 0.0;
+        if (r < nc) {
+            o = (which ? os1 : os0)[(int64_t)r * L + l];
+            const double e_ = (which ? ls1 : ls0)[(int64_t)r * L + l];
+            const double i2 = 1.0 / (e_ * e_);
+            h = 0.5 * i2;
+            i3 = i2 / e_;
+        }
+        kp[which * 24 + r] = o;
+        kp[which * 24 + 8 + r] = h;
+        kp[which * 24 + 16 + r] = i3;
+    }
+    // identity padding of B, zero padding of the K0ss buffer
+    for (int e = lane; e < TP * LDA; e += 32) {
+        const int i = e / LDA, j = e - i * LDA;
+        Am[e] = (i == j && i >= T) ? 1.0 : 0.0;
+        Bm[e] = 0.0;
+    }
+    __syncwarp();
+    const double nz = noise[l];
+    // B_s = K1(x_s, x_s) + noise I (elbo_functions.py:249-250): lower triangle, mirrored
+    {
+        for (int t = lane; t < TL; t += 32) {
+            const int ij = tri[t], i = ij >> 8, j = ij & 255;
+            double k1 = (i == j) ? nz : 0.0;
+            for (int r = 0; r < sp1.ncomp; r++) {
+                CompRegs c;
+                c.load(sp1, r);
+                double d;
+                k1 = fma(kp[24 + r], c.value(xs + i * Q, xs + j * Q, kp[32 + r], d, etab), k1);
+            }
+            Am[i * LDA + j] = k1;
+            Am[j * LDA + i] = k1;
+        }
+    }
+    __syncwarp();
+
+    // ---- Cholesky (:251), left-looking; lane i keeps row i in registers, finished columns are published to Am so
+    // that row j can be read back by every lane at one address
+    double rr[TP];
+    {
+        const int li = lane < TP ? lane : TP - 1;
+#pragma unroll
+        for (int k = 0; k < TP; k++) rr[k] = Am[li * LDA + k];
+    }
+    __syncwarp();
+    bool bad = false;
+    double ljj = 1.0;
+#pragma unroll
+    for (int j = 0; j < TP; j++) {
+        double s0 = rr[j], s1 = 0.0;
+        const double* rj = Am + j * LDA;                 // L[j][0..j) are final (written at steps < j)
+#pragma unroll
+        for (int k = 0; k + 1 < j; k += 2) {
+            const double2 v = *reinterpret_cast<const double2*>(rj + k);
+            s0 = fma(-rr[k], v.x, s0);
+            s1 = fma(-rr[k + 1], v.y, s1);
+        }
+        if (j & 1) s0 = fma(-rr[j - 1], rj[j - 1], s0);
+        const double sum = s0 + s1;
+        const double djj = __shfl_sync(0xffffffffu, sum, j);
+        if (!(djj > 0.0)) bad = true;
+        const double rd = rsqrt(djj);
+        const double val = (lane == j) ? djj * rd : sum * rd;
+        rr[j] = val;
+        if (lane == j) {
+            ljj = val;
+            dinv[j] = rd;                                 // 1 / L_jj for the triangular solve
+        }
+        if (lane >= j && lane < TP) Am[lane * LDA + j] = val;
+        __syncwarp();
+    }
+    if (bad) {                                           // uniform: djj is a broadcast value
+        if (lane == 0) report_status(status, HLVAE_STATUS_NOT_PD, l, s);
+        continue;
+    }
+    // C term (:258): log det B = 2 sum log L_ii
+    const double logdet = warp_sum(lane < T ? 2.0 * log(ljj) : 0.0);
+    // ---- L^-1: lane c solves L y = e_c with y in registers (zero above the diagonal); L[i][k] is a broadcast read
+    {
+#pragma unroll
+        for (int i = 0; i < TP; i++) {
+            double a0 = 0.0, a1 = 0.0;
+            const double* ri = Am + i * LDA;
+#pragma unroll
+            for (int k = 0; k + 1 < i; k += 2) {
+                const double2 v = *reinterpret_cast<const double2*>(ri + k);
+                a0 = fma(v.x, rr[k], a0);                 // rr[k] now holds y[k] for k < i
+                a1 = fma(v.y, rr[k + 1], a1);
+            }
+            if (i & 1) a0 = fma(ri[i - 1], rr[i - 1], a0);
+            const double rdi = dinv[i];
+            const double y = (lane == i) ? rdi : (lane < i ? -(a0 + a1) * rdi : 0.0);
+            rr[i] = y;                                   // overwrites L[lane][i] (dead: row entries k < i only feed the solve)
+        }
+    }
+    // NOTE the solve above reuses rr: entry rr[k] (k < i) must be y[k], and it is - y[k] was stored at iteration k;
+    // entries k >= i still hold L[lane][k], which the loop never reads (k < i only).
+    // publish L^-1 (lane c owns column c) for the tensor-pipe products
+#pragma unroll
+    for (int i = 0; i < TP; i++)
+        if (lane < TP) Bm[i * LDA + lane] = rr[i];
+    __syncwarp();
+    // ---- B^-1 = L^-T L^-1 (explicit inverse, as :252): lower tiles, k from the tile's first row on
+    double* bout = binv + (int64_t)l * tt_total + tt_ptr[s];
+    {
+        double cfr[NT * (NT + 1) / 2][2];
+        int q = 0;
+#pragma unroll
+        for (int ti = 0; ti < NT; ti++)
+#pragma unroll
+            for (int tj = 0; tj <= ti; tj++, q++) {
+                double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+                for (int k0 = ti * 8; k0 < TP; k0 += 4) {
+                    const double a = Bm[(k0 + ac) * LDA + ti * 8 + ar];     // (L^-1)^T[i][k] = L^-1[k][i]
+                    const double b = Bm[(k0 + ac) * LDA + tj * 8 + ar];
+                    dmma884(c0, c1, a, b);
+                }
+                cfr[q][0] = c0;
+                cfr[q][1] = c1;
+            }
+        __syncwarp();
+        q = 0;
+#pragma unroll
+        for (int ti = 0; ti < NT; ti++)
+#pragma unroll
+            for (int tj = 0; tj <= ti; tj++, q++) {
+                const int i = ti * 8 + ar, j = tj * 8 + 2 * ac;
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    const double v = cfr[q][u];
+                    Am[i * LDA + j + u] = v;
+                    Am[(j + u) * LDA + i] = v;
+                    if (i < T && j + u < T) {
+                        bout[i * T + j + u] = v;
+                        bout[(j + u) * T + i] = v;
+                    }
+                }
+            }
+    }
+    __syncwarp();
+
+    // K0(x_s, x_s) (:248), one evaluation per component and entry.  With wgt = B^-1_ij (x2 off the diagonal):
+    //   B + D1 terms (:257,259) = sum_r os_r sum wgt v_r + sum_i B^-1_ii e^logv_i,   dJ/dK0ss = B^-1 / 2.
+    double bd = 0.0;
+    for (int r = 0; r < sp0.ncomp; r++) {
+        CompRegs c;
+        c.load(sp0, r);
+        const double osr = kp[r], hil2 = kp[8 + r], il3 = kp[16 + r];
+        double gos = 0.0, gls = 0.0;
+        for (int t = lane; t < TL; t += 32) {
+            const int ij = tri[t], i = ij >> 8, j = ij & 255;
+            double d;
+            const double v = c.value(xs + i * Q, xs + j * Q, hil2, d, etab);
+            const double wv = ((i == j) ? 1.0 : 2.0) * Am[i * LDA + j] * v;
+            gos += wv;
+            gls = fma(wv * d, d, gls);
+            const double kv = osr * v;
+            Bm[i * LDA + j] = (r == 0) ? kv : Bm[i * LDA + j] + kv;
+        }
+        gos = warp_sum(gos);
+        gls = warp_sum(gls);
+        bd = fma(osr, gos, bd);
+        if (lane == 0) {
+            atomicAdd(acc + off.o[HLVAE_ACC_GOS0] + (int64_t)r * L + l, 0.5 * gos);
+            if (c.se_col >= 0) atomicAdd(acc + off.o[HLVAE_ACC_GLS0] + (int64_t)r * L + l, 0.5 * gls * osr * il3);
+        }
+    }
+    __syncwarp();
+    {   // lower triangle of K0ss is in place (the buffer still holds L^-1 elsewhere): clean the rest and mirror
+        for (int e = lane; e < TP * LDA; e += 32) {
+            const int i = e / LDA, j = e - i * LDA;
+            if (j > i || i >= T || sp0.ncomp == 0) Bm[e] = 0.0;
+        }
+        __syncwarp();
+        for (int t = lane; t < TL; t += 32) {
+            const int ij = tri[t], i = ij >> 8, j = ij & 255;
+            Bm[j * LDA + i] = Bm[i * LDA + j];
+        }
+    }
+    __syncwarp();
+    double bdiag = 0.0;
+    if (lane < T) {   // Ktil = K0ss + diag(e^logv); its B term and the log-variance gradient
+        const double bii = Am[lane * LDA + lane];
+        Bm[lane * LDA + lane] += ev;
+        bdiag = bii * ev;
+        g_logv[(int64_t)g * L + l] = (TS)(gscale * 0.5 * (bii * ev - 1.0));
+    }
+    bd += warp_sum(bdiag);
+    __syncwarp();
+    // ---- X = Ktil B^-1 (all tiles, accumulators in registers), then stored over Ktil
+    {
+        double xf[NT * NT][2];
+#pragma unroll
+        for (int ti = 0; ti < NT; ti++)
+#pragma unroll
+            for (int tj = 0; tj < NT; tj++) {
+                double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+                for (int k0 = 0; k0 < TP; k0 += 4) {
+                    const double a = Bm[(ti * 8 + ar) * LDA + k0 + ac];
+                    const double b = Am[(k0 + ac) * LDA + tj * 8 + ar];
+                    dmma884(c0, c1, a, b);
+                }
+                xf[ti * NT + tj][0] = c0;
+                xf[ti * NT + tj][1] = c1;
+            }
+        __syncwarp();
+#pragma unroll
+        for (int ti = 0; ti < NT; ti++)
+#pragma unroll
+            for (int tj = 0; tj < NT; tj++)
+                *reinterpret_cast<double2*>(&Bm[(ti * 8 + ar) * LDA + tj * 8 + 2 * ac]) =
+                    make_double2(xf[ti * NT + tj][0], xf[ti * NT + tj][1]);
+    }
+    __syncwarp();
+    // ---- dJ/dB_s (part without K0xz) = 1/2 (B^-1 - B^-1 Ktil B^-1): lower tiles on the tensor pipe, contracted with
+    // dB/d(theta1) from the accumulator fragments (symmetric: off-diagonal entries count twice)
+    {
+        double gq[NT * (NT + 1) / 2][2];
+        int q = 0;
+#pragma unroll
+        for (int ti = 0; ti < NT; ti++)
+#pragma unroll
+            for (int tj = 0; tj <= ti; tj++, q++) {
+                double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+                for (int k0 = 0; k0 < TP; k0 += 4) {
+                    const double a = Am[(ti * 8 + ar) * LDA + k0 + ac];
+                    const double b = Bm[(k0 + ac) * LDA + tj * 8 + ar];
+                    dmma884(c0, c1, a, b);
+                }
+                const int i = ti * 8 + ar, j = tj * 8 + 2 * ac;
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    const double cu = u ? c1 : c0;
+                    const bool use = i < T && j + u <= i;
+                    gq[q][u] = use ? ((i == j + u) ? 0.5 : 1.0) * (Am[i * LDA + j + u] - cu) : 0.0;
+                }
+            }
+        for (int r = 0; r < sp1.ncomp; r++) {
+            CompRegs c;
+            c.load(sp1, r);
+            const double osr = kp[24 + r], hil2 = kp[32 + r], il3 = kp[40 + r];
+            double gos = 0.0, gls = 0.0;
+            q = 0;
+#pragma unroll
+            for (int ti = 0; ti < NT; ti++)
+#pragma unroll
+                for (int tj = 0; tj <= ti; tj++, q++) {
+                    const int i = ti * 8 + ar, j = tj * 8 + 2 * ac;
+#pragma unroll
+                    for (int u = 0; u < 2; u++) {
+                        if (gq[q][u] != 0.0) {
+                            double d;
+                            const double gv = gq[q][u] * c.value(xs + i * Q, xs + (j + u) * Q, hil2, d, etab);
+                            gos += gv;
+                            gls = fma(gv * d, d, gls);
+                        }
+                    }
+                }
+            gos = warp_sum(gos);
+            gls = warp_sum(gls);
+            if (lane == 0) {
+                atomicAdd(acc + off.o[HLVAE_ACC_GOS1] + (int64_t)r * L + l, gos);
+                if (c.se_col >= 0) atomicAdd(acc + off.o[HLVAE_ACC_GLS1] + (int64_t)r * L + l, gls * osr * il3);
+            }
+        }
+    }
+    const double fsum = warp_sum(lv);
+    if (lane == 0) {
+        double* scal = acc + off.o[HLVAE_ACC_SCAL] + (int64_t)l * HLVAE_NSCAL;
+        atomicAdd(scal + 1, bd);
+        atomicAdd(scal + 2, logdet);
+        atomicAdd(scal + 3, fsum);
+    }
+    __syncwarp();
+    }   // pairs
+}
+
+template <int TP, typename TS>
+int launch_subject2(const hlvae_kspec_t* spec0, const double* os0, const double* ls0, const hlvae_kspec_t* spec1,
+                    const double* os1, const double* ls1, const double* noise, int L, int Q, const double* x,
+                    int64_t ldx, const int32_t* row_idx, const int32_t* subj_ptr, const int32_t* tt_ptr, int n_subj,
+                    const void* log_v, int64_t ld_lv, double* binv, int64_t tt_total, double* acc, const AccOff& off,
+                    void* g_logv, double gscale, int32_t* status, cudaStream_t st) {
+    const size_t smem = ((size_t)SJ_WARPS * Subj2<TP>::per_warp + Subj2<TP>::shared_doubles) * sizeof(double);
+    auto kern = kl_subject2_k<TP, TS>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    const int64_t pairs = (int64_t)n_subj * L;
+    const unsigned grid = (unsigned)((pairs + SJ_WARPS - 1) / SJ_WARPS);
+    kern<<<grid, SJ_WARPS * 32, smem, st>>>(*spec0, os0, ls0, *spec1, os1, ls1, noise, L, Q, x, ldx, row_idx, subj_ptr,
+                                            tt_ptr, n_subj, (const TS*)log_v, ld_lv, binv, tt_total, acc, off,
+                                            (TS*)g_logv, gscale, status);
+    HLVAE_CHECK_LAUNCH();
+    return 0;
 }
 
 // =====================================================================================
@@ -1082,11 +1462,26 @@ extern "C" int hlvae_kl_subject(const hlvae_kspec_t* spec0, const double* os0, c
     if (n_subj == 0) return 0;
     AccOff off;
     fill_offsets(L, M, Q, off.o);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!getenv("HLVAE_KL_SUBJECT_V1")) {
+#define HLVAE_SUBJ2(TP)                                                                                              \
+    return dtype == HLVAE_F64                                                                                        \
+               ? launch_subject2<TP, double>(spec0, os0, ls0, spec1, os1, ls1, noise, L, Q, x, ldx, row_idx, subj_ptr, \
+                                             tt_ptr, n_subj, log_v, ld_lv, binv, tt_total, acc, off, g_logv, gscale,  \
+                                             status, st)                                                              \
+               : launch_subject2<TP, float>(spec0, os0, ls0, spec1, os1, ls1, noise, L, Q, x, ldx, row_idx, subj_ptr,  \
+                                            tt_ptr, n_subj, log_v, ld_lv, binv, tt_total, acc, off, g_logv, gscale,   \
+                                            status, st)
+        if (t_cap <= 8) { HLVAE_SUBJ2(8); }
+        if (t_cap <= 16) { HLVAE_SUBJ2(16); }
+        if (t_cap <= 24) { HLVAE_SUBJ2(24); }
+        HLVAE_SUBJ2(32);
+#undef HLVAE_SUBJ2
+    }
     const int ldt = t_cap | 1;
     size_t smem = ((size_t)SJ_WARPS * ((size_t)t_cap * Q + 3 * (size_t)t_cap * ldt + SJ_KP) + HLVAE_EXP_TAB) * sizeof(double);
     int64_t pairs = (int64_t)n_subj * L;
     unsigned grid = (unsigned)((pairs + SJ_WARPS - 1) / SJ_WARPS);
-    cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e;
     if (dtype == HLVAE_F64) {
         auto kern = kl_subject_k<double>;
