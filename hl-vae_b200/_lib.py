@@ -48,7 +48,7 @@ _SIGS = {
     "hlvae_kl_subject": ([C.POINTER(KSpec), _P, _P, C.POINTER(KSpec), _P, _P, _P, _I, _I, _P, _L, _P, _P, _P, _I, _I,
                           _P, _L, _I, _P, _L, _P, _I, _P, _D, _P, _P], _I),
     "hlvae_kl_panel": ([C.POINTER(KSpec), _P, _P, C.POINTER(KSpec), _P, _P, _I, _I, _I, _P, _L, _P, _P, _P, _P, _I, _I,
-                        _P, _L, _I, _P, _P, _P, _L, _P, _P, _P, _D, _P, _P], _I),
+                        _P, _L, _I, _P, _P, _P, _L, _P, _P, _P, _D, _P, _I, _P], _I),
     "hlvae_mxm_workspace_doubles": ([_I, _I], _L),
     "hlvae_mxm_pre": ([C.POINTER(KSpec), _P, _P, _I, _I, _I, _P, _D, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P], _I),
     "hlvae_mxm_post": ([_I, _I, _D, _D, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P], _I),

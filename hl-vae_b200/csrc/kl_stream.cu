@@ -6,8 +6,6 @@
 // Forward and backward are produced in one pass: with w = iK m and G = iK H iK - iK held
 // fixed, J = 1/2 (A + B + C + D + E - F) is linear in S, so dJ/d(inputs) needs nothing
 // from a later stage ("single-pass gradient").
-#include <cstdlib>
-
 #include "common.cuh"
 
 using namespace hlvae;
@@ -26,34 +24,6 @@ struct AccOff {
 // kl_subject_k
 // =====================================================================================
 constexpr int SJ_WARPS = 2;
-
-// lower-triangle walk: element t = i (i + 1) / 2 + j, advanced by 32 per step without divisions
-struct TriIdx {
-    int i, j;
-    __device__ __forceinline__ void init(int t) {
-        i = 0;
-        j = t;
-        while (j > i) { j -= i + 1; i++; }
-    }
-    __device__ __forceinline__ void advance32() {
-        j += 32;
-        while (j > i) { j -= i + 1; i++; }
-    }
-};
-
-// square walk: element e = i T + j, advanced by 32 per step without divisions
-struct SqIdx {
-    int i, j;
-    __device__ __forceinline__ void init(int e, int T) {
-        i = 0;
-        j = e;
-        while (j >= T) { j -= T; i++; }
-    }
-    __device__ __forceinline__ void advance32(int T) {
-        j += 32;
-        while (j >= T) { j -= T; i++; }
-    }
-};
 
 // One component's descriptor pulled into registers field by field (a struct copy indexed by a
 // run-time component number would be placed in local memory).
@@ -98,281 +68,10 @@ struct CompRegs {
 // latent dimension by component ({outputscale, 1/(2 l^2), 1/l^3} x {K0, K1}).
 constexpr int SJ_KP = 6 * HLVAE_MAX_COMPS;
 
-template <typename TS>
-__global__ void __launch_bounds__(SJ_WARPS * 32, 9)
-kl_subject_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__ os0, const double* __restrict__ ls0,
-             const __grid_constant__ hlvae_kspec_t sp1, const double* __restrict__ os1, const double* __restrict__ ls1,
-             const double* __restrict__ noise, int L, int Q, const double* __restrict__ x, int64_t ldx,
-             const int32_t* __restrict__ row_idx, const int32_t* __restrict__ subj_ptr,
-             const int32_t* __restrict__ tt_ptr, int n_subj, int tcap, const TS* __restrict__ log_v, int64_t ld_lv,
-             double* __restrict__ binv, int64_t tt_total, double* __restrict__ acc, const AccOff off,
-             TS* __restrict__ g_logv, double gscale, int32_t* __restrict__ status) {
-    extern __shared__ double smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ldt = tcap | 1;
-    const int per_warp = tcap * Q + 3 * tcap * ldt + SJ_KP;
-    double* etab = smem;                                   // 2^(j/64), shared by the CTA's warps
-    double* xs = smem + HLVAE_EXP_TAB + (size_t)warp * per_warp;
-    double* Bw = xs + tcap * Q;
-    double* Bi = Bw + tcap * ldt;
-    double* Ks = Bi + tcap * ldt;
-    double* kp = Ks + tcap * ldt;           // [0..8) os0, [8..16) hil2_0, [16..24) il3_0, [24..48) same for K1
-
-    exp2_table_fill(etab, threadIdx.x, SJ_WARPS * 32);
-    __syncthreads();
-    // grid = one warp per (subject, latent dim) pair, or - when the host caps the CTAs per SM so that the HBM-bound
-    // likelihood kernels can share the SMs with this latency-bound one - a persistent grid striding over the pairs
-    const int64_t n_pairs = (int64_t)n_subj * L;
-    for (int64_t pair = (int64_t)blockIdx.x * SJ_WARPS + warp; pair < n_pairs; pair += (int64_t)gridDim.x * SJ_WARPS) {
-    const int s = (int)(pair / L), l = (int)(pair % L);
-    const int r0 = subj_ptr[s];
-    const int T = subj_ptr[s + 1] - r0;
-    if (T <= 0) continue;
-    if (T > tcap || T > HLVAE_TMAX) {
-        if (lane == 0) report_status(status, HLVAE_STATUS_T_TOO_LARGE, l, s);
-        continue;
-    }
-    const int TL = T * (T + 1) / 2;
-
-    int g = -1;
-    double ev = 0.0, lv = 0.0;
-    if (lane < T) {
-        g = row_idx[r0 + lane];
-        for (int q = 0; q < Q; q++) xs[lane * Q + q] = x[(int64_t)g * ldx + q];
-        lv = (double)log_v[(int64_t)g * ld_lv + l];
-        ev = exp(lv);
-    }
-    if (lane < 2 * HLVAE_MAX_COMPS) {
-        const int which = lane >> 3, r = lane & 7;
-        const int nc = which ? sp1.ncomp : sp0.ncomp;
-        double o = 0.0, h = 0.0, i3 = 0.0;
-        if (r < nc) {
-            o = (which ? os1 : os0)[(int64_t)r * L + l];
-            const double e_ = (which ? ls1 : ls0)[(int64_t)r * L + l];
-            const double i2 = 1.0 / (e_ * e_);
-            h = 0.5 * i2;
-            i3 = i2 / e_;
-        }
-        kp[which * 24 + r] = o;
-        kp[which * 24 + 8 + r] = h;
-        kp[which * 24 + 16 + r] = i3;
-    }
-    __syncwarp();
-    const double nz = noise[l];
-    // B_s = K1(x_s, x_s) + noise I (elbo_functions.py:249-250): lower triangle, mirrored
-    {
-        TriIdx ix;
-        ix.init(lane);
-        for (int t = lane; t < TL; t += 32, ix.advance32()) {
-            const int i = ix.i, j = ix.j;
-            double k1 = (i == j) ? nz : 0.0;
-            for (int r = 0; r < sp1.ncomp; r++) {
-                CompRegs c;
-                c.load(sp1, r);
-                double d;
-                k1 = fma(kp[24 + r], c.value(xs + i * Q, xs + j * Q, kp[32 + r], d, etab), k1);
-            }
-            Bw[i * ldt + j] = k1;
-            Bw[j * ldt + i] = k1;
-        }
-    }
-    __syncwarp();
-
-    // Cholesky, lower, left-looking; lane i owns row i.  (:251)
-    bool bad = false;
-    for (int j = 0; j < T; j++) {
-        double s0 = 0.0, s1 = 0.0;
-        if (lane >= j && lane < T) {
-            const double* ri = Bw + lane * ldt;
-            const double* rj = Bw + j * ldt;
-            s0 = ri[j];
-            int k = 0;
-            for (; k + 1 < j; k += 2) {
-                s0 = fma(-ri[k], rj[k], s0);
-                s1 = fma(-ri[k + 1], rj[k + 1], s1);
-            }
-            if (k < j) s0 = fma(-ri[k], rj[k], s0);
-        }
-        const double sum = s0 + s1;
-        const double djj = __shfl_sync(0xffffffffu, sum, j);
-        if (!(djj > 0.0)) { bad = true; break; }
-        const double rd = rsqrt(djj);
-        if (lane >= j && lane < T) Bw[lane * ldt + j] = (lane == j) ? djj * rd : sum * rd;
-        __syncwarp();
-    }
-    if (bad) {
-        if (lane == 0) report_status(status, HLVAE_STATUS_NOT_PD, l, s);
-        continue;
-    }
-    // C term (:258): log det B = 2 sum log L_ii, one logarithm per lane
-    const double logdet = warp_sum(lane < T ? 2.0 * log(Bw[lane * ldt + lane]) : 0.0);
-    // L^-1 column by column: lane c solves L y = e_c, stored in Bi[:, c].
-    if (lane < T) {
-        const int c = lane;
-        for (int i = 0; i < c; i++) Bi[i * ldt + c] = 0.0;
-        Bi[c * ldt + c] = 1.0 / Bw[c * ldt + c];
-        for (int i = c + 1; i < T; i++) {
-            double a0 = 0.0, a1 = 0.0;
-            int k = c;
-            for (; k + 1 < i; k += 2) {
-                a0 = fma(Bw[i * ldt + k], Bi[k * ldt + c], a0);
-                a1 = fma(Bw[i * ldt + k + 1], Bi[(k + 1) * ldt + c], a1);
-            }
-            if (k < i) a0 = fma(Bw[i * ldt + k], Bi[k * ldt + c], a0);
-            Bi[i * ldt + c] = -(a0 + a1) / Bw[i * ldt + i];
-        }
-    }
-    __syncwarp();
-    // B^-1 = L^-T L^-1 into Bw (explicit inverse, as :252), written to global for the panel kernel
-    double* bout = binv + (int64_t)l * tt_total + tt_ptr[s];
-    {
-        TriIdx ix;
-        ix.init(lane);
-        for (int t = lane; t < TL; t += 32, ix.advance32()) {
-            const int i = ix.i, j = ix.j;      // i >= j
-            double a0 = 0.0, a1 = 0.0;
-            int k = i;
-            for (; k + 1 < T; k += 2) {
-                a0 = fma(Bi[k * ldt + i], Bi[k * ldt + j], a0);
-                a1 = fma(Bi[(k + 1) * ldt + i], Bi[(k + 1) * ldt + j], a1);
-            }
-            if (k < T) a0 = fma(Bi[k * ldt + i], Bi[k * ldt + j], a0);
-            const double a = a0 + a1;
-            Bw[i * ldt + j] = a;
-            Bw[j * ldt + i] = a;
-            bout[i * T + j] = a;
-            bout[j * T + i] = a;
-        }
-    }
-    __syncwarp();
-
-    // K0(x_s, x_s) (:248), one evaluation per component and entry.  With wgt = B^-1_ij (x2 off the diagonal):
-    //   B + D1 terms (:257,259) = sum_r os_r sum wgt v_r + sum_i B^-1_ii e^logv_i,   dJ/dK0ss = B^-1 / 2.
-    double bd = 0.0;
-    for (int r = 0; r < sp0.ncomp; r++) {
-        CompRegs c;
-        c.load(sp0, r);
-        const double osr = kp[r], hil2 = kp[8 + r], il3 = kp[16 + r];
-        double gos = 0.0, gls = 0.0;
-        TriIdx ix;
-        ix.init(lane);
-        for (int t = lane; t < TL; t += 32, ix.advance32()) {
-            const int i = ix.i, j = ix.j;
-            double d;
-            const double v = c.value(xs + i * Q, xs + j * Q, hil2, d, etab);
-            const double wv = ((i == j) ? 1.0 : 2.0) * Bw[i * ldt + j] * v;
-            gos += wv;
-            gls = fma(wv * d, d, gls);
-            const double kv = osr * v;
-            Ks[i * ldt + j] = (r == 0) ? kv : Ks[i * ldt + j] + kv;
-        }
-        gos = warp_sum(gos);
-        gls = warp_sum(gls);
-        bd = fma(osr, gos, bd);
-        if (lane == 0) {
-            atomicAdd(acc + off.o[HLVAE_ACC_GOS0] + (int64_t)r * L + l, 0.5 * gos);
-            if (c.se_col >= 0) atomicAdd(acc + off.o[HLVAE_ACC_GLS0] + (int64_t)r * L + l, 0.5 * gls * osr * il3);
-        }
-    }
-    __syncwarp();
-    {   // mirror K0ss
-        TriIdx ix;
-        ix.init(lane);
-        for (int t = lane; t < TL; t += 32, ix.advance32()) {
-            const int i = ix.i, j = ix.j;
-            const double kv = (sp0.ncomp > 0) ? Ks[i * ldt + j] : 0.0;
-            Ks[i * ldt + j] = kv;
-            Ks[j * ldt + i] = kv;
-        }
-    }
-    __syncwarp();
-    double bdiag = 0.0;
-    if (lane < T) {   // Ktil = K0ss + diag(e^logv); its B term and the log-variance gradient
-        const double bii = Bw[lane * ldt + lane];
-        Ks[lane * ldt + lane] += ev;
-        bdiag = bii * ev;
-        g_logv[(int64_t)g * L + l] = (TS)(gscale * 0.5 * (bii * ev - 1.0));
-    }
-    bd += warp_sum(bdiag);
-    __syncwarp();
-    // X = Ktil B^-1 -> Bi
-    {
-        SqIdx ix;
-        ix.init(lane, T);
-        for (int e = lane; e < T * T; e += 32, ix.advance32(T)) {
-            const int i = ix.i, j = ix.j;
-            const double* kr = Ks + i * ldt;
-            const double* bc = Bw + j * ldt;           // B^-1 is symmetric: column j = row j (contiguous)
-            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-            int k = 0;
-            for (; k + 3 < T; k += 4) {
-                a0 = fma(kr[k], bc[k], a0);
-                a1 = fma(kr[k + 1], bc[k + 1], a1);
-                a2 = fma(kr[k + 2], bc[k + 2], a2);
-                a3 = fma(kr[k + 3], bc[k + 3], a3);
-            }
-            for (; k < T; k++) a0 = fma(kr[k], bc[k], a0);
-            Bi[i * ldt + j] = (a0 + a1) + (a2 + a3);
-        }
-    }
-    __syncwarp();
-    // dJ/dB_s (part without K0xz) = 1/2 (B^-1 - B^-1 Ktil B^-1) (symmetric; off-diagonal entries count twice)
-    // -> lower triangle of Ks (Ktil is no longer needed)
-    {
-        TriIdx ix;
-        ix.init(lane);
-        for (int t = lane; t < TL; t += 32, ix.advance32()) {
-            const int i = ix.i, j = ix.j;
-            const double* br = Bw + i * ldt;
-            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-            int k = 0;
-            for (; k + 3 < T; k += 4) {
-                a0 = fma(br[k], Bi[k * ldt + j], a0);
-                a1 = fma(br[k + 1], Bi[(k + 1) * ldt + j], a1);
-                a2 = fma(br[k + 2], Bi[(k + 2) * ldt + j], a2);
-                a3 = fma(br[k + 3], Bi[(k + 3) * ldt + j], a3);
-            }
-            for (; k < T; k++) a0 = fma(br[k], Bi[k * ldt + j], a0);
-            Ks[i * ldt + j] = ((i == j) ? 0.5 : 1.0) * (br[j] - ((a0 + a1) + (a2 + a3)));
-        }
-    }
-    __syncwarp();
-    // contracted with dB/d(theta1), one component at a time
-    for (int r = 0; r < sp1.ncomp; r++) {
-        CompRegs c;
-        c.load(sp1, r);
-        const double osr = kp[24 + r], hil2 = kp[32 + r], il3 = kp[40 + r];
-        double gos = 0.0, gls = 0.0;
-        TriIdx ix;
-        ix.init(lane);
-        for (int t = lane; t < TL; t += 32, ix.advance32()) {
-            const int i = ix.i, j = ix.j;
-            double d;
-            const double gv = Ks[i * ldt + j] * c.value(xs + i * Q, xs + j * Q, hil2, d, etab);
-            gos += gv;
-            gls = fma(gv * d, d, gls);
-        }
-        gos = warp_sum(gos);
-        gls = warp_sum(gls);
-        if (lane == 0) {
-            atomicAdd(acc + off.o[HLVAE_ACC_GOS1] + (int64_t)r * L + l, gos);
-            if (c.se_col >= 0) atomicAdd(acc + off.o[HLVAE_ACC_GLS1] + (int64_t)r * L + l, gls * osr * il3);
-        }
-    }
-    const double fsum = warp_sum(lv);
-    if (lane == 0) {
-        double* scal = acc + off.o[HLVAE_ACC_SCAL] + (int64_t)l * HLVAE_NSCAL;
-        atomicAdd(scal + 1, bd);
-        atomicAdd(scal + 2, logdet);
-        atomicAdd(scal + 3, fsum);
-    }
-    __syncwarp();
-    }   // pairs
-}
-
 // =====================================================================================
-// kl_subject2_k: the same per-(subject, latent dim) stage with the T x T algebra restructured around what bounded
-// the first version (ncu r01k: shared-memory bandwidth - two conflicting LDS.64 per DFMA in every product):
+// kl_subject_k: one warp per (subject, latent dim).  The T x T algebra is laid out around what bounded the first
+// version of this kernel (ncu r01k: shared-memory bandwidth - two conflicting LDS.64 per DFMA in every product;
+// 0.63 ms at configs[1], this form 0.38 ms):
 //   * Cholesky and the triangular inverse keep "their" row / column in REGISTERS (loops fully unrolled over the
 //     padded size TP, so every register index is static); the only shared-memory operand left is a row of L that all
 //     lanes read at the same address (broadcast, conflict-free, two entries per LDS.128);
@@ -383,7 +82,7 @@ kl_subject_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict
 // Rows T..TP-1 are padded with an identity block (B) / zeros (Ktil), which leaves every result untouched.
 // =====================================================================================
 template <int TP>
-struct Subj2 {
+struct SubjShape {
     static constexpr int LDA = TP + 4;
     static constexpr int NT = TP / 8;
     static constexpr int NTRI = TP * (TP + 1) / 2;
@@ -394,15 +93,15 @@ struct Subj2 {
 };
 
 template <int TP, typename TS>
-__global__ void __launch_bounds__(SJ_WARPS * 32, Subj2<TP>::min_blocks)
-kl_subject2_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__ os0, const double* __restrict__ ls0,
+__global__ void __launch_bounds__(SJ_WARPS * 32, SubjShape<TP>::min_blocks)
+kl_subject_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__ os0, const double* __restrict__ ls0,
               const __grid_constant__ hlvae_kspec_t sp1, const double* __restrict__ os1, const double* __restrict__ ls1,
               const double* __restrict__ noise, int L, int Q, const double* __restrict__ x, int64_t ldx,
               const int32_t* __restrict__ row_idx, const int32_t* __restrict__ subj_ptr,
               const int32_t* __restrict__ tt_ptr, int n_subj, const TS* __restrict__ log_v, int64_t ld_lv,
               double* __restrict__ binv, int64_t tt_total, double* __restrict__ acc, const AccOff off,
               TS* __restrict__ g_logv, double gscale, int32_t* __restrict__ status) {
-    using S2 = Subj2<TP>;
+    using S2 = SubjShape<TP>;
     constexpr int LDA = S2::LDA, NT = S2::NT;
     extern __shared__ __align__(16) double smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -723,13 +422,13 @@ kl_subject2_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restric
 }
 
 template <int TP, typename TS>
-int launch_subject2(const hlvae_kspec_t* spec0, const double* os0, const double* ls0, const hlvae_kspec_t* spec1,
+int launch_subject(const hlvae_kspec_t* spec0, const double* os0, const double* ls0, const hlvae_kspec_t* spec1,
                     const double* os1, const double* ls1, const double* noise, int L, int Q, const double* x,
                     int64_t ldx, const int32_t* row_idx, const int32_t* subj_ptr, const int32_t* tt_ptr, int n_subj,
                     const void* log_v, int64_t ld_lv, double* binv, int64_t tt_total, double* acc, const AccOff& off,
                     void* g_logv, double gscale, int32_t* status, cudaStream_t st) {
-    const size_t smem = ((size_t)SJ_WARPS * Subj2<TP>::per_warp + Subj2<TP>::shared_doubles) * sizeof(double);
-    auto kern = kl_subject2_k<TP, TS>;
+    const size_t smem = ((size_t)SJ_WARPS * SubjShape<TP>::per_warp + SubjShape<TP>::shared_doubles) * sizeof(double);
+    auto kern = kl_subject_k<TP, TS>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     const int64_t pairs = (int64_t)n_subj * L;
@@ -745,9 +444,9 @@ int launch_subject2(const hlvae_kspec_t* spec0, const double* os0, const double*
 // kl_panel_k
 // =====================================================================================
 constexpr int PN_SMAX = 16;   // subjects per panel
-constexpr int PN_NCACHE = 3;  // K0 components whose unscaled values are kept from the K0xz pass to the gradient pass
-
-template <int MP, int RP, bool G_SMEM>
+// NC = K0 components whose unscaled values are kept from the K0xz pass to the gradient pass (the others are
+// re-evaluated there): 3 where one CTA owns the SM, 2 in the two-CTAs-per-SM shape (shared memory)
+template <int MP, int RP, bool G_SMEM, int NC>
 struct PanelSmem {
     static constexpr int LD = MP + 4;          // leading dim of row panels: conflict-free DMMA fragment loads
     static constexpr int LDB = RP + 4;         // leading dim of the dense block-diagonal B^-1 panel
@@ -755,7 +454,7 @@ struct PanelSmem {
                                       2 * (size_t)RP * LD /*Kb,Vb*/ + (size_t)RP * LDB /*Bp*/ +
                                       (size_t)RP * HLVAE_MAX_Q /*xs*/ + 3 * RP /*mus, rv, rho*/ +
                                       (size_t)MP * HLVAE_MAX_COMPS /*zacc*/ + 4 * HLVAE_MAX_COMPS + 8 /*hyper acc + A*/ +
-                                      8 * HLVAE_MAX_COMPS /*kps, kps1*/ + (size_t)PN_NCACHE * RP * MP /*vc*/ +
+                                      8 * HLVAE_MAX_COMPS /*kps, kps1*/ + (size_t)NC * RP * MP /*vc*/ +
                                       HLVAE_EXP_TAB /*etab*/;
     static constexpr size_t ints = 2 * RP + 3 * (PN_SMAX + 1) + 8;
     static constexpr size_t bytes = doubles * 8 + ints * 4;
@@ -763,7 +462,7 @@ struct PanelSmem {
 
 // NT threads per CTA: 512 (one CTA per SM) or 256 with RP = 32 (two CTAs per SM whose barrier and
 // latency stalls cover each other; register file: 2 x 256 x 128).  Warps form a (NT / 128) x 4 grid over tiles.
-template <int MP, int RP, bool G_SMEM, int NT, typename TS>
+template <int MP, int RP, bool G_SMEM, int NT, int NC, typename TS>
 __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1)
 kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__ os0, const double* __restrict__ ls0,
            const __grid_constant__ hlvae_kspec_t sp1, const double* __restrict__ os1, const double* __restrict__ ls1,
@@ -773,14 +472,15 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
            int64_t ld_mu, const double* __restrict__ w, const double* __restrict__ G,
            const double* __restrict__ binv, int64_t tt_total, double* __restrict__ acc, const AccOff off,
            TS* __restrict__ g_mu, TS* __restrict__ qdiag, double gscale, int32_t* __restrict__ status) {
-    using SM = PanelSmem<MP, RP, G_SMEM>;
+    using SM = PanelSmem<MP, RP, G_SMEM, NC>;
+    constexpr int PN_NCACHE = NC;
     constexpr int LD = SM::LD;
     constexpr int LDB = SM::LDB;
     constexpr int PN_THREADS = NT;
     constexpr int WGI = NT / 128;               // warp grid: WGI x 4
     constexpr int SIR = (MP / 8) / WGI;         // S tiles (8x8) per warp, rows
     constexpr int SIC = (MP / 8) / 4;           // S tiles per warp, columns
-    constexpr int WR = (RP / 8) / WGI;          // row tiles per warp for [RP x MP] outputs
+    constexpr int WR = (RP / 8 + WGI - 1) / WGI;   // row tiles per warp for [RP x MP] outputs (the last warp row may own fewer)
     constexpr int WC = (MP / 8) / 4;            // col tiles per warp for [RP x MP] outputs
     constexpr int NGRP = PN_THREADS / MP;       // row groups in the element-wise phases
     constexpr int RPT = RP / NGRP;              // rows per thread in the element-wise phases
@@ -868,7 +568,7 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
         for (int b = 0; b < SIC; b++) sacc[a][b][0] = sacc[a][b][1] = 0.0;
     double p_acc = 0.0, gw_acc = 0.0, a_acc = 0.0;
     // gradient sums of the cached K0 components, kept per thread over the CTA's whole chunk (reduced once at the end)
-    double hg0[PN_NCACHE], hg1[PN_NCACHE], hg2[PN_NCACHE];
+    double hg0[PN_NCACHE > 0 ? PN_NCACHE : 1], hg1[PN_NCACHE > 0 ? PN_NCACHE : 1], hg2[PN_NCACHE > 0 ? PN_NCACHE : 1];
 #pragma unroll
     for (int r = 0; r < PN_NCACHE; r++) hg0[r] = hg1[r] = hg2[r] = 0.0;
 
@@ -968,9 +668,11 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
 #pragma unroll
                     for (int f = 0; f < HLVAE_MAX_DISC; f++) zd[f] = (f < c.ndisc) ? Zs[c.disc_col[f] * MP + em] : 0.0;
                     const double hil2 = kps[HLVAE_MAX_COMPS + r], osr = kps[r];
-                    // Straight-line body (no data-dependent branches): the RPT rows of a thread are independent,
+                    // Straight-line bodies (no data-dependent branches): the RPT rows of a thread are independent,
                     // so their exponentials interleave and hide each other's latency.  Rows >= R read the
-                    // zero-filled tail of xs; their values are never used.
+                    // zero-filled tail of xs; their values are never used.  The number of discrete factors is the
+                    // same for every thread, so it selects one of three bodies without divergence: the components
+                    // kernel_gen.py builds have none or one, and skip the loads and compares of the general body.
                     const int nd = c.ndisc;
                     const bool cat0 = c.disc_kind[0] == HLVAE_KIND_CAT, cat1 = c.disc_kind[1] == HLVAE_KIND_CAT,
                                cat2 = c.disc_kind[2] == HLVAE_KIND_CAT;
@@ -979,17 +681,36 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
                     const int sc = c.se_col >= 0 ? c.se_col : 0;
                     const bool has_se = c.se_col >= 0;
                     double vv[RPT];
+                    if (nd == 0) {
 #pragma unroll
-                    for (int k = 0; k < RPT; k++) {
-                        const double* xr = xs + (eg + k * NGRP) * Q;
-                        const double a0 = xr[dc0], a1 = xr[dc1], a2 = xr[dc2];
-                        bool ok = true;
-                        ok = ok && (nd < 1 || (cat0 ? (a0 == zd[0]) : (a0 + zd[0] == 2.0)));
-                        ok = ok && (nd < 2 || (cat1 ? (a1 == zd[1]) : (a1 + zd[1] == 2.0)));
-                        ok = ok && (nd < 3 || (cat2 ? (a2 == zd[2]) : (a2 + zd[2] == 2.0)));
-                        const double d = xr[sc] - zse;
-                        const double e_ = has_se ? exp_nonpos_tab(-(d * d) * hil2, etab) : 1.0;
-                        vv[k] = ok ? e_ : 0.0;
+                        for (int k = 0; k < RPT; k++) {
+                            const double d = xs[(eg + k * NGRP) * Q + sc] - zse;
+                            vv[k] = has_se ? exp_nonpos_tab(-(d * d) * hil2, etab) : 1.0;
+                        }
+                    } else if (nd == 1) {
+                        const double z0 = zd[0];
+#pragma unroll
+                        for (int k = 0; k < RPT; k++) {
+                            const double* xr = xs + (eg + k * NGRP) * Q;
+                            const double a0 = xr[dc0];
+                            const bool ok = cat0 ? (a0 == z0) : (a0 + z0 == 2.0);
+                            const double d = xr[sc] - zse;
+                            const double e_ = has_se ? exp_nonpos_tab(-(d * d) * hil2, etab) : 1.0;
+                            vv[k] = ok ? e_ : 0.0;
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < RPT; k++) {
+                            const double* xr = xs + (eg + k * NGRP) * Q;
+                            const double a0 = xr[dc0], a1 = xr[dc1], a2 = xr[dc2];
+                            bool ok = true;
+                            ok = ok && (nd < 1 || (cat0 ? (a0 == zd[0]) : (a0 + zd[0] == 2.0)));
+                            ok = ok && (nd < 2 || (cat1 ? (a1 == zd[1]) : (a1 + zd[1] == 2.0)));
+                            ok = ok && (nd < 3 || (cat2 ? (a2 == zd[2]) : (a2 + zd[2] == 2.0)));
+                            const double d = xr[sc] - zse;
+                            const double e_ = has_se ? exp_nonpos_tab(-(d * d) * hil2, etab) : 1.0;
+                            vv[k] = ok ? e_ : 0.0;
+                        }
                     }
 #pragma unroll
                     for (int k = 0; k < RPT; k++) {
@@ -1115,6 +836,8 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
                         const int col = (wj * WC + t) * 8 + ar;       // B frag: row = k0 + lane%4, col = lane/4
                         if (G_SMEM) {
                             bfr[t] = Gs[(k0 + ac) * LD + col];
+                        } else if (M == MP) {                          // full tile: no bounds tests (uniform branch)
+                            bfr[t] = __ldg(Gl + (k0 + ac) * MP + col);
                         } else {
                             bfr[t] = (k0 + ac < M && col < M) ? __ldg(Gl + (int64_t)(k0 + ac) * M + col) : 0.0;
                         }
@@ -1386,15 +1109,15 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
     }
 }
 
-template <int MP, int RP, bool G_SMEM, int NT, typename TS>
+template <int MP, int RP, bool G_SMEM, int NT, int NC, typename TS>
 int launch_panel(const hlvae_kspec_t* spec0, const double* os0, const double* ls0, const hlvae_kspec_t* spec1,
                  const double* os1, const double* ls1, int L, int Q, int M, const double* x, int64_t ldx,
                  const double* z, const int32_t* row_idx, const int32_t* subj_ptr, const int32_t* tt_ptr, int n_subj,
                  int subj_per_chunk, const void* mu, int64_t ld_mu, const double* w, const double* G,
                  const double* binv, int64_t tt_total, double* acc, const AccOff& off, void* g_mu, void* qdiag,
                  double gscale, int32_t* status, cudaStream_t st) {
-    using SM = PanelSmem<MP, RP, G_SMEM>;
-    auto kern = kl_panel_k<MP, RP, G_SMEM, NT, TS>;
+    using SM = PanelSmem<MP, RP, G_SMEM, NC>;
+    auto kern = kl_panel_k<MP, RP, G_SMEM, NT, NC, TS>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::bytes);
     if (e != cudaSuccess) return (int)e;
     int n_chunks = (n_subj + subj_per_chunk - 1) / subj_per_chunk;
@@ -1412,16 +1135,23 @@ int dispatch_panel(int M, const hlvae_kspec_t* spec0, const double* os0, const d
                    int64_t ldx, const double* z, const int32_t* row_idx, const int32_t* subj_ptr,
                    const int32_t* tt_ptr, int n_subj, int subj_per_chunk, const void* mu, int64_t ld_mu,
                    const double* w, const double* G, const double* binv, int64_t tt_total, double* acc,
-                   const AccOff& off, void* g_mu, void* qdiag, double gscale, int32_t* status, cudaStream_t st) {
-#define HLVAE_PANEL(MP, RP, GS, NT)                                                                                   \
-    return launch_panel<MP, RP, GS, NT, TS>(spec0, os0, ls0, spec1, os1, ls1, L, Q, M, x, ldx, z, row_idx, subj_ptr,     \
+                   const AccOff& off, void* g_mu, void* qdiag, double gscale, int32_t* status, int row_panel,
+                   cudaStream_t st) {
+#define HLVAE_PANEL(MP, RP, GS, NT, NC)                                                                               \
+    return launch_panel<MP, RP, GS, NT, NC, TS>(spec0, os0, ls0, spec1, os1, ls1, L, Q, M, x, ldx, z, row_idx, subj_ptr,     \
                                         tt_ptr, n_subj, subj_per_chunk, mu, ld_mu, w, G, binv, tt_total, acc, off,   \
                                         g_mu, qdiag, gscale, status, st)
-    // (a 256-thread, RP = 32, two-CTAs-per-SM shape was measured 9 % slower at M = 64, T = 20: one subject per
-    // panel triples the per-panel fixed cost)
-    if (M <= 32) { HLVAE_PANEL(32, 64, true, 512); }
-    if (M <= 64) { HLVAE_PANEL(64, 64, false, 512); }
-    if (M <= 128) { HLVAE_PANEL(128, 32, false, 512); }
+    // Shapes: one 512-thread CTA per SM walking 64-row panels, or (32 < M <= 64, row_panel = 40) two 256-thread
+    // CTAs per SM walking 40-row panels - two CTAs cover each other's barrier and latency stalls, which pays when
+    // whole subjects fill 40 rows about as well as 64 (T = 20: 2 of 2 against 3 of 3.2; measured 1.32 against
+    // 1.40 ms at configs[1]).  Measured and dropped: 256 threads with 32-row panels (+9 %: one T = 20 subject per
+    // panel), 48-row panels (+10 %), 1024 threads at 64 registers (+18 %: spills, per-thread set-up doubled).
+    if (M <= 32) { HLVAE_PANEL(32, 64, true, 512, 3); }
+    if (M <= 64) {
+        if (row_panel == 40) { HLVAE_PANEL(64, 40, false, 256, 2); }
+        HLVAE_PANEL(64, 64, false, 512, 3);
+    }
+    if (M <= 128) { HLVAE_PANEL(128, 32, false, 512, 3); }
 #undef HLVAE_PANEL
     return HLVAE_E_UNSUPPORTED;
 }
@@ -1463,43 +1193,19 @@ extern "C" int hlvae_kl_subject(const hlvae_kspec_t* spec0, const double* os0, c
     AccOff off;
     fill_offsets(L, M, Q, off.o);
     cudaStream_t st = (cudaStream_t)stream;
-    if (!getenv("HLVAE_KL_SUBJECT_V1")) {
 #define HLVAE_SUBJ2(TP)                                                                                              \
     return dtype == HLVAE_F64                                                                                        \
-               ? launch_subject2<TP, double>(spec0, os0, ls0, spec1, os1, ls1, noise, L, Q, x, ldx, row_idx, subj_ptr, \
+               ? launch_subject<TP, double>(spec0, os0, ls0, spec1, os1, ls1, noise, L, Q, x, ldx, row_idx, subj_ptr, \
                                              tt_ptr, n_subj, log_v, ld_lv, binv, tt_total, acc, off, g_logv, gscale,  \
                                              status, st)                                                              \
-               : launch_subject2<TP, float>(spec0, os0, ls0, spec1, os1, ls1, noise, L, Q, x, ldx, row_idx, subj_ptr,  \
+               : launch_subject<TP, float>(spec0, os0, ls0, spec1, os1, ls1, noise, L, Q, x, ldx, row_idx, subj_ptr,  \
                                             tt_ptr, n_subj, log_v, ld_lv, binv, tt_total, acc, off, g_logv, gscale,   \
                                             status, st)
-        if (t_cap <= 8) { HLVAE_SUBJ2(8); }
-        if (t_cap <= 16) { HLVAE_SUBJ2(16); }
-        if (t_cap <= 24) { HLVAE_SUBJ2(24); }
-        HLVAE_SUBJ2(32);
+    if (t_cap <= 8) { HLVAE_SUBJ2(8); }
+    if (t_cap <= 16) { HLVAE_SUBJ2(16); }
+    if (t_cap <= 24) { HLVAE_SUBJ2(24); }
+    HLVAE_SUBJ2(32);
 #undef HLVAE_SUBJ2
-    }
-    const int ldt = t_cap | 1;
-    size_t smem = ((size_t)SJ_WARPS * ((size_t)t_cap * Q + 3 * (size_t)t_cap * ldt + SJ_KP) + HLVAE_EXP_TAB) * sizeof(double);
-    int64_t pairs = (int64_t)n_subj * L;
-    unsigned grid = (unsigned)((pairs + SJ_WARPS - 1) / SJ_WARPS);
-    cudaError_t e;
-    if (dtype == HLVAE_F64) {
-        auto kern = kl_subject_k<double>;
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        kern<<<grid, SJ_WARPS * 32, smem, st>>>(*spec0, os0, ls0, *spec1, os1, ls1, noise, L, Q, x, ldx, row_idx,
-                                                subj_ptr, tt_ptr, n_subj, t_cap, (const double*)log_v, ld_lv, binv,
-                                                tt_total, acc, off, (double*)g_logv, gscale, status);
-    } else {
-        auto kern = kl_subject_k<float>;
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        kern<<<grid, SJ_WARPS * 32, smem, st>>>(*spec0, os0, ls0, *spec1, os1, ls1, noise, L, Q, x, ldx, row_idx,
-                                                subj_ptr, tt_ptr, n_subj, t_cap, (const float*)log_v, ld_lv, binv,
-                                                tt_total, acc, off, (float*)g_logv, gscale, status);
-    }
-    HLVAE_CHECK_LAUNCH();
-    return 0;
 }
 
 extern "C" int hlvae_kl_panel(const hlvae_kspec_t* spec0, const double* os0, const double* ls0,
@@ -1508,7 +1214,7 @@ extern "C" int hlvae_kl_panel(const hlvae_kspec_t* spec0, const double* os0, con
                               const int32_t* subj_ptr, const int32_t* tt_ptr, int n_subj, int subj_per_chunk,
                               const void* mu, int64_t ld_mu, int dtype, const double* w, const double* G,
                               const double* binv, int64_t tt_total, double* acc, void* g_mu, void* qdiag,
-                              double gscale, int32_t* status, void* stream) {
+                              double gscale, int32_t* status, int row_panel, void* stream) {
     if (!hlvae::spec_valid(spec0, Q) || !hlvae::spec_valid(spec1, Q) || L <= 0 || Q <= 0 || Q > HLVAE_MAX_Q ||
         M <= 0 || n_subj < 0 || subj_per_chunk <= 0 || !x || !z || !row_idx || !subj_ptr || !tt_ptr || !mu || !w ||
         !G || !binv || !acc || !g_mu)
@@ -1521,10 +1227,10 @@ extern "C" int hlvae_kl_panel(const hlvae_kspec_t* spec0, const double* os0, con
     if (dtype == HLVAE_F64)
         return dispatch_panel<double>(M, spec0, os0, ls0, spec1, os1, ls1, L, Q, x, ldx, z, row_idx, subj_ptr, tt_ptr,
                                       n_subj, subj_per_chunk, mu, ld_mu, w, G, binv, tt_total, acc, off, g_mu, qdiag,
-                                      gscale, status, st);
+                                      gscale, status, row_panel, st);
     if (dtype == HLVAE_F32)
         return dispatch_panel<float>(M, spec0, os0, ls0, spec1, os1, ls1, L, Q, x, ldx, z, row_idx, subj_ptr, tt_ptr,
                                      n_subj, subj_per_chunk, mu, ld_mu, w, G, binv, tt_total, acc, off, g_mu, qdiag,
-                                     gscale, status, st);
+                                     gscale, status, row_panel, st);
     return HLVAE_E_ARG;
 }

@@ -92,32 +92,36 @@ class _KLD(torch.autograd.Function):
         g_lv = torch.empty_like(lv_c) if full else torch.zeros_like(lv_c)
         binv = torch.empty(L, max(layout.tt_total, 1), **f64)
 
-        # ---- 2a. per-subject T x T stage on a side stream (independent of the M x M pre-stage)
+        # ---- 1. M x M pre-stage (replicated): iK, iH, w = iK m, G = iK H iK - iK.  2 L CTAs of 166 KB shared
+        # memory each: launched FIRST, so that they are resident before the per-subject stage floods the block
+        # scheduler (launched second, its small CTAs never leave an SM enough shared memory for one of these,
+        # and the two kernels serialise)
         cur = torch.cuda.current_stream(dev)
         side = _side_stream(dev) if (config.overlap and layout.n_subj > 0) else None
+        if side is not None:
+            side.wait_stream(cur)
+        _lib.call("hlvae_mxm_pre", fs0.cspec, _lib.ptr(os0c), _lib.ptr(ls0c), L, Q, M, _lib.ptr(z_c), eps,
+                  _lib.ptr(m_c), _lib.ptr(H_c), _lib.ptr(iK), _lib.ptr(iH), _lib.ptr(w), _lib.ptr(G), _lib.ptr(pre),
+                  _lib.ptr(ws), _lib.ptr(status), st)
+        # ---- 2a. per-subject T x T stage on a side stream (independent of the M x M pre-stage)
         if layout.n_subj > 0:
-            if side is not None:
-                side.wait_stream(cur)
             with torch.cuda.stream(side if side is not None else cur):
                 _lib.call("hlvae_kl_subject", fs0.cspec, _lib.ptr(os0c), _lib.ptr(ls0c), fs1.cspec, _lib.ptr(os1c),
                           _lib.ptr(ls1c), _lib.ptr(noise), L, Q, _lib.ptr(x_c), Q, _lib.ptr(layout.row_idx),
                           _lib.ptr(layout.subj_ptr), _lib.ptr(layout.tt_ptr), layout.n_subj, max(layout.t_max, 1),
                           _lib.ptr(lv_c), L, dcode, _lib.ptr(binv), binv.shape[1], _lib.ptr(acc), M, _lib.ptr(g_lv),
                           scale, _lib.ptr(status), _lib.stream_ptr())
-        # ---- 1. M x M pre-stage (replicated): iK, iH, w = iK m, G = iK H iK - iK
-        _lib.call("hlvae_mxm_pre", fs0.cspec, _lib.ptr(os0c), _lib.ptr(ls0c), L, Q, M, _lib.ptr(z_c), eps,
-                  _lib.ptr(m_c), _lib.ptr(H_c), _lib.ptr(iK), _lib.ptr(iH), _lib.ptr(w), _lib.ptr(G), _lib.ptr(pre),
-                  _lib.ptr(ws), _lib.ptr(status), st)
         if side is not None:
             cur.wait_stream(side)
         # ---- 2b. streaming stage over the minibatch rows
         if layout.n_subj > 0:
-            spc = _subjects_per_chunk(layout.n_subj, layout.t_max, L, M)
+            rp = _row_panel(layout, M)
+            spc = _subjects_per_chunk(layout.n_subj, layout.t_max, L, M, rp=rp)
             _lib.call("hlvae_kl_panel", fs0.cspec, _lib.ptr(os0c), _lib.ptr(ls0c), fs1.cspec, _lib.ptr(os1c),
                       _lib.ptr(ls1c), L, Q, M, _lib.ptr(x_c), Q, _lib.ptr(z_c), _lib.ptr(layout.row_idx),
                       _lib.ptr(layout.subj_ptr), _lib.ptr(layout.tt_ptr), layout.n_subj, spc, _lib.ptr(mu_c), L,
                       dcode, _lib.ptr(w), _lib.ptr(G), _lib.ptr(binv), binv.shape[1], _lib.ptr(acc), _lib.ptr(g_mu),
-                      None, scale, _lib.ptr(status), st)
+                      None, scale, _lib.ptr(status), rp, st)
         # ---- 3. data parallel: one all-reduce of every accumulator (S, p, scalars, replicated-parameter grads)
         if config.process_group is not None:
             torch.distributed.all_reduce(acc, group=config.process_group)
@@ -216,14 +220,32 @@ def minibatch_KLD_upper_bound_iter(covar_module0, covar_module1, likelihood, lat
                 P / P_in_current_batch, latent_dim * N / 2, natural_gradient, eps, (1,))
 
 
-def _subjects_per_chunk(n_subj, t_max, L, M, waves=None):
-    """Subjects per hlvae_kl_panel CTA.  A CTA walks its chunk in row panels of RP rows (64 for M <= 64, else 32) that
-    hold whole subjects, so a chunk should be a whole number of full panels (a trailing panel with one subject costs
-    nearly as much as a full one), and L * n_chunks CTAs should fill a whole number of waves of N_SM CTAs."""
+PANEL_COST_40 = 0.63      # device time of a 40-row panel (two CTAs per SM) relative to a 64-row one, measured (T = 20)
+
+
+def _row_panel(layout, M):
+    """Rows per panel for hlvae_kl_panel: 0 = the library's default shape for M; 40 = the two-CTAs-per-SM shape
+    (32 < M <= 64), chosen when the subjects of this minibatch need so few more 40-row panels than 64-row ones
+    that the cheaper panel wins (fixed T = 20: 2 subjects per 40 rows against 3 per 64)."""
     import os
-    rp = 64 if M <= 64 else 32
+    forced = os.environ.get("HLVAE_PANEL_RP")
+    if forced is not None:
+        return int(forced)
+    if not (32 < M <= 64) or layout.t_max > 40 or layout.n_subj == 0:
+        return 0
+    return 40 if layout.panels(40) * PANEL_COST_40 < layout.panels(64) else 0
+
+
+def _subjects_per_chunk(n_subj, t_max, L, M, waves=None, rp=0):
+    """Subjects per hlvae_kl_panel CTA.  A CTA walks its chunk in row panels of RP rows (64 for M <= 64, else 32; 40
+    in the two-CTAs-per-SM shape) that hold whole subjects, so a chunk should be a whole number of full panels (a
+    trailing panel with one subject costs nearly as much as a full one), and L * n_chunks CTAs should fill a whole
+    number of waves of resident CTAs."""
+    import os
+    two = rp == 40
+    rp = rp or (64 if M <= 64 else 32)
     spp = max(1, rp // max(int(t_max), 1))                    # subjects per full panel
-    waves = int(os.environ.get("HLVAE_PANEL_WAVES", waves or PANEL_WAVES))
+    waves = int(os.environ.get("HLVAE_PANEL_WAVES", waves or (2 * PANEL_WAVES if two else PANEL_WAVES)))
     n_panels = (n_subj + spp - 1) // spp
     # at least `waves` waves of CTAs, and no more than ~30 panels per CTA (large batches: more, shorter CTAs balance
     # the tail better - measured at 64 000 rows)

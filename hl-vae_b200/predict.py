@@ -51,7 +51,7 @@ def _stream_pass(fs0, fs1, hp, L, Q, M, x, z, layout, mu, w, noise, binv=None):
     _lib.call("hlvae_kl_panel", fs0.cspec, _lib.ptr(os0), _lib.ptr(ls0), fs1.cspec, _lib.ptr(os1), _lib.ptr(ls1), L, Q, M,
               _lib.ptr(x), Q, _lib.ptr(z), _lib.ptr(layout.row_idx), _lib.ptr(layout.subj_ptr), _lib.ptr(layout.tt_ptr),
               layout.n_subj, spc, _lib.ptr(mu), L, _lib.F64, _lib.ptr(w), _lib.ptr(G), _lib.ptr(binv), binv.shape[1],
-              _lib.ptr(acc), _lib.ptr(g_mu), None, 1.0, _lib.ptr(status), st)
+              _lib.ptr(acc), _lib.ptr(g_mu), None, 1.0, _lib.ptr(status), 0, st)
     code = int(status[0])
     if code == _lib.STATUS_NOT_PD:
         raise RuntimeError("hlvae_b200: cholesky: B_s is not positive-definite")

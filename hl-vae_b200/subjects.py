@@ -13,9 +13,33 @@ from . import _lib
 
 
 class SubjectLayout:
-    def __init__(self, row_idx, subj_ptr, tt_ptr, n_subj, n_rows, t_max, tt_total):
+    def __init__(self, row_idx, subj_ptr, tt_ptr, n_subj, n_rows, t_max, tt_total, lens=None):
         self.row_idx, self.subj_ptr, self.tt_ptr = row_idx, subj_ptr, tt_ptr
         self.n_subj, self.n_rows, self.t_max, self.tt_total = int(n_subj), int(n_rows), int(t_max), int(tt_total)
+        self._lens = lens               # host copy of the subject lengths (int64 tensor) for panel planning
+        self._panels = {}
+
+    def panels(self, rows_per_panel):
+        """Number of row panels hlvae_kl_panel needs when it packs whole subjects, in order, into panels of
+        `rows_per_panel` rows (and at most 16 subjects) - host arithmetic on the lengths, cached."""
+        rp = int(rows_per_panel)
+        if rp not in self._panels:
+            if self._lens is None or self.n_subj == 0:
+                per = max(1, min(16, rp // max(self.t_max, 1)))
+                self._panels[rp] = (self.n_subj + per - 1) // per
+            else:
+                lens = self._lens.tolist()
+                if len(set(lens)) == 1:
+                    per = max(1, min(16, rp // max(lens[0], 1)))
+                    self._panels[rp] = (len(lens) + per - 1) // per
+                else:
+                    n, rows, ns = 0, 0, 0
+                    for t in lens:
+                        if ns > 0 and (rows + t > rp or ns == 16):
+                            n, rows, ns = n + 1, 0, 0
+                        rows, ns = rows + t, ns + 1
+                    self._panels[rp] = n + (1 if ns else 0)
+        return self._panels[rp]
 
     @staticmethod
     def _finish(row_idx, lengths_host, device):
@@ -32,7 +56,7 @@ class SubjectLayout:
             tp[1:] = torch.cumsum(lens * lens, 0)
         return SubjectLayout(row_idx.to(device=device, dtype=torch.int32).contiguous(),
                              sp.to(device=device, dtype=torch.int32), tp.to(device=device, dtype=torch.int32),
-                             n_subj, int(sp[-1]), t_max, int(tp[-1]))
+                             n_subj, int(sp[-1]), t_max, int(tp[-1]), lens=lens)
 
     @staticmethod
     def fixed(n_rows, T, device):

@@ -69,7 +69,7 @@ def _pieces(L, covar_module0, covar_module1, likelihood, train_xt, m, log_v, z, 
                   L, Q, M, _lib.ptr(x), Q, _lib.ptr(zc), _lib.ptr(layout.row_idx), _lib.ptr(layout.subj_ptr),
                   _lib.ptr(layout.tt_ptr), layout.n_subj, spc, _lib.ptr(mu_), L, _lib.F64, _lib.ptr(zero_w),
                   _lib.ptr(G_), _lib.ptr(binv), binv.shape[1], _lib.ptr(acc_), _lib.ptr(scratch), _lib.ptr(qdiag),
-                  1.0, _lib.ptr(status), st)
+                  1.0, _lib.ptr(status), 0, st)
 
     panel(acc, mu, torch.zeros(L, M, M, **f64), None)
     S = acc[off["S"]:off["S"] + L * M * M].view(L, M, M)

@@ -128,6 +128,10 @@ int hlvae_kernel_matvec(const hlvae_kspec_t* spec, const double* outputscale, co
  * gscale * dJ/dmu and gscale * dJ/dlog_v (gscale = P / P_batch of elbo_functions.py:181,277).
  * qdiag (nullable, [N, L], storage dtype): per row r the quadratic form (B^-1 K0xz)_r G (B^-1 K0xz)_r^T, the
  * diagonal that validation.validation_dubo needs with G = W^-1 (validation.py:69-72).
+ * row_panel: rows per panel of hlvae_kl_panel (whole subjects are packed into panels); 0 = the default shape for M
+ * (64 rows for M <= 64, 32 for M <= 128), 40 = the two-CTAs-per-SM shape for 32 < M <= 64 (every subject must have
+ * <= 40 rows; it pays when subjects fill 40-row panels about as well as 64-row ones, e.g. T = 20).  Scheduling
+ * only: results agree to float64 summation order.
  * ---------------------------------------------------------------------------------- */
 #define HLVAE_ACC_S 0
 #define HLVAE_ACC_P 1
@@ -156,7 +160,7 @@ int hlvae_kl_panel(const hlvae_kspec_t* spec0, const double* os0, const double* 
                    const int32_t* row_idx, const int32_t* subj_ptr, const int32_t* tt_ptr, int n_subj,
                    int subj_per_chunk, const void* mu, int64_t ld_mu, int dtype,
                    const double* w, const double* G, const double* binv, int64_t tt_total,
-                   double* acc, void* g_mu, void* qdiag, double gscale, int32_t* status, void* stream);
+                   double* acc, void* g_mu, void* qdiag, double gscale, int32_t* status, int row_panel, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Replicated M x M stage (float64, one CTA per latent dimension, M <= 128).
