@@ -61,7 +61,7 @@ def parse():
     ap.add_argument("--no-split-backward", action="store_true", help="one backward() of nll + kld instead of one per branch")
     ap.add_argument("--no-natgrad-stream", action="store_true", help="natural-gradient update on the KL stream, not its own")
     ap.add_argument("--no-kl-priority", action="store_true", help="KL stream at default priority")
-    ap.add_argument("--workload", default="elbo", choices=["elbo", "predict", "sweep", "theta", "full", "norm"],
+    ap.add_argument("--workload", default="elbo", choices=["elbo", "predict", "sweep", "theta", "full", "norm", "contraction"],
                     help="elbo: the BASELINE.json metric (default); predict: SURVEY 8(f) row 1, GP posterior-mean "
                          "prediction (utils.batch_predict_varying_T), its own JSON line")
     return ap.parse_args()
@@ -1190,8 +1190,65 @@ def other_configs(dev, s_small, fp64_peak, hbm_peak):
     return out
 
 
+def run_contraction(args):
+    """A/B of the sufficient-statistics contraction S = K^T V (elbo_functions.py:161 / :254,266) on the two tensor
+    pipes at the configs[1] shape (L = 32, M = 64, 16000 rows): FP64 mma.sync against tcgen05.mma kind::i8 with an
+    error-free 8-bit splitting (csrc/contraction_probe.cu).  Device time (CUDA events), error against the float64
+    product, algorithmic and executed operations."""
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    import math
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    import __graft_entry__ as g
+    g.build()
+    from hlvae_b200 import _lib
+    N = args.subjects * T
+    gen = torch.Generator(device=dev).manual_seed(0)
+    K = torch.rand(L, N, M, generator=gen, device=dev, dtype=torch.float64) * 2.0
+    V = torch.randn(L, N, M, generator=gen, device=dev, dtype=torch.float64)
+    ref = K.transpose(1, 2) @ V
+    scale = float((K.abs().transpose(1, 2) @ V.abs()).max())
+    ks = 2.0 ** math.ceil(math.log2(float(K.max()) * (1 + 1e-12)))
+    vs = 2.0 ** math.ceil(math.log2(float(V.abs().max()) * (1 + 1e-12)))
+    status = torch.zeros(4, dtype=torch.int32, device=dev)
+    rows = []
+    for mode, ns, rpc in [(0, 0, 1920), (0, 0, 960)] + [(1, ns, rpc) for ns in (4, 5, 6, 7) for rpc in (1920, 960)]:
+        S = torch.zeros(L, M, M, dtype=torch.float64, device=dev)
+
+        def call():
+            _lib.call("hlvae_contraction_probe", mode, ns, L, N, M, _lib.ptr(K), _lib.ptr(V), ks, vs, rpc, _lib.ptr(S),
+                      _lib.ptr(status), _lib.stream_ptr())
+
+        call()
+        torch.cuda.synchronize()
+        err = float((S - ref).abs().max()) / scale
+        for _ in range(3):
+            call()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            call()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        algo = 2.0 * L * N * M * M
+        pairs = sum(1 for g_ in range(ns) for p in range((ns + 1) // 2) if 0 <= g_ - 2 * p < ns) if mode else 1
+        rows.append(dict(pipe="fp64 mma.sync" if mode == 0 else f"tcgen05 kind::i8, {ns} slices", rows_per_cta=rpc,
+                         ms=round(ms, 4), rel_err=err, algorithmic_tflops=round(algo / (ms * 1e-3) / 1e12, 2),
+                         executed_mma_ops=(2.0 * L * N * 128 * M * pairs) if mode else algo,
+                         hbm_gbs=round(2 * L * N * M * 8 / (ms * 1e-3) / 1e9)))
+    assert int(status[0]) == 0, status.tolist()
+    print(json.dumps(dict(workload=f"contraction A/B: S = K^T V, L={L}, M={M}, {N} rows (operands read from HBM: "
+                                   f"{2 * L * N * M * 8 / 1e6:.0f} MB)", steps=args.steps, cases=rows)), flush=True)
+
+
 def main():
     args = parse()
+    if args.workload == "contraction" and args.impl != "reference":
+        run_contraction(args)
+        return
     if args.workload == "predict" and args.impl != "reference":
         run_predict(args)
         return

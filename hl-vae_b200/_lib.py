@@ -61,6 +61,7 @@ _SIGS = {
     "hlvae_discrete_transform": ([_L, _I, _L, _P, _P, _P, _P, _I, _P, _P], _I),
     "hlvae_loglik_aux_fwd": ([_I, _L, _I, _P, _L, _I, _P, _L, _I, _P, _L, _L, _P, _L, _I, _P, _P, _P, _P, _P, _P, _P], _I),
     "hlvae_loglik_aux_bwd": ([_I, _L, _I, _P, _L, _I, _P, _L, _I, _P, _L, _L, _P, _L, _I, _P, _P, _P, _P, _P, _P, _P, _P], _I),
+    "hlvae_contraction_probe": ([_I, _I, _I, _L, _I, _P, _P, _D, _D, _I, _P, _P, _P], _I),
     "hlvae_batch_norm_stats": ([_L, _I, _L, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _P, _P], _I),
     "hlvae_batch_norm_apply": ([_L, _I, _L, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P], _I),
     "hlvae_theta_fwd": ([_L, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _L, _L, _L, _I, _P, _L, _P], _I),

@@ -340,6 +340,18 @@ int hlvae_batch_norm_apply(int64_t N, int D, int64_t ld_data, const int32_t* var
                            const void* data, const void* mask, int dtype, int data_dtype, int mask_dtype, int conv,
                            const double* meanvar, void* out, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * A/B probe (not on the product path): S[l] += K[l]^T V[l] for K, V [L, N, 64] float64 row-major, S [L, 64, 64],
+ * the sufficient-statistics contraction of elbo_functions.py:161 / :254,266 on the two tensor pipes.
+ *   mode 0: FP64 mma.sync (the form hlvae_kl_panel uses);
+ *   mode 1: tcgen05.mma kind::i8 into TMEM with an error-free 8-bit splitting of the operands (`nslice` slices of
+ *           K / k_scale in [0, 1) and V / v_scale in [-1, 1); k_scale, v_scale: powers of two bounding the data),
+ *           drained with tcgen05.ld and recombined in float64.  rows_per_cta <= 8192 (int32 accumulators).
+ * status: device words {code, l, cta}; code 3 = a tensor-core completion barrier timed out. */
+int hlvae_contraction_probe(int mode, int nslice, int L, int64_t N, int M, const double* K, const double* V,
+                            double k_scale, double v_scale, int rows_per_cta, double* S, int32_t* status,
+                            void* stream);
+
 #ifdef __cplusplus
 }
 #endif
