@@ -91,25 +91,60 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, int32_t (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// byte `b` (0 = least significant) of four 64-bit fixed-point values, packed into one word (value 0 in byte 0)
-__device__ __forceinline__ uint32_t pack_byte(const long long (&q)[16], int first, int b) {
-    uint32_t w = 0;
+// first stacked operand p whose pair (p, b = g - 2 p) exists for accumulator g: the MMA that initialises it
+__device__ __forceinline__ int first_pair(int g, int nslice) {
+    for (int p = 0;; p++)
+        if (g - 2 * p < nslice) return p;
+}
+
+// byte `B` (0 = least significant, compile time) of four 64-bit fixed-point values packed into one word (value 0 in
+// byte 0): three byte-permute instructions
+template <int B>
+__device__ __forceinline__ uint32_t pack_byte(const long long (&q)[16], int first) {
+    uint32_t x[4];
 #pragma unroll
-    for (int u = 0; u < 4; u++) w |= (uint32_t)((unsigned long long)q[first + u] >> (8 * b) & 0xFFull) << (8 * u);
-    return w;
+    for (int u = 0; u < 4; u++)
+        x[u] = B < 4 ? (uint32_t)(unsigned long long)q[first + u] : (uint32_t)((unsigned long long)q[first + u] >> 32);
+    constexpr uint32_t sel = (uint32_t)(B & 3) | ((uint32_t)(4 + (B & 3)) << 4);     // byte B of x[0], byte B of x[1]
+    const uint32_t t0 = __byte_perm(x[0], x[1], sel), t1 = __byte_perm(x[2], x[3], sel);
+    return __byte_perm(t0, t1, 0x5410);
+}
+
+template <int NS, int A>
+__device__ __forceinline__ void store_slices(const long long (&qk)[16], const long long (&qv)[16], uint8_t* a_st,
+                                             uint8_t* b_st, int ks, int kc, int m) {
+    if constexpr (A < NS) {
+        constexpr int B = NS - 1 - A;                      // byte of the fixed-point value that is slice A
+        const int mr = (A & 1) * 64 + m;
+        uint4 w, y;
+        w.x = pack_byte<B>(qk, 0); w.y = pack_byte<B>(qk, 4); w.z = pack_byte<B>(qk, 8); w.w = pack_byte<B>(qk, 12);
+        y.x = pack_byte<B>(qv, 0); y.y = pack_byte<B>(qv, 4); y.z = pack_byte<B>(qv, 8); y.w = pack_byte<B>(qv, 12);
+        // element (row m', k) of a K-major operand: (m' % 8) * 16 + (m' / 8) * 256 + (k / 16) * 128 + k % 16
+        *reinterpret_cast<uint4*>(a_st + (ks * (P_MAXSLICE / 2) + (A >> 1)) * A_BYTES + (mr & 7) * 16 + (mr >> 3) * 256 + kc * 128) = w;
+        *reinterpret_cast<uint4*>(b_st + (ks * P_MAXSLICE + A) * B_BYTES + (m & 7) * 16 + (m >> 3) * 256 + kc * 128) = y;
+        store_slices<NS, A + 1>(qk, qv, a_st, b_st, ks, kc, m);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// mode 1.  CTA = 128 threads: thread (m = tid % 64, h = tid / 64) converts rows h*16 .. h*16+15 of column m of the
-// current 32-row step; thread 0 issues the MMAs; the four warps drain the 128 TMEM lanes at the end.
+// mode 1.  CTA = 256 threads, one CTA per SM (448 of the 512 TMEM columns).  A stage is 64 rows = two K = 32 steps;
+// thread (m = tid % 64, h = tid / 64) converts rows 16 h .. 16 h + 15 of column m.  Two stages of operand buffers:
+// while the tensor core reads stage s, the threads slice stage s + 1 (the completion barrier of a stage is only
+// waited for before that stage is overwritten).  Thread 0 issues the MMAs; warps 0..3 drain the 128 TMEM lanes.
 // Slice a (0 = most significant) of K sits in stacked operand a / 2, rows (a % 2) * 64 + m; accumulator g collects
 // the pairs (operand p, V slice b) with 2 p + b = g: lanes 0..63 carry weight 2^-8g, lanes 64..127 weight 2^-8(g+1).
-__global__ void __launch_bounds__(128, 1)
-probe_i8_k(int nslice, int64_t N, const double* __restrict__ K, const double* __restrict__ V, double k_scale,
+constexpr int PI_THREADS = 256;
+constexpr int PI_STAGE_ROWS = 2 * PK;
+constexpr int PI_A_STAGE = 2 * (P_MAXSLICE / 2) * A_BYTES;      // [kstep][pair][A_BYTES]
+constexpr int PI_B_STAGE = 2 * P_MAXSLICE * B_BYTES;            // [kstep][slice][B_BYTES]
+constexpr int PI_SMEM = 2 * (PI_A_STAGE + PI_B_STAGE);
+
+template <int NS>
+__global__ void __launch_bounds__(PI_THREADS, 1)
+probe_i8_k(int64_t N, const double* __restrict__ K, const double* __restrict__ V, double k_scale,
            double v_scale, int rows_per_cta, double* __restrict__ S, int32_t* __restrict__ status) {
-    __shared__ __align__(1024) uint8_t a_op[P_MAXSLICE / 2][A_BYTES];
-    __shared__ __align__(1024) uint8_t b_op[P_MAXSLICE][B_BYTES];
-    __shared__ __align__(8) uint64_t bar;
+    extern __shared__ __align__(1024) uint8_t pi_smem[];
+    __shared__ __align__(8) uint64_t bar_free[2];
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int l = blockIdx.y;
@@ -117,10 +152,14 @@ probe_i8_k(int nslice, int64_t N, const double* __restrict__ K, const double* __
     const int64_t row_end = min(N, row_begin + rows_per_cta);
     const double* Kl = K + (int64_t)l * N * PM;
     const double* Vl = V + (int64_t)l * N * PM;
-    const int nacc = nslice;                           // accumulators g = 0 .. nslice - 1 (64 columns each)
-    const int np = (nslice + 1) / 2;                   // stacked A operands
+    constexpr int nslice = NS;
+    constexpr int nacc = NS;                           // accumulators g = 0 .. nslice - 1 (64 columns each)
+    constexpr int np = (NS + 1) / 2;                   // stacked A operands
 
-    if (tid == 0) mbar_init(&bar, 1);
+    if (tid == 0) {
+        mbar_init(&bar_free[0], 1);
+        mbar_init(&bar_free[1], 1);
+    }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
                      "r"(512)
@@ -128,21 +167,24 @@ probe_i8_k(int nslice, int64_t N, const double* __restrict__ K, const double* __
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     // an odd slice count leaves the lower half of the last stacked operand unused: it must read as zeros
-    for (int e = tid; e < (P_MAXSLICE / 2) * A_BYTES / 16; e += 128) reinterpret_cast<uint4*>(&a_op[0][0])[e] = make_uint4(0, 0, 0, 0);
+    for (int e = tid; e < PI_SMEM / 16; e += PI_THREADS) reinterpret_cast<uint4*>(pi_smem)[e] = make_uint4(0, 0, 0, 0);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_slot;
 
-    const int m = tid & 63, h = tid >> 6;
+    const int m = tid & 63, h = tid >> 6;              // h: 16-row group of the stage; K step h / 2, K chunk h % 2
     const double kmul = ldexp(1.0, 8 * nslice) / k_scale;          // K / k_scale in [0, 1) -> unsigned 8 nslice bits
     const double vmul = ldexp(1.0, 8 * nslice - 1) / v_scale;      // V / v_scale in [-1, 1) -> signed
-    uint32_t phase = 0;
+    uint32_t phase[2] = {0, 0};
     bool ok = true;
-    bool first_mma = true;
-    for (int64_t r0 = row_begin; r0 < row_end && ok; r0 += PK) {
-        // ---- slice the 32-row step (rows beyond the end contribute zeros)
+    int step = 0;
+    for (int64_t r0 = row_begin; r0 < row_end && ok; r0 += PI_STAGE_ROWS, step++) {
+        const int st = step & 1;
+        uint8_t* a_st = pi_smem + st * (PI_A_STAGE + PI_B_STAGE);
+        uint8_t* b_st = a_st + PI_A_STAGE;
+        // ---- load and convert this thread's 16 rows (rows beyond the end contribute zeros)
         long long qk[16], qv[16];
 #pragma unroll
         for (int u = 0; u < 16; u++) {
@@ -153,47 +195,40 @@ probe_i8_k(int nslice, int64_t N, const double* __restrict__ K, const double* __
             qk[u] = __double2ll_rd(kv * kmul);
             qv[u] = __double2ll_rd(vv * vmul);
         }
-        // element (row m', k) of a K-major operand: (m' % 8) * 16 + (m' / 8) * 256 + (k / 16) * 128 + k % 16
-#pragma unroll
-        for (int a = 0; a < P_MAXSLICE; a++) {
-            if (a < nslice) {
-                const int bsel = nslice - 1 - a;                   // byte of the fixed-point value
-                const int mr = (a & 1) * 64 + m;
-                uint4 w;
-                w.x = pack_byte(qk, 0, bsel); w.y = pack_byte(qk, 4, bsel); w.z = pack_byte(qk, 8, bsel); w.w = pack_byte(qk, 12, bsel);
-                *reinterpret_cast<uint4*>(&a_op[a >> 1][(mr & 7) * 16 + (mr >> 3) * 256 + h * 128]) = w;
-                uint4 y;
-                y.x = pack_byte(qv, 0, bsel); y.y = pack_byte(qv, 4, bsel); y.z = pack_byte(qv, 8, bsel); y.w = pack_byte(qv, 12, bsel);
-                *reinterpret_cast<uint4*>(&b_op[a][(m & 7) * 16 + (m >> 3) * 256 + h * 128]) = y;
-            }
+        if (step >= 2) {                                                   // the MMAs that read this stage are done?
+            ok = mbar_wait(&bar_free[st], phase[st]);
+            phase[st] ^= 1;
         }
+        store_slices<NS, 0>(qk, qv, a_st, b_st, h >> 1, h & 1, m);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic-proxy stores -> tensor-core reads
         __syncthreads();
-        if (tid == 0) {
+        if (tid == 0 && ok) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            for (int g = 0; g < nacc; g++) {
-                bool fresh = first_mma;
-                for (int p = 0; p < np; p++) {
-                    const int b = g - 2 * p;
-                    if (b < 0 || b >= nslice) continue;
-                    const uint64_t ad = umma_desc(smem_u32(&a_op[p][0]), 128, 256);
-                    const uint64_t bd = umma_desc(smem_u32(&b_op[b][0]), 128, 256);
-                    // K slices are unsigned; the most significant V slice carries the sign
-                    umma_i8(tmem + 64 * g, ad, bd, umma_idesc_i8(0, b == 0 ? 1 : 0, 128, PM), fresh ? 0u : 1u);
-                    fresh = false;
-                }
-            }
-            umma_commit(&bar);                                             // arrives when the MMAs above have read smem
+            for (int kk = 0; kk < 2; kk++)
+                for (int g = 0; g < nacc; g++)
+                    for (int p = 0; p < np; p++) {
+                        const int b = g - 2 * p;
+                        if (b < 0 || b >= nslice) continue;
+                        const uint64_t ad = umma_desc(smem_u32(a_st + (kk * (P_MAXSLICE / 2) + p) * A_BYTES), 128, 256);
+                        const uint64_t bd = umma_desc(smem_u32(b_st + (kk * P_MAXSLICE + b) * B_BYTES), 128, 256);
+                        // K slices are unsigned; the most significant V slice carries the sign.  The very first
+                        // MMA into an accumulator overwrites it.
+                        umma_i8(tmem + 64 * g, ad, bd, umma_idesc_i8(0, b == 0 ? 1 : 0, 128, PM),
+                                (step == 0 && kk == 0 && p == first_pair(g, nslice)) ? 0u : 1u);
+                    }
+            umma_commit(&bar_free[st]);                                    // arrives when the MMAs above have read smem
         }
-        first_mma = false;
-        ok = mbar_wait(&bar, phase);                                       // the operands may be overwritten now
-        phase ^= 1;
+    }
+    // all MMAs complete <=> the last commit of each stage has arrived
+    for (int st = 0; st < 2 && ok; st++) {
+        const int uses = (step + 1 - st) / 2;                              // steps that used stage st
+        if (uses > 0) ok = mbar_wait(&bar_free[st], phase[st]);
     }
     if (!ok && tid == 0) report_status(status, 3, l, (int)blockIdx.x);
 
-    // ---- drain: warp w owns TMEM lanes 32 w .. 32 w + 31 (row m' = 32 w + lane of every accumulator)
+    // ---- drain: warp w < 4 owns TMEM lanes 32 w .. 32 w + 31 (row m' = 32 w + lane of every accumulator)
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    if (ok && row_end > row_begin) {
+    if (ok && row_end > row_begin && warp < 4) {
         const int mrow = warp * 32 + lane;                                 // 0..127: upper half = next slice weight
         const int mi = mrow & 63;
         double out[PM];
@@ -291,7 +326,18 @@ extern "C" int hlvae_contraction_probe(int mode, int nslice, int L, int64_t N, i
         // (7 slices = 56 bits cover the 53-bit significand; 8 would overflow the 64-bit fixed-point value)
         if (nslice < 2 || nslice > 7 || !(k_scale > 0.0) || !(v_scale > 0.0) || rows_per_cta > 8192)
             return HLVAE_E_ARG;
-        probe_i8_k<<<grid, 128, 0, (cudaStream_t)stream>>>(nslice, N, K, V, k_scale, v_scale, rows_per_cta, S, status);
+#define HLVAE_PROBE_I8(NS)                                                                                          \
+    case NS: {                                                                                                      \
+        cudaError_t e = cudaFuncSetAttribute(probe_i8_k<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, PI_SMEM); \
+        if (e != cudaSuccess) return (int)e;                                                                        \
+        probe_i8_k<NS><<<grid, PI_THREADS, PI_SMEM, (cudaStream_t)stream>>>(N, K, V, k_scale, v_scale, rows_per_cta, \
+                                                                            S, status);                             \
+        break;                                                                                                      \
+    }
+        switch (nslice) {
+            HLVAE_PROBE_I8(2) HLVAE_PROBE_I8(3) HLVAE_PROBE_I8(4) HLVAE_PROBE_I8(5) HLVAE_PROBE_I8(6) HLVAE_PROBE_I8(7)
+        }
+#undef HLVAE_PROBE_I8
     } else {
         return HLVAE_E_ARG;
     }
