@@ -63,3 +63,52 @@ def test_sum_of_partitions_gloo():
     for p in procs:
         p.join(60)
     assert all(ok for _, ok in res), res
+
+
+def _glue_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import numpy as np
+    import hlvae_b200  # noqa: F401
+    from hlvae_b200 import parallel
+    parallel.enable()
+    torch.manual_seed(0)
+    ids = np.repeat(np.array([7, 3, 9, 1, 4]), [3, 2, 4, 1, 3])          # 5 subjects, rows adjacent
+    N = len(ids)
+    data = torch.randn(N, 6, dtype=torch.float64)
+    net = torch.nn.Linear(6, 2).double()                                  # stands for the NN trunk
+    ref = torch.nn.Linear(6, 2).double()
+    ref.load_state_dict(net.state_dict())
+    # single-process loss: a sum over ALL rows (as nll and the row part of the KL bound are)
+    (ref(data) ** 2).sum().backward()
+    rows = parallel.shard_dataset_rows(ids, rank, world)
+    opt = torch.optim.SGD(net.parameters(), lr=0.1)
+    parallel.attach_gradient_sync(opt, net.parameters())
+    (net(data[rows]) ** 2).sum().backward()                               # this rank's partial sum
+    opt.step()                                                            # pre-hook: one all-reduce(sum) of the bucket
+    ok = all(torch.allclose(p.grad, r.grad, rtol=1e-12, atol=1e-14) for p, r in zip(net.parameters(), ref.parameters()))
+    # whole subjects, disjoint, covering
+    parts = [None] * world
+    dist.all_gather_object(parts, rows.tolist())
+    allrows = sorted(sum(parts, []))
+    ok = ok and allrows == list(range(N)) and all(len(set(ids[np.array(p_)]) & set(ids[np.array(q_)])) == 0
+                                                   for i, p_ in enumerate(parts) for q_ in parts[i + 1:])
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_training_glue_sums_partial_gradients_gloo():
+    """each rank owns whole subjects; NN-weight gradients are SUMMED through an optimiser
+    step pre-hook and then equal the single-process gradients."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_glue_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(60)
+    assert all(ok for _, ok in res), res
