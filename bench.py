@@ -575,7 +575,7 @@ def run_gpu(args):
         d["share_of_step"] = d["ms_avg"] * d["launches_per_step"] / ms_per_step
     top = max((k for k in kern if k in ALGO and ALGO[k][0] in ("hbm", "tensor")), key=lambda k: kern[k]["share_of_step"])
     traffic, traffic_src = None, None
-    tp = os.path.join(ROOT, "profiles", "traffic_r01.json")
+    tp = os.path.join(ROOT, "profiles", "traffic_r02.json")
     if os.path.exists(tp) and n_rows == SUBJ_PER_RANK * T:      # captured at this workload size only
         tj = json.load(open(tp))
         traffic, traffic_src = tj.get(top), tj.get("source")
