@@ -98,6 +98,132 @@ __device__ __forceinline__ double exp_nonpos_tab(double x, const double* __restr
     return fma(s, p, s) * __hiloint2double((k + 1023) << 20, 0);     // k >= -1022 here
 }
 
+// The same with the discrete factor of a product component folded in: the result is exp(x) when `ok` and 0
+// otherwise.  Two instructions of the stand-alone form are replaced by integer ones: the clamp x >= -708 is an
+// unsigned minimum on the high word (non-positive doubles order like their bit patterns; -708.0 = 0xC0862000_00000000;
+// the low word of a clamped argument is left as it is: at most 2^-43 below -708), and the select acts on the one
+// non-zero word of the power-of-two scale instead of on the 64-bit result.
+template <bool SELECT>
+__device__ __forceinline__ double exp_nonpos_tab_sel(double x, const double* __restrict__ tab, bool ok) {
+    const unsigned hi = min((unsigned)__double2hiint(x), 0xC0862000u);
+    x = __hiloint2double((int)hi, __double2loint(x));
+    const double MAGIC = 6755399441055744.0;                 // 1.5 * 2^52
+    const double t = fma(x, 64.0 * 1.4426950408889634074, MAGIC);
+    const int n = __double2loint(t);
+    const double nf = t - MAGIC;
+    double r = fma(nf, -6.93147180369123816490e-01 / 64.0, x);
+    r = fma(nf, -1.90821492927058770002e-10 / 64.0, r);
+    const double s = tab[n & (HLVAE_EXP_TAB - 1)];
+    int sc = ((n >> 6) + 1023) << 20;
+    if (SELECT) sc = ok ? sc : 0;
+    double p = fma(r, 1.0 / 120.0, 1.0 / 24.0);
+    p = fma(p, r, 1.0 / 6.0);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p *= r;
+    return fma(s, p, s) * __hiloint2double(sc, 0);
+}
+
+// ---- Tensor memory (TMEM, 512 columns x 128 lanes x 32 bit per SM) as thread-private scratch: a thread of warp w
+// reaches lane 32 (w % 4) + its lane id of every column through tcgen05.st / tcgen05.ld (shape 32x32b: one 32-bit
+// register per column), so a block of columns is storage that costs neither registers nor shared memory.
+__device__ __forceinline__ uint32_t smem_addr_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot) {                // one whole warp; COLS = power of two >= 32
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr_u32(slot)), "n"(COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t base) {               // one whole warp
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "n"(COLS) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_st_d2(uint32_t a, const double* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(__double2loint(v[0])),
+                 "r"(__double2hiint(v[0])), "r"(__double2loint(v[1])), "r"(__double2hiint(v[1]))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_d4(uint32_t a, const double* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(a),
+                 "r"(__double2loint(v[0])), "r"(__double2hiint(v[0])), "r"(__double2loint(v[1])),
+                 "r"(__double2hiint(v[1])), "r"(__double2loint(v[2])), "r"(__double2hiint(v[2])),
+                 "r"(__double2loint(v[3])), "r"(__double2hiint(v[3]))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_d8(uint32_t a, const double* v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
+        "%15, %16};" ::"r"(a),
+        "r"(__double2loint(v[0])), "r"(__double2hiint(v[0])), "r"(__double2loint(v[1])), "r"(__double2hiint(v[1])),
+        "r"(__double2loint(v[2])), "r"(__double2hiint(v[2])), "r"(__double2loint(v[3])), "r"(__double2hiint(v[3])),
+        "r"(__double2loint(v[4])), "r"(__double2hiint(v[4])), "r"(__double2loint(v[5])), "r"(__double2hiint(v[5])),
+        "r"(__double2loint(v[6])), "r"(__double2hiint(v[6])), "r"(__double2loint(v[7])), "r"(__double2hiint(v[7]))
+        : "memory");
+}
+// loads are issued without waiting; tmem_load_doubles waits once for all of them
+__device__ __forceinline__ void tmem_ld_r4(uint32_t a, int* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(a)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld_r8(uint32_t a, int* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(a)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld_r16(uint32_t a, int* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
+        "%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(a)
+        : "memory");
+}
+template <int NR>
+__device__ __forceinline__ void tmem_issue_loads(uint32_t a, int* r) {
+    if constexpr (NR >= 16) {
+        tmem_ld_r16(a, r);
+        tmem_issue_loads<NR - 16>(a + 16, r + 16);
+    } else if constexpr (NR >= 8) {
+        tmem_ld_r8(a, r);
+        tmem_issue_loads<NR - 8>(a + 8, r + 8);
+    } else if constexpr (NR >= 4) {
+        tmem_ld_r4(a, r);
+    }
+}
+// N doubles of one thread <-> 2 N consecutive columns (N even), split into the power-of-two vector widths
+template <int N>
+__device__ __forceinline__ void tmem_store_doubles(uint32_t a, const double* v) {
+    static_assert(N % 2 == 0 && N >= 0, "even counts");
+    if constexpr (N >= 8) {
+        tmem_st_d8(a, v);
+        tmem_store_doubles<N - 8>(a + 16, v + 8);
+    } else if constexpr (N >= 4) {
+        tmem_st_d4(a, v);
+        tmem_store_doubles<N - 4>(a + 8, v + 4);
+    } else if constexpr (N >= 2) {
+        tmem_st_d2(a, v);
+    }
+}
+template <int N>
+__device__ __forceinline__ void tmem_load_doubles(uint32_t a, double* v) {
+    static_assert(N % 2 == 0 && N >= 2, "even counts");
+    int r[2 * N];
+    tmem_issue_loads<2 * N>(a, r);
+    tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 2 * N; i++) asm volatile("" : "+r"(r[i]));      // the registers are read after the wait
+#pragma unroll
+    for (int i = 0; i < N; i++) v[i] = __hiloint2double(r[2 * i + 1], r[2 * i]);
+}
+
 // Discrete factors of one component: CatKernel (kernel_spec.py:26-32) and BinKernel
 // (kernel_spec.py:9-23); true when every factor equals 1.
 __device__ __forceinline__ bool disc_match(const hlvae_comp_t& c, const double* __restrict__ xa,

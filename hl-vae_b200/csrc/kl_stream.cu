@@ -444,8 +444,13 @@ int launch_subject(const hlvae_kspec_t* spec0, const double* os0, const double* 
 // kl_panel_k
 // =====================================================================================
 constexpr int PN_SMAX = 16;   // subjects per panel
-// NC = K0 components whose unscaled values are kept from the K0xz pass to the gradient pass (the others are
-// re-evaluated there): 3 where one CTA owns the SM, 2 in the two-CTAs-per-SM shape (shared memory)
+// The unscaled values of the K0 components are kept from the K0xz pass to the gradient pass in TENSOR MEMORY: a thread
+// only ever re-reads the values it produced itself (same inducing point, same rows), and a thread of warp w owns lane
+// 32 (w % 4) + lane id of every TMEM column, so 128 columns per group of four warps are 64 private doubles per thread
+// that cost neither registers nor shared memory (r02 kept them in 41 - 98 KB of shared memory, two components at most
+// in the two-CTAs-per-SM shape; the third was evaluated twice).
+// NC = components whose gradient sums stay in registers over the CTA's whole chunk (the others are reduced per panel).
+constexpr int PN_TMEM_COLS_PER_GROUP = 128;
 template <int MP, int RP, bool G_SMEM, int NC>
 struct PanelSmem {
     static constexpr int LD = MP + 4;          // leading dim of row panels: conflict-free DMMA fragment loads
@@ -454,7 +459,7 @@ struct PanelSmem {
                                       2 * (size_t)RP * LD /*Kb,Vb*/ + (size_t)RP * LDB /*Bp*/ +
                                       (size_t)RP * HLVAE_MAX_Q /*xs*/ + 3 * RP /*mus, rv, rho*/ +
                                       (size_t)MP * HLVAE_MAX_COMPS /*zacc*/ + 4 * HLVAE_MAX_COMPS + 8 /*hyper acc + A*/ +
-                                      8 * HLVAE_MAX_COMPS /*kps, kps1*/ + (size_t)NC * RP * MP /*vc*/ +
+                                      8 * HLVAE_MAX_COMPS /*kps, kps1*/ + 2 * (size_t)HLVAE_MAX_COMPS * RP /*xsP*/ +
                                       HLVAE_EXP_TAB /*etab*/;
     static constexpr size_t ints = 2 * RP + 3 * (PN_SMAX + 1) + 8;
     static constexpr size_t bytes = doubles * 8 + ints * 4;
@@ -484,7 +489,12 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
     constexpr int WC = (MP / 8) / 4;            // col tiles per warp for [RP x MP] outputs
     constexpr int NGRP = PN_THREADS / MP;       // row groups in the element-wise phases
     constexpr int RPT = RP / NGRP;              // rows per thread in the element-wise phases
-    static_assert(WR >= 1 && WC >= 1 && SIR >= 1 && SIC >= 1 && RPT >= 1, "tile shape");
+    constexpr int TM_COLS = (NT / 128) * PN_TMEM_COLS_PER_GROUP;                       // TMEM columns of this CTA
+    constexpr int NCT = (PN_TMEM_COLS_PER_GROUP / (2 * RPT)) < HLVAE_MAX_COMPS
+                            ? (PN_TMEM_COLS_PER_GROUP / (2 * RPT)) : HLVAE_MAX_COMPS;  // components cached in TMEM
+    static_assert(WR >= 1 && WC >= 1 && SIR >= 1 && SIC >= 1 && RPT >= 2 && RPT % 2 == 0 && RP % NGRP == 0, "tile shape");
+    static_assert(TM_COLS == 256 || TM_COLS == 512, "TMEM allocation: a power of two");
+    static_assert(RP % 2 == 0 && MP % 2 == 0, "the double2 array xsP sits at an even offset");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* Zs = reinterpret_cast<double*>(smem_raw);          // [Q][MP] transposed
     double* ws = Zs + HLVAE_MAX_Q * MP;
@@ -500,14 +510,14 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
     double* hyp = zacc + MP * HLVAE_MAX_COMPS;                 // gos0, gls0, gos1, gls1, A
     double* kps = hyp + 4 * HLVAE_MAX_COMPS + 8;               // K0 hyper-parameters by component: os, hil2, il2, il3
     double* kps1 = kps + 4 * HLVAE_MAX_COMPS;                  // same for K1
-    double* vc = kps1 + 4 * HLVAE_MAX_COMPS;                   // [PN_NCACHE][RP][MP] unscaled component values (0 = no match)
-    double* etab = vc + PN_NCACHE * RP * MP;                   // 2^(j/64) for exp_nonpos_tab
+    double2* xsP = reinterpret_cast<double2*>(kps1 + 4 * HLVAE_MAX_COMPS);   // [MAX_COMPS][RP] {x[se col], x[first discrete col]}
+    double* etab = kps1 + 4 * HLVAE_MAX_COMPS + 2 * HLVAE_MAX_COMPS * RP;     // 2^(j/64) for exp_nonpos_tab
     int* grow = reinterpret_cast<int*>(etab + HLVAE_EXP_TAB);
     int* sub_of_row = grow + RP;
     int* sub_r0 = sub_of_row + RP;                             // [PN_SMAX+1]
     int* sub_b0 = sub_r0 + PN_SMAX + 1;                        // [PN_SMAX+1] offsets of the T x T blocks
     int* sub_t0 = sub_b0 + PN_SMAX + 1;                        // [PN_SMAX+1] offsets of the lower triangles
-    int* meta = sub_t0 + PN_SMAX + 1;                          // nsub, first subject, next subject
+    int* meta = sub_t0 + PN_SMAX + 1;                          // nsub, first subject, next subject, TMEM base
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wi = warp >> 2, wj = warp & 3;
@@ -524,6 +534,7 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
     }
     for (int m = tid; m < MP; m += PN_THREADS) ws[m] = (m < M) ? w[(int64_t)l * M + m] : 0.0;
     exp2_table_fill(etab, tid, PN_THREADS);
+    if (warp == 0) tmem_alloc<TM_COLS>(reinterpret_cast<uint32_t*>(meta + 3));
     if (G_SMEM) {
         for (int e = tid; e < MP * LD; e += PN_THREADS) {
             int i = e / LD, j = e % LD;
@@ -573,7 +584,12 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
     for (int r = 0; r < PN_NCACHE; r++) hg0[r] = hg1[r] = hg2[r] = 0.0;
 
     if (tid == 0) meta[2] = s_begin;
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = (uint32_t)meta[3];
+    // this thread's private columns: lane quadrant of its warp, column block of its group of four warps
+    const uint32_t tm_mine = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * PN_TMEM_COLS_PER_GROUP);
     const double wm = ws[em];
     const int chunk_row_end = subj_ptr[s_end];
     const int chunk_tt_end = tt_ptr[s_end];
@@ -638,6 +654,13 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
             sub_of_row[tid] = -1;
             for (int q = 0; q < Q; q++) xs[tid * Q + q] = 0.0;
         }
+        if (tid < RP) {   // per component: the row's squared-exponential covariate next to its first discrete one
+            for (int r = 0; r < sp0.ncomp; r++) {
+                const int sc = sp0.comp[r].se_col, dc = sp0.comp[r].disc_col[0];
+                xsP[r * RP + tid] = make_double2(sc >= 0 ? xs[tid * Q + sc] : 0.0,
+                                                 sp0.comp[r].ndisc > 0 ? xs[tid * Q + dc] : 0.0);
+            }
+        }
         {   // scatter the subjects' B^-1 blocks (contiguous in global memory) onto the block diagonal
             const double* bsrc = binv + (int64_t)l * tt_total + tt_ptr[s_first];
             const int nb = sub_b0[nsub];
@@ -653,78 +676,73 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
         __syncthreads();
 
         // ---- P1: K0xz rows (elbo_functions.py:147 / :222), zero padded to [R8][MP].
-        // Thread = (inducing point em, row group eg); components outermost so that the spec and the
-        // inducing point's covariates stay in registers and row covariates are warp broadcasts.
+        // Thread = (inducing point em, row group eg); components outermost so that the spec and the inducing point's
+        // covariates stay in registers and row covariates are warp broadcasts.  Straight-line bodies: the RPT rows of
+        // a thread are independent, so their exponentials interleave and hide each other's latency; rows >= R read
+        // zero-filled covariates and inducing points >= M zeros (their values are finite and never used).  The shape
+        // of a component is the same for every thread and selects one of four bodies without divergence: the three
+        // forms kernel_gen.py:199-310 builds - SE, SE x categorical, categorical - read one packed {SE covariate,
+        // discrete covariate} pair per row (one LDS.128) and fold the discrete factor into the exponent insert of the
+        // exponential; everything else takes the general body.  The unscaled values go to this thread's TMEM columns.
         {
             double kacc[RPT];
 #pragma unroll
             for (int k = 0; k < RPT; k++) kacc[k] = 0.0;
-            if (em < M) {
-                for (int r = 0; r < sp0.ncomp; r++) {
-                    CompRegs c;
-                    c.load(sp0, r);
-                    const double zse = (c.se_col >= 0) ? Zs[c.se_col * MP + em] : 0.0;
-                    double zd[HLVAE_MAX_DISC];
-#pragma unroll
-                    for (int f = 0; f < HLVAE_MAX_DISC; f++) zd[f] = (f < c.ndisc) ? Zs[c.disc_col[f] * MP + em] : 0.0;
-                    const double hil2 = kps[HLVAE_MAX_COMPS + r], osr = kps[r];
-                    // Straight-line bodies (no data-dependent branches): the RPT rows of a thread are independent,
-                    // so their exponentials interleave and hide each other's latency.  Rows >= R read the
-                    // zero-filled tail of xs; their values are never used.  The number of discrete factors is the
-                    // same for every thread, so it selects one of three bodies without divergence: the components
-                    // kernel_gen.py builds have none or one, and skip the loads and compares of the general body.
-                    const int nd = c.ndisc;
-                    const bool cat0 = c.disc_kind[0] == HLVAE_KIND_CAT, cat1 = c.disc_kind[1] == HLVAE_KIND_CAT,
-                               cat2 = c.disc_kind[2] == HLVAE_KIND_CAT;
-                    const int dc0 = nd > 0 ? c.disc_col[0] : 0, dc1 = nd > 1 ? c.disc_col[1] : 0,
-                              dc2 = nd > 2 ? c.disc_col[2] : 0;
-                    const int sc = c.se_col >= 0 ? c.se_col : 0;
-                    const bool has_se = c.se_col >= 0;
-                    double vv[RPT];
-                    if (nd == 0) {
-#pragma unroll
-                        for (int k = 0; k < RPT; k++) {
-                            const double d = xs[(eg + k * NGRP) * Q + sc] - zse;
-                            vv[k] = has_se ? exp_nonpos_tab(-(d * d) * hil2, etab) : 1.0;
-                        }
-                    } else if (nd == 1) {
-                        const double z0 = zd[0];
-#pragma unroll
-                        for (int k = 0; k < RPT; k++) {
-                            const double* xr = xs + (eg + k * NGRP) * Q;
-                            const double a0 = xr[dc0];
-                            const bool ok = cat0 ? (a0 == z0) : (a0 + z0 == 2.0);
-                            const double d = xr[sc] - zse;
-                            const double e_ = has_se ? exp_nonpos_tab(-(d * d) * hil2, etab) : 1.0;
-                            vv[k] = ok ? e_ : 0.0;
-                        }
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < RPT; k++) {
-                            const double* xr = xs + (eg + k * NGRP) * Q;
-                            const double a0 = xr[dc0], a1 = xr[dc1], a2 = xr[dc2];
-                            bool ok = true;
-                            ok = ok && (nd < 1 || (cat0 ? (a0 == zd[0]) : (a0 + zd[0] == 2.0)));
-                            ok = ok && (nd < 2 || (cat1 ? (a1 == zd[1]) : (a1 + zd[1] == 2.0)));
-                            ok = ok && (nd < 3 || (cat2 ? (a2 == zd[2]) : (a2 + zd[2] == 2.0)));
-                            const double d = xr[sc] - zse;
-                            const double e_ = has_se ? exp_nonpos_tab(-(d * d) * hil2, etab) : 1.0;
-                            vv[k] = ok ? e_ : 0.0;
-                        }
-                    }
+            for (int r = 0; r < sp0.ncomp; r++) {
+                CompRegs c;
+                c.load(sp0, r);
+                const int nd = c.ndisc;
+                const bool has_se = c.se_col >= 0;
+                const bool cat0 = c.disc_kind[0] == HLVAE_KIND_CAT;
+                const double zse = has_se ? Zs[c.se_col * MP + em] : 0.0;
+                const double z0 = nd > 0 ? Zs[c.disc_col[0] * MP + em] : 0.0;
+                const double nh = -kps[HLVAE_MAX_COMPS + r], osr = kps[r];
+                const double2* xp = xsP + r * RP + eg;
+                double vv[RPT];
+                if (nd == 0 && has_se) {
 #pragma unroll
                     for (int k = 0; k < RPT; k++) {
-                        const int row = eg + k * NGRP;
-                        kacc[k] = fma(osr, vv[k], kacc[k]);
-                        if (r < PN_NCACHE) vc[(r * RP + row) * MP + em] = vv[k];
+                        const double d = xp[k * NGRP].x - zse;
+                        vv[k] = exp_nonpos_tab_sel<false>((d * nh) * d, etab, true);
+                    }
+                } else if (nd == 1 && cat0 && has_se) {
+#pragma unroll
+                    for (int k = 0; k < RPT; k++) {
+                        const double2 xv = xp[k * NGRP];
+                        const double d = xv.x - zse;
+                        vv[k] = exp_nonpos_tab_sel<true>((d * nh) * d, etab, xv.y == z0);
+                    }
+                } else if (nd == 1 && cat0) {
+#pragma unroll
+                    for (int k = 0; k < RPT; k++) vv[k] = (xp[k * NGRP].y == z0) ? 1.0 : 0.0;
+                } else {
+                    const bool cat1 = c.disc_kind[1] == HLVAE_KIND_CAT, cat2 = c.disc_kind[2] == HLVAE_KIND_CAT;
+                    const int dc0 = nd > 0 ? c.disc_col[0] : 0, dc1 = nd > 1 ? c.disc_col[1] : 0,
+                              dc2 = nd > 2 ? c.disc_col[2] : 0;
+                    const double z1 = nd > 1 ? Zs[dc1 * MP + em] : 0.0, z2 = nd > 2 ? Zs[dc2 * MP + em] : 0.0;
+#pragma unroll
+                    for (int k = 0; k < RPT; k++) {
+                        const double* xr = xs + (eg + k * NGRP) * Q;
+                        const double a0 = xr[dc0], a1 = xr[dc1], a2 = xr[dc2];
+                        bool ok = true;
+                        ok = ok && (nd < 1 || (cat0 ? (a0 == z0) : (a0 + z0 == 2.0)));
+                        ok = ok && (nd < 2 || (cat1 ? (a1 == z1) : (a1 + z1 == 2.0)));
+                        ok = ok && (nd < 3 || (cat2 ? (a2 == z2) : (a2 + z2 == 2.0)));
+                        const double d = xp[k * NGRP].x - zse;
+                        const double e_ = has_se ? exp_nonpos_tab_sel<false>((d * nh) * d, etab, true) : 1.0;
+                        vv[k] = ok ? e_ : 0.0;
                     }
                 }
+#pragma unroll
+                for (int k = 0; k < RPT; k++) kacc[k] = fma(osr, vv[k], kacc[k]);
+                if (r < NCT) tmem_store_doubles<RPT>(tm_mine + r * 2 * RPT, vv);
             }
 #pragma unroll
             for (int k = 0; k < RPT; k++) {
                 const int row = eg + k * NGRP;
-                if (row < R8) Kb[row * LD + em] = (row < R) ? kacc[k] : 0.0;
+                if (row < R8) Kb[row * LD + em] = (row < R && em < M) ? kacc[k] : 0.0;
             }
+            tmem_wait_st();
         }
         if (pf_g >= 0) {
             prefetch_l1(x + (int64_t)pf_g * ldx);
@@ -916,30 +934,28 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
                 // sums of g v, g v d, g v d^2 over this thread's rows (d = x - z); outputscale and lengthscale
                 // factors are applied once at the end
                 double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-                if (em < M) {
-                    if (r < PN_NCACHE) {
-                        const double* vr = vc + (size_t)r * RP * MP + em;
-                        if (c.se_col >= 0) {
+                if (r < NCT) {
+                    // values of this component back from the thread's TMEM columns; rows >= R and inducing points
+                    // >= M carry gk = 0
+                    double vv[RPT];
+                    tmem_load_doubles<RPT>(tm_mine + r * 2 * RPT, vv);
+                    if (c.se_col >= 0) {
+                        const double2* xp = xsP + r * RP + eg;
 #pragma unroll
-                            for (int k = 0; k < RPT; k++) {
-                                const int row = eg + k * NGRP;
-                                if (row < R) {
-                                    const double gkv = gk[k] * vr[row * MP];
-                                    const double d = xs[row * Q + c.se_col] - zse;
-                                    const double t = gkv * d;
-                                    s0 += gkv;
-                                    s1 += t;
-                                    s2 = fma(t, d, s2);
-                                }
-                            }
-                        } else {
-#pragma unroll
-                            for (int k = 0; k < RPT; k++) {
-                                const int row = eg + k * NGRP;
-                                if (row < R) s0 = fma(gk[k], vr[row * MP], s0);
-                            }
+                        for (int k = 0; k < RPT; k++) {
+                            const double gkv = gk[k] * vv[k];
+                            const double d = xp[k * NGRP].x - zse;
+                            const double t = gkv * d;
+                            s0 += gkv;
+                            s1 += t;
+                            s2 = fma(t, d, s2);
                         }
                     } else {
+#pragma unroll
+                        for (int k = 0; k < RPT; k++) s0 = fma(gk[k], vv[k], s0);
+                    }
+                } else {
+                    if (em < M) {
                         double zd[HLVAE_MAX_DISC];
 #pragma unroll
                         for (int f = 0; f < HLVAE_MAX_DISC; f++) zd[f] = (f < c.ndisc) ? Zs[c.disc_col[f] * MP + em] : 0.0;
@@ -1107,6 +1123,9 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
             }
         }
     }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<TM_COLS>(tmem_base);
 }
 
 template <int MP, int RP, bool G_SMEM, int NT, int NC, typename TS>
@@ -1148,7 +1167,7 @@ int dispatch_panel(int M, const hlvae_kspec_t* spec0, const double* os0, const d
     // panel), 48-row panels (+10 %), 1024 threads at 64 registers (+18 %: spills, per-thread set-up doubled).
     if (M <= 32) { HLVAE_PANEL(32, 64, true, 512, 3); }
     if (M <= 64) {
-        if (row_panel == 40) { HLVAE_PANEL(64, 40, false, 256, 2); }
+        if (row_panel == 40) { HLVAE_PANEL(64, 40, false, 256, 3); }
         HLVAE_PANEL(64, 64, false, 512, 3);
     }
     if (M <= 128) { HLVAE_PANEL(128, 32, false, 512, 3); }

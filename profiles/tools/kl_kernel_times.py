@@ -9,7 +9,7 @@ config.check_errors = False
 config.overlap = False
 dev = torch.device("cuda:0")
 L, T = 32, 20
-for M, n_subj in ((120, 20), (120, 800), (64, 20)):
+for M, n_subj in ((64, 800), (120, 800), (32, 800), (64, 20)):
     rng = np.random.default_rng(0); gen = torch.Generator().manual_seed(0)
     x, lens = synth.covariates(n_subj, T, rng)
     pool, _ = synth.covariates(400, T, np.random.default_rng(1))
