@@ -451,6 +451,7 @@ constexpr int PN_SMAX = 16;   // subjects per panel
 // in the two-CTAs-per-SM shape; the third was evaluated twice).
 // NC = components whose gradient sums stay in registers over the CTA's whole chunk (the others are reduced per panel).
 constexpr int PN_TMEM_COLS_PER_GROUP = 128;
+constexpr int PN_CHUNK_CSR = 256;   // subjects of a chunk whose CSR offsets are copied to shared memory
 template <int MP, int RP, bool G_SMEM, int NC>
 struct PanelSmem {
     static constexpr int LD = MP + 4;          // leading dim of row panels: conflict-free DMMA fragment loads
@@ -459,9 +460,10 @@ struct PanelSmem {
                                       2 * (size_t)RP * LD /*Kb,Vb*/ + (size_t)RP * LDB /*Bp*/ +
                                       (size_t)RP * HLVAE_MAX_Q /*xs*/ + 3 * RP /*mus, rv, rho*/ +
                                       (size_t)MP * HLVAE_MAX_COMPS /*zacc*/ + 4 * HLVAE_MAX_COMPS + 8 /*hyper acc + A*/ +
-                                      8 * HLVAE_MAX_COMPS /*kps, kps1*/ + 2 * (size_t)HLVAE_MAX_COMPS * RP /*xsP*/ +
+                                      8 * HLVAE_MAX_COMPS /*kps, kps1*/ + 4 * (size_t)HLVAE_MAX_COMPS * RP /*xsP, xsP1*/ +
                                       HLVAE_EXP_TAB /*etab*/;
-    static constexpr size_t ints = 2 * RP + 3 * (PN_SMAX + 1) + 8;
+    static constexpr int n_lower_tiles = (RP / 8) * (RP / 8 + 1) / 2;
+    static constexpr size_t ints = 2 * RP + 3 * (PN_SMAX + 1) + 8 + n_lower_tiles + 2 * (PN_CHUNK_CSR + 1);
     static constexpr size_t bytes = doubles * 8 + ints * 4;
 };
 
@@ -493,6 +495,7 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
     constexpr int NCT = (PN_TMEM_COLS_PER_GROUP / (2 * RPT)) < HLVAE_MAX_COMPS
                             ? (PN_TMEM_COLS_PER_GROUP / (2 * RPT)) : HLVAE_MAX_COMPS;  // components cached in TMEM
     static_assert(WR >= 1 && WC >= 1 && SIR >= 1 && SIC >= 1 && RPT >= 2 && RPT % 2 == 0 && RP % NGRP == 0, "tile shape");
+    static_assert(NT / 32 >= RP / 8, "one warp per row tile in the r = K0xz w - mu product");
     static_assert(TM_COLS == 256 || TM_COLS == 512, "TMEM allocation: a power of two");
     static_assert(RP % 2 == 0 && MP % 2 == 0, "the double2 array xsP sits at an even offset");
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -511,13 +514,17 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
     double* kps = hyp + 4 * HLVAE_MAX_COMPS + 8;               // K0 hyper-parameters by component: os, hil2, il2, il3
     double* kps1 = kps + 4 * HLVAE_MAX_COMPS;                  // same for K1
     double2* xsP = reinterpret_cast<double2*>(kps1 + 4 * HLVAE_MAX_COMPS);   // [MAX_COMPS][RP] {x[se col], x[first discrete col]}
-    double* etab = kps1 + 4 * HLVAE_MAX_COMPS + 2 * HLVAE_MAX_COMPS * RP;     // 2^(j/64) for exp_nonpos_tab
+    double2* xsP1 = xsP + HLVAE_MAX_COMPS * RP;                               // the same for the components of K1
+    double* etab = kps1 + 4 * HLVAE_MAX_COMPS + 4 * HLVAE_MAX_COMPS * RP;     // 2^(j/64) for exp_nonpos_tab
     int* grow = reinterpret_cast<int*>(etab + HLVAE_EXP_TAB);
     int* sub_of_row = grow + RP;
     int* sub_r0 = sub_of_row + RP;                             // [PN_SMAX+1]
     int* sub_b0 = sub_r0 + PN_SMAX + 1;                        // [PN_SMAX+1] offsets of the T x T blocks
     int* sub_t0 = sub_b0 + PN_SMAX + 1;                        // [PN_SMAX+1] offsets of the lower triangles
     int* meta = sub_t0 + PN_SMAX + 1;                          // nsub, first subject, next subject, TMEM base
+    int* tl_tab = meta + 8;                                    // (row tile << 8 | column tile) of the lower triangle
+    int* csr_r = tl_tab + SM::n_lower_tiles;                   // subj_ptr[s_begin ..] of this chunk
+    int* csr_t = csr_r + PN_CHUNK_CSR + 1;                     // tt_ptr[s_begin ..]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wi = warp >> 2, wj = warp & 3;
@@ -535,6 +542,12 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
     for (int m = tid; m < MP; m += PN_THREADS) ws[m] = (m < M) ? w[(int64_t)l * M + m] : 0.0;
     exp2_table_fill(etab, tid, PN_THREADS);
     if (warp == 0) tmem_alloc<TM_COLS>(reinterpret_cast<uint32_t*>(meta + 3));
+    for (int i = tid; i < RP / 8; i += PN_THREADS)
+        for (int j = 0; j <= i; j++) tl_tab[i * (i + 1) / 2 + j] = (i << 8) | j;
+    for (int i = tid; i <= PN_CHUNK_CSR && s_begin + i <= s_end; i += PN_THREADS) {
+        csr_r[i] = subj_ptr[s_begin + i];
+        csr_t[i] = tt_ptr[s_begin + i];
+    }
     if (G_SMEM) {
         for (int e = tid; e < MP * LD; e += PN_THREADS) {
             int i = e / LD, j = e % LD;
@@ -593,30 +606,33 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
     const double wm = ws[em];
     const int chunk_row_end = subj_ptr[s_end];
     const int chunk_tt_end = tt_ptr[s_end];
+    // CSR offsets of subject s (s_begin <= s <= s_end): from the shared-memory copy where it reaches
+    auto rows_at = [&](int s) { return s - s_begin <= PN_CHUNK_CSR ? csr_r[s - s_begin] : subj_ptr[s]; };
+    auto tt_at = [&](int s) { return s - s_begin <= PN_CHUNK_CSR ? csr_t[s - s_begin] : tt_ptr[s]; };
 
     while (true) {
         // ---- P0: pack whole subjects into a panel of at most RP rows
         if (tid == 0) {
-            int s = meta[2], ns = 0, rows = 0, bsz = 0, tsz = 0;
+            int s = meta[2], ns = 0, rows = 0, bsz = 0;
             meta[1] = s;
             sub_r0[0] = 0;
             sub_b0[0] = 0;
-            sub_t0[0] = 0;
+            int r_lo = rows_at(s);
             while (s < s_end && ns < PN_SMAX) {
-                int T = subj_ptr[s + 1] - subj_ptr[s];
+                const int r_hi = rows_at(s + 1);
+                const int T = r_hi - r_lo;
                 if (T > HLVAE_TMAX) {   // reported by kl_subject_k as well; skip here
-                    if (ns == 0) { s++; meta[1] = s; continue; }
+                    if (ns == 0) { s++; r_lo = r_hi; meta[1] = s; continue; }
                     break;
                 }
                 if (rows + T > RP) break;
                 rows += T;
                 bsz += T * T;
-                tsz += T * (T + 1) / 2;
                 ns++;
                 s++;
+                r_lo = r_hi;
                 sub_r0[ns] = rows;
                 sub_b0[ns] = bsz;
-                sub_t0[ns] = tsz;
             }
             meta[0] = ns;
             meta[2] = s;
@@ -629,16 +645,16 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
         const int s_first = meta[1];
         const int R = sub_r0[nsub];
         const int R8 = (R + 7) & ~7;
-        const int pr0 = subj_ptr[s_first];
+        const int pr0 = rows_at(s_first);
         // look-ahead: the rows and B^-1 blocks the NEXT panel will gather (about the same amount as this one) are
         // pulled into L1 while this panel computes, so that the set-up above stops waiting on L2 / HBM
         int pf_g = -1, pf_b = -1;
         {
             const int s_next = meta[2];
             if (s_next < s_end) {
-                const int prn = subj_ptr[s_next];
+                const int prn = rows_at(s_next);
                 if (tid < RP && prn + tid < chunk_row_end) pf_g = row_idx[prn + tid];
-                const int b0 = tt_ptr[s_next] + tid * 16;          // one 128-byte line per thread
+                const int b0 = tt_at(s_next) + tid * 16;           // one 128-byte line per thread
                 if (tid < RP * HLVAE_TMAX / 16 && b0 < chunk_tt_end) pf_b = b0;
             }
         }
@@ -660,9 +676,14 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
                 xsP[r * RP + tid] = make_double2(sc >= 0 ? xs[tid * Q + sc] : 0.0,
                                                  sp0.comp[r].ndisc > 0 ? xs[tid * Q + dc] : 0.0);
             }
+            for (int r = 0; r < sp1.ncomp; r++) {
+                const int sc = sp1.comp[r].se_col, dc = sp1.comp[r].disc_col[0];
+                xsP1[r * RP + tid] = make_double2(sc >= 0 ? xs[tid * Q + sc] : 0.0,
+                                                  sp1.comp[r].ndisc > 0 ? xs[tid * Q + dc] : 0.0);
+            }
         }
         {   // scatter the subjects' B^-1 blocks (contiguous in global memory) onto the block diagonal
-            const double* bsrc = binv + (int64_t)l * tt_total + tt_ptr[s_first];
+            const double* bsrc = binv + (int64_t)l * tt_total + tt_at(s_first);
             const int nb = sub_b0[nsub];
             int k = 0;
             for (int e = tid; e < nb; e += PN_THREADS) {
@@ -782,11 +803,18 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
                 }
             }
         }
-        for (int r = warp; r < R; r += PN_THREADS / 32) {
-            double a = 0.0;
-            for (int m = lane; m < MP; m += 32) a = fma(Kb[r * LD + m], ws[m], a);
-            a = warp_sum(a);
-            if (lane == 0) rv[r] = a - mus[r];
+        // r = K0xz w - mu (:166 / :230) as one more column tile of the tensor pipe: B fragment = w in column 0
+        if (warp * 8 < R) {
+            const int ar = lane >> 2, ac = lane & 3;
+            double c0 = 0.0, c1 = 0.0;
+#pragma unroll 4
+            for (int k0 = 0; k0 < MP; k0 += 4) {
+                const double a = Kb[(warp * 8 + ar) * LD + k0 + ac];
+                const double b = (ar == 0) ? ws[k0 + ac] : 0.0;
+                dmma884(c0, c1, a, b);
+            }
+            const int row = warp * 8 + ar;
+            if (ac == 0 && row < R) rv[row] = c0 - mus[row];
         }
         __syncthreads();
 
@@ -891,29 +919,87 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
                 if (lane == 0) qdiag[(int64_t)grow[r] * L + l] = (TS)a;
             }
         }
-        // ---- P5a: dJ/dB_s (K0xz part) = -1/2 (rho rho^T + W V^T), symmetric: only the 8x8 tiles on or below
-        // the diagonal that meet the block diagonal, on the FP64 tensor pipe, written over the dense panel Bp
+        // ---- P5a: dJ/dB_s (K0xz part) = -1/2 (rho rho^T + W V^T), symmetric: only the 8x8 tiles on or below the
+        // diagonal that meet the block diagonal, on the FP64 tensor pipe, and contracted with dB_s/d(theta1) straight
+        // from the accumulator fragments (off-diagonal entries count twice) - the tiles are never stored
         {
+            constexpr int NWARP = PN_THREADS / 32;
+            constexpr int NTL = (SM::n_lower_tiles + NWARP - 1) / NWARP;       // tiles per warp
             const int nrt = R8 / 8;
+            const int nlt = nrt * (nrt + 1) / 2;
             const int ar = lane >> 2, ac = lane & 3;
-            for (int tp = warp; tp < nrt * nrt; tp += PN_THREADS / 32) {
-                const int rt = tp / nrt, ct = tp - rt * nrt;
-                const int rl = min(rt * 8 + 7, R - 1), cl = min(ct * 8 + 7, R - 1);
-                const int s_r0 = sub_of_row[rt * 8], s_r1 = sub_of_row[rl];
-                const int s_c0 = sub_of_row[ct * 8], s_c1 = sub_of_row[cl];
-                if (ct <= rt && s_r0 <= s_c1 && s_c0 <= s_r1) {
-                    double c0 = 0.0, c1 = 0.0;
-                    for (int m0 = 0; m0 < MP; m0 += 4) {
-                        const double a = Kb[(rt * 8 + ar) * LD + m0 + ac];
-                        const double b = Vb[(ct * 8 + ar) * LD + m0 + ac];
-                        dmma884(c0, c1, a, b);
+            double gq[NTL][2];
+            int gi[NTL], gj[NTL];
+            bool live[NTL];
+#pragma unroll
+            for (int t = 0; t < NTL; t++) {
+                gq[t][0] = gq[t][1] = 0.0;
+                gi[t] = gj[t] = 0;
+                live[t] = false;
+                const int tp = warp + t * NWARP;
+                if (tp < nlt) {
+                    const int rc = tl_tab[tp], rt = rc >> 8, ct = rc & 255;
+                    if (sub_of_row[min(ct * 8 + 7, R - 1)] >= sub_of_row[rt * 8]) {
+                        double c0 = 0.0, c1 = 0.0;
+#pragma unroll 4
+                        for (int m0 = 0; m0 < MP; m0 += 4) {
+                            const double a = Kb[(rt * 8 + ar) * LD + m0 + ac];
+                            const double b = Vb[(ct * 8 + ar) * LD + m0 + ac];
+                            dmma884(c0, c1, a, b);
+                        }
+                        const int i = rt * 8 + ar, j = ct * 8 + 2 * ac;
+                        if (i < R) {
+                            const int si = sub_of_row[i];
+                            const double ri = rho[i];
+                            if (j <= i && sub_of_row[j] == si) gq[t][0] = (i == j ? -0.5 : -1.0) * (c0 + ri * rho[j]);
+                            if (j + 1 <= i && sub_of_row[j + 1] == si)
+                                gq[t][1] = (i == j + 1 ? -0.5 : -1.0) * (c1 + ri * rho[j + 1]);
+                        }
+                        gi[t] = min(i, RP - 1);
+                        gj[t] = min(j, RP - 2);
+                        live[t] = true;
                     }
-                    const int i = rt * 8 + ar, j = ct * 8 + 2 * ac;
-                    if (i < R) {
-                        const double ri = rho[i];
-                        if (j < R) Bp[i * LDB + j] = -0.5 * (c0 + ri * rho[j]);
-                        if (j + 1 < R) Bp[i * LDB + j + 1] = -0.5 * (c1 + ri * rho[j + 1]);
+                }
+            }
+            for (int r = 0; r < sp1.ncomp; r++) {
+                CompRegs c;
+                c.load(sp1, r);
+                const double osr = kps1[r], hil2 = kps1[HLVAE_MAX_COMPS + r], il3 = kps1[3 * HLVAE_MAX_COMPS + r];
+                const double nh = -hil2;
+                const bool has_se = c.se_col >= 0, cat0 = c.disc_kind[0] == HLVAE_KIND_CAT;
+                const double2* xp = xsP1 + r * RP;
+                double gos = 0.0, gls = 0.0;
+#pragma unroll
+                for (int t = 0; t < NTL; t++) {
+                    if (live[t]) {
+                        if (c.ndisc == 1 && cat0) {                 // categorical (x SE): the forms kernel_gen.py builds
+                            const double2 xi = xp[gi[t]];
+#pragma unroll
+                            for (int u = 0; u < 2; u++) {
+                                const double2 xj = xp[gj[t] + u];
+                                const double d = xi.x - xj.x;
+                                const double v = has_se ? exp_nonpos_tab_sel<true>((d * nh) * d, etab, xi.y == xj.y)
+                                                        : ((xi.y == xj.y) ? 1.0 : 0.0);
+                                const double gv = gq[t][u] * v;
+                                gos += gv;
+                                gls = fma(gv * d, d, gls);
+                            }
+                        } else {
+#pragma unroll
+                            for (int u = 0; u < 2; u++) {
+                                double d;
+                                const double gv = gq[t][u] * c.value(xs + gi[t] * Q, xs + (gj[t] + u) * Q, hil2, d, etab);
+                                gos += gv;
+                                gls = fma(gv * d, d, gls);
+                            }
+                        }
                     }
+                }
+                gos = warp_sum(gos);
+                gls = warp_sum(gls) * osr * il3;
+                if (lane == 0) {
+                    atomicAdd(&hyp[2 * HLVAE_MAX_COMPS + r], gos);
+                    atomicAdd(&hyp[3 * HLVAE_MAX_COMPS + r], gls);
                 }
             }
         }
@@ -999,54 +1085,6 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
                         atomicAdd(&hyp[HLVAE_MAX_COMPS + r], gls);
                     }
                     if (c.se_col >= 0 && s1 != 0.0) atomicAdd(&zacc[em * HLVAE_MAX_COMPS + r], s1 * osr * il2);
-                }
-            }
-        }
-        __syncthreads();
-
-        // ---- P6: contract dJ/dB_s (symmetric: lower triangle, off-diagonal entries twice) with dB_s/d(theta1)
-        {
-            const int nt = sub_t0[nsub];
-            for (int r = 0; r < sp1.ncomp; r++) {
-                CompRegs c;
-                c.load(sp1, r);
-                const double osr = kps1[r], hil2 = kps1[HLVAE_MAX_COMPS + r], il3 = kps1[3 * HLVAE_MAX_COMPS + r];
-                double gos = 0.0, gls = 0.0;
-                int k = 0;
-                for (int e = tid; e < nt; e += PN_THREADS) {
-                    while (e >= sub_t0[k + 1]) k++;
-                    const int rs = sub_r0[k];
-                    const int le = e - sub_t0[k];
-                    int i = (int)((sqrtf(8.0f * (float)le + 1.0f) - 1.0f) * 0.5f);
-                    while (i * (i + 1) / 2 > le) i--;
-                    while ((i + 1) * (i + 2) / 2 <= le) i++;
-                    const int j = le - i * (i + 1) / 2;
-                    const double* xi = xs + (rs + i) * Q;
-                    const double* xj = xs + (rs + j) * Q;
-                    bool ok = true;
-#pragma unroll
-                    for (int f = 0; f < HLVAE_MAX_DISC; f++)
-                        if (f < c.ndisc) {
-                            const double a = xi[c.disc_col[f]], b2 = xj[c.disc_col[f]];
-                            ok = ok && ((c.disc_kind[f] == HLVAE_KIND_CAT) ? (a - b2 == 0.0) : (a + b2 == 2.0));
-                        }
-                    if (ok) {
-                        const double g = Bp[(rs + i) * LDB + rs + j] * (i == j ? 1.0 : 2.0);
-                        double v = 1.0, d = 0.0;
-                        if (c.se_col >= 0) {
-                            d = xi[c.se_col] - xj[c.se_col];
-                            v = exp_nonpos_tab(-(d * d) * hil2, etab);
-                        }
-                        const double gv = g * v;
-                        gos += gv;
-                        gls = fma(gv * d, d, gls);
-                    }
-                }
-                gos = warp_sum(gos);
-                gls = warp_sum(gls) * osr * il3;
-                if (lane == 0) {
-                    atomicAdd(&hyp[2 * HLVAE_MAX_COMPS + r], gos);
-                    atomicAdd(&hyp[3 * HLVAE_MAX_COMPS + r], gls);
                 }
             }
         }
