@@ -304,6 +304,17 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                  : "d"(a), "d"(b));
 }
 
+// Asynchronous global -> shared copies of one 4- / 8- / 16-byte element each (LDGSTS): gathers and scatters whose
+// latency is taken off the issuing thread; completed by cp_async_wait_all of the same thread, then a barrier.
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void* smem_dst, const void* gsrc) {
+    static_assert(BYTES == 4 || BYTES == 8 || BYTES == 16, "cp.async element size");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_addr_u32(smem_dst)), "l"(gsrc), "n"(BYTES)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 __device__ __forceinline__ void prefetch_l1(const void* p) {
     asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
 }

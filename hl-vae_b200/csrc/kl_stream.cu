@@ -458,12 +458,11 @@ struct PanelSmem {
     static constexpr int LDB = RP + 4;         // leading dim of the dense block-diagonal B^-1 panel
     static constexpr size_t doubles = (size_t)HLVAE_MAX_Q * MP /*Zs*/ + MP /*ws*/ + (G_SMEM ? (size_t)MP * LD : 0) +
                                       2 * (size_t)RP * LD /*Kb,Vb*/ + (size_t)RP * LDB /*Bp*/ +
-                                      (size_t)RP * HLVAE_MAX_Q /*xs*/ + 3 * RP /*mus, rv, rho*/ +
+                                      2 * (size_t)RP * HLVAE_MAX_Q /*xs*/ + 5 * RP /*mus, mraw, rv, rho*/ +
                                       (size_t)MP * HLVAE_MAX_COMPS /*zacc*/ + 4 * HLVAE_MAX_COMPS + 8 /*hyper acc + A*/ +
-                                      8 * HLVAE_MAX_COMPS /*kps, kps1*/ + 4 * (size_t)HLVAE_MAX_COMPS * RP /*xsP, xsP1*/ +
-                                      HLVAE_EXP_TAB /*etab*/;
+                                      8 * HLVAE_MAX_COMPS /*kps, kps1*/ + HLVAE_EXP_TAB /*etab*/;
     static constexpr int n_lower_tiles = (RP / 8) * (RP / 8 + 1) / 2;
-    static constexpr size_t ints = 2 * RP + 3 * (PN_SMAX + 1) + 8 + n_lower_tiles + 2 * (PN_CHUNK_CSR + 1);
+    static constexpr size_t ints = 4 * RP + 4 * (PN_SMAX + 1) + 8 + n_lower_tiles + 2 * (PN_CHUNK_CSR + 1);
     static constexpr size_t bytes = doubles * 8 + ints * 4;
 };
 
@@ -497,7 +496,6 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
     static_assert(WR >= 1 && WC >= 1 && SIR >= 1 && SIC >= 1 && RPT >= 2 && RPT % 2 == 0 && RP % NGRP == 0, "tile shape");
     static_assert(NT / 32 >= RP / 8, "one warp per row tile in the r = K0xz w - mu product");
     static_assert(TM_COLS == 256 || TM_COLS == 512, "TMEM allocation: a power of two");
-    static_assert(RP % 2 == 0 && MP % 2 == 0, "the double2 array xsP sits at an even offset");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* Zs = reinterpret_cast<double*>(smem_raw);          // [Q][MP] transposed
     double* ws = Zs + HLVAE_MAX_Q * MP;
@@ -505,23 +503,22 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
     double* Kb = Gs + (G_SMEM ? MP * LD : 0);                  // [RP][LD]  K0xz, later W = V G
     double* Vb = Kb + RP * LD;                                 // [RP][LD]  B^-1 K0xz
     double* Bp = Vb + RP * LD;                                 // [RP][LDB] dense block-diagonal B^-1, later dJ/dB
-    double* xs = Bp + RP * LDB;                                // [RP][Q]
-    double* mus = xs + RP * HLVAE_MAX_Q;
-    double* rv = mus + RP;
+    double* xs = Bp + RP * LDB;                                // [2][RP][8] covariate rows of this / the next panel
+    double* mus = xs + 2 * RP * HLVAE_MAX_Q;
+    TS* mraw = reinterpret_cast<TS*>(mus + RP);                // [2][RP] mu as stored, this / the next panel
+    double* rv = mus + 3 * RP;
     double* rho = rv + RP;
     double* zacc = rho + RP;                                   // [MP][MAX_COMPS]
     double* hyp = zacc + MP * HLVAE_MAX_COMPS;                 // gos0, gls0, gos1, gls1, A
     double* kps = hyp + 4 * HLVAE_MAX_COMPS + 8;               // K0 hyper-parameters by component: os, hil2, il2, il3
     double* kps1 = kps + 4 * HLVAE_MAX_COMPS;                  // same for K1
-    double2* xsP = reinterpret_cast<double2*>(kps1 + 4 * HLVAE_MAX_COMPS);   // [MAX_COMPS][RP] {x[se col], x[first discrete col]}
-    double2* xsP1 = xsP + HLVAE_MAX_COMPS * RP;                               // the same for the components of K1
-    double* etab = kps1 + 4 * HLVAE_MAX_COMPS + 4 * HLVAE_MAX_COMPS * RP;     // 2^(j/64) for exp_nonpos_tab
-    int* grow = reinterpret_cast<int*>(etab + HLVAE_EXP_TAB);
-    int* sub_of_row = grow + RP;
-    int* sub_r0 = sub_of_row + RP;                             // [PN_SMAX+1]
-    int* sub_b0 = sub_r0 + PN_SMAX + 1;                        // [PN_SMAX+1] offsets of the T x T blocks
-    int* sub_t0 = sub_b0 + PN_SMAX + 1;                        // [PN_SMAX+1] offsets of the lower triangles
-    int* meta = sub_t0 + PN_SMAX + 1;                          // nsub, first subject, next subject, TMEM base
+    double* etab = kps1 + 4 * HLVAE_MAX_COMPS;                 // 2^(j/64) for exp_nonpos_tab
+    // panel descriptors, two sets: the panel being computed and the one being loaded
+    int* grow_b = reinterpret_cast<int*>(etab + HLVAE_EXP_TAB);    // [2][RP] minibatch row of a panel row
+    int* sor_b = grow_b + 2 * RP;                              // [2][RP] subject (within the panel) of a panel row, -1 = padding
+    int* sub_r0_b = sor_b + 2 * RP;                            // [2][PN_SMAX+1] first panel row of a subject
+    int* sub_b0_b = sub_r0_b + 2 * (PN_SMAX + 1);              // [2][PN_SMAX+1] offsets of the T x T blocks
+    int* meta = sub_b0_b + 2 * (PN_SMAX + 1);                  // [0,1] subjects, [2,3] first subject, [4] cursor, [5] TMEM base
     int* tl_tab = meta + 8;                                    // (row tile << 8 | column tile) of the lower triangle
     int* csr_r = tl_tab + SM::n_lower_tiles;                   // subj_ptr[s_begin ..] of this chunk
     int* csr_t = csr_r + PN_CHUNK_CSR + 1;                     // tt_ptr[s_begin ..]
@@ -541,7 +538,7 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
     }
     for (int m = tid; m < MP; m += PN_THREADS) ws[m] = (m < M) ? w[(int64_t)l * M + m] : 0.0;
     exp2_table_fill(etab, tid, PN_THREADS);
-    if (warp == 0) tmem_alloc<TM_COLS>(reinterpret_cast<uint32_t*>(meta + 3));
+    if (warp == 0) tmem_alloc<TM_COLS>(reinterpret_cast<uint32_t*>(meta + 5));
     for (int i = tid; i < RP / 8; i += PN_THREADS)
         for (int j = 0; j <= i; j++) tl_tab[i * (i + 1) / 2 + j] = (i << 8) | j;
     for (int i = tid; i <= PN_CHUNK_CSR && s_begin + i <= s_end; i += PN_THREADS) {
@@ -596,105 +593,112 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
 #pragma unroll
     for (int r = 0; r < PN_NCACHE; r++) hg0[r] = hg1[r] = hg2[r] = 0.0;
 
-    if (tid == 0) meta[2] = s_begin;
+    if (tid == 0) meta[4] = s_begin;
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = (uint32_t)meta[3];
+    const uint32_t tmem_base = (uint32_t)meta[5];
     // this thread's private columns: lane quadrant of its warp, column block of its group of four warps
     const uint32_t tm_mine = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * PN_TMEM_COLS_PER_GROUP);
     const double wm = ws[em];
-    const int chunk_row_end = subj_ptr[s_end];
-    const int chunk_tt_end = tt_ptr[s_end];
     // CSR offsets of subject s (s_begin <= s <= s_end): from the shared-memory copy where it reaches
     auto rows_at = [&](int s) { return s - s_begin <= PN_CHUNK_CSR ? csr_r[s - s_begin] : subj_ptr[s]; };
     auto tt_at = [&](int s) { return s - s_begin <= PN_CHUNK_CSR ? csr_t[s - s_begin] : tt_ptr[s]; };
 
-    while (true) {
-        // ---- P0: pack whole subjects into a panel of at most RP rows
-        if (tid == 0) {
-            int s = meta[2], ns = 0, rows = 0, bsz = 0;
-            meta[1] = s;
-            sub_r0[0] = 0;
-            sub_b0[0] = 0;
-            int r_lo = rows_at(s);
-            while (s < s_end && ns < PN_SMAX) {
-                const int r_hi = rows_at(s + 1);
-                const int T = r_hi - r_lo;
-                if (T > HLVAE_TMAX) {   // reported by kl_subject_k as well; skip here
-                    if (ns == 0) { s++; r_lo = r_hi; meta[1] = s; continue; }
-                    break;
-                }
-                if (rows + T > RP) break;
-                rows += T;
-                bsz += T * T;
-                ns++;
-                s++;
-                r_lo = r_hi;
-                sub_r0[ns] = rows;
-                sub_b0[ns] = bsz;
+    // ---- P0, software pipelined: while panel n is computed, thread 0 packs whole subjects into panel n + 1 (at most
+    // RP rows) and every thread issues the asynchronous copies (cp.async) that gather its covariate rows, its mu
+    // column and the subjects' B^-1 blocks - scattered onto the block diagonal of the dense panel, the rest of each
+    // row zero-filled by the same thread - so that a panel starts with its inputs in shared memory instead of
+    // waiting for L2 / HBM behind two barriers (r02: 14 % of the kernel's stall samples).
+    auto pack = [&](int pz) {                                  // thread 0
+        int s = meta[4], ns = 0, rows = 0, bsz = 0, first = s;
+        int* r0 = sub_r0_b + pz * (PN_SMAX + 1);
+        int* b0 = sub_b0_b + pz * (PN_SMAX + 1);
+        int* so = sor_b + pz * RP;
+        r0[0] = 0;
+        b0[0] = 0;
+        int r_lo = rows_at(s);
+        while (s < s_end && ns < PN_SMAX) {
+            const int r_hi = rows_at(s + 1);
+            const int T = r_hi - r_lo;
+            if (T > HLVAE_TMAX) {   // reported by kl_subject_k as well; skip here
+                if (ns == 0) { s++; r_lo = r_hi; first = s; continue; }
+                break;
             }
-            meta[0] = ns;
-            meta[2] = s;
+            if (rows + T > RP) break;
+            for (int i = 0; i < T; i++) so[rows + i] = ns;
+            rows += T;
+            bsz += T * T;
+            ns++;
+            s++;
+            r_lo = r_hi;
+            r0[ns] = rows;
+            b0[ns] = bsz;
         }
-        // clear the dense B^-1 panel while thread 0 packs
-        for (int e = tid; e < RP * LDB; e += PN_THREADS) Bp[e] = 0.0;
-        __syncthreads();
-        const int nsub = meta[0];
+        for (int i = rows; i < RP; i++) so[i] = -1;
+        meta[pz] = ns;
+        meta[2 + pz] = first;
+        meta[4] = s;
+    };
+    // minibatch row of this thread's panel row in descriptor set pz (-1: none)
+    auto next_row = [&](int pz) {
+        const int ns = meta[pz];
+        if (ns == 0 || tid >= sub_r0_b[pz * (PN_SMAX + 1) + ns]) return -1;
+        return (int)row_idx[rows_at(meta[2 + pz]) + tid];
+    };
+    auto issue_loads = [&](int pz, int g) {
+        const int ns = meta[pz];
+        if (ns > 0) {
+            const int* r0 = sub_r0_b + pz * (PN_SMAX + 1);
+            const int* b0 = sub_b0_b + pz * (PN_SMAX + 1);
+            const int* so = sor_b + pz * RP;
+            if (tid < RP) {
+                double* xn = xs + (pz * RP + tid) * HLVAE_MAX_Q;
+                if (g >= 0) {
+                    grow_b[pz * RP + tid] = g;
+                    const double* src = x + (int64_t)g * ldx;
+                    for (int q = 0; q < Q; q++) cp_async<8>(xn + q, src + q);
+                    cp_async<(int)sizeof(TS)>(mraw + pz * RP + tid, mu + (int64_t)g * ld_mu + l);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < HLVAE_MAX_Q; q++) xn[q] = 0.0;
+                }
+            }
+            const double* bsrc = binv + (int64_t)l * tt_total + tt_at(meta[2 + pz]);
+            for (int row = warp; row < RP; row += PN_THREADS / 32) {
+                const int k = so[row];
+                int rs = 0, T = 0, bo = 0;
+                if (k >= 0) {
+                    rs = r0[k];
+                    T = r0[k + 1] - rs;
+                    bo = b0[k] + (row - rs) * T - rs;          // block element (row - rs, col - rs)
+                }
+                for (int col = lane; col < LDB; col += 32) {
+                    if (col >= rs && col < rs + T) cp_async<8>(&Bp[row * LDB + col], bsrc + bo + col);
+                    else Bp[row * LDB + col] = 0.0;
+                }
+            }
+        }
+        cp_async_commit();
+    };
+    if (tid == 0) pack(0);
+    __syncthreads();
+    issue_loads(0, next_row(0));
+    int par = 0;
+
+    while (true) {
+        cp_async_wait_all();
+        __syncthreads();      // the inputs of this panel have landed; every thread is done with the previous one
+        const int nsub = meta[par];
         if (nsub == 0) break;
-        const int s_first = meta[1];
+        const int* sub_r0 = sub_r0_b + par * (PN_SMAX + 1);
+        const int* sub_of_row = sor_b + par * RP;
+        const int* grow = grow_b + par * RP;
+        const double* xsc = xs + par * RP * HLVAE_MAX_Q;       // [RP][8]
         const int R = sub_r0[nsub];
         const int R8 = (R + 7) & ~7;
-        const int pr0 = rows_at(s_first);
-        // look-ahead: the rows and B^-1 blocks the NEXT panel will gather (about the same amount as this one) are
-        // pulled into L1 while this panel computes, so that the set-up above stops waiting on L2 / HBM
-        int pf_g = -1, pf_b = -1;
-        {
-            const int s_next = meta[2];
-            if (s_next < s_end) {
-                const int prn = rows_at(s_next);
-                if (tid < RP && prn + tid < chunk_row_end) pf_g = row_idx[prn + tid];
-                const int b0 = tt_at(s_next) + tid * 16;           // one 128-byte line per thread
-                if (tid < RP * HLVAE_TMAX / 16 && b0 < chunk_tt_end) pf_b = b0;
-            }
-        }
-        if (tid < R) {
-            int k = 0;
-            while (tid >= sub_r0[k + 1]) k++;
-            sub_of_row[tid] = k;
-            int g = row_idx[pr0 + tid];
-            grow[tid] = g;
-            for (int q = 0; q < Q; q++) xs[tid * Q + q] = x[(int64_t)g * ldx + q];
-            mus[tid] = (double)mu[(int64_t)g * ld_mu + l];
-        } else if (tid < RP) {
-            sub_of_row[tid] = -1;
-            for (int q = 0; q < Q; q++) xs[tid * Q + q] = 0.0;
-        }
-        if (tid < RP) {   // per component: the row's squared-exponential covariate next to its first discrete one
-            for (int r = 0; r < sp0.ncomp; r++) {
-                const int sc = sp0.comp[r].se_col, dc = sp0.comp[r].disc_col[0];
-                xsP[r * RP + tid] = make_double2(sc >= 0 ? xs[tid * Q + sc] : 0.0,
-                                                 sp0.comp[r].ndisc > 0 ? xs[tid * Q + dc] : 0.0);
-            }
-            for (int r = 0; r < sp1.ncomp; r++) {
-                const int sc = sp1.comp[r].se_col, dc = sp1.comp[r].disc_col[0];
-                xsP1[r * RP + tid] = make_double2(sc >= 0 ? xs[tid * Q + sc] : 0.0,
-                                                  sp1.comp[r].ndisc > 0 ? xs[tid * Q + dc] : 0.0);
-            }
-        }
-        {   // scatter the subjects' B^-1 blocks (contiguous in global memory) onto the block diagonal
-            const double* bsrc = binv + (int64_t)l * tt_total + tt_at(s_first);
-            const int nb = sub_b0[nsub];
-            int k = 0;
-            for (int e = tid; e < nb; e += PN_THREADS) {
-                while (e >= sub_b0[k + 1]) k++;
-                const int rs = sub_r0[k], T = sub_r0[k + 1] - rs;
-                const int le = e - sub_b0[k];
-                const int i = le / T, j = le - i * T;
-                Bp[(rs + i) * LDB + rs + j] = bsrc[e];
-            }
-        }
-        __syncthreads();
+        if (tid == 0) pack(par ^ 1);
+        if (tid < R) mus[tid] = (double)mraw[par * RP + tid];
 
         // ---- P1: K0xz rows (elbo_functions.py:147 / :222), zero padded to [R8][MP].
         // Thread = (inducing point em, row group eg); components outermost so that the spec and the inducing point's
@@ -718,24 +722,26 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
                 const double zse = has_se ? Zs[c.se_col * MP + em] : 0.0;
                 const double z0 = nd > 0 ? Zs[c.disc_col[0] * MP + em] : 0.0;
                 const double nh = -kps[HLVAE_MAX_COMPS + r], osr = kps[r];
-                const double2* xp = xsP + r * RP + eg;
+                // this thread's rows are eg + k NGRP: fixed offsets from one base per covariate column
+                const double* xa = xsc + eg * HLVAE_MAX_Q + (has_se ? c.se_col : 0);
+                const double* xb = xsc + eg * HLVAE_MAX_Q + (nd > 0 ? c.disc_col[0] : 0);
+                constexpr int XS = NGRP * HLVAE_MAX_Q;
                 double vv[RPT];
                 if (nd == 0 && has_se) {
 #pragma unroll
                     for (int k = 0; k < RPT; k++) {
-                        const double d = xp[k * NGRP].x - zse;
+                        const double d = xa[k * XS] - zse;
                         vv[k] = exp_nonpos_tab_sel<false>((d * nh) * d, etab, true);
                     }
                 } else if (nd == 1 && cat0 && has_se) {
 #pragma unroll
                     for (int k = 0; k < RPT; k++) {
-                        const double2 xv = xp[k * NGRP];
-                        const double d = xv.x - zse;
-                        vv[k] = exp_nonpos_tab_sel<true>((d * nh) * d, etab, xv.y == z0);
+                        const double d = xa[k * XS] - zse;
+                        vv[k] = exp_nonpos_tab_sel<true>((d * nh) * d, etab, xb[k * XS] == z0);
                     }
                 } else if (nd == 1 && cat0) {
 #pragma unroll
-                    for (int k = 0; k < RPT; k++) vv[k] = (xp[k * NGRP].y == z0) ? 1.0 : 0.0;
+                    for (int k = 0; k < RPT; k++) vv[k] = (xb[k * XS] == z0) ? 1.0 : 0.0;
                 } else {
                     const bool cat1 = c.disc_kind[1] == HLVAE_KIND_CAT, cat2 = c.disc_kind[2] == HLVAE_KIND_CAT;
                     const int dc0 = nd > 0 ? c.disc_col[0] : 0, dc1 = nd > 1 ? c.disc_col[1] : 0,
@@ -743,13 +749,13 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
                     const double z1 = nd > 1 ? Zs[dc1 * MP + em] : 0.0, z2 = nd > 2 ? Zs[dc2 * MP + em] : 0.0;
 #pragma unroll
                     for (int k = 0; k < RPT; k++) {
-                        const double* xr = xs + (eg + k * NGRP) * Q;
+                        const double* xr = xsc + (eg + k * NGRP) * HLVAE_MAX_Q;
                         const double a0 = xr[dc0], a1 = xr[dc1], a2 = xr[dc2];
                         bool ok = true;
                         ok = ok && (nd < 1 || (cat0 ? (a0 == z0) : (a0 + z0 == 2.0)));
                         ok = ok && (nd < 2 || (cat1 ? (a1 == z1) : (a1 + z1 == 2.0)));
                         ok = ok && (nd < 3 || (cat2 ? (a2 == z2) : (a2 + z2 == 2.0)));
-                        const double d = xp[k * NGRP].x - zse;
+                        const double d = xa[k * XS] - zse;
                         const double e_ = has_se ? exp_nonpos_tab_sel<false>((d * nh) * d, etab, true) : 1.0;
                         vv[k] = ok ? e_ : 0.0;
                     }
@@ -765,12 +771,8 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
             }
             tmem_wait_st();
         }
-        if (pf_g >= 0) {
-            prefetch_l1(x + (int64_t)pf_g * ldx);
-            prefetch_l1(mu + (int64_t)pf_g * ld_mu + l);
-        }
-        if (pf_b >= 0) prefetch_l1(binv + (int64_t)l * tt_total + pf_b);
         __syncthreads();
+        const int g_next = next_row(par ^ 1);     // (the next panel's descriptors were written before this barrier)
 
         // ---- P2: V = B^-1 K0xz (block diagonal, :160 / :254) on the FP64 tensor pipe, k-range
         // limited to the subjects a row tile touches; r = K0xz w - mu (:166 / :230)
@@ -860,6 +862,8 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
             }
         }
         __syncthreads();
+
+        issue_loads(par ^ 1, g_next);             // Bp, mraw and the other xs / descriptor set are free from here on
 
         // ---- P4: W = V G  (dJ/dS = G / 2 applied on both sides -> dJ/dK0xz = W + rho w^T), into Kb.
         // One G fragment per k-step serves all of the warp's row tiles.
@@ -967,19 +971,20 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
                 const double osr = kps1[r], hil2 = kps1[HLVAE_MAX_COMPS + r], il3 = kps1[3 * HLVAE_MAX_COMPS + r];
                 const double nh = -hil2;
                 const bool has_se = c.se_col >= 0, cat0 = c.disc_kind[0] == HLVAE_KIND_CAT;
-                const double2* xp = xsP1 + r * RP;
+                const double* xa = xsc + (has_se ? c.se_col : 0);
+                const double* xb = xsc + (c.ndisc > 0 ? c.disc_col[0] : 0);
                 double gos = 0.0, gls = 0.0;
 #pragma unroll
                 for (int t = 0; t < NTL; t++) {
                     if (live[t]) {
                         if (c.ndisc == 1 && cat0) {                 // categorical (x SE): the forms kernel_gen.py builds
-                            const double2 xi = xp[gi[t]];
+                            const double xia = xa[gi[t] * HLVAE_MAX_Q], xib = xb[gi[t] * HLVAE_MAX_Q];
 #pragma unroll
                             for (int u = 0; u < 2; u++) {
-                                const double2 xj = xp[gj[t] + u];
-                                const double d = xi.x - xj.x;
-                                const double v = has_se ? exp_nonpos_tab_sel<true>((d * nh) * d, etab, xi.y == xj.y)
-                                                        : ((xi.y == xj.y) ? 1.0 : 0.0);
+                                const double xja = xa[(gj[t] + u) * HLVAE_MAX_Q], xjb = xb[(gj[t] + u) * HLVAE_MAX_Q];
+                                const double d = xia - xja;
+                                const double v = has_se ? exp_nonpos_tab_sel<true>((d * nh) * d, etab, xib == xjb)
+                                                        : ((xib == xjb) ? 1.0 : 0.0);
                                 const double gv = gq[t][u] * v;
                                 gos += gv;
                                 gls = fma(gv * d, d, gls);
@@ -988,7 +993,7 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
 #pragma unroll
                             for (int u = 0; u < 2; u++) {
                                 double d;
-                                const double gv = gq[t][u] * c.value(xs + gi[t] * Q, xs + (gj[t] + u) * Q, hil2, d, etab);
+                                const double gv = gq[t][u] * c.value(xsc + gi[t] * HLVAE_MAX_Q, xsc + (gj[t] + u) * HLVAE_MAX_Q, hil2, d, etab);
                                 gos += gv;
                                 gls = fma(gv * d, d, gls);
                             }
@@ -1026,11 +1031,11 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
                     double vv[RPT];
                     tmem_load_doubles<RPT>(tm_mine + r * 2 * RPT, vv);
                     if (c.se_col >= 0) {
-                        const double2* xp = xsP + r * RP + eg;
+                        const double* xa = xsc + eg * HLVAE_MAX_Q + c.se_col;
 #pragma unroll
                         for (int k = 0; k < RPT; k++) {
                             const double gkv = gk[k] * vv[k];
-                            const double d = xp[k * NGRP].x - zse;
+                            const double d = xa[k * NGRP * HLVAE_MAX_Q] - zse;
                             const double t = gkv * d;
                             s0 += gkv;
                             s1 += t;
@@ -1049,7 +1054,7 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
                         for (int k = 0; k < RPT; k++) {
                             const int row = eg + k * NGRP;
                             if (row < R) {
-                                const double* xr = xs + row * Q;
+                                const double* xr = xsc + row * HLVAE_MAX_Q;
                                 bool ok = true;
 #pragma unroll
                                 for (int f = 0; f < HLVAE_MAX_DISC; f++)
@@ -1088,7 +1093,7 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
                 }
             }
         }
-        __syncthreads();
+        par ^= 1;
     }
 
     // ---- cached components: reduce the per-thread gradient sums into hyp / zacc

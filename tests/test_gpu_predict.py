@@ -36,7 +36,8 @@ def test_golden(name, device):
     # zt_list may also be a list of per-latent [M, Q] tensors (utils.py:104)
     zl = predict.batch_predict_varying_T(L, k0, k1, lik, x, xt, mu, [z[i] for i in range(L)], kargs["id_covariate"],
                                          float(g["eps"]))
-    assert torch.equal(zl, zp)
+    # same arithmetic; only the order in which the chunks' partial sums reach the accumulators may differ
+    assert h.rel_err(zl, zp) < 1e-12
 
 
 @pytest.mark.parametrize("L,M,n_subj,T", [(8, 64, 60, 20), (3, 128, 25, 32), (4, 32, 40, 9)])
