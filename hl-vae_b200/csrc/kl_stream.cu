@@ -610,35 +610,42 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
     // column and the subjects' B^-1 blocks - scattered onto the block diagonal of the dense panel, the rest of each
     // row zero-filled by the same thread - so that a panel starts with its inputs in shared memory instead of
     // waiting for L2 / HBM behind two barriers (r02: 14 % of the kernel's stall samples).
-    auto pack = [&](int pz) {                                  // thread 0
-        int s = meta[4], ns = 0, rows = 0, bsz = 0, first = s;
+    auto pack = [&](int pz) {                                  // the 32 lanes of one warp: lane i looks at subject cursor + i
         int* r0 = sub_r0_b + pz * (PN_SMAX + 1);
         int* b0 = sub_b0_b + pz * (PN_SMAX + 1);
         int* so = sor_b + pz * RP;
-        r0[0] = 0;
-        b0[0] = 0;
-        int r_lo = rows_at(s);
-        while (s < s_end && ns < PN_SMAX) {
-            const int r_hi = rows_at(s + 1);
-            const int T = r_hi - r_lo;
-            if (T > HLVAE_TMAX) {   // reported by kl_subject_k as well; skip here
-                if (ns == 0) { s++; r_lo = r_hi; first = s; continue; }
-                break;
+        int s0 = meta[4], ns, T, incl, incl2;
+        while (true) {
+            const int s = s0 + lane;
+            const bool valid = lane < PN_SMAX && s < s_end;
+            T = valid ? rows_at(s + 1) - rows_at(s) : 0;
+            const bool big = T > HLVAE_TMAX;                   // reported by kl_subject_k as well; skipped here
+            incl = T;
+            incl2 = T * T;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {                 // inclusive prefix sums of T and T^2
+                const int a = __shfl_up_sync(0xffffffffu, incl, o), b2 = __shfl_up_sync(0xffffffffu, incl2, o);
+                if (lane >= o) { incl += a; incl2 += b2; }
             }
-            if (rows + T > RP) break;
-            for (int i = 0; i < T; i++) so[rows + i] = ns;
-            rows += T;
-            bsz += T * T;
-            ns++;
-            s++;
-            r_lo = r_hi;
-            r0[ns] = rows;
-            b0[ns] = bsz;
+            const unsigned okm = __ballot_sync(0xffffffffu, valid && !big && incl <= RP);
+            ns = __ffs(~okm) - 1;                              // the leading run of subjects that fit (lanes >= PN_SMAX never do)
+            if (ns == 0 && (__ballot_sync(0xffffffffu, big) & 1u)) { s0++; continue; }
+            break;
         }
-        for (int i = rows; i < RP; i++) so[i] = -1;
-        meta[pz] = ns;
-        meta[2 + pz] = first;
-        meta[4] = s;
+        if (lane < ns) {
+            r0[lane + 1] = incl;
+            b0[lane + 1] = incl2;
+            for (int t = 0; t < T; t++) so[incl - T + t] = lane;
+        }
+        const int rows = ns > 0 ? __shfl_sync(0xffffffffu, incl, ns - 1) : 0;
+        for (int row = rows + lane; row < RP; row += 32) so[row] = -1;
+        if (lane == 0) {
+            r0[0] = 0;
+            b0[0] = 0;
+            meta[pz] = ns;
+            meta[2 + pz] = s0;
+            meta[4] = s0 + ns;
+        }
     };
     // minibatch row of this thread's panel row in descriptor set pz (-1: none)
     auto next_row = [&](int pz) {
@@ -681,7 +688,7 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
         }
         cp_async_commit();
     };
-    if (tid == 0) pack(0);
+    if (warp == PN_THREADS / 32 - 1) pack(0);
     __syncthreads();
     issue_loads(0, next_row(0));
     int par = 0;
@@ -697,7 +704,6 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
         const double* xsc = xs + par * RP * HLVAE_MAX_Q;       // [RP][8]
         const int R = sub_r0[nsub];
         const int R8 = (R + 7) & ~7;
-        if (tid == 0) pack(par ^ 1);
         if (tid < R) mus[tid] = (double)mraw[par * RP + tid];
 
         // ---- P1: K0xz rows (elbo_functions.py:147 / :222), zero padded to [R8][MP].
@@ -772,7 +778,6 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
             tmem_wait_st();
         }
         __syncthreads();
-        const int g_next = next_row(par ^ 1);     // (the next panel's descriptors were written before this barrier)
 
         // ---- P2: V = B^-1 K0xz (block diagonal, :160 / :254) on the FP64 tensor pipe, k-range
         // limited to the subjects a row tile touches; r = K0xz w - mu (:166 / :230)
@@ -816,20 +821,32 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
                 dmma884(c0, c1, a, b);
             }
             const int row = warp * 8 + ar;
-            if (ac == 0 && row < R) rv[row] = c0 - mus[row];
+            if (ac == 0) rv[row] = row < R ? c0 - mus[row] : 0.0;       // rows R..R8-1: zeros (operand of rho below)
         }
+        // the next panel is packed by the warp with the least to do in this phase (last row tiles, no part in r)
+        if (warp == PN_THREADS / 32 - 1) pack(par ^ 1);
         __syncthreads();
+        const int g_next = next_row(par ^ 1);
 
-        // ---- P3a: rho = B^-1 r; A += r . rho (:167 / :256); dJ/dmu = -rho
-        if (tid < R) {
-            const int k = sub_of_row[tid];
-            const int rs = sub_r0[k], re = sub_r0[k + 1];
-            const double* brow = Bp + tid * LDB;
-            double a = 0.0;
-            for (int t = rs; t < re; t++) a = fma(brow[t], rv[t], a);
-            rho[tid] = a;
-            a_acc = fma(rv[tid], a, a_acc);
-            g_mu[(int64_t)grow[tid] * L + l] = (TS)(-a * gscale);
+        // ---- P3a: rho = B^-1 r (one more column tile of the tensor pipe: B fragment = r in column 0, k-range = the
+        // subjects a row tile touches); A += r . rho (:167 / :256); dJ/dmu = -rho
+        if (warp * 8 < R) {
+            const int ar = lane >> 2, ac = lane & 3;
+            const int rlast = min(warp * 8 + 7, R - 1);
+            const int klo = sub_r0[sub_of_row[warp * 8]] & ~3;
+            const int khi = (sub_r0[sub_of_row[rlast] + 1] + 3) & ~3;
+            double c0 = 0.0, c1 = 0.0;
+            for (int k0 = klo; k0 < khi; k0 += 4) {
+                const double a = Bp[(warp * 8 + ar) * LDB + k0 + ac];
+                const double b = (ar == 0) ? rv[k0 + ac] : 0.0;
+                dmma884(c0, c1, a, b);
+            }
+            const int row = warp * 8 + ar;
+            if (ac == 0 && row < R) {
+                rho[row] = c0;
+                a_acc = fma(rv[row], c0, a_acc);
+                g_mu[(int64_t)grow[row] * L + l] = (TS)(-c0 * gscale);
+            }
         }
         // p = sum_r V[r] mu_r (:188 / :265) and dJ/dw = K0xz^T rho = V^T r (B^-1 is symmetric): per-thread partial
         // sums over this thread's rows, kept over the CTA's whole chunk; they need only V, mu and r, so they share this
