@@ -67,6 +67,39 @@ template <typename TS> __device__ __forceinline__ void st(void* p, int64_t i, do
 
 __device__ __forceinline__ int d0_(int tile, int tile_vars) { return tile * tile_vars; }
 
+// Thread -> variable of the tile.  A warp that holds variables of several types executes every type's code path for
+// every row (the D4 layout alternates runs of 18 real and 18 categorical variables: half of the warps paid for both).
+// The tile's variables are therefore handed out sorted by type (stable: runs stay contiguous, so the accesses of a
+// warp stay on neighbouring columns): thread t takes the variable of rank t.  Returns its index inside the tile
+// (>= n_vars: no variable).  One ballot per type and warp, once per CTA.
+__device__ __forceinline__ int tile_variable_by_type(int tid, int d0, int n_vars, const int32_t* __restrict__ var_kind) {
+    constexpr int NW = LL_THREADS / 32, NK = 6;               // 5 types + "no variable"
+    __shared__ int s_cnt[NW][NK], s_perm[LL_THREADS];
+    const int lane = tid & 31, w = tid >> 5;
+    int kind = NK - 1;
+    if (tid < n_vars) {
+        const int k = var_kind[d0 + tid];
+        kind = (k >= 0 && k < NK - 1) ? k : NK - 2;
+    }
+    int below = 0;                                           // same type, lower lane of this warp
+#pragma unroll
+    for (int k = 0; k < NK; k++) {
+        const unsigned m = __ballot_sync(0xffffffffu, kind == k);
+        if (lane == 0) s_cnt[w][k] = __popc(m);
+        if (kind == k) below = __popc(m & ((1u << lane) - 1u));
+    }
+    __syncthreads();
+    int rank = below;
+#pragma unroll
+    for (int k = 0; k < NK; k++)
+#pragma unroll
+        for (int w2 = 0; w2 < NW; w2++)
+            if (k < kind || (k == kind && w2 < w)) rank += s_cnt[w2][k];
+    s_perm[rank] = tid;
+    __syncthreads();
+    return s_perm[tid];
+}
+
 // Per-variable constants, computed once per thread (float64, then rounded to R).
 template <typename R> struct VarC {
     int kind, C, xo, po;      // type, classes, offsets of the variable inside the staged spans
@@ -481,7 +514,8 @@ loglik_fwd_k(int64_t N, int D, int tile_vars, int cap, int64_t ld_data, int64_t 
     const int tid = threadIdx.x;
     const int d0 = blockIdx.x * tile_vars;
     const int d1 = min(D, d0 + tile_vars);
-    const int d = d0 + tid;
+    const int lt = tile_variable_by_type(tid, d0, d1 - d0, var_kind);   // this thread's variable inside the tile
+    const int d = d0 + lt;
     const bool active = d < d1;
     const int xs0 = var_dcol[d0], ps0 = var_pcol[d0];
     const int span_x = max(0, min(cap, var_dcol[d1 - 1] + var_nclass[d1 - 1] - xs0));
@@ -571,7 +605,7 @@ loglik_fwd_k(int64_t N, int D, int tile_vars, int cap, int64_t ld_data, int64_t 
 #pragma unroll 1
             for (int r = 0; r < nr; r++) {
                 R lp = R(0), rmean = R(0), rmode = R(0), dtr = R(0);
-                const R m_ = (R)sK[r * LL_CAPM + sShiftM[stg][r] + tid];
+                const R m_ = (R)sK[r * LL_CAPM + sShiftM[stg][r] + lt];
                 if (v.ok) {
                     var_forward<R, TD>(v, sX + r * capx + sShift[stg][r] + v.xo, sT + r * capt + sShiftT[stg][r] + v.po,
                                        m_ != R(0), lp, rmean, rmode, dtr);
@@ -767,7 +801,8 @@ loglik_bwd_k(int64_t N, int D, int tile_vars, int cap, int64_t ld_data, int64_t 
     const int tid = threadIdx.x;
     const int d0 = blockIdx.x * tile_vars;
     const int d1 = min(D, d0 + tile_vars);
-    const int d = d0 + tid;
+    const int lt = tile_variable_by_type(tid, d0, d1 - d0, var_kind);   // this thread's variable inside the tile
+    const int d = d0 + lt;
     const bool active = d < d1;
     const int xs0 = var_dcol[d0], ps0 = var_pcol[d0];
     const int span_x = max(0, min(cap, var_dcol[d1 - 1] + var_nclass[d1 - 1] - xs0));
@@ -869,8 +904,8 @@ loglik_bwd_k(int64_t N, int D, int tile_vars, int cap, int64_t ld_data, int64_t 
             for (int r = 0; r < nr; r++) {
                 if (v.ok) {
                     R ge = R(0);
-                    const R m_ = (R)sK[r * LL_CAPM + sShiftM[stg][r] + tid];
-                    const R g_ = gs + (g_lp ? sG[r * LL_CAPM + sShiftG[stg][r] + tid] : R(0));
+                    const R m_ = (R)sK[r * LL_CAPM + sShiftM[stg][r] + lt];
+                    const R g_ = gs + (g_lp ? sG[r * LL_CAPM + sShiftG[stg][r] + lt] : R(0));
                     var_backward<R, TD>(v, sX + r * capx + sShift[stg][r] + v.xo, sT + r * capt + sShiftT[stg][r] + v.po,
                                         m_ != R(0), g_ * m_, ge);
                     ge_acc += (double)ge;
