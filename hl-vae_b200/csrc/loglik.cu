@@ -205,13 +205,12 @@ __device__ __forceinline__ void cat_forward(const XT* __restrict__ x, R* __restr
     R tv[CMAX];
 #pragma unroll
     for (int c = 0; c < CMAX; c++) tv[c] = (c < C) ? t[c] : R(-INFINITY);
-    R mx = tv[0], second = -INFINITY;                                        // second: largest logit strictly below mx
+    R mx = tv[0];
     int am = 0;
 #pragma unroll
     for (int c = 1; c < CMAX; c++) {
         const R tc = tv[c];
-        if (tc > mx) { second = mx; mx = tc; am = c; }                       // first index wins ties
-        else if (tc < mx) second = fmax(second, tc);
+        if (tc > mx) { mx = tc; am = c; }                                    // first index wins ties
     }
     R se = R(0);
 #pragma unroll
@@ -219,10 +218,18 @@ __device__ __forceinline__ void cat_forward(const XT* __restrict__ x, R* __restr
     const R lse = mx + Mth<R>::lg(se);                                       // torch.logsumexp
     if constexpr (sizeof(R) == 4) {
         // The reference takes argmax of fl64(theta_c - lse); it can differ from argmax(theta) only when two
-        // DISTINCT logits collapse onto one double after the subtraction.
-        const R gap = mx - second;
-        if (gap > R(0) && gap < R(1e-13) * (fabs(mx) + fabs(lse)) + R(1e-37))
-            am = cat_argmax_f64(reinterpret_cast<const float*>(t), C);
+        // DISTINCT logits collapse onto one double after the subtraction: gap = mx - (largest logit below mx) <
+        // 1e-13 (|mx| + |lse|).  Distinct float32 logits are at least 2^-24 |mx| apart and |lse| <= |mx| + ln 16, so
+        // that needs |mx| < 4.7e-6: only then is the runner-up looked for at all.
+        if (fabs(mx) < R(1e-5)) {
+            R second = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < CMAX; c++)
+                if (tv[c] < mx) second = fmax(second, tv[c]);
+            const R gap = mx - second;
+            if (gap > R(0) && gap < R(1e-13) * (fabs(mx) + fabs(lse)) + R(1e-37))
+                am = cat_argmax_f64(reinterpret_cast<const float*>(t), C);
+        }
     } else {
         am = 0;
         R best = tv[0] - lse;
@@ -444,6 +451,31 @@ __device__ __forceinline__ void tma_unstage_row(T* __restrict__ dst, const T* __
     if (tid >= E && tid - E < span - tail0) dst[tail0 + tid - E] = src[shift + tail0 + tid - E];
 }
 
+// The same for a whole batch of rows in one pass when every row has the same alignment shift (row stride a multiple
+// of 16 bytes): thread = (row tid / 16, job tid % 16) - job 0 issues the row's bulk store, the jobs after it write
+// the at most E - 1 elements of the partial chunk at either end.  (Row by row, every thread redid the chunk
+// arithmetic for every row: 13 % of the forward kernel's instructions.)
+template <typename T>
+__device__ __forceinline__ void tma_unstage_batch(T* __restrict__ dst0, int64_t ld, const T* __restrict__ src0, int lds,
+                                                  int shift, int span, int nr, int tid) {
+    constexpr int E = 16 / (int)sizeof(T);
+    static_assert(LL_THREADS / LL_ROWS >= 2 * E - 1 || E > 8, "jobs per row");
+    const int r = tid / (LL_THREADS / LL_ROWS), j = tid % (LL_THREADS / LL_ROWS);
+    if (r >= nr) return;
+    const int i0 = shift > 0 ? 1 : 0;
+    const int i1 = (shift + span) / E;
+    const int head = min(span, E * i0 - shift);
+    const int tail0 = max(head, E * i1 - shift);
+    T* dst = dst0 + (int64_t)r * ld;
+    const T* src = src0 + r * lds;
+    if (j == 0) {
+        if (i1 > i0) bulk_s2g(dst + (E * i0 - shift), src + E * i0, (unsigned)((i1 - i0) * 16));
+    } else {
+        for (int e = j - 1; e < head; e += LL_THREADS / LL_ROWS - 1) dst[e] = src[shift + e];
+        for (int e = tail0 + j - 1; e < span; e += LL_THREADS / LL_ROWS - 1) dst[e] = src[shift + e];
+    }
+}
+
 // Stage `span` elements of one row as aligned 16-byte chunks: the copy starts at the 16-byte boundary
 // below `src` (`shift` elements early; the caller finds element j at dst[shift + j]) and ends at the
 // boundary above the last element.  The over-read stays inside the array as long as the array itself
@@ -524,6 +556,9 @@ loglik_fwd_k(int64_t N, int D, int tile_vars, int cap, int64_t ld_data, int64_t 
     const int64_t stride = (int64_t)gridDim.y * LL_ROWS;
     __shared__ __align__(8) unsigned long long mbar[LL_STAGES];
     const bool use_tma = x_ok && t_ok && m_ok;   // every staged array starts and ends on a 16-byte boundary
+    // row stride of theta / params a multiple of 16 bytes: every row of the tile has the same alignment shift
+    const bool uni_t = use_tma && ld_theta % (16 / (int)sizeof(TS)) == 0;
+    const int shift_t = (int)((reinterpret_cast<uintptr_t>(theta + ps0) & 15) / sizeof(TS));
     unsigned phase[LL_STAGES];
 #pragma unroll
     for (int i = 0; i < LL_STAGES; i++) phase[i] = 0;
@@ -602,8 +637,9 @@ loglik_fwd_k(int64_t N, int D, int tile_vars, int cap, int64_t ld_data, int64_t 
         TM* sK = reinterpret_cast<TM*>(sX + LL_ROWS * capx);
         const int nr = (int)min((int64_t)LL_ROWS, N - n0);
         if (active) {
+            int64_t o = n0 * D + d;
 #pragma unroll 1
-            for (int r = 0; r < nr; r++) {
+            for (int r = 0; r < nr; r++, o += D) {
                 R lp = R(0), rmean = R(0), rmode = R(0), dtr = R(0);
                 const R m_ = (R)sK[r * LL_CAPM + sShiftM[stg][r] + lt];
                 if (v.ok) {
@@ -621,7 +657,6 @@ loglik_fwd_k(int64_t N, int D, int tile_vars, int cap, int64_t ld_data, int64_t 
                 }
                 const R lpo = lp * m_;
                 ll += (double)lpo;
-                const int64_t o = (n0 + r) * D + d;
                 if (log_p_x) log_p_x[o] = lpo;
                 if (log_p_x_missing) log_p_x_missing[o] = lp * (R(1) - m_);
                 if (recon_mean) recon_mean[o] = rmean;
@@ -632,7 +667,13 @@ loglik_fwd_k(int64_t N, int D, int tile_vars, int cap, int64_t ld_data, int64_t 
         if (use_tma) fence_async_smem();         // params written through the generic proxy, read by the bulk store
         __syncthreads();
         if (params) {
-            if (use_tma) {
+            if (uni_t) {
+                tma_unstage_batch<TS>(params + n0 * ld_theta + ps0, ld_theta, sT, capt, shift_t, span_p, nr, tid);
+                if (tid % (LL_THREADS / LL_ROWS) == 0) {     // the issuing threads
+                    bulk_commit();
+                    bulk_wait_read();            // the staged rows have been read; the stage may be refilled
+                }
+            } else if (use_tma) {
                 for (int r = 0; r < nr; r++)
                     tma_unstage_row<TS>(params + (n0 + r) * ld_theta + ps0, sT + r * capt, sShiftT[stg][r], span_p, tid, r);
                 if (tid < nr) {                  // thread r issued row r
@@ -812,6 +853,8 @@ loglik_bwd_k(int64_t N, int D, int tile_vars, int cap, int64_t ld_data, int64_t 
     const int64_t stride = (int64_t)gridDim.y * LL_ROWS;
     __shared__ __align__(8) unsigned long long mbar[LL_STAGES];
     const bool use_tma = x_ok && t_ok && m_ok && (!g_lp || g_ok);
+    const bool uni_t = use_tma && ld_theta % (16 / (int)sizeof(TS)) == 0;
+    const int shift_t = (int)((reinterpret_cast<uintptr_t>(theta + ps0) & 15) / sizeof(TS));
     unsigned phase[LL_STAGES];
 #pragma unroll
     for (int i = 0; i < LL_STAGES; i++) phase[i] = 0;
@@ -917,7 +960,13 @@ loglik_bwd_k(int64_t N, int D, int tile_vars, int cap, int64_t ld_data, int64_t 
         }
         if (use_tma) fence_async_smem();
         __syncthreads();
-        if (use_tma) {
+        if (uni_t) {
+            tma_unstage_batch<TS>(g_theta + n0 * ld_theta + ps0, ld_theta, sT, capt, shift_t, span_p, nr, tid);
+            if (tid % (LL_THREADS / LL_ROWS) == 0) {
+                bulk_commit();
+                bulk_wait_read();
+            }
+        } else if (use_tma) {
             for (int r = 0; r < nr; r++)
                 tma_unstage_row<TS>(g_theta + (n0 + r) * ld_theta + ps0, sT + r * capt, sShiftT[stg][r], span_p, tid, r);
             if (tid < nr) {

@@ -1,0 +1,22 @@
+"""Three fused-likelihood forward + backward calls at the configs[1] shape (16 000 rows, D4: 324 real + 972
+categorical x 5, float32 theta, uint8 data / mask): the short command ncu profiles for the likelihood kernels."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+import torch
+import __graft_entry__ as g
+g.build()
+from hlvae_b200 import loglik, synth
+dev = torch.device("cuda:0")
+lay = loglik.VarLayout(synth.HEALTHMNIST_D4_TYPES, dev)
+gen = torch.Generator(device=dev).manual_seed(0)
+N = int(os.environ.get("ROWS", "16000"))
+data, mask = synth.device_likelihood_batch(lay, N, dev, gen, dtype=torch.uint8)
+theta = torch.randn(N, lay.P_theta, device=dev, generator=gen).requires_grad_(True)
+lvr = torch.zeros(324, dtype=torch.float64, device=dev)
+vparam = lay.vparam(log_vy_real=lvr, conv=True)
+for _ in range(3):
+    theta.grad = None
+    out = loglik.fused_loglik(lay, data, mask, theta, vparam, monitor=True)
+    (-out["log_p_x_sum"]).backward()
+torch.cuda.synchronize()
+print("nll", float(-out["log_p_x_sum"]))
