@@ -559,6 +559,9 @@ loglik_fwd_k(int64_t N, int D, int tile_vars, int cap, int64_t ld_data, int64_t 
     // row stride of theta / params a multiple of 16 bytes: every row of the tile has the same alignment shift
     const bool uni_t = use_tma && ld_theta % (16 / (int)sizeof(TS)) == 0;
     const int shift_t = (int)((reinterpret_cast<uintptr_t>(theta + ps0) & 15) / sizeof(TS));
+    const bool uni = uni_t && ld_data % (16 / (int)sizeof(TD)) == 0 && D % (16 / (int)sizeof(TM)) == 0;
+    const int shift_x = (int)((reinterpret_cast<uintptr_t>(data + xs0) & 15) / sizeof(TD));
+    const int shift_m = (int)((reinterpret_cast<uintptr_t>(mask + d0) & 15) / sizeof(TM));
     unsigned phase[LL_STAGES];
 #pragma unroll
     for (int i = 0; i < LL_STAGES; i++) phase[i] = 0;
@@ -638,13 +641,47 @@ loglik_fwd_k(int64_t N, int D, int tile_vars, int cap, int64_t ld_data, int64_t 
         const int nr = (int)min((int64_t)LL_ROWS, N - n0);
         if (active) {
             int64_t o = n0 * D + d;
+            // The row loop exists once per evaluator: the variable's type (and its validity) is fixed per thread, so
+            // the dispatch is made once per batch instead of once per row - real variables and 5-class categorical
+            // ones get loops of their own, everything else shares the general one.
+            auto rows = [&](auto&& eval) {
 #pragma unroll 1
-            for (int r = 0; r < nr; r++, o += D) {
-                R lp = R(0), rmean = R(0), rmode = R(0), dtr = R(0);
-                const R m_ = (R)sK[r * LL_CAPM + sShiftM[stg][r] + lt];
-                if (v.ok) {
-                    var_forward<R, TD>(v, sX + r * capx + sShift[stg][r] + v.xo, sT + r * capt + sShiftT[stg][r] + v.po,
-                                       m_ != R(0), lp, rmean, rmode, dtr);
+                for (int r = 0; r < nr; r++, o += D) {
+                    const int sm_ = uni ? shift_m : sShiftM[stg][r];
+                    const int sx_ = uni ? shift_x : sShift[stg][r];
+                    const int st_ = uni ? shift_t : sShiftT[stg][r];
+                    const R m_ = (R)sK[r * LL_CAPM + sm_ + lt];
+                    R lp = R(0), rmean = R(0), rmode = R(0), dtr = R(0);
+                    eval(sX + r * capx + sx_ + v.xo, sT + r * capt + st_ + v.po, m_ != R(0), lp, rmean, rmode, dtr, r);
+                    const R lpo = lp * m_;
+                    ll += (double)lpo;
+                    if (log_p_x) log_p_x[o] = lpo;
+                    if (log_p_x_missing) log_p_x_missing[o] = lp * (R(1) - m_);
+                    if (recon_mean) recon_mean[o] = rmean;
+                    if (recon_mode) recon_mode[o] = rmode;
+                    if (data_tr) data_tr[o] = dtr;
+                }
+            };
+            if (!v.ok) {
+                rows([&](const TD*, R*, bool, R& lp, R& rmean, R& rmode, R& dtr, int) { lp = rmean = rmode = dtr = (R)NAN; });
+            } else if (v.kind == HLVAE_VAR_REAL) {
+                rows([&](const TD* x, R* t, bool, R& lp, R& rmean, R& rmode, R& dtr, int) {     // loglik.py:27-70
+                    const R x0 = (R)x[0];
+                    const R mean = v.snv * t[0] + v.nm;
+                    const R rr = x0 * v.idiv - mean;
+                    lp = R(-0.5) * rr * rr * v.ivar - v.lconst;
+                    t[0] = mean;
+                    rmean = mean; rmode = mean;
+                    dtr = x0;
+                });
+            } else if (v.kind == HLVAE_VAR_CAT && v.C == 5) {
+                rows([&](const TD* x, R* t, bool, R& lp, R& rmean, R& rmode, R& dtr, int) {
+                    cat_forward<R, TD, 5>(x, t, 5, lp, rmean, dtr);
+                    rmode = rmean;
+                });
+            } else {
+                rows([&](const TD* x, R* t, bool obs, R& lp, R& rmean, R& rmode, R& dtr, int r) {
+                    var_forward<R, TD>(v, x, t, obs, lp, rmean, rmode, dtr);
                     if constexpr (sizeof(R) == 4) {
                         if (v.kind == HLVAE_VAR_ORDINAL && rmean < R(0)) {   // float32 could not prove the argmax: redo from theta
                             const R am = (R)ord_argmax_f64(reinterpret_cast<const float*>(theta) +
@@ -652,16 +689,7 @@ loglik_fwd_k(int64_t N, int D, int tile_vars, int cap, int64_t ld_data, int64_t 
                             rmean = am; rmode = am;
                         }
                     }
-                } else {
-                    lp = rmean = rmode = dtr = (R)NAN;
-                }
-                const R lpo = lp * m_;
-                ll += (double)lpo;
-                if (log_p_x) log_p_x[o] = lpo;
-                if (log_p_x_missing) log_p_x_missing[o] = lp * (R(1) - m_);
-                if (recon_mean) recon_mean[o] = rmean;
-                if (recon_mode) recon_mode[o] = rmode;
-                if (data_tr) data_tr[o] = dtr;
+                });
             }
         }
         if (use_tma) fence_async_smem();         // params written through the generic proxy, read by the bulk store
@@ -855,6 +883,11 @@ loglik_bwd_k(int64_t N, int D, int tile_vars, int cap, int64_t ld_data, int64_t 
     const bool use_tma = x_ok && t_ok && m_ok && (!g_lp || g_ok);
     const bool uni_t = use_tma && ld_theta % (16 / (int)sizeof(TS)) == 0;
     const int shift_t = (int)((reinterpret_cast<uintptr_t>(theta + ps0) & 15) / sizeof(TS));
+    const bool uni = uni_t && ld_data % (16 / (int)sizeof(TD)) == 0 && D % (16 / (int)sizeof(TM)) == 0 &&
+                     (!g_lp || D % (16 / (int)sizeof(TS)) == 0);
+    const int shift_x = (int)((reinterpret_cast<uintptr_t>(data + xs0) & 15) / sizeof(TD));
+    const int shift_m = (int)((reinterpret_cast<uintptr_t>(mask + d0) & 15) / sizeof(TM));
+    const int shift_g = g_lp ? (int)((reinterpret_cast<uintptr_t>(g_lp + d0) & 15) / sizeof(TS)) : 0;
     unsigned phase[LL_STAGES];
 #pragma unroll
     for (int i = 0; i < LL_STAGES; i++) phase[i] = 0;
@@ -943,19 +976,34 @@ loglik_bwd_k(int64_t N, int D, int tile_vars, int cap, int64_t ld_data, int64_t 
         TM* sK = reinterpret_cast<TM*>(sX + LL_ROWS * capx);
         const int nr = (int)min((int64_t)LL_ROWS, N - n0);
         if (active) {
+            // one row loop per evaluator (the type of a thread's variable is fixed): see loglik_fwd_k
+            auto rows = [&](auto&& eval) {
 #pragma unroll 1
-            for (int r = 0; r < nr; r++) {
-                if (v.ok) {
+                for (int r = 0; r < nr; r++) {
+                    const int sm_ = uni ? shift_m : sShiftM[stg][r];
+                    const int sx_ = uni ? shift_x : sShift[stg][r];
+                    const int st_ = uni ? shift_t : sShiftT[stg][r];
+                    const R m_ = (R)sK[r * LL_CAPM + sm_ + lt];
+                    const R g_ = gs + (g_lp ? sG[r * LL_CAPM + (uni ? shift_g : sShiftG[stg][r]) + lt] : R(0));
                     R ge = R(0);
-                    const R m_ = (R)sK[r * LL_CAPM + sShiftM[stg][r] + lt];
-                    const R g_ = gs + (g_lp ? sG[r * LL_CAPM + sShiftG[stg][r] + lt] : R(0));
-                    var_backward<R, TD>(v, sX + r * capx + sShift[stg][r] + v.xo, sT + r * capt + sShiftT[stg][r] + v.po,
-                                        m_ != R(0), g_ * m_, ge);
+                    eval(sX + r * capx + sx_ + v.xo, sT + r * capt + st_ + v.po, m_ != R(0), g_ * m_, ge);
                     ge_acc += (double)ge;
-                } else {
+                }
+            };
+            if (!v.ok) {
+                for (int r = 0; r < nr; r++)
                     for (int c = 0; c < v.C && v.po >= 0 && v.po + c < cap; c++)
                         sT[r * capt + sShiftT[stg][r] + v.po + c] = (R)NAN;
-                }
+            } else if (v.kind == HLVAE_VAR_REAL) {
+                rows([&](const TD* x, R* t, bool, R g, R& ge) {
+                    const R rr = (R)x[0] * v.idiv - (v.snv * t[0] + v.nm);
+                    t[0] = g * v.snv * rr * v.ivar;
+                    ge = g * (R(0.5) * rr * rr * v.ivar - R(0.5)) * v.sg8;
+                });
+            } else if (v.kind == HLVAE_VAR_CAT && v.C == 5) {
+                rows([&](const TD* x, R* t, bool, R g, R&) { cat_backward<R, TD, 5>(x, t, 5, g); });
+            } else {
+                rows([&](const TD* x, R* t, bool obs, R g, R& ge) { var_backward<R, TD>(v, x, t, obs, g, ge); });
             }
         }
         if (use_tma) fence_async_smem();
