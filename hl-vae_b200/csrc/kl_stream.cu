@@ -62,6 +62,25 @@ struct CompRegs {
         d = xa[se_col] - xb[se_col];
         return exp_nonpos_tab(-(d * d) * hil2, etab);
     }
+    // The same value through straight-line bodies for the three shapes kernel_gen.py:199-310 builds (SE, SE x
+    // categorical, categorical): no data-dependent branch, the discrete factor folded into the exponent insert of the
+    // exponential.  The shape is the same for every lane (and loop invariant for the caller).  For a mismatch the
+    // value is 0 and d is left at the covariate difference (every consumer multiplies d by the value).
+    __device__ __forceinline__ double value_fast(const double* __restrict__ xa, const double* __restrict__ xb, double hil2,
+                                                 double& d, const double* __restrict__ etab) const {
+        const bool cat0 = disc_kind[0] == HLVAE_KIND_CAT;
+        if (se_col >= 0 && (ndisc == 0 || (ndisc == 1 && cat0))) {
+            d = xa[se_col] - xb[se_col];
+            const double arg = (d * -hil2) * d;
+            if (ndisc == 0) return exp_nonpos_tab_sel<false>(arg, etab, true);
+            return exp_nonpos_tab_sel<true>(arg, etab, xa[disc_col[0]] == xb[disc_col[0]]);
+        }
+        if (se_col < 0 && ndisc == 1 && cat0) {
+            d = 0.0;
+            return (xa[disc_col[0]] == xb[disc_col[0]]) ? 1.0 : 0.0;
+        }
+        return value(xa, xb, hil2, d, etab);
+    }
 };
 
 // Per-warp shared memory: covariate rows, three T x T matrices, and the hyper-parameters of this
@@ -161,18 +180,24 @@ kl_subject_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict
     __syncwarp();
     const double nz = noise[l];
     // B_s = K1(x_s, x_s) + noise I (elbo_functions.py:249-250): lower triangle, mirrored
-    {
+    {   // components outermost (descriptor and hyper-parameters in registers), lower triangle, then mirrored
         for (int t = lane; t < TL; t += 32) {
             const int ij = tri[t], i = ij >> 8, j = ij & 255;
-            double k1 = (i == j) ? nz : 0.0;
-            for (int r = 0; r < sp1.ncomp; r++) {
-                CompRegs c;
-                c.load(sp1, r);
+            if (i == j) Am[i * LDA + j] = nz;                // (off-diagonal entries were zero-filled above)
+        }
+        for (int r = 0; r < sp1.ncomp; r++) {
+            CompRegs c;
+            c.load(sp1, r);
+            const double osr = kp[24 + r], hil2 = kp[32 + r];
+            for (int t = lane; t < TL; t += 32) {
+                const int ij = tri[t], i = ij >> 8, j = ij & 255;
                 double d;
-                k1 = fma(kp[24 + r], c.value(xs + i * Q, xs + j * Q, kp[32 + r], d, etab), k1);
+                Am[i * LDA + j] = fma(osr, c.value_fast(xs + i * Q, xs + j * Q, hil2, d, etab), Am[i * LDA + j]);
             }
-            Am[i * LDA + j] = k1;
-            Am[j * LDA + i] = k1;
+        }
+        for (int t = lane; t < TL; t += 32) {
+            const int ij = tri[t], i = ij >> 8, j = ij & 255;
+            Am[j * LDA + i] = Am[i * LDA + j];
         }
     }
     __syncwarp();
@@ -294,7 +319,7 @@ kl_subject_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict
         for (int t = lane; t < TL; t += 32) {
             const int ij = tri[t], i = ij >> 8, j = ij & 255;
             double d;
-            const double v = c.value(xs + i * Q, xs + j * Q, hil2, d, etab);
+            const double v = c.value_fast(xs + i * Q, xs + j * Q, hil2, d, etab);
             const double wv = ((i == j) ? 1.0 : 2.0) * Am[i * LDA + j] * v;
             gos += wv;
             gls = fma(wv * d, d, gls);
@@ -396,7 +421,7 @@ kl_subject_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict
                     for (int u = 0; u < 2; u++) {
                         if (gq[q][u] != 0.0) {
                             double d;
-                            const double gv = gq[q][u] * c.value(xs + i * Q, xs + (j + u) * Q, hil2, d, etab);
+                            const double gv = gq[q][u] * c.value_fast(xs + i * Q, xs + (j + u) * Q, hil2, d, etab);
                             gos += gv;
                             gls = fma(gv * d, d, gls);
                         }
