@@ -487,7 +487,8 @@ struct PanelSmem {
                                       (size_t)MP * HLVAE_MAX_COMPS /*zacc*/ + 4 * HLVAE_MAX_COMPS + 8 /*hyper acc + A*/ +
                                       8 * HLVAE_MAX_COMPS /*kps, kps1*/ + HLVAE_EXP_TAB /*etab*/;
     static constexpr int n_lower_tiles = (RP / 8) * (RP / 8 + 1) / 2;
-    static constexpr size_t ints = 4 * RP + 4 * (PN_SMAX + 1) + 8 + n_lower_tiles + 2 * (PN_CHUNK_CSR + 1);
+    static constexpr int n_s_tiles = (MP / 8) * (MP / 8 + 1) / 2;
+    static constexpr size_t ints = 4 * RP + 4 * (PN_SMAX + 1) + 8 + n_lower_tiles + n_s_tiles + 2 * (PN_CHUNK_CSR + 1);
     static constexpr size_t bytes = doubles * 8 + ints * 4;
 };
 
@@ -509,8 +510,11 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
     constexpr int LDB = SM::LDB;
     constexpr int PN_THREADS = NT;
     constexpr int WGI = NT / 128;               // warp grid: WGI x 4
-    constexpr int SIR = (MP / 8) / WGI;         // S tiles (8x8) per warp, rows
-    constexpr int SIC = (MP / 8) / 4;           // S tiles per warp, columns
+    // S = sum K0xz^T B^-1 K0xz is symmetric: only the 8x8 tiles on or below the diagonal are accumulated (36 of 64
+    // at M = 64, 136 of 256 at M = 128), handed out to the warps in runs of the row-major order so that consecutive
+    // tiles of a warp mostly share their row; the flush mirrors the off-diagonal tiles.
+    constexpr int SNT = (MP / 8) * (MP / 8 + 1) / 2;            // lower tiles of S
+    constexpr int SPW = (SNT + NT / 32 - 1) / (NT / 32);        // tiles per warp
     constexpr int WR = (RP / 8 + WGI - 1) / WGI;   // row tiles per warp for [RP x MP] outputs (the last warp row may own fewer)
     constexpr int WC = (MP / 8) / 4;            // col tiles per warp for [RP x MP] outputs
     constexpr int NGRP = PN_THREADS / MP;       // row groups in the element-wise phases
@@ -518,7 +522,7 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
     constexpr int TM_COLS = (NT / 128) * PN_TMEM_COLS_PER_GROUP;                       // TMEM columns of this CTA
     constexpr int NCT = (PN_TMEM_COLS_PER_GROUP / (2 * RPT)) < HLVAE_MAX_COMPS
                             ? (PN_TMEM_COLS_PER_GROUP / (2 * RPT)) : HLVAE_MAX_COMPS;  // components cached in TMEM
-    static_assert(WR >= 1 && WC >= 1 && SIR >= 1 && SIC >= 1 && RPT >= 2 && RPT % 2 == 0 && RP % NGRP == 0, "tile shape");
+    static_assert(WR >= 1 && WC >= 1 && SPW >= 1 && RPT >= 2 && RPT % 2 == 0 && RP % NGRP == 0, "tile shape");
     static_assert(NT / 32 >= RP / 8, "one warp per row tile in the r = K0xz w - mu product");
     static_assert(TM_COLS == 256 || TM_COLS == 512, "TMEM allocation: a power of two");
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -545,7 +549,8 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
     int* sub_b0_b = sub_r0_b + 2 * (PN_SMAX + 1);              // [2][PN_SMAX+1] offsets of the T x T blocks
     int* meta = sub_b0_b + 2 * (PN_SMAX + 1);                  // [0,1] subjects, [2,3] first subject, [4] cursor, [5] TMEM base
     int* tl_tab = meta + 8;                                    // (row tile << 8 | column tile) of the lower triangle
-    int* csr_r = tl_tab + SM::n_lower_tiles;                   // subj_ptr[s_begin ..] of this chunk
+    int* s_tab = tl_tab + SM::n_lower_tiles;                   // the same for the M x M tiles of S
+    int* csr_r = s_tab + SM::n_s_tiles;                        // subj_ptr[s_begin ..] of this chunk
     int* csr_t = csr_r + PN_CHUNK_CSR + 1;                     // tt_ptr[s_begin ..]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -566,6 +571,8 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
     if (warp == 0) tmem_alloc<TM_COLS>(reinterpret_cast<uint32_t*>(meta + 5));
     for (int i = tid; i < RP / 8; i += PN_THREADS)
         for (int j = 0; j <= i; j++) tl_tab[i * (i + 1) / 2 + j] = (i << 8) | j;
+    for (int i = tid; i < MP / 8; i += PN_THREADS)
+        for (int j = 0; j <= i; j++) s_tab[i * (i + 1) / 2 + j] = (i << 8) | j;
     for (int i = tid; i <= PN_CHUNK_CSR && s_begin + i <= s_end; i += PN_THREADS) {
         csr_r[i] = subj_ptr[s_begin + i];
         csr_t[i] = tt_ptr[s_begin + i];
@@ -607,11 +614,9 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
     }
     const double* Gl = G + (int64_t)l * M * M;
 
-    double sacc[SIR][SIC][2];
+    double sacc[SPW][2];
 #pragma unroll
-    for (int a = 0; a < SIR; a++)
-#pragma unroll
-        for (int b = 0; b < SIC; b++) sacc[a][b][0] = sacc[a][b][1] = 0.0;
+    for (int t = 0; t < SPW; t++) sacc[t][0] = sacc[t][1] = 0.0;
     double p_acc = 0.0, gw_acc = 0.0, a_acc = 0.0;
     // gradient sums of the cached K0 components, kept per thread over the CTA's whole chunk (reduced once at the end)
     double hg0[PN_NCACHE > 0 ? PN_NCACHE : 1], hg1[PN_NCACHE > 0 ? PN_NCACHE : 1], hg2[PN_NCACHE > 0 ? PN_NCACHE : 1];
@@ -887,20 +892,32 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
                 }
             }
         }
-        // ---- P3b: S += K0xz^T V on the FP64 tensor pipe (:161 / :254,266)
+        // ---- P3b: S += K0xz^T V on the FP64 tensor pipe (:161 / :254,266), lower tiles only
         {
             const int R4 = (R + 3) & ~3;
             const int kr = lane & 3, kc = lane >> 2;
+            int ao[SPW], bo[SPW];                                       // column offsets of this warp's tiles in Kb / Vb
+            bool live[SPW], newrow[SPW];
+#pragma unroll
+            for (int t = 0; t < SPW; t++) {
+                const int tp = warp * SPW + t;
+                live[t] = tp < SNT;
+                const int rc = s_tab[live[t] ? tp : 0];
+                ao[t] = (rc >> 8) * 8 + kc;
+                bo[t] = (rc & 255) * 8 + kc;
+                newrow[t] = t == 0 || ao[t] != ao[t - 1];
+            }
             for (int k0 = 0; k0 < R4; k0 += 4) {
-                double af[SIR], bf[SIC];
+                const double* kr_ = Kb + (k0 + kr) * LD;
+                const double* vr_ = Vb + (k0 + kr) * LD;
+                double af = 0.0;
 #pragma unroll
-                for (int t = 0; t < SIR; t++) af[t] = Kb[(k0 + kr) * LD + (wi * SIR + t) * 8 + kc];
-#pragma unroll
-                for (int t = 0; t < SIC; t++) bf[t] = Vb[(k0 + kr) * LD + (wj * SIC + t) * 8 + kc];
-#pragma unroll
-                for (int a = 0; a < SIR; a++)
-#pragma unroll
-                    for (int b = 0; b < SIC; b++) dmma884(sacc[a][b][0], sacc[a][b][1], af[a], bf[b]);
+                for (int t = 0; t < SPW; t++) {
+                    if (live[t]) {
+                        if (newrow[t]) af = kr_[ao[t]];                 // the A fragment serves every tile of its row
+                        dmma884(sacc[t][0], sacc[t][1], af, vr_[bo[t]]);
+                    }
+                }
             }
         }
         __syncthreads();
@@ -1158,15 +1175,20 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
         double* Sg = acc + off.o[HLVAE_ACC_S] + (int64_t)l * M * M;
         const int cr = lane >> 2, cc = 2 * (lane & 3);
 #pragma unroll
-        for (int a = 0; a < SIR; a++)
+        for (int t = 0; t < SPW; t++) {
+            const int tp = warp * SPW + t;
+            if (tp < SNT) {
+                const int rc = s_tab[tp], ta = rc >> 8, tb = rc & 255;
+                const int i = ta * 8 + cr, j = tb * 8 + cc;
 #pragma unroll
-            for (int b = 0; b < SIC; b++) {
-                int i = (wi * SIR + a) * 8 + cr, j = (wj * SIC + b) * 8 + cc;
-                if (i < M) {
-                    if (j < M) atomicAdd(Sg + (int64_t)i * M + j, sacc[a][b][0]);
-                    if (j + 1 < M) atomicAdd(Sg + (int64_t)i * M + j + 1, sacc[a][b][1]);
+                for (int u = 0; u < 2; u++) {
+                    if (i < M && j + u < M) {
+                        atomicAdd(Sg + (int64_t)i * M + j + u, sacc[t][u]);
+                        if (ta != tb) atomicAdd(Sg + (int64_t)(j + u) * M + i, sacc[t][u]);     // the mirrored tile
+                    }
                 }
             }
+        }
         // every row group holds a partial sum of its inducing point: summed in a fixed order through shared memory
         // (the row panels are free by now), then one atomic per inducing point and CTA
         Kb[eg * MP + em] = p_acc;
@@ -1245,17 +1267,25 @@ int dispatch_panel(int M, const hlvae_kspec_t* spec0, const double* os0, const d
     return launch_panel<MP, RP, GS, NT, NC, TS>(spec0, os0, ls0, spec1, os1, ls1, L, Q, M, x, ldx, z, row_idx, subj_ptr,     \
                                         tt_ptr, n_subj, subj_per_chunk, mu, ld_mu, w, G, binv, tt_total, acc, off,   \
                                         g_mu, qdiag, gscale, status, st)
-    // Shapes: one 512-thread CTA per SM walking 64-row panels, or (32 < M <= 64, row_panel = 40) two 256-thread
-    // CTAs per SM walking 40-row panels - two CTAs cover each other's barrier and latency stalls, which pays when
-    // whole subjects fill 40 rows about as well as 64 (T = 20: 2 of 2 against 3 of 3.2; measured 1.32 against
-    // 1.40 ms at configs[1]).  Measured and dropped: 256 threads with 32-row panels (+9 %: one T = 20 subject per
-    // panel), 48-row panels (+10 %), 1024 threads at 64 registers (+18 %: spills, per-thread set-up doubled).
-    if (M <= 32) { HLVAE_PANEL(32, 64, true, 512, 3); }
+    // Shapes (row_panel = rows per panel, 0 = the default of the M class; measured at 16 000 rows, T = 20):
+    //   M <= 32 : two 256-thread CTAs per SM, 64-row panels (0.52 ms against 0.67 ms for one 512-thread CTA);
+    //   M <= 64 : two 256-thread CTAs per SM walking 40-row panels (they cover each other's barrier and latency
+    //             stalls; 0.94 ms) when whole subjects fill 40 rows about as well as 64 (T = 20: 2 of 2 against 3 of
+    //             3.2), else one 512-thread CTA with 64-row panels (1.05 ms);
+    //   M <= 128: one 512-thread CTA, 64- / 48- / 32-row panels (M = 120: 2.56 / 3.10 / 4.16 ms - the shared memory
+    //             the component values left when they moved to tensor memory pays for the larger panels).
+    // Measured and dropped: 256 threads with 32-row panels at M = 64 (+9 %), 48-row panels at M = 64 (+10 %), 1024
+    // threads at 64 registers (+18 %: spills, per-thread set-up doubled), G in shared memory at M = 64 (one CTA per SM).
+    if (M <= 32) { HLVAE_PANEL(32, 64, true, 256, 3); }
     if (M <= 64) {
         if (row_panel == 40) { HLVAE_PANEL(64, 40, false, 256, 3); }
         HLVAE_PANEL(64, 64, false, 512, 3);
     }
-    if (M <= 128) { HLVAE_PANEL(128, 32, false, 512, 3); }
+    if (M <= 128) {
+        if (row_panel == 32) { HLVAE_PANEL(128, 32, false, 512, 3); }
+        if (row_panel == 48) { HLVAE_PANEL(128, 48, false, 512, 3); }
+        HLVAE_PANEL(128, 64, false, 512, 3);
+    }
 #undef HLVAE_PANEL
     return HLVAE_E_UNSUPPORTED;
 }

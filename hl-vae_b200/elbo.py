@@ -220,32 +220,44 @@ def minibatch_KLD_upper_bound_iter(covar_module0, covar_module1, likelihood, lat
                 P / P_in_current_batch, latent_dim * N / 2, natural_gradient, eps, (1,))
 
 
-PANEL_COST_40 = 0.63      # device time of a 40-row panel (two CTAs per SM) relative to a 64-row one, measured (T = 20)
+PANEL_COST_40 = 0.60      # device time of a 40-row panel (two CTAs per SM) relative to a 64-row one, measured (T = 20)
+PANEL_COST_M128 = {32: 5.2, 48: 7.75, 64: 9.6}     # relative device time of a panel at 64 < M <= 128, measured (T = 20)
 
 
 def _row_panel(layout, M):
-    """Rows per panel for hlvae_kl_panel: 0 = the library's default shape for M; 40 = the two-CTAs-per-SM shape
-    (32 < M <= 64), chosen when the subjects of this minibatch need so few more 40-row panels than 64-row ones
-    that the cheaper panel wins (fixed T = 20: 2 subjects per 40 rows against 3 per 64)."""
+    """Rows per panel for hlvae_kl_panel, chosen per minibatch from how its whole subjects pack (host arithmetic on
+    the lengths): M <= 32 -> 64; 32 < M <= 64 -> 40 (the two-CTAs-per-SM shape) when the subjects need so few more
+    40-row panels than 64-row ones that the cheaper panel wins (fixed T = 20: 2 subjects per 40 rows against 3 per
+    64), else 64; 64 < M <= 128 -> the cheapest of 32 / 48 / 64."""
     import os
     forced = os.environ.get("HLVAE_PANEL_RP")
     if forced is not None:
         return int(forced)
-    if not (32 < M <= 64) or layout.t_max > 40 or layout.n_subj == 0:
-        return 0
-    return 40 if layout.panels(40) * PANEL_COST_40 < layout.panels(64) else 0
+    if M <= 32 or layout.n_subj == 0:
+        return 64
+    if M <= 64:
+        if layout.t_max > 40:
+            return 64
+        return 40 if layout.panels(40) * PANEL_COST_40 < layout.panels(64) else 64
+    fits = [rp for rp in (32, 48, 64) if rp >= layout.t_max] or [64]
+    return min(fits, key=lambda rp: layout.panels(rp) * PANEL_COST_M128[rp])
+
+
+def _two_ctas_per_sm(M, rp):
+    return M <= 32 or (M <= 64 and rp == 40)
 
 
 def _subjects_per_chunk(n_subj, t_max, L, M, waves=None, rp=0):
-    """Subjects per hlvae_kl_panel CTA.  A CTA walks its chunk in row panels of RP rows (64 for M <= 64, else 32; 40
-    in the two-CTAs-per-SM shape) that hold whole subjects, so a chunk should be a whole number of full panels (a
+    """Subjects per hlvae_kl_panel CTA.  A CTA walks its chunk in row panels of `rp` rows (see _row_panel) that hold
+    whole subjects, so a chunk should be a whole number of full panels (a
     trailing panel with one subject costs nearly as much as a full one), and L * n_chunks CTAs should fill a whole
     number of waves of resident CTAs."""
     import os
-    two = rp == 40
-    rp = rp or (64 if M <= 64 else 32)
+    rp = rp or 64
+    two = _two_ctas_per_sm(M, rp)
     spp = max(1, rp // max(int(t_max), 1))                    # subjects per full panel
-    waves = int(os.environ.get("HLVAE_PANEL_WAVES", waves or (2 * PANEL_WAVES if two else PANEL_WAVES)))
+    # (measured: 8 waves for the two-CTA shape at M = 64, 4 waves everywhere else incl. the two-CTA shape at M <= 32)
+    waves = int(os.environ.get("HLVAE_PANEL_WAVES", waves or (2 * PANEL_WAVES if (two and M > 32) else PANEL_WAVES)))
     n_panels = (n_subj + spp - 1) // spp
     # at least `waves` waves of CTAs, and no more than ~30 panels per CTA (large batches: more, shorter CTAs balance
     # the tail better - measured at 64 000 rows)

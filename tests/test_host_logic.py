@@ -119,7 +119,7 @@ def test_panel_chunks_are_whole_panels():
     for n_subj, t_max, L, M in ((1, 20, 32, 64), (7, 20, 32, 64), (200, 20, 32, 64), (800, 20, 32, 64), (3200, 20, 32, 64),
                                 (800, 5, 8, 32), (800, 32, 32, 128), (513, 13, 4, 64)):
         spc = elbo._subjects_per_chunk(n_subj, t_max, L, M)
-        rp = 64 if M <= 64 else 32
+        rp = 64
         spp = max(1, rp // t_max)
         assert spc >= 1 and spc % spp == 0
         n_chunks = (n_subj + spc - 1) // spc
