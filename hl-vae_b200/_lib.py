@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # HLVAE_B200_LIB: load another build of the same sources (A/B runs of kernel variants); default = the in-tree build
 LIB_PATH = os.environ.get("HLVAE_B200_LIB") or os.path.join(_HERE, "lib", "libhlvae_b200.so")
 
-MAX_COMPS, MAX_DISC, MAX_Q, TMAX, MAX_CLASS, MAX_Y = 8, 3, 8, 32, 16, 16
+MAX_COMPS, MAX_DISC, MAX_Q, TMAX, MAX_CLASS, MAX_Y = 8, 3, 8, 64, 16, 16
 HEAD_AFFINE, HEAD_SIGMOID, HEAD_ZERO, HEAD_BIAS = 0, 1, 2, 3
 F32, F64, U8 = 0, 1, 2
 KIND_CAT, KIND_BIN = 1, 2

@@ -24,6 +24,7 @@ struct AccOff {
 // kl_subject_k
 // =====================================================================================
 constexpr int SJ_WARPS = 2;
+constexpr int SJ_TW = 32;     // longest subject of the warp-per-pair kernel (a subject's rows are the lanes of a warp)
 
 // One component's descriptor pulled into registers field by field (a struct copy indexed by a
 // run-time component number would be placed in local memory).
@@ -105,7 +106,7 @@ struct SubjShape {
     static constexpr int LDA = TP + 4;
     static constexpr int NT = TP / 8;
     static constexpr int NTRI = TP * (TP + 1) / 2;
-    static constexpr int per_warp = HLVAE_TMAX * HLVAE_MAX_Q + 2 * TP * LDA + TP + SJ_KP;
+    static constexpr int per_warp = SJ_TW * HLVAE_MAX_Q + 2 * TP * LDA + TP + SJ_KP;
     // per CTA: exp table, then the (i, j) pairs of the lower-triangle walk (16 bits each)
     static constexpr int shared_doubles = (HLVAE_EXP_TAB + (NTRI + 3) / 4 + 1) & ~1;   // even: 16-byte aligned rows
     static constexpr int min_blocks = TP <= 24 ? 8 : 4;
@@ -127,7 +128,7 @@ kl_subject_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict
     double* etab = smem;
     unsigned short* tri = reinterpret_cast<unsigned short*>(smem + HLVAE_EXP_TAB);   // element t -> (i << 8) | j
     double* xs = smem + S2::shared_doubles + (size_t)warp * S2::per_warp;
-    double* Am = xs + HLVAE_TMAX * HLVAE_MAX_Q;        // B -> L -> B^-1
+    double* Am = xs + SJ_TW * HLVAE_MAX_Q;             // B -> L -> B^-1
     double* Bm = Am + TP * LDA;                         // L^-1 -> K0ss / Ktil -> X
     double* dinv = Bm + TP * LDA;                       // 1 / L_jj
     double* kp = dinv + TP;
@@ -143,7 +144,8 @@ kl_subject_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict
     const int r0 = subj_ptr[s];
     const int T = subj_ptr[s + 1] - r0;
     if (T <= 0) continue;
-    if (T > TP || T > HLVAE_TMAX) {
+    if (T > SJ_TW && T <= HLVAE_TMAX) continue;         // kl_subject_big_k's
+    if (T > TP) {
         if (lane == 0) report_status(status, HLVAE_STATUS_T_TOO_LARGE, l, s);
         continue;
     }
@@ -446,6 +448,256 @@ kl_subject_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict
     }   // pairs
 }
 
+// =====================================================================================
+// kl_subject_big_k: the same per-(subject, latent dim) work for subjects of 33 .. HLVAE_TMAX rows, which do not fit
+// the lanes of one warp: one CTA of SB_THREADS threads per pair, the three T x T matrices in shared memory, thread =
+// row in the factorisation (two barriers per column), thread = entries (i, j) in the products.  Plain FP64 FMAs -
+// long subjects are the exception (the reference's Python loop, elbo_functions.py:243-266, takes any length), so this
+// path is built for correctness first; the shipped data sets (T = 20) never reach it.
+// =====================================================================================
+constexpr int SB_THREADS = 128;
+constexpr int SB_LD = HLVAE_TMAX + 1;      // odd leading dimension: conflict-free rows and columns
+constexpr size_t SB_SMEM_DOUBLES = (size_t)HLVAE_TMAX * HLVAE_MAX_Q + 3 * (size_t)HLVAE_TMAX * SB_LD + 2 * HLVAE_TMAX +
+                                   SJ_KP + HLVAE_EXP_TAB + 2 * (SB_THREADS / 32) + 2;
+
+__device__ __forceinline__ double block_sum(double v, double* red, int tid) {   // every thread gets the sum
+    v = warp_sum(v);
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = v;
+    __syncthreads();
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < SB_THREADS / 32; w++) s += red[w];
+    return s;
+}
+
+template <typename TS>
+__global__ void __launch_bounds__(SB_THREADS)
+kl_subject_big_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__ os0, const double* __restrict__ ls0,
+                 const __grid_constant__ hlvae_kspec_t sp1, const double* __restrict__ os1, const double* __restrict__ ls1,
+                 const double* __restrict__ noise, int L, int Q, const double* __restrict__ x, int64_t ldx,
+                 const int32_t* __restrict__ row_idx, const int32_t* __restrict__ subj_ptr,
+                 const int32_t* __restrict__ tt_ptr, int n_subj, const TS* __restrict__ log_v, int64_t ld_lv,
+                 double* __restrict__ binv, int64_t tt_total, double* __restrict__ acc, const AccOff off,
+                 TS* __restrict__ g_logv, double gscale, int32_t* __restrict__ status) {
+    extern __shared__ __align__(16) double smem[];
+    constexpr int LD = SB_LD;
+    double* xs = smem;                                   // [T][Q]
+    double* Am = xs + HLVAE_TMAX * HLVAE_MAX_Q;          // B -> L -> B^-1
+    double* Bm = Am + HLVAE_TMAX * LD;                   // L^-1 -> K0ss / Ktil
+    double* Cm = Bm + HLVAE_TMAX * LD;                   // products
+    double* evs = Cm + HLVAE_TMAX * LD;                  // e^logv
+    double* dcol = evs + HLVAE_TMAX;                     // diagonal of L
+    double* kp = dcol + HLVAE_TMAX;                      // hyper-parameters, as in kl_subject_k
+    double* etab = kp + SJ_KP;
+    double* red = etab + HLVAE_EXP_TAB;
+    int* flag = reinterpret_cast<int*>(red + SB_THREADS / 32);
+    const int tid = threadIdx.x;
+    exp2_table_fill(etab, tid, SB_THREADS);
+    const int64_t n_pairs = (int64_t)n_subj * L;
+    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+        const int s = (int)(pair / L), l = (int)(pair % L);
+        const int r0 = subj_ptr[s];
+        const int T = subj_ptr[s + 1] - r0;
+        if (T <= SJ_TW) continue;                        // kl_subject_k's
+        if (T > HLVAE_TMAX) {
+            if (tid == 0) report_status(status, HLVAE_STATUS_T_TOO_LARGE, l, s);
+            continue;
+        }
+        __syncthreads();                                 // the previous pair is done with shared memory
+        int g = -1;
+        double lv = 0.0;
+        if (tid < T) {
+            g = row_idx[r0 + tid];
+            for (int q = 0; q < Q; q++) xs[tid * Q + q] = x[(int64_t)g * ldx + q];
+            lv = (double)log_v[(int64_t)g * ld_lv + l];
+            evs[tid] = exp(lv);
+        }
+        if (tid < 2 * HLVAE_MAX_COMPS) {
+            const int which = tid >> 3, r = tid & 7;
+            const int nc = which ? sp1.ncomp : sp0.ncomp;
+            double o = 0.0, h = 0.0, i3 = 0.0;
+            if (r < nc) {
+                o = (which ? os1 : os0)[(int64_t)r * L + l];
+                const double e_ = (which ? ls1 : ls0)[(int64_t)r * L + l];
+                const double i2 = 1.0 / (e_ * e_);
+                h = 0.5 * i2;
+                i3 = i2 / e_;
+            }
+            kp[which * 24 + r] = o;
+            kp[which * 24 + 8 + r] = h;
+            kp[which * 24 + 16 + r] = i3;
+        }
+        if (tid == 0) *flag = 0;
+        __syncthreads();
+        const double nz = noise[l];
+        // ---- B_s = K1(x_s, x_s) + noise I (elbo_functions.py:249-250)
+        for (int e = tid; e < T * T; e += SB_THREADS) {
+            const int i = e / T, j = e - i * T;
+            if (j > i) continue;
+            double k1 = (i == j) ? nz : 0.0;
+            for (int r = 0; r < sp1.ncomp; r++) {
+                CompRegs c;
+                c.load(sp1, r);
+                double d;
+                k1 = fma(kp[24 + r], c.value_fast(xs + i * Q, xs + j * Q, kp[32 + r], d, etab), k1);
+            }
+            Am[i * LD + j] = k1;
+            Am[j * LD + i] = k1;
+        }
+        __syncthreads();
+        // ---- Cholesky (:251), left-looking: thread i owns row i
+        for (int j = 0; j < T; j++) {
+            double sum = 0.0;
+            if (tid >= j && tid < T) {
+                sum = Am[tid * LD + j];
+                for (int k = 0; k < j; k++) sum = fma(-Am[tid * LD + k], Am[j * LD + k], sum);
+                if (tid == j) {
+                    if (!(sum > 0.0)) *flag = 1;
+                    dcol[j] = sqrt(sum);
+                }
+            }
+            __syncthreads();
+            if (tid >= j && tid < T) Am[tid * LD + j] = (tid == j) ? dcol[j] : sum / dcol[j];
+            __syncthreads();
+        }
+        if (*flag) {
+            if (tid == 0) report_status(status, HLVAE_STATUS_NOT_PD, l, s);
+            continue;
+        }
+        // C term (:258)
+        const double logdet = block_sum(tid < T ? 2.0 * log(dcol[tid]) : 0.0, red, tid);
+        // ---- L^-1: thread c solves L y = e_c down its own column of Bm
+        if (tid < T) {
+            const int c = tid;
+            for (int i = 0; i < T; i++) {
+                double y = 0.0;
+                if (i >= c) {
+                    double a = (i == c) ? 1.0 : 0.0;
+                    for (int k = c; k < i; k++) a = fma(-Am[i * LD + k], Bm[k * LD + c], a);
+                    y = a / dcol[i];
+                }
+                Bm[i * LD + c] = y;
+            }
+        }
+        __syncthreads();
+        // ---- B^-1 = L^-T L^-1 (:252) -> Cm, then over Am and out to global memory
+        double* bout = binv + (int64_t)l * tt_total + tt_ptr[s];
+        for (int e = tid; e < T * T; e += SB_THREADS) {
+            const int i = e / T, j = e - i * T;
+            if (j > i) continue;
+            double a = 0.0;
+            for (int k = i; k < T; k++) a = fma(Bm[k * LD + i], Bm[k * LD + j], a);
+            Cm[i * LD + j] = a;
+            Cm[j * LD + i] = a;
+        }
+        __syncthreads();
+        for (int e = tid; e < T * T; e += SB_THREADS) {
+            const int i = e / T, j = e - i * T;
+            const double v = Cm[i * LD + j];
+            Am[i * LD + j] = v;
+            bout[e] = v;
+        }
+        __syncthreads();
+        // ---- K0(x_s, x_s) (:248) into Bm; B + D1 terms (:257,259) and the K0 hyper-gradients (dJ/dK0ss = B^-1 / 2)
+        for (int e = tid; e < T * T; e += SB_THREADS) Bm[(e / T) * LD + e % T] = 0.0;
+        __syncthreads();
+        double bd = 0.0;
+        for (int r = 0; r < sp0.ncomp; r++) {
+            CompRegs c;
+            c.load(sp0, r);
+            const double osr = kp[r], hil2 = kp[8 + r], il3 = kp[16 + r];
+            double gos = 0.0, gls = 0.0;
+            for (int e = tid; e < T * T; e += SB_THREADS) {
+                const int i = e / T, j = e - i * T;
+                double d;
+                const double v = c.value_fast(xs + i * Q, xs + j * Q, hil2, d, etab);
+                const double wv = Am[i * LD + j] * v;
+                gos += wv;
+                gls = fma(wv * d, d, gls);
+                Bm[i * LD + j] = fma(osr, v, Bm[i * LD + j]);
+            }
+            gos = block_sum(gos, red, tid);
+            gls = block_sum(gls, red, tid);
+            bd = fma(osr, gos, bd);
+            if (tid == 0) {
+                atomicAdd(acc + off.o[HLVAE_ACC_GOS0] + (int64_t)r * L + l, 0.5 * gos);
+                if (c.se_col >= 0) atomicAdd(acc + off.o[HLVAE_ACC_GLS0] + (int64_t)r * L + l, 0.5 * gls * osr * il3);
+            }
+        }
+        __syncthreads();
+        double bdiag = 0.0;
+        if (tid < T) {   // Ktil = K0ss + diag(e^logv); its B term and the log-variance gradient
+            const double bii = Am[tid * LD + tid], ev = evs[tid];
+            Bm[tid * LD + tid] += ev;
+            bdiag = bii * ev;
+            g_logv[(int64_t)g * L + l] = (TS)(gscale * 0.5 * (bii * ev - 1.0));
+        }
+        bd += block_sum(bdiag, red, tid);
+        // ---- X = Ktil B^-1 -> Cm
+        for (int e = tid; e < T * T; e += SB_THREADS) {
+            const int i = e / T, j = e - i * T;
+            double a = 0.0;
+            for (int k = 0; k < T; k++) a = fma(Bm[i * LD + k], Am[k * LD + j], a);
+            Cm[i * LD + j] = a;
+        }
+        __syncthreads();
+        // ---- dJ/dB_s (part without K0xz) = 1/2 (B^-1 - B^-1 Ktil B^-1) -> Bm, contracted with dB/d(theta1)
+        for (int e = tid; e < T * T; e += SB_THREADS) {
+            const int i = e / T, j = e - i * T;
+            double a = 0.0;
+            for (int k = 0; k < T; k++) a = fma(Am[i * LD + k], Cm[k * LD + j], a);
+            Bm[i * LD + j] = 0.5 * (Am[i * LD + j] - a);
+        }
+        __syncthreads();
+        for (int r = 0; r < sp1.ncomp; r++) {
+            CompRegs c;
+            c.load(sp1, r);
+            const double osr = kp[24 + r], hil2 = kp[32 + r], il3 = kp[40 + r];
+            double gos = 0.0, gls = 0.0;
+            for (int e = tid; e < T * T; e += SB_THREADS) {
+                const int i = e / T, j = e - i * T;
+                double d;
+                const double gv = Bm[i * LD + j] * c.value_fast(xs + i * Q, xs + j * Q, hil2, d, etab);
+                gos += gv;
+                gls = fma(gv * d, d, gls);
+            }
+            gos = block_sum(gos, red, tid);
+            gls = block_sum(gls, red, tid);
+            if (tid == 0) {
+                atomicAdd(acc + off.o[HLVAE_ACC_GOS1] + (int64_t)r * L + l, gos);
+                if (c.se_col >= 0) atomicAdd(acc + off.o[HLVAE_ACC_GLS1] + (int64_t)r * L + l, gls * osr * il3);
+            }
+        }
+        const double fsum = block_sum(lv, red, tid);
+        if (tid == 0) {
+            double* scal = acc + off.o[HLVAE_ACC_SCAL] + (int64_t)l * HLVAE_NSCAL;
+            atomicAdd(scal + 1, bd);
+            atomicAdd(scal + 2, logdet);
+            atomicAdd(scal + 3, fsum);
+        }
+    }
+}
+
+template <typename TS>
+int launch_subject_big(const hlvae_kspec_t* spec0, const double* os0, const double* ls0, const hlvae_kspec_t* spec1,
+                       const double* os1, const double* ls1, const double* noise, int L, int Q, const double* x,
+                       int64_t ldx, const int32_t* row_idx, const int32_t* subj_ptr, const int32_t* tt_ptr, int n_subj,
+                       const void* log_v, int64_t ld_lv, double* binv, int64_t tt_total, double* acc, const AccOff& off,
+                       void* g_logv, double gscale, int32_t* status, cudaStream_t st) {
+    const size_t smem = SB_SMEM_DOUBLES * sizeof(double);
+    auto kern = kl_subject_big_k<TS>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    const int64_t pairs = (int64_t)n_subj * L;
+    const unsigned grid = (unsigned)(pairs < 148 * 8 ? pairs : 148 * 8);
+    kern<<<grid, SB_THREADS, smem, st>>>(*spec0, os0, ls0, *spec1, os1, ls1, noise, L, Q, x, ldx, row_idx, subj_ptr,
+                                         tt_ptr, n_subj, (const TS*)log_v, ld_lv, binv, tt_total, acc, off, (TS*)g_logv,
+                                         gscale, status);
+    HLVAE_CHECK_LAUNCH();
+    return 0;
+}
+
 template <int TP, typename TS>
 int launch_subject(const hlvae_kspec_t* spec0, const double* os0, const double* ls0, const hlvae_kspec_t* spec1,
                     const double* os1, const double* ls1, const double* noise, int L, int Q, const double* x,
@@ -649,7 +901,7 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
             const int s = s0 + lane;
             const bool valid = lane < PN_SMAX && s < s_end;
             T = valid ? rows_at(s + 1) - rows_at(s) : 0;
-            const bool big = T > HLVAE_TMAX;                   // reported by kl_subject_k as well; skipped here
+            const bool big = T > HLVAE_TMAX || T > RP;         // cannot be packed: skipped and reported
             incl = T;
             incl2 = T * T;
 #pragma unroll
@@ -659,7 +911,11 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
             }
             const unsigned okm = __ballot_sync(0xffffffffu, valid && !big && incl <= RP);
             ns = __ffs(~okm) - 1;                              // the leading run of subjects that fit (lanes >= PN_SMAX never do)
-            if (ns == 0 && (__ballot_sync(0xffffffffu, big) & 1u)) { s0++; continue; }
+            if (ns == 0 && (__ballot_sync(0xffffffffu, big) & 1u)) {
+                if (lane == 0) report_status(status, HLVAE_STATUS_T_TOO_LARGE, l, s0);
+                s0++;
+                continue;
+            }
             break;
         }
         if (lane < ns) {
@@ -1335,6 +1591,16 @@ extern "C" int hlvae_kl_subject(const hlvae_kspec_t* spec0, const double* os0, c
                : launch_subject<TP, float>(spec0, os0, ls0, spec1, os1, ls1, noise, L, Q, x, ldx, row_idx, subj_ptr,  \
                                             tt_ptr, n_subj, log_v, ld_lv, binv, tt_total, acc, off, g_logv, gscale,   \
                                             status, st)
+    if (t_cap > SJ_TW) {     // subjects of 33 .. HLVAE_TMAX rows: CTA per pair (each kernel skips the other's subjects)
+        const int rc = dtype == HLVAE_F64
+                           ? launch_subject_big<double>(spec0, os0, ls0, spec1, os1, ls1, noise, L, Q, x, ldx, row_idx,
+                                                        subj_ptr, tt_ptr, n_subj, log_v, ld_lv, binv, tt_total, acc, off,
+                                                        g_logv, gscale, status, st)
+                           : launch_subject_big<float>(spec0, os0, ls0, spec1, os1, ls1, noise, L, Q, x, ldx, row_idx,
+                                                       subj_ptr, tt_ptr, n_subj, log_v, ld_lv, binv, tt_total, acc, off,
+                                                       g_logv, gscale, status, st);
+        if (rc != 0) return rc;
+    }
     if (t_cap <= 8) { HLVAE_SUBJ2(8); }
     if (t_cap <= 16) { HLVAE_SUBJ2(16); }
     if (t_cap <= 24) { HLVAE_SUBJ2(24); }

@@ -35,7 +35,7 @@ extern "C" {
 #define HLVAE_MAX_COMPS 8   /* additive components per kernel                      */
 #define HLVAE_MAX_DISC 3    /* categorical / binary factors per component          */
 #define HLVAE_MAX_Q 8       /* covariate columns                                   */
-#define HLVAE_TMAX 32       /* rows per subject handled by the per-subject kernels */
+#define HLVAE_TMAX 64       /* rows per subject (T <= 32: warp per (subject, latent dim); 33..64: CTA per pair) */
 
 #define HLVAE_F32 0
 #define HLVAE_F64 1

@@ -83,6 +83,21 @@ def test_against_oracle(L, M, n_subj, T, ragged, device):
     print((L, M, n_subj, T), {k: f"{v:.1e}" for k, v in errs.items()})
 
 
+@pytest.mark.parametrize("L,M,n_subj,T,ragged", [(3, 64, 6, 64, False), (4, 32, 14, 64, True), (2, 120, 8, 48, True),
+                                                 (3, 64, 9, 33, False)])
+def test_long_subjects_against_oracle(L, M, n_subj, T, ragged, device):
+    """Subjects of 33 .. 64 rows (HLVAE_TMAX): the CTA-per-pair kernel next to the warp-per-pair one (ragged batches
+    mix both), 64-row panels.  The reference's loop (elbo_functions.py:243-266) takes any subject length."""
+    errs = h.check_kl_vs_oracle(device, L, M, n_subj, T, seed=300 + M + T, tol=1e-6, hyper_tol=1e-4, ragged=ragged)
+    print((L, M, n_subj, T), {k: f"{v:.1e}" for k, v in errs.items()})
+
+
+def test_too_long_subject_raises(device):
+    inp = h.make_kl_inputs(2, 16, 3, 70, seed=5, ragged=False)
+    with pytest.raises((RuntimeError, ValueError), match="rows"):
+        h.run_kl_product(inp, device)
+
+
 def test_well_conditioned_is_tight(device):
     """With few, distinct inducing points (cond(K0zz) small) the same comparison holds to 1e-9 on
     every term and gradient, which separates implementation error from the conditioning floor."""

@@ -85,8 +85,9 @@ def test_subject_layouts():
     assert a.n_subj == 2 and b.n_subj == 1 and a.row_idx.tolist() == [0, 1, 2, 3, 4] and b.row_idx.tolist() == [5]
     empty = subjects.SubjectLayout.from_lengths([], "cpu")
     assert empty.n_subj == 0 and empty.tt_total == 0
+    assert subjects.SubjectLayout.from_lengths([33, 64], "cpu").t_max == 64      # HLVAE_TMAX = 64
     with pytest.raises(RuntimeError):
-        subjects.SubjectLayout.from_lengths([33], "cpu")
+        subjects.SubjectLayout.from_lengths([65], "cpu")
 
 
 def test_var_layout_matches_oracle():
