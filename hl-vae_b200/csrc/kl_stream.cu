@@ -813,10 +813,22 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
     const int em = tid % MP;                                   // this thread's inducing point in element-wise phases
     const int eg = tid / MP;                                   // and its row group
 
-    // ---- per-CTA setup: inducing points of this latent dim (transposed), w, G
-    for (int e = tid; e < HLVAE_MAX_Q * MP; e += PN_THREADS) {
-        int q = e / MP, m = e % MP;
-        Zs[e] = (q < Q && m < M) ? z[((int64_t)l * M + m) * Q + q] : 0.0;
+    // ---- per-CTA setup: inducing points of this latent dim (transposed), w, G.  The [M, Q] block of Z is one
+    // contiguous 16-byte aligned span (whenever M Q is even): a single TMA bulk copy (cp.async.bulk + mbarrier) brings
+    // it into the not yet used K0xz buffer while the rest of the set-up runs; it is transposed from there.
+    const bool z_bulk = ((M * Q) & 1) == 0 && (reinterpret_cast<uintptr_t>(z) & 15) == 0;
+    unsigned long long* zbar = reinterpret_cast<unsigned long long*>(rho);       // (rho is first written in P3a)
+    if (z_bulk) {
+        if (tid == 0) {
+            tma_mbar_init(zbar, 1);
+            tma_mbar_expect_tx(zbar, (unsigned)(M * Q * 8));
+            tma_bulk_g2s(Kb, z + (int64_t)l * M * Q, (unsigned)(M * Q * 8), zbar);
+        }
+    } else {
+        for (int e = tid; e < HLVAE_MAX_Q * MP; e += PN_THREADS) {
+            int q = e / MP, m = e % MP;
+            Zs[e] = (q < Q && m < M) ? z[((int64_t)l * M + m) * Q + q] : 0.0;
+        }
     }
     for (int m = tid; m < MP; m += PN_THREADS) ws[m] = (m < M) ? w[(int64_t)l * M + m] : 0.0;
     exp2_table_fill(etab, tid, PN_THREADS);
@@ -879,6 +891,14 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (z_bulk) {                                              // Z has landed in Kb as [M][Q]: transpose, zero padded
+        tma_mbar_wait(zbar, 0);
+        for (int e = tid; e < HLVAE_MAX_Q * MP; e += PN_THREADS) {
+            int q = e / MP, m = e % MP;
+            Zs[e] = (q < Q && m < M) ? Kb[m * Q + q] : 0.0;
+        }
+        __syncthreads();                                       // Kb is free again; Zs is complete
+    }
     const uint32_t tmem_base = (uint32_t)meta[5];
     // this thread's private columns: lane quadrant of its warp, column block of its group of four warps
     const uint32_t tm_mine = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * PN_TMEM_COLS_PER_GROUP);
