@@ -766,7 +766,8 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
     // at M = 64, 136 of 256 at M = 128), handed out to the warps in runs of the row-major order so that consecutive
     // tiles of a warp mostly share their row; the flush mirrors the off-diagonal tiles.
     constexpr int SNT = (MP / 8) * (MP / 8 + 1) / 2;            // lower tiles of S
-    constexpr int SPW = (SNT + NT / 32 - 1) / (NT / 32);        // tiles per warp
+    constexpr int SBASE = SNT / (NT / 32), SREM = SNT % (NT / 32);   // every warp owns SBASE tiles, the first SREM one more
+    constexpr int SPW = SBASE + (SREM ? 1 : 0);                 // accumulator slots per warp
     constexpr int WR = (RP / 8 + WGI - 1) / WGI;   // row tiles per warp for [RP x MP] outputs (the last warp row may own fewer)
     constexpr int WC = (MP / 8) / 4;            // col tiles per warp for [RP x MP] outputs
     constexpr int NGRP = PN_THREADS / MP;       // row groups in the element-wise phases
@@ -1172,28 +1173,22 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
         {
             const int R4 = (R + 3) & ~3;
             const int kr = lane & 3, kc = lane >> 2;
+            // slots 0 .. SBASE-1 are live in every warp (straight-line code); only the last slot depends on the warp
+            const int t_first = warp * SBASE + min(warp, SREM);
+            const bool last_live = SREM != 0 && warp < SREM;
             int ao[SPW], bo[SPW];                                       // column offsets of this warp's tiles in Kb / Vb
-            bool live[SPW], newrow[SPW];
 #pragma unroll
             for (int t = 0; t < SPW; t++) {
-                const int tp = warp * SPW + t;
-                live[t] = tp < SNT;
-                const int rc = s_tab[live[t] ? tp : 0];
+                const int rc = s_tab[(t < SBASE || last_live) ? t_first + t : 0];
                 ao[t] = (rc >> 8) * 8 + kc;
                 bo[t] = (rc & 255) * 8 + kc;
-                newrow[t] = t == 0 || ao[t] != ao[t - 1];
             }
             for (int k0 = 0; k0 < R4; k0 += 4) {
                 const double* kr_ = Kb + (k0 + kr) * LD;
                 const double* vr_ = Vb + (k0 + kr) * LD;
-                double af = 0.0;
 #pragma unroll
-                for (int t = 0; t < SPW; t++) {
-                    if (live[t]) {
-                        if (newrow[t]) af = kr_[ao[t]];                 // the A fragment serves every tile of its row
-                        dmma884(sacc[t][0], sacc[t][1], af, vr_[bo[t]]);
-                    }
-                }
+                for (int t = 0; t < SBASE; t++) dmma884(sacc[t][0], sacc[t][1], kr_[ao[t]], vr_[bo[t]]);
+                if (SREM != 0 && last_live) dmma884(sacc[SPW - 1][0], sacc[SPW - 1][1], kr_[ao[SPW - 1]], vr_[bo[SPW - 1]]);
             }
         }
         __syncthreads();
@@ -1452,8 +1447,8 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
         const int cr = lane >> 2, cc = 2 * (lane & 3);
 #pragma unroll
         for (int t = 0; t < SPW; t++) {
-            const int tp = warp * SPW + t;
-            if (tp < SNT) {
+            const int tp = warp * SBASE + min(warp, SREM) + t;
+            if (t < SBASE || (SREM != 0 && warp < SREM)) {
                 const int rc = s_tab[tp], ta = rc >> 8, tb = rc & 255;
                 const int i = ta * 8 + cr, j = tb * 8 + cc;
 #pragma unroll
