@@ -409,6 +409,22 @@ def parity_sharded(dev, rank, world, n_subj_rank=64):
     return out
 
 
+def bind_to_gpu_numa_node(dev):
+    """Pin this process to the CPUs next to its GPU (NVML's ideal affinity for the device) before the pinned host
+    buffers of the end-to-end loop are allocated: first touch then places them in the memory of that socket, and the
+    8 ranks of a box stop pulling their 440 MB per step through one socket's memory controllers and the inter-socket
+    link.  Returns a short description for the JSON line (None when NVML or the call is not available)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(dev.index if dev.index is not None else torch.cuda.current_device())
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        cpus = sorted(os.sched_getaffinity(0))
+        return f"{len(cpus)} cpus ({cpus[0]}-{cpus[-1]}) next to GPU {dev.index}"
+    except Exception as e:                                     # keep going unbound
+        return f"unbound ({type(e).__name__})"
+
+
 def allreduce_latency_us(dev, n_doubles, reps=50):
     """Device time of one NCCL all-reduce of the accumulator buffer (CUDA events, average of `reps` back to back)."""
     import torch.distributed as dist
@@ -593,6 +609,7 @@ def run_gpu(args):
     e2e = None
     if not args.no_e2e:
         reset_state()
+        numa = bind_to_gpu_numa_node(dev)          # pinned pages are placed where the allocating thread runs
         host = {k: s[k].detach().cpu().pin_memory() for k in INPUT_KEYS}
         h2d = sum(v.numel() * v.element_size() for v in host.values())
         sets = []
@@ -656,7 +673,7 @@ def run_gpu(args):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             dt = float(tt.item())
         e2e = dict(value=world * (n_rows / (SUBJ_PER_RANK * T)) * n_e2e / dt, unit="steps/s", h2d_bytes_per_step=h2d,
-                   d2h_bytes_per_step=8, steps=n_e2e, h2d_gb_per_s_per_rank=h2d * n_e2e / dt / 1e9,
+                   d2h_bytes_per_step=8, steps=n_e2e, h2d_gb_per_s_per_rank=h2d * n_e2e / dt / 1e9, host_binding=numa,
                    bound="host -> device copies (PCIe 5 x16, ~55 GB/s per GPU; the ranks of one box share the host's "
                          "memory and PCIe root bandwidth): the step itself needs a third of this time",
                    how="pinned host -> device copy of data, mask, covariates, theta, mu, log_v every step on a copy "

@@ -128,10 +128,11 @@ int hlvae_kernel_matvec(const hlvae_kspec_t* spec, const double* outputscale, co
  * gscale * dJ/dmu and gscale * dJ/dlog_v (gscale = P / P_batch of elbo_functions.py:181,277).
  * qdiag (nullable, [N, L], storage dtype): per row r the quadratic form (B^-1 K0xz)_r G (B^-1 K0xz)_r^T, the
  * diagonal that validation.validation_dubo needs with G = W^-1 (validation.py:69-72).
- * row_panel: rows per panel of hlvae_kl_panel (whole subjects are packed into panels); 0 = the default shape for M
- * (64 rows for M <= 64, 32 for M <= 128), 40 = the two-CTAs-per-SM shape for 32 < M <= 64 (every subject must have
- * <= 40 rows; it pays when subjects fill 40-row panels about as well as 64-row ones, e.g. T = 20).  Scheduling
- * only: results agree to float64 summation order.
+ * row_panel: rows per panel of hlvae_kl_panel (whole subjects are packed into panels, so every subject must have
+ * <= row_panel rows; a subject that cannot be packed is skipped and reported as HLVAE_STATUS_T_TOO_LARGE); 0 = the
+ * default (64 rows for every M); 40 = the two-CTAs-per-SM shape for 32 < M <= 64 (it pays when subjects fill 40-row
+ * panels about as well as 64-row ones, e.g. T = 20); 32 / 48 = smaller panels for 64 < M <= 128.  Scheduling only:
+ * results agree to float64 summation order.
  * ---------------------------------------------------------------------------------- */
 #define HLVAE_ACC_S 0
 #define HLVAE_ACC_P 1
