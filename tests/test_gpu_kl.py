@@ -176,6 +176,29 @@ def test_kernel_sweep_config(M, device):
     print(M, {k: f"{v:.1e}" for k, v in errs.items()})
 
 
+@pytest.mark.parametrize("M,rp", [(64, 40), (64, 64), (120, 32), (120, 48), (120, 64), (24, 64)])
+def test_every_panel_shape_against_oracle(M, rp, device, monkeypatch):
+    """hlvae_kl_panel's shapes are picked per minibatch by elbo._row_panel; here each one is forced in turn
+    (HLVAE_PANEL_RP) on the same ragged batch: two-CTA 40-row and one-CTA 64-row panels at M = 64, 32 / 48 / 64-row
+    panels at M = 120, the two-CTA 64-row shape at M <= 32."""
+    monkeypatch.setenv("HLVAE_PANEL_RP", str(rp))
+    errs = h.check_kl_vs_oracle(device, 3, M, 17, 20, seed=700 + M, tol=1e-6, hyper_tol=1e-4, ragged=True)
+    print((M, rp), {k: f"{v:.1e}" for k, v in errs.items()})
+
+
+def test_row_panel_choice():
+    """elbo._row_panel: rows per panel from the subject packing, never below the longest subject."""
+    from hlvae_b200 import elbo, subjects
+    lay = subjects.SubjectLayout.from_lengths([20] * 40, "cpu")
+    assert elbo._row_panel(lay, 16) == 64 and elbo._row_panel(lay, 64) == 40 and elbo._row_panel(lay, 120) == 64
+    lay = subjects.SubjectLayout.from_lengths([30] * 40, "cpu")          # one subject per 40 rows, two per 64
+    assert elbo._row_panel(lay, 64) == 64
+    lay = subjects.SubjectLayout.from_lengths([45, 12, 7, 60], "cpu")
+    assert elbo._row_panel(lay, 64) == 64 and elbo._row_panel(lay, 120) == 64
+    lay = subjects.SubjectLayout.from_lengths([33] * 6, "cpu")
+    assert elbo._row_panel(lay, 120) in (48, 64)
+
+
 def test_masked_bin_spec_against_oracle(device):
     """BinKernel factors, missing-covariate masks and bin x SE interactions (5 components in K0, two
     beyond the cached three) on fresh seeded inputs."""

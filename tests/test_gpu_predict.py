@@ -40,7 +40,7 @@ def test_golden(name, device):
     assert h.rel_err(zl, zp) < 1e-12
 
 
-@pytest.mark.parametrize("L,M,n_subj,T", [(8, 64, 60, 20), (3, 128, 25, 32), (4, 32, 40, 9)])
+@pytest.mark.parametrize("L,M,n_subj,T", [(8, 64, 60, 20), (3, 128, 25, 32), (4, 32, 40, 9), (3, 64, 9, 60), (2, 120, 7, 48)])
 def test_against_oracle(L, M, n_subj, T, device):
     inp = h.make_kl_inputs(L, M, n_subj, T, seed=500 + M, ragged=True)
     k0, k1, lik = h.build_product_kernels(inp["kargs"], L, device, inp["ros0"], inp["rls0"], inp["ros1"], inp["rls1"],
