@@ -1162,6 +1162,34 @@ def run_sweep(args):
                           tabular_loglik=ll_rows, hbm_peak_gbs=hbm_peak)), flush=True)
 
 
+def sweep_theta(dev, N, reps, hbm_peak):
+    """SURVEY 8(f) row 2 in the default line: the observation-head kernels (hlvae_theta_fwd / _bwd) at the configs[1]
+    batch (D4, y_dim 5, conv layout, float32 storage, uint8 mask) - same set-up as `--workload theta`."""
+    from hlvae_b200 import _lib, synth, theta as th
+    types = synth.HEALTHMNIST_D4_TYPES
+    Y, D = 5, len(types)
+    gen = torch.Generator(device=dev).manual_seed(0)
+    lay = th.HeadLayout(types, True, dev)
+    P = lay.P
+    y = torch.randn(N, Y, D, generator=gen, device=dev, dtype=torch.float32).permute(0, 2, 1).requires_grad_(True)
+    mask = (torch.rand(N, D, generator=gen, device=dev) < 0.75).to(torch.uint8)
+    W = (torch.randn(P, Y, generator=gen, device=dev, dtype=torch.float64) * 0.3).requires_grad_(True)
+    b = (torch.randn(P, generator=gen, device=dev, dtype=torch.float64) * 0.3).requires_grad_(True)
+    g_up = torch.randn(N, P, generator=gen, device=dev, dtype=torch.float32)
+
+    def step():
+        y.grad = W.grad = b.grad = None
+        th.theta_heads(lay, y, mask, W, b).backward(g_up)
+
+    _, per = _timed_profile(step, reps)
+    bytes_fwd = N * (4 * D * Y + 4 * P)
+    bytes_bwd = N * (4 * D * Y + D + 4 * P + 4 * D * Y)
+    f, bw = per["hlvae_theta_fwd"], per["hlvae_theta_bwd"]
+    return dict(rows=N, fwd_ms=round(f, 3), bwd_ms=round(bw, 3), fwd_gbs=round(bytes_fwd / f / 1e6),
+                fwd_frac=round(bytes_fwd / f / 1e6 / hbm_peak, 3), bwd_gbs=round(bytes_bwd / bw / 1e6),
+                bwd_frac=round(bytes_bwd / bw / 1e6 / hbm_peak, 3))
+
+
 def other_configs(dev, s_small, fp64_peak, hbm_peak):
     """Compact, driver-visible figures for the BASELINE.json configurations that are not the headline line
     (configs[2], [3], [4]) and for float64 storage; eager single-stream launches, CUDA events, 5 repetitions."""
@@ -1171,6 +1199,8 @@ def other_configs(dev, s_small, fp64_peak, hbm_peak):
     out["configs2_kernel_sweep_16k_rows"] = sweep_kl(dev, [(32, 800, False), (64, 800, False), (128, 800, False)], 5,
                                                      fp64_peak)
     out["configs3_tabular_64k_rows"] = sweep_tabular(dev, (64000,), 5, hbm_peak)[0]
+    out["survey_8f_observation_heads_16k_rows"] = sweep_theta(dev, SUBJ_PER_RANK * T, 5, hbm_peak)
+    torch.cuda.empty_cache()
 
     def eager_ms(st, reps=5):
         for _ in range(2):

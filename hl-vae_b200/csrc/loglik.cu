@@ -17,6 +17,7 @@
 // (ex2/lg2.approx), which makes the kernel HBM-bound.  In the float32 path the categorical /
 // ordinal argmax imputations (which must be bit-exact against the float64 reference) re-evaluate
 // the variable in float64 whenever the float32 decision is not provably the float64 one.
+#include <type_traits>
 #include "common.cuh"
 
 using namespace hlvae;
@@ -278,13 +279,15 @@ __device__ __forceinline__ void cat_backward(const XT* __restrict__ x, R* __rest
 }
 
 // ------------------------------------------------------------------------------------
-// One variable, forward.  x / t point into the staged spans (t is overwritten with `params`).
-template <typename R, typename XT>
+// One variable, forward.  x / t point into the staged spans (t is overwritten with `params`).  KIND >= 0 / CFIX > 0:
+// the type / class count as compile-time constants (the callers' per-type row loops), else read from v.
+template <typename R, typename XT, int KIND = -1, int CFIX = 0>
 __device__ __forceinline__ void var_forward(const VarC<R>& v, const XT* __restrict__ x_, R* __restrict__ t, bool observed,
                                             R& lp, R& rmean, R& rmode, R& dtr) {
     struct { const XT* p; __device__ __forceinline__ R operator[](int c) const { return (R)p[c]; } } x{x_};
-    const int C = v.C;
-    if (v.kind == HLVAE_VAR_REAL) {                                          // loglik.py:27-70
+    const int C = CFIX > 0 ? CFIX : v.C;
+    const int kind = KIND >= 0 ? KIND : v.kind;
+    if (kind == HLVAE_VAR_REAL) {                                          // loglik.py:27-70
         const R xv = x[0] * v.idiv;                                          // HLVAE.py:393-394
         const R mean = v.snv * t[0] + v.nm;                                  // :55
         const R r = xv - mean;
@@ -292,7 +295,7 @@ __device__ __forceinline__ void var_forward(const VarC<R>& v, const XT* __restri
         t[0] = mean;
         rmean = mean; rmode = mean;                                          // read_functions.py:275-278
         dtr = x[0];                                                          // read_functions.py:233
-    } else if (v.kind == HLVAE_VAR_POS) {                                    // loglik.py:73-121
+    } else if (kind == HLVAE_VAR_POS) {                                    // loglik.py:73-121
         const R ld = Mth<R>::lg1p(x[0]);                                     // :84
         const R mean = v.snv * t[0] + v.nm;                                  // :96
         const R r = ld - mean;
@@ -301,14 +304,14 @@ __device__ __forceinline__ void var_forward(const VarC<R>& v, const XT* __restri
         rmean = Mth<R>::ex(mean + R(0.5) * v.ev) - R(1);                     // read_functions.py:287
         rmode = Mth<R>::ex(mean - v.ev) - R(1);                              // :289
         dtr = x[0];
-    } else if (v.kind == HLVAE_VAR_COUNT) {                                  // loglik.py:191-213
+    } else if (kind == HLVAE_VAR_COUNT) {                                  // loglik.py:191-213
         const R lam = clamp_<R>(softplus_<R>(t[0]), R(1e-6), R(1e20));       // :203
         const R xv = x[0];
         lp = xv * Mth<R>::lg(lam) - lam - Mth<R>::lgam(xv + R(1));           // Poisson.log_prob
         t[0] = lam;
         rmean = lam; rmode = floor(lam);                                     // read_functions.py:293-295
         dtr = xv;
-    } else if (v.kind == HLVAE_VAR_CAT) {                                    // loglik.py:124-146
+    } else if (kind == HLVAE_VAR_CAT) {                                    // loglik.py:124-146
         switch (C) {     // common class counts run fully unrolled from registers
             case 2: cat_forward<R, XT, 2>(x_, t, 2, lp, rmean, dtr); break;
             case 3: cat_forward<R, XT, 3>(x_, t, 3, lp, rmean, dtr); break;
@@ -679,17 +682,33 @@ loglik_fwd_k(int64_t N, int D, int tile_vars, int cap, int64_t ld_data, int64_t 
                     cat_forward<R, TD, 5>(x, t, 5, lp, rmean, dtr);
                     rmode = rmean;
                 });
-            } else {
-                rows([&](const TD* x, R* t, bool obs, R& lp, R& rmean, R& rmode, R& dtr, int r) {
-                    var_forward<R, TD>(v, x, t, obs, lp, rmean, rmode, dtr);
-                    if constexpr (sizeof(R) == 4) {
-                        if (v.kind == HLVAE_VAR_ORDINAL && rmean < R(0)) {   // float32 could not prove the argmax: redo from theta
-                            const R am = (R)ord_argmax_f64(reinterpret_cast<const float*>(theta) +
-                                                           (n0 + r) * ld_theta + ps0 + v.po, v.C);
-                            rmean = am; rmode = am;
-                        }
-                    }
+            } else if (v.kind == HLVAE_VAR_POS) {
+                rows([&](const TD* x, R* t, bool obs, R& lp, R& rmean, R& rmode, R& dtr, int) {
+                    var_forward<R, TD, HLVAE_VAR_POS>(v, x, t, obs, lp, rmean, rmode, dtr);
                 });
+            } else if (v.kind == HLVAE_VAR_COUNT) {
+                rows([&](const TD* x, R* t, bool obs, R& lp, R& rmean, R& rmode, R& dtr, int) {
+                    var_forward<R, TD, HLVAE_VAR_COUNT>(v, x, t, obs, lp, rmean, rmode, dtr);
+                });
+            } else if (v.kind == HLVAE_VAR_CAT) {
+                rows([&](const TD* x, R* t, bool obs, R& lp, R& rmean, R& rmode, R& dtr, int) {
+                    var_forward<R, TD, HLVAE_VAR_CAT>(v, x, t, obs, lp, rmean, rmode, dtr);
+                });
+            } else {
+                auto ordinal = [&](auto cfix) {
+                    rows([&](const TD* x, R* t, bool obs, R& lp, R& rmean, R& rmode, R& dtr, int r) {
+                        var_forward<R, TD, HLVAE_VAR_ORDINAL, decltype(cfix)::value>(v, x, t, obs, lp, rmean, rmode, dtr);
+                        if constexpr (sizeof(R) == 4) {
+                            if (rmean < R(0)) {              // float32 could not prove the argmax: redo from theta
+                                const R am = (R)ord_argmax_f64(reinterpret_cast<const float*>(theta) +
+                                                               (n0 + r) * ld_theta + ps0 + v.po, v.C);
+                                rmean = am; rmode = am;
+                            }
+                        }
+                    });
+                };
+                if (v.C == 5) ordinal(std::integral_constant<int, 5>{});
+                else ordinal(std::integral_constant<int, 0>{});
             }
         }
         if (use_tma) fence_async_smem();         // params written through the generic proxy, read by the bulk store
@@ -802,26 +821,27 @@ __device__ __forceinline__ void ord_backward(const XT* __restrict__ x_, R* __res
 // ------------------------------------------------------------------------------------
 // One variable, backward: d log_p_x / d theta (times g) into t (in place of theta), and the
 // derivative w.r.t. the raw log-variance parameter (real / pos).
-template <typename R, typename XT>
+template <typename R, typename XT, int KIND = -1, int CFIX = 0>
 __device__ __forceinline__ void var_backward(const VarC<R>& v, const XT* __restrict__ x_, R* __restrict__ t, bool observed,
                                              R g, R& ge) {
     struct { const XT* p; __device__ __forceinline__ R operator[](int c) const { return (R)p[c]; } } x{x_};
-    const int C = v.C;
-    if (v.kind == HLVAE_VAR_REAL) {
+    const int C = CFIX > 0 ? CFIX : v.C;
+    const int kind = KIND >= 0 ? KIND : v.kind;
+    if (kind == HLVAE_VAR_REAL) {
         const R r = x[0] * v.idiv - (v.snv * t[0] + v.nm);
         t[0] = g * v.snv * r * v.ivar;
         ge = g * (R(0.5) * r * r * v.ivar - R(0.5)) * v.sg8;
-    } else if (v.kind == HLVAE_VAR_POS) {
+    } else if (kind == HLVAE_VAR_POS) {
         const R r = Mth<R>::lg1p(x[0]) - (v.snv * t[0] + v.nm);
         t[0] = g * v.snv * r * v.ivar;
         ge = g * (R(0.5) * r * r * v.ivar - R(0.5));
-    } else if (v.kind == HLVAE_VAR_COUNT) {
+    } else if (kind == HLVAE_VAR_COUNT) {
         const R t0 = t[0];
         const R sp = softplus_<R>(t0);
         R gl = R(0);
         if (sp >= R(1e-6) && sp <= R(1e20)) gl = (x[0] * Mth<R>::rcp(sp) - R(1)) * dsoftplus_<R>(t0);
         t[0] = g * gl;
-    } else if (v.kind == HLVAE_VAR_CAT) {
+    } else if (kind == HLVAE_VAR_CAT) {
         switch (C) {
             case 2: cat_backward<R, XT, 2>(x_, t, 2, g); break;
             case 3: cat_backward<R, XT, 3>(x_, t, 3, g); break;
@@ -1002,8 +1022,16 @@ loglik_bwd_k(int64_t N, int D, int tile_vars, int cap, int64_t ld_data, int64_t 
                 });
             } else if (v.kind == HLVAE_VAR_CAT && v.C == 5) {
                 rows([&](const TD* x, R* t, bool, R g, R&) { cat_backward<R, TD, 5>(x, t, 5, g); });
+            } else if (v.kind == HLVAE_VAR_POS) {
+                rows([&](const TD* x, R* t, bool obs, R g, R& ge) { var_backward<R, TD, HLVAE_VAR_POS>(v, x, t, obs, g, ge); });
+            } else if (v.kind == HLVAE_VAR_COUNT) {
+                rows([&](const TD* x, R* t, bool obs, R g, R& ge) { var_backward<R, TD, HLVAE_VAR_COUNT>(v, x, t, obs, g, ge); });
+            } else if (v.kind == HLVAE_VAR_CAT) {
+                rows([&](const TD* x, R* t, bool obs, R g, R& ge) { var_backward<R, TD, HLVAE_VAR_CAT>(v, x, t, obs, g, ge); });
+            } else if (v.C == 5) {
+                rows([&](const TD* x, R* t, bool obs, R g, R& ge) { var_backward<R, TD, HLVAE_VAR_ORDINAL, 5>(v, x, t, obs, g, ge); });
             } else {
-                rows([&](const TD* x, R* t, bool obs, R g, R& ge) { var_backward<R, TD>(v, x, t, obs, g, ge); });
+                rows([&](const TD* x, R* t, bool obs, R g, R& ge) { var_backward<R, TD, HLVAE_VAR_ORDINAL>(v, x, t, obs, g, ge); });
             }
         }
         if (use_tma) fence_async_smem();
