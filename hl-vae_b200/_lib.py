@@ -43,6 +43,7 @@ _SIGS = {
     "hlvae_sizeof_kspec": ([], _I),
     "hlvae_kernel_eval_fwd": ([C.POINTER(KSpec), _P, _P, _I, _I, _P, _I, _L, _L, _P, _I, _L, _L, _P, _P], _I),
     "hlvae_kernel_eval_bwd": ([C.POINTER(KSpec), _P, _P, _I, _I, _P, _I, _L, _L, _P, _I, _L, _L, _P, _P, _P, _P, _P, _P], _I),
+    "hlvae_hyper_constrain": ([_I, _I, C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.POINTER(C.c_double), _P, _P, _P, _P], _I),
     "hlvae_subject_matvec": ([C.POINTER(KSpec), _P, _P, _I, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P], _I),
     "hlvae_kl_acc_layout": ([_I, _I, _I, C.POINTER(_L)], _I),
     "hlvae_kl_subject": ([C.POINTER(KSpec), _P, _P, C.POINTER(KSpec), _P, _P, _P, _I, _I, _P, _L, _P, _P, _P, _I, _I,

@@ -203,3 +203,67 @@ extern "C" int hlvae_kernel_matvec(const hlvae_kspec_t* spec, const double* outp
     HLVAE_CHECK_LAUNCH();
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Constrained hyper-parameters of both additive kernels in one launch: out[row, l] = softplus(raw_row[l]) + lb_row
+// (gpytorch's Positive / GreaterThan constraints as the reference's kernels use them, kernel_spec.py:58-69 and
+// kernel_gen.py:219-310; torch.nn.functional.softplus semantics: beta 1, threshold 20), 1 for rows without a
+// parameter.  The backward direction multiplies the upstream gradient by softplus' (and sums over l for a scalar
+// parameter).  Replaces ~20 stock element-wise / concatenation kernels per step in front of the KL kernels.
+namespace {
+struct HyperRows {
+    const double* raw[HLVAE_MAX_HYPER_ROWS];
+    double lb[HLVAE_MAX_HYPER_ROWS];
+    int bcast[HLVAE_MAX_HYPER_ROWS];
+};
+
+__global__ void __launch_bounds__(256)
+hyper_constrain_k(const HyperRows rows, int n_rows, int L, double* __restrict__ out, const double* __restrict__ g_out,
+                  double* __restrict__ g_raw) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_rows * L) return;
+    const int row = e / L, l = e - row * L;
+    const double* raw = rows.raw[row];
+    if (!g_out) {
+        double v = 1.0;
+        if (raw) {
+            const double x = raw[rows.bcast[row] ? 0 : l];
+            v = (x > 20.0 ? x : log1p(exp(x))) + rows.lb[row];
+        }
+        out[e] = v;
+    } else {
+        double g = 0.0;
+        if (raw) {
+            if (!rows.bcast[row]) {
+                const double x = raw[l];
+                const double z = exp(x);
+                g = x > 20.0 ? g_out[e] : g_out[e] * z / (z + 1.0);
+            } else if (l == 0) {
+                const double x = raw[0];
+                const double z = exp(x);
+                const double d = x > 20.0 ? 1.0 : z / (z + 1.0);
+                for (int k = 0; k < L; k++) g += g_out[row * L + k];
+                g *= d;
+            }
+        }
+        g_raw[e] = g;
+    }
+}
+}  // namespace
+
+extern "C" int hlvae_hyper_constrain(int n_rows, int L, const double* const* raw, const int32_t* bcast, const double* lb,
+                                     double* out, const double* g_out, double* g_raw, void* stream) {
+    if (n_rows <= 0 || n_rows > HLVAE_MAX_HYPER_ROWS || L <= 0 || !raw || !bcast || !lb || (!g_out && !out) ||
+        (g_out && !g_raw))
+        return HLVAE_E_ARG;
+    HyperRows rows;
+    for (int i = 0; i < HLVAE_MAX_HYPER_ROWS; i++) {
+        rows.raw[i] = i < n_rows ? raw[i] : nullptr;
+        rows.lb[i] = i < n_rows ? lb[i] : 0.0;
+        rows.bcast[i] = i < n_rows ? bcast[i] : 0;
+    }
+    const int n = n_rows * L;
+    hyper_constrain_k<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(rows, n_rows, L, out, g_out, g_raw);
+    HLVAE_CHECK_LAUNCH();
+    return 0;
+}

@@ -17,7 +17,7 @@ from __future__ import annotations
 import torch
 
 from . import _lib, config
-from .kernels import compile_spec
+from .kernels import compile_spec, constrained_pair
 from .subjects import SubjectLayout
 
 N_SM = 148
@@ -189,8 +189,7 @@ def _kld(covar_module0, covar_module1, likelihood, latent_dim, m, H, train_xt, m
         raise RuntimeError("hlvae_b200: the KL upper bound runs on CUDA tensors only (no CPU fallback)")
     fs0, fs1 = compile_spec(covar_module0), compile_spec(covar_module1)
     L = latent_dim
-    os0, ls0 = fs0.constrained(L, train_xt.device)
-    os1, ls1 = fs1.constrained(L, train_xt.device)
+    os0, ls0, os1, ls1 = constrained_pair(fs0, fs1, L, train_xt.device)
     noise = _noise_vector(likelihood, L, train_xt.device)
     kld, grad_m, grad_H, iH = _KLD.apply(mu, log_v, z, m, H, os0, ls0, os1, ls1, noise, train_xt, fs0, fs1, layout,
                                          float(scale), float(const), float(eps), bool(natural_gradient), out_shape)

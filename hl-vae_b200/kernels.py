@@ -231,6 +231,69 @@ class FlatSpec:
         return torch.stack([vals[pos[i]] if i in pos else one for i in range(len(mods))]).contiguous()
 
 
+class _ConstrainRows(torch.autograd.Function):
+    """softplus(raw) + lower bound for every outputscale / lengthscale of both additive kernels in ONE launch
+    (hlvae_hyper_constrain), and one launch for the chain rule on the way back.  `plan`: per output row the index
+    into `raws` or -1 (no parameter: the row is 1) and the lower bound; `blocks`: the row ranges handed back as
+    separate tensors (outputscale / lengthscale of kernel 0 / 1)."""
+
+    @staticmethod
+    def forward(ctx, plan, blocks, L, *raws):
+        import ctypes as C
+        n_rows = len(plan)
+        dev = raws[0].device
+        out = torch.empty(n_rows, L, dtype=torch.float64, device=dev)
+        ptrs = (C.c_void_p * n_rows)(*[raws[j].data_ptr() if j >= 0 else None for j, _ in plan])
+        bc = (C.c_int32 * n_rows)(*[1 if (j >= 0 and raws[j].numel() == 1 and L > 1) else 0 for j, _ in plan])
+        lb = (C.c_double * n_rows)(*[float(b) for _, b in plan])
+        ctx.hold = (ptrs, bc, lb, n_rows, L, plan, blocks)
+        ctx.save_for_backward(*raws)
+        _lib.call("hlvae_hyper_constrain", n_rows, L, ptrs, bc, lb, _lib.ptr(out), None, None, _lib.stream_ptr())
+        return tuple(out[a:b] for a, b in blocks)
+
+    @staticmethod
+    def backward(ctx, *g_blocks):
+        ptrs, bc, lb, n_rows, L, plan, blocks = ctx.hold
+        raws = ctx.saved_tensors
+        dev = raws[0].device
+        parts = [g if g is not None else torch.zeros(b - a, L, dtype=torch.float64, device=dev)
+                 for g, (a, b) in zip(g_blocks, blocks)]
+        g_out = torch.cat(parts) if len(parts) > 1 else parts[0].contiguous()
+        g_raw = torch.empty(n_rows, L, dtype=torch.float64, device=dev)
+        _lib.call("hlvae_hyper_constrain", n_rows, L, ptrs, bc, lb, None, _lib.ptr(g_out), _lib.ptr(g_raw),
+                  _lib.stream_ptr())
+        grads = [None] * len(raws)
+        for row, (j, _) in enumerate(plan):
+            if j >= 0:
+                r = raws[j]
+                grads[j] = (g_raw[row, :1] if r.numel() == 1 and L > 1 else g_raw[row]).reshape(r.shape)
+        return (None, None, None) + tuple(grads)
+
+
+def constrained_pair(fs0, fs1, L, device):
+    """(outputscale0, lengthscale0, outputscale1, lengthscale1), each [ncomp, L] float64 and attached to autograd:
+    what FlatSpec.constrained returns for the two kernels of the KL bound, computed by one launch.  Falls back to the
+    stock-PyTorch formulation when a raw parameter is not a contiguous float64 CUDA tensor of L (or 1) values."""
+    plan, raws = [], []
+    blocks = []
+    for fs in (fs0, fs1):
+        for mods, name in ((fs.scale_mods, "raw_outputscale"), (fs.rbf_mods, "raw_lengthscale")):
+            start = len(plan)
+            for m in mods:
+                if m is None:
+                    plan.append((-1, 0.0))
+                else:
+                    r = getattr(m, name)
+                    if not (r.is_cuda and r.dtype == torch.float64 and r.is_contiguous() and r.numel() in (1, L)):
+                        return fs0.constrained(L, device) + fs1.constrained(L, device)
+                    plan.append((len(raws), getattr(m, name + "_constraint").lower_bound_value))
+                    raws.append(r)
+            blocks.append((start, len(plan)))
+    if not raws or len(plan) > 4 * _lib.MAX_COMPS:
+        return fs0.constrained(L, device) + fs1.constrained(L, device)
+    return _ConstrainRows.apply(tuple(plan), tuple(blocks), L, *raws)
+
+
 def _flatten_product(k, factors):
     if isinstance(k, ProductKernel):
         for c in k.kernels:

@@ -164,6 +164,18 @@ int hlvae_kl_panel(const hlvae_kspec_t* spec0, const double* os0, const double* 
                    double* acc, void* g_mu, void* qdiag, double gscale, int32_t* status, int row_panel, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Constrained hyper-parameters (gpytorch Positive / GreaterThan: softplus(raw) + lower bound) of the outputscales
+ * and lengthscales the reference's kernel objects own (kernel_spec.py:58-69, kernel_gen.py:219-310; the
+ * `outputscale` / `lengthscale` arguments of every entry point above): one launch for up to HLVAE_MAX_HYPER_ROWS
+ * parameters of L (or 1, broadcast) values each.  raw / bcast / lb are HOST arrays of n_rows entries (raw[i] = device
+ * pointer or NULL for "no parameter": the row is 1).  Forward (g_out == NULL): out[n_rows, L].  Backward (g_out =
+ * d loss / d out [n_rows, L]): g_raw[n_rows, L] = g_out * softplus'(raw); a broadcast row holds its sum in column 0.
+ * ---------------------------------------------------------------------------------- */
+#define HLVAE_MAX_HYPER_ROWS (4 * HLVAE_MAX_COMPS)
+int hlvae_hyper_constrain(int n_rows, int L, const double* const* raw, const int32_t* bcast, const double* lb,
+                          double* out, const double* g_out, double* g_raw, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Replicated M x M stage (float64, one CTA per latent dimension, M <= 128).
  * hlvae_mxm_pre : K0zz = K0(Z,Z) + eps I (:148,153 / :223-224), Cholesky and explicit inverses
  *   iK, iH (:154-157,162-163 / :225-228), w = iK m, G = sym(iK H iK) - iK; pre[l] =
