@@ -25,11 +25,20 @@ using namespace hlvae;
 namespace {
 
 constexpr int LL_THREADS = 128;                          // threads per CTA = max variables per tile
-constexpr int LL_ROWS = 8;                               // rows staged per batch
+#ifndef HLVAE_LL_ROWS
+#define HLVAE_LL_ROWS 8
+#endif
+#ifndef HLVAE_LL_STAGES
+#define HLVAE_LL_STAGES 1
+#endif
+constexpr int LL_ROWS = HLVAE_LL_ROWS;                   // rows staged per batch
 constexpr int LL_CAPM = LL_THREADS + 16;                  // staged mask / upstream-gradient row (with alignment shift)
 static_assert(4 * LL_ROWS <= 32, "one warp issues every bulk copy of a row batch");
-constexpr int LL_STAGES = 1;                             // 2: prefetch the next row batch while this one is evaluated (measured: no gain,
-                                                         // the resident CTAs of an SM already cover each other's loads)
+constexpr int LL_STAGES = HLVAE_LL_STAGES;               // 2: prefetch the next row batch while this one is evaluated.  Measured
+                                                         // again after the r02 instruction diet (fwd / bwd ms at configs[1]):
+                                                         // 1 stage x 8 rows 0.270 / 0.179, 2 x 8 0.356 / 0.237 (4 CTAs per SM),
+                                                         // 2 x 4 0.329 / 0.207, 1 x 4 0.305 / 0.213 - the resident CTAs of an
+                                                         // SM already cover each other's loads
 constexpr double LOG_2PI = 1.8378770664093454835606594728112;
 
 // ------------------------------------------------------------------------------------

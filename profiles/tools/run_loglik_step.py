@@ -20,3 +20,19 @@ for _ in range(3):
     (-out["log_p_x_sum"]).backward()
 torch.cuda.synchronize()
 print("nll", float(-out["log_p_x_sum"]))
+if os.environ.get("TIME_LL"):
+    import numpy as np
+    from hlvae_b200 import _lib
+    def step():
+        theta.grad = None
+        out = loglik.fused_loglik(lay, data, mask, theta, vparam, monitor=True)
+        (-out["log_p_x_sum"]).backward()
+    for _ in range(3): step()
+    torch.cuda.synchronize()
+    _lib.PROFILE = []
+    for _ in range(20): step()
+    torch.cuda.synchronize()
+    per = {}
+    for name, a, b in _lib.PROFILE: per.setdefault(name, []).append(a.elapsed_time(b))
+    _lib.PROFILE = None
+    print({k[6:]: round(float(np.mean(v)), 4) for k, v in per.items()})
