@@ -26,93 +26,145 @@ struct Mat {
 };
 
 // C = X Y (TRANSX = false) or X^T Y (TRANSX = true); all M x M.  C must not alias X or Y.
-// Each thread owns a 4 x 4 register tile whose rows / columns are interleaved with stride nt = ceil(M / 4)
-// (rows ic + a nt, columns jc + b nt): per k it loads 4 + 4 operands for 16 FMAs, consecutive threads read
-// consecutive columns of Y (conflict-free in shared memory, coalesced in the global workspace) and share
-// the X operands (broadcast).  `k_from_diag`: X^T Y with X, Y lower triangular - the sum may start at
-// max(ic, jc) because rows above the diagonal hold zeros.
-template <bool TRANSX, bool K_FROM_DIAG = false>
-__device__ void mm(Mat C, Mat X, Mat Y, int M, double* __restrict__ gout = nullptr) {
-    const int nt = (M + 3) >> 2;
-    for (int t = threadIdx.x; t < nt * nt; t += MX_THREADS) {
-        const int ic = t / nt, jc = t - ic * nt;
-        double acc[4][4];
+// On the FP64 tensor pipe (mma.sync.m8n8k4): a warp owns 8 x 8 output tiles (tile t = warp, warp + 8, ...), per k-step
+// one A and one B fragment element per lane and one DMMA.  r02: 4 x 4 register tiles with scalar FMAs spent 75
+// instructions per k on 16 FMAs (per-element address arithmetic and bounds predicates inside the k loop) - 80 % of
+// hlvae_mxm_post's instructions.  Sizes that are not a multiple of 8 take the predicated (zero-filled) loads.
+// `K_FROM_DIAG`: X^T Y with X, Y lower triangular - the sum may start at the tile's first row / column because rows
+// above the diagonal hold zeros.
+template <bool TRANSX, bool K_FROM_DIAG, int NB>              // NB column tiles in flight per warp: independent DMMA chains
+__device__ void mm_tiles(Mat C, Mat X, Mat Y, int M, double* __restrict__ gout) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ar = lane >> 2, ac = lane & 3;
+    const int nt = (M + 7) >> 3;
+    const int ng = (nt + NB - 1) / NB;
+    const int M4 = (M + 3) & ~3;
+    const bool full = (M & 7) == 0 && (nt % NB) == 0;
+    for (int t = warp; t < nt * ng; t += MX_THREADS / 32) {
+        const int it = t / ng, jg = (t - it * ng) * NB;
+        const int i = it * 8 + ar;
+        const int kbeg = K_FROM_DIAG ? (max(it, jg) * 8) : 0;
+        double c[NB][2];
 #pragma unroll
-        for (int a = 0; a < 4; a++)
+        for (int u = 0; u < NB; u++) c[u][0] = c[u][1] = 0.0;
+        if (full) {
+            const double* ap = TRANSX ? &X(kbeg + ac, i) : &X(i, kbeg + ac);
+            const double* bp = &Y(kbeg + ac, jg * 8 + ar);
+            const int astep = TRANSX ? 4 * X.ld : 4, bstep = 4 * Y.ld;
+#pragma unroll 2
+            for (int k0 = kbeg; k0 < M; k0 += 4) {
+                const double a = *ap;
 #pragma unroll
-            for (int b2 = 0; b2 < 4; b2++) acc[a][b2] = 0.0;
-        bool iv[4], jv[4];
-#pragma unroll
-        for (int a = 0; a < 4; a++) { iv[a] = ic + a * nt < M; jv[a] = jc + a * nt < M; }
-        for (int k = K_FROM_DIAG ? max(ic, jc) : 0; k < M; k++) {
-            double xv[4], yv[4];
-#pragma unroll
-            for (int a = 0; a < 4; a++) {
-                const int i = ic + a * nt;
-                xv[a] = iv[a] ? (TRANSX ? X(k, i) : X(i, k)) : 0.0;
-                yv[a] = jv[a] ? Y(k, jc + a * nt) : 0.0;
+                for (int u = 0; u < NB; u++) dmma884(c[u][0], c[u][1], a, bp[u * 8]);
+                ap += astep;
+                bp += bstep;
             }
+        } else {
+            for (int k0 = kbeg; k0 < M4; k0 += 4) {
+                const int kk = k0 + ac;
+                const double a = (i < M && kk < M) ? (TRANSX ? X(kk, i) : X(i, kk)) : 0.0;
 #pragma unroll
-            for (int a = 0; a < 4; a++)
-#pragma unroll
-                for (int b2 = 0; b2 < 4; b2++) acc[a][b2] = fma(xv[a], yv[b2], acc[a][b2]);
-        }
-#pragma unroll
-        for (int a = 0; a < 4; a++)
-#pragma unroll
-            for (int b2 = 0; b2 < 4; b2++)
-                if (iv[a] && jv[b2]) {
-                    const int i = ic + a * nt, j = jc + b2 * nt;
-                    C(i, j) = acc[a][b2];
-                    if (gout) gout[i * M + j] = acc[a][b2];
+                for (int u = 0; u < NB; u++) {
+                    const int j = (jg + u) * 8 + ar;
+                    const double b = (j < M && kk < M) ? Y(kk, j) : 0.0;
+                    dmma884(c[u][0], c[u][1], a, b);
                 }
+            }
+        }
+        if (i < M) {
+#pragma unroll
+            for (int u = 0; u < NB; u++) {
+                const int oj = (jg + u) * 8 + 2 * ac;
+                if (oj < M) {
+                    C(i, oj) = c[u][0];
+                    if (gout) gout[i * M + oj] = c[u][0];
+                }
+                if (oj + 1 < M) {
+                    C(i, oj + 1) = c[u][1];
+                    if (gout) gout[i * M + oj + 1] = c[u][1];
+                }
+            }
+        }
     }
     __syncthreads();
 }
 
-// In-place lower Cholesky of A (column by column, thread i owns row i).  Returns false when a
-// pivot is not positive.  logdet = 2 sum log L_jj.  `tmp` holds M doubles in shared memory.
+// Shared-memory operands (M <= 64): four independent accumulation chains per warp (a single chain is bound by the
+// DMMA latency: hlvae_mxm_post 0.074 ms against 0.054 ms); operands in the L2-resident workspace (M > 64): one tile at
+// a time (four in flight: 0.55 ms against 0.40 ms at M = 120 - the predicated path over a 15 x 15 tile grid).
+template <bool TRANSX, bool K_FROM_DIAG = false>
+__device__ void mm(Mat C, Mat X, Mat Y, int M, double* __restrict__ gout = nullptr) {
+    if (M <= 64) mm_tiles<TRANSX, K_FROM_DIAG, 4>(C, X, Y, M, gout);
+    else mm_tiles<TRANSX, K_FROM_DIAG, 1>(C, X, Y, M, gout);
+}
+
+// In-place lower Cholesky of A, column by column.  Returns false when a pivot is not positive.  logdet = 2 sum
+// log L_jj.  `tmp` holds M doubles in shared memory.  Four threads share a row (each sums a quarter of the dot
+// product, two shuffles combine them), the column is scaled by one reciprocal square root instead of a square root
+// and a division per row, and the logarithms are taken once after the loop: a column costs ~450 cycles instead of
+// ~1100 (the factorisations are the latency chain of hlvae_natgrad_update and hlvae_mxm_pre).  Measured and dropped: the
+// register-resident scheme of kl_subject_k on two warps (thread = row, 64 x 64 fully unrolled): straight-line code that
+// runs once per launch is bound by instruction fetch (hlvae_natgrad_update 0.089 -> 0.098 ms at M = 64).
 __device__ bool chol(Mat A, int M, double* tmp, double& logdet) {
-    const int i = threadIdx.x;
-    double ld = 0.0;
+    const int i = threadIdx.x >> 2, q = threadIdx.x & 3;       // MX_THREADS = 4 x 64 rows; M <= 64 rows per pass
+    const int passes = (M + MX_THREADS / 4 - 1) / (MX_THREADS / 4);
     for (int j = 0; j < M; j++) {
-        if (i >= j && i < M) {
-            double s0 = A(i, j), s1 = 0.0;
-            int k = 0;
-            for (; k + 1 < j; k += 2) {
-                s0 = fma(-A(i, k), A(j, k), s0);
-                s1 = fma(-A(i, k + 1), A(j, k + 1), s1);
+        for (int ps = 0; ps < passes; ps++) {
+            const int row = i + ps * (MX_THREADS / 4);
+            double s = 0.0;
+            if (row >= j && row < M) {
+                for (int k = q; k < j; k += 4) s = fma(-A(row, k), A(j, k), s);
             }
-            if (k < j) s0 = fma(-A(i, k), A(j, k), s0);
-            tmp[i] = s0 + s1;
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            if (q == 0 && row >= j && row < M) tmp[row] = A(row, j) + s;
         }
         __syncthreads();
         const double djj = tmp[j];
         if (!(djj > 0.0)) return false;       // uniform: every thread reads the same value
-        const double d = sqrt(djj);
-        ld += 2.0 * log(d);
-        if (i >= j && i < M) A(i, j) = (i == j) ? d : tmp[i] / d;
+        const double rs = rsqrt(djj);
+        for (int row = threadIdx.x; row < M; row += MX_THREADS)
+            if (row >= j) A(row, j) = (row == j) ? djj * rs : tmp[row] * rs;
         __syncthreads();
     }
-    logdet = ld;
+    // every thread needs the sum, in a fixed order: one logarithm per diagonal entry through tmp (free again)
+    for (int j = threadIdx.x; j < M; j += MX_THREADS) tmp[j] = 2.0 * log(A(j, j));
+    __syncthreads();
+    double tot = 0.0;
+    for (int j = 0; j < M; j++) tot += tmp[j];
+    __syncthreads();
+    logdet = tot;
     return true;
 }
 
-// B = L^-1 for lower-triangular L (thread c solves L y = e_c).  B must not alias L.
-__device__ void tri_inv(Mat B, Mat Lm, int M) {
-    const int c = threadIdx.x;
-    if (c < M) {
-        for (int i = 0; i < c; i++) B(i, c) = 0.0;
-        B(c, c) = 1.0 / Lm(c, c);
-        for (int i = c + 1; i < M; i++) {
-            double s0 = 0.0, s1 = 0.0;
-            int k = c;
-            for (; k + 1 < i; k += 2) {
-                s0 = fma(Lm(i, k), B(k, c), s0);
-                s1 = fma(Lm(i, k + 1), B(k + 1, c), s1);
-            }
-            if (k < i) s0 = fma(Lm(i, k), B(k, c), s0);
-            B(i, c) = -(s0 + s1) / Lm(i, i);
+// B = L^-1 for lower-triangular L (column c: forward substitution L y = e_c).  B must not alias L.  Four threads
+// share a column (each sums a quarter of every dot product, two shuffles combine them - the columns of the first rows
+// are the long ones and only M of the 256 threads had work before); `dinv` (M doubles of shared scratch) receives the
+// reciprocal diagonal first: one division per row instead of one per entry.
+__device__ void tri_inv(Mat B, Mat Lm, int M, double* dinv) {
+    for (int c = threadIdx.x; c < M; c += MX_THREADS) dinv[c] = 1.0 / Lm(c, c);
+    __syncthreads();
+    const int q = threadIdx.x & 3;
+    const int passes = (M + MX_THREADS / 4 - 1) / (MX_THREADS / 4);
+    for (int ps = 0; ps < passes; ps++) {
+        const int c = (threadIdx.x >> 2) + ps * (MX_THREADS / 4);
+        const bool live = c < M;
+        if (live && q == 0) {
+            for (int i = 0; i < c; i++) B(i, c) = 0.0;
+            B(c, c) = dinv[c];
+        }
+        __syncwarp();
+        // the four threads of a column walk the rows together; rows beyond a column's range cost nothing but the
+        // shuffles (all 32 lanes take part in them)
+        int cmin = ((threadIdx.x & ~31) >> 2) + ps * (MX_THREADS / 4);      // first column of this warp
+        for (int i = cmin + 1; i < M; i++) {
+            double s = 0.0;
+            if (live && i > c)
+                for (int k = c + q; k < i; k += 4) s = fma(Lm(i, k), B(k, c), s);
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            if (live && i > c && q == 0) B(i, c) = -s * dinv[i];
+            __syncwarp();
         }
     }
     __syncthreads();
@@ -191,7 +243,7 @@ mxm_pre_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__ 
             if (tid == 0) report_status(status, HLVAE_STATUS_NOT_PD, l, -2);
             return;
         }
-        tri_inv(P1, A, M);
+        tri_inv(P1, A, M, tmp);
         ata_lower(A, P1, M, iH + mm_off);
         if (tid == 0) pre[l * 4 + 1] = logdetH;
         return;
@@ -212,7 +264,7 @@ mxm_pre_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__ 
         if (tid == 0) report_status(status, HLVAE_STATUS_NOT_PD, l, -1);
         return;
     }
-    tri_inv(P1, A, M);
+    tri_inv(P1, A, M, tmp);
     ata_lower(A, P1, M, iK + mm_off);                                  // iK (:155 / :226), kept in A
     // w = iK m, qf1 = m^T iK m (:177 / :272)
     for (int i = tid; i < M; i += MX_THREADS) {
@@ -365,34 +417,51 @@ natgrad_k(int L, int M, double lr, const double* __restrict__ m, const double* _
             if (tid == 0) report_status(status, HLVAE_STATUS_NOT_PD, l, -3);
             return;
         }
-        tri_inv(P1, A, M);
+        tri_inv(P1, A, M, tmp);
         ata_lower(P2, P1, M, nullptr);                                 // iH (:132)
     }
-    // v = iH m - lr (grad_m - 2 grad_H m)   (:136-137)
-    for (int i = tid; i < M; i += MX_THREADS) {
-        double a = 0.0, b = 0.0;
-        for (int k = 0; k < M; k++) {
-            a = fma(P2(i, k), mv[k], a);
-            b = fma(grad_H[mm_off + (size_t)i * M + k], mv[k], b);
+    // grad_H goes through P1 (free until the triangular inverse): coalesced loads once, instead of a strided global
+    // read per thread and k in the product below and a transposed one in the update
+    load(P1, grad_H + mm_off, M);
+    // v = iH m - lr (grad_m - 2 grad_H m)   (:136-137): four threads per row
+    {
+        const int q = tid & 3;
+        for (int i0 = 0; i0 < M; i0 += MX_THREADS / 4) {               // uniform trip count: every lane shuffles
+            const int i = i0 + (tid >> 2);
+            double a = 0.0, b = 0.0;
+            for (int k = q; k < M && i < M; k += 4) {
+                a = fma(P2(i, k), mv[k], a);
+                b = fma(P1(i, k), mv[k], b);
+            }
+            a += __shfl_xor_sync(0xffffffffu, a, 1);
+            b += __shfl_xor_sync(0xffffffffu, b, 1);
+            a += __shfl_xor_sync(0xffffffffu, a, 2);
+            b += __shfl_xor_sync(0xffffffffu, b, 2);
+            if (q == 0 && i < M) v[i] = a - lr * (grad_m[(size_t)l * M + i] - 2.0 * b);
         }
-        v[i] = a - lr * (grad_m[(size_t)l * M + i] - 2.0 * b);
     }
     // iH_new = iH + lr (grad_H + grad_H^T)   (:133)
     for (int e = tid; e < M * M; e += MX_THREADS) {
         int i = e / M, j = e % M;
-        A(i, j) = P2(i, j) + lr * (grad_H[mm_off + e] + grad_H[mm_off + (size_t)j * M + i]);
+        A(i, j) = P2(i, j) + lr * (P1(i, j) + P1(j, i));
     }
     __syncthreads();
     if (!chol(A, M, tmp, ldet)) {                                      // :134
         if (tid == 0) report_status(status, HLVAE_STATUS_NOT_PD, l, -4);
         return;
     }
-    tri_inv(P1, A, M);
+    tri_inv(P1, A, M, tmp);
     ata_lower(P3, P1, M, H_out + mm_off);                              // H_new (:135)
-    for (int i = tid; i < M; i += MX_THREADS) {
-        double a = 0.0;
-        for (int k = 0; k < M; k++) a = fma(P3(i, k), v[k], a);
-        m_out[(size_t)l * M + i] = a;                                  // m_new (:136)
+    {
+        const int q = tid & 3;
+        for (int i0 = 0; i0 < M; i0 += MX_THREADS / 4) {
+            const int i = i0 + (tid >> 2);
+            double a = 0.0;
+            for (int k = q; k < M && i < M; k += 4) a = fma(P3(i, k), v[k], a);
+            a += __shfl_xor_sync(0xffffffffu, a, 1);
+            a += __shfl_xor_sync(0xffffffffu, a, 2);
+            if (q == 0 && i < M) m_out[(size_t)l * M + i] = a;         // m_new (:136)
+        }
     }
 }
 
@@ -436,7 +505,7 @@ mxm_aux_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__ 
         if (tid == 0) report_status(status, HLVAE_STATUS_NOT_PD, l, -1);
         return;
     }
-    tri_inv(P1, A, M);
+    tri_inv(P1, A, M, tmp);
     ata_lower(P2, P1, M, nullptr);                                     // iK
     double trS = 0.0;
     if (S)
@@ -446,7 +515,7 @@ mxm_aux_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__ 
         if (tid == 0) report_status(status, HLVAE_STATUS_NOT_PD, l, -5);
         return;
     }
-    tri_inv(P1, Wm, M);                                                // L_W^-1 (lower)
+    tri_inv(P1, Wm, M, tmp);                                                // L_W^-1 (lower)
     for (int i = tid; i < M; i += MX_THREADS) {
         double s = 0.0;
         for (int k = 0; k <= i; k++) s = fma(P1(i, k), pv[k], s);

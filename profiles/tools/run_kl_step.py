@@ -21,3 +21,7 @@ for _ in range(3):
     kld.backward()
 torch.cuda.synchronize()
 print("kld", float(kld))
+if os.environ.get("WITH_NATGRAD"):
+    for _ in range(2):
+        elbo.natural_gradient_update(s["m"], s["H"], gm, gH, bench.NG_LR)
+    torch.cuda.synchronize()
