@@ -773,8 +773,15 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
     constexpr int NGRP = PN_THREADS / MP;       // row groups in the element-wise phases
     constexpr int RPT = RP / NGRP;              // rows per thread in the element-wise phases
     constexpr int TM_COLS = (NT / 128) * PN_TMEM_COLS_PER_GROUP;                       // TMEM columns of this CTA
-    constexpr int NCT = (PN_TMEM_COLS_PER_GROUP / (2 * RPT)) < HLVAE_MAX_COMPS
-                            ? (PN_TMEM_COLS_PER_GROUP / (2 * RPT)) : HLVAE_MAX_COMPS;  // components cached in TMEM
+    // PARK (two-CTA shapes): the S accumulators and the per-component gradient sums live in this thread's TMEM
+    // columns between the phases that use them, which frees ~40 registers for the exponential pipelines of P1 / P5b
+    constexpr bool PARK = NT == 256;
+    constexpr int HGN = (3 * NC + 1) & ~1;                                              // gradient sums (padded: even)
+    constexpr int PARK_S = PARK ? 4 * SPW : 0;                                          // columns (2 per double)
+    constexpr int PARK_H = PARK ? 2 * HGN : 0;
+    constexpr int NCT_RAW = (PN_TMEM_COLS_PER_GROUP - PARK_S - PARK_H) / (2 * RPT);
+    constexpr int NCT = NCT_RAW < HLVAE_MAX_COMPS ? NCT_RAW : HLVAE_MAX_COMPS;          // components cached in TMEM
+    static_assert(NCT >= 1, "TMEM column plan");
     static_assert(WR >= 1 && WC >= 1 && SPW >= 1 && RPT >= 2 && RPT % 2 == 0 && RP % NGRP == 0, "tile shape");
     static_assert(NT / 32 >= RP / 8, "one warp per row tile in the r = K0xz w - mu product");
     static_assert(TM_COLS == 256 || TM_COLS == 512, "TMEM allocation: a power of two");
@@ -884,9 +891,9 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
     for (int t = 0; t < SPW; t++) sacc[t][0] = sacc[t][1] = 0.0;
     double p_acc = 0.0, gw_acc = 0.0, a_acc = 0.0;
     // gradient sums of the cached K0 components, kept per thread over the CTA's whole chunk (reduced once at the end)
-    double hg0[PN_NCACHE > 0 ? PN_NCACHE : 1], hg1[PN_NCACHE > 0 ? PN_NCACHE : 1], hg2[PN_NCACHE > 0 ? PN_NCACHE : 1];
+    double hgs[HGN];                                           // [3 r + {0, 1, 2}]: sums of g v, g v d, g v d^2
 #pragma unroll
-    for (int r = 0; r < PN_NCACHE; r++) hg0[r] = hg1[r] = hg2[r] = 0.0;
+    for (int r = 0; r < HGN; r++) hgs[r] = 0.0;
 
     if (tid == 0) meta[4] = s_begin;
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -903,6 +910,12 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
     const uint32_t tmem_base = (uint32_t)meta[5];
     // this thread's private columns: lane quadrant of its warp, column block of its group of four warps
     const uint32_t tm_mine = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * PN_TMEM_COLS_PER_GROUP);
+    const uint32_t tm_comp = tm_mine + PARK_S + PARK_H;       // the cached component values start here
+    if constexpr (PARK) {
+        tmem_store_doubles<2 * SPW>(tm_mine, &sacc[0][0]);
+        tmem_store_doubles<HGN>(tm_mine + PARK_S, hgs);
+        tmem_wait_st();
+    }
     const double wm = ws[em];
     // CSR offsets of subject s (s_begin <= s <= s_end): from the shared-memory copy where it reaches
     auto rows_at = [&](int s) { return s - s_begin <= PN_CHUNK_CSR ? csr_r[s - s_begin] : subj_ptr[s]; };
@@ -1075,7 +1088,7 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
                 }
 #pragma unroll
                 for (int k = 0; k < RPT; k++) kacc[k] = fma(osr, vv[k], kacc[k]);
-                if (r < NCT) tmem_store_doubles<RPT>(tm_mine + r * 2 * RPT, vv);
+                if (r < NCT) tmem_store_doubles<RPT>(tm_comp + r * 2 * RPT, vv);
             }
 #pragma unroll
             for (int k = 0; k < RPT; k++) {
@@ -1183,12 +1196,17 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
                 ao[t] = (rc >> 8) * 8 + kc;
                 bo[t] = (rc & 255) * 8 + kc;
             }
+            if constexpr (PARK) tmem_load_doubles<2 * SPW>(tm_mine, &sacc[0][0]);
             for (int k0 = 0; k0 < R4; k0 += 4) {
                 const double* kr_ = Kb + (k0 + kr) * LD;
                 const double* vr_ = Vb + (k0 + kr) * LD;
 #pragma unroll
                 for (int t = 0; t < SBASE; t++) dmma884(sacc[t][0], sacc[t][1], kr_[ao[t]], vr_[bo[t]]);
                 if (SREM != 0 && last_live) dmma884(sacc[SPW - 1][0], sacc[SPW - 1][1], kr_[ao[SPW - 1]], vr_[bo[SPW - 1]]);
+            }
+            if constexpr (PARK) {
+                tmem_store_doubles<2 * SPW>(tm_mine, &sacc[0][0]);
+                tmem_wait_st();
             }
         }
         __syncthreads();
@@ -1340,6 +1358,7 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
         }
         // ---- P5b: dJ/dK0xz = W + rho w^T, contracted with dK0xz/d{outputscale, lengthscale, Z}
         {
+            if constexpr (PARK) tmem_load_doubles<HGN>(tm_mine + PARK_S, hgs);
             double gk[RPT];
 #pragma unroll
             for (int k = 0; k < RPT; k++) {
@@ -1359,7 +1378,7 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
                     // values of this component back from the thread's TMEM columns; rows >= R and inducing points
                     // >= M carry gk = 0
                     double vv[RPT];
-                    tmem_load_doubles<RPT>(tm_mine + r * 2 * RPT, vv);
+                    tmem_load_doubles<RPT>(tm_comp + r * 2 * RPT, vv);
                     if (c.se_col >= 0) {
                         const double* xa = xsc + eg * HLVAE_MAX_Q + c.se_col;
 #pragma unroll
@@ -1411,7 +1430,7 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
                 if (r < PN_NCACHE) {
 #pragma unroll
                     for (int q = 0; q < PN_NCACHE; q++)
-                        if (q == r) { hg0[q] += s0; hg1[q] += s1; hg2[q] += s2; }
+                        if (q == r) { hgs[3 * q] += s0; hgs[3 * q + 1] += s1; hgs[3 * q + 2] += s2; }
                 } else {
                     const double gos = warp_sum(s0);
                     const double gls = warp_sum(s2) * osr * il3;
@@ -1422,8 +1441,16 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
                     if (c.se_col >= 0 && s1 != 0.0) atomicAdd(&zacc[em * HLVAE_MAX_COMPS + r], s1 * osr * il2);
                 }
             }
+            if constexpr (PARK) {
+                tmem_store_doubles<HGN>(tm_mine + PARK_S, hgs);
+                tmem_wait_st();
+            }
         }
         par ^= 1;
+    }
+    if constexpr (PARK) {
+        tmem_load_doubles<2 * SPW>(tm_mine, &sacc[0][0]);
+        tmem_load_doubles<HGN>(tm_mine + PARK_S, hgs);
     }
 
     // ---- cached components: reduce the per-thread gradient sums into hyp / zacc
@@ -1431,13 +1458,14 @@ kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__
     for (int r = 0; r < PN_NCACHE; r++) {
         if (r < sp0.ncomp) {
             const double osr = kps[r], il2 = kps[2 * HLVAE_MAX_COMPS + r], il3 = kps[3 * HLVAE_MAX_COMPS + r];
-            const double gos = warp_sum(hg0[r]);
-            const double gls = warp_sum(hg2[r]) * osr * il3;
+            const double gos = warp_sum(hgs[3 * r]);
+            const double gls = warp_sum(hgs[3 * r + 2]) * osr * il3;
             if (lane == 0) {
                 atomicAdd(&hyp[r], gos);
                 atomicAdd(&hyp[HLVAE_MAX_COMPS + r], gls);
             }
-            if (sp0.comp[r].se_col >= 0 && hg1[r] != 0.0) atomicAdd(&zacc[em * HLVAE_MAX_COMPS + r], hg1[r] * osr * il2);
+            if (sp0.comp[r].se_col >= 0 && hgs[3 * r + 1] != 0.0)
+                atomicAdd(&zacc[em * HLVAE_MAX_COMPS + r], hgs[3 * r + 1] * osr * il2);
         }
     }
     __syncthreads();
