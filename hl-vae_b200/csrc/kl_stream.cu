@@ -140,7 +140,14 @@ kl_subject_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict
     __syncthreads();
     const int64_t n_pairs = (int64_t)n_subj * L;
     for (int64_t pair = (int64_t)blockIdx.x * SJ_WARPS + warp; pair < n_pairs; pair += (int64_t)gridDim.x * SJ_WARPS) {
-    const int s = (int)(pair / L), l = (int)(pair % L);
+    int s, l;
+    if (n_pairs <= 0x7fffffff) {                          // 32-bit division (the 64-bit one is ~50 instructions)
+        s = (int)((unsigned)pair / (unsigned)L);
+        l = (int)((unsigned)pair - (unsigned)s * (unsigned)L);
+    } else {
+        s = (int)(pair / L);
+        l = (int)(pair % L);
+    }
     const int r0 = subj_ptr[s];
     const int T = subj_ptr[s + 1] - r0;
     if (T <= 0) continue;
@@ -173,12 +180,10 @@ kl_subject_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict
         kp[which * 24 + 8 + r] = h;
         kp[which * 24 + 16 + r] = i3;
     }
-    // identity padding of B, zero padding of the K0ss buffer
-    for (int e = lane; e < TP * LDA; e += 32) {
-        const int i = e / LDA, j = e - i * LDA;
-        Am[e] = (i == j && i >= T) ? 1.0 : 0.0;
-        Bm[e] = 0.0;
-    }
+    // zero both matrices (contiguous, 16-byte aligned: 128-bit stores), then the identity padding of B
+    for (int e = lane; e < TP * LDA; e += 32) reinterpret_cast<double2*>(Am)[e] = make_double2(0.0, 0.0);
+    __syncwarp();
+    if (lane >= T && lane < TP) Am[lane * LDA + lane] = 1.0;
     __syncwarp();
     const double nz = noise[l];
     // B_s = K1(x_s, x_s) + noise I (elbo_functions.py:249-250): lower triangle, mirrored
