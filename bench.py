@@ -609,8 +609,10 @@ def run_gpu(args):
     e2e = None
     if not args.no_e2e:
         reset_state()
+        cpus_before = os.sched_getaffinity(0)
         numa = bind_to_gpu_numa_node(dev)          # pinned pages are placed where the allocating thread runs
         host = {k: s[k].detach().cpu().pin_memory() for k in INPUT_KEYS}
+        os.sched_setaffinity(0, cpus_before)       # only the allocation is bound: the CPU legs keep every core
         h2d = sum(v.numel() * v.element_size() for v in host.values())
         sets = []
         for _ in range(2):
