@@ -1,8 +1,10 @@
 // Streaming part of the KL upper bound (elbo_functions.py:118-285): everything that scales
-// with the minibatch.  Two kernels:
-//   kl_subject_k : one warp per (subject, latent dim)  - T x T work (B_s, Cholesky, inverse)
-//   kl_panel_k   : one CTA per (latent dim, subject chunk) - K0xz rows on the fly,
-//                  B^-1 K0xz, sufficient statistics on the FP64 tensor pipe, gradients.
+// with the minibatch.  Kernels:
+//   kl_subject_k     : one warp per (subject, latent dim)  - T x T work (B_s, Cholesky, inverse), T <= 32
+//   kl_subject_big_k : one CTA per (subject, latent dim) for subjects of 33 .. HLVAE_TMAX rows
+//   kl_panel_k       : one CTA per (latent dim, subject chunk) - K0xz rows on the fly (values parked in tensor
+//                      memory for the gradient pass), B^-1 K0xz, sufficient statistics on the FP64 tensor pipe,
+//                      gradients; panel inputs software-pipelined with cp.async, Z by a TMA bulk copy.
 // Forward and backward are produced in one pass: with w = iK m and G = iK H iK - iK held
 // fixed, J = 1/2 (A + B + C + D + E - F) is linear in S, so dJ/d(inputs) needs nothing
 // from a later stage ("single-pass gradient").
@@ -749,8 +751,8 @@ struct PanelSmem {
     static constexpr size_t bytes = doubles * 8 + ints * 4;
 };
 
-// NT threads per CTA: 512 (one CTA per SM) or 256 with RP = 32 (two CTAs per SM whose barrier and
-// latency stalls cover each other; register file: 2 x 256 x 128).  Warps form a (NT / 128) x 4 grid over tiles.
+// NT threads per CTA: 512 (one CTA per SM) or 256 (two CTAs per SM whose barrier and latency stalls cover each other;
+// register file: 2 x 256 x 128).  Warps form a (NT / 128) x 4 grid over the tiles of the [RP x MP] products.
 template <int MP, int RP, bool G_SMEM, int NT, int NC, typename TS>
 __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1)
 kl_panel_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict__ os0, const double* __restrict__ ls0,
