@@ -258,3 +258,49 @@ def test_device_loader_layout_feeds_the_kl_kernels(device):
     a = h.run_kl_product(sub, device, layout=batch["layout"])
     b = h.run_kl_product(sub, device, layout=subjects.SubjectLayout.from_ids(sub["x"][:, 2].to(device)))
     assert h.rel_err(a["kld"], b["kld"]) < 1e-9 and h.rel_err(a["d_mu"], b["d_mu"]) < 1e-7
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("batched", [True, False])
+def test_fused_hyper_constraint_matches_stock_formulation(batched, device):
+    """hlvae_hyper_constrain (one launch for softplus + lower bound of every outputscale / lengthscale of both
+    kernels, one for the chain rule back) against the stock-PyTorch formulation FlatSpec.constrained: values and
+    gradients of the raw parameters, for parameters batched over the latent dimensions and for scalar ones that are
+    broadcast (their gradient is the sum over the latent dimensions)."""
+    from hlvae_b200 import kernels
+    L = 5
+    if batched:
+        k0, k1 = kernels.generate_kernel_batched(L, **h.synth.MASKED_KERNEL_ARGS)
+    else:
+        k0, k1 = kernels.generate_kernel_approx(**h.synth.MASKED_KERNEL_ARGS)
+    k0, k1 = k0.to(device).double(), k1.to(device).double()
+    gen = torch.Generator().manual_seed(3)
+    for prm in list(k0.parameters()) + list(k1.parameters()):
+        prm.data += (torch.randn(prm.shape, generator=gen, dtype=torch.float64) * 0.7).to(device)
+    fs0, fs1 = kernels.compile_spec(k0), kernels.compile_spec(k1)
+    ws = [torch.randn(n, L, generator=gen, dtype=torch.float64).to(device) for n in (fs0.ncomp, fs0.ncomp, fs1.ncomp, fs1.ncomp)]
+
+    def run(outs):
+        for prm in list(k0.parameters()) + list(k1.parameters()):
+            prm.grad = None
+        sum((o * w_).sum() for o, w_ in zip(outs, ws)).backward()
+        return [o.detach().clone() for o in outs], [prm.grad.clone() for prm in list(k0.parameters()) + list(k1.parameters())]
+
+    got_v, got_g = run(kernels.constrained_pair(fs0, fs1, L, device))
+    ref_v, ref_g = run(fs0.constrained(L, device) + fs1.constrained(L, device))
+    for a, b in zip(got_v, ref_v):
+        assert a.shape == b.shape and h.rel_err(a, b) < 1e-14
+    for a, b in zip(got_g, ref_g):
+        assert a.shape == b.shape and h.rel_err(a, b) < 1e-13
+
+
+@pytest.mark.gpu
+def test_many_tiny_subjects_per_chunk(device, monkeypatch):
+    """Chunks of more than 256 subjects (the part of the subject CSR a CTA copies to shared memory): 1500 subjects of
+    three or four rows in four chunks per latent dimension."""
+    monkeypatch.setenv("HLVAE_PANEL_WAVES", "0")
+    # 5200 rows against 16 inducing points drawn from them: cond(K0zz + eps I) puts the float64 floor of grad_m / grad_H
+    # at ~5e-6 (the same with chunks below 256 subjects: 3e-6 / 6e-6); every streamed quantity agrees to 1e-7
+    errs = h.check_kl_vs_oracle(device, 2, 16, 1500, 4, seed=41, tol=5e-5, hyper_tol=1e-3, ragged=True)
+    assert errs["kld"] < 1e-6 and errs["d_mu"] < 1e-8 and errs["d_z"] < 1e-6
+    print({k: f"{v:.1e}" for k, v in errs.items()})
