@@ -319,6 +319,9 @@ kl_subject_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict
 
     // K0(x_s, x_s) (:248), one evaluation per component and entry.  With wgt = B^-1_ij (x2 off the diagonal):
     //   B + D1 terms (:257,259) = sum_r os_r sum wgt v_r + sum_i B^-1_ii e^logv_i,   dJ/dK0ss = B^-1 / 2.
+    // (L^-1 is dead: its buffer is zeroed with 128-bit stores and collects K0ss)
+    for (int e = lane; e < TP * LDA / 2; e += 32) reinterpret_cast<double2*>(Bm)[e] = make_double2(0.0, 0.0);
+    __syncwarp();
     double bd = 0.0;
     for (int r = 0; r < sp0.ncomp; r++) {
         CompRegs c;
@@ -332,8 +335,7 @@ kl_subject_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict
             const double wv = ((i == j) ? 1.0 : 2.0) * Am[i * LDA + j] * v;
             gos += wv;
             gls = fma(wv * d, d, gls);
-            const double kv = osr * v;
-            Bm[i * LDA + j] = (r == 0) ? kv : Bm[i * LDA + j] + kv;
+            Bm[i * LDA + j] = fma(osr, v, Bm[i * LDA + j]);
         }
         gos = warp_sum(gos);
         gls = warp_sum(gls);
@@ -344,12 +346,7 @@ kl_subject_k(const __grid_constant__ hlvae_kspec_t sp0, const double* __restrict
         }
     }
     __syncwarp();
-    {   // lower triangle of K0ss is in place (the buffer still holds L^-1 elsewhere): clean the rest and mirror
-        for (int e = lane; e < TP * LDA; e += 32) {
-            const int i = e / LDA, j = e - i * LDA;
-            if (j > i || i >= T || sp0.ncomp == 0) Bm[e] = 0.0;
-        }
-        __syncwarp();
+    {   // lower triangle of K0ss is in place (zeros elsewhere): mirror
         for (int t = lane; t < TL; t += 32) {
             const int ij = tri[t], i = ij >> 8, j = ij & 255;
             Bm[j * LDA + i] = Bm[i * LDA + j];

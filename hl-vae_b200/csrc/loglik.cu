@@ -875,8 +875,10 @@ __device__ __forceinline__ void var_backward(const VarC<R>& v, const XT* __restr
     }
 }
 
+// (8 resident CTAs at 64 registers: 0.178 -> 0.172 ms at configs[1]; the forward kernel loses at that setting,
+// 0.273 -> 0.292 ms, and stays at 6 x 80)
 template <typename TS, typename TD, typename TM>
-__global__ void __launch_bounds__(LL_THREADS, sizeof(TS) == 4 ? 6 : 3)
+__global__ void __launch_bounds__(LL_THREADS, sizeof(TS) == 4 ? 8 : 3)
 loglik_bwd_k(int64_t N, int D, int tile_vars, int cap, int64_t ld_data, int64_t ld_theta,
              const int32_t* __restrict__ var_kind, const int32_t* __restrict__ var_nclass,
              const int32_t* __restrict__ var_dcol, const int32_t* __restrict__ var_pcol,
