@@ -762,17 +762,29 @@ template <typename R, typename XT, int CMAX>
 __device__ __forceinline__ void ord_backward(const XT* __restrict__ x_, R* __restrict__ t, int C, bool observed, R g) {
     struct { const XT* p; __device__ __forceinline__ R operator[](int c) const { return (R)p[c]; } } x{x_};
     const R eps = R(1e-6);
+    // softplus and its derivative of every logit from ONE exponential each (the second loop below used to evaluate
+    // both again): softplus = log1p(e^t), softplus' = e^t / (1 + e^t), t > 20 -> (t, 1)
+    auto sp_dsp = [](R tc, R& sp, R& dsp) {
+        const R et = Mth<R>::ex(fmin(tc, R(30)));
+        sp = tc > R(20) ? tc : Mth<R>::lg1p(et);
+        dsp = tc > R(20) ? R(1) : et * Mth<R>::rcp(R(1) + et);
+    };
     const R t_loc = t[C - 1];
-    const R loc = softplus_<R>(t_loc);
+    R loc, dloc;
+    sp_dsp(t_loc, loc, dloc);
     R dsg[CMAX], q[CMAX];      // dsg_c = sigma'(u_c) = sigma(u_c) sigma(-u_c)
+    R spv[CMAX], dspv[CMAX];
     R cum = R(0), prev = R(0), tot = R(0), sneg_prev = R(1);
     int vals = 0;
 #pragma unroll
     for (int c = 0; c < CMAX; c++) {
+        spv[c] = R(0);
+        dspv[c] = R(0);
         if (c < C) {
             R sg = R(1), qc, ds = R(0);
             if (c < C - 1) {
-                const R delta = clamp_<R>(softplus_<R>(t[c]), eps, R(1e20));
+                sp_dsp(t[c], spv[c], dspv[c]);
+                const R delta = clamp_<R>(spv[c], eps, R(1e20));
                 cum += delta;
                 const R e = Mth<R>::ex(loc - cum);                      // exp(-u_c)
                 sg = Mth<R>::rcp(R(1) + e);
@@ -817,13 +829,12 @@ __device__ __forceinline__ void ord_backward(const XT* __restrict__ x_, R* __res
             gq_next = gqc;
             g_loc -= gu;
             run += gu;                                   // reverse cumulative sum -> d/d delta_c
-            const R tc = t[c];
-            const R sp = softplus_<R>(tc);
-            const R ga = (sp >= eps && sp <= R(1e20)) ? run * dsoftplus_<R>(tc) : R(0);
+            const R sp = spv[c];
+            const R ga = (sp >= eps && sp <= R(1e20)) ? run * dspv[c] : R(0);
             t[c] = g * ga;
         }
     }
-    t[C - 1] = g * g_loc * dsoftplus_<R>(t_loc);
+    t[C - 1] = g * g_loc * dloc;
 
 }
 
