@@ -361,11 +361,17 @@ __device__ __forceinline__ void var_forward(const VarC<R>& v, const XT* __restri
             for (int c = 0; c < C; c++) {
                 R pc;
                 if (c < C - 1) {
-                    const R delta = clamp_<R>(softplus_<R>(t[c]), eps, R(1e20));
+                    // delta = softplus(t) and 1 - exp(-delta) = sigmoid(t) from one exponential (below the clamp:
+                    // 1 - exp(-eps)); the expm1 this replaces was the most expensive call of the path
+                    const R tc = t[c];
+                    const R et = Mth<R>::ex(fmin(tc, R(30)));
+                    const R sp = tc > R(20) ? tc : Mth<R>::lg1p(et);
+                    const R omx = sp < eps ? R(9.999995e-7) : (tc > R(20) ? R(1) : et * Mth<R>::rcp(R(1) + et));
+                    const R delta = clamp_<R>(sp, eps, R(1e20));
                     cum += delta;
                     const R e = Mth<R>::ex(loc - cum);                       // exp(-u_c)
                     const R sg = Mth<R>::rcp(R(1) + e);                      // sigma(u_c)
-                    pc = (c == 0) ? sg : sg * sneg_prev * (-Mth<R>::exm1(-delta));
+                    pc = (c == 0) ? sg : sg * sneg_prev * omx;
                     sneg_prev = (e > R(1e30)) ? R(1) : e * sg;               // sigma(-u_c)
                 } else {
                     pc = sneg_prev;                                          // 1 - sigma(u_{C-2})
@@ -791,7 +797,7 @@ __device__ __forceinline__ void ord_backward(const XT* __restrict__ x_, R* __res
                 const R sneg = (e > R(1e30)) ? R(1) : e * sg;           // sigma(-u_c), no cancellation
                 ds = sg * sneg;
                 if constexpr (sizeof(R) == 4) {
-                    qc = (c == 0) ? sg : sg * sneg_prev * (-Mth<R>::exm1(-delta));
+                    qc = (c == 0) ? sg : sg * sneg_prev * (spv[c] < eps ? R(9.999995e-7) : dspv[c]);   // 1 - exp(-delta)
                 } else {
                     qc = sg - prev;
                 }
