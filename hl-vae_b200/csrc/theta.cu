@@ -317,6 +317,10 @@ int launch_bwd(int64_t N, int D, int Y, int n_tiles, const int32_t* col_var, con
     auto kern = theta_bwd_k<TS, TM, YP>;
     constexpr int RB = ThRows<TS, YP, true>::value;
     const size_t smem = ((size_t)2 * RB * TH_THREADS + (size_t)TH_THREADS * Y) * sizeof(TS) + (size_t)TH_THREADS * Y * sizeof(int);
+    if (smem > 48 * 1024) {      // float64 storage with y_dim 15 / 16: above the default dynamic shared-memory limit
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+    }
     // CTAs per SM worth of row stripes: 9 / 18 / 36 / 72 measured 0.517 / 0.484 / 0.478 / 0.497 ms at the configs[1] batch
     dim3 grid(n_tiles, grid_stripes(N, n_tiles, RB, 36));
     kern<<<grid, TH_THREADS, smem, st>>>(N, D, Y, col_var, col_mode, var_pcol, tile_var, weight, bias, (const TS*)y, sn,
