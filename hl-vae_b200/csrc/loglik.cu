@@ -47,6 +47,7 @@ template <> struct Mth<double> {
     static __device__ __forceinline__ double ex(double x) { return exp(x); }
     static __device__ __forceinline__ double lg(double x) { return log(x); }
     static __device__ __forceinline__ double lg1p(double x) { return log1p(x); }
+    static __device__ __forceinline__ double lg1p_nn(double x) { return log1p(x); }
     static __device__ __forceinline__ double exm1(double x) { return expm1(x); }
     static __device__ __forceinline__ double lgam(double x) { return lgamma(x); }
     static __device__ __forceinline__ double rcp(double x) { return 1.0 / x; }
@@ -55,6 +56,17 @@ template <> struct Mth<float> {
     static __device__ __forceinline__ float ex(float x) { return __expf(x); }
     static __device__ __forceinline__ float lg(float x) { return __logf(x); }
     static __device__ __forceinline__ float lg1p(float x) { return log1pf(x); }
+    // log1p of a NON-NEGATIVE argument (the softplus sites: x = e^t).  [0, 0.25): x * degree-5 minimax polynomial of
+    // log1p(x) / x (1.1e-7 relative); above: lg2.approx of 1 + x, whose 2^-22 absolute error is at most 1e-6 of
+    // log(1.25).  11 instructions against log1pf's 28 (17 % of the tabular backward kernel's instructions).
+    static __device__ __forceinline__ float lg1p_nn(float x) {
+        float p = fmaf(-0.09238353371620178f, x, 0.1817312091588974f);
+        p = fmaf(p, x, -0.2477860152721405f);
+        p = fmaf(p, x, 0.33320868015289307f);
+        p = fmaf(p, x, -0.49999740719795227f);
+        p = fmaf(p, x, 1.0f);
+        return x < 0.25f ? p * x : __logf(1.0f + x);
+    }
     static __device__ __forceinline__ float exm1(float x) { return expm1f(x); }
     static __device__ __forceinline__ float lgam(float x) { return lgammaf(x); }
     static __device__ __forceinline__ float rcp(float x) { return __fdividef(1.0f, x); }
@@ -62,7 +74,7 @@ template <> struct Mth<float> {
 
 // torch.nn.functional.softplus (beta = 1, threshold = 20) and its derivative
 template <typename R> __device__ __forceinline__ R softplus_(R x) {
-    return x > R(20) ? x : Mth<R>::lg1p(Mth<R>::ex(x));
+    return x > R(20) ? x : Mth<R>::lg1p_nn(Mth<R>::ex(x));
 }
 template <typename R> __device__ __forceinline__ R sigmoid_(R x) { return Mth<R>::rcp(R(1) + Mth<R>::ex(-x)); }
 template <typename R> __device__ __forceinline__ R dsoftplus_(R x) { return x > R(20) ? R(1) : sigmoid_<R>(x); }
@@ -365,7 +377,7 @@ __device__ __forceinline__ void var_forward(const VarC<R>& v, const XT* __restri
                     // 1 - exp(-eps)); the expm1 this replaces was the most expensive call of the path
                     const R tc = t[c];
                     const R et = Mth<R>::ex(fmin(tc, R(30)));
-                    const R sp = tc > R(20) ? tc : Mth<R>::lg1p(et);
+                    const R sp = tc > R(20) ? tc : Mth<R>::lg1p_nn(et);
                     const R omx = sp < eps ? R(9.999995e-7) : (tc > R(20) ? R(1) : et * Mth<R>::rcp(R(1) + et));
                     const R delta = clamp_<R>(sp, eps, R(1e20));
                     cum += delta;
@@ -473,12 +485,12 @@ __device__ __forceinline__ void tma_unstage_row(T* __restrict__ dst, const T* __
 // of 16 bytes): thread = (row tid / 16, job tid % 16) - job 0 issues the row's bulk store, the jobs after it write
 // the at most E - 1 elements of the partial chunk at either end.  (Row by row, every thread redid the chunk
 // arithmetic for every row: 13 % of the forward kernel's instructions.)
-template <typename T>
+template <typename T, int ROWS = LL_ROWS>
 __device__ __forceinline__ void tma_unstage_batch(T* __restrict__ dst0, int64_t ld, const T* __restrict__ src0, int lds,
                                                   int shift, int span, int nr, int tid) {
     constexpr int E = 16 / (int)sizeof(T);
-    static_assert(LL_THREADS / LL_ROWS >= 2 * E - 1 || E > 8, "jobs per row");
-    const int r = tid / (LL_THREADS / LL_ROWS), j = tid % (LL_THREADS / LL_ROWS);
+    static_assert(LL_THREADS / ROWS >= 2 * E - 1 || E > 8, "jobs per row");
+    const int r = tid / (LL_THREADS / ROWS), j = tid % (LL_THREADS / ROWS);
     if (r >= nr) return;
     const int i0 = shift > 0 ? 1 : 0;
     const int i1 = (shift + span) / E;
@@ -489,8 +501,8 @@ __device__ __forceinline__ void tma_unstage_batch(T* __restrict__ dst0, int64_t 
     if (j == 0) {
         if (i1 > i0) bulk_s2g(dst + (E * i0 - shift), src + E * i0, (unsigned)((i1 - i0) * 16));
     } else {
-        for (int e = j - 1; e < head; e += LL_THREADS / LL_ROWS - 1) dst[e] = src[shift + e];
-        for (int e = tail0 + j - 1; e < span; e += LL_THREADS / LL_ROWS - 1) dst[e] = src[shift + e];
+        for (int e = j - 1; e < head; e += LL_THREADS / ROWS - 1) dst[e] = src[shift + e];
+        for (int e = tail0 + j - 1; e < span; e += LL_THREADS / ROWS - 1) dst[e] = src[shift + e];
     }
 }
 
@@ -772,7 +784,7 @@ __device__ __forceinline__ void ord_backward(const XT* __restrict__ x_, R* __res
     // both again): softplus = log1p(e^t), softplus' = e^t / (1 + e^t), t > 20 -> (t, 1)
     auto sp_dsp = [](R tc, R& sp, R& dsp) {
         const R et = Mth<R>::ex(fmin(tc, R(30)));
-        sp = tc > R(20) ? tc : Mth<R>::lg1p(et);
+        sp = tc > R(20) ? tc : Mth<R>::lg1p_nn(et);
         dsp = tc > R(20) ? R(1) : et * Mth<R>::rcp(R(1) + et);
     };
     const R t_loc = t[C - 1];
@@ -911,6 +923,15 @@ __device__ __forceinline__ void var_backward(const VarC<R>& v, const XT* __restr
 
 // (8 resident CTAs at 64 registers: 0.178 -> 0.172 ms at configs[1]; the forward kernel loses at that setting,
 // 0.273 -> 0.292 ms, and stays at 6 x 80)
+// Rows per batch of the backward kernel.  With float data the stage of 8 rows is 47 KB (4 CTAs = 16 warps per SM, and the
+// single-stage pipeline leaves the SM idle while a CTA waits for its copies): 4 rows -> 8 CTAs per SM, tabular
+// 64 000 rows 0.253 -> 0.213 ms.  uint8 data (D4: 30 KB, 6+ CTAs): 8 rows stay faster (0.178 vs 0.192 ms); so does the
+// forward kernel on both layouts (0.250 vs 0.266, 0.276 vs 0.308 ms).
+template <typename TS, typename TD>
+struct BwdRows {
+    static constexpr int value = (sizeof(TD) >= 4 && LL_ROWS > 4) ? 4 : LL_ROWS;
+};
+
 template <typename TS, typename TD, typename TM>
 __global__ void __launch_bounds__(LL_THREADS, sizeof(TS) == 4 ? 8 : 3)
 loglik_bwd_k(int64_t N, int D, int tile_vars, int cap, int64_t ld_data, int64_t ld_theta,
@@ -920,13 +941,14 @@ loglik_bwd_k(int64_t N, int D, int tile_vars, int cap, int64_t ld_data, int64_t 
              const TM* __restrict__ mask, const TS* __restrict__ g_lp, const double* __restrict__ g_scalar,
              TS* __restrict__ g_theta, double* __restrict__ g_lvy) {
     using R = TS;
+    constexpr int LR = BwdRows<TS, TD>::value;
     extern __shared__ __align__(16) unsigned char ll_smem[];
     const int capt = cap + 8, capx = cap + 16;
-    // per stage: sT [LL_ROWS][capt] theta (overwritten with g_theta), sG [LL_ROWS][LL_CAPM] upstream gradient,
-    // sX [LL_ROWS][capx] data, sK [LL_ROWS][LL_CAPM] mask
-    const size_t stage_bytes = (size_t)LL_ROWS * ((capt + LL_CAPM) * sizeof(R) + capx * sizeof(TD) + LL_CAPM * sizeof(TM));
-    __shared__ int sShift[LL_STAGES][LL_ROWS], sShiftT[LL_STAGES][LL_ROWS], sShiftM[LL_STAGES][LL_ROWS],
-        sShiftG[LL_STAGES][LL_ROWS];
+    // per stage: sT [LR][capt] theta (overwritten with g_theta), sG [LR][LL_CAPM] upstream gradient,
+    // sX [LR][capx] data, sK [LR][LL_CAPM] mask
+    const size_t stage_bytes = (size_t)LR * ((capt + LL_CAPM) * sizeof(R) + capx * sizeof(TD) + LL_CAPM * sizeof(TM));
+    __shared__ int sShift[LL_STAGES][LR], sShiftT[LL_STAGES][LR], sShiftM[LL_STAGES][LR],
+        sShiftG[LL_STAGES][LR];
     const bool m_ok = (((uintptr_t)mask | (uintptr_t)(N * D * (int64_t)sizeof(TM))) & 15) == 0;
     const bool g_ok = (((uintptr_t)g_lp | (uintptr_t)(N * D * (int64_t)sizeof(TS))) & 15) == 0;
     const int span_m = min(D, d0_(blockIdx.x, tile_vars) + tile_vars) - d0_(blockIdx.x, tile_vars);
@@ -943,7 +965,7 @@ loglik_bwd_k(int64_t N, int D, int tile_vars, int cap, int64_t ld_data, int64_t 
     const int span_p = max(0, min(cap, var_pcol[d1 - 1] + var_nclass[d1 - 1] - ps0));
     const VarC<R> v = load_var<R>(d, D, active, var_kind, var_nclass, var_dcol, var_pcol, vparam, xs0, ps0, cap);
     const R gs = g_scalar ? (R)(*g_scalar) : R(0);
-    const int64_t stride = (int64_t)gridDim.y * LL_ROWS;
+    const int64_t stride = (int64_t)gridDim.y * LR;
     __shared__ __align__(8) unsigned long long mbar[LL_STAGES];
     const bool use_tma = x_ok && t_ok && m_ok && (!g_lp || g_ok);
     const bool uni_t = use_tma && ld_theta % (16 / (int)sizeof(TS)) == 0;
@@ -966,11 +988,11 @@ loglik_bwd_k(int64_t N, int D, int tile_vars, int cap, int64_t ld_data, int64_t 
         if (n0 < N && use_tma) {
             if (tid < 32) {        // warp 0: lane = (array, row); every lane issues its own bulk copy
                 R* sT = reinterpret_cast<R*>(ll_smem + stg * stage_bytes);
-                R* sG = sT + LL_ROWS * capt;
-                TD* sX = reinterpret_cast<TD*>(sG + LL_ROWS * LL_CAPM);
-                TM* sK = reinterpret_cast<TM*>(sX + LL_ROWS * capx);
-                const int nr = (int)min((int64_t)LL_ROWS, N - n0);
-                const int r = tid % LL_ROWS, arr = tid / LL_ROWS;
+                R* sG = sT + LR * capt;
+                TD* sX = reinterpret_cast<TD*>(sG + LR * LL_CAPM);
+                TM* sK = reinterpret_cast<TM*>(sX + LR * capx);
+                const int nr = (int)min((int64_t)LR, N - n0);
+                const int r = tid % LR, arr = tid / LR;
                 const bool job = r < nr && (arr < 3 || (arr == 3 && g_lp != nullptr));
                 unsigned bytes = 0;
                 int shift = 0;
@@ -1003,10 +1025,10 @@ loglik_bwd_k(int64_t N, int D, int tile_vars, int cap, int64_t ld_data, int64_t 
             }
         } else if (n0 < N) {
             R* sT = reinterpret_cast<R*>(ll_smem + stg * stage_bytes);
-            R* sG = sT + LL_ROWS * capt;
-            TD* sX = reinterpret_cast<TD*>(sG + LL_ROWS * LL_CAPM);
-            TM* sK = reinterpret_cast<TM*>(sX + LL_ROWS * capx);
-            const int nr = (int)min((int64_t)LL_ROWS, N - n0);
+            R* sG = sT + LR * capt;
+            TD* sX = reinterpret_cast<TD*>(sG + LR * LL_CAPM);
+            TM* sK = reinterpret_cast<TM*>(sX + LR * capx);
+            const int nr = (int)min((int64_t)LR, N - n0);
             for (int r = 0; r < nr; r++) {
                 const int st_ = stage_row<TS>(sT + r * capt, theta + (n0 + r) * ld_theta + ps0, span_p, tid, t_ok);
                 const int sh = stage_row<TD>(sX + r * capx, data + (n0 + r) * ld_data + xs0, span_x, tid, x_ok);
@@ -1021,8 +1043,8 @@ loglik_bwd_k(int64_t N, int D, int tile_vars, int cap, int64_t ld_data, int64_t 
 
     double ge_acc = 0.0;
     int stg = 0;
-    if (LL_STAGES == 2) prefetch((int64_t)blockIdx.y * LL_ROWS, 0);
-    for (int64_t n0 = (int64_t)blockIdx.y * LL_ROWS; n0 < N; n0 += stride, stg ^= (LL_STAGES - 1)) {
+    if (LL_STAGES == 2) prefetch((int64_t)blockIdx.y * LR, 0);
+    for (int64_t n0 = (int64_t)blockIdx.y * LR; n0 < N; n0 += stride, stg ^= (LL_STAGES - 1)) {
         if (LL_STAGES == 2) {
             prefetch(n0 + stride, stg ^ 1);
             cp_async_wait_group<1>();
@@ -1036,10 +1058,10 @@ loglik_bwd_k(int64_t N, int D, int tile_vars, int cap, int64_t ld_data, int64_t 
             phase[stg] ^= 1;
         }
         R* sT = reinterpret_cast<R*>(ll_smem + stg * stage_bytes);
-        R* sG = sT + LL_ROWS * capt;
-        TD* sX = reinterpret_cast<TD*>(sG + LL_ROWS * LL_CAPM);
-        TM* sK = reinterpret_cast<TM*>(sX + LL_ROWS * capx);
-        const int nr = (int)min((int64_t)LL_ROWS, N - n0);
+        R* sG = sT + LR * capt;
+        TD* sX = reinterpret_cast<TD*>(sG + LR * LL_CAPM);
+        TM* sK = reinterpret_cast<TM*>(sX + LR * capx);
+        const int nr = (int)min((int64_t)LR, N - n0);
         if (active) {
             // one row loop per evaluator (the type of a thread's variable is fixed): see loglik_fwd_k
             auto rows = [&](auto&& eval) {
@@ -1082,8 +1104,8 @@ loglik_bwd_k(int64_t N, int D, int tile_vars, int cap, int64_t ld_data, int64_t 
         if (use_tma) fence_async_smem();
         __syncthreads();
         if (uni_t) {
-            tma_unstage_batch<TS>(g_theta + n0 * ld_theta + ps0, ld_theta, sT, capt, shift_t, span_p, nr, tid);
-            if (tid % (LL_THREADS / LL_ROWS) == 0) {
+            tma_unstage_batch<TS, LR>(g_theta + n0 * ld_theta + ps0, ld_theta, sT, capt, shift_t, span_p, nr, tid);
+            if (tid % (LL_THREADS / LR) == 0) {
                 bulk_commit();
                 bulk_wait_read();
             }
@@ -1189,8 +1211,8 @@ struct Tiling {
 // 0.354 / 0.367 ms; tabular D = 256 at 64 000 rows: 0.46 -> 0.39 ms forward, 0.51 -> 0.40 ms backward at 6): shorter
 // CTAs let the SMs that finish early pick up more work instead of idling through the tail of a single wave.
 constexpr int LL_WAVES = 6;
-Tiling make_tiling(int64_t N, int D, int ctas_per_sm) {
-    N = (N + LL_ROWS - 1) / LL_ROWS;            // row batches
+Tiling make_tiling(int64_t N, int D, int ctas_per_sm, int rows_per_batch = LL_ROWS) {
+    N = (N + rows_per_batch - 1) / rows_per_batch;            // row batches
     Tiling t;
     t.n_tiles = (D + LL_THREADS - 1) / LL_THREADS;
     t.tile_vars = (D + t.n_tiles - 1) / t.n_tiles;
@@ -1281,15 +1303,16 @@ extern "C" int hlvae_loglik_bwd(int64_t N, int D, int64_t ld_data, int64_t ld_th
     Tiling tl = make_tiling(N, D, 1);
     const int cap = (tl.tile_vars * max_class + 15) & ~15;
     const size_t msz = mask_dtype == HLVAE_U8 ? 1 : esz;
-    const size_t smem = (size_t)LL_STAGES * LL_ROWS * ((cap + 8 + LL_CAPM) * esz + (cap + 16) * xsz + LL_CAPM * msz);
 #define HLVAE_LL_BWD(TS, TD, TM)                                                                                     \
     {                                                                                                                \
         auto kern = loglik_bwd_k<TS, TD, TM>;                                                                        \
+        constexpr int LR = BwdRows<TS, TD>::value;                                                                   \
+        const size_t smem = (size_t)LL_STAGES * LR * ((cap + 8 + LL_CAPM) * esz + (cap + 16) * xsz + LL_CAPM * msz); \
         int rc = set_smem(kern, smem);                                                                               \
         if (rc) return rc;                                                                                           \
         int nb = 1;                                                                                                  \
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, LL_THREADS, smem);                                  \
-        tl = make_tiling(N, D, nb < 1 ? 1 : nb);                                                                     \
+        tl = make_tiling(N, D, nb < 1 ? 1 : nb, LR);                                                                   \
         dim3 grid(tl.n_tiles, tl.rows);                                                                              \
         kern<<<grid, LL_THREADS, smem, st>>>(N, D, tl.tile_vars, cap, ld_data, ld_theta, var_kind, var_nclass,       \
                                              var_dcol, var_pcol, vparam, (const TD*)data, (const TS*)theta,          \

@@ -7,13 +7,25 @@ import __graft_entry__ as g
 g.build()
 from hlvae_b200 import loglik, synth
 dev = torch.device("cuda:0")
-lay = loglik.VarLayout(synth.HEALTHMNIST_D4_TYPES, dev)
 gen = torch.Generator(device=dev).manual_seed(0)
 N = int(os.environ.get("ROWS", "16000"))
-data, mask = synth.device_likelihood_batch(lay, N, dev, gen, dtype=torch.uint8)
-theta = torch.randn(N, lay.P_theta, device=dev, generator=gen).requires_grad_(True)
-lvr = torch.zeros(324, dtype=torch.float64, device=dev)
-vparam = lay.vparam(log_vy_real=lvr, conv=True)
+if os.environ.get("LAYOUT") == "tabular":                  # BASELINE.json configs[3]: float32 data, uint8 mask
+    import numpy as np
+    lay = loglik.VarLayout(synth.TABULAR_TYPES, dev)
+    d4k, m4k = synth.likelihood_batch(synth.TABULAR_TYPES, 4000, np.random.default_rng(9))
+    data = d4k.float().repeat(N // 4000, 1).to(dev)
+    mask = m4k.to(torch.uint8).repeat(N // 4000, 1).to(dev)
+    N = data.shape[0]
+    z32 = torch.zeros(32, dtype=torch.float64, device=dev)
+    vparam = lay.vparam(z32.clone(), z32.clone(), [z32, torch.ones_like(z32)], [z32, torch.ones_like(z32)])
+else:
+    lay = loglik.VarLayout(synth.HEALTHMNIST_D4_TYPES, dev)
+    data, mask = synth.device_likelihood_batch(lay, N, dev, gen, dtype=torch.uint8)
+    vparam = lay.vparam(log_vy_real=torch.zeros(324, dtype=torch.float64, device=dev), conv=True)
+theta = torch.randn(N, lay.P_theta, device=dev, generator=gen)
+if os.environ.get("STORAGE") == "f64":                     # the reference's storage: every tensor float64
+    theta, data, mask = theta.double(), data.double(), mask.double()
+theta.requires_grad_(True)
 for _ in range(3):
     theta.grad = None
     out = loglik.fused_loglik(lay, data, mask, theta, vparam, monitor=True)
