@@ -66,7 +66,7 @@ _SIGS = {
     "hlvae_batch_norm_stats": ([_L, _I, _L, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _P, _P], _I),
     "hlvae_batch_norm_apply": ([_L, _I, _L, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P], _I),
     "hlvae_theta_fwd": ([_L, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _L, _L, _L, _I, _P, _L, _P], _I),
-    "hlvae_theta_bwd": ([_L, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _L, _L, _L, _I, _P, _I, _P, _L, _P, _P, _P, _P], _I),
+    "hlvae_theta_bwd": ([_L, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _L, _L, _L, _I, _P, _I, _P, _L, _P, _P, _P, _P], _I),
 }
 EXPORTED = tuple(_SIGS)
 

@@ -21,6 +21,9 @@
 #ifndef HLVAE_TH_BWD_CTAS
 #define HLVAE_TH_BWD_CTAS 3
 #endif
+#ifndef HLVAE_TV_BWD_CTAS
+#define HLVAE_TV_BWD_CTAS 32      // CTAs per SM worth of row stripes, thread-per-variable backward kernel
+#endif
 
 namespace {
 
@@ -279,6 +282,232 @@ theta_bwd_k(int64_t N, int D, int Y, const int32_t* __restrict__ col_var, const 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Thread-per-VARIABLE backward kernel: layouts whose variables own at most TV_CV theta columns (up to 5 classes:
+// every layout the reference ships) with y_dim <= 8.  The thread-per-column kernel above re-loads a variable's y
+// values once per column, crosses shared memory for d/dy and spends 435 instructions per (row, variable); here a
+// thread owns a variable: its heads and its weight / bias gradient sums sit in registers, the g_theta rows of the tile
+// (coalesced row segments) and the thread's own y values of the NEXT row batch arrive by cp.async while the current
+// batch is evaluated, d/dy is formed and written by the same thread (coalesced in the convolutional layout):
+// 270 instructions per (row, variable), configs[1] batch 0.478 -> 0.395 ms, tabular 64 000 rows 0.317 -> 0.278 ms.
+// (The forward direction was measured the same way and dropped: 0.250 against 0.205 ms for thread-per-column, whose
+// stores are already coalesced and which needs no staging at all.)
+constexpr int TV_THREADS = 128;   // variables per tile
+constexpr int TV_CV = 5;          // theta columns per variable held in registers
+#ifndef HLVAE_TV_BWD_MIN_CTAS
+#define HLVAE_TV_BWD_MIN_CTAS 1
+#endif
+#ifndef HLVAE_TV_BWD_BYTES
+#define HLVAE_TV_BWD_BYTES 80
+#endif
+template <typename TS, int YP>
+struct TvRows {
+    static constexpr int raw = HLVAE_TV_BWD_BYTES / (YP * (int)sizeof(TS));
+    static constexpr int value = raw < 1 ? 1 : (raw > 8 ? 8 : raw);
+};
+
+template <typename TS, int YP>
+struct TvVar {            // one variable's heads
+    TS w[TV_CV][YP], b[TV_CV];
+    int pc, lp, nc;       // first theta column (global / inside the tile), number of columns
+    unsigned dep, sig, bo;   // bit c: column c depends on y / has the Sigmoid / is its bias (ordinal thresholds)
+};
+
+template <typename TS, int YP>
+__device__ __forceinline__ void tv_load(TvVar<TS, YP>& v, bool live, int d, int p0, const int32_t* __restrict__ var_pcol,
+                                        const int32_t* __restrict__ col_mode, const double* __restrict__ weight,
+                                        const double* __restrict__ bias) {
+    v.pc = live ? var_pcol[d] : p0;
+    v.lp = v.pc - p0;
+    v.nc = live ? var_pcol[d + 1] - v.pc : 0;
+    v.dep = v.sig = v.bo = 0;
+#pragma unroll
+    for (int c = 0; c < TV_CV; c++) {
+        const bool on = c < v.nc;
+        const int mode = on ? col_mode[v.pc + c] : HLVAE_HEAD_ZERO;
+        const bool ydep = (mode == HLVAE_HEAD_AFFINE || mode == HLVAE_HEAD_SIGMOID);
+        if (ydep) v.dep |= 1u << c;
+        if (mode == HLVAE_HEAD_SIGMOID) v.sig |= 1u << c;
+        if (mode == HLVAE_HEAD_BIAS) v.bo |= 1u << c;
+        v.b[c] = (mode != HLVAE_HEAD_ZERO) ? (TS)bias[v.pc + c] : (TS)0;
+#pragma unroll
+        for (int k = 0; k < YP; k++) v.w[c][k] = ydep ? (TS)weight[(int64_t)(v.pc + c) * YP + k] : (TS)0;
+    }
+}
+
+struct TvTile {
+    int d0, d1, p0, ncols;
+    int64_t r_begin, r_end;
+};
+__device__ __forceinline__ TvTile tv_tile(const int32_t* __restrict__ var_pcol, int D, int64_t N, int RB) {
+    TvTile t;
+    t.d0 = blockIdx.x * TV_THREADS;
+    t.d1 = min(D, t.d0 + TV_THREADS);
+    t.p0 = var_pcol[t.d0];
+    t.ncols = var_pcol[t.d1] - t.p0;
+    const int64_t batches = (N + RB - 1) / RB;
+    const int64_t per = (batches + gridDim.y - 1) / gridDim.y;
+    t.r_begin = (int64_t)blockIdx.y * per * RB;
+    t.r_end = t.r_begin + per * RB;
+    if (t.r_end > N) t.r_end = N;
+    return t;
+}
+
+// Rows of the tile's column span, global (row stride ld) -> shared ([RB][cap]) by cp.async: thread i of the CTA moves
+// columns i, i + 128, ... (every warp instruction covers 128 contiguous bytes; no registers, no wait on the issuing thread)
+template <typename TS, int RB>
+__device__ __forceinline__ void tv_rows_in(TS* __restrict__ dst, int cap, const TS* __restrict__ src, int ld, int ncols,
+                                           int nr, int tid) {
+#pragma unroll
+    for (int r = 0; r < RB; r++) {
+        if (r < nr) {
+#pragma unroll
+            for (int j = 0; j < TV_CV; j++) {
+                const int i = tid + j * TV_THREADS;
+                if (i < ncols) hlvae::cp_async<(int)sizeof(TS)>(dst + r * cap + i, src + r * ld + i);
+            }
+        }
+    }
+    hlvae::cp_async_commit();
+}
+
+// A thread's own y values of one row batch, global -> shared by cp.async: sY[r][k][thread].  Thread-private (the
+// thread that copies an element is the only one that reads it), so cp.async.wait_all alone orders copy and use.
+template <typename TS, int YP, int RB>
+__device__ __forceinline__ void tv_y_in(TS* __restrict__ sy, const TS* __restrict__ src, int sn, int sk, int nr, int tid) {
+#pragma unroll
+    for (int r = 0; r < RB; r++) {
+        if (r < nr) {
+#pragma unroll
+            for (int k = 0; k < YP; k++)
+                hlvae::cp_async<(int)sizeof(TS)>(sy + (r * YP + k) * TV_THREADS + tid, src + r * sn + k * sk);
+        }
+    }
+}
+
+template <typename TS, typename TM, int YP>
+__global__ void __launch_bounds__(TV_THREADS, sizeof(TS) == 4 ? HLVAE_TV_BWD_MIN_CTAS : 1)
+theta_bwd_var_k(int64_t N, int D, int cap, const int32_t* __restrict__ col_mode, const int32_t* __restrict__ var_pcol,
+                const double* __restrict__ weight, const double* __restrict__ bias, const TS* __restrict__ y, int64_t sn,
+                int64_t sd, int64_t sk, const TM* __restrict__ mask, const TS* __restrict__ g_theta, int64_t ld_theta,
+                TS* __restrict__ g_y, double* __restrict__ g_weight, double* __restrict__ g_bias) {
+    constexpr int RB = TvRows<TS, YP>::value;
+    constexpr int FLUSH = (256 + RB - 1) / RB;   // batches between two flushes of the storage-type parameter-gradient sums
+    extern __shared__ __align__(16) unsigned char tv_smem[];
+    TS* sG = reinterpret_cast<TS*>(tv_smem);                  // [2][RB][cap] upstream gradient rows of the tile
+    TS* sY = sG + 2 * RB * cap;                               // [2][RB][YP][128] the threads' y values
+    const int tid = threadIdx.x;
+    const TvTile t = tv_tile(var_pcol, D, N, RB);
+    if (t.r_begin >= t.r_end) return;
+    const int d = t.d0 + tid;
+    const bool live = d < t.d1;
+    const int dd = live ? d : t.d0;
+    const TS* yv = y + (int64_t)dd * sd;
+    TS* gyv = g_y + (int64_t)dd * sd;
+    const TM* mv = mask + dd;
+    const TS* gin = g_theta + t.p0;
+    int sn32 = (int)sn, sk32 = (int)sk, D32 = D;
+    // software pipeline: g_theta rows (shared by the CTA) and the thread's own y values of batch j + 1 travel to the
+    // other buffer (cp.async) and its mask entries to registers while batch j is evaluated
+    auto issue = [&](int64_t n0, int b) {
+        const int nr = (int)min((int64_t)RB, t.r_end - n0);
+        tv_y_in<TS, YP, RB>(sY + b * RB * YP * TV_THREADS, yv + n0 * sn, sn32, sk32, nr, tid);
+        tv_rows_in<TS, RB>(sG + b * RB * cap, cap, gin + n0 * ld_theta, (int)ld_theta, t.ncols, nr, tid);   // commits
+    };
+    auto load_mask = [&](TM (&m)[RB], int64_t n0) {
+        const TM* pm = mv + n0 * D;
+#pragma unroll
+        for (int r = 0; r < RB; r++) m[r] = (n0 + r < t.r_end) ? pm[r * D32] : (TM)0;
+    };
+    issue(t.r_begin, 0);
+    TM m[RB], m_next[RB];
+    load_mask(m, t.r_begin);
+    TvVar<TS, YP> v;
+    tv_load<TS, YP>(v, live, d, t.p0, var_pcol, col_mode, weight, bias);
+    const unsigned grad_cols = v.dep | v.bo;                  // columns that receive a gradient at all
+    TS gw[TV_CV][YP], gb[TV_CV];
+#pragma unroll
+    for (int c = 0; c < TV_CV; c++) {
+        gb[c] = (TS)0;
+#pragma unroll
+        for (int k = 0; k < YP; k++) gw[c][k] = (TS)0;
+    }
+    auto flush = [&]() {
+#pragma unroll
+        for (int c = 0; c < TV_CV; c++) {
+            if ((grad_cols >> c) & 1u) {
+                if (gb[c] != (TS)0) atomicAdd(g_bias + v.pc + c, (double)gb[c]);
+                if ((v.dep >> c) & 1u) {
+#pragma unroll
+                    for (int k = 0; k < YP; k++)
+                        if (gw[c][k] != (TS)0) atomicAdd(g_weight + (int64_t)(v.pc + c) * YP + k, (double)gw[c][k]);
+                }
+            }
+            gb[c] = (TS)0;
+#pragma unroll
+            for (int k = 0; k < YP; k++) gw[c][k] = (TS)0;
+        }
+    };
+    int buf = 0, since = 0;
+    for (int64_t n0 = t.r_begin; n0 < t.r_end; n0 += RB, buf ^= 1) {
+        const int nr = (int)min((int64_t)RB, t.r_end - n0);
+        const TS* sg = sG + buf * RB * cap;
+        const TS* sy = sY + buf * RB * YP * TV_THREADS + tid;
+        asm volatile("" : "+r"(sn32), "+r"(sk32), "+r"(D32));
+        hlvae::cp_async_wait_all();
+        __syncthreads();                                      // batch j's g rows are visible; batch j - 1 is done with buf ^ 1
+        const bool more = n0 + RB < t.r_end;
+        if (more) {
+            issue(n0 + RB, buf ^ 1);
+            load_mask(m_next, n0 + RB);
+        }
+        if (live) {
+            TS* pg = gyv + n0 * sn;
+#pragma unroll
+            for (int r = 0; r < RB; r++) {
+                if (r < nr) {
+                    TS yk[YP], dy[YP];
+#pragma unroll
+                    for (int k = 0; k < YP; k++) {
+                        yk[k] = sy[(r * YP + k) * TV_THREADS];
+                        dy[k] = (TS)0;
+                    }
+#pragma unroll
+                    for (int c = 0; c < TV_CV; c++) {
+                        if (c < v.nc) {
+                            TS gr = (m[r] != (TM)0 && ((grad_cols >> c) & 1u)) ? sg[r * cap + v.lp + c] : (TS)0;
+                            if ((v.sig >> c) & 1u) {
+                                TS z = v.b[c];
+#pragma unroll
+                                for (int k = 0; k < YP; k++) z = fma(v.w[c][k], yk[k], z);
+                                const TS s_ = sigmoid_t<TS>(z);
+                                gr *= s_ * ((TS)1 - s_);
+                            }
+                            gb[c] += gr;
+#pragma unroll
+                            for (int k = 0; k < YP; k++) {
+                                dy[k] = fma(gr, v.w[c][k], dy[k]);
+                                gw[c][k] = fma(gr, yk[k], gw[c][k]);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < YP; k++) pg[r * sn32 + k * sk32] = dy[k];
+                }
+            }
+            if (++since == FLUSH) {
+                flush();
+                since = 0;
+            }
+        }
+        if (more) {
+#pragma unroll
+            for (int r = 0; r < RB; r++) m[r] = m_next[r];
+        }
+    }
+    if (live) flush();
+}
+
 // 32-bit in-batch offsets: (rows in flight) * row stride + y_dim * k stride must fit in an int
 bool th_offsets_fit(int64_t sn, int64_t sd, int64_t sk, int64_t ld, int Y) {
     const int64_t lim = (int64_t)1 << 31;
@@ -330,6 +559,28 @@ int launch_bwd(int64_t N, int D, int Y, int n_tiles, const int32_t* col_var, con
     return 0;
 }
 
+template <typename TS, typename TM, int YP>
+int launch_bwd_var(int64_t N, int D, int max_cols, const int32_t* col_mode, const int32_t* var_pcol, const double* weight,
+                   const double* bias, const void* y, int64_t sn, int64_t sd, int64_t sk, const void* mask,
+                   const void* g_theta, int64_t ld_theta, void* g_y, double* g_weight, double* g_bias, cudaStream_t st) {
+    auto kern = theta_bwd_var_k<TS, TM, YP>;
+    constexpr int RB = TvRows<TS, YP>::value;
+    const int cap = TV_THREADS * max_cols, n_tiles = (D + TV_THREADS - 1) / TV_THREADS;
+    const size_t smem = (size_t)2 * RB * (cap + YP * TV_THREADS) * sizeof(TS);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    dim3 grid(n_tiles, grid_stripes(N, n_tiles, RB, HLVAE_TV_BWD_CTAS));
+    kern<<<grid, TV_THREADS, smem, st>>>(N, D, cap, col_mode, var_pcol, weight, bias, (const TS*)y, sn, sd, sk,
+                                         (const TM*)mask, (const TS*)g_theta, ld_theta, (TS*)g_y, g_weight, g_bias);
+    HLVAE_CHECK_LAUNCH();
+    return 0;
+}
+
+// the thread-per-variable kernels cover this call
+bool tv_covers(int max_cols, int Y) { return max_cols >= 1 && max_cols <= TV_CV && Y <= 8; }
+
 }  // namespace
 
 extern "C" int hlvae_theta_fwd(int64_t N, int D, int P, int Y, int n_tiles, const int32_t* col_var,
@@ -357,7 +608,7 @@ extern "C" int hlvae_theta_fwd(int64_t N, int D, int P, int Y, int n_tiles, cons
 #undef HLVAE_TH_FWD
 }
 
-extern "C" int hlvae_theta_bwd(int64_t N, int D, int P, int Y, int n_tiles, const int32_t* col_var,
+extern "C" int hlvae_theta_bwd(int64_t N, int D, int P, int Y, int n_tiles, int max_cols, const int32_t* col_var,
                                const int32_t* col_mode, const int32_t* var_pcol, const int32_t* tile_var,
                                const double* weight, const double* bias, const void* y, int64_t sn, int64_t sd,
                                int64_t sk, int dtype, const void* mask, int mask_dtype, const void* g_theta,
@@ -370,6 +621,25 @@ extern "C" int hlvae_theta_bwd(int64_t N, int D, int P, int Y, int n_tiles, cons
     if (mask_dtype != dtype && mask_dtype != HLVAE_U8) return HLVAE_E_ARG;
     if (N == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
+    if (tv_covers(max_cols, Y)) {
+#define HLVAE_TV_BWD(TS, TM, YP)                                                                                       \
+    return launch_bwd_var<TS, TM, YP>(N, D, max_cols, col_mode, var_pcol, weight, bias, y, sn, sd, sk, mask, g_theta,  \
+                                      ld_theta, g_y, g_weight, g_bias, st)
+#define HLVAE_TV_BWD_Y(TS, TM)                                                                                         \
+    switch (Y) {                                                                                                       \
+        case 1: HLVAE_TV_BWD(TS, TM, 1); case 2: HLVAE_TV_BWD(TS, TM, 2); case 3: HLVAE_TV_BWD(TS, TM, 3);             \
+        case 4: HLVAE_TV_BWD(TS, TM, 4); case 5: HLVAE_TV_BWD(TS, TM, 5); case 6: HLVAE_TV_BWD(TS, TM, 6);             \
+        case 7: HLVAE_TV_BWD(TS, TM, 7); default: HLVAE_TV_BWD(TS, TM, 8);                                             \
+    }
+        if (dtype == HLVAE_F32) {
+            if (mask_dtype == HLVAE_U8) { HLVAE_TV_BWD_Y(float, unsigned char) }
+            HLVAE_TV_BWD_Y(float, float)
+        }
+        if (mask_dtype == HLVAE_U8) { HLVAE_TV_BWD_Y(double, unsigned char) }
+        HLVAE_TV_BWD_Y(double, double)
+#undef HLVAE_TV_BWD_Y
+#undef HLVAE_TV_BWD
+    }
 #define HLVAE_TH_BWD(TS, TM, YP)                                                                                       \
     return launch_bwd<TS, TM, YP>(N, D, Y, n_tiles, col_var, col_mode, var_pcol, tile_var, weight, bias, y, sn, sd, sk, \
                                   mask, g_theta, ld_theta, g_y, g_weight, g_bias, st)

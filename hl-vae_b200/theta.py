@@ -14,6 +14,8 @@ There is no CPU path: tensors must be on a CUDA device.
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
@@ -56,6 +58,9 @@ class HeadLayout:
         self.var_pcol = torch.tensor(var_pcol, **i32)
         self.tile_var = torch.tensor(tiles, **i32)
         self.n_tiles = len(tiles) - 1
+        # widest variable: layouts with <= 5 columns per variable take the thread-per-variable backward kernel
+        # (csrc/theta.cu); HLVAE_THETA_PER_COLUMN=1 keeps the thread-per-column one (A/B runs)
+        self.max_cols = 0 if os.environ.get("HLVAE_THETA_PER_COLUMN") else int(np.diff(var_pcol).max())
         self.D, self.P = D, P
         # type groups in the reference's order: sorted set of (type, nclass-string) tuples (read_functions.py:176-180)
         if set_of_types is None:
@@ -166,7 +171,7 @@ class _ThetaHeads(torch.autograd.Function):
         if N > 0:
             g = g_theta.to(yd.dtype).contiguous()
             sn, sd, sk = yd.stride()
-            _lib.call("hlvae_theta_bwd", N, D, layout.P, Y, layout.n_tiles, _lib.ptr(layout.col_var),
+            _lib.call("hlvae_theta_bwd", N, D, layout.P, Y, layout.n_tiles, layout.max_cols, _lib.ptr(layout.col_var),
                       _lib.ptr(layout.col_mode), _lib.ptr(layout.var_pcol), _lib.ptr(layout.tile_var), _lib.ptr(W),
                       _lib.ptr(b), _lib.ptr(yd), sn, sd, sk, _lib.dtype_code(yd), _lib.ptr(mk), ctx.mk_code, _lib.ptr(g),
                       layout.P, _lib.ptr(g_y), _lib.ptr(g_W), _lib.ptr(g_b), _lib.stream_ptr())

@@ -315,6 +315,10 @@ int hlvae_loglik_aux_bwd(int mode, int64_t N, int Dg, const void* data, int64_t 
  *   mask [N, D] contiguous, `mask_dtype` = dtype or HLVAE_U8.
  * bwd: g_theta [N, ld_theta] -> g_y (same strides as y, overwritten), g_weight [P, Y], g_bias [P]
  *   float64 (accumulated, caller zero-fills).
+ *   max_cols = the largest number of theta columns one variable owns (max_d var_pcol[d+1] - var_pcol[d]), or 0 when
+ *   the caller does not know it: layouts with max_cols <= 5 and Y <= 8 take a thread-per-variable kernel (the
+ *   variable's heads and gradient sums in registers, inputs of the next row batch in flight by cp.async), every other
+ *   call the thread-per-column kernel.
  * ---------------------------------------------------------------------------------- */
 #define HLVAE_MAX_Y 16
 #define HLVAE_HEAD_AFFINE 0
@@ -325,10 +329,11 @@ int hlvae_theta_fwd(int64_t N, int D, int P, int Y, int n_tiles, const int32_t* 
                     const int32_t* var_pcol, const int32_t* tile_var, const double* weight, const double* bias,
                     const void* y, int64_t sn, int64_t sd, int64_t sk, int dtype, void* theta, int64_t ld_theta,
                     void* stream);
-int hlvae_theta_bwd(int64_t N, int D, int P, int Y, int n_tiles, const int32_t* col_var, const int32_t* col_mode,
-                    const int32_t* var_pcol, const int32_t* tile_var, const double* weight, const double* bias,
-                    const void* y, int64_t sn, int64_t sd, int64_t sk, int dtype, const void* mask, int mask_dtype,
-                    const void* g_theta, int64_t ld_theta, void* g_y, double* g_weight, double* g_bias, void* stream);
+int hlvae_theta_bwd(int64_t N, int D, int P, int Y, int n_tiles, int max_cols, const int32_t* col_var,
+                    const int32_t* col_mode, const int32_t* var_pcol, const int32_t* tile_var, const double* weight,
+                    const double* bias, const void* y, int64_t sn, int64_t sd, int64_t sk, int dtype, const void* mask,
+                    int mask_dtype, const void* g_theta, int64_t ld_theta, void* g_y, double* g_weight, double* g_bias,
+                    void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Batch normalisation of the data batch.  Replaces HL_VAE/utils.py:88-143

@@ -28,10 +28,11 @@ for case in range(n_cases):
     f32 = bool(rng.integers(0, 2))
     observed = float(rng.choice([0.0, 0.3, 0.7, 1.0]))
     scale = float(rng.choice([0.5, 1.5, 4.0]))
-    tag = f"D={D} N={N} Y={Y} conv={conv} {layout} f32={f32} obs={observed} scale={scale}"
+    per_column = bool(rng.integers(0, 2))
+    tag = f"D={D} N={N} Y={Y} conv={conv} {layout} f32={f32} obs={observed} scale={scale} per_column={per_column}"
     try:
         errs = tt._random_case(types, conv, N, Y, layout, dev, 900 + case, storage=torch.float32 if f32 else torch.float64,
-                               observed=observed, scale=scale)
+                               observed=observed, scale=scale, per_column=per_column)
         tol = 1e-5 if f32 else 1e-11
         worst = {k: v for k, v in errs.items() if not v < tol}
         if worst:

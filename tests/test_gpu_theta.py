@@ -67,12 +67,21 @@ def _product_layers(ti, heads, conv, device):
     ([('cat', 16)] * 40 + [('ordinal', 9)] * 7 + [('real', 1)], False, 19, 4, "dense"),   # 16-class variables: 16 per tile
 ])
 def test_random_vs_oracle(types, conv, N, Y, layout, device):
-    errs = _random_case(types, conv, N, Y, layout, device, seed=N + Y)
-    bad = {k: v for k, v in errs.items() if not v < (1e-12 if k in ("theta", "d_y") else 1e-11)}
+    for per_column in (False, True):
+        errs = _random_case(types, conv, N, Y, layout, device, seed=N + Y, per_column=per_column)
+        bad = {k: v for k, v in errs.items() if not v < (1e-12 if k in ("theta", "d_y") else 1e-11)}
+        assert not bad, (per_column, bad)
+
+
+def test_long_stripes_float32_parameter_gradients(device):
+    """Many rows per CTA stripe: the thread-per-variable backward keeps its weight / bias gradient sums in float32 and
+    flushes them to the float64 accumulators every 256 rows."""
+    errs = _random_case(synth.TABULAR_TYPES[::8], False, 40000, 5, "dense", device, seed=5, storage=torch.float32)
+    bad = {k: v for k, v in errs.items() if not v < 1e-5}
     assert not bad, bad
 
 
-def _random_case(types, conv, N, Y, layout, device, seed, storage=DT, observed=0.7, scale=1.0):
+def _random_case(types, conv, N, Y, layout, device, seed, storage=DT, observed=0.7, scale=1.0, per_column=False):
     """One seeded comparison of theta_heads (forward, d y, d head parameters) with the oracle; returns the relative
     errors.  `storage` float32 = float32 y / theta in HBM with a uint8 mask (the benchmarked arithmetic)."""
     gen = torch.Generator().manual_seed(seed)
@@ -93,6 +102,8 @@ def _random_case(types, conv, N, Y, layout, device, seed, storage=DT, observed=0
 
     obs_layer = _product_layers(ti, heads, conv, device)
     lay = th.HeadLayout(types, conv, device)
+    if per_column:                                        # keep the thread-per-column backward kernel (layouts with <= 5
+        lay.max_cols = 0                                  # columns per variable and y_dim <= 8 take the thread-per-variable one)
     yd = y0.to(device).to(storage)
     if layout == "permuted":
         yd = yd.permute(0, 2, 1).contiguous().permute(0, 2, 1)
