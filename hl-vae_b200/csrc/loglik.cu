@@ -1211,10 +1211,10 @@ struct Tiling {
 // 0.354 / 0.367 ms; tabular D = 256 at 64 000 rows: 0.46 -> 0.39 ms forward, 0.51 -> 0.40 ms backward at 6): shorter
 // CTAs let the SMs that finish early pick up more work instead of idling through the tail of a single wave.
 constexpr int LL_WAVES = 6;
-Tiling make_tiling(int64_t N, int D, int ctas_per_sm, int rows_per_batch = LL_ROWS) {
+Tiling make_tiling(int64_t N, int D, int ctas_per_sm, int rows_per_batch = LL_ROWS, int max_tile_vars = LL_THREADS) {
     N = (N + rows_per_batch - 1) / rows_per_batch;            // row batches
     Tiling t;
-    t.n_tiles = (D + LL_THREADS - 1) / LL_THREADS;
+    t.n_tiles = (D + max_tile_vars - 1) / max_tile_vars;
     t.tile_vars = (D + t.n_tiles - 1) / t.n_tiles;
     t.n_tiles = (D + t.tile_vars - 1) / t.tile_vars;
     int64_t want = ((int64_t)148 * ctas_per_sm * LL_WAVES) / t.n_tiles;
@@ -1223,6 +1223,18 @@ Tiling make_tiling(int64_t N, int D, int ctas_per_sm, int rows_per_batch = LL_RO
     if (want < 1) want = 1;
     t.rows = (unsigned)want;
     return t;
+}
+
+// Variables per tile such that the stage of one CTA (rows x (theta + data [+ upstream gradient]) of the tile's widest
+// possible span, tile_vars * max_class columns) stays within LL_SMEM_BUDGET: float64 storage with 16-class variables
+// would otherwise ask for 272 KB (more than an SM has) - the tile shrinks instead.  Every layout of the reference's
+// data sets (<= 5 classes) keeps the full 128-variable tile.
+constexpr size_t LL_SMEM_BUDGET = 96 * 1024;                  // two CTAs per SM at least
+int max_tile_vars(int rows, int max_class, size_t col_bytes, size_t var_bytes) {
+    int tv = LL_THREADS;
+    while (tv > 8 && (size_t)LL_STAGES * rows * (((size_t)tv * max_class + 16) * col_bytes + LL_CAPM * var_bytes) > LL_SMEM_BUDGET)
+        tv -= 8;
+    return tv;
 }
 
 template <typename K>
@@ -1262,9 +1274,10 @@ extern "C" int hlvae_loglik_fwd(int64_t N, int D, int64_t ld_data, int64_t ld_th
     if (max_class < 1 || max_class > HLVAE_MAX_CLASS) return HLVAE_E_ARG;
     const size_t esz = dtype == HLVAE_F64 ? 8 : 4;
     const size_t xsz = data_dtype == HLVAE_U8 ? 1 : esz;
-    Tiling tl = make_tiling(N, D, 1);
-    const int cap = (tl.tile_vars * max_class + 15) & ~15;
     const size_t msz = mask_dtype == HLVAE_U8 ? 1 : esz;
+    const int tv_max = max_tile_vars(LL_ROWS, max_class, esz + xsz, msz);
+    Tiling tl = make_tiling(N, D, 1, LL_ROWS, tv_max);
+    const int cap = (tl.tile_vars * max_class + 15) & ~15;
     const size_t smem = (size_t)LL_STAGES * LL_ROWS * ((cap + 8) * esz + (cap + 16) * xsz + LL_CAPM * msz);
 #define HLVAE_LL_FWD(TS, TD, TM)                                                                                     \
     {                                                                                                                \
@@ -1273,7 +1286,7 @@ extern "C" int hlvae_loglik_fwd(int64_t N, int D, int64_t ld_data, int64_t ld_th
         if (rc) return rc;                                                                                           \
         int nb = 1;                                                                                                  \
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, LL_THREADS, smem);                                  \
-        tl = make_tiling(N, D, nb < 1 ? 1 : nb);                                                                     \
+        tl = make_tiling(N, D, nb < 1 ? 1 : nb, LL_ROWS, tv_max);                                                                   \
         dim3 grid(tl.n_tiles, tl.rows);                                                                              \
         kern<<<grid, LL_THREADS, smem, st>>>(N, D, tl.tile_vars, cap, ld_data, ld_theta, var_kind, var_nclass,       \
                                              var_dcol, var_pcol, vparam, (const TD*)data, (const TS*)theta,          \
@@ -1300,9 +1313,11 @@ extern "C" int hlvae_loglik_bwd(int64_t N, int D, int64_t ld_data, int64_t ld_th
     if (max_class < 1 || max_class > HLVAE_MAX_CLASS) return HLVAE_E_ARG;
     const size_t esz = dtype == HLVAE_F64 ? 8 : 4;
     const size_t xsz = data_dtype == HLVAE_U8 ? 1 : esz;
-    Tiling tl = make_tiling(N, D, 1);
-    const int cap = (tl.tile_vars * max_class + 15) & ~15;
     const size_t msz = mask_dtype == HLVAE_U8 ? 1 : esz;
+    // (the tile is sized for the 8-row stage; instantiations that stage 4 rows just use half the budget)
+    const int tv_max = max_tile_vars(LL_ROWS, max_class, esz + xsz, msz + esz);
+    Tiling tl = make_tiling(N, D, 1, LL_ROWS, tv_max);
+    const int cap = (tl.tile_vars * max_class + 15) & ~15;
 #define HLVAE_LL_BWD(TS, TD, TM)                                                                                     \
     {                                                                                                                \
         auto kern = loglik_bwd_k<TS, TD, TM>;                                                                        \
@@ -1312,7 +1327,7 @@ extern "C" int hlvae_loglik_bwd(int64_t N, int D, int64_t ld_data, int64_t ld_th
         if (rc) return rc;                                                                                           \
         int nb = 1;                                                                                                  \
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, LL_THREADS, smem);                                  \
-        tl = make_tiling(N, D, nb < 1 ? 1 : nb, LR);                                                                   \
+        tl = make_tiling(N, D, nb < 1 ? 1 : nb, LR, tv_max);                                                                   \
         dim3 grid(tl.n_tiles, tl.rows);                                                                              \
         kern<<<grid, LL_THREADS, smem, st>>>(N, D, tl.tile_vars, cap, ld_data, ld_theta, var_kind, var_nclass,       \
                                              var_dcol, var_pcol, vparam, (const TD*)data, (const TS*)theta,          \

@@ -27,21 +27,23 @@ for case in range(n_cases):
     u8 = bool(rng.integers(0, 2)) and all(k in ('cat', 'ordinal') for k, _ in types)
     observed = float(rng.choice([0.3, 0.7, 1.0]))
     scale = float(rng.choice([0.5, 1.5, 4.0]))
+    f64 = bool(rng.integers(0, 3) == 0)                    # the drop-in case: every tensor float64
     try:
-        got, ref, disc = tl._fp32_case(types, N, 500 + case, dev, observed=observed, u8=u8, theta_scale=scale)
+        got, ref, disc = tl._fp32_case(types, N, 500 + case, dev, observed=observed, u8=u8, theta_scale=scale,
+                                       storage=torch.float64 if f64 else torch.float32)
         if not all(bool(torch.isfinite(ref[k]).all()) for k in ("log_p_x", "params", "d_theta")):
             print(f"skip D={D} N={N}: the oracle itself is not finite here (normalisation of a column without two "
                   "observed values)", flush=True)
             continue
         errs = {k: h.rel_err(got[k], ref[k]) for k in ("log_p_x", "log_p_x_missing", "params", "d_theta")}
-        ok = all(v < 2e-5 for v in errs.values())
-        ok = ok and np.array_equal(got["recon_mean"].cpu().numpy()[:, disc], ref["recon_mean"].numpy()[:, disc].astype(np.float32))
-        ok = ok and np.array_equal(got["data_transformed"].cpu().numpy(), ref["data_transformed"].numpy().astype(np.float32))
+        ok = all(v < (1e-9 if f64 else 2e-5) for v in errs.values())
+        ok = ok and np.array_equal(got["recon_mean"].cpu().numpy()[:, disc], ref["recon_mean"].numpy()[:, disc].astype(np.float64 if f64 else np.float32))
+        ok = ok and np.array_equal(got["data_transformed"].cpu().numpy(), ref["data_transformed"].numpy().astype(np.float64 if f64 else np.float32))
         if not ok:
             raise AssertionError(str(errs))
-        print(f"ok   D={D} N={N} u8={u8} obs={observed} scale={scale} worst {max(errs.values()):.1e}", flush=True)
+        print(f"ok   D={D} N={N} u8={u8} f64={f64} obs={observed} scale={scale} worst {max(errs.values()):.1e}", flush=True)
     except Exception as e:
         bad += 1
-        print(f"FAIL D={D} N={N} u8={u8} obs={observed} scale={scale}: {str(e)[:300]}", flush=True)
+        print(f"FAIL D={D} N={N} u8={u8} f64={f64} obs={observed} scale={scale}: {str(e)[:300]}", flush=True)
 print("stress:", "OK" if bad == 0 else f"{bad} failures", "of", n_cases)
 sys.exit(1 if bad else 0)

@@ -70,13 +70,13 @@ def test_float32_storage_argmax_exact(device):
     assert out["log_p_x"].dtype == torch.float32
 
 
-def _fp32_case(types, N, seed, device, conv=False, observed=0.7, u8=False, theta_scale=1.5):
+def _fp32_case(types, N, seed, device, conv=False, observed=0.7, u8=False, theta_scale=1.5, storage=torch.float32):
     rng = np.random.default_rng(seed)
     gen = torch.Generator().manual_seed(seed)
     data, mask = synth.likelihood_batch(types, N, rng, observed=observed, pixel_like=conv)
-    data = data.float().double()                       # the oracle sees the float32-rounded inputs
+    data = data.to(storage).double()                   # the oracle sees the inputs as stored (float32-rounded or float64)
     descs, E_x, P_th = orc.build_layout(types)
-    theta = (torch.randn(N, P_th, generator=gen, dtype=DT) * theta_scale).float()
+    theta = (torch.randn(N, P_th, generator=gen, dtype=DT) * theta_scale).to(storage)
     n_real = sum(k == "real" for k, _ in types)
     n_pos = sum(k == "pos" for k, _ in types)
     lvr = torch.randn(n_real, generator=gen, dtype=DT) * 0.3
@@ -85,8 +85,8 @@ def _fp32_case(types, N, seed, device, conv=False, observed=0.7, u8=False, theta
         nr, npos = None, None
     else:
         nr, npos = orc.batch_norm_params(descs, data, mask)
-    g_up = torch.randn(N, len(types), generator=gen, dtype=DT).float()
-    th64 = theta.double().requires_grad_(True)
+    g_up = torch.randn(N, len(types), generator=gen, dtype=DT).to(storage)
+    th64 = theta.double().clone().requires_grad_(True)
     lvr64, lvp64 = lvr.clone().requires_grad_(True), lvp.clone().requires_grad_(True)
     olpx, olpm, oparams = orc.loglik_and_reconstruction(descs, data, mask, th64, lvr64, lvp64, nr, npos, conv=conv)
     (olpx * g_up.double()).sum().backward()
@@ -97,9 +97,9 @@ def _fp32_case(types, N, seed, device, conv=False, observed=0.7, u8=False, theta
     vparam = lay.vparam(lvr_d if n_real else None, lvp_d if n_pos else None,
                         None if nr is None else [a.to(device) for a in nr],
                         None if npos is None else [a.to(device) for a in npos], conv=conv)
-    th = theta.to(device).requires_grad_(True)
-    d_in = data.to(torch.uint8) if u8 else data.float()
-    m_in = mask.to(torch.uint8) if u8 else mask.float()
+    th = theta.detach().to(device).requires_grad_(True)
+    d_in = data.to(torch.uint8) if u8 else data.to(storage)
+    m_in = mask.to(torch.uint8) if u8 else mask.to(storage)
     out = loglik.fused_loglik(lay, d_in.to(device), m_in.to(device), th, vparam)
     (out["log_p_x"] * g_up.to(device)).sum().backward()
     disc = np.array([k in ("cat", "ordinal") for k, _ in types])
@@ -137,6 +137,16 @@ def test_float32_fast_path_tabular_all_types(device):
     assert h.rel_err(got["d_lvr"], ref["d_lvr"]) < 1e-4 and h.rel_err(got["d_lvp"], ref["d_lvp"]) < 1e-4
     assert np.array_equal(got["recon_mean"].cpu().numpy()[:, disc], ref["recon_mean"].numpy()[:, disc].astype(np.float32))
     assert np.array_equal(got["data_transformed"].cpu().numpy(), ref["data_transformed"].numpy().astype(np.float32))
+
+
+def test_float64_storage_wide_classes(device):
+    """The drop-in case (every tensor float64) with 16-class variables in a full tile: 128 variables x 16 classes x 8 rows
+    of float64 theta and data do not fit one CTA's shared memory - the tile must shrink, not the launch fail."""
+    types = [('cat', 16)] * 70 + [('ordinal', 16)] * 50 + [('real', 1)] * 5 + [('count', 1)] * 5 + [('cat', 3)] * 10
+    got, ref, disc = _fp32_case(types, 41, 77, device, storage=torch.float64)
+    for k in ("log_p_x", "log_p_x_missing", "params", "d_theta"):
+        assert got[k].dtype == torch.float64 and h.rel_err(got[k], ref[k]) < 1e-9, k
+    assert np.array_equal(got["recon_mean"].cpu().numpy()[:, disc], ref["recon_mean"].numpy()[:, disc])
 
 
 @pytest.mark.parametrize("C", [5, 11])
