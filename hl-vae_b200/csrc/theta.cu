@@ -419,12 +419,21 @@ theta_bwd_var_k(int64_t N, int D, int cap, const int32_t* __restrict__ col_mode,
 #pragma unroll
         for (int r = 0; r < RB; r++) m[r] = (n0 + r < t.r_end) ? pm[r * D32] : (TM)0;
     };
+    if (t.ncols > cap) {      // more columns than max_cols promised for 128 variables (a caller error): the tile does not
+        if (live)             // fit its staging buffer - poison its d/dy instead of overrunning shared memory
+            for (int64_t n = t.r_begin; n < t.r_end; n++)
+                for (int k = 0; k < YP; k++) gyv[n * sn + k * sk] = (TS)NAN;
+        return;
+    }
     issue(t.r_begin, 0);
     TM m[RB], m_next[RB];
     load_mask(m, t.r_begin);
     TvVar<TS, YP> v;
     tv_load<TS, YP>(v, live, d, t.p0, var_pcol, col_mode, weight, bias);
     const unsigned grad_cols = v.dep | v.bo;                  // columns that receive a gradient at all
+    // a variable with more columns than the caller's max_cols promised (a caller error): its d/dy is poisoned with
+    // NaN instead of silently missing the columns beyond TV_CV
+    const bool wide = v.nc > TV_CV;
     TS gw[TV_CV][YP], gb[TV_CV];
 #pragma unroll
     for (int c = 0; c < TV_CV; c++) {
@@ -492,7 +501,7 @@ theta_bwd_var_k(int64_t N, int D, int cap, const int32_t* __restrict__ col_mode,
                         }
                     }
 #pragma unroll
-                    for (int k = 0; k < YP; k++) pg[r * sn32 + k * sk32] = dy[k];
+                    for (int k = 0; k < YP; k++) pg[r * sn32 + k * sk32] = wide ? (TS)NAN : dy[k];
                 }
             }
             if (++since == FLUSH) {

@@ -318,7 +318,8 @@ int hlvae_loglik_aux_bwd(int mode, int64_t N, int Dg, const void* data, int64_t 
  *   max_cols = the largest number of theta columns one variable owns (max_d var_pcol[d+1] - var_pcol[d]), or 0 when
  *   the caller does not know it: layouts with max_cols <= 5 and Y <= 8 take a thread-per-variable kernel (the
  *   variable's heads and gradient sums in registers, inputs of the next row batch in flight by cp.async), every other
- *   call the thread-per-column kernel.
+ *   call the thread-per-column kernel.  max_cols below the true maximum is a caller error: d/dy of the wider variables
+ *   comes back NaN.
  * ---------------------------------------------------------------------------------- */
 #define HLVAE_MAX_Y 16
 #define HLVAE_HEAD_AFFINE 0

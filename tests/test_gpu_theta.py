@@ -122,3 +122,28 @@ def _random_case(types, conv, N, Y, layout, device, seed, storage=DT, observed=0
             errs[f"g{i}_{tpl[0]}_{n}"] = h.rel_err(prm.grad, hd[n].grad)
         layer += 2 if (tpl[0] == 'real' and conv) else 1
     return errs
+
+
+def test_understated_max_cols_poisons_dy(device):
+    """hlvae_theta_bwd's max_cols selects the thread-per-variable kernel (<= 5 columns per variable).  A caller that
+    understates it gets NaN in d/dy of the wider variables, not a silently truncated gradient."""
+    types = [('cat', 7)] * 3 + [('real', 1)] * 4
+    gen = torch.Generator().manual_seed(3)
+    ti, heads = _random_heads(types, False, 4, gen)
+    lay = th.HeadLayout(types, False, device)
+    assert lay.max_cols == 7
+    W, b = th.pack_heads(_product_layers(ti, heads, False, device), lay, 4)
+    y = torch.randn(9, len(types), 4, generator=gen, dtype=DT).to(device).requires_grad_(True)
+    mask = torch.ones(9, len(types), dtype=DT, device=device)
+    lay.max_cols = 5                                         # the caller's error
+    th.theta_heads(lay, y, mask, W, b).sum().backward()
+    assert bool(torch.isnan(y.grad[:, :3]).all()) and bool(torch.isfinite(y.grad[:, 3:]).all())
+    # a whole tile wider than its staging buffer (128 variables x 7 columns against 128 x 5): poisoned, no overrun
+    types = [('cat', 7)] * 130
+    ti, heads = _random_heads(types, False, 4, gen)
+    lay = th.HeadLayout(types, False, device)
+    W, b = th.pack_heads(_product_layers(ti, heads, False, device), lay, 4)
+    y = torch.randn(9, len(types), 4, generator=gen, dtype=DT).to(device).requires_grad_(True)
+    lay.max_cols = 5
+    th.theta_heads(lay, y, torch.ones(9, len(types), dtype=DT, device=device), W, b).sum().backward()
+    assert bool(torch.isnan(y.grad).all())
