@@ -22,7 +22,10 @@
 #define HLVAE_TH_BWD_CTAS 3
 #endif
 #ifndef HLVAE_TV_BWD_CTAS
-#define HLVAE_TV_BWD_CTAS 32      // CTAs per SM worth of row stripes, thread-per-variable backward kernel
+// CTAs per SM worth of row stripes, thread-per-variable backward kernel.  Measured with 80 bytes of y per thread in
+// flight, 8 / 12 / 16 / 32 / 64: 0.406 / 0.381 / 0.389 / 0.399 / 0.453 ms at the configs[1] batch, 0.269 / 0.257 / 0.270 /
+// 0.283 / 0.382 ms on the tabular layout; 16 with 40 bytes (the default): 0.383 / 0.253 ms
+#define HLVAE_TV_BWD_CTAS 16
 #endif
 
 namespace {
@@ -298,7 +301,7 @@ constexpr int TV_CV = 5;          // theta columns per variable held in register
 #define HLVAE_TV_BWD_MIN_CTAS 1
 #endif
 #ifndef HLVAE_TV_BWD_BYTES
-#define HLVAE_TV_BWD_BYTES 80
+#define HLVAE_TV_BWD_BYTES 40      // y values of one row batch per thread (y_dim 5, float32: 2 rows); 80: see above, 160: 0.60 ms
 #endif
 template <typename TS, int YP>
 struct TvRows {
