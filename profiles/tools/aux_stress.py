@@ -13,6 +13,17 @@ import helpers as h
 from hlvae_b200 import normalize as nz, predict, synth, validation
 from oracle import hlvae_oracle as orc
 dev = torch.device("cuda:0")
+
+
+def kl_random_kargs(rng):
+    """The random kernel structures of kl_stress.py (that file runs its sweep on import, so the generator is read out of
+    its source)."""
+    src = open(os.path.join(ROOT, "profiles", "tools", "kl_stress.py")).read()
+    ns = {}
+    exec(src[src.index("def random_kargs"):src.index("for case in range(n_cases):")], {"np": np}, ns)
+    return ns["random_kargs"](rng)
+
+
 rng = np.random.default_rng(int(os.environ.get("SEED", "0")))
 n_cases = int(os.environ.get("CASES", "30"))
 which = os.environ.get("WHICH", "norm,predict,dubo").split(",")
@@ -99,8 +110,14 @@ for case in range(n_cases):
         T = int(rng.choice([1, 2, 3, 5, 9, 16, 20, 25, 32, 33, 47, 64]))
         ragged = kind == "predict" and bool(rng.integers(0, 2)) and T >= 4
         n_subj = int(rng.integers(1, max(2, min(50, 1000 // T))))
-        ki = int(rng.integers(0, 3))
-        kargs = [synth.DEFAULT_KERNEL_ARGS, synth.SWEEP_KERNEL_ARGS, synth.MASKED_KERNEL_ARGS][ki]
+        ki = int(rng.integers(0, 4))
+        if ki == 3:                                        # a random additive structure (see kl_stress.random_kargs)
+            while True:
+                kargs = kl_random_kargs(rng)
+                if all(len(sp.comps) <= 8 for sp in orc.compile_spec(**kargs)):
+                    break
+        else:
+            kargs = [synth.DEFAULT_KERNEL_ARGS, synth.SWEEP_KERNEL_ARGS, synth.MASKED_KERNEL_ARGS][ki]
         report(f"{kind} L={L} M={M} subj={n_subj} T={T} ragged={ragged} kernel={ki}",
                lambda: gp_case(kind, L, M, n_subj, T, ragged, kargs, 700 + case))
 print("stress:", "OK" if bad == 0 else f"{bad} failures", "of", n_cases)
