@@ -13,6 +13,7 @@
 // end) and leaves its masked upstream gradient in (double-buffered) shared memory; after ONE barrier per row
 // batch, thread = (variable, k) forms d/dy from the <= 16 columns of the variable, decoded so that consecutive
 // threads write consecutive addresses of the caller's layout.  HBM-bound: y and theta cross once.
+// Layouts with <= 5 theta columns per variable and y_dim <= 8 take a thread-per-VARIABLE backward kernel instead (below).
 #include "common.cuh"
 
 #ifndef HLVAE_TH_BWD_BYTES
@@ -292,7 +293,7 @@ theta_bwd_k(int64_t N, int D, int Y, const int32_t* __restrict__ col_var, const 
 // thread owns a variable: its heads and its weight / bias gradient sums sit in registers, the g_theta rows of the tile
 // (coalesced row segments) and the thread's own y values of the NEXT row batch arrive by cp.async while the current
 // batch is evaluated, d/dy is formed and written by the same thread (coalesced in the convolutional layout):
-// 270 instructions per (row, variable), configs[1] batch 0.478 -> 0.395 ms, tabular 64 000 rows 0.317 -> 0.278 ms.
+// 270 instructions per (row, variable), configs[1] batch 0.478 -> 0.374 ms, tabular 64 000 rows 0.317 -> 0.253 ms.
 // (The forward direction was measured the same way and dropped: 0.250 against 0.205 ms for thread-per-column, whose
 // stores are already coalesced and which needs no staging at all.)
 constexpr int TV_THREADS = 128;   // variables per tile
