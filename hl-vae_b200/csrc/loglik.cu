@@ -1210,7 +1210,12 @@ struct Tiling {
 // Measured (waves 1 / 2 / 4 / 6 / 8 / 12 / 25 at 16 000 rows, D4: forward 0.376 / 0.368 / 0.362 / 0.357 / 0.354 /
 // 0.354 / 0.367 ms; tabular D = 256 at 64 000 rows: 0.46 -> 0.39 ms forward, 0.51 -> 0.40 ms backward at 6): shorter
 // CTAs let the SMs that finish early pick up more work instead of idling through the tail of a single wave.
-constexpr int LL_WAVES = 6;
+// (re-measured at the end of r02, 4 / 6 / 8 / 10: D4 forward 0.283 / 0.277 / 0.271 / 0.267 ms, backward 0.181 / 0.179 / 0.179 /
+// 0.183 ms; tabular forward 0.244 / 0.235 / 0.236 / 0.238 ms, backward 0.194 / 0.192 / 0.195 / 0.199 ms: 6 stays)
+#ifndef HLVAE_LL_WAVES
+#define HLVAE_LL_WAVES 6
+#endif
+constexpr int LL_WAVES = HLVAE_LL_WAVES;
 Tiling make_tiling(int64_t N, int D, int ctas_per_sm, int rows_per_batch = LL_ROWS, int max_tile_vars = LL_THREADS) {
     N = (N + rows_per_batch - 1) / rows_per_batch;            // row batches
     Tiling t;
