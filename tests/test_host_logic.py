@@ -25,6 +25,35 @@ def test_library_exports_every_declared_symbol(built_lib):
     assert built_lib.hlvae_sizeof_kspec() == ctypes.sizeof(_lib.KSpec)
 
 
+def test_binding_signatures_match_header():
+    """Every prototype of include/hlvae_b200.h against the ctypes signature in _lib._SIGS: same number of parameters
+    and the same kind per position (pointer / int / int64_t / double) - a parameter added on one side only would
+    shift every later argument silently."""
+    hdr = open(os.path.join(ROOT, "include", "hlvae_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    protos = re.findall(r"^(?:int|int64_t)\s+(hlvae_\w+)\s*\(([^;]*?)\)\s*;", hdr, flags=re.M | re.S)
+    assert len(protos) == len(_lib.EXPORTED)
+
+    def kind(param):
+        param = " ".join(param.split())
+        if "*" in param:
+            return "ptr"
+        if param.startswith("int64_t"):
+            return "i64"
+        if param.startswith("double"):
+            return "f64"
+        if param.startswith("int"):
+            return "int"
+        raise AssertionError(f"unparsed parameter '{param}'")
+
+    ckind = {_lib._P: "ptr", _lib._I: "int", _lib._L: "i64", _lib._D: "f64"}
+    for name, params in protos:
+        params = [] if params.strip() in ("", "void") else [q for q in params.split(",")]
+        args, _ = _lib._SIGS[name]
+        got = [ckind.get(a, "ptr") for a in args]                      # POINTER(...) types are pointers
+        assert [kind(q) for q in params] == got, name
+
+
 def test_acc_layout(built_lib):
     off = _lib.acc_layout(4, 12, 6)
     assert off["S"] == 0 and off["p"] == 4 * 12 * 12 and off["gw"] == off["p"] + 48
